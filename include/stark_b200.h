@@ -1,0 +1,179 @@
+/*
+ * stark_b200.h — C ABI of libstark_b200.so: the B200 (sm_100a) implementation of the data-parallel hot
+ * path of RazorClient/Stark-prover (crate `stark-101`).
+ *
+ * This is the seam a thin Rust FFI shim in src/polynomial, src/merkle and src/fri binds (INTEGRATION.md
+ * shows the `extern "C"` block and build.rs).  The reference has no FFI of its own, so every entry
+ * point names the reference `pub fn` it stands behind (paths relative to the reference repo).
+ *
+ * Conventions
+ *   - Field elements cross the boundary as the reference stores them: one canonical u64 per
+ *     FieldElement<MODULUS> (src/fields/element.rs:7-10).  Inputs are reduced `% modulus` like
+ *     FieldElement::new (:13-17).  The modulus must be an odd prime < 2^32 — the reference's own domain
+ *     of validity (`pow` multiplies in u64, :45,47).
+ *   - Every function returns 0 on success; non-zero = STARK_E_* and stark_last_error() (thread-local)
+ *     describes it.  Nothing unwinds across this boundary; the Rust shim maps non-zero to `panic!`,
+ *     the reference's error convention (e.g. src/polynomial/ops.rs:143, src/merkle/mod.rs:25).
+ *   - Host pointers are caller-owned.  Opaque handles (stark_ctx, stark_vec, stark_tree, stark_fri,
+ *     stark_channel) are library-owned and released with their *_destroy function.
+ *   - A context is bound to one CUDA device and one modulus and serialises its callers (safe to call
+ *     from rayon workers, cf. src/polynomial/interpolation.rs:89-111).
+ *   - There is no CPU fallback: without a CUDA device stark_ctx_create fails with STARK_E_CUDA.
+ */
+#ifndef STARK_B200_H
+#define STARK_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STARK_OK 0
+#define STARK_E_INVALID 1      /* bad argument (the reference would panic) */
+#define STARK_E_CUDA 2         /* CUDA runtime / no device */
+#define STARK_E_UNSUPPORTED 3  /* outside the supported domain (modulus >= 2^32, size not dividing p-1, ...) */
+#define STARK_E_INTERNAL 4
+
+typedef struct stark_ctx stark_ctx;
+typedef struct stark_vec stark_vec;         /* device-resident Vec<FieldElement<M>> */
+typedef struct stark_tree stark_tree;       /* MerkleTree<M>            (src/merkle/mod.rs:5-7) */
+typedef struct stark_fri stark_fri;         /* FRIProof                 (src/fri/fri_commit.rs:9-13) */
+typedef struct stark_channel stark_channel; /* Channel<M>               (src/channel/channel.rs:14-20) */
+
+const char* stark_last_error(void);
+const char* stark_version(void);
+
+/* ---- context -------------------------------------------------------------------------------------
+ * generator: a generator of F_p^* (5 for p = 3221225473); w_n = generator^((p-1)/n) is the n-th root of
+ * unity used for every domain, the convention of SURVEY.md 8(c)/(d).  generator == 0 lets the library
+ * pick the smallest one. */
+int stark_ctx_create(uint64_t modulus, uint64_t generator, int device, stark_ctx** out);
+void stark_ctx_destroy(stark_ctx* ctx);
+int stark_ctx_sync(stark_ctx* ctx);
+uint64_t stark_ctx_modulus(const stark_ctx* ctx);
+uint64_t stark_ctx_generator(const stark_ctx* ctx);
+uint64_t stark_ctx_root_of_unity(const stark_ctx* ctx, unsigned log_n);
+unsigned stark_ctx_two_adicity(const stark_ctx* ctx);
+/* number of kernels launched through this context so far (bench.py's gpu_launches) */
+unsigned long long stark_ctx_launch_count(const stark_ctx* ctx);
+/* The stream all work of this context is issued on (a cudaStream_t), for CUDA-event timing. */
+void* stark_ctx_stream(const stark_ctx* ctx);
+
+/* ---- device vectors ------------------------------------------------------------------------------ */
+int stark_vec_upload(stark_ctx* ctx, const uint64_t* host, size_t n, stark_vec** out);
+int stark_vec_alloc(stark_ctx* ctx, size_t n, stark_vec** out);                 /* zero-filled */
+int stark_vec_download(const stark_vec* v, size_t offset, size_t n, uint64_t* host);
+size_t stark_vec_len(const stark_vec* v);
+/* device address of the n canonical u32 values (for NCCL exchanges issued by the caller) */
+void* stark_vec_device_ptr(const stark_vec* v);
+void stark_vec_destroy(stark_vec* v);
+
+/* ---- polynomial: src/polynomial ------------------------------------------------------------------
+ * Domains are power-of-two cosets D[i] = offset * w_n^i in natural order (src/fri/coset_fri.rs:32-36).
+ *
+ * stark_coset_evaluate   == domain.iter().map(|x| poly.evaluate(x))      ops.rs:76-83 at fri_commit.rs:78
+ * stark_coset_interpolate== Polynomial::interpolate(domain, evals)       ops.rs:239-241 -> interpolation.rs:121-152
+ *                           (n coefficients, low -> high, NOT trimmed; the shim's Polynomial::new trims)
+ * stark_coset_lde        == interpolate on offset_in*<w_n>, evaluate on offset_out*<w_{n*2^log_blowup}>
+ * stark_ntt / stark_intt == the same with offset 1, in place
+ * stark_batch_inverse    == a.iter().map(|x| x.inverse())                element.rs:54-57 (inverse(0) == 0)
+ * stark_quotient_pointwise == num[i] / den[i]                            element.rs:116-122; the evaluation-
+ *                           space form of Polynomial::div by a vanishing polynomial (ops.rs:141-191, :412-421)
+ */
+int stark_ntt(stark_ctx* ctx, uint64_t* inout, unsigned log_n);
+int stark_intt(stark_ctx* ctx, uint64_t* inout, unsigned log_n);
+int stark_coset_evaluate(stark_ctx* ctx, const uint64_t* coeffs, size_t n_coeffs, unsigned log_n, uint64_t offset,
+                         uint64_t* out);
+int stark_coset_interpolate(stark_ctx* ctx, const uint64_t* evals, unsigned log_n, uint64_t offset, uint64_t* coeffs_out);
+int stark_coset_lde(stark_ctx* ctx, const uint64_t* evals, unsigned log_n, uint64_t offset_in, unsigned log_blowup,
+                    uint64_t offset_out, uint64_t* out);
+int stark_batch_inverse(stark_ctx* ctx, uint64_t* inout, size_t n);
+int stark_quotient_pointwise(stark_ctx* ctx, const uint64_t* num, const uint64_t* den, size_t n, uint64_t* out);
+int stark_coset_domain(stark_ctx* ctx, unsigned log_n, uint64_t offset, uint64_t* out);   /* coset_fri.rs:32-36 */
+/* device-resident variants (inputs already in HBM; outputs are new vectors) */
+int stark_coset_evaluate_dev(stark_ctx* ctx, const stark_vec* coeffs, unsigned log_n, uint64_t offset, stark_vec** out);
+int stark_coset_interpolate_dev(stark_ctx* ctx, const stark_vec* evals, uint64_t offset, stark_vec** out);
+int stark_coset_lde_dev(stark_ctx* ctx, const stark_vec* evals, uint64_t offset_in, unsigned log_blowup,
+                        uint64_t offset_out, stark_vec** out);
+int stark_batch_inverse_dev(stark_ctx* ctx, const stark_vec* a, stark_vec** out);
+int stark_quotient_pointwise_dev(stark_ctx* ctx, const stark_vec* num, const stark_vec* den, stark_vec** out);
+
+/* ---- merkle: src/merkle/mod.rs -------------------------------------------------------------------
+ * stark_merkle_commit == MerkleTree::new(data)   :10-22   leaf = SHA-256(value.to_be_bytes()), rs_merkle tree
+ * stark_merkle_root_hex == MerkleTree::root()    :24-26   64 lowercase hex chars + NUL
+ * stark_merkle_open   == the `get_authentication_path(idx)` that src/fri/fri_commit.rs:157 calls and the
+ *                        reference never defines: sibling digests bottom -> top, 32 bytes each
+ *                        (rs_merkle MerkleProof::to_bytes for one leaf).
+ * n == 0 is STARK_E_INVALID (root() would panic on unwrap, :25). */
+int stark_merkle_commit(stark_ctx* ctx, const uint64_t* leaves, size_t n, stark_tree** out);
+int stark_merkle_commit_dev(stark_ctx* ctx, const stark_vec* leaves, stark_tree** out);
+int stark_merkle_root(const stark_tree* t, uint8_t root[32]);
+int stark_merkle_root_hex(const stark_tree* t, char out[65]);
+size_t stark_merkle_num_leaves(const stark_tree* t);
+size_t stark_merkle_depth(const stark_tree* t);
+int stark_merkle_open(const stark_tree* t, size_t idx, uint8_t* path, size_t cap, size_t* path_len);
+/* digest j of level l >= 1 (level 0 digests are not stored; they are SHA-256 of the leaf) */
+int stark_merkle_node(const stark_tree* t, size_t level, size_t j, uint8_t out[32]);
+void stark_tree_destroy(stark_tree* t);
+
+/* ---- channel: src/channel/channel.rs (host side; kept here so C/C++ callers have the transcript) -- */
+int stark_channel_new(uint64_t modulus, stark_channel** out);                                  /* :24-30 */
+void stark_channel_destroy(stark_channel* ch);
+int stark_channel_send(stark_channel* ch, const uint8_t* msg, size_t len);                       /* :35-44 */
+int stark_channel_receive_random_field_element(stark_channel* ch, uint64_t* out);               /* :47-55 */
+int stark_channel_receive_random_int(stark_channel* ch, uint64_t min, uint64_t max, int show_in_proof, uint64_t* out); /* :58-84 */
+size_t stark_channel_proof_size(const stark_channel* ch);                                       /* :88-90 */
+size_t stark_channel_compressed_proof_size(const stark_channel* ch);                            /* :93-95 */
+const char* stark_channel_state(const stark_channel* ch);
+size_t stark_channel_proof_len(const stark_channel* ch);
+size_t stark_channel_proof_msg(const stark_channel* ch, size_t i, const uint8_t** data);
+/* all proof messages as  u32-LE length || bytes  records; returns total size (out may be NULL) */
+size_t stark_channel_proof_flat(const stark_channel* ch, uint8_t* out);
+
+/* ---- FRI: src/fri/fri_commit.rs ------------------------------------------------------------------
+ * Step API (the Rust shim keeps its own Channel and drives these):
+ *   stark_fri_begin  == lines :78-86   evaluate on the coset, build the tree; root returned
+ *   stark_fri_degree == poly.degree    (exact, ops.rs:19-37), the loop condition of :89
+ *   stark_fri_fold   == lines :91-103  given beta: next_fri_layer (:53-65) fused with MerkleTree::new (:97)
+ *   stark_fri_final  == lines :109-113 the constant that is sent last
+ * Whole-loop API with the library's Channel:
+ *   stark_fri_commit          == fri_commit(poly, domain, &mut channel)        :72-122
+ *   stark_decommit_fri_layers == decommit_fri_layers(index, ..., &mut channel) :137-165
+ *   stark_decommit_fri        == decommit_fri(num_queries, max_index, ...)     :168-179
+ * The domain is offset*<w_{2^log_n}>; root messages are the 64 ASCII bytes of the hex root
+ * (src/fri/fri_verify.rs:24-25). */
+int stark_fri_begin(stark_ctx* ctx, const uint64_t* coeffs, size_t n_coeffs, unsigned log_n, uint64_t offset,
+                    stark_fri** out, uint8_t root[32]);
+int stark_fri_begin_dev(stark_ctx* ctx, const stark_vec* coeffs, unsigned log_n, uint64_t offset, stark_fri** out,
+                        uint8_t root[32]);
+int stark_fri_degree(const stark_fri* f, long long* degree);
+int stark_fri_fold(stark_fri* f, uint64_t beta, uint8_t root[32]);
+int stark_fri_final(const stark_fri* f, uint64_t* value, size_t* final_poly_len);
+size_t stark_fri_num_layers(const stark_fri* f);
+size_t stark_fri_layer_len(const stark_fri* f, size_t k);
+int stark_fri_layer_read(const stark_fri* f, size_t k, size_t offset, size_t n, uint64_t* out);
+const stark_tree* stark_fri_layer_tree(const stark_fri* f, size_t k);           /* borrowed */
+/* Openings of `n_idx` query indices across all layers in one launch.  For each query, for each layer k:
+ *   BE8(evals[idx]) || path(idx) || BE8(evals[sib]) || path(sib),  idx = index % len_k, sib = (idx+len_k/2) % len_k
+ * written back to back.  *len receives the total; call with out == NULL to size. */
+int stark_fri_open(const stark_fri* f, const uint64_t* indices, size_t n_idx, uint8_t* out, size_t cap, size_t* len);
+void stark_fri_destroy(stark_fri* f);
+
+int stark_fri_commit(stark_ctx* ctx, const uint64_t* coeffs, size_t n_coeffs, unsigned log_n, uint64_t offset,
+                     stark_channel* ch, stark_fri** out);
+int stark_fri_commit_dev(stark_ctx* ctx, const stark_vec* coeffs, unsigned log_n, uint64_t offset,
+                         stark_channel* ch, stark_fri** out);
+int stark_decommit_fri_layers(const stark_fri* f, size_t index, stark_channel* ch);
+int stark_decommit_fri(const stark_fri* f, size_t num_queries, size_t max_index, stark_channel* ch);
+
+/* ---- prover (build-defined: src/prover, src/trace, src/composition are empty in the reference) ----
+ * STARK-101 FibonacciSq statement a0 = 1, a1 = `a1`, a_{n+2} = a_{n+1}^2 + a_n^2 over 2^log_trace - 1 rows;
+ * protocol and transcript order in DESIGN.md "cfg1". */
+int stark101_prove(stark_ctx* ctx, uint64_t a1, unsigned log_trace, unsigned log_blowup, size_t num_queries,
+                   stark_channel* ch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

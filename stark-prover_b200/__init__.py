@@ -1,0 +1,513 @@
+"""stark-prover_b200 — ctypes binding of libstark_b200.so (include/stark_b200.h).
+
+The product is the CUDA library; this module is the Python host-side mirror used by the tests and the
+benchmark.  Names follow the reference crate (RazorClient/Stark-prover): `MerkleTree.new/root`
+(src/merkle/mod.rs:10-26), `Channel.send/receive_random_*` (src/channel/channel.rs:35-84),
+`CosetFri.generate_coset_domain` (src/fri/coset_fri.rs:32-36), `fri_commit`, `decommit_fri_layers`,
+`decommit_fri` (src/fri/fri_commit.rs:72-179), `Polynomial.evaluate/interpolate` over a coset
+(src/polynomial/ops.rs:76-83, :239-241).
+
+There is no CPU fallback: importing works anywhere (so the symbol table can be checked), but every
+compute entry point needs a CUDA device and raises `StarkError` otherwise.  The package directory name
+contains a hyphen; import it with `importlib.import_module("stark-prover_b200")` or through the
+`stark_prover_b200` alias module at the repo root.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Iterable, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstark_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "stark_b200.h")
+
+P_DEFAULT = 3221225473          # 3 * 2^30 + 1, the STARK-101 field
+G_DEFAULT = 5                   # generator of F_p^*
+
+u64, u64p, u8p, szt, vp = C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.c_size_t, C.c_void_p
+
+
+class StarkError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    """Loads libstark_b200.so; fails loudly when it has not been built (python build_ext.py)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise StarkError(4, f"{LIB_PATH} is missing: build it with `python build_ext.py` (nvcc, sm_100a). "
+                            "There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+
+    def sig(name, res, *args):
+        f = getattr(L, name)
+        f.restype, f.argtypes = res, list(args)
+
+    I = C.c_int
+    sig("stark_last_error", C.c_char_p)
+    sig("stark_version", C.c_char_p)
+    sig("stark_ctx_create", I, u64, u64, I, C.POINTER(vp))
+    sig("stark_ctx_destroy", None, vp)
+    sig("stark_ctx_sync", I, vp)
+    sig("stark_ctx_modulus", u64, vp)
+    sig("stark_ctx_generator", u64, vp)
+    sig("stark_ctx_root_of_unity", u64, vp, C.c_uint)
+    sig("stark_ctx_two_adicity", C.c_uint, vp)
+    sig("stark_ctx_launch_count", C.c_ulonglong, vp)
+    sig("stark_ctx_stream", vp, vp)
+    sig("stark_vec_upload", I, vp, vp, szt, C.POINTER(vp))
+    sig("stark_vec_alloc", I, vp, szt, C.POINTER(vp))
+    sig("stark_vec_download", I, vp, szt, szt, vp)
+    sig("stark_vec_len", szt, vp)
+    sig("stark_vec_device_ptr", vp, vp)
+    sig("stark_vec_destroy", None, vp)
+    sig("stark_ntt", I, vp, vp, C.c_uint)
+    sig("stark_intt", I, vp, vp, C.c_uint)
+    sig("stark_coset_evaluate", I, vp, vp, szt, C.c_uint, u64, vp)
+    sig("stark_coset_interpolate", I, vp, vp, C.c_uint, u64, vp)
+    sig("stark_coset_lde", I, vp, vp, C.c_uint, u64, C.c_uint, u64, vp)
+    sig("stark_batch_inverse", I, vp, vp, szt)
+    sig("stark_quotient_pointwise", I, vp, vp, vp, szt, vp)
+    sig("stark_coset_domain", I, vp, C.c_uint, u64, vp)
+    sig("stark_coset_evaluate_dev", I, vp, vp, C.c_uint, u64, C.POINTER(vp))
+    sig("stark_coset_interpolate_dev", I, vp, vp, u64, C.POINTER(vp))
+    sig("stark_coset_lde_dev", I, vp, vp, u64, C.c_uint, u64, C.POINTER(vp))
+    sig("stark_batch_inverse_dev", I, vp, vp, C.POINTER(vp))
+    sig("stark_quotient_pointwise_dev", I, vp, vp, vp, C.POINTER(vp))
+    sig("stark_merkle_commit", I, vp, vp, szt, C.POINTER(vp))
+    sig("stark_merkle_commit_dev", I, vp, vp, C.POINTER(vp))
+    sig("stark_merkle_root", I, vp, vp)
+    sig("stark_merkle_root_hex", I, vp, C.c_char_p)
+    sig("stark_merkle_num_leaves", szt, vp)
+    sig("stark_merkle_depth", szt, vp)
+    sig("stark_merkle_open", I, vp, szt, vp, szt, C.POINTER(szt))
+    sig("stark_merkle_node", I, vp, szt, szt, vp)
+    sig("stark_tree_destroy", None, vp)
+    sig("stark_channel_new", I, u64, C.POINTER(vp))
+    sig("stark_channel_destroy", None, vp)
+    sig("stark_channel_send", I, vp, C.c_char_p, szt)
+    sig("stark_channel_receive_random_field_element", I, vp, C.POINTER(u64))
+    sig("stark_channel_receive_random_int", I, vp, u64, u64, I, C.POINTER(u64))
+    sig("stark_channel_proof_size", szt, vp)
+    sig("stark_channel_compressed_proof_size", szt, vp)
+    sig("stark_channel_state", C.c_char_p, vp)
+    sig("stark_channel_proof_len", szt, vp)
+    sig("stark_channel_proof_msg", szt, vp, szt, C.POINTER(u8p))
+    sig("stark_channel_proof_flat", szt, vp, vp)
+    sig("stark_fri_begin", I, vp, vp, szt, C.c_uint, u64, C.POINTER(vp), vp)
+    sig("stark_fri_begin_dev", I, vp, vp, C.c_uint, u64, C.POINTER(vp), vp)
+    sig("stark_fri_degree", I, vp, C.POINTER(C.c_longlong))
+    sig("stark_fri_fold", I, vp, u64, vp)
+    sig("stark_fri_final", I, vp, C.POINTER(u64), C.POINTER(szt))
+    sig("stark_fri_num_layers", szt, vp)
+    sig("stark_fri_layer_len", szt, vp, szt)
+    sig("stark_fri_layer_read", I, vp, szt, szt, szt, vp)
+    sig("stark_fri_layer_tree", vp, vp, szt)
+    sig("stark_fri_open", I, vp, vp, szt, vp, szt, C.POINTER(szt))
+    sig("stark_fri_destroy", None, vp)
+    sig("stark_fri_commit", I, vp, vp, szt, C.c_uint, u64, vp, C.POINTER(vp))
+    sig("stark_fri_commit_dev", I, vp, vp, C.c_uint, u64, vp, C.POINTER(vp))
+    sig("stark_decommit_fri_layers", I, vp, szt, vp)
+    sig("stark_decommit_fri", I, vp, szt, szt, vp)
+    sig("stark101_prove", I, vp, u64, C.c_uint, C.c_uint, szt, vp)
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise StarkError(rc, lib().stark_last_error().decode(errors="replace"))
+
+
+def _arr(x) -> np.ndarray:
+    """Contiguous uint64 view/copy of x (pinned torch tensors pass through .numpy() untouched)."""
+    if isinstance(x, np.ndarray) and x.dtype == np.uint64 and x.flags["C_CONTIGUOUS"]:
+        return x
+    return np.ascontiguousarray(np.asarray(x, dtype=np.uint64))
+
+
+def _ptr(a: np.ndarray):
+    return C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """One per (device, modulus).  `generator` fixes w_n = generator^((p-1)/n)."""
+
+    def __init__(self, modulus: int = P_DEFAULT, generator: int = G_DEFAULT, device: int = 0):
+        h = vp()
+        _check(lib().stark_ctx_create(modulus, generator, device, C.byref(h)))
+        self.h = h
+        self.modulus = lib().stark_ctx_modulus(h)
+        self.generator = lib().stark_ctx_generator(h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().stark_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self): _check(lib().stark_ctx_sync(self.h))
+    def root_of_unity(self, log_n: int) -> int: return lib().stark_ctx_root_of_unity(self.h, log_n)
+    @property
+    def two_adicity(self) -> int: return lib().stark_ctx_two_adicity(self.h)
+    @property
+    def launch_count(self) -> int: return lib().stark_ctx_launch_count(self.h)
+    @property
+    def stream(self) -> int: return lib().stark_ctx_stream(self.h) or 0
+
+    # ---- device vectors
+    def upload(self, host) -> "Vec":
+        a = _arr(host)
+        h = vp()
+        _check(lib().stark_vec_upload(self.h, _ptr(a), a.size, C.byref(h)))
+        return Vec(self, h)
+
+    def zeros(self, n: int) -> "Vec":
+        h = vp()
+        _check(lib().stark_vec_alloc(self.h, n, C.byref(h)))
+        return Vec(self, h)
+
+    # ---- polynomial (host buffers)
+    def ntt(self, a, log_n: int) -> np.ndarray:
+        a = _arr(a).copy()
+        assert a.size == 1 << log_n
+        _check(lib().stark_ntt(self.h, _ptr(a), log_n))
+        return a
+
+    def intt(self, a, log_n: int) -> np.ndarray:
+        a = _arr(a).copy()
+        assert a.size == 1 << log_n
+        _check(lib().stark_intt(self.h, _ptr(a), log_n))
+        return a
+
+    def coset_evaluate(self, coeffs, log_n: int, offset: int = 1, out: Optional[np.ndarray] = None) -> np.ndarray:
+        c = _arr(coeffs)
+        if out is None:
+            out = np.empty(1 << log_n, dtype=np.uint64)
+        _check(lib().stark_coset_evaluate(self.h, _ptr(c), c.size, log_n, offset, _ptr(out)))
+        return out
+
+    def coset_interpolate(self, evals, log_n: int, offset: int = 1) -> np.ndarray:
+        e = _arr(evals)
+        assert e.size == 1 << log_n
+        out = np.empty(1 << log_n, dtype=np.uint64)
+        _check(lib().stark_coset_interpolate(self.h, _ptr(e), log_n, offset, _ptr(out)))
+        return out
+
+    def coset_lde(self, evals, log_n: int, offset_in: int, log_blowup: int, offset_out: int) -> np.ndarray:
+        e = _arr(evals)
+        assert e.size == 1 << log_n
+        out = np.empty(1 << (log_n + log_blowup), dtype=np.uint64)
+        _check(lib().stark_coset_lde(self.h, _ptr(e), log_n, offset_in, log_blowup, offset_out, _ptr(out)))
+        return out
+
+    def batch_inverse(self, a) -> np.ndarray:
+        a = _arr(a).copy()
+        _check(lib().stark_batch_inverse(self.h, _ptr(a), a.size))
+        return a
+
+    def quotient_pointwise(self, num, den) -> np.ndarray:
+        n, d = _arr(num), _arr(den)
+        assert n.size == d.size
+        out = np.empty(n.size, dtype=np.uint64)
+        _check(lib().stark_quotient_pointwise(self.h, _ptr(n), _ptr(d), n.size, _ptr(out)))
+        return out
+
+    def coset_domain(self, log_n: int, offset: int = 1) -> np.ndarray:
+        out = np.empty(1 << log_n, dtype=np.uint64)
+        _check(lib().stark_coset_domain(self.h, log_n, offset, _ptr(out)))
+        return out
+
+    # ---- polynomial (device vectors)
+    def coset_evaluate_dev(self, coeffs: "Vec", log_n: int, offset: int = 1) -> "Vec":
+        h = vp()
+        _check(lib().stark_coset_evaluate_dev(self.h, coeffs.h, log_n, offset, C.byref(h)))
+        return Vec(self, h)
+
+    def coset_interpolate_dev(self, evals: "Vec", offset: int = 1) -> "Vec":
+        h = vp()
+        _check(lib().stark_coset_interpolate_dev(self.h, evals.h, offset, C.byref(h)))
+        return Vec(self, h)
+
+    def coset_lde_dev(self, evals: "Vec", offset_in: int, log_blowup: int, offset_out: int) -> "Vec":
+        h = vp()
+        _check(lib().stark_coset_lde_dev(self.h, evals.h, offset_in, log_blowup, offset_out, C.byref(h)))
+        return Vec(self, h)
+
+    def batch_inverse_dev(self, a: "Vec") -> "Vec":
+        h = vp()
+        _check(lib().stark_batch_inverse_dev(self.h, a.h, C.byref(h)))
+        return Vec(self, h)
+
+    def quotient_pointwise_dev(self, num: "Vec", den: "Vec") -> "Vec":
+        h = vp()
+        _check(lib().stark_quotient_pointwise_dev(self.h, num.h, den.h, C.byref(h)))
+        return Vec(self, h)
+
+
+class Vec:
+    """Device-resident Vec<FieldElement<M>> (canonical u32 values in HBM)."""
+
+    def __init__(self, ctx: Context, h):
+        self.ctx, self.h = ctx, h
+
+    def __len__(self): return lib().stark_vec_len(self.h)
+    @property
+    def device_ptr(self) -> int: return lib().stark_vec_device_ptr(self.h) or 0
+
+    def download(self, offset: int = 0, n: Optional[int] = None) -> np.ndarray:
+        n = len(self) - offset if n is None else n
+        out = np.empty(n, dtype=np.uint64)
+        _check(lib().stark_vec_download(self.h, offset, n, _ptr(out)))
+        return out
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (len(self),), "typestr": "<u4", "data": (self.device_ptr, False), "version": 3}
+
+    def free(self):
+        if getattr(self, "h", None):
+            lib().stark_vec_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class MerkleTree:
+    """MerkleTree<M> (src/merkle/mod.rs:5-27): `new` hashes and builds, `root` is 64 lowercase hex chars."""
+
+    def __init__(self, ctx: Context, h, owned: bool = True, keep=None):
+        self.ctx, self.h, self._owned, self._keep = ctx, h, owned, keep
+
+    @classmethod
+    def new(cls, ctx: Context, data) -> "MerkleTree":
+        h = vp()
+        if isinstance(data, Vec):
+            _check(lib().stark_merkle_commit_dev(ctx.h, data.h, C.byref(h)))
+        else:
+            a = _arr(data)
+            _check(lib().stark_merkle_commit(ctx.h, _ptr(a), a.size, C.byref(h)))
+        return cls(ctx, h)
+
+    def root(self) -> str:
+        buf = C.create_string_buffer(65)
+        _check(lib().stark_merkle_root_hex(self.h, buf))
+        return buf.value.decode()
+
+    def root_bytes(self) -> bytes:
+        out = np.zeros(32, dtype=np.uint8)
+        _check(lib().stark_merkle_root(self.h, _ptr(out)))
+        return out.tobytes()
+
+    @property
+    def num_leaves(self) -> int: return lib().stark_merkle_num_leaves(self.h)
+    @property
+    def depth(self) -> int: return lib().stark_merkle_depth(self.h)
+
+    def get_authentication_path(self, idx: int) -> bytes:
+        out = np.zeros(32 * (self.depth + 1), dtype=np.uint8)
+        n = szt(0)
+        _check(lib().stark_merkle_open(self.h, idx, _ptr(out), out.size, C.byref(n)))
+        return out[: n.value].tobytes()
+
+    def node(self, level: int, j: int) -> bytes:
+        out = np.zeros(32, dtype=np.uint8)
+        _check(lib().stark_merkle_node(self.h, level, j, _ptr(out)))
+        return out.tobytes()
+
+    def free(self):
+        if self._owned and getattr(self, "h", None):
+            lib().stark_tree_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Channel:
+    """Channel<M> (src/channel/channel.rs:14-95)."""
+
+    def __init__(self, modulus: int = P_DEFAULT):
+        h = vp()
+        _check(lib().stark_channel_new(modulus, C.byref(h)))
+        self.h, self.modulus = h, modulus
+
+    def send(self, msg: bytes): _check(lib().stark_channel_send(self.h, msg, len(msg)))
+
+    def receive_random_field_element(self) -> int:
+        v = u64(0)
+        _check(lib().stark_channel_receive_random_field_element(self.h, C.byref(v)))
+        return v.value
+
+    def receive_random_int(self, lo: int, hi: int, show_in_proof: bool = False) -> int:
+        v = u64(0)
+        _check(lib().stark_channel_receive_random_int(self.h, lo, hi, int(show_in_proof), C.byref(v)))
+        return v.value
+
+    def proof_size(self) -> int: return lib().stark_channel_proof_size(self.h)
+    def compressed_proof_size(self) -> int: return lib().stark_channel_compressed_proof_size(self.h)
+    @property
+    def state(self) -> str: return lib().stark_channel_state(self.h).decode()
+
+    @property
+    def proof(self) -> list[bytes]:
+        out = []
+        for i in range(lib().stark_channel_proof_len(self.h)):
+            p = u8p()
+            n = lib().stark_channel_proof_msg(self.h, i, C.byref(p))
+            out.append(bytes(C.cast(p, C.POINTER(C.c_uint8 * n)).contents) if n else b"")
+        return out
+
+    def proof_flat(self) -> bytes:
+        n = lib().stark_channel_proof_flat(self.h, None)
+        out = np.zeros(max(n, 1), dtype=np.uint8)
+        lib().stark_channel_proof_flat(self.h, _ptr(out))
+        return out[:n].tobytes()
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().stark_channel_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class CosetFri:
+    """CosetFri<M> (src/fri/coset_fri.rs:9-51): D = { offset * omega^i }."""
+
+    def __init__(self, ctx: Context, offset: int, log_size: int):
+        self.ctx, self.offset, self.log_size = ctx, offset, log_size
+        self.omega = ctx.root_of_unity(log_size)
+        self.domain_size = 1 << log_size
+
+    def generate_coset_domain(self) -> np.ndarray:
+        return self.ctx.coset_domain(self.log_size, self.offset)
+
+    def next(self) -> "CosetFri":
+        """First half squared (src/fri/fri_commit.rs:18-24): offset^2, omega^2, half the size."""
+        return CosetFri(self.ctx, self.offset * self.offset % self.ctx.modulus, self.log_size - 1)
+
+
+class FriProof:
+    """FRIProof (src/fri/fri_commit.rs:9-13): fri_layers, fri_merkles, final_poly."""
+
+    def __init__(self, ctx: Context, h):
+        self.ctx, self.h = ctx, h
+
+    @property
+    def num_layers(self) -> int: return lib().stark_fri_num_layers(self.h)
+    def layer_len(self, k: int) -> int: return lib().stark_fri_layer_len(self.h, k)
+
+    def layer(self, k: int, offset: int = 0, n: Optional[int] = None) -> np.ndarray:
+        n = self.layer_len(k) - offset if n is None else n
+        out = np.empty(n, dtype=np.uint64)
+        _check(lib().stark_fri_layer_read(self.h, k, offset, n, _ptr(out)))
+        return out
+
+    def tree(self, k: int) -> MerkleTree:
+        return MerkleTree(self.ctx, lib().stark_fri_layer_tree(self.h, k), owned=False, keep=self)
+
+    @property
+    def degree(self) -> int:
+        d = C.c_longlong(0)
+        _check(lib().stark_fri_degree(self.h, C.byref(d)))
+        return d.value
+
+    def fold(self, beta: int) -> bytes:
+        out = np.zeros(32, dtype=np.uint8)
+        _check(lib().stark_fri_fold(self.h, beta, _ptr(out)))
+        return out.tobytes()
+
+    def final_poly(self) -> np.ndarray:
+        v, n = u64(0), szt(0)
+        _check(lib().stark_fri_final(self.h, C.byref(v), C.byref(n)))
+        return np.array([v.value] if n.value else [], dtype=np.uint64)
+
+    def open(self, indices: Sequence[int]) -> bytes:
+        idx = _arr(list(indices))
+        n = szt(0)
+        _check(lib().stark_fri_open(self.h, _ptr(idx), idx.size, None, 0, C.byref(n)))
+        out = np.zeros(max(n.value, 1), dtype=np.uint8)
+        _check(lib().stark_fri_open(self.h, _ptr(idx), idx.size, _ptr(out), out.size, C.byref(n)))
+        return out[: n.value].tobytes()
+
+    def free(self):
+        if getattr(self, "h", None):
+            lib().stark_fri_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def fri_begin(ctx: Context, coeffs, log_n: int, offset: int) -> tuple[FriProof, bytes]:
+    """Layer 0 only (fri_commit.rs:78-86 without the send): returns the proof object and the root."""
+    h = vp()
+    root = np.zeros(32, dtype=np.uint8)
+    if isinstance(coeffs, Vec):
+        _check(lib().stark_fri_begin_dev(ctx.h, coeffs.h, log_n, offset, C.byref(h), _ptr(root)))
+    else:
+        c = _arr(coeffs)
+        _check(lib().stark_fri_begin(ctx.h, _ptr(c), c.size, log_n, offset, C.byref(h), _ptr(root)))
+    return FriProof(ctx, h), root.tobytes()
+
+
+def fri_commit(ctx: Context, poly, domain: CosetFri, channel: Channel) -> FriProof:
+    """fri_commit(poly, domain, &mut channel) (src/fri/fri_commit.rs:72-122)."""
+    h = vp()
+    if isinstance(poly, Vec):
+        _check(lib().stark_fri_commit_dev(ctx.h, poly.h, domain.log_size, domain.offset, channel.h, C.byref(h)))
+    else:
+        c = _arr(poly)
+        _check(lib().stark_fri_commit(ctx.h, _ptr(c), c.size, domain.log_size, domain.offset, channel.h, C.byref(h)))
+    return FriProof(ctx, h)
+
+
+def decommit_fri_layers(index: int, proof: FriProof, channel: Channel) -> None:
+    """src/fri/fri_commit.rs:137-165."""
+    _check(lib().stark_decommit_fri_layers(proof.h, index, channel.h))
+
+
+def decommit_fri(num_queries: int, max_index: int, proof: FriProof, channel: Channel) -> None:
+    """src/fri/fri_commit.rs:168-179."""
+    _check(lib().stark_decommit_fri(proof.h, num_queries, max_index, channel.h))
+
+
+def stark101_prove(ctx: Context, channel: Channel, a1: int = 3141592, log_trace: int = 10, log_blowup: int = 3,
+                   num_queries: int = 3) -> None:
+    """Build-defined FibonacciSq prover."""
+    _check(lib().stark101_prove(ctx.h, a1, log_trace, log_blowup, num_queries, channel.h))
+
+
+def exported_symbols() -> list[str]:
+    """Function names declared in include/stark_b200.h (for the symbol-table test)."""
+    import re
+    txt = open(HEADER_PATH).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(stark\w*)\s*\(", txt)))

@@ -1,0 +1,791 @@
+// api.cu — the extern "C" boundary declared in include/stark_b200.h.
+// Everything here is host orchestration: argument checks, HBM allocation, kernel sequencing on the
+// context's stream, and the one sync per commitment that hands a root to the (host) Channel.
+#include <string.h>
+
+#include <algorithm>
+
+#include "../../include/stark_b200.h"
+#include "handles.hpp"
+
+using namespace starkb200;
+
+namespace {
+thread_local std::string g_last_error;
+void set_error(const std::string& s) { g_last_error = s; }
+}  // namespace
+
+#define STARK_API_GUARD_NULL(cond)                      \
+    if (!(cond)) { set_error("null argument"); return ST_INVALID; }
+#define API_BEGIN try {
+#define API_END                                                                        \
+    }                                                                                  \
+    catch (const StarkError& e) { set_error(e.what()); return e.code; }                \
+    catch (const std::bad_alloc&) { set_error("host out of memory"); return ST_INTERNAL; } \
+    catch (const std::exception& e) { set_error(e.what()); return ST_INTERNAL; }       \
+    return ST_OK;
+
+struct CtxGuard {
+    std::lock_guard<std::recursive_mutex> lk;
+    explicit CtxGuard(stark_ctx* c) : lk(c->mu) { STARK_CUDA(cudaSetDevice(c->device)); }
+};
+
+extern "C" const char* stark_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* stark_version(void) { return "stark-b200 0.1 (sm_100a)"; }
+
+// ======================================================================================= context
+static bool is_prime_u64(uint64_t n) {
+    if (n < 2) return false;
+    for (uint64_t q : {2ull, 3ull, 5ull, 7ull, 11ull, 13ull, 17ull, 19ull, 23ull, 29ull, 31ull, 37ull}) {
+        if (n % q == 0) return n == q;
+    }
+    uint64_t d = n - 1; int s = 0;
+    while ((d & 1) == 0) { d >>= 1; s++; }
+    for (uint64_t a : {2ull, 3ull, 5ull, 7ull, 11ull, 13ull, 17ull, 19ull, 23ull, 29ull, 31ull, 37ull}) {
+        uint64_t x = h_pow(a, d, n);
+        if (x == 1 || x == n - 1) continue;
+        bool comp = true;
+        for (int i = 1; i < s && comp; i++) { x = h_mul(x, x, n); if (x == n - 1) comp = false; }
+        if (comp) return false;
+    }
+    return true;
+}
+static std::vector<uint64_t> prime_factors(uint64_t n) {
+    std::vector<uint64_t> f;
+    for (uint64_t q = 2; q * q <= n; q += (q == 2 ? 1 : 2))
+        if (n % q == 0) { f.push_back(q); while (n % q == 0) n /= q; }
+    if (n > 1) f.push_back(n);
+    return f;
+}
+static bool is_generator(uint64_t g, uint64_t p, const std::vector<uint64_t>& fac) {
+    if (g % p == 0) return false;
+    for (uint64_t q : fac) if (h_pow(g, (p - 1) / q, p) == 1) return false;
+    return true;
+}
+
+extern "C" int stark_ctx_create(uint64_t modulus, uint64_t generator, int device, stark_ctx** out) {
+    API_BEGIN
+    STARK_REQUIRE(out != nullptr, "ctx_create: out is null");
+    *out = nullptr;
+    if (modulus >= ((uint64_t)1 << 32) || modulus < 3 || (modulus & 1) == 0 || !is_prime_u64(modulus))
+        throw StarkError(ST_UNSUPPORTED, "modulus must be an odd prime < 2^32 (the reference's pow() multiplies in u64, element.rs:45,47)");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        throw StarkError(ST_CUDA, std::string("no CUDA device: this library has no CPU fallback (") + cudaGetErrorString(ce) + ")");
+    STARK_REQUIRE(device >= 0 && device < ndev, "ctx_create: bad device ordinal");
+    auto fac = prime_factors(modulus - 1);
+    if (generator == 0) { for (generator = 2; !is_generator(generator, modulus, fac); generator++) {} }
+    STARK_REQUIRE(is_generator(generator, modulus, fac), "ctx_create: `generator` does not generate F_p^*");
+    std::unique_ptr<stark_ctx> c(new stark_ctx());
+    c->device = device; c->modulus = modulus; c->generator = generator % modulus;
+    for (uint64_t m = modulus - 1; (m & 1) == 0; m >>= 1) c->two_adicity++;
+    c->small_log = c->two_adicity < 12 ? c->two_adicity : 12;
+    c->fp.p = (uint32_t)modulus;
+    uint32_t inv = c->fp.p;
+    for (int i = 0; i < 5; i++) inv *= 2u - c->fp.p * inv;
+    c->fp.pinv = inv;
+    c->fp.one = (uint32_t)(((uint64_t)1 << 32) % modulus);
+    c->fp.r2 = (uint32_t)h_mul(c->fp.one, c->fp.one, modulus);
+    STARK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    STARK_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    STARK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    cudaMemPool_t pool;
+    STARK_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;
+    STARK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    STARK_CUDA(cudaHostAlloc((void**)&c->h_result, sizeof(HostResult), cudaHostAllocMapped));
+    memset(c->h_result, 0, sizeof(HostResult));
+    STARK_CUDA(cudaHostGetDevicePointer((void**)&c->d_result, c->h_result, 0));
+    // in-tile twiddles: w_{2^small_log}^k, k < 2^(small_log-1)
+    size_t ns = c->small_log ? ((size_t)1 << (c->small_log - 1)) : 1;
+    std::vector<uint32_t> f(ns), b(ns);
+    uint64_t w = c->root_of_unity(c->small_log), wi = h_inv(w, modulus), af = 1, ab = 1;
+    for (size_t k = 0; k < ns; k++) { f[k] = c->to_mont(af); b[k] = c->to_mont(ab); af = h_mul(af, w, modulus); ab = h_mul(ab, wi, modulus); }
+    c->small_fwd = DevBuf(ns * 4, c->stream); c->small_inv = DevBuf(ns * 4, c->stream);
+    STARK_CUDA(cudaMemcpyAsync(c->small_fwd.p, f.data(), ns * 4, cudaMemcpyHostToDevice, c->stream));
+    STARK_CUDA(cudaMemcpyAsync(c->small_inv.p, b.data(), ns * 4, cudaMemcpyHostToDevice, c->stream));
+    STARK_CUDA(cudaStreamSynchronize(c->stream));
+    *out = c.release();
+    API_END
+}
+extern "C" void stark_ctx_destroy(stark_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->tw.clear();
+    ctx->small_fwd.release(); ctx->small_inv.release();
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->h_result) cudaFreeHost(ctx->h_result);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+extern "C" int stark_ctx_sync(stark_ctx* ctx) {
+    API_BEGIN
+    STARK_REQUIRE(ctx, "null ctx");
+    CtxGuard g(ctx);
+    STARK_CUDA(cudaStreamSynchronize(ctx->stream));
+    API_END
+}
+extern "C" uint64_t stark_ctx_modulus(const stark_ctx* ctx) { return ctx ? ctx->modulus : 0; }
+extern "C" uint64_t stark_ctx_generator(const stark_ctx* ctx) { return ctx ? ctx->generator : 0; }
+extern "C" uint64_t stark_ctx_root_of_unity(const stark_ctx* ctx, unsigned log_n) {
+    return (ctx && log_n <= ctx->two_adicity) ? ctx->root_of_unity(log_n) : 0;
+}
+extern "C" unsigned stark_ctx_two_adicity(const stark_ctx* ctx) { return ctx ? ctx->two_adicity : 0; }
+extern "C" unsigned long long stark_ctx_launch_count(const stark_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void* stark_ctx_stream(const stark_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+// ======================================================================================= vectors
+static DevBufPtr upload_u64(stark_ctx* ctx, const uint64_t* host, size_t n, size_t alloc_n = 0) {
+    if (alloc_n < n) alloc_n = n;
+    DevBufPtr buf = make_buf(std::max<size_t>(alloc_n, 1) * 4, ctx->stream);
+    if (alloc_n > n) STARK_CUDA(cudaMemsetAsync(buf->as<uint32_t>() + n, 0, (alloc_n - n) * 4, ctx->stream));
+    if (n) {
+        DevBuf stage(n * 8, ctx->stream);
+        STARK_CUDA(cudaMemcpyAsync(stage.p, host, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        narrow_u64(ctx, stage.as<uint64_t>(), buf->as<uint32_t>(), n);
+    }
+    return buf;
+}
+static void download_u64(stark_ctx* ctx, const uint32_t* dev, size_t n, uint64_t* host) {
+    if (!n) return;
+    DevBuf stage(n * 8, ctx->stream);
+    widen_u32(ctx, dev, stage.as<uint64_t>(), n);
+    STARK_CUDA(cudaMemcpyAsync(host, stage.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    STARK_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+static stark_vec* new_vec(stark_ctx* ctx, DevBufPtr b, size_t n) {
+    stark_vec* v = new stark_vec(); v->ctx = ctx; v->buf = std::move(b); v->n = n; return v;
+}
+
+extern "C" int stark_vec_upload(stark_ctx* ctx, const uint64_t* host, size_t n, stark_vec** out) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && out && (host || n == 0), "vec_upload: null argument");
+    CtxGuard g(ctx);
+    *out = new_vec(ctx, upload_u64(ctx, host, n), n);
+    API_END
+}
+extern "C" int stark_vec_alloc(stark_ctx* ctx, size_t n, stark_vec** out) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && out, "vec_alloc: null argument");
+    CtxGuard g(ctx);
+    DevBufPtr b = make_buf(std::max<size_t>(n, 1) * 4, ctx->stream);
+    fill_zero(ctx, b->as<uint32_t>(), n);
+    *out = new_vec(ctx, b, n);
+    API_END
+}
+extern "C" int stark_vec_download(const stark_vec* v, size_t offset, size_t n, uint64_t* host) {
+    API_BEGIN
+    STARK_REQUIRE(v && (host || n == 0), "vec_download: null argument");
+    STARK_REQUIRE(offset <= v->n && n <= v->n - offset, "vec_download: range out of bounds");
+    CtxGuard g(v->ctx);
+    download_u64(v->ctx, v->buf->as<uint32_t>() + offset, n, host);
+    API_END
+}
+extern "C" size_t stark_vec_len(const stark_vec* v) { return v ? v->n : 0; }
+extern "C" void* stark_vec_device_ptr(const stark_vec* v) { return v ? v->buf->p : nullptr; }
+extern "C" void stark_vec_destroy(stark_vec* v) {
+    if (!v) return;
+    cudaSetDevice(v->ctx->device);
+    delete v;
+}
+
+// ======================================================================================= polynomial
+static unsigned ceil_log2(size_t n) { unsigned l = 0; while (((size_t)1 << l) < n) l++; return l; }
+static void check_offset(stark_ctx* ctx, uint64_t offset) {
+    STARK_REQUIRE(offset % ctx->modulus != 0, "coset offset must be non-zero");
+}
+
+// coefficients (natural, length len <= 2^log_m, buffer of 2^log_m zero-padded) -> evaluations on offset*<w_{2^log_n}>
+static DevBufPtr evaluate_on_coset(stark_ctx* ctx, const uint32_t* coeffs_padded, unsigned log_m, unsigned log_n, uint64_t offset) {
+    STARK_REQUIRE(log_m <= log_n, "evaluate: more coefficients than domain points");
+    STARK_REQUIRE(log_n <= ctx->two_adicity, "evaluate: 2^log_n does not divide p-1");
+    size_t m = (size_t)1 << log_m, n = (size_t)1 << log_n;
+    DevBuf tmp(m * 4, ctx->stream);
+    bool unit = (offset % ctx->modulus) == 1;
+    ScaleTable st;
+    if (!unit) build_scale_table(ctx, offset, 1, log_m, st);
+    bitrev_permute(ctx, coeffs_padded, tmp.as<uint32_t>(), log_m, unit ? nullptr : &st.view, true);
+    DevBufPtr out = make_buf(n * 4, ctx->stream);
+    ntt_dit(ctx, tmp.as<uint32_t>(), out->as<uint32_t>(), log_n, log_n - log_m, nullptr, false);
+    return out;
+}
+// evaluations on offset*<w_n> (natural) -> n coefficients (natural)
+static DevBufPtr interpolate_on_coset(stark_ctx* ctx, const uint32_t* evals, unsigned log_n, uint64_t offset) {
+    STARK_REQUIRE(log_n <= ctx->two_adicity, "interpolate: 2^log_n does not divide p-1");
+    size_t n = (size_t)1 << log_n;
+    DevBuf tmp(n * 4, ctx->stream);
+    STARK_CUDA(cudaMemcpyAsync(tmp.p, evals, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    ntt_dif(ctx, tmp.as<uint32_t>(), log_n, true);
+    ScaleTable st;   // c_j = n^-1 * offset^-j * raw_j
+    build_scale_table(ctx, h_inv(offset % ctx->modulus, ctx->modulus), h_inv(n % ctx->modulus, ctx->modulus), log_n, st);
+    DevBufPtr out = make_buf(n * 4, ctx->stream);
+    bitrev_permute(ctx, tmp.as<uint32_t>(), out->as<uint32_t>(), log_n, &st.view, false);
+    return out;
+}
+// evaluations on offset_in*<w_n> -> evaluations on offset_out*<w_{n*2^b}>; no permutation anywhere
+static DevBufPtr lde_on_coset(stark_ctx* ctx, const uint32_t* evals, unsigned log_n, uint64_t offset_in, unsigned log_blowup, uint64_t offset_out) {
+    unsigned log_N = log_n + log_blowup;
+    STARK_REQUIRE(log_N <= ctx->two_adicity, "lde: 2^(log_n+log_blowup) does not divide p-1");
+    size_t n = (size_t)1 << log_n, N = (size_t)1 << log_N;
+    DevBuf tmp(n * 4, ctx->stream);
+    STARK_CUDA(cudaMemcpyAsync(tmp.p, evals, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    ntt_dif(ctx, tmp.as<uint32_t>(), log_n, true);                       // bit-reversed, unscaled coefficients
+    uint64_t p = ctx->modulus;
+    ScaleTable st;   // c_j * n^-1 * (offset_out/offset_in)^j, applied on the way into the DIT
+    build_scale_table(ctx, h_mul(offset_out % p, h_inv(offset_in % p, p), p), h_inv(n % p, p), log_n, st);
+    DevBufPtr out = make_buf(N * 4, ctx->stream);
+    ntt_dit(ctx, tmp.as<uint32_t>(), out->as<uint32_t>(), log_N, log_blowup, &st.view, false);
+    return out;
+}
+
+extern "C" int stark_ntt(stark_ctx* ctx, uint64_t* inout, unsigned log_n) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && inout, "ntt: null argument");
+    CtxGuard g(ctx);
+    size_t n = (size_t)1 << log_n;
+    DevBufPtr c = upload_u64(ctx, inout, n);
+    DevBufPtr e = evaluate_on_coset(ctx, c->as<uint32_t>(), log_n, log_n, 1);
+    download_u64(ctx, e->as<uint32_t>(), n, inout);
+    API_END
+}
+extern "C" int stark_intt(stark_ctx* ctx, uint64_t* inout, unsigned log_n) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && inout, "intt: null argument");
+    CtxGuard g(ctx);
+    size_t n = (size_t)1 << log_n;
+    DevBufPtr e = upload_u64(ctx, inout, n);
+    DevBufPtr c = interpolate_on_coset(ctx, e->as<uint32_t>(), log_n, 1);
+    download_u64(ctx, c->as<uint32_t>(), n, inout);
+    API_END
+}
+extern "C" int stark_coset_evaluate(stark_ctx* ctx, const uint64_t* coeffs, size_t n_coeffs, unsigned log_n, uint64_t offset, uint64_t* out) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && out && (coeffs || n_coeffs == 0), "coset_evaluate: null argument");
+    CtxGuard g(ctx);
+    check_offset(ctx, offset);
+    STARK_REQUIRE(log_n <= 30 && n_coeffs <= ((size_t)1 << log_n), "coset_evaluate: more coefficients than domain points");
+    unsigned log_m = ceil_log2(std::max<size_t>(n_coeffs, 1));
+    DevBufPtr c = upload_u64(ctx, coeffs, n_coeffs, (size_t)1 << log_m);
+    DevBufPtr e = evaluate_on_coset(ctx, c->as<uint32_t>(), log_m, log_n, offset);
+    download_u64(ctx, e->as<uint32_t>(), (size_t)1 << log_n, out);
+    API_END
+}
+extern "C" int stark_coset_interpolate(stark_ctx* ctx, const uint64_t* evals, unsigned log_n, uint64_t offset, uint64_t* coeffs_out) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && evals && coeffs_out, "coset_interpolate: null argument");
+    CtxGuard g(ctx);
+    check_offset(ctx, offset);
+    STARK_REQUIRE(log_n <= 30, "coset_interpolate: log_n too large");
+    size_t n = (size_t)1 << log_n;
+    DevBufPtr e = upload_u64(ctx, evals, n);
+    DevBufPtr c = interpolate_on_coset(ctx, e->as<uint32_t>(), log_n, offset);
+    download_u64(ctx, c->as<uint32_t>(), n, coeffs_out);
+    API_END
+}
+extern "C" int stark_coset_lde(stark_ctx* ctx, const uint64_t* evals, unsigned log_n, uint64_t offset_in, unsigned log_blowup,
+                               uint64_t offset_out, uint64_t* out) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && evals && out, "coset_lde: null argument");
+    CtxGuard g(ctx);
+    check_offset(ctx, offset_in); check_offset(ctx, offset_out);
+    STARK_REQUIRE(log_n + log_blowup <= 30, "coset_lde: domain too large");
+    size_t n = (size_t)1 << log_n;
+    DevBufPtr e = upload_u64(ctx, evals, n);
+    DevBufPtr r = lde_on_coset(ctx, e->as<uint32_t>(), log_n, offset_in, log_blowup, offset_out);
+    download_u64(ctx, r->as<uint32_t>(), n << log_blowup, out);
+    API_END
+}
+extern "C" int stark_batch_inverse(stark_ctx* ctx, uint64_t* inout, size_t n) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && (inout || n == 0), "batch_inverse: null argument");
+    CtxGuard g(ctx);
+    DevBufPtr a = upload_u64(ctx, inout, n);
+    batch_inverse(ctx, a->as<uint32_t>(), nullptr, a->as<uint32_t>(), n);
+    download_u64(ctx, a->as<uint32_t>(), n, inout);
+    API_END
+}
+extern "C" int stark_quotient_pointwise(stark_ctx* ctx, const uint64_t* num, const uint64_t* den, size_t n, uint64_t* out) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && ((num && den && out) || n == 0), "quotient_pointwise: null argument");
+    CtxGuard g(ctx);
+    DevBufPtr a = upload_u64(ctx, num, n), b = upload_u64(ctx, den, n);
+    batch_inverse(ctx, b->as<uint32_t>(), a->as<uint32_t>(), b->as<uint32_t>(), n);
+    download_u64(ctx, b->as<uint32_t>(), n, out);
+    API_END
+}
+extern "C" int stark_coset_domain(stark_ctx* ctx, unsigned log_n, uint64_t offset, uint64_t* out) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && out, "coset_domain: null argument");
+    CtxGuard g(ctx);
+    STARK_REQUIRE(log_n <= 30 && log_n <= ctx->two_adicity, "coset_domain: 2^log_n does not divide p-1");
+    size_t n = (size_t)1 << log_n;
+    DevBuf d(n * 4, ctx->stream);
+    coset_domain(ctx, offset, log_n, d.as<uint32_t>());
+    download_u64(ctx, d.as<uint32_t>(), n, out);
+    API_END
+}
+static unsigned exact_log2(size_t n, const char* what) {
+    STARK_REQUIRE(n >= 1 && (n & (n - 1)) == 0, std::string(what) + ": length must be a power of two");
+    return ceil_log2(n);
+}
+extern "C" int stark_coset_evaluate_dev(stark_ctx* ctx, const stark_vec* coeffs, unsigned log_n, uint64_t offset, stark_vec** out) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && coeffs && out && coeffs->ctx == ctx, "coset_evaluate_dev: bad argument");
+    CtxGuard g(ctx);
+    check_offset(ctx, offset);
+    STARK_REQUIRE(log_n <= 30 && coeffs->n <= ((size_t)1 << log_n), "coset_evaluate_dev: more coefficients than domain points");
+    unsigned log_m = ceil_log2(std::max<size_t>(coeffs->n, 1));
+    size_t m = (size_t)1 << log_m;
+    DevBufPtr c = coeffs->buf;
+    if (m != coeffs->n) {
+        c = make_buf(m * 4, ctx->stream);
+        STARK_CUDA(cudaMemsetAsync(c->p, 0, m * 4, ctx->stream));
+        STARK_CUDA(cudaMemcpyAsync(c->p, coeffs->buf->p, coeffs->n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    *out = new_vec(ctx, evaluate_on_coset(ctx, c->as<uint32_t>(), log_m, log_n, offset), (size_t)1 << log_n);
+    API_END
+}
+extern "C" int stark_coset_interpolate_dev(stark_ctx* ctx, const stark_vec* evals, uint64_t offset, stark_vec** out) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && evals && out && evals->ctx == ctx, "coset_interpolate_dev: bad argument");
+    CtxGuard g(ctx);
+    check_offset(ctx, offset);
+    unsigned log_n = exact_log2(evals->n, "coset_interpolate_dev");
+    *out = new_vec(ctx, interpolate_on_coset(ctx, evals->buf->as<uint32_t>(), log_n, offset), evals->n);
+    API_END
+}
+extern "C" int stark_coset_lde_dev(stark_ctx* ctx, const stark_vec* evals, uint64_t offset_in, unsigned log_blowup, uint64_t offset_out, stark_vec** out) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && evals && out && evals->ctx == ctx, "coset_lde_dev: bad argument");
+    CtxGuard g(ctx);
+    check_offset(ctx, offset_in); check_offset(ctx, offset_out);
+    unsigned log_n = exact_log2(evals->n, "coset_lde_dev");
+    STARK_REQUIRE(log_n + log_blowup <= 30, "coset_lde_dev: domain too large");
+    *out = new_vec(ctx, lde_on_coset(ctx, evals->buf->as<uint32_t>(), log_n, offset_in, log_blowup, offset_out), evals->n << log_blowup);
+    API_END
+}
+extern "C" int stark_batch_inverse_dev(stark_ctx* ctx, const stark_vec* a, stark_vec** out) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && a && out && a->ctx == ctx, "batch_inverse_dev: bad argument");
+    CtxGuard g(ctx);
+    DevBufPtr r = make_buf(std::max<size_t>(a->n, 1) * 4, ctx->stream);
+    batch_inverse(ctx, a->buf->as<uint32_t>(), nullptr, r->as<uint32_t>(), a->n);
+    *out = new_vec(ctx, r, a->n);
+    API_END
+}
+extern "C" int stark_quotient_pointwise_dev(stark_ctx* ctx, const stark_vec* num, const stark_vec* den, stark_vec** out) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && num && den && out && num->ctx == ctx && den->ctx == ctx, "quotient_pointwise_dev: bad argument");
+    STARK_REQUIRE(num->n == den->n, "quotient_pointwise_dev: length mismatch");
+    CtxGuard g(ctx);
+    DevBufPtr r = make_buf(std::max<size_t>(num->n, 1) * 4, ctx->stream);
+    batch_inverse(ctx, den->buf->as<uint32_t>(), num->buf->as<uint32_t>(), r->as<uint32_t>(), num->n);
+    *out = new_vec(ctx, r, num->n);
+    API_END
+}
+
+// ======================================================================================= merkle
+static void words_to_bytes(const uint32_t w[8], uint8_t out[32]) {
+    for (int i = 0; i < 8; i++) { out[4 * i] = (uint8_t)(w[i] >> 24); out[4 * i + 1] = (uint8_t)(w[i] >> 16); out[4 * i + 2] = (uint8_t)(w[i] >> 8); out[4 * i + 3] = (uint8_t)w[i]; }
+}
+// Builds the tree over `src` on the stream (no sync); the root lands in ctx->h_result.
+static std::unique_ptr<stark_tree> tree_launch(stark_ctx* ctx, DevBufPtr leaves, size_t n, const LeafSource& src) {
+    std::unique_ptr<stark_tree> t(new stark_tree());
+    t->ctx = ctx; t->leaves = std::move(leaves);
+    t->shape = TreeShape::make(n);
+    t->nodes = DevBuf(t->shape.total * 32, ctx->stream);
+    merkle_build(ctx, src, t->shape, t->nodes.as<uint32_t>(), ctx->d_result);
+    return t;
+}
+static void tree_take_root(stark_tree* t) {   // after a stream sync
+    memcpy(t->root_words, t->ctx->h_result->root, 32);
+}
+static std::unique_ptr<stark_tree> tree_commit(stark_ctx* ctx, DevBufPtr leaves, size_t n) {
+    STARK_REQUIRE(n >= 1, "MerkleTree::new on an empty vector: root() would panic on unwrap (merkle/mod.rs:25)");
+    STARK_REQUIRE(n <= ((size_t)1 << 32), "merkle: more than 2^32 leaves");
+    LeafSource src; src.vals = leaves->as<uint32_t>();
+    auto t = tree_launch(ctx, leaves, n, src);
+    STARK_CUDA(cudaStreamSynchronize(ctx->stream));
+    tree_take_root(t.get());
+    return t;
+}
+extern "C" int stark_merkle_commit(stark_ctx* ctx, const uint64_t* leaves, size_t n, stark_tree** out) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && out && (leaves || n == 0), "merkle_commit: null argument");
+    CtxGuard g(ctx);
+    STARK_REQUIRE(n >= 1, "MerkleTree::new on an empty vector: root() would panic on unwrap (merkle/mod.rs:25)");
+    *out = tree_commit(ctx, upload_u64(ctx, leaves, n), n).release();
+    API_END
+}
+extern "C" int stark_merkle_commit_dev(stark_ctx* ctx, const stark_vec* leaves, stark_tree** out) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && out && leaves && leaves->ctx == ctx, "merkle_commit_dev: bad argument");
+    CtxGuard g(ctx);
+    *out = tree_commit(ctx, leaves->buf, leaves->n).release();
+    API_END
+}
+extern "C" int stark_merkle_root(const stark_tree* t, uint8_t root[32]) {
+    API_BEGIN
+    STARK_REQUIRE(t && root, "merkle_root: null argument");
+    words_to_bytes(t->root_words, root);
+    API_END
+}
+extern "C" int stark_merkle_root_hex(const stark_tree* t, char out[65]) {
+    API_BEGIN
+    STARK_REQUIRE(t && out, "merkle_root_hex: null argument");
+    uint8_t r[32]; words_to_bytes(t->root_words, r);
+    std::string h = HostSha256::hex(r, 32);
+    memcpy(out, h.c_str(), 65);
+    API_END
+}
+extern "C" size_t stark_merkle_num_leaves(const stark_tree* t) { return t ? t->shape.n : 0; }
+extern "C" size_t stark_merkle_depth(const stark_tree* t) { return t ? t->shape.depth : 0; }
+
+// One launch for a batch of (tree, idx) records; records are BE8(value) || path.
+static void open_records(stark_ctx* ctx, const std::vector<OpenDesc>& descs, size_t total_bytes, uint8_t* host_out) {
+    if (descs.empty()) return;
+    DevBuf d_desc(descs.size() * sizeof(OpenDesc), ctx->stream), d_out(total_bytes, ctx->stream);
+    STARK_CUDA(cudaMemcpyAsync(d_desc.p, descs.data(), descs.size() * sizeof(OpenDesc), cudaMemcpyHostToDevice, ctx->stream));
+    merkle_open(ctx, d_desc.as<OpenDesc>(), descs.size(), d_out.as<uint8_t>());
+    STARK_CUDA(cudaMemcpyAsync(host_out, d_out.p, total_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    STARK_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+extern "C" int stark_merkle_open(const stark_tree* t, size_t idx, uint8_t* path, size_t cap, size_t* path_len) {
+    API_BEGIN
+    STARK_REQUIRE(t && path_len, "merkle_open: null argument");
+    STARK_REQUIRE(idx < t->shape.n, "merkle_open: leaf index out of range");
+    size_t pl = merkle_path_len(t->shape.n, idx);
+    *path_len = pl;
+    if (!path) return ST_OK;
+    STARK_REQUIRE(cap >= pl, "merkle_open: buffer too small");
+    CtxGuard g(t->ctx);
+    std::vector<OpenDesc> d(1);
+    d[0] = OpenDesc{t->leaves->as<uint32_t>(), t->nodes.as<uint32_t>(), t->shape.n, idx, 0};
+    std::vector<uint8_t> rec(8 + pl);
+    open_records(t->ctx, d, rec.size(), rec.data());
+    memcpy(path, rec.data() + 8, pl);
+    API_END
+}
+extern "C" int stark_merkle_node(const stark_tree* t, size_t level, size_t j, uint8_t out[32]) {
+    API_BEGIN
+    STARK_REQUIRE(t && out, "merkle_node: null argument");
+    STARK_REQUIRE(level >= 1 && level <= t->shape.depth && j < t->shape.len[level], "merkle_node: no such node (level 0 digests are not stored)");
+    CtxGuard g(t->ctx);
+    uint32_t w[8];
+    STARK_CUDA(cudaMemcpyAsync(w, t->nodes.as<uint32_t>() + 8 * (t->shape.off[level] + j), 32, cudaMemcpyDeviceToHost, t->ctx->stream));
+    STARK_CUDA(cudaStreamSynchronize(t->ctx->stream));
+    words_to_bytes(w, out);
+    API_END
+}
+extern "C" void stark_tree_destroy(stark_tree* t) {
+    if (!t) return;
+    cudaSetDevice(t->ctx->device);
+    delete t;
+}
+
+// ======================================================================================= channel
+extern "C" int stark_channel_new(uint64_t modulus, stark_channel** out) {
+    API_BEGIN
+    STARK_REQUIRE(out && modulus >= 2, "channel_new: bad argument");
+    *out = new stark_channel(modulus);
+    API_END
+}
+extern "C" void stark_channel_destroy(stark_channel* ch) { delete ch; }
+extern "C" int stark_channel_send(stark_channel* ch, const uint8_t* msg, size_t len) {
+    API_BEGIN
+    STARK_REQUIRE(ch && (msg || len == 0), "channel_send: null argument");
+    ch->ch.send(msg, len);
+    API_END
+}
+extern "C" int stark_channel_receive_random_field_element(stark_channel* ch, uint64_t* out) {
+    API_BEGIN
+    STARK_REQUIRE(ch && out, "channel: null argument");
+    STARK_REQUIRE(ch->ch.receive_random_field_element(out), "Channel state is not valid hex (receive before any send, channel.rs:64-65)");
+    API_END
+}
+extern "C" int stark_channel_receive_random_int(stark_channel* ch, uint64_t min, uint64_t max, int show, uint64_t* out) {
+    API_BEGIN
+    STARK_REQUIRE(ch && out, "channel: null argument");
+    STARK_REQUIRE(ch->ch.receive_random_int(min, max, show != 0, out), "Channel state is not valid hex / empty range (channel.rs:64-68)");
+    API_END
+}
+extern "C" size_t stark_channel_proof_size(const stark_channel* ch) { return ch ? ch->ch.proof_size() : 0; }
+extern "C" size_t stark_channel_compressed_proof_size(const stark_channel* ch) { return ch ? ch->ch.compressed_proof_size() : 0; }
+extern "C" const char* stark_channel_state(const stark_channel* ch) { return ch ? ch->ch.state.c_str() : ""; }
+extern "C" size_t stark_channel_proof_len(const stark_channel* ch) { return ch ? ch->ch.proof.size() : 0; }
+extern "C" size_t stark_channel_proof_msg(const stark_channel* ch, size_t i, const uint8_t** data) {
+    if (!ch || i >= ch->ch.proof.size()) return 0;
+    if (data) *data = ch->ch.proof[i].data();
+    return ch->ch.proof[i].size();
+}
+extern "C" size_t stark_channel_proof_flat(const stark_channel* ch, uint8_t* out) {
+    if (!ch) return 0;
+    size_t w = 0;
+    for (auto& m : ch->ch.proof) {
+        uint32_t n = (uint32_t)m.size();
+        if (out) { out[w] = n & 255; out[w + 1] = (n >> 8) & 255; out[w + 2] = (n >> 16) & 255; out[w + 3] = n >> 24; if (n) memcpy(out + w + 4, m.data(), n); }
+        w += 4 + n;
+    }
+    return w;
+}
+
+// ======================================================================================= FRI
+static void fri_begin_impl(stark_ctx* ctx, DevBufPtr coeffs_padded, size_t len, unsigned log_m, unsigned log_n,
+                           uint64_t offset, stark_fri** out, uint8_t root[32]) {
+    STARK_REQUIRE(log_n <= ctx->two_adicity && log_n <= 30, "fri: 2^log_n does not divide p-1");
+    STARK_REQUIRE(log_m <= log_n, "fri: polynomial has more coefficients than the domain has points");
+    std::unique_ptr<stark_fri> f(new stark_fri());
+    f->ctx = ctx; f->log_n = log_n; f->offset0 = offset % ctx->modulus;
+    f->cur_log = log_n; f->cur_offset = f->offset0;
+    f->coeffs = coeffs_padded; f->coeff_len = len;
+    DevBufPtr ev = evaluate_on_coset(ctx, f->coeffs->as<uint32_t>(), log_m, log_n, offset);          // fri_commit.rs:78
+    LeafSource src; src.vals = ev->as<uint32_t>();
+    auto t = tree_launch(ctx, ev, (size_t)1 << log_n, src);                                          // :79
+    STARK_CUDA(cudaStreamSynchronize(ctx->stream));
+    tree_take_root(t.get());
+    if (root) words_to_bytes(t->root_words, root);
+    f->trees.push_back(std::move(t));
+    *out = f.release();
+}
+extern "C" int stark_fri_begin(stark_ctx* ctx, const uint64_t* coeffs, size_t n_coeffs, unsigned log_n, uint64_t offset,
+                               stark_fri** out, uint8_t root[32]) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && out && (coeffs || n_coeffs == 0), "fri_begin: null argument");
+    CtxGuard g(ctx);
+    check_offset(ctx, offset);
+    size_t len = n_coeffs;                                               // Polynomial::new trims (ops.rs:19-37)
+    while (len > 0 && coeffs[len - 1] % ctx->modulus == 0) len--;
+    STARK_REQUIRE(log_n <= 30 && len <= ((size_t)1 << log_n), "fri: polynomial has more coefficients than the domain has points");
+    unsigned log_m = ceil_log2(std::max<size_t>(len, 1));
+    DevBufPtr c = upload_u64(ctx, coeffs, len, (size_t)1 << log_m);
+    fri_begin_impl(ctx, c, len, log_m, log_n, offset, out, root);
+    API_END
+}
+extern "C" int stark_fri_begin_dev(stark_ctx* ctx, const stark_vec* coeffs, unsigned log_n, uint64_t offset, stark_fri** out,
+                                   uint8_t root[32]) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && out && coeffs && coeffs->ctx == ctx, "fri_begin_dev: bad argument");
+    CtxGuard g(ctx);
+    check_offset(ctx, offset);
+    size_t len = 0;
+    if (coeffs->n) {
+        poly_degree(ctx, coeffs->buf->as<uint32_t>(), coeffs->n, ctx->d_result);
+        STARK_CUDA(cudaStreamSynchronize(ctx->stream));
+        len = (size_t)ctx->h_result->degree_plus1;
+    }
+    STARK_REQUIRE(log_n <= 30 && len <= ((size_t)1 << log_n), "fri: polynomial has more coefficients than the domain has points");
+    unsigned log_m = ceil_log2(std::max<size_t>(len, 1));
+    size_t m = (size_t)1 << log_m;
+    DevBufPtr c = make_buf(m * 4, ctx->stream);       // private copy: folds overwrite it
+    STARK_CUDA(cudaMemsetAsync(c->p, 0, m * 4, ctx->stream));
+    if (len) STARK_CUDA(cudaMemcpyAsync(c->p, coeffs->buf->p, len * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    fri_begin_impl(ctx, c, len, log_m, log_n, offset, out, root);
+    API_END
+}
+extern "C" int stark_fri_degree(const stark_fri* f, long long* degree) {
+    API_BEGIN
+    STARK_REQUIRE(f && degree, "fri_degree: null argument");
+    *degree = (long long)f->coeff_len - 1;
+    API_END
+}
+extern "C" int stark_fri_fold(stark_fri* f, uint64_t beta, uint8_t root[32]) {
+    API_BEGIN
+    STARK_REQUIRE(f, "fri_fold: null argument");
+    stark_ctx* ctx = f->ctx;
+    CtxGuard g(ctx);
+    STARK_REQUIRE(f->cur_log >= 1, "fri_fold: the domain has one point left; the next layer would be empty and "
+                                   "MerkleTree::root() would panic (fri_commit.rs:97-100, merkle/mod.rs:25)");
+    const uint64_t p = ctx->modulus;
+    const size_t n = (size_t)1 << f->cur_log, half = n >> 1;
+    // coefficient space: exact degree of even + beta*odd (fri_commit.rs:32-50)
+    if (f->coeff_len > 0) {
+        size_t out_len = (f->coeff_len + 1) / 2;
+        DevBufPtr nc = make_buf(out_len * 4, ctx->stream);
+        coeff_fold(ctx, f->coeffs->as<uint32_t>(), f->coeff_len, ctx->to_mont(beta), nc->as<uint32_t>(), ctx->d_result);
+        f->coeffs = nc;
+    }
+    // evaluation space fused with the next tree (fri_commit.rs:53-65, :97)
+    const stark_tree* prev = f->trees.back().get();
+    DevBufPtr ev = make_buf(half * 4, ctx->stream);
+    LeafSource src;
+    src.prev = prev->leaves->as<uint32_t>(); src.fold_out = ev->as<uint32_t>(); src.half = half;
+    uint64_t inv2 = h_inv(2 % p, p);
+    src.inv2_m = ctx->to_mont(inv2);
+    src.sb_m = ctx->to_mont(h_mul(h_mul(beta % p, inv2, p), h_inv(f->cur_offset, p), p));
+    src.winv = ctx->twiddles(f->cur_log).inv();
+    auto t = tree_launch(ctx, ev, half, src);
+    STARK_CUDA(cudaStreamSynchronize(ctx->stream));
+    tree_take_root(t.get());
+    if (f->coeff_len > 0) f->coeff_len = (size_t)ctx->h_result->degree_plus1;
+    if (root) words_to_bytes(t->root_words, root);
+    f->trees.push_back(std::move(t));
+    f->cur_log -= 1;
+    f->cur_offset = h_mul(f->cur_offset, f->cur_offset, p);
+    API_END
+}
+extern "C" int stark_fri_final(const stark_fri* f, uint64_t* value, size_t* final_poly_len) {
+    API_BEGIN
+    STARK_REQUIRE(f && value, "fri_final: null argument");
+    CtxGuard g(f->ctx);
+    uint32_t c0 = 0;
+    if (f->coeff_len > 0) {
+        STARK_CUDA(cudaMemcpyAsync(&c0, f->coeffs->p, 4, cudaMemcpyDeviceToHost, f->ctx->stream));
+        STARK_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    }
+    *value = c0;                                            // fri_commit.rs:109-113
+    if (final_poly_len) *final_poly_len = f->coeff_len;
+    API_END
+}
+extern "C" size_t stark_fri_num_layers(const stark_fri* f) { return f ? f->trees.size() : 0; }
+extern "C" size_t stark_fri_layer_len(const stark_fri* f, size_t k) { return (f && k < f->trees.size()) ? f->trees[k]->shape.n : 0; }
+extern "C" int stark_fri_layer_read(const stark_fri* f, size_t k, size_t offset, size_t n, uint64_t* out) {
+    API_BEGIN
+    STARK_REQUIRE(f && (out || n == 0) && k < f->trees.size(), "fri_layer_read: bad argument");
+    const stark_tree* t = f->trees[k].get();
+    STARK_REQUIRE(offset <= t->shape.n && n <= t->shape.n - offset, "fri_layer_read: range out of bounds");
+    CtxGuard g(f->ctx);
+    download_u64(f->ctx, t->leaves->as<uint32_t>() + offset, n, out);
+    API_END
+}
+extern "C" const stark_tree* stark_fri_layer_tree(const stark_fri* f, size_t k) { return (f && k < f->trees.size()) ? f->trees[k].get() : nullptr; }
+
+// descriptors for one query index across all layers (fri_commit.rs:145-163)
+static size_t fri_query_descs(const stark_fri* f, size_t index, size_t out_off, std::vector<OpenDesc>& d) {
+    for (auto& tp : f->trees) {
+        const stark_tree* t = tp.get();
+        size_t len = t->shape.n;
+        size_t idx = index % len, sib = (idx + len / 2) % len;              // :152-153
+        for (size_t which : {idx, sib}) {
+            d.push_back(OpenDesc{t->leaves->as<uint32_t>(), t->nodes.as<uint32_t>(), len, which, out_off});
+            out_off += 8 + merkle_path_len(len, which);
+        }
+    }
+    return out_off;
+}
+extern "C" int stark_fri_open(const stark_fri* f, const uint64_t* indices, size_t n_idx, uint8_t* out, size_t cap, size_t* len) {
+    API_BEGIN
+    STARK_REQUIRE(f && len && (indices || n_idx == 0), "fri_open: null argument");
+    std::vector<OpenDesc> d;
+    d.reserve(n_idx * f->trees.size() * 2);
+    size_t total = 0;
+    for (size_t q = 0; q < n_idx; q++) total = fri_query_descs(f, (size_t)indices[q], total, d);
+    *len = total;
+    if (!out) return ST_OK;
+    STARK_REQUIRE(cap >= total, "fri_open: buffer too small");
+    CtxGuard g(f->ctx);
+    open_records(f->ctx, d, total, out);
+    API_END
+}
+extern "C" void stark_fri_destroy(stark_fri* f) {
+    if (!f) return;
+    cudaSetDevice(f->ctx->device);
+    delete f;
+}
+
+// ---- whole-loop API with the library's Channel ----
+static void send_root(Channel& ch, const stark_tree* t) {
+    uint8_t r[32]; words_to_bytes(t->root_words, r);
+    std::string h = HostSha256::hex(r, 32);
+    ch.send(reinterpret_cast<const uint8_t*>(h.data()), 64);    // root().as_bytes(): 64 ASCII hex chars (fri_verify.rs:24-25)
+}
+static int fri_commit_loop(stark_fri* f, stark_channel* chan) {
+    Channel& ch = chan->ch;
+    send_root(ch, f->trees[0].get());                                        // fri_commit.rs:86
+    while ((long long)f->coeff_len - 1 >= 1) {                               // :89
+        uint64_t beta;
+        STARK_REQUIRE(ch.receive_random_field_element(&beta), "channel: receive before send");   // :91
+        int rc = stark_fri_fold(f, beta, nullptr);                           // :94-97
+        if (rc != ST_OK) return rc;
+        send_root(ch, f->trees.back().get());                                // :100
+    }
+    uint64_t fv; size_t fl;
+    int rc = stark_fri_final(f, &fv, &fl);
+    if (rc != ST_OK) return rc;
+    uint8_t b[8]; be8(fv, b);
+    ch.send(b, 8);                                                           // :114
+    return ST_OK;
+}
+extern "C" int stark_fri_commit(stark_ctx* ctx, const uint64_t* coeffs, size_t n_coeffs, unsigned log_n, uint64_t offset,
+                                stark_channel* ch, stark_fri** out) {
+    STARK_API_GUARD_NULL(ctx && ch && out);
+    int rc = stark_fri_begin(ctx, coeffs, n_coeffs, log_n, offset, out, nullptr);
+    if (rc != ST_OK) return rc;
+    API_BEGIN
+    rc = fri_commit_loop(*out, ch);
+    if (rc != ST_OK) { stark_fri_destroy(*out); *out = nullptr; return rc; }
+    API_END
+}
+extern "C" int stark_fri_commit_dev(stark_ctx* ctx, const stark_vec* coeffs, unsigned log_n, uint64_t offset,
+                                    stark_channel* ch, stark_fri** out) {
+    STARK_API_GUARD_NULL(ctx && ch && out && coeffs);
+    int rc = stark_fri_begin_dev(ctx, coeffs, log_n, offset, out, nullptr);
+    if (rc != ST_OK) return rc;
+    API_BEGIN
+    rc = fri_commit_loop(*out, ch);
+    if (rc != ST_OK) { stark_fri_destroy(*out); *out = nullptr; return rc; }
+    API_END
+}
+// feeds one query's records to the channel in the reference's order (fri_commit.rs:145-163)
+static void send_query_records(const stark_fri* f, const uint8_t* rec, Channel& ch, size_t index) {
+    size_t off = 0;
+    for (auto& tp : f->trees) {
+        size_t len = tp->shape.n;
+        size_t idx = index % len, sib = (idx + len / 2) % len;
+        if (len == 1) ch.send(rec + off, 8);                                 // :147-149 (then falls through, as written)
+        for (size_t which : {idx, sib}) {
+            size_t pl = merkle_path_len(len, which);
+            ch.send(rec + off, 8);                                           // :156 / :161
+            ch.send(rec + off + 8, pl);                                      // :157-158 / :162-163
+            off += 8 + pl;
+        }
+    }
+}
+extern "C" int stark_decommit_fri_layers(const stark_fri* f, size_t index, stark_channel* ch) {
+    API_BEGIN
+    STARK_REQUIRE(f && ch, "decommit_fri_layers: null argument");
+    std::vector<OpenDesc> d;
+    size_t total = fri_query_descs(f, index, 0, d);
+    std::vector<uint8_t> rec(total);
+    { CtxGuard g(f->ctx); open_records(f->ctx, d, total, rec.data()); }
+    send_query_records(f, rec.data(), ch->ch, index);
+    API_END
+}
+extern "C" int stark_decommit_fri(const stark_fri* f, size_t num_queries, size_t max_index, stark_channel* ch) {
+    API_BEGIN
+    STARK_REQUIRE(f && ch, "decommit_fri: null argument");
+    for (size_t q = 0; q < num_queries; q++) {                               // :175-178
+        uint64_t idx;
+        STARK_REQUIRE(ch->ch.receive_random_int(0, max_index, true, &idx), "channel: receive before send");
+        int rc = stark_decommit_fri_layers(f, (size_t)idx, ch);
+        if (rc != ST_OK) return rc;
+    }
+    API_END
+}
+
+// ======================================================================================= shared with stark101.cu
+namespace starkb200 {
+DevBufPtr api_upload_u64(stark_ctx* ctx, const uint64_t* host, size_t n) { return upload_u64(ctx, host, n); }
+DevBufPtr api_lde_on_coset(stark_ctx* ctx, const uint32_t* evals, unsigned log_n, uint64_t offset_in, unsigned log_blowup, uint64_t offset_out) {
+    return lde_on_coset(ctx, evals, log_n, offset_in, log_blowup, offset_out);
+}
+DevBufPtr api_interpolate_on_coset(stark_ctx* ctx, const uint32_t* evals, unsigned log_n, uint64_t offset) {
+    return interpolate_on_coset(ctx, evals, log_n, offset);
+}
+std::unique_ptr<stark_tree> api_tree_commit(stark_ctx* ctx, DevBufPtr leaves, size_t n) { return tree_commit(ctx, std::move(leaves), n); }
+void api_send_root(Channel& ch, const stark_tree* t) { send_root(ch, t); }
+void api_open_and_send(const stark_tree* t, size_t idx, Channel& ch) {
+    STARK_REQUIRE(idx < t->shape.n, "open: leaf index out of range");
+    size_t pl = merkle_path_len(t->shape.n, idx);
+    std::vector<OpenDesc> d(1);
+    d[0] = OpenDesc{t->leaves->as<uint32_t>(), t->nodes.as<uint32_t>(), t->shape.n, idx, 0};
+    std::vector<uint8_t> rec(8 + pl);
+    open_records(t->ctx, d, rec.size(), rec.data());
+    ch.send(rec.data(), 8);
+    ch.send(rec.data() + 8, pl);
+}
+void api_set_error(const std::string& s) { set_error(s); }
+}  // namespace starkb200

@@ -1,0 +1,108 @@
+// common.hpp — context, device buffers and error plumbing shared by the C-ABI and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "field.cuh"
+
+namespace starkb200 {
+
+enum : int { ST_OK = 0, ST_INVALID = 1, ST_CUDA = 2, ST_UNSUPPORTED = 3, ST_INTERNAL = 4 };
+
+struct StarkError : std::runtime_error {
+    int code;
+    StarkError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define STARK_CUDA(expr)                                                                              \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess)                                                                        \
+            throw ::starkb200::StarkError(::starkb200::ST_CUDA, std::string(#expr) + ": " +           \
+                                                                    cudaGetErrorString(_e));          \
+    } while (0)
+
+#define STARK_REQUIRE(cond, msg)                                                                      \
+    do {                                                                                              \
+        if (!(cond)) throw ::starkb200::StarkError(::starkb200::ST_INVALID, msg);                     \
+    } while (0)
+
+// Stream-ordered device allocation (cudaMallocAsync pool: steady-state allocations cost ~1 us).
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf() = default;
+    DevBuf(size_t b, cudaStream_t s) : bytes(b), stream(s) {
+        if (b) STARK_CUDA(cudaMallocAsync(&p, b, s));
+    }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes), stream(o.stream) { o.p = nullptr; o.bytes = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; bytes = o.bytes; stream = o.stream; o.p = nullptr; o.bytes = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFreeAsync(p, stream);
+        p = nullptr; bytes = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+using DevBufPtr = std::shared_ptr<DevBuf>;
+inline DevBufPtr make_buf(size_t bytes, cudaStream_t s) { return std::make_shared<DevBuf>(bytes, s); }
+
+// Two-level twiddle tables for one transform size: w^e = lo[e & mask] * hi[e >> shift].
+struct TwiddleSet {
+    DevBuf fwd_lo, fwd_hi, inv_lo, inv_hi;
+    uint32_t shift = 0, mask = 0;
+    PowTable fwd() const { return PowTable{fwd_lo.as<uint32_t>(), fwd_hi.as<uint32_t>(), shift, mask}; }
+    PowTable inv() const { return PowTable{inv_lo.as<uint32_t>(), inv_hi.as<uint32_t>(), shift, mask}; }
+};
+
+// What the host reads after each commit without issuing a copy (mapped pinned memory).
+struct HostResult {
+    uint32_t root[8];
+    int32_t degree_plus1;
+    uint32_t flag;
+};
+
+// ---- host-side modular helpers (u128; setup only, never on the data path) ----
+inline uint64_t h_mul(uint64_t a, uint64_t b, uint64_t m) { return (uint64_t)((unsigned __int128)a * b % m); }
+inline uint64_t h_pow(uint64_t a, uint64_t e, uint64_t m) {
+    uint64_t r = 1 % m; a %= m;
+    while (e) { if (e & 1) r = h_mul(r, a, m); a = h_mul(a, a, m); e >>= 1; }
+    return r;
+}
+inline uint64_t h_inv(uint64_t a, uint64_t m) { return h_pow(a, m - 2, m); }
+
+}  // namespace starkb200
+
+// The opaque C-ABI context (one per device x modulus).
+struct stark_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t modulus = 0, generator = 0;
+    unsigned two_adicity = 0;       // largest k with 2^k | p-1
+    unsigned small_log = 0;         // size (log2) of the in-tile twiddle table
+    starkb200::FieldParams fp{};
+    std::recursive_mutex mu;
+    starkb200::DevBuf small_fwd, small_inv;    // w_{2^small_log}^k, k < 2^(small_log-1), Montgomery form
+    std::map<unsigned, std::unique_ptr<starkb200::TwiddleSet>> tw;
+    starkb200::HostResult* h_result = nullptr;  // pinned + mapped
+    starkb200::HostResult* d_result = nullptr;  // device alias of h_result
+    int sm_count = 148;
+    unsigned long long launches = 0;            // kernels launched through this context
+
+    uint32_t to_mont(uint64_t a) const { return (uint32_t)starkb200::h_mul(a % modulus, (uint64_t)1 << 32, modulus); }
+    uint64_t root_of_unity(unsigned log_n) const { return starkb200::h_pow(generator, (modulus - 1) >> log_n, modulus); }
+    const starkb200::TwiddleSet& twiddles(unsigned log_n);
+};

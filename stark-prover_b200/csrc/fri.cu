@@ -1,0 +1,177 @@
+// fri.cu — element-wise field kernels around the NTT and Merkle kernels (HBM bound):
+// u64<->u32 boundary conversion, FRI folds in evaluation and coefficient space, zero-safe batched
+// inverse (Montgomery trick), point-wise products, coset domain generation.
+//
+// Reference semantics restated here:
+//   fold          src/fri/fri_commit.rs:32-50 (even + beta*odd), evaluated on the squared half
+//                 domain (:18-24, :60-63) — done in evaluation space:
+//                 e'[i] = (e[i]+e[i+n/2])/2 + beta*(e[i]-e[i+n/2])/(2*D[i]),  D[i] = offset*w^i
+//   degree        src/polynomial/ops.rs:19-37 (trailing zeros trimmed) drives `while poly.degree >= 1`
+//                 (fri_commit.rs:89), so the exact degree of the folded polynomial is tracked
+//   inverse       src/fields/element.rs:54-57: a^(p-2), hence inverse(0) == 0
+#include "kernels.hpp"
+
+namespace starkb200 {
+
+// ---------------- boundary conversions ----------------
+__global__ void narrow_kernel(const uint64_t* in, uint32_t* out, size_t n, uint32_t p) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t v = in[i];
+    out[i] = v < p ? (uint32_t)v : (uint32_t)(v % p);     // FieldElement::new: value % MODULUS (element.rs:13-17)
+}
+__global__ void widen_kernel(const uint32_t* in, uint64_t* out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+void narrow_u64(stark_ctx* ctx, const uint64_t* in, uint32_t* out, size_t n) {
+    if (!n) return;
+    narrow_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(in, out, n, ctx->fp.p);
+    ctx->launches++;
+    STARK_CUDA(cudaGetLastError());
+}
+void widen_u32(stark_ctx* ctx, const uint32_t* in, uint64_t* out, size_t n) {
+    if (!n) return;
+    widen_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(in, out, n);
+    ctx->launches++;
+    STARK_CUDA(cudaGetLastError());
+}
+void fill_zero(stark_ctx* ctx, uint32_t* p, size_t n) {
+    if (n) STARK_CUDA(cudaMemsetAsync(p, 0, n * sizeof(uint32_t), ctx->stream));
+}
+
+// ---------------- coefficient-space fold + exact degree ----------------
+struct DegScratch { int maxv; unsigned ticket; };
+__device__ DegScratch g_deg_scratch;    // zero-initialised; the last block of every launch resets it
+
+template <bool FOLD>
+__global__ void coeff_fold_kernel(const uint32_t* c, size_t len, uint32_t beta_m, uint32_t* out, size_t out_len,
+                                  HostResult* result, FieldParams fp) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int mine = 0;
+    if (j < out_len) {
+        uint32_t v;
+        if (FOLD) {
+            uint32_t e = c[2 * j];
+            uint32_t o = (2 * j + 1 < len) ? mont_mul(c[2 * j + 1], beta_m, fp) : 0u;
+            v = fadd(o, e, fp);
+            out[j] = v;
+        } else {
+            v = c[j];
+        }
+        if (v != 0) mine = (int)(j + 1);
+    }
+    // block max -> global max -> last block publishes
+    __shared__ int smax;
+    if (threadIdx.x == 0) smax = 0;
+    __syncthreads();
+    mine = max(mine, __shfl_xor_sync(0xffffffffu, mine, 16));
+    mine = max(mine, __shfl_xor_sync(0xffffffffu, mine, 8));
+    mine = max(mine, __shfl_xor_sync(0xffffffffu, mine, 4));
+    mine = max(mine, __shfl_xor_sync(0xffffffffu, mine, 2));
+    mine = max(mine, __shfl_xor_sync(0xffffffffu, mine, 1));
+    if ((threadIdx.x & 31) == 0 && mine) atomicMax(&smax, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (smax) atomicMax(&g_deg_scratch.maxv, smax);
+        __threadfence();
+        unsigned t = atomicAdd(&g_deg_scratch.ticket, 1u);
+        if (t == gridDim.x - 1) {
+            __threadfence();
+            result->degree_plus1 = atomicExch(&g_deg_scratch.maxv, 0);
+            g_deg_scratch.ticket = 0;
+        }
+    }
+}
+void coeff_fold(stark_ctx* ctx, const uint32_t* c, size_t len, uint32_t beta_m, uint32_t* out, HostResult* result) {
+    size_t out_len = (len + 1) / 2;
+    if (out_len == 0) { throw StarkError(ST_INTERNAL, "coeff_fold: empty polynomial"); }
+    coeff_fold_kernel<true><<<(unsigned)((out_len + 255) / 256), 256, 0, ctx->stream>>>(c, len, beta_m, out, out_len, result, ctx->fp);
+    ctx->launches++;
+    STARK_CUDA(cudaGetLastError());
+}
+void poly_degree(stark_ctx* ctx, const uint32_t* c, size_t len, HostResult* result) {
+    STARK_REQUIRE(len > 0, "poly_degree: empty");
+    coeff_fold_kernel<false><<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>(c, len, 0, nullptr, len, result, ctx->fp);
+    ctx->launches++;
+    STARK_CUDA(cudaGetLastError());
+}
+
+// ---------------- zero-safe batched inverse (Montgomery trick), optional numerator ----------------
+constexpr int INV_K = 8;
+constexpr int INV_THREADS = 256;
+__global__ void __launch_bounds__(INV_THREADS)
+batch_inverse_kernel(const uint32_t* a, const uint32_t* num, uint32_t* out, size_t n, FieldParams fp) {
+    const size_t base = (size_t)blockIdx.x * (INV_THREADS * INV_K) + threadIdx.x;
+    uint32_t x[INV_K], pre[INV_K];
+    uint32_t acc = fp.one;
+#pragma unroll
+    for (int j = 0; j < INV_K; j++) {
+        size_t i = base + (size_t)j * INV_THREADS;
+        uint32_t v = i < n ? a[i] : 0u;
+        x[j] = v ? to_mont(v, fp) : 0u;          // 0 marks "skip": zero (or out of range) contributes a factor 1
+        pre[j] = acc;
+        if (v) acc = mont_mul(acc, x[j], fp);
+    }
+    uint32_t inv = mont_inv(acc, fp);            // one Fermat exponentiation per INV_K elements
+#pragma unroll
+    for (int j = INV_K - 1; j >= 0; j--) {
+        size_t i = base + (size_t)j * INV_THREADS;
+        if (i >= n) continue;
+        uint32_t r = 0;
+        if (x[j]) {
+            uint32_t r_m = mont_mul(inv, pre[j], fp);
+            inv = mont_mul(inv, x[j], fp);
+            r = num ? mont_mul(r_m, num[i], fp) : from_mont(r_m, fp);
+        }
+        out[i] = r;
+    }
+}
+void batch_inverse(stark_ctx* ctx, const uint32_t* a, const uint32_t* num, uint32_t* out, size_t n) {
+    if (!n) return;
+    size_t per = (size_t)INV_THREADS * INV_K;
+    batch_inverse_kernel<<<(unsigned)((n + per - 1) / per), INV_THREADS, 0, ctx->stream>>>(a, num, out, n, ctx->fp);
+    ctx->launches++;
+    STARK_CUDA(cudaGetLastError());
+}
+
+__global__ void pointwise_mul_kernel(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, FieldParams fp) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = mont_mul(to_mont(a[i], fp), b[i], fp);
+}
+void pointwise_mul(stark_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
+    if (!n) return;
+    pointwise_mul_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(a, b, out, n, ctx->fp);
+    ctx->launches++;
+    STARK_CUDA(cudaGetLastError());
+}
+
+// ---------------- coset domain D[i] = offset * w^i (coset_fri.rs:32-36) ----------------
+__global__ void coset_domain_kernel(uint32_t offset, PowTable tw, uint32_t* out, size_t n, FieldParams fp) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = mont_mul(pow_lookup(tw, (uint32_t)i, fp), offset, fp);
+}
+void coset_domain(stark_ctx* ctx, uint64_t offset, unsigned log_n, uint32_t* out) {
+    const TwiddleSet& tws = ctx->twiddles(log_n);
+    size_t n = (size_t)1 << log_n;
+    coset_domain_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((uint32_t)(offset % ctx->modulus), tws.fwd(), out, n, ctx->fp);
+    ctx->launches++;
+    STARK_CUDA(cudaGetLastError());
+}
+
+// ---------------- plain evaluation-space fold (the fused version lives in merkle.cu) ----------------
+__global__ void fri_fold_kernel(LeafSource src, FieldParams fp) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= src.half) return;
+    uint32_t a = src.prev[i], b = src.prev[i + src.half];
+    uint32_t s = mont_mul(pow_lookup(src.winv, (uint32_t)i, fp), src.sb_m, fp);
+    src.fold_out[i] = fadd(mont_mul(fadd(a, b, fp), src.inv2_m, fp), mont_mul(fsub(a, b, fp), s, fp), fp);
+}
+void fri_fold(stark_ctx* ctx, const LeafSource& src) {
+    if (!src.half) return;
+    fri_fold_kernel<<<(unsigned)((src.half + 255) / 256), 256, 0, ctx->stream>>>(src, ctx->fp);
+    ctx->launches++;
+    STARK_CUDA(cudaGetLastError());
+}
+
+}  // namespace starkb200

@@ -1,0 +1,39 @@
+// handles.hpp — the opaque objects behind the C ABI.
+#pragma once
+#include "host_channel.hpp"
+#include "kernels.hpp"
+
+struct stark_vec {
+    stark_ctx* ctx = nullptr;
+    starkb200::DevBufPtr buf;        // n canonical u32 values
+    size_t n = 0;
+};
+
+// MerkleTree<M> (reference src/merkle/mod.rs:5-7): the leaf values it was built over (shared with the
+// FRI layer or vector that owns them) plus levels 1..depth of digests.
+struct stark_tree {
+    stark_ctx* ctx = nullptr;
+    starkb200::DevBufPtr leaves;
+    starkb200::TreeShape shape;
+    starkb200::DevBuf nodes;
+    uint32_t root_words[8] = {0};
+};
+
+// FRIProof (reference src/fri/fri_commit.rs:9-13): trees[k]->leaves are fri_layers[k], trees[k] is
+// fri_merkles[k]; `coeffs` tracks the folded polynomial so that its exact degree and the final
+// constant are the reference's.
+struct stark_fri {
+    stark_ctx* ctx = nullptr;
+    unsigned log_n = 0;
+    uint64_t offset0 = 1;
+    unsigned cur_log = 0;
+    uint64_t cur_offset = 1;
+    starkb200::DevBufPtr coeffs;
+    size_t coeff_len = 0;            // degree + 1 (0 = zero polynomial)
+    std::vector<std::unique_ptr<stark_tree>> trees;
+};
+
+struct stark_channel {
+    starkb200::Channel ch;
+    explicit stark_channel(uint64_t m) : ch(m) {}
+};

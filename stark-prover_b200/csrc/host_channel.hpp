@@ -1,0 +1,124 @@
+// host_channel.hpp — the Fiat-Shamir transcript, host side (it is sequential string hashing; it stays on
+// the CPU exactly as in the reference, src/channel/channel.rs:14-95).  Product code: this is the
+// library's own Channel, not the test oracle.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+namespace starkb200 {
+
+// FIPS 180-4 SHA-256 (what sha256 1.5.0 `digest` computes for the transcript strings).
+class HostSha256 {
+  public:
+    static void digest(const uint8_t* msg, size_t len, uint8_t out[32]) {
+        uint32_t st[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+        size_t off = 0;
+        for (; off + 64 <= len; off += 64) block(st, msg + off);
+        uint8_t tail[128];
+        size_t r = len - off;
+        memset(tail, 0, sizeof tail);
+        memcpy(tail, msg + off, r);
+        tail[r] = 0x80;
+        size_t tl = (r + 9 <= 64) ? 64 : 128;
+        uint64_t bits = (uint64_t)len * 8;
+        for (int i = 0; i < 8; i++) tail[tl - 1 - i] = (uint8_t)(bits >> (8 * i));
+        block(st, tail);
+        if (tl == 128) block(st, tail + 64);
+        for (int i = 0; i < 8; i++) {
+            out[4 * i] = (uint8_t)(st[i] >> 24); out[4 * i + 1] = (uint8_t)(st[i] >> 16);
+            out[4 * i + 2] = (uint8_t)(st[i] >> 8); out[4 * i + 3] = (uint8_t)st[i];
+        }
+    }
+    static std::string hex(const uint8_t* b, size_t n) {       // lowercase, like const-hex / rs_merkle root_hex
+        static const char* d = "0123456789abcdef";
+        std::string s(2 * n, '0');
+        for (size_t i = 0; i < n; i++) { s[2 * i] = d[b[i] >> 4]; s[2 * i + 1] = d[b[i] & 15]; }
+        return s;
+    }
+    static std::string hex_digest(const std::string& s) {
+        uint8_t dg[32];
+        digest(reinterpret_cast<const uint8_t*>(s.data()), s.size(), dg);
+        return hex(dg, 32);
+    }
+
+  private:
+    static uint32_t ror(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+    static void block(uint32_t st[8], const uint8_t* p) {
+        static const uint32_t K[64] = {
+            0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
+            0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
+            0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
+            0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
+            0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+            0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
+            0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
+            0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+        uint32_t w[64];
+        for (int i = 0; i < 16; i++)
+            w[i] = ((uint32_t)p[4 * i] << 24) | ((uint32_t)p[4 * i + 1] << 16) | ((uint32_t)p[4 * i + 2] << 8) | p[4 * i + 3];
+        for (int i = 16; i < 64; i++) {
+            uint32_t s0 = ror(w[i - 15], 7) ^ ror(w[i - 15], 18) ^ (w[i - 15] >> 3);
+            uint32_t s1 = ror(w[i - 2], 17) ^ ror(w[i - 2], 19) ^ (w[i - 2] >> 10);
+            w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+        }
+        uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+        for (int i = 0; i < 64; i++) {
+            uint32_t t1 = h + (ror(e, 6) ^ ror(e, 11) ^ ror(e, 25)) + ((e & f) ^ (~e & g)) + K[i] + w[i];
+            uint32_t t2 = (ror(a, 2) ^ ror(a, 13) ^ ror(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+            h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        }
+        st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+    }
+};
+
+inline void be8(uint64_t v, uint8_t out[8]) {            // FieldElement::to_bytes, element.rs:59-61
+    for (int i = 0; i < 8; i++) out[i] = (uint8_t)(v >> (56 - 8 * i));
+}
+
+// Channel<MODULUS> — channel.rs:14-95, field for field.
+struct Channel {
+    std::vector<std::vector<uint8_t>> proof;              // :16
+    std::vector<std::vector<uint8_t>> compressed_proof;   // :17
+    std::string state;                                     // :19, "" initially (:24-30)
+    uint64_t modulus;
+
+    explicit Channel(uint64_t m) : modulus(m) {}
+
+    void send(const uint8_t* msg, size_t len) {            // :35-44
+        state = HostSha256::hex_digest(state + HostSha256::hex(msg, len));
+        proof.emplace_back(msg, msg + len);
+        compressed_proof.emplace_back(msg, msg + len);
+    }
+    // :58-84.  Returns false where the reference would panic ("Channel state is not valid hex" on "").
+    bool receive_random_int(uint64_t min, uint64_t max, bool show_in_proof, uint64_t* out) {
+        if (state.empty() || max < min) return false;
+        const uint64_t range = (max - min) + 1;           // :68
+        if (range == 0) return false;                     // usize overflow in the reference
+        // (U256::from_str_radix(state,16) + min) % range  (:72), digit by digit
+        unsigned __int128 acc = 0;
+        for (char ch : state) {
+            unsigned d = (ch >= '0' && ch <= '9') ? (unsigned)(ch - '0') : (unsigned)(ch - 'a' + 10);
+            acc = (acc * 16 + d) % range;
+        }
+        uint64_t num = (uint64_t)((acc + (unsigned __int128)(min % range)) % range);
+        state = HostSha256::hex_digest(state);            // :75-76
+        if (show_in_proof) { uint8_t b[8]; be8(num, b); proof.emplace_back(b, b + 8); }   // :78-80
+        *out = num;                                        // :83
+        return true;
+    }
+    bool receive_random_field_element(uint64_t* out) {     // :47-55
+        uint64_t num;
+        if (!receive_random_int(0, modulus - 1, false, &num)) return false;
+        uint8_t b[8]; be8(num, b);
+        proof.emplace_back(b, b + 8);
+        *out = num % modulus;
+        return true;
+    }
+    size_t proof_size() const { size_t s = 0; for (auto& m : proof) s += m.size(); return s; }                       // :88-90
+    size_t compressed_proof_size() const { size_t s = 0; for (auto& m : compressed_proof) s += m.size(); return s; } // :93-95
+};
+
+}  // namespace starkb200

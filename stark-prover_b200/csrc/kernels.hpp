@@ -1,0 +1,89 @@
+// kernels.hpp — host-callable launchers for the CUDA kernels (implemented in the *.cu files).
+#pragma once
+#include "common.hpp"
+
+namespace starkb200 {
+
+// ---------------- Merkle (merkle.cu) ----------------
+struct TreeShape {
+    size_t n = 0;                      // leaves
+    unsigned depth = 0;                // levels above the leaves
+    std::vector<size_t> len;           // len[l], l = 0..depth   (len[0] = n)
+    std::vector<size_t> off;           // digest offset of level l (l >= 1) inside the node buffer
+    size_t total = 0;                  // digests in the node buffer (levels 1..depth, +1 slot when depth == 0)
+    static TreeShape make(size_t n);
+};
+
+// Source of the leaf VALUES of a tree: either an existing layer, or the FRI fold of the previous layer
+// computed on the fly (and written to `fold_out`) — the fused fold-and-hash of fri_commit.rs:94-97.
+struct LeafSource {
+    const uint32_t* vals = nullptr;    // plain: leaf values
+    // fold: e'[i] = (a+b)/2 + s_i (a-b),  a = prev[i], b = prev[i+half], s_i = beta/(2*offset) * w^-i
+    const uint32_t* prev = nullptr;
+    uint32_t* fold_out = nullptr;
+    size_t half = 0;
+    uint32_t inv2_m = 0;               // 1/2, Montgomery form
+    uint32_t sb_m = 0;                 // beta/(2*offset), Montgomery form
+    PowTable winv{};                   // w^-i for this layer's size
+};
+
+// Builds levels 1..depth into `nodes` (TreeShape layout); when `result` is non-null the root's 8 state
+// words are also written there (mapped host memory).  Leaf digests are not stored.
+void merkle_build(stark_ctx* ctx, const LeafSource& src, const TreeShape& shape, uint32_t* nodes,
+                  HostResult* result);
+
+// One authentication path / element read per descriptor; see merkle.cu.
+struct OpenDesc {
+    const uint32_t* vals;      // leaf values of the tree
+    const uint32_t* nodes;     // node buffer (levels 1..depth)
+    unsigned long long n;      // leaves
+    unsigned long long idx;    // leaf index
+    unsigned long long out_off;// byte offset of this record in the output: BE8(value) || path bytes
+};
+void merkle_open(stark_ctx* ctx, const OpenDesc* d_desc, size_t n_desc, uint8_t* d_out);
+// host-side: bytes of the path of leaf idx in a tree of n leaves (32 per level that has a sibling)
+size_t merkle_path_len(size_t n, size_t idx);
+
+// ---------------- NTT (ntt.cu) ----------------
+// forward (or inverse-root) decimation-in-time: bit-reversed input -> natural output, in `data`.
+//   log_pad > 0: the bit-reversed input is the size-2^(log_n-log_pad) array `src`, zero-padded
+//   (position q*2^log_pad holds src[q]), and src[q] is first multiplied by scale(bitrev(q)).
+void ntt_dit(stark_ctx* ctx, const uint32_t* src, uint32_t* data, unsigned log_n, unsigned log_pad,
+             const PowTable* scale, bool inverse_root);
+// decimation-in-frequency: natural input -> bit-reversed output, in place.
+void ntt_dif(stark_ctx* ctx, uint32_t* data, unsigned log_n, bool inverse_root);
+// out[i] = in[bitrev(i)] * scale(scale_on_input_index ? bitrev(i) : i)   (scale optional)
+void bitrev_permute(stark_ctx* ctx, const uint32_t* in, uint32_t* out, unsigned log_n, const PowTable* scale,
+                    bool scale_by_input_index);
+// lo[j] = base^j (j < 2^shift), hi[j] = c0 * base^(j << shift); Montgomery form
+struct ScaleTable {
+    DevBuf lo, hi;
+    PowTable view{};
+};
+void build_scale_table(stark_ctx* ctx, uint64_t base, uint64_t c0, unsigned log_n, ScaleTable& out);
+
+// ---------------- element-wise / FRI helpers (fri.cu) ----------------
+void narrow_u64(stark_ctx* ctx, const uint64_t* in, uint32_t* out, size_t n);      // v % p  (FieldElement::new)
+void widen_u32(stark_ctx* ctx, const uint32_t* in, uint64_t* out, size_t n);
+void fill_zero(stark_ctx* ctx, uint32_t* p, size_t n);
+// c'[j] = c[2j] + beta*c[2j+1]; result->degree_plus1 = 1 + max{j : c'[j] != 0} (0 for the zero poly)
+void coeff_fold(stark_ctx* ctx, const uint32_t* c, size_t len, uint32_t beta_m, uint32_t* out, HostResult* result);
+void poly_degree(stark_ctx* ctx, const uint32_t* c, size_t len, HostResult* result);
+// a[i] <- a[i]^-1 (0 stays 0); if num != null: out[i] = num[i] * a[i]^-1
+void batch_inverse(stark_ctx* ctx, const uint32_t* a, const uint32_t* num, uint32_t* out, size_t n);
+void pointwise_mul(stark_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n);
+// out[i] = offset * w^i
+void coset_domain(stark_ctx* ctx, uint64_t offset, unsigned log_n, uint32_t* out);
+// plain (unfused) evaluation-space fold of one layer
+void fri_fold(stark_ctx* ctx, const LeafSource& src);
+
+// STARK-101 FibonacciSq composition on the LDE coset (build-defined)
+struct FibSqParams {
+    unsigned log_trace, log_blowup;
+    uint64_t offset;             // coset offset w
+    uint64_t alpha[3];
+    uint64_t last_value;         // a[T-2]
+};
+void fibsq_composition(stark_ctx* ctx, const uint32_t* f_eval, const FibSqParams& prm, uint32_t* cp_eval);
+
+}  // namespace starkb200

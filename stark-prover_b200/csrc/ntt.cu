@@ -1,0 +1,364 @@
+// ntt.cu — Cooley-Tukey NTT / iNTT passes in F_p (p < 2^32, Montgomery multiplication on the integer
+// pipes; no tensor cores — a butterfly network is not a dense contraction).
+//
+// Replaces the reference's per-point Horner evaluation over a domain (src/polynomial/ops.rs:76-83 mapped
+// at src/fri/fri_commit.rs:78) and its Lagrange interpolation (src/polynomial/interpolation.rs:121-152):
+// on a power-of-two coset both are an NTT, and canonical results are unique, hence bit-identical.
+//
+// Structure.  A size-2^log_n transform is split into passes of <= 9 bits.  Each pass stages a tile of
+// 2^r points x 32 columns in shared memory (33-word rows: conflict-free for both the coalesced global
+// side and the butterfly side), runs the r stages as register-resident radix-8/16 groups, applies one
+// inter-pass twiddle per element (two-level table, 2 loads + 1 multiply) and writes the tile back to the
+// addresses it came from.  Decimation-in-time consumes bit-reversed input and produces natural order;
+// decimation-in-frequency is its mirror.  The LDE chain  iNTT(DIF) -> coset scale -> NTT(DIT)  therefore
+// needs no permutation at all; natural->natural entry points add one bit-reversal gather.
+#include "kernels.hpp"
+
+namespace starkb200 {
+
+constexpr int NTT_C = 32;
+constexpr int NTT_TS = NTT_C + 1;
+
+struct NttPass {
+    const uint32_t* src;
+    uint32_t* dst;
+    unsigned log_n;
+    unsigned lo;          // lowest bit of this pass (0: contiguous tile)
+    unsigned ncols;       // valid columns per tile
+    unsigned log_pad;     // DIT/contiguous only: input is zero-padded by 2^log_pad
+    unsigned log_m;       // log_n - log_pad
+    int has_scale;
+    PowTable scale;
+    PowTable tw;
+    const uint32_t* small;
+    unsigned small_log;
+};
+
+template <int G, bool DIF>
+__device__ __forceinline__ void butterfly_group(uint32_t* col, const int s, const int base, const uint32_t* tws,
+                                                const int r_log, const FieldParams& fp) {
+    uint32_t x[1 << G];
+#pragma unroll
+    for (int j = 0; j < (1 << G); j++) x[j] = col[(base + (j << s)) * NTT_TS];
+    const int bl = base & ((1 << s) - 1);
+#pragma unroll
+    for (int uu = 0; uu < G; uu++) {
+        const int u = DIF ? (G - 1 - uu) : uu;
+        const int level = s + u + 1;                 // butterflies of span 2^(s+u) use w_{2^level}
+#pragma unroll
+        for (int jj = 0; jj < (1 << G); jj++) {
+            if (jj & (1 << u)) continue;
+            const int k = bl + ((jj & ((1 << u) - 1)) << s);
+            const uint32_t w = tws[k << (r_log - level)];
+            if (DIF) {
+                uint32_t a = x[jj], b = x[jj + (1 << u)];
+                x[jj] = fadd(a, b, fp);
+                x[jj + (1 << u)] = mont_mul(fsub(a, b, fp), w, fp);
+            } else {
+                uint32_t a = x[jj], b = mont_mul(x[jj + (1 << u)], w, fp);
+                x[jj] = fadd(a, b, fp);
+                x[jj + (1 << u)] = fsub(a, b, fp);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < (1 << G); j++) col[(base + (j << s)) * NTT_TS] = x[j];
+}
+
+template <int R_LOG, int G, bool DIF>
+__device__ __forceinline__ void run_round(uint32_t* tile, const int s, const uint32_t* tws, const FieldParams& fp,
+                                          const unsigned ncols) {
+    constexpr int items = ((1 << R_LOG) >> G) * NTT_C;
+    for (int w = threadIdx.x; w < items; w += blockDim.x) {
+        const int c = w % NTT_C, bi = w / NTT_C;
+        if ((unsigned)c >= ncols) continue;
+        const int base = ((bi >> s) << (s + G)) | (bi & ((1 << s) - 1));
+        butterfly_group<G, DIF>(tile + c, s, base, tws, R_LOG, fp);
+    }
+    __syncthreads();
+}
+
+template <int R_LOG, bool DIF>
+__device__ __forceinline__ void run_rounds(uint32_t* tile, const uint32_t* tws, const FieldParams& fp, unsigned ncols) {
+    // stage groups (sum = R_LOG); DIT walks spans upward, DIF downward
+    if constexpr (R_LOG <= 4) {
+        run_round<R_LOG, R_LOG, DIF>(tile, 0, tws, fp, ncols);
+    } else if constexpr (R_LOG == 5) {
+        if (!DIF) { run_round<5, 3, DIF>(tile, 0, tws, fp, ncols); run_round<5, 2, DIF>(tile, 3, tws, fp, ncols); }
+        else      { run_round<5, 2, DIF>(tile, 3, tws, fp, ncols); run_round<5, 3, DIF>(tile, 0, tws, fp, ncols); }
+    } else if constexpr (R_LOG == 6) {
+        if (!DIF) { run_round<6, 3, DIF>(tile, 0, tws, fp, ncols); run_round<6, 3, DIF>(tile, 3, tws, fp, ncols); }
+        else      { run_round<6, 3, DIF>(tile, 3, tws, fp, ncols); run_round<6, 3, DIF>(tile, 0, tws, fp, ncols); }
+    } else if constexpr (R_LOG == 7) {
+        if (!DIF) { run_round<7, 4, DIF>(tile, 0, tws, fp, ncols); run_round<7, 3, DIF>(tile, 4, tws, fp, ncols); }
+        else      { run_round<7, 3, DIF>(tile, 4, tws, fp, ncols); run_round<7, 4, DIF>(tile, 0, tws, fp, ncols); }
+    } else if constexpr (R_LOG == 8) {
+        if (!DIF) { run_round<8, 4, DIF>(tile, 0, tws, fp, ncols); run_round<8, 4, DIF>(tile, 4, tws, fp, ncols); }
+        else      { run_round<8, 4, DIF>(tile, 4, tws, fp, ncols); run_round<8, 4, DIF>(tile, 0, tws, fp, ncols); }
+    } else {
+        static_assert(R_LOG == 9, "pass width");
+        if (!DIF) { run_round<9, 3, DIF>(tile, 0, tws, fp, ncols); run_round<9, 3, DIF>(tile, 3, tws, fp, ncols); run_round<9, 3, DIF>(tile, 6, tws, fp, ncols); }
+        else      { run_round<9, 3, DIF>(tile, 6, tws, fp, ncols); run_round<9, 3, DIF>(tile, 3, tws, fp, ncols); run_round<9, 3, DIF>(tile, 0, tws, fp, ncols); }
+    }
+}
+
+__device__ __forceinline__ uint32_t bitrev_bits(uint32_t x, unsigned bits) { return bits ? (__brev(x) >> (32 - bits)) : 0u; }
+
+template <int R_LOG, bool DIF, bool STRIDED>
+__global__ void ntt_pass_kernel(NttPass ps, FieldParams fp) {
+    extern __shared__ uint32_t smem[];
+    constexpr int R = 1 << R_LOG;
+    uint32_t* tile = smem;                    // [R][33]
+    uint32_t* tws = smem + R * NTT_TS;        // [R/2] twiddles of w_R
+    for (int k = threadIdx.x; k < (R >> 1); k += blockDim.x) tws[k] = ps.small[(size_t)k << (ps.small_log - R_LOG)];
+
+    const size_t tile_id = blockIdx.x;
+    size_t gbase;
+    uint32_t low0 = 0;
+    if (STRIDED) {
+        const size_t tiles_per_high = ((size_t)1 << ps.lo) / NTT_C;
+        const size_t high = tile_id / tiles_per_high;
+        low0 = (uint32_t)(tile_id % tiles_per_high) * NTT_C;
+        gbase = (high << (ps.lo + R_LOG)) | low0;
+    } else {
+        gbase = tile_id * (size_t)R * ps.ncols;
+    }
+    const unsigned tw_shift = ps.log_n - ps.lo - R_LOG;   // exponent scale into the size-2^log_n tables
+    const int total = R * (int)ps.ncols;
+
+    // ---- load (coalesced) ----
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        int t, c;
+        size_t g;
+        if (STRIDED) { t = i / NTT_C; c = i % NTT_C; g = gbase + ((size_t)t << ps.lo) + c; }
+        else         { c = i >> R_LOG; t = i & (R - 1); g = gbase + i; }
+        uint32_t x;
+        if (!STRIDED && !DIF && ps.log_pad) {
+            if (g & (((size_t)1 << ps.log_pad) - 1)) x = 0;
+            else {
+                uint32_t q = (uint32_t)(g >> ps.log_pad);
+                x = ps.src[q];
+                if (ps.has_scale) x = mont_mul(x, pow_lookup(ps.scale, bitrev_bits(q, ps.log_m), fp), fp);
+            }
+        } else {
+            x = ps.src[g];
+            if (!STRIDED && !DIF && ps.has_scale) x = mont_mul(x, pow_lookup(ps.scale, bitrev_bits((uint32_t)g, ps.log_n), fp), fp);
+        }
+        if (STRIDED && !DIF) {   // DIT inter-pass twiddle on the way in: w_{2^(lo+r)}^(bitrev(t) * low)
+            uint32_t e = bitrev_bits((uint32_t)t, R_LOG) * (low0 + (uint32_t)c);
+            x = mont_mul(x, pow_lookup(ps.tw, e << tw_shift, fp), fp);
+        }
+        tile[t * NTT_TS + c] = x;
+    }
+    __syncthreads();
+
+    run_rounds<R_LOG, DIF>(tile, tws, fp, ps.ncols);
+
+    // ---- store (same addresses) ----
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        int t, c;
+        size_t g;
+        if (STRIDED) { t = i / NTT_C; c = i % NTT_C; g = gbase + ((size_t)t << ps.lo) + c; }
+        else         { c = i >> R_LOG; t = i & (R - 1); g = gbase + i; }
+        uint32_t x = tile[t * NTT_TS + c];
+        if (STRIDED && DIF) {    // DIF inter-pass twiddle on the way out
+            uint32_t e = bitrev_bits((uint32_t)t, R_LOG) * (low0 + (uint32_t)c);
+            x = mont_mul(x, pow_lookup(ps.tw, e << tw_shift, fp), fp);
+        }
+        ps.dst[g] = x;
+    }
+}
+
+template <int R_LOG, bool DIF, bool STRIDED>
+static void launch_pass(stark_ctx* ctx, const NttPass& ps, size_t tiles) {
+    constexpr int R = 1 << R_LOG;
+    int threads = (R * NTT_C) >> 4;
+    if (threads < 32) threads = 32;
+    if (threads > 1024) threads = 1024;
+    size_t smem = (size_t)(R * NTT_TS + (R >> 1) + 1) * sizeof(uint32_t);
+    auto kern = ntt_pass_kernel<R_LOG, DIF, STRIDED>;
+    if (smem > 48 * 1024) {
+        static bool once = false;   // per instantiation
+        if (!once) { STARK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); once = true; }
+    }
+    kern<<<(unsigned)tiles, threads, smem, ctx->stream>>>(ps, ctx->fp);
+    ctx->launches++;
+}
+
+template <bool DIF, bool STRIDED>
+static void dispatch_pass(stark_ctx* ctx, unsigned r, const NttPass& ps, size_t tiles) {
+    switch (r) {
+        case 1: if constexpr (!STRIDED) launch_pass<1, DIF, false>(ctx, ps, tiles); break;
+        case 2: if constexpr (!STRIDED) launch_pass<2, DIF, false>(ctx, ps, tiles); break;
+        case 3: if constexpr (!STRIDED) launch_pass<3, DIF, false>(ctx, ps, tiles); break;
+        case 4: if constexpr (!STRIDED) launch_pass<4, DIF, false>(ctx, ps, tiles); break;
+        case 5: launch_pass<5, DIF, STRIDED>(ctx, ps, tiles); break;
+        case 6: launch_pass<6, DIF, STRIDED>(ctx, ps, tiles); break;
+        case 7: launch_pass<7, DIF, STRIDED>(ctx, ps, tiles); break;
+        case 8: launch_pass<8, DIF, STRIDED>(ctx, ps, tiles); break;
+        case 9: launch_pass<9, DIF, STRIDED>(ctx, ps, tiles); break;
+        default: throw StarkError(ST_INTERNAL, "ntt: bad pass width");
+    }
+}
+
+__global__ void point_scale_kernel(const uint32_t* src, uint32_t* dst, int has_scale, PowTable scale, FieldParams fp) {
+    uint32_t x = src[0];
+    if (has_scale) x = mont_mul(x, pow_lookup(scale, 0, fp), fp);
+    dst[0] = x;
+}
+
+static std::vector<unsigned> plan_bits(unsigned log_n) {
+    if (log_n <= 9) return {log_n};
+    unsigned k = (log_n + 8) / 9, base = log_n / k, rem = log_n % k;
+    std::vector<unsigned> v;
+    for (unsigned i = 0; i < k; i++) v.push_back(base + (i < rem ? 1u : 0u));
+    return v;   // every entry is in [5, 9]
+}
+
+static void check_size(stark_ctx* ctx, unsigned log_n) {
+    STARK_REQUIRE(log_n <= ctx->two_adicity, "ntt: 2^log_n does not divide p-1 (no root of unity of that order)");
+    STARK_REQUIRE(log_n <= 30, "ntt: log_n > 30 not supported");
+}
+
+void ntt_dit(stark_ctx* ctx, const uint32_t* src, uint32_t* data, unsigned log_n, unsigned log_pad,
+             const PowTable* scale, bool inverse_root) {
+    check_size(ctx, log_n);
+    STARK_REQUIRE(log_pad <= log_n, "ntt: padding larger than the transform");
+    if (log_n == 0) {   // single point: X[0] = x[0] * scale(0)
+        point_scale_kernel<<<1, 1, 0, ctx->stream>>>(src, data, scale != nullptr, scale ? *scale : PowTable{}, ctx->fp);
+        ctx->launches++;
+        STARK_CUDA(cudaGetLastError());
+        return;
+    }
+    const TwiddleSet& tws = ctx->twiddles(log_n);
+    const size_t n = (size_t)1 << log_n;
+    std::vector<unsigned> bits = plan_bits(log_n);
+    unsigned lo = 0;
+    for (size_t i = 0; i < bits.size(); i++) {
+        unsigned r = bits[i];
+        NttPass ps{};
+        ps.src = (i == 0) ? src : data;
+        ps.dst = data;
+        ps.log_n = log_n; ps.lo = lo;
+        ps.tw = inverse_root ? tws.inv() : tws.fwd();
+        ps.small = inverse_root ? ctx->small_inv.as<uint32_t>() : ctx->small_fwd.as<uint32_t>();
+        ps.small_log = ctx->small_log;
+        if (i == 0) {
+            ps.log_pad = log_pad; ps.log_m = log_n - log_pad;
+            ps.has_scale = scale != nullptr;
+            if (scale) ps.scale = *scale;
+            size_t cols = n >> r;
+            ps.ncols = (unsigned)(cols < (size_t)NTT_C ? cols : NTT_C);
+            dispatch_pass<false, false>(ctx, r, ps, (n >> r) / ps.ncols);
+        } else {
+            ps.ncols = NTT_C;
+            dispatch_pass<false, true>(ctx, r, ps, n / ((size_t)NTT_C << r));
+        }
+        lo += r;
+    }
+    STARK_CUDA(cudaGetLastError());
+}
+
+void ntt_dif(stark_ctx* ctx, uint32_t* data, unsigned log_n, bool inverse_root) {
+    check_size(ctx, log_n);
+    if (log_n == 0) return;
+    const TwiddleSet& tws = ctx->twiddles(log_n);
+    const size_t n = (size_t)1 << log_n;
+    std::vector<unsigned> bits = plan_bits(log_n);
+    unsigned hi = log_n;
+    for (size_t ii = bits.size(); ii-- > 0;) {
+        unsigned r = bits[ii];
+        unsigned lo = hi - r;
+        NttPass ps{};
+        ps.src = data; ps.dst = data;
+        ps.log_n = log_n; ps.lo = lo;
+        ps.tw = inverse_root ? tws.inv() : tws.fwd();
+        ps.small = inverse_root ? ctx->small_inv.as<uint32_t>() : ctx->small_fwd.as<uint32_t>();
+        ps.small_log = ctx->small_log;
+        if (lo == 0) {
+            size_t cols = n >> r;
+            ps.ncols = (unsigned)(cols < (size_t)NTT_C ? cols : NTT_C);
+            dispatch_pass<true, false>(ctx, r, ps, (n >> r) / ps.ncols);
+        } else {
+            ps.ncols = NTT_C;
+            dispatch_pass<true, true>(ctx, r, ps, n / ((size_t)NTT_C << r));
+        }
+        hi = lo;
+    }
+    STARK_CUDA(cudaGetLastError());
+}
+
+// ---- bit-reversal gather (natural <-> bit-reversed), optional scale ------------------------------
+__global__ void bitrev_kernel(const uint32_t* in, uint32_t* out, unsigned log_n, int has_scale, PowTable scale,
+                              int by_input, FieldParams fp) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >> log_n) return;
+    uint32_t j = bitrev_bits((uint32_t)i, log_n);
+    uint32_t x = in[j];
+    if (has_scale) x = mont_mul(x, pow_lookup(scale, by_input ? j : (uint32_t)i, fp), fp);
+    out[i] = x;
+}
+void bitrev_permute(stark_ctx* ctx, const uint32_t* in, uint32_t* out, unsigned log_n, const PowTable* scale,
+                    bool scale_by_input_index) {
+    size_t n = (size_t)1 << log_n;
+    PowTable sc{};
+    if (scale) sc = *scale;
+    bitrev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(in, out, log_n, scale != nullptr, sc,
+                                                                         scale_by_input_index, ctx->fp);
+    ctx->launches++;
+    STARK_CUDA(cudaGetLastError());
+}
+
+// ---- per-call power tables (coset offsets, 1/n) --------------------------------------------------
+__global__ void scale_table_kernel(uint32_t base_m, uint32_t c0_m, unsigned shift, unsigned n_lo, unsigned n_hi,
+                                   uint32_t* lo, uint32_t* hi, FieldParams fp) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_lo) lo[i] = mont_pow(base_m, i, fp);
+    else if (i < n_lo + n_hi) {
+        unsigned j = i - n_lo;
+        hi[j] = mont_mul(c0_m, mont_pow(base_m, (uint64_t)j << shift, fp), fp);
+    }
+}
+void build_scale_table(stark_ctx* ctx, uint64_t base, uint64_t c0, unsigned log_n, ScaleTable& out) {
+    unsigned shift = (log_n + 1) / 2;
+    unsigned n_lo = 1u << shift, n_hi = 1u << (log_n - shift);
+    out.lo = DevBuf(n_lo * sizeof(uint32_t), ctx->stream);
+    out.hi = DevBuf(n_hi * sizeof(uint32_t), ctx->stream);
+    out.view = PowTable{out.lo.as<uint32_t>(), out.hi.as<uint32_t>(), shift, n_lo - 1};
+    unsigned total = n_lo + n_hi;
+    scale_table_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(ctx->to_mont(base), ctx->to_mont(c0), shift, n_lo, n_hi,
+                                                                     out.lo.as<uint32_t>(), out.hi.as<uint32_t>(), ctx->fp);
+    ctx->launches++;
+    STARK_CUDA(cudaGetLastError());
+}
+
+}  // namespace starkb200
+
+// ---- twiddle cache (host builds 2*2^(log_n/2) values once per size) -------------------------------
+const starkb200::TwiddleSet& stark_ctx::twiddles(unsigned log_n) {
+    using namespace starkb200;
+    auto it = tw.find(log_n);
+    if (it != tw.end()) return *it->second;
+    STARK_REQUIRE(log_n <= two_adicity, "twiddles: 2^log_n does not divide p-1");
+    auto ts = std::make_unique<TwiddleSet>();
+    unsigned shift = (log_n + 1) / 2;
+    size_t n_lo = (size_t)1 << shift, n_hi = (size_t)1 << (log_n - shift);
+    ts->shift = shift; ts->mask = (uint32_t)(n_lo - 1);
+    uint64_t w = root_of_unity(log_n), wi = h_inv(w, modulus);
+    auto fill = [&](uint64_t base, DevBuf& lo, DevBuf& hi) {
+        std::vector<uint32_t> a(n_lo), b(n_hi);
+        uint64_t acc = 1;
+        for (size_t j = 0; j < n_lo; j++) { a[j] = to_mont(acc); acc = h_mul(acc, base, modulus); }
+        uint64_t step = h_pow(base, n_lo, modulus); acc = 1;
+        for (size_t j = 0; j < n_hi; j++) { b[j] = to_mont(acc); acc = h_mul(acc, step, modulus); }
+        lo = DevBuf(n_lo * 4, stream); hi = DevBuf(n_hi * 4, stream);
+        STARK_CUDA(cudaMemcpyAsync(lo.p, a.data(), n_lo * 4, cudaMemcpyHostToDevice, stream));
+        STARK_CUDA(cudaMemcpyAsync(hi.p, b.data(), n_hi * 4, cudaMemcpyHostToDevice, stream));
+        STARK_CUDA(cudaStreamSynchronize(stream));   // a, b die here
+    };
+    fill(w, ts->fwd_lo, ts->fwd_hi);
+    fill(wi, ts->inv_lo, ts->inv_hi);
+    auto& ref = *ts;
+    tw[log_n] = std::move(ts);
+    return ref;
+}

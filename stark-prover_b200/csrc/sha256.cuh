@@ -1,0 +1,141 @@
+// sha256.cuh — SHA-256 compression on the integer pipes (SHF / LOP3 / IADD3), fully unrolled.
+//
+// Implements exactly the hash the reference's Merkle tree uses (src/merkle/mod.rs:13-16 via
+// rs_merkle 1.4.2 `algorithms::Sha256` = sha2 0.10.8):
+//   leaf   = SHA-256(value.to_be_bytes())  — one 64-byte block: W0:W1 = value, W2 = 0x80000000, W15 = 64
+//   parent = SHA-256(left || right)        — block 1 = the children's 16 state words,
+//                                            block 2 = constant padding (W0 = 0x80000000, W15 = 512)
+// Digests live in registers / HBM as the eight big-endian state WORDS, so no byte swaps are needed
+// until a digest leaves the device.
+#pragma once
+#include <stdint.h>
+
+namespace starkb200 {
+
+struct Digest { uint32_t w[8]; };
+
+__device__ __forceinline__ uint32_t rotr32(uint32_t x, unsigned n) { return __funnelshift_r(x, x, n); }
+__device__ __forceinline__ uint32_t big_s0(uint32_t x) { return rotr32(x, 2) ^ rotr32(x, 13) ^ rotr32(x, 22); }
+__device__ __forceinline__ uint32_t big_s1(uint32_t x) { return rotr32(x, 6) ^ rotr32(x, 11) ^ rotr32(x, 25); }
+__device__ __forceinline__ uint32_t sml_s0(uint32_t x) { return rotr32(x, 7) ^ rotr32(x, 18) ^ (x >> 3); }
+__device__ __forceinline__ uint32_t sml_s1(uint32_t x) { return rotr32(x, 17) ^ rotr32(x, 19) ^ (x >> 10); }
+__device__ __forceinline__ uint32_t ch(uint32_t e, uint32_t f, uint32_t g) { return (e & f) ^ (~e & g); }
+__device__ __forceinline__ uint32_t maj(uint32_t a, uint32_t b, uint32_t c) { return (a & b) ^ (a & c) ^ (b & c); }
+
+#define STARK_SHA_K                                                                                        \
+    { 0x428a2f98u,0x71374491u,0xb5c0fbcfu,0xe9b5dba5u,0x3956c25bu,0x59f111f1u,0x923f82a4u,0xab1c5ed5u,      \
+      0xd807aa98u,0x12835b01u,0x243185beu,0x550c7dc3u,0x72be5d74u,0x80deb1feu,0x9bdc06a7u,0xc19bf174u,      \
+      0xe49b69c1u,0xefbe4786u,0x0fc19dc6u,0x240ca1ccu,0x2de92c6fu,0x4a7484aau,0x5cb0a9dcu,0x76f988dau,      \
+      0x983e5152u,0xa831c66du,0xb00327c8u,0xbf597fc7u,0xc6e00bf3u,0xd5a79147u,0x06ca6351u,0x14292967u,      \
+      0x27b70a85u,0x2e1b2138u,0x4d2c6dfcu,0x53380d13u,0x650a7354u,0x766a0abbu,0x81c2c92eu,0x92722c85u,      \
+      0xa2bfe8a1u,0xa81a664bu,0xc24b8b70u,0xc76c51a3u,0xd192e819u,0xd6990624u,0xf40e3585u,0x106aa070u,      \
+      0x19a4c116u,0x1e376c08u,0x2748774cu,0x34b0bcb5u,0x391c0cb3u,0x4ed8aa4au,0x5b9cca4fu,0x682e6ff3u,      \
+      0x748f82eeu,0x78a5636fu,0x84c87814u,0x8cc70208u,0x90befffau,0xa4506cebu,0xbef9a3f7u,0xc67178f2u }
+
+// K[i] + W[i] of the constant second block of a 64-byte message (generated offline; checked by the
+// parity tests against hashlib through every Merkle root).
+#define STARK_SHA_KW_PAD64                                                                                 \
+    { 0xc28a2f98u,0x71374491u,0xb5c0fbcfu,0xe9b5dba5u,0x3956c25bu,0x59f111f1u,0x923f82a4u,0xab1c5ed5u,      \
+      0xd807aa98u,0x12835b01u,0x243185beu,0x550c7dc3u,0x72be5d74u,0x80deb1feu,0x9bdc06a7u,0xc19bf374u,      \
+      0x649b69c1u,0xf0fe4786u,0x0fe1edc6u,0x240cf254u,0x4fe9346fu,0x6cc984beu,0x61b9411eu,0x16f988fau,      \
+      0xf2c65152u,0xa88e5a6du,0xb019fc65u,0xb9d99ec7u,0x9a1231c3u,0xe70eeaa0u,0xfdb1232bu,0xc7353eb0u,      \
+      0x3069bad5u,0xcb976d5fu,0x5a0f118fu,0xdc1eeefdu,0x0a35b689u,0xde0b7a04u,0x58f4ca9du,0xe15d5b16u,      \
+      0x007f3e86u,0x37088980u,0xa507ea32u,0x6fab9537u,0x17406110u,0x0d8cd6f1u,0xcdaa3b6du,0xc0bbbe37u,      \
+      0x83613bdau,0xdb48a363u,0x0b02e931u,0x6fd15ca7u,0x521afacau,0x31338431u,0x6ed41a95u,0x6d437890u,      \
+      0xc39c91f2u,0x9eccabbdu,0xb5c9a0e6u,0x532fb63cu,0xd2c741c6u,0x07237ea3u,0xa4954b68u,0x4c191d76u }
+
+#define STARK_SHA_ROUND(a, b, c, d, e, f, g, h, kw)                 \
+    {                                                               \
+        uint32_t t1 = (h) + big_s1(e) + ch(e, f, g) + (kw);         \
+        uint32_t t2 = big_s0(a) + maj(a, b, c);                     \
+        (d) += t1;                                                  \
+        (h) = t1 + t2;                                              \
+    }
+
+// One compression of state `st` with the 16 message words in `w` (clobbered).
+__device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16]) {
+    constexpr uint32_t K[64] = STARK_SHA_K;
+    uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll
+    for (int i = 0; i < 64; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int t = i + j;
+            if (t >= 16)
+                w[t & 15] += sml_s0(w[(t + 1) & 15]) + w[(t + 9) & 15] + sml_s1(w[(t + 14) & 15]);
+        }
+        STARK_SHA_ROUND(a, b, c, d, e, f, g, h, K[i + 0] + w[(i + 0) & 15]);
+        STARK_SHA_ROUND(h, a, b, c, d, e, f, g, K[i + 1] + w[(i + 1) & 15]);
+        STARK_SHA_ROUND(g, h, a, b, c, d, e, f, K[i + 2] + w[(i + 2) & 15]);
+        STARK_SHA_ROUND(f, g, h, a, b, c, d, e, K[i + 3] + w[(i + 3) & 15]);
+        STARK_SHA_ROUND(e, f, g, h, a, b, c, d, K[i + 4] + w[(i + 4) & 15]);
+        STARK_SHA_ROUND(d, e, f, g, h, a, b, c, K[i + 5] + w[(i + 5) & 15]);
+        STARK_SHA_ROUND(c, d, e, f, g, h, a, b, K[i + 6] + w[(i + 6) & 15]);
+        STARK_SHA_ROUND(b, c, d, e, f, g, h, a, K[i + 7] + w[(i + 7) & 15]);
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+
+// Compression with the constant padding block of a 64-byte message: no schedule, K+W are immediates.
+__device__ __forceinline__ void sha256_compress_pad64(uint32_t st[8]) {
+    constexpr uint32_t KW[64] = STARK_SHA_KW_PAD64;
+    uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll
+    for (int i = 0; i < 64; i += 8) {
+        STARK_SHA_ROUND(a, b, c, d, e, f, g, h, KW[i + 0]);
+        STARK_SHA_ROUND(h, a, b, c, d, e, f, g, KW[i + 1]);
+        STARK_SHA_ROUND(g, h, a, b, c, d, e, f, KW[i + 2]);
+        STARK_SHA_ROUND(f, g, h, a, b, c, d, e, KW[i + 3]);
+        STARK_SHA_ROUND(e, f, g, h, a, b, c, d, KW[i + 4]);
+        STARK_SHA_ROUND(d, e, f, g, h, a, b, c, KW[i + 5]);
+        STARK_SHA_ROUND(c, d, e, f, g, h, a, b, KW[i + 6]);
+        STARK_SHA_ROUND(b, c, d, e, f, g, h, a, KW[i + 7]);
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+
+__device__ __forceinline__ void sha256_init(uint32_t st[8]) {
+    st[0] = 0x6a09e667u; st[1] = 0xbb67ae85u; st[2] = 0x3c6ef372u; st[3] = 0xa54ff53au;
+    st[4] = 0x510e527fu; st[5] = 0x9b05688cu; st[6] = 0x1f83d9abu; st[7] = 0x5be0cd19u;
+}
+
+// leaf = SHA-256(BE8(value)); value < 2^32 on this path (canonical element of a field with p < 2^32),
+// the high word is still taken so the rule is the reference's for any u64.
+__device__ __forceinline__ void sha256_leaf(uint32_t hi, uint32_t lo, Digest& out) {
+    uint32_t w[16];
+    w[0] = hi; w[1] = lo; w[2] = 0x80000000u;
+#pragma unroll
+    for (int i = 3; i < 15; i++) w[i] = 0;
+    w[15] = 64;
+    sha256_init(out.w);
+    sha256_compress(out.w, w);
+}
+
+// parent = SHA-256(left || right)
+__device__ __forceinline__ void sha256_node(const Digest& l, const Digest& r, Digest& out) {
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { w[i] = l.w[i]; w[8 + i] = r.w[i]; }
+    uint32_t st[8];
+    sha256_init(st);
+    sha256_compress(st, w);
+    sha256_compress_pad64(st);
+#pragma unroll
+    for (int i = 0; i < 8; i++) out.w[i] = st[i];
+}
+
+__device__ __forceinline__ Digest load_digest(const uint32_t* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    Digest d;
+    d.w[0] = a.x; d.w[1] = a.y; d.w[2] = a.z; d.w[3] = a.w;
+    d.w[4] = b.x; d.w[5] = b.y; d.w[6] = b.z; d.w[7] = b.w;
+    return d;
+}
+__device__ __forceinline__ void store_digest(uint32_t* p, const Digest& d) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(d.w[0], d.w[1], d.w[2], d.w[3]);
+    q[1] = make_uint4(d.w[4], d.w[5], d.w[6], d.w[7]);
+}
+
+}  // namespace starkb200

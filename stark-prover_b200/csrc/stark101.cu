@@ -1,0 +1,164 @@
+// stark101.cu — the FibonacciSq (STARK-101) prover on top of the hot path.
+//
+// BUILD-DEFINED: src/prover/*, src/trace/*, src/composition/* are empty files in the reference, so there
+// is nothing to match there; the statement, constraints and transcript order are written down in
+// DESIGN.md ("cfg1") and pinned by the oracle's literal (Horner / Lagrange / long-division) restatement.
+// Every primitive it calls — interpolate, evaluate over the coset, MerkleTree::new, Channel,
+// fri_commit, decommit — is the reference-backed one.
+//
+//   trace      a0 = 1, a1 = given, a_{n+2} = a_{n+1}^2 + a_n^2, T-1 rows (T = 2^log_trace)
+//   f          interpolant of the trace over g^i, i < T-1 (degree <= T-2)
+//   p0         (f(x) - 1) / (x - 1)
+//   p1         (f(x) - a_{T-2}) / (x - g^(T-2))
+//   p2         (f(g^2 x) - f(g x)^2 - f(x)^2) (x-g^(T-3))(x-g^(T-2))(x-g^(T-1)) / (x^T - 1)
+//   CP         alpha0 p0 + alpha1 p1 + alpha2 p2, committed by fri_commit on the coset w*<h>
+#include <string.h>
+
+#include "../../include/stark_b200.h"
+#include "handles.hpp"
+
+using namespace starkb200;
+
+namespace starkb200 {
+
+struct FibSqDev {
+    uint32_t offset;          // w (canonical)
+    uint32_t one;             // 1
+    uint32_t x_last;          // g^(T-2)
+    uint32_t ex[3];           // g^(T-3), g^(T-2), g^(T-1)
+    uint32_t last_value;      // a_{T-2}
+    uint32_t alpha_m[3];      // Montgomery form
+    uint32_t blow;            // 2^log_blowup
+    const uint32_t* zinv_m;   // blow entries: (x^T - 1)^-1 for i mod blow, Montgomery form
+};
+
+// d0[i] = x_i - 1, d1[i] = x_i - g^(T-2),  x_i = w h^i
+__global__ void fibsq_denoms_kernel(FibSqDev q, PowTable tw, uint32_t* d0, uint32_t* d1, size_t n, FieldParams fp) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t x = mont_mul(pow_lookup(tw, (uint32_t)i, fp), q.offset, fp);
+    d0[i] = fsub(x, q.one, fp);
+    d1[i] = fsub(x, q.x_last, fp);
+}
+// i0 = 1/d0, i1 = 1/d1 (canonical) -> CP(x_i)
+__global__ void fibsq_combine_kernel(FibSqDev q, PowTable tw, const uint32_t* f, const uint32_t* i0, const uint32_t* i1,
+                                     uint32_t* cp, size_t n, FieldParams fp) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t x = mont_mul(pow_lookup(tw, (uint32_t)i, fp), q.offset, fp);
+    uint32_t fx = f[i], fgx = f[(i + q.blow) & (n - 1)], fg2x = f[(i + 2 * (size_t)q.blow) & (n - 1)];   // g = h^blow
+    uint32_t p0 = mont_mul(to_mont(fsub(fx, q.one, fp), fp), i0[i], fp);
+    uint32_t p1 = mont_mul(to_mont(fsub(fx, q.last_value, fp), fp), i1[i], fp);
+    uint32_t sq1 = mont_mul(to_mont(fgx, fp), fgx, fp), sq0 = mont_mul(to_mont(fx, fp), fx, fp);
+    uint32_t num = fsub(fsub(fg2x, sq1, fp), sq0, fp);
+    uint32_t e = mont_mul(to_mont(fsub(x, q.ex[0], fp), fp), fsub(x, q.ex[1], fp), fp);
+    e = mont_mul(to_mont(e, fp), fsub(x, q.ex[2], fp), fp);
+    uint32_t p2 = mont_mul(to_mont(num, fp), e, fp);
+    p2 = mont_mul(p2, __ldg(q.zinv_m + (i & (q.blow - 1))), fp);
+    uint32_t r = fadd(mont_mul(p0, q.alpha_m[0], fp), mont_mul(p1, q.alpha_m[1], fp), fp);
+    cp[i] = fadd(r, mont_mul(p2, q.alpha_m[2], fp), fp);
+}
+
+void fibsq_composition(stark_ctx* ctx, const uint32_t* f_eval, const FibSqParams& prm, uint32_t* cp_eval) {
+    const uint64_t p = ctx->modulus;
+    const unsigned log_N = prm.log_trace + prm.log_blowup;
+    const size_t T = (size_t)1 << prm.log_trace, N = (size_t)1 << log_N, blow = (size_t)1 << prm.log_blowup;
+    const uint64_t g = ctx->root_of_unity(prm.log_trace), h = ctx->root_of_unity(log_N), w = prm.offset % p;
+    FibSqDev q{};
+    q.offset = (uint32_t)w; q.one = (uint32_t)(1 % p);
+    q.x_last = (uint32_t)h_pow(g, T - 2, p);
+    q.ex[0] = (uint32_t)h_pow(g, T - 3, p); q.ex[1] = q.x_last; q.ex[2] = (uint32_t)h_pow(g, T - 1, p);
+    q.last_value = (uint32_t)(prm.last_value % p);
+    for (int k = 0; k < 3; k++) q.alpha_m[k] = ctx->to_mont(prm.alpha[k]);
+    q.blow = (uint32_t)blow;
+    // x^T - 1 takes `blow` distinct values on the coset: w^T (h^T)^i
+    std::vector<uint32_t> zinv(blow);
+    uint64_t wT = h_pow(w, T, p), hT = h_pow(h, T, p), cur = wT;
+    for (size_t i = 0; i < blow; i++) { zinv[i] = ctx->to_mont(h_inv((cur + p - 1) % p, p)); cur = h_mul(cur, hT, p); }
+    DevBuf d_z(blow * 4, ctx->stream), d0(N * 4, ctx->stream), d1(N * 4, ctx->stream);
+    STARK_CUDA(cudaMemcpyAsync(d_z.p, zinv.data(), blow * 4, cudaMemcpyHostToDevice, ctx->stream));
+    STARK_CUDA(cudaStreamSynchronize(ctx->stream));
+    q.zinv_m = d_z.as<uint32_t>();
+    PowTable tw = ctx->twiddles(log_N).fwd();
+    unsigned blocks = (unsigned)((N + 255) / 256);
+    fibsq_denoms_kernel<<<blocks, 256, 0, ctx->stream>>>(q, tw, d0.as<uint32_t>(), d1.as<uint32_t>(), N, ctx->fp);
+    ctx->launches++;
+    batch_inverse(ctx, d0.as<uint32_t>(), nullptr, d0.as<uint32_t>(), N);
+    batch_inverse(ctx, d1.as<uint32_t>(), nullptr, d1.as<uint32_t>(), N);
+    fibsq_combine_kernel<<<blocks, 256, 0, ctx->stream>>>(q, tw, f_eval, d0.as<uint32_t>(), d1.as<uint32_t>(), cp_eval, N, ctx->fp);
+    ctx->launches++;
+    STARK_CUDA(cudaGetLastError());
+}
+
+}  // namespace starkb200
+
+// helpers implemented in api.cu
+namespace starkb200 {
+DevBufPtr api_upload_u64(stark_ctx* ctx, const uint64_t* host, size_t n);
+DevBufPtr api_lde_on_coset(stark_ctx* ctx, const uint32_t* evals, unsigned log_n, uint64_t offset_in, unsigned log_blowup, uint64_t offset_out);
+DevBufPtr api_interpolate_on_coset(stark_ctx* ctx, const uint32_t* evals, unsigned log_n, uint64_t offset);
+std::unique_ptr<stark_tree> api_tree_commit(stark_ctx* ctx, DevBufPtr leaves, size_t n);
+void api_send_root(Channel& ch, const stark_tree* t);
+void api_open_and_send(const stark_tree* t, size_t idx, Channel& ch);
+void api_set_error(const std::string& s);
+}  // namespace starkb200
+
+extern "C" int stark101_prove(stark_ctx* ctx, uint64_t a1, unsigned log_trace, unsigned log_blowup, size_t num_queries,
+                              stark_channel* chan) {
+    try {
+        STARK_REQUIRE(ctx && chan, "stark101_prove: null argument");
+        STARK_REQUIRE(log_trace >= 2 && log_trace + log_blowup <= ctx->two_adicity && log_trace + log_blowup <= 30,
+                      "stark101_prove: trace/blowup sizes not supported by this field");
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        STARK_CUDA(cudaSetDevice(ctx->device));
+        Channel& ch = chan->ch;
+        const uint64_t p = ctx->modulus;
+        const unsigned log_N = log_trace + log_blowup;
+        const size_t T = (size_t)1 << log_trace, rows = T - 1, N = (size_t)1 << log_N, blow = (size_t)1 << log_blowup;
+        const uint64_t g = ctx->root_of_unity(log_trace), w = ctx->generator;
+        // ---- src/trace: the recurrence is sequential, it stays on the host ----
+        std::vector<uint64_t> a(T);
+        a[0] = 1 % p; a[1] = a1 % p;
+        for (size_t i = 2; i < rows; i++) a[i] = (h_mul(a[i - 1], a[i - 1], p) + h_mul(a[i - 2], a[i - 2], p)) % p;
+        // T-th value chosen so that the x^(T-1) coefficient of the size-T interpolant vanishes:
+        // the result is the unique degree <= T-2 interpolant through the T-1 rows (Polynomial::interpolate).
+        uint64_t s = 0, gi = 1;
+        for (size_t i = 0; i < rows; i++) { s = (s + h_mul(a[i], gi, p)) % p; gi = h_mul(gi, g, p); }
+        a[rows] = h_mul((p - s) % p, h_inv(gi, p), p);
+        // ---- LDE of the trace column and its commitment ----
+        DevBufPtr tr = api_upload_u64(ctx, a.data(), T);
+        DevBufPtr f_eval = api_lde_on_coset(ctx, tr->as<uint32_t>(), log_trace, 1, log_blowup, w);
+        auto f_tree = api_tree_commit(ctx, f_eval, N);
+        api_send_root(ch, f_tree.get());
+        FibSqParams prm{};
+        prm.log_trace = log_trace; prm.log_blowup = log_blowup; prm.offset = w; prm.last_value = a[rows - 1];
+        for (int k = 0; k < 3; k++) STARK_REQUIRE(ch.receive_random_field_element(&prm.alpha[k]), "channel: receive before send");
+        // ---- src/composition: CP on the coset, then its coefficients ----
+        DevBuf cp_eval(N * 4, ctx->stream);
+        fibsq_composition(ctx, f_eval->as<uint32_t>(), prm, cp_eval.as<uint32_t>());
+        DevBufPtr cp_coef = api_interpolate_on_coset(ctx, cp_eval.as<uint32_t>(), log_N, w);
+        stark_vec cpv; cpv.ctx = ctx; cpv.buf = cp_coef; cpv.n = N;
+        // ---- src/fri ----
+        stark_fri* fri = nullptr;
+        int rc = stark_fri_commit_dev(ctx, &cpv, log_N, w, chan, &fri);
+        if (rc != ST_OK) return rc;
+        std::unique_ptr<stark_fri> fri_guard(fri);
+        // ---- queries ----
+        for (size_t qn = 0; qn < num_queries; qn++) {
+            uint64_t idx;
+            STARK_REQUIRE(ch.receive_random_int(0, N - 1 - 2 * blow, true, &idx), "channel: receive before send");
+            api_open_and_send(f_tree.get(), (size_t)idx, ch);
+            api_open_and_send(f_tree.get(), (size_t)idx + blow, ch);
+            api_open_and_send(f_tree.get(), (size_t)idx + 2 * blow, ch);
+            rc = stark_decommit_fri_layers(fri, (size_t)idx, chan);
+            if (rc != ST_OK) return rc;
+        }
+        return ST_OK;
+    } catch (const StarkError& e) {
+        api_set_error(e.what());
+        return e.code;
+    } catch (const std::exception& e) {
+        api_set_error(e.what());
+        return ST_INTERNAL;
+    }
+}

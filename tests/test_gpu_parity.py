@@ -1,0 +1,329 @@
+"""GPU parity tests: every result of the CUDA path, called through the C ABI, must be bit-identical to
+the CPU oracle on the same seeded inputs (integer work: exact equality, no tolerance)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+P = 3221225473
+
+
+# ---------------------------------------------------------------- merkle
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 7, 8, 9, 13, 64, 100, 257, 511, 512, 513, 1000, 4096, 4097, 12345, 1 << 16])
+def test_merkle_root_and_levels(sp, orc, ctx, n):
+    vals = orc.synthetic_column(n, n)
+    t = sp.MerkleTree.new(ctx, vals)
+    ot = orc.Tree(vals)
+    assert t.root() == ot.root_hex()
+    assert t.depth == ot.depth and t.num_leaves == n
+    rng = np.random.default_rng(n)
+    for l in range(1, t.depth + 1):
+        m = -(-n // (1 << l))
+        for j in {0, m - 1, int(rng.integers(0, m))}:
+            assert t.node(l, j) == ot.node(l, j), (l, j)
+    for idx in {0, n - 1, n // 2, int(rng.integers(0, n))}:
+        assert t.get_authentication_path(idx) == ot.path(idx), idx
+
+
+def test_merkle_anchors(sp, ctx, golden):
+    a = golden["spec_anchors"]
+    for v, h in a["leaf"].items():
+        assert sp.MerkleTree.new(ctx, [int(v)]).root() == h
+    assert sp.MerkleTree.new(ctx, list(range(8))).root() == a["root_0_to_7"]
+    assert sp.MerkleTree.new(ctx, [0, 1, 2]).root() == a["root_0_1_2"]
+
+
+def test_merkle_empty_is_error(sp, ctx):
+    with pytest.raises(sp.StarkError) as e:
+        sp.MerkleTree.new(ctx, [])
+    assert e.value.code == 1
+
+
+def test_merkle_reduces_like_field_new(sp, orc, ctx):
+    # FieldElement::new reduces mod p before hashing (element.rs:13-17)
+    vals = np.array([P, P + 1, 2 * P + 5, 7], dtype=np.uint64)
+    assert sp.MerkleTree.new(ctx, vals).root() == orc.Tree(vals % np.uint64(P)).root_hex()
+
+
+def test_merkle_large_2e20(sp, orc, ctx):
+    n = 1 << 20
+    vals = orc.synthetic_column(42, n)
+    t = sp.MerkleTree.new(ctx, vals)
+    assert t.root_bytes() == orc.merkle_root_only(vals)
+    ot = orc.Tree(vals)
+    for idx in (0, 1, n - 1, 777777):
+        p = t.get_authentication_path(idx)
+        assert p == ot.path(idx)
+        assert orc.merkle_verify(t.root_bytes(), n, idx, int(vals[idx]), p)
+
+
+# ---------------------------------------------------------------- NTT / LDE
+@pytest.mark.parametrize("log_n", list(range(0, 21)))
+def test_ntt_roundtrip_and_oracle(sp, orc, ctx, log_n):
+    n = 1 << log_n
+    a = orc.synthetic_column(1000 + log_n, n)
+    w = orc.root_of_unity(log_n)
+    fwd = ctx.ntt(a, log_n)
+    assert np.array_equal(fwd, orc.ntt(a, log_n, w, P))
+    assert np.array_equal(ctx.intt(fwd, log_n), a)
+    assert np.array_equal(ctx.intt(a, log_n), orc.intt(a, log_n, w, P))
+
+
+@pytest.mark.parametrize("log_n,log_deg,offset", [(3, 0, 5), (4, 2, 5), (10, 7, 5), (13, 10, 5), (13, 13, 3), (17, 14, 5),
+                                                   (20, 17, 5), (19, 10, 7), (12, 0, 5), (22, 19, 5)])
+def test_coset_evaluate(sp, orc, ctx, log_n, log_deg, offset):
+    c = orc.synthetic_column(log_n * 100 + log_deg, 1 << log_deg)
+    w = orc.root_of_unity(log_n)
+    got = ctx.coset_evaluate(c, log_n, offset)
+    assert np.array_equal(got, orc.coset_evaluate(c, log_n, offset, w, P))
+    if log_n <= 10:   # against the reference's literal Horner
+        d = orc.coset_domain(offset, w, 1 << log_n, P)
+        assert got.tolist() == [orc.poly_evaluate(c, int(x), P) for x in d]
+
+
+def test_coset_evaluate_ragged_lengths(sp, orc, ctx):
+    w = orc.root_of_unity(10)
+    for ln in (0, 1, 3, 5, 100, 129, 1023):
+        c = orc.synthetic_column(ln + 1, ln)
+        assert np.array_equal(ctx.coset_evaluate(c, 10, 5), orc.coset_evaluate(c, 10, 5, w, P)), ln
+
+
+@pytest.mark.parametrize("log_n,offset", [(0, 5), (1, 5), (5, 5), (10, 3), (14, 5), (18, 5)])
+def test_coset_interpolate(sp, orc, ctx, log_n, offset):
+    e = orc.synthetic_column(77 + log_n, 1 << log_n)
+    w = orc.root_of_unity(log_n)
+    got = ctx.coset_interpolate(e, log_n, offset)
+    assert np.array_equal(got, orc.coset_interpolate(e, log_n, offset, w, P))
+    if log_n == 5:   # the reference's Lagrange interpolation
+        xs = orc.coset_domain(offset, w, 1 << log_n, P)
+        assert np.array_equal(orc.poly_trim(got), orc.poly_interpolate(xs, e, P))
+
+
+@pytest.mark.parametrize("log_n,log_blowup,off_in,off_out", [(0, 3, 1, 5), (3, 1, 1, 5), (10, 3, 1, 5), (12, 3, 5, 5),
+                                                             (17, 3, 1, 5), (16, 4, 7, 3), (20, 2, 1, 5), (9, 0, 1, 5)])
+def test_coset_lde(sp, orc, ctx, log_n, log_blowup, off_in, off_out):
+    e = orc.synthetic_column(5 + log_n, 1 << log_n)
+    got = ctx.coset_lde(e, log_n, off_in, log_blowup, off_out)
+    coeffs = orc.coset_interpolate(e, log_n, off_in, orc.root_of_unity(log_n), P)
+    want = orc.coset_evaluate(coeffs, log_n + log_blowup, off_out, orc.root_of_unity(log_n + log_blowup), P)
+    assert np.array_equal(got, want)
+
+
+def test_coset_domain(sp, orc, ctx):
+    for log_n in (0, 1, 7, 13):
+        assert np.array_equal(ctx.coset_domain(log_n, 5), orc.coset_domain(5, orc.root_of_unity(log_n), 1 << log_n, P))
+
+
+def test_ntt_linearity_large(sp, orc, ctx):
+    # size-independent property at 2^22: NTT(a + c*b) == NTT(a) + c*NTT(b)
+    log_n, c = 22, 987654321
+    a, b = orc.synthetic_column(1, 1 << log_n), orc.synthetic_column(2, 1 << log_n)
+    comb = ((a.astype(object) + c * b.astype(object)) % P).astype(np.uint64)
+    fa, fb, fc = ctx.ntt(a, log_n), ctx.ntt(b, log_n), ctx.ntt(comb, log_n)
+    want = ((fa.astype(object) + c * fb.astype(object)) % P).astype(np.uint64)
+    assert np.array_equal(fc, want)
+
+
+def test_unsupported_sizes(sp, ctx):
+    with pytest.raises(sp.StarkError):
+        ctx.coset_evaluate(np.zeros(4, dtype=np.uint64), 31, 5)
+    with pytest.raises(sp.StarkError):
+        ctx.coset_evaluate(np.zeros(32, dtype=np.uint64), 4, 5)      # more coefficients than points
+    with pytest.raises(sp.StarkError):
+        ctx.coset_evaluate(np.zeros(4, dtype=np.uint64), 4, 0)       # zero offset
+
+
+# ---------------------------------------------------------------- inverse / quotient
+@pytest.mark.parametrize("n", [0, 1, 7, 2048, 2049, 100003])
+def test_batch_inverse(sp, orc, ctx, n):
+    a = orc.synthetic_column(n + 3, n)
+    if n > 5:
+        a[[0, 3, n - 1]] = 0                                          # inverse(0) == 0 (element.rs:54-57)
+    got = ctx.batch_inverse(a)
+    assert np.array_equal(got, orc.batch_inverse(a, P))
+    if n:
+        i = n // 2
+        assert int(got[i]) == orc.fe_inverse(int(a[i]), P)
+
+
+def test_quotient_pointwise(sp, orc, ctx):
+    n = 5000
+    num, den = orc.synthetic_column(1, n), orc.synthetic_column(2, n)
+    den[[5, 77]] = 0
+    got = ctx.quotient_pointwise(num, den)
+    inv = orc.batch_inverse(den, P)
+    want = np.array([orc.fe_mul(int(x), int(y), P) for x, y in zip(num, inv)], dtype=np.uint64)
+    assert np.array_equal(got, want)
+    assert got[5] == 0                                                # a / 0 == a * 0 (element.rs:116-122)
+
+
+def test_vanishing_quotient_is_polynomial(sp, orc, ctx):
+    # (f(x) - f(1)) / (x - 1) evaluated point-wise on the coset interpolates to a polynomial of degree deg f - 1
+    log_t, log_n = 6, 9
+    f = orc.synthetic_column(11, 1 << log_t)
+    ev = ctx.coset_evaluate(f, log_n, 5)
+    f1 = orc.poly_evaluate(f, 1, P)
+    dom = ctx.coset_domain(log_n, 5)
+    num = (ev + np.uint64(P) - np.uint64(f1)) % np.uint64(P)
+    den = (dom + np.uint64(P) - np.uint64(1)) % np.uint64(P)
+    q = orc.poly_trim(ctx.coset_interpolate(ctx.quotient_pointwise(num, den), log_n, 5))
+    ql, rl = orc.poly_div_rem(orc.poly_sub(f, [f1], P), [P - 1, 1], P)            # ops.rs:141-191
+    assert len(rl) == 0 and np.array_equal(q, ql)
+
+
+# ---------------------------------------------------------------- FRI
+def _check_fri(sp, orc, ctx, coeffs, log_n, offset, queries):
+    w = orc.root_of_unity(log_n)
+    ch, och = sp.Channel(P), orc.Channel(P)
+    pr = sp.fri_commit(ctx, coeffs, sp.CosetFri(ctx, offset, log_n), ch)
+    opr = orc.fri_commit_fast(coeffs, log_n, offset, w, och, P)
+    assert pr.num_layers == opr.num_layers
+    for k in range(pr.num_layers):
+        assert pr.layer_len(k) == len(opr.layer(k))
+        assert np.array_equal(pr.layer(k), opr.layer(k)), f"layer {k}"
+        assert pr.tree(k).root() == opr.tree(k).root_hex(), f"root {k}"
+    assert np.array_equal(pr.final_poly(), opr.final_poly())
+    assert ch.state == och.state
+    sp.decommit_fri(queries, (1 << log_n) - 1, pr, ch)
+    orc.decommit_fri(queries, (1 << log_n) - 1, opr, och)
+    assert ch.state == och.state and ch.proof == och.proof
+    assert ch.proof_size() == och.proof_size() and ch.compressed_proof_size() == och.compressed_proof_size()
+    return pr, opr, ch
+
+
+@pytest.mark.parametrize("log_n,log_deg,offset,q", [(10, 7, 5, 3), (13, 10, 5, 3), (8, 8, 3, 2), (6, 6, 3, 2), (4, 0, 5, 1),
+                                                    (16, 13, 5, 4), (12, 3, 9, 2), (3, 1, 5, 1), (20, 17, 5, 8)])
+def test_fri_commit_and_decommit(sp, orc, ctx, log_n, log_deg, offset, q):
+    c = orc.synthetic_poly_exact_degree(43 + log_n, 1 << log_deg)
+    _check_fri(sp, orc, ctx, c, log_n, offset, q)
+
+
+def test_fri_non_power_of_two_degree_and_trailing_zeros(sp, orc, ctx):
+    c = orc.synthetic_column(9, 300)
+    c[-40:] = 0                                                       # Polynomial::new trims (ops.rs:19-37)
+    _check_fri(sp, orc, ctx, c, 12, 5, 2)
+
+
+def test_fri_zero_and_constant(sp, orc, ctx):
+    for coeffs in ([0, 0, 0], [7], [0]):
+        pr, _, ch = _check_fri(sp, orc, ctx, np.array(coeffs, dtype=np.uint64), 4, 5, 1)
+        assert pr.num_layers == 1
+
+
+def test_fri_leading_coefficient_cancels(sp, orc, ctx):
+    """A fold whose beta kills the leading coefficient drops the degree by more than half; the layer
+    count must follow the exact degree (fri_commit.rs:89), so drive the step API with a chosen beta."""
+    log_n = 8
+    c = orc.synthetic_poly_exact_degree(5, 32)
+    beta = orc.fe_mul(orc.fe_neg(int(c[30]), P), orc.fe_inverse(int(c[31]), P), P)   # c30 + beta*c31 == 0
+    pr, _ = sp.fri_begin(ctx, c, log_n, 5)
+    assert pr.degree == 31
+    pr.fold(beta)
+    want = orc.next_fri_polynomial(c, beta, P)
+    assert pr.degree == len(want) - 1 < 15
+    e1 = orc.fri_fold_evals(orc.coset_evaluate(c, log_n, 5, orc.root_of_unity(log_n), P), beta, 5, orc.root_of_unity(log_n), P)
+    assert np.array_equal(pr.layer(1), e1)
+
+
+def test_fri_golden_transcripts(sp, orc, ctx, golden):
+    for case in golden["transcripts"]["fri"]:
+        log_n = case["log_n"]
+        c = orc.synthetic_poly_exact_degree(case["seed"], 1 << case["log_deg"])
+        ch = sp.Channel(P)
+        pr = sp.fri_commit(ctx, c, sp.CosetFri(ctx, case["offset"], log_n), ch)
+        assert ch.state == case["state_after_commit"]
+        sp.decommit_fri(case["queries"], (1 << log_n) - 1, pr, ch)
+        assert [pr.tree(k).root() for k in range(pr.num_layers)] == case["roots"]
+        assert [hashlib.sha256(pr.layer(k).astype("<u8").tobytes()).hexdigest() for k in range(pr.num_layers)] == case["layer_sha256"]
+        assert pr.final_poly().tolist() == case["final_poly"]
+        assert ch.state == case["final_state"] and ch.proof_size() == case["proof_size"]
+        assert hashlib.sha256(ch.proof_flat()).hexdigest() == case["proof_sha256"]
+
+
+def test_fri_batched_open_matches_sequential(sp, orc, ctx):
+    log_n = 12
+    c = orc.synthetic_poly_exact_degree(3, 1 << 9)
+    ch = sp.Channel(P)
+    pr = sp.fri_commit(ctx, c, sp.CosetFri(ctx, 5, log_n), ch)
+    idxs = [0, 1, 4095, 2048, 1234]
+    blob = pr.open(idxs)
+    ch2 = sp.Channel(P); ch2.send(b"x")
+    before = len(ch2.proof)
+    for i in idxs:
+        sp.decommit_fri_layers(i, pr, ch2)
+    assert b"".join(ch2.proof[before:]) == blob
+    # every opened path verifies against its layer root
+    off = 0
+    for i in idxs:
+        for k in range(pr.num_layers):
+            n = pr.layer_len(k)
+            for which in (i % n, (i % n + n // 2) % n):
+                val = int.from_bytes(blob[off:off + 8], "big"); off += 8
+                plen = 32 * (n.bit_length() - 1)
+                assert orc.merkle_verify(pr.tree(k).root_bytes(), n, which, val, blob[off:off + plen]); off += plen
+    assert off == len(blob)
+
+
+def test_fri_device_resident_input(sp, orc, ctx):
+    log_n = 14
+    c = orc.synthetic_poly_exact_degree(8, 1 << 11)
+    v = ctx.upload(c)
+    ch1, ch2 = sp.Channel(P), sp.Channel(P)
+    p1 = sp.fri_commit(ctx, v, sp.CosetFri(ctx, 5, log_n), ch1)
+    p2 = sp.fri_commit(ctx, c, sp.CosetFri(ctx, 5, log_n), ch2)
+    assert ch1.state == ch2.state and p1.num_layers == p2.num_layers
+    assert np.array_equal(v.download(), c)
+
+
+def test_fri_too_many_folds_is_error(sp, orc, ctx):
+    # degree >= domain size: the reference would reach an empty layer and panic in MerkleTree::root()
+    pr, _ = sp.fri_begin(ctx, orc.synthetic_poly_exact_degree(1, 4), 2, 5)
+    pr.fold(3); pr.fold(5)
+    with pytest.raises(sp.StarkError):
+        pr.fold(7)
+
+
+# ---------------------------------------------------------------- cfg1: the STARK-101 transcript
+def test_stark101_transcript(sp, orc, ctx, golden):
+    s = golden["transcripts"]["stark101"]
+    ch = sp.Channel(P)
+    sp.stark101_prove(ctx, ch, s["a1"], s["log_trace"], s["log_blowup"], s["queries"])
+    och = orc.Channel(P)
+    orc.stark101_prove(och, literal=True)
+    assert ch.proof == och.proof and ch.state == och.state
+    assert ch.state == s["final_state"] and ch.proof_size() == s["proof_size"]
+    assert ch.compressed_proof_size() == s["compressed_proof_size"]
+    assert hashlib.sha256(ch.proof_flat()).hexdigest() == s["proof_sha256"]
+
+
+@pytest.mark.parametrize("log_trace,log_blowup,a1,q", [(5, 2, 7, 2), (8, 3, 3141592, 3), (12, 3, 99, 4), (14, 4, 5, 2)])
+def test_stark101_other_sizes(sp, orc, ctx, log_trace, log_blowup, a1, q):
+    ch, och = sp.Channel(P), orc.Channel(P)
+    sp.stark101_prove(ctx, ch, a1, log_trace, log_blowup, q)
+    orc.stark101_prove(och, a1=a1, log_trace=log_trace, log_blowup=log_blowup, num_queries=q, literal=False)
+    assert ch.proof == och.proof and ch.state == och.state
+
+
+# ---------------------------------------------------------------- other fields
+@pytest.mark.parametrize("modulus,gen", [(998244353, 3), (2013265921, 31), (17, 3), (7, 3), (257, 3)])
+def test_other_moduli(sp, orc, modulus, gen):
+    c = sp.Context(modulus, gen, 0)
+    try:
+        adic = c.two_adicity
+        log_n = min(adic, 12)
+        w = orc.root_of_unity(log_n, modulus, gen)
+        assert c.root_of_unity(log_n) == w
+        coeffs = orc.synthetic_column(1, 1 << max(log_n - 2, 0), modulus)
+        off = gen
+        assert np.array_equal(c.coset_evaluate(coeffs, log_n, off), orc.coset_evaluate(coeffs, log_n, off, w, modulus))
+        a = orc.synthetic_column(2, 500, modulus)
+        assert np.array_equal(c.batch_inverse(a), orc.batch_inverse(a, modulus))
+        ch, och = sp.Channel(modulus), orc.Channel(modulus)
+        pr = sp.fri_commit(c, coeffs, sp.CosetFri(c, off, log_n), ch)
+        opr = orc.fri_commit_fast(coeffs, log_n, off, w, och, modulus)
+        sp.decommit_fri(2, (1 << log_n) - 1, pr, ch)
+        orc.decommit_fri(2, (1 << log_n) - 1, opr, och)
+        assert ch.proof == och.proof and ch.state == och.state
+    finally:
+        c.close()
