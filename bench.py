@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py — LDE + Merkle + FRI-commit throughput (Melem/s) at a 2^24 domain on N B200s.
+
+A step = one pass of the hot path over one synthetic polynomial (BASELINE.json configs[2]):
+coset evaluation of a degree-(2^21-1) polynomial on the 2^24-point domain 5*<w>, 22 Merkle commitments,
+21 fused fold-and-hash layers driven by the host Fiat-Shamir channel, and the openings of 32 queries
+(`fri_commit` + `decommit_fri`, reference src/fri/fri_commit.rs:72-179).
+
+  value   device-timed (CUDA events on the library's stream), coefficients already resident in HBM
+  e2e     the same step through the host-buffer C ABI: pinned u64 coefficients -> stark_fri_commit (H2D
+          inside) -> roots/openings back in the host channel
+  N > 1   one process per GPU (torchrun); every rank commits its own column (weak scaling, no data-path
+          collective), then the 32-byte layer-0 roots are all-gathered (the root gather of SURVEY.md 8e)
+  --impl reference   the CPU oracle port of the reference algorithm (the Rust crate cannot be built here),
+          all host threads, on a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+P = 3221225473
+OFFSET = 5
+QUERIES = 32
+METRIC = "lde_merkle_fri_commit_throughput"
+UNIT = "Melem/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log-n", type=int, default=24, help="log2 of the LDE/FRI domain (headline: 24)")
+    ap.add_argument("--log-blowup", type=int, default=3)
+    ap.add_argument("--cpu-log-n", type=int, default=20, help="bounded CPU sample: domain 2^this")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-timing", action="store_true")
+    ap.add_argument("--profile-mode", action="store_true",
+                    help="for runs under ncu: exactly --warmup warm-up steps and --steps steps of the device-resident path, nothing else")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------- helpers
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, pw = [], None, set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax = float(r[2]); pw.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        busy = [x for x in sm if smax and x > 0.5 * smax] or sm
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+def measured_peaks() -> tuple[float, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def layer_sizes(log_n: int, log_deg: int) -> list[int]:
+    return [1 << (log_n - k) for k in range(log_deg + 1)]
+
+
+def algorithmic_counts(log_n: int, log_deg: int) -> dict:
+    """bytes at 8 B/element, 32 B/digest; 1384 int-ops per SHA-256 compression."""
+    sizes = layer_sizes(log_n, log_deg)
+    comp = sum(3 * n - 2 for n in sizes)
+    lde = 8 * (1 << log_deg) + 8 * (1 << log_n)
+    trees = sum(8 * n + 32 * (2 * n - 1) for n in sizes)
+    folds = sum(8 * n + 8 * (n // 2) for n in sizes[:-1])
+    fused = lde + sum(32 * (2 * n - 1) for n in sizes) + sum(8 * n for n in sizes[:-1]) + sum(8 * n for n in sizes[1:])
+    return {"compressions": comp, "int_ops": 1384 * comp, "bytes_per_op_sum": lde + trees + folds, "bytes_fused_min": fused}
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def cpu_step(orc, coeffs, log_n, queries):
+    """The reference's fri_commit + decommit_fri on the CPU (oracle port, NTT tier, retained trees)."""
+    ch = orc.Channel(P)
+    pr = orc.fri_commit_fast(coeffs, log_n, OFFSET, orc.root_of_unity(log_n, P), ch, P)
+    orc.decommit_fri(queries, (1 << log_n) - 1, pr, ch)
+    return ch
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pyoracle as orc
+    orc.build()
+    log_n = args.cpu_log_n
+    log_deg = log_n - args.log_blowup
+    coeffs = orc.synthetic_poly_exact_degree(43, 1 << log_deg, P)
+    for _ in range(max(args.warmup, 1)):
+        cpu_step(orc, coeffs, log_n, QUERIES)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(orc, coeffs, log_n, QUERIES)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = (1 << log_n) / dt / 1e6
+    cores = orc.num_threads()
+    sample = (f"fri_commit+decommit_fri at a 2^{log_n} domain (degree 2^{log_deg}-1, blowup {1 << args.log_blowup}, {QUERIES} queries): "
+              f"1/{1 << (args.log_n - log_n)} of the 2^{args.log_n} workload per step; oracle NTT tier, OpenMP, SHA-NI="
+              f"{bool(orc.lib().or_sha256_accel_active())}")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"cfg3: FRI commit at 2^{args.log_n} domain, blowup 8, {QUERIES} queries (bounded CPU sample at 2^{log_n})",
+                       "log_domain": args.log_n, "sample_log_domain": log_n},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "the reference is Rust nightly + un-vendored crates and cannot be built in this image; this is the C oracle port of its "
+                    "algorithm (NTT tier: same bits as the literal Horner tier, which is O(N*d) and cannot reach this size)"}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sp = importlib.import_module("stark-prover_b200")
+    from oracle import pyoracle as orc   # input generator + cpu_baseline leg only
+
+    log_n, log_deg = args.log_n, args.log_n - args.log_blowup
+    n = 1 << log_n
+    ctx = sp.Context(P, sp.G_DEFAULT, local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local)
+    coeffs = orc.synthetic_poly_exact_degree(43 + rank, 1 << log_deg, P)
+    pinned = torch.empty(1 << log_deg, dtype=torch.int64).pin_memory()
+    pinned_np = pinned.numpy().view(np.uint64)
+    pinned_np[:] = coeffs
+    dev_coeffs = ctx.upload(coeffs)
+    domain = sp.CosetFri(ctx, OFFSET, log_n)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
+    roots_out = torch.zeros(world, 32, dtype=torch.uint8, device=f"cuda:{local}") if world > 1 else None
+
+    def step(src):
+        ch = sp.Channel(P)
+        pr = sp.fri_commit(ctx, src, domain, ch)
+        sp.decommit_fri(QUERIES, n - 1, pr, ch)
+        return pr, ch
+
+    def gather_roots(pr):
+        if world == 1:
+            return
+        mine = torch.frombuffer(bytearray(pr.tree(0).root_bytes()), dtype=torch.uint8).to(f"cuda:{local}")
+        dist.all_gather_into_tensor(roots_out.view(-1), mine)
+
+    def timed(src, steps, flush_l2=True):
+        """max-over-ranks device time per step (ms) and the last step's artefacts."""
+        total = 0.0
+        pr = ch = None
+        for _ in range(steps):
+            if pr is not None:
+                pr.free()
+            if flush_l2:
+                with torch.cuda.stream(stream):
+                    flush.zero_()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            pr, ch = step(src)
+            gather_roots(pr)
+            if world > 1:
+                stream.wait_stream(torch.cuda.current_stream())
+            e1.record(stream)
+            torch.cuda.synchronize()
+            total += e0.elapsed_time(e1)
+        ms = total / steps
+        if world > 1:
+            t = torch.tensor([ms], device=f"cuda:{local}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, pr, ch
+
+    if args.profile_mode:
+        timed(dev_coeffs, args.warmup, flush_l2=False)
+        ms, pr, ch = timed(dev_coeffs, args.steps, flush_l2=False)
+        print(json.dumps({"profile_mode": True, "ms_per_step_under_profiler": ms, "launches": ctx.launch_count}), flush=True)
+        pr.free()
+        ctx.close()
+        return
+    # ---- warm-up, then the device-resident timed region
+    timed(dev_coeffs, max(args.warmup, 3))
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ctx.launch_count
+    ms_dev, pr, ch = timed(dev_coeffs, args.steps)
+    launches = (ctx.launch_count - l0) // args.steps
+    clocks = sampler.stop()
+    final_state = ch.state
+    n_layers = pr.num_layers
+    d2h = 32 * n_layers + 8 * n_layers + len(pr.open([0])) * QUERIES
+    pr.free()
+
+    # ---- end to end: pinned host coefficients through the host-buffer ABI
+    timed(pinned_np, 1)
+    ms_e2e, pr2, ch2 = timed(pinned_np, args.steps)
+    assert ch2.state == final_state, "device-resident and host-buffer paths disagree"
+    pr2.free()
+
+    line = {"metric": METRIC, "value": world * n / (ms_dev * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 field arithmetic (p < 2^32, u64 at the ABI) + u32 SHA-256", "data": "synthetic",
+            "config": {"workload": f"cfg3: fri_commit + decommit_fri, degree 2^{log_deg}-1 polynomial on the 2^{log_n} coset 5*<w>, "
+                                   f"p=3221225473, {n_layers} layers, {QUERIES} queries; one column per GPU",
+                       "log_domain": log_n, "blowup": 1 << args.log_blowup, "queries": QUERIES, "layers": n_layers,
+                       "l2": "256 MiB buffer written between timed iterations; layer 0 + its tree = 576 MiB > L2",
+                       "prove_ms": ms_dev},
+            "e2e": {"value": world * n / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": 8 << log_deg, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clocks, "transcript_state": final_state}
+
+    if rank == 0:
+        # ---- per-kernel durations, live, CUDA events on the launching stream (separate instrumented steps)
+        hbm_peak, peak_src = measured_peaks()
+        alg = algorithmic_counts(log_n, log_deg)
+        if not args.no_kernel_timing and world == 1:
+            ctx.set_timing(True)
+            ctx.read_timing()
+            ksteps = max(2, min(args.steps, 5))
+            ms_instr, pr3, _ = timed(dev_coeffs, ksteps)
+            kt = ctx.read_timing()
+            ctx.set_timing(False)
+            pr3.free()
+            alu_peak, mix_peak = ctx.measure_int_peak()
+            hash_ms = (kt["merkle_leaf"]["ms"] + kt["merkle_node"]["ms"]) / ksteps
+            hash_ops = (kt["merkle_leaf"]["units"] + kt["merkle_node"]["units"]) / ksteps
+            hash_launches = (kt["merkle_leaf"]["launches"] + kt["merkle_node"]["launches"]) // ksteps
+            achieved = hash_ops / (hash_ms * 1e-3) / 1e12
+            line["roofline"] = {
+                "kernel": "merkle_leaf_kernel (fused fold + leaf hash + 3 levels) + merkle_node_kernel / merkle_top_kernel",
+                "bound": "int", "achieved": achieved, "peak": alu_peak, "unit": "Tint-op/s", "frac": achieved / alu_peak,
+                "peak_source": "stark_measure_int_peak on this GPU: SHF+LOP3+IADD3 register chains (ALU pipe); "
+                               f"with IMAD co-issue {mix_peak:.1f}",
+                "traffic": None, "launches_per_step": hash_launches, "kernel_ms_per_step": hash_ms,
+                "share_of_step": hash_ms / ms_instr,
+                "algorithmic": "1384 int-ops per SHA-256 compression; leaf = 1, node = 2 compressions (SURVEY.md 8d)"}
+            ntt_ms = kt["ntt"]["ms"] / ksteps
+            ntt_gbs = kt["ntt"]["units"] / ksteps / (ntt_ms * 1e-3) / 1e9 if ntt_ms else None
+            # the fused fold+hash launches also stream every layer once: algorithmic bytes of those launches
+            leaf_bytes = alg["bytes_fused_min"] - (8 * (1 << log_deg) + 8 * n)
+            line["roofline_hbm"] = {
+                "ntt": {"bound": "hbm", "achieved": ntt_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ntt_gbs / hbm_peak if ntt_gbs else None,
+                        "kernel_ms_per_step": ntt_ms, "launches_per_step": kt["ntt"]["launches"] // ksteps,
+                        "algorithmic": "8 B per coefficient read + 8 B per evaluation written (SURVEY.md 8d LDE n->N)"},
+                "fold_and_hash": {"bound": "hbm", "achieved": leaf_bytes / (hash_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                  "frac": leaf_bytes / (hash_ms * 1e-3) / 1e9 / hbm_peak,
+                                  "note": "same launches as `roofline`: integer-bound, HBM fraction shown for completeness"},
+                "peak_source": peak_src}
+            line["kernel_ms"] = {k: v["ms"] / ksteps for k, v in kt.items()}
+            line["instrumented_ms_per_step"] = ms_instr
+        line["algorithmic"] = alg
+        # ---- CPU baseline beside it (bounded sample, all host threads)
+        if not args.no_cpu_baseline and world == 1:
+            cl = args.cpu_log_n
+            cc = orc.synthetic_poly_exact_degree(43, 1 << (cl - args.log_blowup), P)
+            cpu_step(orc, cc, cl, QUERIES)
+            reps, t0 = 0, time.perf_counter()
+            while reps < 3 or time.perf_counter() - t0 < 10.0:
+                cpu_step(orc, cc, cl, QUERIES)
+                reps += 1
+                if time.perf_counter() - t0 > 30.0:
+                    break
+            dt = (time.perf_counter() - t0) / reps
+            line["cpu_baseline"] = {"value": (1 << cl) / dt / 1e6, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+                                    "sample": f"{reps} x fri_commit+decommit_fri at a 2^{cl} domain (1/{1 << (log_n - cl)} of the workload), "
+                                              f"oracle NTT tier + OpenMP, SHA-NI={bool(orc.lib().or_sha256_accel_active())}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

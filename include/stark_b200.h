@@ -59,6 +59,16 @@ unsigned stark_ctx_two_adicity(const stark_ctx* ctx);
 unsigned long long stark_ctx_launch_count(const stark_ctx* ctx);
 /* The stream all work of this context is issued on (a cudaStream_t), for CUDA-event timing. */
 void* stark_ctx_stream(const stark_ctx* ctx);
+/* Measurement aid: while on, every kernel launch is bracketed by a CUDA-event pair on the context's stream.
+ * stark_ctx_read_timing syncs, returns per category {0: leaf hashing (incl. the fused FRI fold), 1: node
+ * hashing, 2: NTT passes, 3: everything else} the summed kernel milliseconds, the algorithmic work issued
+ * (int-ops for 0/1, bytes for 2/3; SURVEY.md 8d figures) and the launch count, and resets the counters. */
+int stark_ctx_set_timing(stark_ctx* ctx, int on);
+int stark_ctx_read_timing(stark_ctx* ctx, double ms[4], double units[4], unsigned long long launches[4]);
+/* Integer-pipe issue peak of this device in 1e12 thread-instructions/s: tops[0] = SHF+LOP3+IADD3 chains (ALU
+ * pipe only, what SHA-256's rotates and boolean functions are bound by), tops[1] = the same with one IMAD per
+ * three ALU instructions (ALU + FMA pipes).  MEASURED_PEAKS.json has no integer figure. */
+int stark_measure_int_peak(stark_ctx* ctx, double tops[2]);
 
 /* ---- device vectors ------------------------------------------------------------------------------ */
 int stark_vec_upload(stark_ctx* ctx, const uint64_t* host, size_t n, stark_vec** out);

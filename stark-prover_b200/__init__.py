@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from typing import Iterable, Optional, Sequence
 
 import numpy as np
@@ -65,6 +66,9 @@ def lib() -> C.CDLL:
     sig("stark_ctx_two_adicity", C.c_uint, vp)
     sig("stark_ctx_launch_count", C.c_ulonglong, vp)
     sig("stark_ctx_stream", vp, vp)
+    sig("stark_measure_int_peak", I, vp, C.POINTER(C.c_double))
+    sig("stark_ctx_set_timing", I, vp, I)
+    sig("stark_ctx_read_timing", I, vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_ulonglong))
     sig("stark_vec_upload", I, vp, vp, szt, C.POINTER(vp))
     sig("stark_vec_alloc", I, vp, szt, C.POINTER(vp))
     sig("stark_vec_download", I, vp, szt, szt, vp)
@@ -149,9 +153,15 @@ class Context:
         self.h = h
         self.modulus = lib().stark_ctx_modulus(h)
         self.generator = lib().stark_ctx_generator(h)
+        self._children = weakref.WeakSet()      # device objects that must die before the context
+
+    def _adopt(self, child):
+        self._children.add(child)
 
     def close(self):
         if getattr(self, "h", None):
+            for child in list(self._children):
+                child.free()
             lib().stark_ctx_destroy(self.h)
             self.h = None
 
@@ -169,6 +179,19 @@ class Context:
     def launch_count(self) -> int: return lib().stark_ctx_launch_count(self.h)
     @property
     def stream(self) -> int: return lib().stark_ctx_stream(self.h) or 0
+
+    def measure_int_peak(self) -> tuple[float, float]:
+        t = (C.c_double * 2)()
+        _check(lib().stark_measure_int_peak(self.h, t))
+        return t[0], t[1]
+
+    def set_timing(self, on: bool): _check(lib().stark_ctx_set_timing(self.h, int(on)))
+
+    def read_timing(self) -> dict:
+        ms, un, ln = (C.c_double * 4)(), (C.c_double * 4)(), (C.c_ulonglong * 4)()
+        _check(lib().stark_ctx_read_timing(self.h, ms, un, ln))
+        names = ["merkle_leaf", "merkle_node", "ntt", "other"]
+        return {names[i]: {"ms": ms[i], "units": un[i], "launches": int(ln[i])} for i in range(4)}
 
     # ---- device vectors
     def upload(self, host) -> "Vec":
@@ -265,6 +288,7 @@ class Vec:
 
     def __init__(self, ctx: Context, h):
         self.ctx, self.h = ctx, h
+        ctx._adopt(self)
 
     def __len__(self): return lib().stark_vec_len(self.h)
     @property
@@ -297,6 +321,8 @@ class MerkleTree:
 
     def __init__(self, ctx: Context, h, owned: bool = True, keep=None):
         self.ctx, self.h, self._owned, self._keep = ctx, h, owned, keep
+        if owned:
+            ctx._adopt(self)
 
     @classmethod
     def new(cls, ctx: Context, data) -> "MerkleTree":
@@ -416,6 +442,7 @@ class FriProof:
 
     def __init__(self, ctx: Context, h):
         self.ctx, self.h = ctx, h
+        ctx._adopt(self)
 
     @property
     def num_layers(self) -> int: return lib().stark_fri_num_layers(self.h)

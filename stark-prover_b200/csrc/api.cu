@@ -118,6 +118,8 @@ extern "C" void stark_ctx_destroy(stark_ctx* ctx) {
     ctx->tw.clear();
     ctx->small_fwd.release(); ctx->small_inv.release();
     cudaStreamSynchronize(ctx->stream);
+    for (int c = 0; c < stark_ctx::CAT_COUNT; c++) for (auto& pr : ctx->ev_used[c]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto e : ctx->ev_free) cudaEventDestroy(e);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -137,6 +139,32 @@ extern "C" uint64_t stark_ctx_root_of_unity(const stark_ctx* ctx, unsigned log_n
 extern "C" unsigned stark_ctx_two_adicity(const stark_ctx* ctx) { return ctx ? ctx->two_adicity : 0; }
 extern "C" unsigned long long stark_ctx_launch_count(const stark_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" void* stark_ctx_stream(const stark_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+extern "C" int stark_ctx_set_timing(stark_ctx* ctx, int on) {
+    API_BEGIN
+    STARK_REQUIRE(ctx, "null ctx");
+    CtxGuard g(ctx);
+    ctx->timing = on != 0;
+    API_END
+}
+extern "C" int stark_ctx_read_timing(stark_ctx* ctx, double ms[4], double units[4], unsigned long long launches[4]) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && ms && units && launches, "read_timing: null argument");
+    CtxGuard g(ctx);
+    STARK_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int c = 0; c < stark_ctx::CAT_COUNT; c++) {
+        double tot = 0;
+        for (auto& pr : ctx->ev_used[c]) {
+            float t = 0;
+            STARK_CUDA(cudaEventElapsedTime(&t, pr.first, pr.second));
+            tot += t;
+            ctx->ev_free.push_back(pr.first); ctx->ev_free.push_back(pr.second);
+        }
+        ms[c] = tot; units[c] = ctx->algo_units[c]; launches[c] = ctx->ev_used[c].size();
+        ctx->ev_used[c].clear(); ctx->algo_units[c] = 0;
+    }
+    API_END
+}
 
 // ======================================================================================= vectors
 static DevBufPtr upload_u64(stark_ctx* ctx, const uint64_t* host, size_t n, size_t alloc_n = 0) {

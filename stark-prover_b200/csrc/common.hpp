@@ -86,6 +86,16 @@ inline uint64_t h_inv(uint64_t a, uint64_t m) { return h_pow(a, m - 2, m); }
 
 }  // namespace starkb200
 
+struct stark_ctx;
+namespace starkb200 {
+// RAII: brackets the launches issued in its scope with a CUDA-event pair when ctx->timing is on.
+struct KernelTimer {
+    stark_ctx* ctx; int cat; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    KernelTimer(stark_ctx* c, int category, double units = 0);
+    ~KernelTimer();
+};
+}  // namespace starkb200
+
 // The opaque C-ABI context (one per device x modulus).
 struct stark_ctx {
     int device = 0;
@@ -101,6 +111,13 @@ struct stark_ctx {
     starkb200::HostResult* d_result = nullptr;  // device alias of h_result
     int sm_count = 148;
     unsigned long long launches = 0;            // kernels launched through this context
+
+    // optional per-category kernel timing (CUDA events on `stream`); see KernelTimer
+    enum { CAT_MERKLE_LEAF = 0, CAT_MERKLE_NODE = 1, CAT_NTT = 2, CAT_OTHER = 3, CAT_COUNT = 4 };
+    bool timing = false;
+    std::vector<cudaEvent_t> ev_free;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_used[CAT_COUNT];
+    double algo_units[CAT_COUNT] = {0, 0, 0, 0};   // algorithmic work issued per category while timing (int-ops or bytes)
 
     uint32_t to_mont(uint64_t a) const { return (uint32_t)starkb200::h_mul(a % modulus, (uint64_t)1 << 32, modulus); }
     uint64_t root_of_unity(unsigned log_n) const { return starkb200::h_pow(generator, (modulus - 1) >> log_n, modulus); }

@@ -13,6 +13,24 @@
 
 namespace starkb200 {
 
+KernelTimer::KernelTimer(stark_ctx* c, int category, double units) : ctx(c), cat(category) {
+    if (!ctx->timing) return;
+    auto get = [&]() {
+        cudaEvent_t e;
+        if (!ctx->ev_free.empty()) { e = ctx->ev_free.back(); ctx->ev_free.pop_back(); }
+        else STARK_CUDA(cudaEventCreate(&e));
+        return e;
+    };
+    e0 = get(); e1 = get();
+    ctx->algo_units[cat] += units;
+    cudaEventRecord(e0, ctx->stream);
+}
+KernelTimer::~KernelTimer() {
+    if (!e0) return;
+    cudaEventRecord(e1, ctx->stream);
+    ctx->ev_used[cat].emplace_back(e0, e1);
+}
+
 // ---------------- boundary conversions ----------------
 __global__ void narrow_kernel(const uint64_t* in, uint32_t* out, size_t n, uint32_t p) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -25,12 +43,14 @@ __global__ void widen_kernel(const uint32_t* in, uint64_t* out, size_t n) {
     if (i < n) out[i] = in[i];
 }
 void narrow_u64(stark_ctx* ctx, const uint64_t* in, uint32_t* out, size_t n) {
+    KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 12.0 * n);
     if (!n) return;
     narrow_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(in, out, n, ctx->fp.p);
     ctx->launches++;
     STARK_CUDA(cudaGetLastError());
 }
 void widen_u32(stark_ctx* ctx, const uint32_t* in, uint64_t* out, size_t n) {
+    KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 12.0 * n);
     if (!n) return;
     widen_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(in, out, n);
     ctx->launches++;
@@ -84,6 +104,7 @@ __global__ void coeff_fold_kernel(const uint32_t* c, size_t len, uint32_t beta_m
     }
 }
 void coeff_fold(stark_ctx* ctx, const uint32_t* c, size_t len, uint32_t beta_m, uint32_t* out, HostResult* result) {
+    KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 12.0 * len);
     size_t out_len = (len + 1) / 2;
     if (out_len == 0) { throw StarkError(ST_INTERNAL, "coeff_fold: empty polynomial"); }
     coeff_fold_kernel<true><<<(unsigned)((out_len + 255) / 256), 256, 0, ctx->stream>>>(c, len, beta_m, out, out_len, result, ctx->fp);
@@ -91,6 +112,7 @@ void coeff_fold(stark_ctx* ctx, const uint32_t* c, size_t len, uint32_t beta_m, 
     STARK_CUDA(cudaGetLastError());
 }
 void poly_degree(stark_ctx* ctx, const uint32_t* c, size_t len, HostResult* result) {
+    KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 8.0 * len);
     STARK_REQUIRE(len > 0, "poly_degree: empty");
     coeff_fold_kernel<false><<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>(c, len, 0, nullptr, len, result, ctx->fp);
     ctx->launches++;
@@ -128,6 +150,7 @@ batch_inverse_kernel(const uint32_t* a, const uint32_t* num, uint32_t* out, size
     }
 }
 void batch_inverse(stark_ctx* ctx, const uint32_t* a, const uint32_t* num, uint32_t* out, size_t n) {
+    KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 16.0 * n);
     if (!n) return;
     size_t per = (size_t)INV_THREADS * INV_K;
     batch_inverse_kernel<<<(unsigned)((n + per - 1) / per), INV_THREADS, 0, ctx->stream>>>(a, num, out, n, ctx->fp);
@@ -140,6 +163,7 @@ __global__ void pointwise_mul_kernel(const uint32_t* a, const uint32_t* b, uint3
     if (i < n) out[i] = mont_mul(to_mont(a[i], fp), b[i], fp);
 }
 void pointwise_mul(stark_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
+    KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 24.0 * n);
     if (!n) return;
     pointwise_mul_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(a, b, out, n, ctx->fp);
     ctx->launches++;
@@ -152,6 +176,7 @@ __global__ void coset_domain_kernel(uint32_t offset, PowTable tw, uint32_t* out,
     if (i < n) out[i] = mont_mul(pow_lookup(tw, (uint32_t)i, fp), offset, fp);
 }
 void coset_domain(stark_ctx* ctx, uint64_t offset, unsigned log_n, uint32_t* out) {
+    KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 8.0 * ((size_t)1 << log_n));
     const TwiddleSet& tws = ctx->twiddles(log_n);
     size_t n = (size_t)1 << log_n;
     coset_domain_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((uint32_t)(offset % ctx->modulus), tws.fwd(), out, n, ctx->fp);
@@ -168,6 +193,7 @@ __global__ void fri_fold_kernel(LeafSource src, FieldParams fp) {
     src.fold_out[i] = fadd(mont_mul(fadd(a, b, fp), src.inv2_m, fp), mont_mul(fsub(a, b, fp), s, fp), fp);
 }
 void fri_fold(stark_ctx* ctx, const LeafSource& src) {
+    KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 12.0 * 2 * src.half);
     if (!src.half) return;
     fri_fold_kernel<<<(unsigned)((src.half + 255) / 256), 256, 0, ctx->stream>>>(src, ctx->fp);
     ctx->launches++;

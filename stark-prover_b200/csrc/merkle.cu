@@ -211,6 +211,10 @@ void merkle_build(stark_ctx* ctx, const LeafSource& src, const TreeShape& shape,
         size_t threads = (n + (1 << SUB) - 1) >> SUB;
         unsigned blocks = (unsigned)((threads + MERKLE_THREADS - 1) / MERKLE_THREADS);
         int last = (unsigned)nlev == depth;
+        // algorithmic int-ops: 1384 per compression; leaf = 1, node = 2; nodes in levels 1..nlev
+        double comp = (double)n;
+        for (int l = 1; l <= nlev; l++) comp += 2.0 * (double)shape.len[l];
+        KernelTimer kt(ctx, stark_ctx::CAT_MERKLE_LEAF, 1384.0 * comp);
         if (fold) merkle_leaf_kernel<true><<<blocks, MERKLE_THREADS, 0, ctx->stream>>>(src, n, nlev, lv, ctx->fp, result, last);
         else merkle_leaf_kernel<false><<<blocks, MERKLE_THREADS, 0, ctx->stream>>>(src, n, nlev, lv, ctx->fp, result, last);
         ctx->launches++;
@@ -219,6 +223,9 @@ void merkle_build(stark_ctx* ctx, const LeafSource& src, const TreeShape& shape,
     while (cur < depth) {
         size_t cur_len = shape.len[cur];
         if (cur_len <= (size_t)TOP_MAX) {
+            double comp = 0;
+            for (unsigned l = cur + 1; l <= depth; l++) comp += 2.0 * (double)shape.len[l];
+            KernelTimer kt(ctx, stark_ctx::CAT_MERKLE_NODE, 1384.0 * comp);
             merkle_top_kernel<<<1, TOP_MAX / 2, 0, ctx->stream>>>(level_ptr(cur), (int)cur_len, level_ptr(cur + 1), result);
             ctx->launches++;
             cur = depth;
@@ -230,6 +237,9 @@ void merkle_build(stark_ctx* ctx, const LeafSource& src, const TreeShape& shape,
         size_t threads = (cur_len + (1 << SUB) - 1) >> SUB;
         unsigned blocks = (unsigned)((threads + MERKLE_THREADS - 1) / MERKLE_THREADS);
         int last = cur + (unsigned)nlev == depth;
+        double comp = 0;
+        for (int l = 1; l <= nlev; l++) comp += 2.0 * (double)shape.len[cur + l];
+        KernelTimer kt(ctx, stark_ctx::CAT_MERKLE_NODE, 1384.0 * comp);
         merkle_node_kernel<<<blocks, MERKLE_THREADS, 0, ctx->stream>>>(level_ptr(cur), cur_len, nlev, lv, result, last);
         ctx->launches++;
         cur += (unsigned)nlev;
@@ -273,6 +283,7 @@ __global__ void merkle_open_kernel(const OpenDesc* desc, size_t n_desc, uint8_t*
 void merkle_open(stark_ctx* ctx, const OpenDesc* d_desc, size_t n_desc, uint8_t* d_out) {
     if (n_desc == 0) return;
     unsigned blocks = (unsigned)((n_desc * 32 + 127) / 128);
+    KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 0);
     merkle_open_kernel<<<blocks, 128, 0, ctx->stream>>>(d_desc, n_desc, d_out);
     ctx->launches++;
     STARK_CUDA(cudaGetLastError());

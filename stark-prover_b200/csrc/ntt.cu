@@ -233,6 +233,8 @@ void ntt_dit(stark_ctx* ctx, const uint32_t* src, uint32_t* data, unsigned log_n
     const TwiddleSet& tws = ctx->twiddles(log_n);
     const size_t n = (size_t)1 << log_n;
     std::vector<unsigned> bits = plan_bits(log_n);
+    // algorithmic bytes of the whole transform at 8 B per element: read the input once, write the output once
+    KernelTimer kt(ctx, stark_ctx::CAT_NTT, 8.0 * (double)(n >> log_pad) + 8.0 * (double)n);
     unsigned lo = 0;
     for (size_t i = 0; i < bits.size(); i++) {
         unsigned r = bits[i];
@@ -265,6 +267,7 @@ void ntt_dif(stark_ctx* ctx, uint32_t* data, unsigned log_n, bool inverse_root) 
     const TwiddleSet& tws = ctx->twiddles(log_n);
     const size_t n = (size_t)1 << log_n;
     std::vector<unsigned> bits = plan_bits(log_n);
+    KernelTimer kt(ctx, stark_ctx::CAT_NTT, 16.0 * (double)n);
     unsigned hi = log_n;
     for (size_t ii = bits.size(); ii-- > 0;) {
         unsigned r = bits[ii];
@@ -303,6 +306,7 @@ void bitrev_permute(stark_ctx* ctx, const uint32_t* in, uint32_t* out, unsigned 
     size_t n = (size_t)1 << log_n;
     PowTable sc{};
     if (scale) sc = *scale;
+    KernelTimer kt(ctx, stark_ctx::CAT_NTT, 16.0 * (double)n);
     bitrev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(in, out, log_n, scale != nullptr, sc,
                                                                          scale_by_input_index, ctx->fp);
     ctx->launches++;
@@ -326,6 +330,7 @@ void build_scale_table(stark_ctx* ctx, uint64_t base, uint64_t c0, unsigned log_
     out.hi = DevBuf(n_hi * sizeof(uint32_t), ctx->stream);
     out.view = PowTable{out.lo.as<uint32_t>(), out.hi.as<uint32_t>(), shift, n_lo - 1};
     unsigned total = n_lo + n_hi;
+    KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 0);
     scale_table_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(ctx->to_mont(base), ctx->to_mont(c0), shift, n_lo, n_hi,
                                                                      out.lo.as<uint32_t>(), out.hi.as<uint32_t>(), ctx->fp);
     ctx->launches++;
