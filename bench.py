@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -255,6 +255,17 @@ def run_b200(args):
     d2h = 32 * n_layers + 8 * n_layers + len(pr.open([0])) * QUERIES
     pr.free()
 
+    # ---- where the step's wall time goes on the host side (one extra, untimed-for-the-metric step)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    chx = sp.Channel(P)
+    prx = sp.fri_commit(ctx, dev_coeffs, domain, chx)
+    t1 = time.perf_counter()
+    sp.decommit_fri(QUERIES, n - 1, prx, chx)
+    t2 = time.perf_counter()
+    prx.free()
+    host_breakdown = {"fri_commit_ms": (t1 - t0) * 1e3, "decommit_fri_ms": (t2 - t1) * 1e3}
+
     # ---- end to end: pinned host coefficients through the host-buffer ABI
     timed(pinned_np, 1)
     ms_e2e, pr2, ch2 = timed(pinned_np, args.steps)
@@ -271,7 +282,8 @@ def run_b200(args):
                        "prove_ms": ms_dev},
             "e2e": {"value": world * n / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": 8 << log_deg, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "clocks": clocks, "transcript_state": final_state}
+            "gpu_launches": int(launches), "clocks": clocks, "transcript_state": final_state,
+            "host_breakdown_ms": host_breakdown}
 
     if rank == 0:
         # ---- per-kernel durations, live, CUDA events on the launching stream (separate instrumented steps)

@@ -120,6 +120,7 @@ extern "C" void stark_ctx_destroy(stark_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (int c = 0; c < stark_ctx::CAT_COUNT; c++) for (auto& pr : ctx->ev_used[c]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto e : ctx->ev_free) cudaEventDestroy(e);
+    ctx->pin_desc.release(); ctx->pin_out.release();
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -476,11 +477,13 @@ extern "C" size_t stark_merkle_depth(const stark_tree* t) { return t ? t->shape.
 // One launch for a batch of (tree, idx) records; records are BE8(value) || path.
 static void open_records(stark_ctx* ctx, const std::vector<OpenDesc>& descs, size_t total_bytes, uint8_t* host_out) {
     if (descs.empty()) return;
-    DevBuf d_desc(descs.size() * sizeof(OpenDesc), ctx->stream), d_out(total_bytes, ctx->stream);
-    STARK_CUDA(cudaMemcpyAsync(d_desc.p, descs.data(), descs.size() * sizeof(OpenDesc), cudaMemcpyHostToDevice, ctx->stream));
-    merkle_open(ctx, d_desc.as<OpenDesc>(), descs.size(), d_out.as<uint8_t>());
-    STARK_CUDA(cudaMemcpyAsync(host_out, d_out.p, total_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    STARK_CUDA(cudaStreamSynchronize(ctx->stream));      // the pinned buffers may still be in use by an earlier launch
+    ctx->pin_desc.ensure(descs.size() * sizeof(OpenDesc));
+    ctx->pin_out.ensure(total_bytes);
+    memcpy(ctx->pin_desc.h, descs.data(), descs.size() * sizeof(OpenDesc));
+    merkle_open(ctx, static_cast<const OpenDesc*>(ctx->pin_desc.d), descs.size(), static_cast<uint8_t*>(ctx->pin_out.d));
     STARK_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(host_out, ctx->pin_out.h, total_bytes);
 }
 extern "C" int stark_merkle_open(const stark_tree* t, size_t idx, uint8_t* path, size_t cap, size_t* path_len) {
     API_BEGIN

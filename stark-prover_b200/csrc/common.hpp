@@ -68,6 +68,27 @@ struct TwiddleSet {
     PowTable inv() const { return PowTable{inv_lo.as<uint32_t>(), inv_hi.as<uint32_t>(), shift, mask}; }
 };
 
+// Growable pinned, device-mapped host buffer: kernels read descriptors from / write small results to it
+// directly over PCIe, so a query opening costs one launch and one stream sync, no copy calls.
+struct PinnedBuf {
+    void* h = nullptr;
+    void* d = nullptr;
+    size_t cap = 0;
+    void ensure(size_t n) {
+        if (n <= cap) return;
+        release();
+        size_t c = 1 << 16;
+        while (c < n) c <<= 1;
+        STARK_CUDA(cudaHostAlloc(&h, c, cudaHostAllocMapped));
+        STARK_CUDA(cudaHostGetDevicePointer(&d, h, 0));
+        cap = c;
+    }
+    void release() {
+        if (h) cudaFreeHost(h);
+        h = d = nullptr; cap = 0;
+    }
+};
+
 // What the host reads after each commit without issuing a copy (mapped pinned memory).
 struct HostResult {
     uint32_t root[8];
@@ -109,6 +130,7 @@ struct stark_ctx {
     std::map<unsigned, std::unique_ptr<starkb200::TwiddleSet>> tw;
     starkb200::HostResult* h_result = nullptr;  // pinned + mapped
     starkb200::HostResult* d_result = nullptr;  // device alias of h_result
+    starkb200::PinnedBuf pin_desc, pin_out;     // opening descriptors in, opening records out
     int sm_count = 148;
     unsigned long long launches = 0;            // kernels launched through this context
 

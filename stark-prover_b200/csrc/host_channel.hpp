@@ -7,6 +7,10 @@
 
 #include <string>
 #include <vector>
+#if defined(__x86_64__)
+#include <cpuid.h>
+#include <immintrin.h>
+#endif
 
 namespace starkb200 {
 
@@ -16,7 +20,8 @@ class HostSha256 {
     static void digest(const uint8_t* msg, size_t len, uint8_t out[32]) {
         uint32_t st[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
         size_t off = 0;
-        for (; off + 64 <= len; off += 64) block(st, msg + off);
+        const bool ni = have_sha_ni();
+        for (; off + 64 <= len; off += 64) ni ? block_ni(st, msg + off) : block(st, msg + off);
         uint8_t tail[128];
         size_t r = len - off;
         memset(tail, 0, sizeof tail);
@@ -25,8 +30,8 @@ class HostSha256 {
         size_t tl = (r + 9 <= 64) ? 64 : 128;
         uint64_t bits = (uint64_t)len * 8;
         for (int i = 0; i < 8; i++) tail[tl - 1 - i] = (uint8_t)(bits >> (8 * i));
-        block(st, tail);
-        if (tl == 128) block(st, tail + 64);
+        ni ? block_ni(st, tail) : block(st, tail);
+        if (tl == 128) ni ? block_ni(st, tail + 64) : block(st, tail + 64);
         for (int i = 0; i < 8; i++) {
             out[4 * i] = (uint8_t)(st[i] >> 24); out[4 * i + 1] = (uint8_t)(st[i] >> 16);
             out[4 * i + 2] = (uint8_t)(st[i] >> 8); out[4 * i + 3] = (uint8_t)st[i];
@@ -45,6 +50,68 @@ class HostSha256 {
     }
 
   private:
+    // The transcript hashes ~40 KB of hex text per query; like sha2 0.10.8 in the reference, use the x86 SHA
+    // extensions when the CPU has them (checked once against the portable rounds).
+    static bool have_sha_ni() {
+#if defined(__x86_64__)
+        static const bool ok = [] {
+            unsigned a, b, c, d;
+            if (!__get_cpuid_count(7, 0, &a, &b, &c, &d) || !((b >> 29) & 1)) return false;
+            uint8_t blk[64];
+            for (int i = 0; i < 64; i++) blk[i] = (uint8_t)(i * 29 + 5);
+            uint32_t x[8] = {1, 2, 3, 4, 5, 6, 7, 8}, y[8] = {1, 2, 3, 4, 5, 6, 7, 8};
+            block(x, blk); block_ni(y, blk);
+            return memcmp(x, y, 32) == 0;
+        }();
+        return ok;
+#else
+        return false;
+#endif
+    }
+#if defined(__x86_64__)
+    __attribute__((target("sha,sse4.1,ssse3"))) static void block_ni(uint32_t st[8], const uint8_t* p) {
+        static const uint32_t K[64] = {
+            0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
+            0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
+            0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
+            0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
+            0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+            0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
+            0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
+            0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+        const __m128i MASK = _mm_set_epi64x(0x0c0d0e0f08090a0bULL, 0x0405060700010203ULL);
+        __m128i TMP = _mm_loadu_si128((const __m128i*)&st[0]);
+        __m128i S1 = _mm_loadu_si128((const __m128i*)&st[4]);
+        TMP = _mm_shuffle_epi32(TMP, 0xB1);
+        S1 = _mm_shuffle_epi32(S1, 0x1B);
+        __m128i S0 = _mm_alignr_epi8(TMP, S1, 8);
+        S1 = _mm_blend_epi16(S1, TMP, 0xF0);
+        const __m128i S0_SAVE = S0, S1_SAVE = S1;
+        __m128i M[4];
+        for (int i = 0; i < 4; i++) M[i] = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i*)(p + 16 * i)), MASK);
+        for (int r = 0; r < 16; r++) {
+            __m128i MSG = _mm_add_epi32(M[r & 3], _mm_loadu_si128((const __m128i*)&K[4 * r]));
+            S1 = _mm_sha256rnds2_epu32(S1, S0, MSG);
+            if (r >= 3 && r < 15) {
+                __m128i T = _mm_alignr_epi8(M[r & 3], M[(r + 3) & 3], 4);
+                M[(r + 1) & 3] = _mm_sha256msg2_epu32(_mm_add_epi32(M[(r + 1) & 3], T), M[r & 3]);
+            }
+            MSG = _mm_shuffle_epi32(MSG, 0x0E);
+            S0 = _mm_sha256rnds2_epu32(S0, S1, MSG);
+            if (r >= 1 && r < 13) M[(r + 3) & 3] = _mm_sha256msg1_epu32(M[(r + 3) & 3], M[r & 3]);
+        }
+        S0 = _mm_add_epi32(S0, S0_SAVE);
+        S1 = _mm_add_epi32(S1, S1_SAVE);
+        TMP = _mm_shuffle_epi32(S0, 0x1B);
+        S1 = _mm_shuffle_epi32(S1, 0xB1);
+        S0 = _mm_blend_epi16(TMP, S1, 0xF0);
+        S1 = _mm_alignr_epi8(S1, TMP, 8);
+        _mm_storeu_si128((__m128i*)&st[0], S0);
+        _mm_storeu_si128((__m128i*)&st[4], S1);
+    }
+#else
+    static void block_ni(uint32_t st[8], const uint8_t* p) { block(st, p); }
+#endif
     static uint32_t ror(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
     static void block(uint32_t st[8], const uint8_t* p) {
         static const uint32_t K[64] = {
@@ -84,11 +151,17 @@ struct Channel {
     std::vector<std::vector<uint8_t>> compressed_proof;   // :17
     std::string state;                                     // :19, "" initially (:24-30)
     uint64_t modulus;
+    std::string scratch;
 
     explicit Channel(uint64_t m) : modulus(m) {}
 
     void send(const uint8_t* msg, size_t len) {            // :35-44
-        state = HostSha256::hex_digest(state + HostSha256::hex(msg, len));
+        static const char* dg = "0123456789abcdef";
+        scratch.resize(state.size() + 2 * len);
+        memcpy(&scratch[0], state.data(), state.size());
+        char* o = &scratch[state.size()];
+        for (size_t i = 0; i < len; i++) { o[2 * i] = dg[msg[i] >> 4]; o[2 * i + 1] = dg[msg[i] & 15]; }
+        state = HostSha256::hex_digest(scratch);           // sha256::digest(old_state + hex::encode(message))
         proof.emplace_back(msg, msg + len);
         compressed_proof.emplace_back(msg, msg + len);
     }

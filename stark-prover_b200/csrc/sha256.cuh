@@ -52,44 +52,60 @@ __device__ __forceinline__ uint32_t maj(uint32_t a, uint32_t b, uint32_t c) { re
         (h) = t1 + t2;                                              \
     }
 
-// One compression of state `st` with the 16 message words in `w` (clobbered).
+// Round constants live in the constant bank: with a compile-time index they are instruction operands, with
+// the loop index of the rolled rounds they are uniform-datapath loads (the index is warp-uniform), so they
+// cost no ALU-pipe slot either way.
+static __constant__ uint32_t c_sha_k[64] = STARK_SHA_K;
+static __constant__ uint32_t c_sha_kw_pad64[64] = STARK_SHA_KW_PAD64;
+
+#define STARK_SHA_8ROUNDS(a, b, c, d, e, f, g, h, KW)                 \
+    STARK_SHA_ROUND(a, b, c, d, e, f, g, h, KW(0));                   \
+    STARK_SHA_ROUND(h, a, b, c, d, e, f, g, KW(1));                   \
+    STARK_SHA_ROUND(g, h, a, b, c, d, e, f, KW(2));                   \
+    STARK_SHA_ROUND(f, g, h, a, b, c, d, e, KW(3));                   \
+    STARK_SHA_ROUND(e, f, g, h, a, b, c, d, KW(4));                   \
+    STARK_SHA_ROUND(d, e, f, g, h, a, b, c, KW(5));                   \
+    STARK_SHA_ROUND(c, d, e, f, g, h, a, b, KW(6));                   \
+    STARK_SHA_ROUND(b, c, d, e, f, g, h, a, KW(7));
+
+// One compression of state `st` with the 16 message words in `w` (clobbered).  The 64 rounds are rolled
+// into 4 iterations of 16 (the a..h rotation and the w[] window both close after 16 rounds), so one
+// compression is ~600 instructions of code instead of ~1400: a thread that reduces a whole subtree
+// (22 compressions) otherwise streams half a megabyte of straight-line code through the instruction cache.
 __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16]) {
-    constexpr uint32_t K[64] = STARK_SHA_K;
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#define KW_A(j) (c_sha_k[j] + w[j])
+#define KW_B(j) (c_sha_k[8 + j] + w[8 + j])
+    STARK_SHA_8ROUNDS(a, b, c, d, e, f, g, h, KW_A)
+    STARK_SHA_8ROUNDS(a, b, c, d, e, f, g, h, KW_B)
+#undef KW_A
+#undef KW_B
+#pragma unroll 1
+    for (int i = 16; i < 64; i += 16) {
 #pragma unroll
-    for (int i = 0; i < 64; i += 8) {
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int t = i + j;
-            if (t >= 16)
-                w[t & 15] += sml_s0(w[(t + 1) & 15]) + w[(t + 9) & 15] + sml_s1(w[(t + 14) & 15]);
-        }
-        STARK_SHA_ROUND(a, b, c, d, e, f, g, h, K[i + 0] + w[(i + 0) & 15]);
-        STARK_SHA_ROUND(h, a, b, c, d, e, f, g, K[i + 1] + w[(i + 1) & 15]);
-        STARK_SHA_ROUND(g, h, a, b, c, d, e, f, K[i + 2] + w[(i + 2) & 15]);
-        STARK_SHA_ROUND(f, g, h, a, b, c, d, e, K[i + 3] + w[(i + 3) & 15]);
-        STARK_SHA_ROUND(e, f, g, h, a, b, c, d, K[i + 4] + w[(i + 4) & 15]);
-        STARK_SHA_ROUND(d, e, f, g, h, a, b, c, K[i + 5] + w[(i + 5) & 15]);
-        STARK_SHA_ROUND(c, d, e, f, g, h, a, b, K[i + 6] + w[(i + 6) & 15]);
-        STARK_SHA_ROUND(b, c, d, e, f, g, h, a, K[i + 7] + w[(i + 7) & 15]);
+        for (int j = 0; j < 16; j++)
+            w[j] += sml_s0(w[(j + 1) & 15]) + w[(j + 9) & 15] + sml_s1(w[(j + 14) & 15]);
+#define KW_A(j) (c_sha_k[i + j] + w[j])
+#define KW_B(j) (c_sha_k[i + 8 + j] + w[8 + j])
+        STARK_SHA_8ROUNDS(a, b, c, d, e, f, g, h, KW_A)
+        STARK_SHA_8ROUNDS(a, b, c, d, e, f, g, h, KW_B)
+#undef KW_A
+#undef KW_B
     }
     st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
 }
 
-// Compression with the constant padding block of a 64-byte message: no schedule, K+W are immediates.
+// Compression with the constant padding block of a 64-byte message: no schedule, K+W precomputed.
 __device__ __forceinline__ void sha256_compress_pad64(uint32_t st[8]) {
-    constexpr uint32_t KW[64] = STARK_SHA_KW_PAD64;
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
-#pragma unroll
-    for (int i = 0; i < 64; i += 8) {
-        STARK_SHA_ROUND(a, b, c, d, e, f, g, h, KW[i + 0]);
-        STARK_SHA_ROUND(h, a, b, c, d, e, f, g, KW[i + 1]);
-        STARK_SHA_ROUND(g, h, a, b, c, d, e, f, KW[i + 2]);
-        STARK_SHA_ROUND(f, g, h, a, b, c, d, e, KW[i + 3]);
-        STARK_SHA_ROUND(e, f, g, h, a, b, c, d, KW[i + 4]);
-        STARK_SHA_ROUND(d, e, f, g, h, a, b, c, KW[i + 5]);
-        STARK_SHA_ROUND(c, d, e, f, g, h, a, b, KW[i + 6]);
-        STARK_SHA_ROUND(b, c, d, e, f, g, h, a, KW[i + 7]);
+#pragma unroll 1
+    for (int i = 0; i < 64; i += 16) {
+#define KW_A(j) (c_sha_kw_pad64[i + j])
+#define KW_B(j) (c_sha_kw_pad64[i + 8 + j])
+        STARK_SHA_8ROUNDS(a, b, c, d, e, f, g, h, KW_A)
+        STARK_SHA_8ROUNDS(a, b, c, d, e, f, g, h, KW_B)
+#undef KW_A
+#undef KW_B
     }
     st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
 }
