@@ -228,7 +228,7 @@ def run_b200(args):
             e1.record(stream)
             torch.cuda.synchronize()
             total += e0.elapsed_time(e1)
-        ms = total / steps
+        ms = total / max(steps, 1)
         if world > 1:
             t = torch.tensor([ms], device=f"cuda:{local}")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

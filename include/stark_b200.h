@@ -138,6 +138,8 @@ size_t stark_channel_compressed_proof_size(const stark_channel* ch);            
 const char* stark_channel_state(const stark_channel* ch);
 size_t stark_channel_proof_len(const stark_channel* ch);
 size_t stark_channel_proof_msg(const stark_channel* ch, size_t i, const uint8_t** data);
+size_t stark_channel_compressed_len(const stark_channel* ch);
+size_t stark_channel_compressed_msg(const stark_channel* ch, size_t i, const uint8_t** data);
 /* all proof messages as  u32-LE length || bytes  records; returns total size (out may be NULL) */
 size_t stark_channel_proof_flat(const stark_channel* ch, uint8_t* out);
 

@@ -108,6 +108,8 @@ def lib() -> C.CDLL:
     sig("stark_channel_proof_len", szt, vp)
     sig("stark_channel_proof_msg", szt, vp, szt, C.POINTER(u8p))
     sig("stark_channel_proof_flat", szt, vp, vp)
+    sig("stark_channel_compressed_len", szt, vp)
+    sig("stark_channel_compressed_msg", szt, vp, szt, C.POINTER(u8p))
     sig("stark_fri_begin", I, vp, vp, szt, C.c_uint, u64, C.POINTER(vp), vp)
     sig("stark_fri_begin_dev", I, vp, vp, C.c_uint, u64, C.POINTER(vp), vp)
     sig("stark_fri_degree", I, vp, C.POINTER(C.c_longlong))
@@ -403,6 +405,15 @@ class Channel:
         for i in range(lib().stark_channel_proof_len(self.h)):
             p = u8p()
             n = lib().stark_channel_proof_msg(self.h, i, C.byref(p))
+            out.append(bytes(C.cast(p, C.POINTER(C.c_uint8 * n)).contents) if n else b"")
+        return out
+
+    @property
+    def compressed_proof(self) -> list[bytes]:
+        out = []
+        for i in range(lib().stark_channel_compressed_len(self.h)):
+            p = u8p()
+            n = lib().stark_channel_compressed_msg(self.h, i, C.byref(p))
             out.append(bytes(C.cast(p, C.POINTER(C.c_uint8 * n)).contents) if n else b"")
         return out
 

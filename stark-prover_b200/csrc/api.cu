@@ -553,6 +553,13 @@ extern "C" size_t stark_channel_proof_msg(const stark_channel* ch, size_t i, con
     if (data) *data = ch->ch.proof[i].data();
     return ch->ch.proof[i].size();
 }
+extern "C" size_t stark_channel_compressed_len(const stark_channel* ch) { return ch ? ch->ch.compressed_idx.size() : 0; }
+extern "C" size_t stark_channel_compressed_msg(const stark_channel* ch, size_t i, const uint8_t** data) {
+    if (!ch || i >= ch->ch.compressed_idx.size()) return 0;
+    const auto& m = ch->ch.compressed_msg(i);
+    if (data) *data = m.data();
+    return m.size();
+}
 extern "C" size_t stark_channel_proof_flat(const stark_channel* ch, uint8_t* out) {
     if (!ch) return 0;
     size_t w = 0;

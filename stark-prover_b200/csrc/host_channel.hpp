@@ -37,6 +37,51 @@ class HostSha256 {
             out[4 * i + 2] = (uint8_t)(st[i] >> 8); out[4 * i + 3] = (uint8_t)st[i];
         }
     }
+    // Streaming form used by Channel::send: H(state || hex(msg)) without materialising the concatenation.
+    struct Stream {
+        uint32_t st[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+        uint8_t buf[64];
+        size_t fill = 0;
+        uint64_t total = 0;
+        bool ni = have_sha_ni();
+        void blocks(const uint8_t* p, size_t nblk) {
+            if (ni) for (size_t i = 0; i < nblk; i++) block_ni(st, p + 64 * i);
+            else for (size_t i = 0; i < nblk; i++) block(st, p + 64 * i);
+        }
+        void update(const uint8_t* p, size_t n) {
+            total += n;
+            if (fill) {
+                size_t take = 64 - fill < n ? 64 - fill : n;
+                memcpy(buf + fill, p, take); fill += take; p += take; n -= take;
+                if (fill == 64) { blocks(buf, 1); fill = 0; }
+            }
+            if (n >= 64) { blocks(p, n / 64); p += (n / 64) * 64; n %= 64; }
+            if (n) { memcpy(buf, p, n); fill = n; }
+        }
+        void finish(uint8_t out[32]) {
+            uint8_t tail[128];
+            memset(tail, 0, sizeof tail);
+            memcpy(tail, buf, fill);
+            tail[fill] = 0x80;
+            size_t tl = (fill + 9 <= 64) ? 64 : 128;
+            uint64_t bits = total * 8;
+            for (int i = 0; i < 8; i++) tail[tl - 1 - i] = (uint8_t)(bits >> (8 * i));
+            blocks(tail, tl / 64);
+            for (int i = 0; i < 8; i++) {
+                out[4 * i] = (uint8_t)(st[i] >> 24); out[4 * i + 1] = (uint8_t)(st[i] >> 16);
+                out[4 * i + 2] = (uint8_t)(st[i] >> 8); out[4 * i + 3] = (uint8_t)st[i];
+            }
+        }
+    };
+    // lowercase hex of n bytes into out[2n] (no terminator); 16 bytes per step with SSSE3 when available
+    static void hex_into(const uint8_t* b, size_t n, char* out) {
+        size_t i = 0;
+#if defined(__x86_64__)
+        if (have_ssse3()) i = hex_ssse3(b, n, out);
+#endif
+        static const char* d = "0123456789abcdef";
+        for (; i < n; i++) { out[2 * i] = d[b[i] >> 4]; out[2 * i + 1] = d[b[i] & 15]; }
+    }
     static std::string hex(const uint8_t* b, size_t n) {       // lowercase, like const-hex / rs_merkle root_hex
         static const char* d = "0123456789abcdef";
         std::string s(2 * n, '0');
@@ -50,6 +95,25 @@ class HostSha256 {
     }
 
   private:
+#if defined(__x86_64__)
+    static bool have_ssse3() {
+        static const bool ok = [] { unsigned a, b, c, d; return __get_cpuid(1, &a, &b, &c, &d) && ((c >> 9) & 1); }();
+        return ok;
+    }
+    __attribute__((target("ssse3"))) static size_t hex_ssse3(const uint8_t* b, size_t n, char* out) {
+        const __m128i lut = _mm_setr_epi8('0', '1', '2', '3', '4', '5', '6', '7', '8', '9', 'a', 'b', 'c', 'd', 'e', 'f');
+        const __m128i m4 = _mm_set1_epi8(0x0f);
+        size_t i = 0;
+        for (; i + 16 <= n; i += 16) {
+            __m128i v = _mm_loadu_si128((const __m128i*)(b + i));
+            __m128i hi = _mm_shuffle_epi8(lut, _mm_and_si128(_mm_srli_epi16(v, 4), m4));
+            __m128i lo = _mm_shuffle_epi8(lut, _mm_and_si128(v, m4));
+            _mm_storeu_si128((__m128i*)(out + 2 * i), _mm_unpacklo_epi8(hi, lo));
+            _mm_storeu_si128((__m128i*)(out + 2 * i + 16), _mm_unpackhi_epi8(hi, lo));
+        }
+        return i;
+    }
+#endif
     // The transcript hashes ~40 KB of hex text per query; like sha2 0.10.8 in the reference, use the x86 SHA
     // extensions when the CPU has them (checked once against the portable rounds).
     static bool have_sha_ni() {
@@ -89,6 +153,7 @@ class HostSha256 {
         const __m128i S0_SAVE = S0, S1_SAVE = S1;
         __m128i M[4];
         for (int i = 0; i < 4; i++) M[i] = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i*)(p + 16 * i)), MASK);
+#pragma GCC unroll 16
         for (int r = 0; r < 16; r++) {
             __m128i MSG = _mm_add_epi32(M[r & 3], _mm_loadu_si128((const __m128i*)&K[4 * r]));
             S1 = _mm_sha256rnds2_epu32(S1, S0, MSG);
@@ -148,22 +213,28 @@ inline void be8(uint64_t v, uint8_t out[8]) {            // FieldElement::to_byt
 // Channel<MODULUS> — channel.rs:14-95, field for field.
 struct Channel {
     std::vector<std::vector<uint8_t>> proof;              // :16
-    std::vector<std::vector<uint8_t>> compressed_proof;   // :17
+    std::vector<size_t> compressed_idx;                    // :17 compressed_proof: the same bytes as proof[i], stored once
     std::string state;                                     // :19, "" initially (:24-30)
     uint64_t modulus;
-    std::string scratch;
 
     explicit Channel(uint64_t m) : modulus(m) {}
 
     void send(const uint8_t* msg, size_t len) {            // :35-44
-        static const char* dg = "0123456789abcdef";
-        scratch.resize(state.size() + 2 * len);
-        memcpy(&scratch[0], state.data(), state.size());
-        char* o = &scratch[state.size()];
-        for (size_t i = 0; i < len; i++) { o[2 * i] = dg[msg[i] >> 4]; o[2 * i + 1] = dg[msg[i] & 15]; }
-        state = HostSha256::hex_digest(scratch);           // sha256::digest(old_state + hex::encode(message))
+        // state = sha256::digest(old_state + hex::encode(message)), streamed in 2 KB pieces of hex text
+        HostSha256::Stream h;
+        h.update(reinterpret_cast<const uint8_t*>(state.data()), state.size());
+        char hx[2048];
+        for (size_t off = 0; off < len; off += 1024) {
+            size_t take = len - off < 1024 ? len - off : 1024;
+            HostSha256::hex_into(msg + off, take, hx);
+            h.update(reinterpret_cast<const uint8_t*>(hx), 2 * take);
+        }
+        uint8_t dg[32];
+        h.finish(dg);
+        state.resize(64);
+        HostSha256::hex_into(dg, 32, &state[0]);
         proof.emplace_back(msg, msg + len);
-        compressed_proof.emplace_back(msg, msg + len);
+        compressed_idx.push_back(proof.size() - 1);      // compressed_proof.push(message.to_vec()), kept as an index
     }
     // :58-84.  Returns false where the reference would panic ("Channel state is not valid hex" on "").
     bool receive_random_int(uint64_t min, uint64_t max, bool show_in_proof, uint64_t* out) {
@@ -191,7 +262,8 @@ struct Channel {
         return true;
     }
     size_t proof_size() const { size_t s = 0; for (auto& m : proof) s += m.size(); return s; }                       // :88-90
-    size_t compressed_proof_size() const { size_t s = 0; for (auto& m : compressed_proof) s += m.size(); return s; } // :93-95
+    size_t compressed_proof_size() const { size_t s = 0; for (size_t i : compressed_idx) s += proof[i].size(); return s; } // :93-95
+    const std::vector<uint8_t>& compressed_msg(size_t k) const { return proof[compressed_idx[k]]; }
 };
 
 }  // namespace starkb200

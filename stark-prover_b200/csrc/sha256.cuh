@@ -44,12 +44,33 @@ __device__ __forceinline__ uint32_t maj(uint32_t a, uint32_t b, uint32_t c) { re
       0x83613bdau,0xdb48a363u,0x0b02e931u,0x6fd15ca7u,0x521afacau,0x31338431u,0x6ed41a95u,0x6d437890u,      \
       0xc39c91f2u,0x9eccabbdu,0xb5c9a0e6u,0x532fb63cu,0xd2c741c6u,0x07237ea3u,0xa4954b68u,0x4c191d76u }
 
-#define STARK_SHA_ROUND(a, b, c, d, e, f, g, h, kw)                 \
-    {                                                               \
-        uint32_t t1 = (h) + big_s1(e) + ch(e, f, g) + (kw);         \
-        uint32_t t2 = big_s0(a) + maj(a, b, c);                     \
-        (d) += t1;                                                  \
-        (h) = t1 + t2;                                              \
+// Pipe balancing.  Rotates and boolean functions (SHF, LOP3) can only issue on the ALU pipe, which
+// retires one warp instruction every 2 cycles per SM sub-partition and is what bounds this kernel.  Integer
+// adds can also run on the FMA pipe as IMAD (x * 1 + y).  `c_sha_one` is a 1 the compiler cannot see
+// through (constant memory), so every add below becomes an IMAD and the ALU pipe is left with the
+// 10 (round) + 8 (schedule) instructions that have no other home.
+static __constant__ uint32_t c_sha_one = 1;
+#ifndef STARK_SHA_ADDS_ON_FMA
+#define STARK_SHA_ADDS_ON_FMA 1
+#endif
+#if STARK_SHA_ADDS_ON_FMA
+#define SHA_ADD(x, y) ((x) * sha_one + (y))
+#else
+#define SHA_ADD(x, y) ((x) + (y))
+#endif
+
+// Operand order keeps the per-round dependency chain short: h + kw is known a round early, Ch needs one
+// LOP3 after the new e, Sigma1 two dependent ALU ops, so the new e is 4 dependent instructions after the old
+// one (SHF, LOP3, add, add) and the new a likewise.  Latency-bound launches (the top of every tree) run
+// one warp per scheduler, so this chain is their speed.
+#define STARK_SHA_ROUND(a, b, c, d, e, f, g, h, kw)                                        \
+    {                                                                                      \
+        uint32_t t0 = SHA_ADD((h), (kw));                                                  \
+        t0 = SHA_ADD(t0, ch(e, f, g));                                                     \
+        uint32_t t1 = SHA_ADD(t0, big_s1(e));                                              \
+        (d) = SHA_ADD((d), t1);                                                            \
+        t1 = SHA_ADD(t1, maj(a, b, c));                                                    \
+        (h) = SHA_ADD(t1, big_s0(a));                                                      \
     }
 
 // Round constants live in the constant bank: with a compile-time index they are instruction operands, with
@@ -73,9 +94,10 @@ static __constant__ uint32_t c_sha_kw_pad64[64] = STARK_SHA_KW_PAD64;
 // compression is ~600 instructions of code instead of ~1400: a thread that reduces a whole subtree
 // (22 compressions) otherwise streams half a megabyte of straight-line code through the instruction cache.
 __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16]) {
+    const uint32_t sha_one = c_sha_one; (void)sha_one;
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
-#define KW_A(j) (c_sha_k[j] + w[j])
-#define KW_B(j) (c_sha_k[8 + j] + w[8 + j])
+#define KW_A(j) SHA_ADD(w[j], c_sha_k[j])
+#define KW_B(j) SHA_ADD(w[8 + j], c_sha_k[8 + j])
     STARK_SHA_8ROUNDS(a, b, c, d, e, f, g, h, KW_A)
     STARK_SHA_8ROUNDS(a, b, c, d, e, f, g, h, KW_B)
 #undef KW_A
@@ -84,19 +106,21 @@ __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16]) 
     for (int i = 16; i < 64; i += 16) {
 #pragma unroll
         for (int j = 0; j < 16; j++)
-            w[j] += sml_s0(w[(j + 1) & 15]) + w[(j + 9) & 15] + sml_s1(w[(j + 14) & 15]);
-#define KW_A(j) (c_sha_k[i + j] + w[j])
-#define KW_B(j) (c_sha_k[i + 8 + j] + w[8 + j])
+            w[j] = SHA_ADD(SHA_ADD(SHA_ADD(w[j], sml_s0(w[(j + 1) & 15])), w[(j + 9) & 15]), sml_s1(w[(j + 14) & 15]));
+#define KW_A(j) SHA_ADD(w[j], c_sha_k[i + j])
+#define KW_B(j) SHA_ADD(w[8 + j], c_sha_k[i + 8 + j])
         STARK_SHA_8ROUNDS(a, b, c, d, e, f, g, h, KW_A)
         STARK_SHA_8ROUNDS(a, b, c, d, e, f, g, h, KW_B)
 #undef KW_A
 #undef KW_B
     }
-    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+    st[0] = SHA_ADD(st[0], a); st[1] = SHA_ADD(st[1], b); st[2] = SHA_ADD(st[2], c); st[3] = SHA_ADD(st[3], d);
+    st[4] = SHA_ADD(st[4], e); st[5] = SHA_ADD(st[5], f); st[6] = SHA_ADD(st[6], g); st[7] = SHA_ADD(st[7], h);
 }
 
 // Compression with the constant padding block of a 64-byte message: no schedule, K+W precomputed.
 __device__ __forceinline__ void sha256_compress_pad64(uint32_t st[8]) {
+    const uint32_t sha_one = c_sha_one; (void)sha_one;
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
 #pragma unroll 1
     for (int i = 0; i < 64; i += 16) {

@@ -85,6 +85,7 @@ def test_host_channel_matches_oracle(sp, orc, golden):
             assert a.receive_random_int(step, step * step + 9, step % 2 == 1) == b.receive_random_int(step, step * step + 9, step % 2 == 1)
         assert a.state == b.state
     assert a.proof == b.proof and a.proof_flat() == b.proof_flat()
+    assert a.compressed_proof == b.compressed_proof
 
 
 def test_channel_receive_before_send_is_error(sp):
