@@ -53,18 +53,19 @@ def parse():
 
 # ------------------------------------------------------------------------------------------- helpers
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md).
+    The sampler runs from before the warm-up; only rows stamped inside [mark_start, mark_stop] are used."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device: int):
-        self.device, self.rows, self.proc = device, [], None
+        self.device, self.rows, self.proc, self.t0, self.t1 = device, [], None, None, None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "10", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -72,18 +73,24 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_start(self): self.t0 = time.time()
+    def mark_stop(self): self.t1 = time.time()
 
     def stop(self) -> dict:
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
         sm, smax, reasons, pw = [], None, set(), []
-        for r in self.rows:
+        for ts, r in self.rows:
+            if self.t0 is not None and not (self.t0 - 0.02 <= ts <= (self.t1 or ts) + 0.05):
+                continue
             try:
                 sm.append(float(r[1])); smax = float(r[2]); pw.append(float(r[3]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
@@ -92,9 +99,8 @@ class ClockSampler:
             except Exception:
                 pass
         sm.sort()
-        busy = [x for x in sm if smax and x > 0.5 * smax] or sm
-        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "power_w_max": max(pw) if pw else None, "samples": len(sm)}
 
 
 def measured_peaks() -> tuple[float, str]:
@@ -243,11 +249,13 @@ def run_b200(args):
         ctx.close()
         return
     # ---- warm-up, then the device-resident timed region
-    timed(dev_coeffs, max(args.warmup, 3))
     sampler = ClockSampler(local)
     sampler.start()
+    timed(dev_coeffs, max(args.warmup, 3))
     l0 = ctx.launch_count
+    sampler.mark_start()
     ms_dev, pr, ch = timed(dev_coeffs, args.steps)
+    sampler.mark_stop()
     launches = (ctx.launch_count - l0) // args.steps
     clocks = sampler.stop()
     final_state = ch.state

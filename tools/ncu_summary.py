@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Summarise ncu artefacts into profiles/ (tracked).  No GPU needed: reads what gpurun brought back.
+
+  python tools/ncu_summary.py launches gpurun_out/launches_r1d.csv profiles/r01_launches.md
+  python tools/ncu_summary.py full gpurun_out/prof_merkle_r1c.ncu-rep profiles/r01_merkle_full.md
+"""
+import collections
+import csv
+import io
+import re
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__occupancy_limit_registers",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.sum", "sm__inst_executed_pipe_fma.sum", "smsp__inst_executed.sum",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__sass_inst_executed_op_shared_ld.sum"]
+
+
+def short(name: str) -> str:
+    return re.sub(r"\(.*", "", name).replace("void ", "").replace("starkb200::", "")
+
+
+def launches(src, dst):
+    lines = [l for l in open(src) if not l.startswith("==")]
+    rows = list(csv.DictReader(lines))
+    half = len(rows) // 2           # --profile-mode runs 1 warm-up step + 1 step: keep the second
+    step = rows[half:]
+    agg, tot = collections.OrderedDict(), 0.0
+    for r in step:
+        t = float(r["Metric Value"].replace(",", "")) / 1e3
+        a = agg.setdefault(short(r["Kernel Name"]), [0, 0.0])
+        a[0] += 1; a[1] += t; tot += t
+    with open(dst, "w") as f:
+        f.write(f"# ncu launch list ({src}): one step of `bench.py --profile-mode --steps 1 --warmup 1`\n\n")
+        f.write("`ncu --metrics gpu__time_duration.sum --clock-control none`; per-launch times are cold-cache and serialised,\n"
+                "so compare SHARES with the live CUDA-event numbers in the bench JSON, not absolutes.\n\n")
+        f.write("| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| `{k}` | {v[0]} | {v[1]:.1f} | {v[1] / tot:.3f} |\n")
+        f.write(f"| **all** | {len(step)} | {tot:.1f} | 1.000 |\n\n## launches of the step, in order\n\n| # | kernel | grid | block | us |\n|---:|---|---|---|---:|\n")
+        for i, r in enumerate(step):
+            f.write(f"| {i} | `{short(r['Kernel Name'])}` | {r['Grid Size']} | {r['Block Size']} | {float(r['Metric Value'].replace(',', '')) / 1e3:.1f} |\n")
+    print("wrote", dst)
+
+
+def full(src, dst):
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    with open(dst, "w") as f:
+        f.write(f"# ncu --set full summary ({src})\n\n`ncu --set full --clock-control none --import-source on`; raw page, selected metrics.\n")
+        for r in rows[2:]:
+            f.write(f"\n## `{short(r[hdr.index('Kernel Name')])}` grid {r[hdr.index('Grid Size')]} block {r[hdr.index('Block Size')]}\n\n| metric | value | unit |\n|---|---:|---|\n")
+            for k in KEYS:
+                if k in hdr:
+                    i = hdr.index(k)
+                    f.write(f"| {k} | {r[i]} | {units[i]} |\n")
+    print("wrote", dst)
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
