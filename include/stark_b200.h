@@ -74,6 +74,8 @@ int stark_measure_int_peak(stark_ctx* ctx, double tops[2]);
 int stark_vec_upload(stark_ctx* ctx, const uint64_t* host, size_t n, stark_vec** out);
 int stark_vec_alloc(stark_ctx* ctx, size_t n, stark_vec** out);                 /* zero-filled */
 int stark_vec_download(const stark_vec* v, size_t offset, size_t n, uint64_t* host);
+/* copies n canonical u32 values from caller-owned device memory (e.g. the receive buffer of an NCCL exchange) */
+int stark_vec_from_device(stark_ctx* ctx, const void* device_u32, size_t n, stark_vec** out);
 size_t stark_vec_len(const stark_vec* v);
 /* device address of the n canonical u32 values (for NCCL exchanges issued by the caller) */
 void* stark_vec_device_ptr(const stark_vec* v);
@@ -108,6 +110,17 @@ int stark_coset_lde_dev(stark_ctx* ctx, const stark_vec* evals, uint64_t offset_
                         uint64_t offset_out, stark_vec** out);
 int stark_batch_inverse_dev(stark_ctx* ctx, const stark_vec* a, stark_vec** out);
 int stark_quotient_pointwise_dev(stark_ctx* ctx, const stark_vec* num, const stark_vec* den, stark_vec** out);
+
+/* Building blocks of the multi-GPU four-step NTT (the all-to-all between them is the caller's
+ * NCCL call, see stark-prover_b200/multi_gpu.py):
+ *   stark_ntt_batch_dev: len/2^log_m independent size-2^log_m transforms (offset 1, natural order), in place;
+ *   stark_pow_mul_dev:   v[i] *= c0 * base^e(i) over a [outer][inner] array with inner = i % inner_len and
+ *                        outer = outer0 + i / inner_len;  product != 0: e = inner*outer (the twiddle w_N^(n2*k1)),
+ *                        else e = inner*inner_stride + outer (coset scaling of a column-distributed array);
+ *                        every e must be < 2^log_table. */
+int stark_ntt_batch_dev(stark_ctx* ctx, stark_vec* v, unsigned log_m, int inverse);
+int stark_pow_mul_dev(stark_ctx* ctx, stark_vec* v, size_t inner_len, size_t outer0, int product, size_t inner_stride,
+                      uint64_t base, uint64_t c0, unsigned log_table);
 
 /* ---- merkle: src/merkle/mod.rs -------------------------------------------------------------------
  * stark_merkle_commit == MerkleTree::new(data)   :10-22   leaf = SHA-256(value.to_be_bytes()), rs_merkle tree

@@ -72,6 +72,9 @@ def lib() -> C.CDLL:
     sig("stark_vec_upload", I, vp, vp, szt, C.POINTER(vp))
     sig("stark_vec_alloc", I, vp, szt, C.POINTER(vp))
     sig("stark_vec_download", I, vp, szt, szt, vp)
+    sig("stark_vec_from_device", I, vp, vp, szt, C.POINTER(vp))
+    sig("stark_ntt_batch_dev", I, vp, vp, C.c_uint, I)
+    sig("stark_pow_mul_dev", I, vp, vp, szt, szt, I, szt, u64, u64, C.c_uint)
     sig("stark_vec_len", szt, vp)
     sig("stark_vec_device_ptr", vp, vp)
     sig("stark_vec_destroy", None, vp)
@@ -202,6 +205,19 @@ class Context:
         _check(lib().stark_vec_upload(self.h, _ptr(a), a.size, C.byref(h)))
         return Vec(self, h)
 
+    def from_device(self, device_ptr: int, n: int) -> "Vec":
+        """Copies n u32 values from caller-owned device memory (a torch tensor's data_ptr())."""
+        h = vp()
+        _check(lib().stark_vec_from_device(self.h, C.c_void_p(device_ptr), n, C.byref(h)))
+        return Vec(self, h)
+
+    def ntt_batch_dev(self, v: "Vec", log_m: int, inverse: bool = False) -> None:
+        _check(lib().stark_ntt_batch_dev(self.h, v.h, log_m, int(inverse)))
+
+    def pow_mul_dev(self, v: "Vec", inner_len: int, outer0: int, product: bool, inner_stride: int, base: int, c0: int,
+                    log_table: int) -> None:
+        _check(lib().stark_pow_mul_dev(self.h, v.h, inner_len, outer0, int(product), inner_stride, base, c0, log_table))
+
     def zeros(self, n: int) -> "Vec":
         h = vp()
         _check(lib().stark_vec_alloc(self.h, n, C.byref(h)))
@@ -304,7 +320,8 @@ class Vec:
 
     @property
     def __cuda_array_interface__(self):
-        return {"shape": (len(self),), "typestr": "<u4", "data": (self.device_ptr, False), "version": 3}
+        # int32 view of the u32 values: torch moves the bits (permute / all_to_all), it never does arithmetic on them
+        return {"shape": (len(self),), "typestr": "<i4", "data": (self.device_ptr, False), "version": 3}
 
     def free(self):
         if getattr(self, "h", None):

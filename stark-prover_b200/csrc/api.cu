@@ -214,6 +214,16 @@ extern "C" int stark_vec_download(const stark_vec* v, size_t offset, size_t n, u
     download_u64(v->ctx, v->buf->as<uint32_t>() + offset, n, host);
     API_END
 }
+extern "C" int stark_vec_from_device(stark_ctx* ctx, const void* device_u32, size_t n, stark_vec** out) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && out && (device_u32 || n == 0), "vec_from_device: null argument");
+    CtxGuard g(ctx);
+    DevBufPtr b = make_buf(std::max<size_t>(n, 1) * 4, ctx->stream);
+    if (n) STARK_CUDA(cudaMemcpyAsync(b->p, device_u32, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    STARK_CUDA(cudaStreamSynchronize(ctx->stream));      // the source belongs to the caller (another stream)
+    *out = new_vec(ctx, b, n);
+    API_END
+}
 extern "C" size_t stark_vec_len(const stark_vec* v) { return v ? v->n : 0; }
 extern "C" void* stark_vec_device_ptr(const stark_vec* v) { return v ? v->buf->p : nullptr; }
 extern "C" void stark_vec_destroy(stark_vec* v) {
@@ -414,6 +424,40 @@ extern "C" int stark_quotient_pointwise_dev(stark_ctx* ctx, const stark_vec* num
     DevBufPtr r = make_buf(std::max<size_t>(num->n, 1) * 4, ctx->stream);
     batch_inverse(ctx, den->buf->as<uint32_t>(), num->buf->as<uint32_t>(), r->as<uint32_t>(), num->n);
     *out = new_vec(ctx, r, num->n);
+    API_END
+}
+
+// ---- building blocks of the multi-GPU four-step NTT; the exchange itself is the caller's NCCL call
+extern "C" int stark_ntt_batch_dev(stark_ctx* ctx, stark_vec* v, unsigned log_m, int inverse) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && v && v->ctx == ctx, "ntt_batch_dev: bad argument");
+    CtxGuard g(ctx);
+    size_t m = (size_t)1 << log_m;
+    STARK_REQUIRE(log_m >= 1 && log_m <= 30 && v->n % m == 0 && v->n >= m, "ntt_batch_dev: length is not a multiple of 2^log_m");
+    STARK_REQUIRE(log_m <= ctx->two_adicity, "ntt_batch_dev: 2^log_m does not divide p-1");
+    size_t batch = v->n / m;
+    DevBuf tmp(v->n * 4, ctx->stream);
+    if (!inverse) {
+        bitrev_permute(ctx, v->buf->as<uint32_t>(), tmp.as<uint32_t>(), log_m, nullptr, false, batch);
+        ntt_dit(ctx, tmp.as<uint32_t>(), v->buf->as<uint32_t>(), log_m, 0, nullptr, false, batch);
+    } else {
+        ntt_dif(ctx, v->buf->as<uint32_t>(), log_m, true, batch);
+        ScaleTable st;   // 1/m on the way out of the permutation
+        build_scale_table(ctx, 1, h_inv(m % ctx->modulus, ctx->modulus), log_m, st);
+        STARK_CUDA(cudaMemcpyAsync(tmp.p, v->buf->p, v->n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        bitrev_permute(ctx, tmp.as<uint32_t>(), v->buf->as<uint32_t>(), log_m, &st.view, false, batch);
+    }
+    API_END
+}
+extern "C" int stark_pow_mul_dev(stark_ctx* ctx, stark_vec* v, size_t inner_len, size_t outer0, int product, size_t inner_stride,
+                                 uint64_t base, uint64_t c0, unsigned log_table) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && v && v->ctx == ctx && inner_len >= 1, "pow_mul_dev: bad argument");
+    STARK_REQUIRE(log_table <= 31, "pow_mul_dev: table too large");
+    CtxGuard g(ctx);
+    ScaleTable st;
+    build_scale_table(ctx, base % ctx->modulus, c0 % ctx->modulus, log_table, st);
+    pow_mul(ctx, v->buf->as<uint32_t>(), v->n, inner_len, outer0, product != 0, inner_stride, st.view);
     API_END
 }
 

@@ -184,6 +184,24 @@ void coset_domain(stark_ctx* ctx, uint64_t offset, unsigned log_n, uint32_t* out
     STARK_CUDA(cudaGetLastError());
 }
 
+// ---------------- index-dependent powers (four-step twiddles, coset scaling of a column-distributed array) -------
+__global__ void pow_mul_kernel(uint32_t* v, size_t n, size_t inner_len, size_t outer0, int product, size_t inner_stride,
+                               PowTable table, FieldParams fp) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    size_t inner = i % inner_len, outer = outer0 + i / inner_len;
+    size_t e = product ? inner * outer : inner * inner_stride + outer;
+    v[i] = mont_mul(v[i], pow_lookup(table, (uint32_t)e, fp), fp);      // e < 2^log_table by construction
+}
+void pow_mul(stark_ctx* ctx, uint32_t* v, size_t n, size_t inner_len, size_t outer0, bool product, size_t inner_stride,
+             const PowTable& table) {
+    if (!n) return;
+    KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 16.0 * n);
+    pow_mul_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(v, n, inner_len, outer0, product, inner_stride, table, ctx->fp);
+    ctx->launches++;
+    STARK_CUDA(cudaGetLastError());
+}
+
 // ---------------- plain evaluation-space fold (the fused version lives in merkle.cu) ----------------
 __global__ void fri_fold_kernel(LeafSource src, FieldParams fp) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

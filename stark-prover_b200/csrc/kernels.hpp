@@ -49,12 +49,12 @@ size_t merkle_path_len(size_t n, size_t idx);
 //   log_pad > 0: the bit-reversed input is the size-2^(log_n-log_pad) array `src`, zero-padded
 //   (position q*2^log_pad holds src[q]), and src[q] is first multiplied by scale(bitrev(q)).
 void ntt_dit(stark_ctx* ctx, const uint32_t* src, uint32_t* data, unsigned log_n, unsigned log_pad,
-             const PowTable* scale, bool inverse_root);
+             const PowTable* scale, bool inverse_root, size_t batch = 1);
 // decimation-in-frequency: natural input -> bit-reversed output, in place.
-void ntt_dif(stark_ctx* ctx, uint32_t* data, unsigned log_n, bool inverse_root);
+void ntt_dif(stark_ctx* ctx, uint32_t* data, unsigned log_n, bool inverse_root, size_t batch = 1);
 // out[i] = in[bitrev(i)] * scale(scale_on_input_index ? bitrev(i) : i)   (scale optional)
 void bitrev_permute(stark_ctx* ctx, const uint32_t* in, uint32_t* out, unsigned log_n, const PowTable* scale,
-                    bool scale_by_input_index);
+                    bool scale_by_input_index, size_t batch = 1);
 // lo[j] = base^j (j < 2^shift), hi[j] = c0 * base^(j << shift); Montgomery form
 struct ScaleTable {
     DevBuf lo, hi;
@@ -74,6 +74,10 @@ void batch_inverse(stark_ctx* ctx, const uint32_t* a, const uint32_t* num, uint3
 void pointwise_mul(stark_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n);
 // out[i] = offset * w^i
 void coset_domain(stark_ctx* ctx, uint64_t offset, unsigned log_n, uint32_t* out);
+// v[i] *= c0 * base^e(i) for a [outer][inner] array: inner = i % inner_len, outer = outer0 + i / inner_len;
+//   product mode: e = inner * outer (the four-step twiddle w_N^(n2*k1));  affine: e = inner * inner_stride + outer
+void pow_mul(stark_ctx* ctx, uint32_t* v, size_t n, size_t inner_len, size_t outer0, bool product, size_t inner_stride,
+             const PowTable& table);
 // plain (unfused) evaluation-space fold of one layer
 void fri_fold(stark_ctx* ctx, const LeafSource& src);
 

@@ -221,9 +221,10 @@ static void check_size(stark_ctx* ctx, unsigned log_n) {
 }
 
 void ntt_dit(stark_ctx* ctx, const uint32_t* src, uint32_t* data, unsigned log_n, unsigned log_pad,
-             const PowTable* scale, bool inverse_root) {
+             const PowTable* scale, bool inverse_root, size_t batch) {
     check_size(ctx, log_n);
     STARK_REQUIRE(log_pad <= log_n, "ntt: padding larger than the transform");
+    STARK_REQUIRE(batch >= 1 && (batch == 1 || (log_pad == 0 && scale == nullptr && log_n >= 1)), "ntt: batched transforms take no padding/scale");
     if (log_n == 0) {   // single point: X[0] = x[0] * scale(0)
         point_scale_kernel<<<1, 1, 0, ctx->stream>>>(src, data, scale != nullptr, scale ? *scale : PowTable{}, ctx->fp);
         ctx->launches++;
@@ -234,7 +235,7 @@ void ntt_dit(stark_ctx* ctx, const uint32_t* src, uint32_t* data, unsigned log_n
     const size_t n = (size_t)1 << log_n;
     std::vector<unsigned> bits = plan_bits(log_n);
     // algorithmic bytes of the whole transform at 8 B per element: read the input once, write the output once
-    KernelTimer kt(ctx, stark_ctx::CAT_NTT, 8.0 * (double)(n >> log_pad) + 8.0 * (double)n);
+    KernelTimer kt(ctx, stark_ctx::CAT_NTT, (8.0 * (double)(n >> log_pad) + 8.0 * (double)n) * (double)batch);
     unsigned lo = 0;
     for (size_t i = 0; i < bits.size(); i++) {
         unsigned r = bits[i];
@@ -249,25 +250,26 @@ void ntt_dit(stark_ctx* ctx, const uint32_t* src, uint32_t* data, unsigned log_n
             ps.log_pad = log_pad; ps.log_m = log_n - log_pad;
             ps.has_scale = scale != nullptr;
             if (scale) ps.scale = *scale;
-            size_t cols = n >> r;
+            size_t cols = (n * batch) >> r;           // groups of 2^r contiguous points, across the whole batch
             ps.ncols = (unsigned)(cols < (size_t)NTT_C ? cols : NTT_C);
-            dispatch_pass<false, false>(ctx, r, ps, (n >> r) / ps.ncols);
+            dispatch_pass<false, false>(ctx, r, ps, cols / ps.ncols);
         } else {
             ps.ncols = NTT_C;
-            dispatch_pass<false, true>(ctx, r, ps, n / ((size_t)NTT_C << r));
+            dispatch_pass<false, true>(ctx, r, ps, batch * n / ((size_t)NTT_C << r));
         }
         lo += r;
     }
     STARK_CUDA(cudaGetLastError());
 }
 
-void ntt_dif(stark_ctx* ctx, uint32_t* data, unsigned log_n, bool inverse_root) {
+void ntt_dif(stark_ctx* ctx, uint32_t* data, unsigned log_n, bool inverse_root, size_t batch) {
     check_size(ctx, log_n);
     if (log_n == 0) return;
+    STARK_REQUIRE(batch >= 1, "ntt: empty batch");
     const TwiddleSet& tws = ctx->twiddles(log_n);
     const size_t n = (size_t)1 << log_n;
     std::vector<unsigned> bits = plan_bits(log_n);
-    KernelTimer kt(ctx, stark_ctx::CAT_NTT, 16.0 * (double)n);
+    KernelTimer kt(ctx, stark_ctx::CAT_NTT, 16.0 * (double)n * (double)batch);
     unsigned hi = log_n;
     for (size_t ii = bits.size(); ii-- > 0;) {
         unsigned r = bits[ii];
@@ -279,12 +281,12 @@ void ntt_dif(stark_ctx* ctx, uint32_t* data, unsigned log_n, bool inverse_root) 
         ps.small = inverse_root ? ctx->small_inv.as<uint32_t>() : ctx->small_fwd.as<uint32_t>();
         ps.small_log = ctx->small_log;
         if (lo == 0) {
-            size_t cols = n >> r;
+            size_t cols = (n * batch) >> r;
             ps.ncols = (unsigned)(cols < (size_t)NTT_C ? cols : NTT_C);
-            dispatch_pass<true, false>(ctx, r, ps, (n >> r) / ps.ncols);
+            dispatch_pass<true, false>(ctx, r, ps, cols / ps.ncols);
         } else {
             ps.ncols = NTT_C;
-            dispatch_pass<true, true>(ctx, r, ps, n / ((size_t)NTT_C << r));
+            dispatch_pass<true, true>(ctx, r, ps, batch * n / ((size_t)NTT_C << r));
         }
         hi = lo;
     }
@@ -292,22 +294,24 @@ void ntt_dif(stark_ctx* ctx, uint32_t* data, unsigned log_n, bool inverse_root) 
 }
 
 // ---- bit-reversal gather (natural <-> bit-reversed), optional scale ------------------------------
-__global__ void bitrev_kernel(const uint32_t* in, uint32_t* out, unsigned log_n, int has_scale, PowTable scale,
+__global__ void bitrev_kernel(const uint32_t* in, uint32_t* out, unsigned log_n, size_t total, int has_scale, PowTable scale,
                               int by_input, FieldParams fp) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >> log_n) return;
-    uint32_t j = bitrev_bits((uint32_t)i, log_n);
-    uint32_t x = in[j];
-    if (has_scale) x = mont_mul(x, pow_lookup(scale, by_input ? j : (uint32_t)i, fp), fp);
-    out[i] = x;
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    uint32_t i = (uint32_t)(g & (((size_t)1 << log_n) - 1));     // index inside its transform
+    size_t base = g - i;
+    uint32_t j = bitrev_bits(i, log_n);
+    uint32_t x = in[base + j];
+    if (has_scale) x = mont_mul(x, pow_lookup(scale, by_input ? j : i, fp), fp);
+    out[g] = x;
 }
 void bitrev_permute(stark_ctx* ctx, const uint32_t* in, uint32_t* out, unsigned log_n, const PowTable* scale,
-                    bool scale_by_input_index) {
-    size_t n = (size_t)1 << log_n;
+                    bool scale_by_input_index, size_t batch) {
+    size_t n = ((size_t)1 << log_n) * batch;
     PowTable sc{};
     if (scale) sc = *scale;
     KernelTimer kt(ctx, stark_ctx::CAT_NTT, 16.0 * (double)n);
-    bitrev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(in, out, log_n, scale != nullptr, sc,
+    bitrev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(in, out, log_n, n, scale != nullptr, sc,
                                                                          scale_by_input_index, ctx->fp);
     ctx->launches++;
     STARK_CUDA(cudaGetLastError());

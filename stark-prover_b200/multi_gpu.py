@@ -1,0 +1,261 @@
+"""Multi-GPU sharding of the hot path: one process per GPU, torch.distributed for plumbing.
+
+What shards (and nothing else does):
+  * independent trace columns -- column c goes to rank c mod G; each rank runs iNTT -> coset NTT -> Merkle
+    tree per column with no data-path collective, then the 32-byte roots are all-gathered
+    (`commit_columns`, BASELINE cfg4);
+  * one large column -- contiguous leaf ranges of size N/G are exact subtrees of the rs_merkle tree shape
+    (G a power of two): every rank hashes its range, subtree roots are gathered and the top log2(G)
+    levels are finished identically on every rank (`combine_subtree_roots`, `commit_leaf_ranges`);
+  * the four-step NTT for domains too large for one launch chain (`four_step_lde`, BASELINE cfg5): local
+    batched transforms, one all-to-all transpose, local transforms, and a second exchange that puts the
+    evaluations back into natural order in contiguous blocks so that leaf ranges can be hashed locally.
+
+The collective calls work with any torch.distributed backend (NCCL on the GPUs, gloo in the CPU tests,
+where the compute callbacks are injected).
+"""
+from __future__ import annotations
+
+import hashlib
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+
+def shard_columns(n_cols: int, rank: int, world: int) -> list[int]:
+    """Columns owned by `rank`: c mod world == rank."""
+    return [c for c in range(n_cols) if c % world == rank]
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def _comm_device(group=None):
+    import torch
+    dist = _dist()
+    backend = dist.get_backend(group) if dist.is_initialized() else "gloo"
+    return torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+
+
+def all_gather_bytes(local: np.ndarray, group=None) -> np.ndarray:
+    """All-gathers a uint8 array of identical shape on every rank; returns [world, *shape]."""
+    import torch
+    dist = _dist()
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local[None, ...].copy()
+    dev = _comm_device(group)
+    t = torch.from_numpy(np.ascontiguousarray(local)).to(dev)
+    out = torch.empty((dist.get_world_size(group),) + tuple(t.shape), dtype=t.dtype, device=dev)
+    dist.all_gather_into_tensor(out.view(-1), t.view(-1), group=group)
+    return out.cpu().numpy()
+
+
+def commit_columns(n_cols: int, commit_fn: Callable[[int], bytes], rank: int, world: int, group=None) -> list[bytes]:
+    """Column-parallel commitment: `commit_fn(c)` returns the 32-byte Merkle root of column c (LDE + tree on
+    this rank's GPU).  Returns the roots of ALL columns, in column order, identical on every rank."""
+    mine = shard_columns(n_cols, rank, world)
+    per_rank = -(-n_cols // world)
+    local = np.zeros((per_rank, 32), dtype=np.uint8)
+    for slot, c in enumerate(mine):
+        root = commit_fn(c)
+        assert len(root) == 32
+        local[slot] = np.frombuffer(root, dtype=np.uint8)
+    allr = all_gather_bytes(local, group)                       # [world, per_rank, 32]
+    return [allr[c % world, c // world].tobytes() for c in range(n_cols)]
+
+
+def gpu_column_committer(sp, ctx, get_column: Callable[[int], np.ndarray], log_blowup: int, offset_in: int, offset_out: int,
+                         keep: Optional[dict] = None) -> Callable[[int], bytes]:
+    """commit_fn for `commit_columns` on a GPU context: trace column (evaluations on offset_in*<g>) ->
+    coset LDE on offset_out*<h> -> MerkleTree (reference: interpolate + evaluate + MerkleTree::new)."""
+    def commit(c: int) -> bytes:
+        col = ctx.upload(get_column(c))
+        lde = ctx.coset_lde_dev(col, offset_in, log_blowup, offset_out)
+        col.free()
+        tree = sp.MerkleTree.new(ctx, lde)
+        root = tree.root_bytes()
+        if keep is not None:
+            keep[c] = (lde, tree)
+        else:
+            tree.free(); lde.free()
+        return root
+    return commit
+
+
+def combine_subtree_roots(roots: Sequence[bytes]) -> bytes:
+    """Finishes a tree whose leaves were hashed in G equal contiguous ranges: the G subtree roots are the
+    nodes of one level; pairs are hashed upward (rs_merkle rule; lone node promoted).  Host-side: G <= 8."""
+    level = list(roots)
+    while len(level) > 1:
+        nxt = [hashlib.sha256(level[i] + level[i + 1]).digest() for i in range(0, len(level) - 1, 2)]
+        if len(level) & 1:
+            nxt.append(level[-1])
+        level = nxt
+    return level[0]
+
+
+def top_path(roots: Sequence[bytes], owner: int) -> bytes:
+    """Authentication-path bytes for the levels above the subtree roots (sibling digests bottom -> top)."""
+    out, level, j = b"", list(roots), owner
+    while len(level) > 1:
+        sib = j ^ 1
+        if sib < len(level):
+            out += level[sib]
+        nxt = [hashlib.sha256(level[i] + level[i + 1]).digest() for i in range(0, len(level) - 1, 2)]
+        if len(level) & 1:
+            nxt.append(level[-1])
+        level, j = nxt, j >> 1
+    return out
+
+
+def commit_leaf_ranges(subtree_root_fn: Callable[[], bytes], rank: int, world: int, group=None) -> tuple[bytes, list[bytes]]:
+    """One big column whose leaves are split into `world` equal contiguous ranges (world a power of two and
+    the range a power of two, so each range is an exact subtree).  Returns (root, all subtree roots)."""
+    assert world & (world - 1) == 0, "leaf-range sharding needs a power-of-two world size"
+    local = np.frombuffer(subtree_root_fn(), dtype=np.uint8).reshape(1, 32)
+    allr = all_gather_bytes(local, group)
+    subs = [allr[r, 0].tobytes() for r in range(world)]
+    return combine_subtree_roots(subs), subs
+
+
+# ------------------------------------------------------------------------------------------------ four-step NTT
+def four_step_plan(log_n: int, world: int) -> tuple[int, int]:
+    """Splits 2^log_n = N1 * N2 with both factors divisible by the world size."""
+    a = log_n // 2
+    b = log_n - a
+    g = world.bit_length() - 1
+    assert world == 1 << g and a >= g and b >= g, "four-step NTT: world must be a power of two <= sqrt(N)"
+    return a, b          # N1 = 2^a (high digit of the input index), N2 = 2^b
+
+
+def four_step_scatter_input(coeffs: np.ndarray, log_n: int, rank: int, world: int) -> np.ndarray:
+    """Host-side input layout for rank `rank`: columns n2 in its slice, each column contiguous over n1:
+    A[n2'][n1] = x[n1*N2 + rank*N2/G + n2'] (x zero-padded to 2^log_n)."""
+    a, b = four_step_plan(log_n, world)
+    n1, n2 = 1 << a, 1 << b
+    x = np.zeros(1 << log_n, dtype=np.uint64)
+    x[: len(coeffs)] = coeffs
+    m = x.reshape(n1, n2)
+    w = n2 // world
+    return np.ascontiguousarray(m[:, rank * w:(rank + 1) * w].T)       # [n2/G][n1]
+
+
+def four_step_reference(coeffs: np.ndarray, log_n: int, offset: int, ntt_fn, modulus: int, omega: int, world: int) -> list[np.ndarray]:
+    """Pure-numpy model of the distributed data flow (used by the CPU tests to pin the index algebra):
+    returns, for each rank, its natural-order block of the evaluations of `coeffs` on offset*<omega>.
+    `ntt_fn(a, log_m, w)` is a size-2^log_m forward NTT with root w (natural in, natural out)."""
+    a, b = four_step_plan(log_n, world)
+    n1, n2, n = 1 << a, 1 << b, 1 << log_n
+    x = np.zeros(n, dtype=object)
+    pw = 1
+    for j, c in enumerate(coeffs):
+        x[j] = int(c) * pw % modulus
+        pw = pw * offset % modulus
+    m = x.reshape(n1, n2)
+    w1, w2 = pow(omega, n2, modulus), pow(omega, n1, modulus)
+    # phase A: column transforms over n1, then the twiddle w^(n2*k1)
+    y = np.zeros((n1, n2), dtype=object)
+    for c in range(n2):
+        col = ntt_fn(np.array([int(v) for v in m[:, c]], dtype=np.uint64), a, w1)
+        for k1 in range(n1):
+            y[k1, c] = int(col[k1]) * pow(omega, c * k1, modulus) % modulus
+    # phase C: row transforms over n2: X[k1 + N1*k2]
+    out = np.zeros(n, dtype=np.uint64)
+    for k1 in range(n1):
+        row = ntt_fn(np.array([int(v) for v in y[k1, :]], dtype=np.uint64), b, w2)
+        out[k1 + n1 * np.arange(n2)] = row
+    blk = n // world
+    return [out[r * blk:(r + 1) * blk] for r in range(world)]
+
+
+# ---- the same flow on the GPUs ------------------------------------------------------------------------
+def _as_torch(vec):
+    import torch
+    return torch.as_tensor(vec, device=torch.device("cuda", torch.cuda.current_device()))
+
+
+class FourStepLDE:
+    """Distributed coset evaluation X[k] = sum_j c_j (offset*w^k)^j of size N = N1*N2 over `world` ranks.
+
+    Index algebra (n = n1*N2 + n2 with n1 the high digit, k = k1 + N1*k2):
+        X[k1 + N1*k2] = sum_{n2} w_{N2}^(n2 k2) * w_N^(n2 k1) * sum_{n1} x[n1*N2 + n2] w_{N1}^(n1 k1)
+    phase A  rank r owns the columns n2 in its slice ([n2'][n1], each column contiguous): coset scaling,
+             batched size-N1 NTTs, twiddle w_N^(n2*k1)                                  (local kernels)
+    exch. 1  all-to-all: rank s receives the rows k1 in its slice                        (NCCL / NVLink)
+    phase C  batched size-N2 NTTs over n2 for the local rows                             (local kernels)
+    exch. 2  all-to-all back to natural order: rank t receives k in [t*N/G, (t+1)*N/G)   (NCCL / NVLink)
+    Each exchange moves 4*N/G bytes per rank, (G-1)/G of it over NVLink.
+    """
+
+    def __init__(self, sp, ctx, log_n: int, offset: int, rank: int, world: int):
+        self.sp, self.ctx, self.log_n, self.offset, self.rank, self.world = sp, ctx, log_n, offset, rank, world
+        self.a, self.b = four_step_plan(log_n, world)
+        self.n1, self.n2 = 1 << self.a, 1 << self.b
+        self.omega = ctx.root_of_unity(log_n)
+
+    def phase_a(self, coeffs: np.ndarray):
+        """-> torch int32 tensor [world (dest)][n2/G][n1/G] ready for the first exchange."""
+        ctx, w = self.ctx, self.n2 // self.world
+        v = ctx.upload(four_step_scatter_input(coeffs, self.log_n, self.rank, self.world).reshape(-1))
+        if self.offset % ctx.modulus != 1:
+            ctx.pow_mul_dev(v, self.n1, self.rank * w, False, self.n2, self.offset, 1, self.log_n)
+        ctx.ntt_batch_dev(v, self.a)
+        ctx.pow_mul_dev(v, self.n1, self.rank * w, True, 0, self.omega, 1, self.log_n)
+        ctx.sync()
+        t = _as_torch(v).view(w, self.world, self.n1 // self.world).permute(1, 0, 2).contiguous()
+        self._keep = v
+        return t
+
+    def phase_c(self, recv):
+        """recv: [world (src)][n2/G][n1/G] == [n2][k1'] -> tensor [world (dest)][n1/G][n2/G] for the second exchange."""
+        import torch
+        ctx = self.ctx
+        z = recv.reshape(self.n2, self.n1 // self.world).t().contiguous()           # [k1'][n2]
+        torch.cuda.current_stream().synchronize()
+        v = ctx.from_device(z.data_ptr(), z.numel())
+        ctx.ntt_batch_dev(v, self.b)
+        ctx.sync()
+        t = _as_torch(v).view(self.n1 // self.world, self.world, self.n2 // self.world).permute(1, 0, 2).contiguous()
+        self._keep = v
+        return t
+
+    def finish(self, recv):
+        """recv: [world (src)][n1/G][n2/G] == [k1][k2'] -> Vec with this rank's natural-order block."""
+        import torch
+        nat = recv.reshape(self.n1, self.n2 // self.world).t().contiguous()        # [k2'][k1]: p = k1 + N1*k2'
+        torch.cuda.current_stream().synchronize()
+        out = self.ctx.from_device(nat.data_ptr(), nat.numel())
+        self._keep = None
+        return out
+
+
+def _all_to_all(t, group=None):
+    import torch
+    dist = _dist()
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return t.clone()
+    out = torch.empty_like(t)
+    dist.all_to_all_single(out.view(-1), t.view(-1), group=group)
+    return out
+
+
+def four_step_lde(sp, ctx, coeffs: np.ndarray, log_n: int, offset: int, rank: int, world: int, group=None):
+    """This rank's contiguous natural-order block of the evaluations of `coeffs` on offset*<w_{2^log_n}>."""
+    fs = FourStepLDE(sp, ctx, log_n, offset, rank, world)
+    r1 = _all_to_all(fs.phase_a(coeffs), group)
+    r2 = _all_to_all(fs.phase_c(r1), group)
+    return fs.finish(r2)
+
+
+def four_step_lde_emulated(sp, ctx, coeffs: np.ndarray, log_n: int, offset: int, world: int) -> list:
+    """All `world` ranks of the flow on ONE GPU (the exchanges happen in memory): exercises the multi-rank
+    index algebra and every local kernel without needing `world` devices."""
+    import torch
+    ranks = [FourStepLDE(sp, ctx, log_n, offset, r, world) for r in range(world)]
+    send = [fs.phase_a(coeffs).clone() for fs in ranks]
+    recv = [torch.stack([send[src][dst] for src in range(world)]) for dst in range(world)]
+    send2 = [fs.phase_c(recv[r]).clone() for r, fs in enumerate(ranks)]
+    recv2 = [torch.stack([send2[src][dst] for src in range(world)]) for dst in range(world)]
+    return [fs.finish(recv2[r]) for r, fs in enumerate(ranks)]

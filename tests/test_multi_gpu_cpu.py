@@ -1,0 +1,102 @@
+"""CPU tests of the multi-GPU host logic: column sharding and root gathering over a real
+world_size-2 gloo group (compute injected from the oracle), subtree-root combination, and the index algebra
+of the four-step NTT against the oracle."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = 3221225473
+
+
+def _mg():
+    return importlib.import_module("stark-prover_b200.multi_gpu")
+
+
+def test_shard_columns():
+    mg = _mg()
+    assert mg.shard_columns(8, 1, 4) == [1, 5]
+    got = sorted(c for r in range(3) for c in mg.shard_columns(10, r, 3))
+    assert got == list(range(10))
+
+
+def test_combine_subtree_roots_matches_full_tree(orc):
+    mg = _mg()
+    vals = orc.synthetic_column(3, 1 << 10)
+    full = orc.Tree(vals)
+    for g in (1, 2, 4, 8):
+        blk = len(vals) // g
+        subs = [orc.Tree(vals[r * blk:(r + 1) * blk]).root() for r in range(g)]
+        assert mg.combine_subtree_roots(subs) == full.root()
+        # a path = path inside the owner's subtree + the top levels
+        idx = 777
+        owner = idx // blk
+        local = orc.Tree(vals[owner * blk:(owner + 1) * blk]).path(idx - owner * blk)
+        assert local + mg.top_path(subs, owner) == full.path(idx)
+
+
+def test_four_step_index_algebra(orc):
+    mg = _mg()
+    log_n, offset = 8, 5
+    w = orc.root_of_unity(log_n)
+    coeffs = orc.synthetic_column(21, 1 << 5)
+    want = orc.coset_evaluate(coeffs, log_n, offset, w, P)
+    for world in (1, 2, 4):
+        blocks = mg.four_step_reference(coeffs, log_n, offset, lambda a, lm, ww: orc.ntt(a, lm, ww, P), P, w, world)
+        assert np.array_equal(np.concatenate(blocks), want), world
+        a, b = mg.four_step_plan(log_n, world)
+        loc = mg.four_step_scatter_input(coeffs, log_n, world - 1, world)
+        assert loc.shape == ((1 << b) // world, 1 << a)
+
+
+def _worker(rank, world, port, n_cols, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from oracle import pyoracle as orc
+    mg = importlib.import_module("stark-prover_b200.multi_gpu")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        log_rows, log_blowup = 6, 3
+        calls = []
+
+        def commit(c):     # the GPU committer's contract, computed by the oracle here
+            calls.append(c)
+            col = orc.synthetic_column(100 + c, 1 << log_rows)
+            coef = orc.coset_interpolate(col, log_rows, 1, orc.root_of_unity(log_rows), P)
+            lde = orc.coset_evaluate(coef, log_rows + log_blowup, 5, orc.root_of_unity(log_rows + log_blowup), P)
+            return orc.Tree(lde).root()
+
+        roots = mg.commit_columns(n_cols, commit, rank, world)
+        top, subs = mg.commit_leaf_ranges(lambda: orc.Tree(orc.synthetic_column(9, 256)[rank * 128:(rank + 1) * 128]).root(), rank, world)
+        q.put((rank, calls, [r.hex() for r in roots], top.hex()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_commit_columns_gloo_world2(orc):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    n_cols = 5
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_cols, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=100) for _ in procs)
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    (r0, calls0, roots0, top0), (r1, calls1, roots1, top1) = res
+    assert calls0 == [0, 2, 4] and calls1 == [1, 3]          # no column is computed twice
+    assert roots0 == roots1 and top0 == top1                 # every rank ends with the same commitment
+    for c in range(n_cols):                                   # and it is the single-process answer
+        col = orc.synthetic_column(100 + c, 64)
+        coef = orc.coset_interpolate(col, 6, 1, orc.root_of_unity(6), P)
+        lde = orc.coset_evaluate(coef, 9, 5, orc.root_of_unity(9), P)
+        assert roots0[c] == orc.Tree(lde).root_hex()
+    assert top0 == orc.Tree(orc.synthetic_column(9, 256)).root_hex()

@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""Real multi-GPU check + timing (run under torchrun, one rank per GPU):
+  torchrun --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py [--full]
+cfg4: 64 columns x 2^22 rows (LDE 2^25) sharded by column, roots all-gathered (small sizes unless --full)
+cfg5: four-step LDE of one 2^26-point column (2^22 unless --full) + per-rank subtree + root gather.
+Every result is compared with the single-GPU path (and the CPU oracle at the small sizes)."""
+import argparse
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+P = 3221225473
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true")
+    ap.add_argument("--cols", type=int, default=None)
+    args = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sp = importlib.import_module("stark-prover_b200")
+    mg = importlib.import_module("stark-prover_b200.multi_gpu")
+    from oracle import pyoracle as orc
+    ctx = sp.Context(P, 5, local)
+    out = {"world": world}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- cfg4: column-parallel LDE + commit
+    log_rows, n_cols = (22, 64) if args.full else (16, 16)
+    if args.cols:
+        n_cols = args.cols
+    cols = {c: orc.synthetic_column(100 + c, 1 << log_rows) for c in mg.shard_columns(n_cols, rank, world)}
+    commit = mg.gpu_column_committer(sp, ctx, lambda c: cols[c], 3, 1, 5)
+    mg.commit_columns(min(n_cols, world), commit if rank < n_cols else (lambda c: b"\0" * 32), rank, world)   # warm-up
+    barrier(); t0 = time.perf_counter()
+    roots = mg.commit_columns(n_cols, commit, rank, world)
+    barrier(); dt = time.perf_counter() - t0
+    out["cfg4"] = {"columns": n_cols, "log_rows": log_rows, "log_lde": log_rows + 3, "seconds": dt,
+                   "Melem_per_s": n_cols * (1 << (log_rows + 3)) / dt / 1e6, "root0": roots[0].hex()}
+    if rank == 0 and not args.full:
+        for c in (0, n_cols - 1):
+            col = orc.synthetic_column(100 + c, 1 << log_rows)
+            coef = orc.coset_interpolate(col, log_rows, 1, orc.root_of_unity(log_rows), P)
+            lde = orc.coset_evaluate(coef, log_rows + 3, 5, orc.root_of_unity(log_rows + 3), P)
+            assert roots[c] == orc.merkle_root_only(lde), f"cfg4 column {c} root differs from the oracle"
+    # every rank must hold identical roots
+    if world > 1:
+        h = torch.tensor(list(roots[-1]), dtype=torch.uint8, device="cuda")
+        hs = [torch.empty_like(h) for _ in range(world)]
+        dist.all_gather(hs, h)
+        assert all(torch.equal(hs[0], x) for x in hs)
+
+    # ---------------- cfg5: four-step LDE + leaf-range commit
+    log_n = 26 if args.full else 22
+    coeffs = orc.synthetic_poly_exact_degree(43, 1 << (log_n - 3), P)
+    blk = mg.four_step_lde(sp, ctx, coeffs, log_n, 5, rank, world)            # warm-up
+    blk.free()
+    barrier(); t0 = time.perf_counter()
+    blk = mg.four_step_lde(sp, ctx, coeffs, log_n, 5, rank, world)
+    ctx.sync(); barrier(); t_lde = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    tree = sp.MerkleTree.new(ctx, blk)
+    root, subs = mg.commit_leaf_ranges(tree.root_bytes, rank, world)
+    barrier(); t_commit = time.perf_counter() - t0
+    out["cfg5"] = {"log_domain": log_n, "lde_seconds": t_lde, "commit_seconds": t_commit, "root": root.hex(),
+                   "Melem_per_s": (1 << log_n) / (t_lde + t_commit) / 1e6}
+    if rank == 0:
+        # single-GPU answer for the same column
+        ref = sp.MerkleTree.new(ctx, ctx.coset_evaluate_dev(ctx.upload(coeffs), log_n, 5))
+        assert ref.root_bytes() == root, "cfg5 root differs from the single-GPU path"
+        if log_n <= 22:
+            want = orc.coset_evaluate(coeffs, log_n, 5, orc.root_of_unity(log_n), P)
+            n_blk = (1 << log_n) // world
+            assert np.array_equal(blk.download(), want[:n_blk]), "cfg5 block differs from the oracle"
+        print(json.dumps(out), flush=True)
+    barrier()
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
