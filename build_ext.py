@@ -31,7 +31,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     os.makedirs(BUILD, exist_ok=True)
     ccbin = _host_cxx()
-    base = [nvcc] + NVCC_FLAGS + (["-ccbin", ccbin] if ccbin else [])
+    extra = os.environ.get("STARK_NVCC_DEFS", "").split()     # e.g. "-DSTARK_SHA_ADDS_ON_FMA=0" for kernel experiments
+    base = [nvcc] + NVCC_FLAGS + extra + (["-ccbin", ccbin] if ccbin else [])
     objs, jobs = [], []
     for s in SOURCES:
         src = os.path.join(CSRC, s)

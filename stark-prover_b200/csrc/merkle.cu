@@ -73,8 +73,11 @@ enum { SRC_VALUES = 0, SRC_FOLD = 1, SRC_DIGESTS = 2 };
 // item i is hashed, then merged upward while its index is odd.  One leaf site and one node site in the
 // code; trip counts depend only on i, so a warp never diverges.  A ragged tail (cnt < 2^SUB) is finished
 // by the flush loop, which applies rs_merkle's rule: a node without a right sibling is promoted.
+#ifndef STARK_MERKLE_MIN_BLOCKS
+#define STARK_MERKLE_MIN_BLOCKS 1
+#endif
 template <int SRC>
-__global__ void __launch_bounds__(MERKLE_THREADS)
+__global__ void __launch_bounds__(MERKLE_THREADS, STARK_MERKLE_MIN_BLOCKS)
 merkle_subtree_kernel(LeafSource src, const uint32_t* in_digests, size_t n, int nlev, LevelPtrs lv, FieldParams fp,
                       HostResult* result, int last) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -53,7 +53,15 @@ static __constant__ uint32_t c_sha_one = 1;
 #ifndef STARK_SHA_ADDS_ON_FMA
 #define STARK_SHA_ADDS_ON_FMA 1
 #endif
-#if STARK_SHA_ADDS_ON_FMA
+#if STARK_SHA_ADDS_ON_FMA == 2
+// mad.lo with a literal 1: SASS `IMAD.IADD Rd, Ra, 0x1, Rb` -- FMA pipe, two register reads
+__device__ __forceinline__ uint32_t sha_add_imad(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+#define SHA_ADD(x, y) sha_add_imad((x), (y))
+#elif STARK_SHA_ADDS_ON_FMA
 #define SHA_ADD(x, y) ((x) * sha_one + (y))
 #else
 #define SHA_ADD(x, y) ((x) + (y))

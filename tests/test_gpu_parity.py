@@ -327,3 +327,78 @@ def test_other_moduli(sp, orc, modulus, gen):
         assert ch.proof == och.proof and ch.state == och.state
     finally:
         c.close()
+
+
+# ---------------------------------------------------------------- BASELINE.json's full sizes
+def test_cfg2_lde_commit_2e20(sp, orc, ctx):
+    """configs[1]: single-column coset LDE (2^17 coefficients, seed 42) + Merkle commit at a 2^20 domain."""
+    log_n = 20
+    c = orc.synthetic_column(42, 1 << 17)
+    ev = ctx.coset_evaluate(c, log_n, 5)
+    want = orc.coset_evaluate(c, log_n, 5, orc.root_of_unity(log_n), P)
+    assert np.array_equal(ev, want)
+    assert sp.MerkleTree.new(ctx, ev).root_bytes() == orc.merkle_root_only(want)
+
+
+@pytest.mark.timeout(600)
+def test_cfg3_fri_commit_2e24_exact(sp, orc, ctx):
+    """configs[2] at full size against the oracle's NTT tier: every root, the final constant, and the
+    transcript after 32 query openings, bit for bit; plus size-independent properties on the layers."""
+    log_n, log_deg, q = 24, 21, 32
+    c = orc.synthetic_poly_exact_degree(43, 1 << log_deg)
+    ch, och = sp.Channel(P), orc.Channel(P)
+    pr = sp.fri_commit(ctx, c, sp.CosetFri(ctx, 5, log_n), ch)
+    opr = orc.fri_commit_fast(c, log_n, 5, orc.root_of_unity(log_n), och, P)
+    assert pr.num_layers == opr.num_layers == 22
+    assert sum(pr.layer_len(k) for k in range(22)) == 33554424            # SURVEY 2.2
+    for k in range(22):
+        assert pr.tree(k).root() == opr.tree(k).root_hex(), k
+    assert ch.state == och.state
+    assert np.array_equal(pr.final_poly(), opr.final_poly())
+    # sampled rows of every layer
+    rng = np.random.default_rng(7)
+    for k in range(22):
+        n = pr.layer_len(k)
+        off = int(rng.integers(0, max(n - 64, 1)))
+        assert np.array_equal(pr.layer(k, off, min(64, n)), opr.layer(k)[off:off + min(64, n)]), k
+    # the last layer is the constant polynomial
+    assert set(pr.layer(21).tolist()) == {int(pr.final_poly()[0])}
+    sp.decommit_fri(q, (1 << log_n) - 1, pr, ch)
+    orc.decommit_fri(q, (1 << log_n) - 1, opr, och)
+    assert ch.state == och.state and ch.proof_size() == och.proof_size()
+    assert hashlib.sha256(ch.proof_flat()).hexdigest() == hashlib.sha256(och.proof_flat()).hexdigest()
+
+
+def test_fold_property_at_full_size(sp, orc, ctx):
+    """encode -> fold consistency without the oracle's big arrays: e'[i] recomputed from e[i], e[i+n/2]
+    with the reference's field operators at sampled indices of a 2^22 layer."""
+    log_n = 22
+    c = orc.synthetic_poly_exact_degree(11, 1 << 19)
+    pr, _ = sp.fri_begin(ctx, c, log_n, 5)
+    beta = 123456789
+    pr.fold(beta)
+    n, w = 1 << log_n, orc.root_of_unity(log_n)
+    inv2 = orc.fe_inverse(2, P)
+    rng = np.random.default_rng(3)
+    for i in [0, 1, n // 2 - 1] + [int(x) for x in rng.integers(0, n // 2, 20)]:
+        a, b = int(pr.layer(0, i, 1)[0]), int(pr.layer(0, i + n // 2, 1)[0])
+        d = orc.fe_mul(5, orc.fe_pow(w, i, P), P)
+        want = orc.fe_add(orc.fe_mul(orc.fe_add(a, b, P), inv2, P),
+                          orc.fe_mul(orc.fe_mul(beta, orc.fe_sub(a, b, P), P), orc.fe_inverse(orc.fe_mul(2, d, P), P), P), P)
+        assert int(pr.layer(1, i, 1)[0]) == want, i
+    # openings of the folded layer verify against its root
+    t = pr.tree(1)
+    for idx in (0, 12345, n // 2 - 1):
+        assert orc.merkle_verify(t.root_bytes(), n // 2, idx, int(pr.layer(1, idx, 1)[0]), t.get_authentication_path(idx))
+
+
+def test_lde_roundtrip_2e24(sp, orc, ctx):
+    """interpolate(evaluate(c)) == c at 2^24 (idempotence), device resident."""
+    log_n = 24
+    c = orc.synthetic_column(5, 1 << log_n)
+    v = ctx.upload(c)
+    ev = ctx.coset_evaluate_dev(v, log_n, 5)
+    back = ctx.coset_interpolate_dev(ev, 5)
+    assert np.array_equal(back.download(), c)
+    lde = ctx.coset_lde_dev(ev, 5, 1, 7)           # same polynomial on a 2x larger coset
+    assert int(lde.download(0, 1)[0]) == orc.poly_evaluate(c, 7, P)    # the reference's Horner at the first coset point (2^24 steps)
