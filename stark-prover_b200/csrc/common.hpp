@@ -131,6 +131,8 @@ struct stark_ctx {
     starkb200::HostResult* h_result = nullptr;  // pinned + mapped
     starkb200::HostResult* d_result = nullptr;  // device alias of h_result
     starkb200::PinnedBuf pin_desc, pin_out;     // opening descriptors in, opening records out
+    starkb200::DevBuf tail_counter;             // grid-barrier arrival counter of merkle_tail_kernel (monotone)
+    unsigned tail_count = 0;                    // its value once every launch issued so far has finished
     int sm_count = 148;
     unsigned long long launches = 0;            // kernels launched through this context
 

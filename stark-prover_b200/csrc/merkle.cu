@@ -40,9 +40,6 @@ size_t merkle_path_len(size_t n, size_t idx) {
 }
 
 constexpr int SUB = 3;            // levels advanced per launch (2^SUB items per thread)
-constexpr int TOP_MAX = 512;      // a level this small is finished by the single-CTA kernel
-constexpr int SMALL_MAX = 2048;   // a tree this small is built by one CTA in one launch
-constexpr int SMALL_THREADS = 512;
 constexpr int MERKLE_THREADS = 128;
 
 struct LevelPtrs { uint32_t* p[SUB + 1]; };   // p[l], l = 1..SUB: storage of the l-th level produced by this launch
@@ -146,49 +143,148 @@ merkle_subtree_kernel(LeafSource src, const uint32_t* in_digests, size_t n, int 
         for (int i = 0; i < 8; i++) result->root[i] = d.w[i];
 }
 
-// Finishes a tree whose current level has <= TOP_MAX nodes: one CTA, one barrier per level.
-// Levels are contiguous in the node buffer, so `out` simply advances.
-__device__ __forceinline__ void finish_levels(const uint32_t* in, int in_len, uint32_t* out, HostResult* result) {
-    while (in_len > 1) {
-        int out_len = (in_len + 1) >> 1;
-        for (int j = threadIdx.x; j < out_len; j += blockDim.x) {
-            Digest l = load_digest(in + 16 * j), o;
-            if (2 * j + 1 < in_len) { Digest r = load_digest(in + 16 * j + 8); sha256_node_fn(&l, &r, &o); }
-            else o = l;
-            store_digest(out + 8 * j, o);
-        }
-        __syncthreads();
-        in = out; out += 8 * (size_t)out_len; in_len = out_len;
-    }
-    if (threadIdx.x == 0 && result)
-        for (int i = 0; i < 8; i++) result->root[i] = in[i];
-}
-__global__ void __launch_bounds__(TOP_MAX / 2)
-merkle_top_kernel(const uint32_t* in, int in_len, uint32_t* out, HostResult* result) {
-    finish_levels(in, in_len, out, result);
-}
+// ---- latency-bound part of every tree: one launch, one node per thread per level ------------------------
+// Below ~2^15 nodes a level no longer fills the machine and what matters is the length of the dependency
+// chain: 2 compressions per level.  Giving each thread 8 items (merkle_subtree_kernel) makes that chain 14
+// compressions per 3 levels.  This kernel instead walks the remaining levels with one parent per thread:
+// levels wider than a CTA are separated by a grid-wide barrier (cooperative launch: all CTAs are resident;
+// digests cross SMs through L2 with ld.global.cg), the last <= 256-parent levels run in CTA 0 alone.
+constexpr int TAIL_THREADS = 256;
+constexpr int TAIL_MAX_CTAS = 64;
+constexpr int TAIL_MAX = 2 * TAIL_THREADS * TAIL_MAX_CTAS;      // 32768 items -> 16384 parents, one per thread
 
-// Whole tree of a small layer (n <= SMALL_MAX) in one launch: the late FRI layers are latency bound
-// (one launch + one host round trip each), so spread the leaves over one CTA's threads instead of
-// giving 8 of them to each of a few threads.
-template <bool FOLD>
-__global__ void __launch_bounds__(SMALL_THREADS)
-merkle_small_kernel(LeafSource src, int n, uint32_t* nodes, FieldParams fp, HostResult* result) {
-    const int len1 = (n + 1) >> 1;
-    for (int j = threadIdx.x; j < len1; j += blockDim.x) {
-        uint32_t v0 = FOLD ? fold_at(src, 2 * (size_t)j, fp) : src.vals[2 * j];
-        Digest l, o;
-        sha256_leaf(0u, v0, l);
-        if (2 * j + 1 < n) {
-            uint32_t v1 = FOLD ? fold_at(src, 2 * (size_t)j + 1, fp) : src.vals[2 * j + 1];
-            Digest r;
-            sha256_leaf(0u, v1, r);
-            sha256_node_fn(&l, &r, &o);
-        } else o = l;
-        store_digest(nodes + 8 * j, o);          // for n == 1 this is the root slot
+__device__ __forceinline__ Digest load_digest_cg(const uint32_t* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldcg(q), b = __ldcg(q + 1);
+    Digest d;
+    d.w[0] = a.x; d.w[1] = a.y; d.w[2] = a.z; d.w[3] = a.w;
+    d.w[4] = b.x; d.w[5] = b.y; d.w[6] = b.z; d.w[7] = b.w;
+    return d;
+}
+// monotone counter barrier: arrival k of a launch waits for base + k * gridDim.x
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while ((int)(atomicAdd(counter, 0u) - target) < 0) { }
+        __threadfence();
     }
     __syncthreads();
-    finish_levels(nodes, len1, nodes + 8 * (size_t)len1, result);
+}
+
+struct TailArgs {
+    LeafSource src;              // SRC_VALUES / SRC_FOLD: the items are leaf values
+    const uint32_t* in_digests;  // SRC_DIGESTS: the items are stored digests
+    int n_items;
+    uint32_t* out;               // storage of the next level; the levels above follow contiguously
+    unsigned* barrier;
+    unsigned barrier_base;
+    HostResult* result;
+    FieldParams fp;
+};
+
+template <int SRC>
+__global__ void __launch_bounds__(TAIL_THREADS) merkle_tail_kernel(TailArgs a) {
+    const int tid = blockIdx.x * TAIL_THREADS + threadIdx.x;
+    const int nthreads = gridDim.x * TAIL_THREADS;
+    int len = a.n_items;
+    const uint32_t* in = a.in_digests;
+    uint32_t* out = a.out;
+    unsigned arrivals = 0;
+    bool first = true;
+    if (len == 1) {                              // one-leaf tree: the root is the leaf digest (slot 0)
+        if (tid == 0) {
+            Digest d;
+            if (SRC == SRC_DIGESTS) d = load_digest_cg(in);
+            else sha256_leaf(0u, SRC == SRC_FOLD ? fold_at(a.src, 0, a.fp) : a.src.vals[0], d);
+            store_digest(out, d);
+            if (a.result) for (int i = 0; i < 8; i++) a.result->root[i] = d.w[i];
+        }
+        return;
+    }
+    while (len > 1) {
+        const int out_len = (len + 1) >> 1;
+        for (int j = tid; j < out_len; j += nthreads) {
+            Digest l, r, o;
+            const bool pair = 2 * j + 1 < len;
+            if (first && SRC != SRC_DIGESTS) {
+                sha256_leaf(0u, SRC == SRC_FOLD ? fold_at(a.src, 2 * (size_t)j, a.fp) : a.src.vals[2 * j], l);
+                if (pair) sha256_leaf(0u, SRC == SRC_FOLD ? fold_at(a.src, 2 * (size_t)j + 1, a.fp) : a.src.vals[2 * j + 1], r);
+            } else {
+                l = load_digest_cg(in + 16 * (size_t)j);
+                if (pair) r = load_digest_cg(in + 16 * (size_t)j + 8);
+            }
+            if (pair) sha256_node_fn(&l, &r, &o); else o = l;      // lone node promoted
+            store_digest(out + 8 * (size_t)j, o);
+        }
+        first = false;
+        in = out; out += 8 * (size_t)out_len; len = out_len;
+        if (len == 1) break;
+        if (gridDim.x > 1) {
+            // the next level has (len+1)/2 parents; while the grid is still needed every CTA arrives
+            arrivals++;
+            grid_barrier(a.barrier, a.barrier_base + arrivals * gridDim.x);
+            if (((len + 1) >> 1) <= TAIL_THREADS) {           // from here CTA 0 finishes alone
+                if (blockIdx.x != 0) return;
+                // fall through to the single-CTA loop below
+                while (len > 1) {
+                    const int ol = (len + 1) >> 1;
+                    for (int j = threadIdx.x; j < ol; j += TAIL_THREADS) {
+                        Digest l = load_digest_cg(in + 16 * (size_t)j), o;
+                        if (2 * j + 1 < len) { Digest r = load_digest_cg(in + 16 * (size_t)j + 8); sha256_node_fn(&l, &r, &o); }
+                        else o = l;
+                        store_digest(out + 8 * (size_t)j, o);
+                    }
+                    __syncthreads();
+                    in = out; out += 8 * (size_t)ol; len = ol;
+                }
+                break;
+            }
+        } else {
+            __syncthreads();
+        }
+    }
+    if (tid == 0 && a.result) {
+        Digest d = load_digest_cg(in);
+        for (int i = 0; i < 8; i++) a.result->root[i] = d.w[i];
+    }
+}
+
+// number of grid-wide barrier arrivals the kernel above performs for (n_items, ctas): mirrors its control flow
+static unsigned tail_barriers(int n_items, int ctas) {
+    if (ctas <= 1 || n_items <= 1) return 0;
+    unsigned arrivals = 0;
+    int len = n_items;
+    while (len > 1) {
+        len = (len + 1) >> 1;
+        if (len == 1) break;
+        arrivals++;
+        if (((len + 1) >> 1) <= TAIL_THREADS) break;
+    }
+    return arrivals;
+}
+
+template <int SRC>
+static void launch_tail(stark_ctx* ctx, const LeafSource& src, const uint32_t* in_digests, size_t n_items, uint32_t* out,
+                        HostResult* result) {
+    if (!ctx->tail_counter.p) {                      // one counter per context (= per stream): launches are ordered
+        ctx->tail_counter = DevBuf(sizeof(unsigned), ctx->stream);
+        STARK_CUDA(cudaMemsetAsync(ctx->tail_counter.p, 0, sizeof(unsigned), ctx->stream));
+        ctx->tail_count = 0;
+    }
+    int parents = (int)((n_items + 1) / 2);
+    int ctas = (parents + TAIL_THREADS - 1) / TAIL_THREADS;
+    if (ctas < 1) ctas = 1;
+    if (ctas > TAIL_MAX_CTAS) ctas = TAIL_MAX_CTAS;
+    TailArgs a{};
+    a.src = src; a.in_digests = in_digests; a.n_items = (int)n_items; a.out = out;
+    a.barrier = ctx->tail_counter.as<unsigned>(); a.barrier_base = ctx->tail_count; a.result = result; a.fp = ctx->fp;
+    ctx->tail_count += tail_barriers((int)n_items, ctas) * (unsigned)ctas;
+    void* args[] = {&a};
+    if (ctas > 1) STARK_CUDA(cudaLaunchCooperativeKernel((const void*)merkle_tail_kernel<SRC>, dim3(ctas), dim3(TAIL_THREADS), args, 0, ctx->stream));
+    else merkle_tail_kernel<SRC><<<1, TAIL_THREADS, 0, ctx->stream>>>(a);
+    ctx->launches++;
 }
 
 void merkle_build(stark_ctx* ctx, const LeafSource& src, const TreeShape& shape, uint32_t* nodes, HostResult* result) {
@@ -199,47 +295,39 @@ void merkle_build(stark_ctx* ctx, const LeafSource& src, const TreeShape& shape,
     const bool fold = src.prev != nullptr;
     // algorithmic int-ops: 1384 per compression; leaf = 1, node = 2
     auto comp_levels = [&](unsigned from, unsigned to) { double c = 0; for (unsigned l = from; l <= to; l++) c += 2.0 * (double)shape.len[l]; return c; };
-    if (n <= (size_t)SMALL_MAX) {
+    if (n <= (size_t)TAIL_MAX) {                     // a small layer: the whole tree in one launch
         KernelTimer kt(ctx, stark_ctx::CAT_MERKLE_LEAF, 1384.0 * ((double)n + comp_levels(1, depth)));
-        if (fold) merkle_small_kernel<true><<<1, SMALL_THREADS, 0, ctx->stream>>>(src, (int)n, nodes, ctx->fp, result);
-        else merkle_small_kernel<false><<<1, SMALL_THREADS, 0, ctx->stream>>>(src, (int)n, nodes, ctx->fp, result);
-        ctx->launches++;
+        if (fold) launch_tail<SRC_FOLD>(ctx, src, nullptr, n, nodes, result);
+        else launch_tail<SRC_VALUES>(ctx, src, nullptr, n, nodes, result);
         STARK_CUDA(cudaGetLastError());
         return;
     }
     unsigned cur = 0;
     {
-        int nlev = (int)(depth < (unsigned)SUB ? depth : SUB);
         LevelPtrs lv{};
-        for (int l = 1; l <= nlev; l++) lv.p[l] = level_ptr(l);
+        for (int l = 1; l <= SUB; l++) lv.p[l] = level_ptr(l);        // n > TAIL_MAX: depth > SUB
         size_t threads = (n + (1 << SUB) - 1) >> SUB;
         unsigned blocks = (unsigned)((threads + MERKLE_THREADS - 1) / MERKLE_THREADS);
-        int last = (unsigned)nlev == depth;
-        KernelTimer kt(ctx, stark_ctx::CAT_MERKLE_LEAF, 1384.0 * ((double)n + comp_levels(1, nlev)));
-        if (fold) merkle_subtree_kernel<SRC_FOLD><<<blocks, MERKLE_THREADS, 0, ctx->stream>>>(src, nullptr, n, nlev, lv, ctx->fp, result, last);
-        else merkle_subtree_kernel<SRC_VALUES><<<blocks, MERKLE_THREADS, 0, ctx->stream>>>(src, nullptr, n, nlev, lv, ctx->fp, result, last);
+        KernelTimer kt(ctx, stark_ctx::CAT_MERKLE_LEAF, 1384.0 * ((double)n + comp_levels(1, SUB)));
+        if (fold) merkle_subtree_kernel<SRC_FOLD><<<blocks, MERKLE_THREADS, 0, ctx->stream>>>(src, nullptr, n, SUB, lv, ctx->fp, result, 0);
+        else merkle_subtree_kernel<SRC_VALUES><<<blocks, MERKLE_THREADS, 0, ctx->stream>>>(src, nullptr, n, SUB, lv, ctx->fp, result, 0);
         ctx->launches++;
-        cur = (unsigned)nlev;
+        cur = SUB;
     }
-    while (cur < depth) {
+    while (shape.len[cur] > (size_t)TAIL_MAX) {      // throughput-bound levels: 3 per launch
         size_t cur_len = shape.len[cur];
-        if (cur_len <= (size_t)TOP_MAX) {
-            KernelTimer kt(ctx, stark_ctx::CAT_MERKLE_NODE, 1384.0 * comp_levels(cur + 1, depth));
-            merkle_top_kernel<<<1, TOP_MAX / 2, 0, ctx->stream>>>(level_ptr(cur), (int)cur_len, level_ptr(cur + 1), result);
-            ctx->launches++;
-            cur = depth;
-            break;
-        }
-        int nlev = (int)((depth - cur) < (unsigned)SUB ? (depth - cur) : SUB);
         LevelPtrs lv{};
-        for (int l = 1; l <= nlev; l++) lv.p[l] = level_ptr(cur + l);
+        for (int l = 1; l <= SUB; l++) lv.p[l] = level_ptr(cur + l);
         size_t threads = (cur_len + (1 << SUB) - 1) >> SUB;
         unsigned blocks = (unsigned)((threads + MERKLE_THREADS - 1) / MERKLE_THREADS);
-        int last = cur + (unsigned)nlev == depth;
-        KernelTimer kt(ctx, stark_ctx::CAT_MERKLE_NODE, 1384.0 * comp_levels(cur + 1, cur + nlev));
-        merkle_subtree_kernel<SRC_DIGESTS><<<blocks, MERKLE_THREADS, 0, ctx->stream>>>(LeafSource{}, level_ptr(cur), cur_len, nlev, lv, ctx->fp, result, last);
+        KernelTimer kt(ctx, stark_ctx::CAT_MERKLE_NODE, 1384.0 * comp_levels(cur + 1, cur + SUB));
+        merkle_subtree_kernel<SRC_DIGESTS><<<blocks, MERKLE_THREADS, 0, ctx->stream>>>(LeafSource{}, level_ptr(cur), cur_len, SUB, lv, ctx->fp, result, 0);
         ctx->launches++;
-        cur += (unsigned)nlev;
+        cur += SUB;
+    }
+    {
+        KernelTimer kt(ctx, stark_ctx::CAT_MERKLE_NODE, 1384.0 * comp_levels(cur + 1, depth));
+        launch_tail<SRC_DIGESTS>(ctx, LeafSource{}, level_ptr(cur), shape.len[cur], level_ptr(cur + 1), result);
     }
     STARK_CUDA(cudaGetLastError());
 }
