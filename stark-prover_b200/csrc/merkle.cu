@@ -148,9 +148,11 @@ merkle_subtree_kernel(LeafSource src, const uint32_t* in_digests, size_t n, int 
 // chain: 2 compressions per level.  Giving each thread 8 items (merkle_subtree_kernel) makes that chain 14
 // compressions per 3 levels.  This kernel instead walks the remaining levels with one parent per thread:
 // levels wider than a CTA are separated by a grid-wide barrier (cooperative launch: all CTAs are resident;
-// digests cross SMs through L2 with ld.global.cg), the last <= 256-parent levels run in CTA 0 alone.
-constexpr int TAIL_THREADS = 256;
-constexpr int TAIL_MAX_CTAS = 64;
+// digests cross SMs through L2 with ld.global.cg), the last <= 128-parent levels run in CTA 0 alone.
+// 128-thread CTAs, at most 128 of them: every warp gets a scheduler (SM sub-partition) to itself, so the
+// ALU pipe (one warp instruction per 2 cycles) is never shared -- two warps per scheduler double the level time.
+constexpr int TAIL_THREADS = 128;
+constexpr int TAIL_MAX_CTAS = 128;
 constexpr int TAIL_MAX = 2 * TAIL_THREADS * TAIL_MAX_CTAS;      // 32768 items -> 16384 parents, one per thread
 
 __device__ __forceinline__ Digest load_digest_cg(const uint32_t* p) {
