@@ -89,6 +89,8 @@ struct PinnedBuf {
     }
 };
 
+struct DegScratch { int maxv; unsigned ticket; };     // coeff_fold_kernel's cross-block reduction state
+
 // What the host reads after each commit without issuing a copy (mapped pinned memory).
 struct HostResult {
     uint32_t root[8];
@@ -131,6 +133,7 @@ struct stark_ctx {
     starkb200::HostResult* h_result = nullptr;  // pinned + mapped
     starkb200::HostResult* d_result = nullptr;  // device alias of h_result
     starkb200::PinnedBuf pin_desc, pin_out;     // opening descriptors in, opening records out
+    starkb200::DevBuf deg_scratch;              // DegScratch of coeff_fold_kernel
     starkb200::DevBuf tail_counter;             // grid-barrier arrival counter of merkle_tail_kernel (monotone)
     unsigned tail_count = 0;                    // its value once every launch issued so far has finished
     int sm_count = 148;

@@ -61,12 +61,11 @@ void fill_zero(stark_ctx* ctx, uint32_t* p, size_t n) {
 }
 
 // ---------------- coefficient-space fold + exact degree ----------------
-struct DegScratch { int maxv; unsigned ticket; };
-__device__ DegScratch g_deg_scratch;    // zero-initialised; the last block of every launch resets it
+// {running max, ticket}: lives in the context (zeroed once); the last block of every launch resets it
 
 template <bool FOLD>
 __global__ void coeff_fold_kernel(const uint32_t* c, size_t len, uint32_t beta_m, uint32_t* out, size_t out_len,
-                                  HostResult* result, FieldParams fp) {
+                                  HostResult* result, DegScratch* scratch, FieldParams fp) {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int mine = 0;
     if (j < out_len) {
@@ -93,28 +92,35 @@ __global__ void coeff_fold_kernel(const uint32_t* c, size_t len, uint32_t beta_m
     if ((threadIdx.x & 31) == 0 && mine) atomicMax(&smax, mine);
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (smax) atomicMax(&g_deg_scratch.maxv, smax);
+        if (smax) atomicMax(&scratch->maxv, smax);
         __threadfence();
-        unsigned t = atomicAdd(&g_deg_scratch.ticket, 1u);
+        unsigned t = atomicAdd(&scratch->ticket, 1u);
         if (t == gridDim.x - 1) {
             __threadfence();
-            result->degree_plus1 = atomicExch(&g_deg_scratch.maxv, 0);
-            g_deg_scratch.ticket = 0;
+            result->degree_plus1 = atomicExch(&scratch->maxv, 0);
+            scratch->ticket = 0;
         }
     }
+}
+static DegScratch* deg_scratch(stark_ctx* ctx) {
+    if (!ctx->deg_scratch.p) {
+        ctx->deg_scratch = DevBuf(sizeof(DegScratch), ctx->stream);
+        STARK_CUDA(cudaMemsetAsync(ctx->deg_scratch.p, 0, sizeof(DegScratch), ctx->stream));
+    }
+    return ctx->deg_scratch.as<DegScratch>();
 }
 void coeff_fold(stark_ctx* ctx, const uint32_t* c, size_t len, uint32_t beta_m, uint32_t* out, HostResult* result) {
     KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 12.0 * len);
     size_t out_len = (len + 1) / 2;
     if (out_len == 0) { throw StarkError(ST_INTERNAL, "coeff_fold: empty polynomial"); }
-    coeff_fold_kernel<true><<<(unsigned)((out_len + 255) / 256), 256, 0, ctx->stream>>>(c, len, beta_m, out, out_len, result, ctx->fp);
+    coeff_fold_kernel<true><<<(unsigned)((out_len + 255) / 256), 256, 0, ctx->stream>>>(c, len, beta_m, out, out_len, result, deg_scratch(ctx), ctx->fp);
     ctx->launches++;
     STARK_CUDA(cudaGetLastError());
 }
 void poly_degree(stark_ctx* ctx, const uint32_t* c, size_t len, HostResult* result) {
     KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 8.0 * len);
     STARK_REQUIRE(len > 0, "poly_degree: empty");
-    coeff_fold_kernel<false><<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>(c, len, 0, nullptr, len, result, ctx->fp);
+    coeff_fold_kernel<false><<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>(c, len, 0, nullptr, len, result, deg_scratch(ctx), ctx->fp);
     ctx->launches++;
     STARK_CUDA(cudaGetLastError());
 }

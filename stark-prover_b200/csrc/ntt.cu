@@ -177,10 +177,8 @@ static void launch_pass(stark_ctx* ctx, const NttPass& ps, size_t tiles) {
     if (threads > 1024) threads = 1024;
     size_t smem = (size_t)(R * NTT_TS + (R >> 1) + 1) * sizeof(uint32_t);
     auto kern = ntt_pass_kernel<R_LOG, DIF, STRIDED>;
-    if (smem > 48 * 1024) {
-        static bool once = false;   // per instantiation
-        if (!once) { STARK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); once = true; }
-    }
+    if (smem > 48 * 1024)   // opt in per launch: the attribute is per device, contexts may live on several
+        STARK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)tiles, threads, smem, ctx->stream>>>(ps, ctx->fp);
     ctx->launches++;
 }

@@ -46,7 +46,7 @@ def all_gather_bytes(local: np.ndarray, group=None) -> np.ndarray:
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return local[None, ...].copy()
     dev = _comm_device(group)
-    t = torch.from_numpy(np.ascontiguousarray(local)).to(dev)
+    t = torch.from_numpy(np.array(local, copy=True)).to(dev)
     out = torch.empty((dist.get_world_size(group),) + tuple(t.shape), dtype=t.dtype, device=dev)
     dist.all_gather_into_tensor(out.view(-1), t.view(-1), group=group)
     return out.cpu().numpy()
@@ -196,9 +196,22 @@ class FourStepLDE:
         self.omega = ctx.root_of_unity(log_n)
 
     def phase_a(self, coeffs: np.ndarray):
-        """-> torch int32 tensor [world (dest)][n2/G][n1/G] ready for the first exchange."""
+        """-> torch int32 tensor [world (dest)][n2/G][n1/G] ready for the first exchange.
+        Only the rows of the [N1][N2] coefficient matrix that hold coefficients are uploaded (an LDE input is
+        zero above n = N/blowup); the column-major local layout [n2'][n1] is assembled on the device."""
+        import torch
         ctx, w = self.ctx, self.n2 // self.world
-        v = ctx.upload(four_step_scatter_input(coeffs, self.log_n, self.rank, self.world).reshape(-1))
+        rows = -(-len(coeffs) // self.n2)                      # rows of the matrix that are not all zero
+        host = np.zeros((rows, w), dtype=np.uint64)
+        padded = np.zeros(rows * self.n2, dtype=np.uint64)
+        padded[: len(coeffs)] = coeffs
+        host[:, :] = padded.reshape(rows, self.n2)[:, self.rank * w:(self.rank + 1) * w]
+        up = ctx.upload(host.reshape(-1))                      # [rows][w]
+        v = ctx.zeros(w * self.n1)                             # [w][n1]
+        ctx.sync()
+        _as_torch(v).view(w, self.n1)[:, :rows] = _as_torch(up).view(rows, w).t()
+        torch.cuda.current_stream().synchronize()
+        up.free()
         if self.offset % ctx.modulus != 1:
             ctx.pow_mul_dev(v, self.n1, self.rank * w, False, self.n2, self.offset, 1, self.log_n)
         ctx.ntt_batch_dev(v, self.a)
