@@ -243,6 +243,12 @@ static DevBufPtr evaluate_on_coset(stark_ctx* ctx, const uint32_t* coeffs_padded
     STARK_REQUIRE(log_m <= log_n, "evaluate: more coefficients than domain points");
     STARK_REQUIRE(log_n <= ctx->two_adicity, "evaluate: 2^log_n does not divide p-1");
     size_t m = (size_t)1 << log_m, n = (size_t)1 << log_n;
+    if (log_n >= 3 && log_m <= log_n - 3 && lde8_supported(log_n - 3)) {
+        // blow-up >= 8: eight interleaved size-(n/8) transforms that share all their twiddles (ntt.cu, lde8)
+        DevBufPtr out = make_buf(n * 4, ctx->stream);
+        lde8_forward(ctx, coeffs_padded, m, false, out->as<uint32_t>(), log_n - 3, offset, 1);
+        return out;
+    }
     DevBuf tmp(m * 4, ctx->stream);
     bool unit = (offset % ctx->modulus) == 1;
     ScaleTable st;
@@ -274,6 +280,12 @@ static DevBufPtr lde_on_coset(stark_ctx* ctx, const uint32_t* evals, unsigned lo
     STARK_CUDA(cudaMemcpyAsync(tmp.p, evals, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     ntt_dif(ctx, tmp.as<uint32_t>(), log_n, true);                       // bit-reversed, unscaled coefficients
     uint64_t p = ctx->modulus;
+    if (log_blowup == 3 && lde8_supported(log_n)) {
+        DevBufPtr out8 = make_buf(N * 4, ctx->stream);
+        lde8_forward(ctx, tmp.as<uint32_t>(), n, true, out8->as<uint32_t>(), log_n,
+                     h_mul(offset_out % p, h_inv(offset_in % p, p), p), h_inv(n % p, p));
+        return out8;
+    }
     ScaleTable st;   // c_j * n^-1 * (offset_out/offset_in)^j, applied on the way into the DIT
     build_scale_table(ctx, h_mul(offset_out % p, h_inv(offset_in % p, p), p), h_inv(n % p, p), log_n, st);
     DevBufPtr out = make_buf(N * 4, ctx->stream);

@@ -52,6 +52,11 @@ void ntt_dit(stark_ctx* ctx, const uint32_t* src, uint32_t* data, unsigned log_n
              const PowTable* scale, bool inverse_root, size_t batch = 1);
 // decimation-in-frequency: natural input -> bit-reversed output, in place.
 void ntt_dif(stark_ctx* ctx, uint32_t* data, unsigned log_n, bool inverse_root, size_t batch = 1);
+// Blow-up-by-8 forward transform (the LDE / evaluate hot path): dst[8k'+s] = sum_j c_j (base w_N^s)^j w_n^(j k'),
+// c_j = c0 * (natural coefficients src[j], or src in bit-reversed order when src_bitrev).  n = 2^log_rows >= 2^10.
+bool lde8_supported(unsigned log_rows);
+void lde8_forward(stark_ctx* ctx, const uint32_t* src, size_t src_len, bool src_bitrev, uint32_t* dst, unsigned log_rows,
+                  uint64_t base, uint64_t c0);
 // out[i] = in[bitrev(i)] * scale(scale_on_input_index ? bitrev(i) : i)   (scale optional)
 void bitrev_permute(stark_ctx* ctx, const uint32_t* in, uint32_t* out, unsigned log_n, const PowTable* scale,
                     bool scale_by_input_index, size_t batch = 1);

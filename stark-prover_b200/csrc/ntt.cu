@@ -34,7 +34,21 @@ struct NttPass {
     unsigned small_log;
 };
 
-template <int G, bool DIF>
+// Lazy (DIT only): values are "weak" -- any u32 congruent to the element (2^32 < 2p, so canonical or
+// canonical + p).  A Montgomery product accepts a weak operand and returns a canonical one, so in
+// a + w*b / a - w*b only `a` is weak; the sum wraps past 2^32 at most once and the difference goes negative
+// at most once, which makes the add 3 instructions instead of 6.  The last pass canonicalises on store.
+__device__ __forceinline__ uint32_t ladd(uint32_t a_weak, uint32_t b, const FieldParams& f) {
+    uint32_t s = a_weak + b;
+    return s < a_weak ? s - f.p : s;
+}
+__device__ __forceinline__ uint32_t lsub(uint32_t a_weak, uint32_t b, const FieldParams& f) {
+    uint32_t d = a_weak - b;
+    return a_weak < b ? d + f.p : d;
+}
+__device__ __forceinline__ uint32_t canonical(uint32_t x, const FieldParams& f) { return x >= f.p ? x - f.p : x; }
+
+template <int G, bool DIF, bool LAZY>
 __device__ __forceinline__ void butterfly_group(uint32_t* col, const int s, const int base, const uint32_t* tws,
                                                 const int r_log, const FieldParams& fp) {
     uint32_t x[1 << G];
@@ -49,13 +63,19 @@ __device__ __forceinline__ void butterfly_group(uint32_t* col, const int s, cons
         for (int jj = 0; jj < (1 << G); jj++) {
             if (jj & (1 << u)) continue;
             const int k = bl + ((jj & ((1 << u) - 1)) << s);
-            const uint32_t w = tws[k << (r_log - level)];
+            const bool unit = (s == 0 && u == 0);    // w_2^0 = 1: no multiplication in the span-1 stage
+            const uint32_t w = unit ? 0u : tws[k << (r_log - level)];
             if (DIF) {
                 uint32_t a = x[jj], b = x[jj + (1 << u)];
                 x[jj] = fadd(a, b, fp);
-                x[jj + (1 << u)] = mont_mul(fsub(a, b, fp), w, fp);
+                uint32_t d = fsub(a, b, fp);
+                x[jj + (1 << u)] = unit ? d : mont_mul(d, w, fp);
+            } else if (LAZY) {
+                uint32_t a = x[jj], b = unit ? x[jj + (1 << u)] : mont_mul(x[jj + (1 << u)], w, fp);
+                x[jj] = ladd(a, b, fp);
+                x[jj + (1 << u)] = lsub(a, b, fp);
             } else {
-                uint32_t a = x[jj], b = mont_mul(x[jj + (1 << u)], w, fp);
+                uint32_t a = x[jj], b = unit ? x[jj + (1 << u)] : mont_mul(x[jj + (1 << u)], w, fp);
                 x[jj] = fadd(a, b, fp);
                 x[jj + (1 << u)] = fsub(a, b, fp);
             }
@@ -65,7 +85,7 @@ __device__ __forceinline__ void butterfly_group(uint32_t* col, const int s, cons
     for (int j = 0; j < (1 << G); j++) col[(base + (j << s)) * NTT_TS] = x[j];
 }
 
-template <int R_LOG, int G, bool DIF>
+template <int R_LOG, int G, bool DIF, bool LAZY>
 __device__ __forceinline__ void run_round(uint32_t* tile, const int s, const uint32_t* tws, const FieldParams& fp,
                                           const unsigned ncols) {
     constexpr int items = ((1 << R_LOG) >> G) * NTT_C;
@@ -73,32 +93,32 @@ __device__ __forceinline__ void run_round(uint32_t* tile, const int s, const uin
         const int c = w % NTT_C, bi = w / NTT_C;
         if ((unsigned)c >= ncols) continue;
         const int base = ((bi >> s) << (s + G)) | (bi & ((1 << s) - 1));
-        butterfly_group<G, DIF>(tile + c, s, base, tws, R_LOG, fp);
+        butterfly_group<G, DIF, LAZY>(tile + c, s, base, tws, R_LOG, fp);
     }
     __syncthreads();
 }
 
-template <int R_LOG, bool DIF>
+template <int R_LOG, bool DIF, bool LAZY = false>
 __device__ __forceinline__ void run_rounds(uint32_t* tile, const uint32_t* tws, const FieldParams& fp, unsigned ncols) {
     // stage groups (sum = R_LOG); DIT walks spans upward, DIF downward
     if constexpr (R_LOG <= 4) {
-        run_round<R_LOG, R_LOG, DIF>(tile, 0, tws, fp, ncols);
+        run_round<R_LOG, R_LOG, DIF, LAZY>(tile, 0, tws, fp, ncols);
     } else if constexpr (R_LOG == 5) {
-        if (!DIF) { run_round<5, 3, DIF>(tile, 0, tws, fp, ncols); run_round<5, 2, DIF>(tile, 3, tws, fp, ncols); }
-        else      { run_round<5, 2, DIF>(tile, 3, tws, fp, ncols); run_round<5, 3, DIF>(tile, 0, tws, fp, ncols); }
+        if (!DIF) { run_round<5, 3, DIF, LAZY>(tile, 0, tws, fp, ncols); run_round<5, 2, DIF, LAZY>(tile, 3, tws, fp, ncols); }
+        else      { run_round<5, 2, DIF, LAZY>(tile, 3, tws, fp, ncols); run_round<5, 3, DIF, LAZY>(tile, 0, tws, fp, ncols); }
     } else if constexpr (R_LOG == 6) {
-        if (!DIF) { run_round<6, 3, DIF>(tile, 0, tws, fp, ncols); run_round<6, 3, DIF>(tile, 3, tws, fp, ncols); }
-        else      { run_round<6, 3, DIF>(tile, 3, tws, fp, ncols); run_round<6, 3, DIF>(tile, 0, tws, fp, ncols); }
+        if (!DIF) { run_round<6, 3, DIF, LAZY>(tile, 0, tws, fp, ncols); run_round<6, 3, DIF, LAZY>(tile, 3, tws, fp, ncols); }
+        else      { run_round<6, 3, DIF, LAZY>(tile, 3, tws, fp, ncols); run_round<6, 3, DIF, LAZY>(tile, 0, tws, fp, ncols); }
     } else if constexpr (R_LOG == 7) {
-        if (!DIF) { run_round<7, 4, DIF>(tile, 0, tws, fp, ncols); run_round<7, 3, DIF>(tile, 4, tws, fp, ncols); }
-        else      { run_round<7, 3, DIF>(tile, 4, tws, fp, ncols); run_round<7, 4, DIF>(tile, 0, tws, fp, ncols); }
+        if (!DIF) { run_round<7, 4, DIF, LAZY>(tile, 0, tws, fp, ncols); run_round<7, 3, DIF, LAZY>(tile, 4, tws, fp, ncols); }
+        else      { run_round<7, 3, DIF, LAZY>(tile, 4, tws, fp, ncols); run_round<7, 4, DIF, LAZY>(tile, 0, tws, fp, ncols); }
     } else if constexpr (R_LOG == 8) {
-        if (!DIF) { run_round<8, 4, DIF>(tile, 0, tws, fp, ncols); run_round<8, 4, DIF>(tile, 4, tws, fp, ncols); }
-        else      { run_round<8, 4, DIF>(tile, 4, tws, fp, ncols); run_round<8, 4, DIF>(tile, 0, tws, fp, ncols); }
+        if (!DIF) { run_round<8, 4, DIF, LAZY>(tile, 0, tws, fp, ncols); run_round<8, 4, DIF, LAZY>(tile, 4, tws, fp, ncols); }
+        else      { run_round<8, 4, DIF, LAZY>(tile, 4, tws, fp, ncols); run_round<8, 4, DIF, LAZY>(tile, 0, tws, fp, ncols); }
     } else {
         static_assert(R_LOG == 9, "pass width");
-        if (!DIF) { run_round<9, 3, DIF>(tile, 0, tws, fp, ncols); run_round<9, 3, DIF>(tile, 3, tws, fp, ncols); run_round<9, 3, DIF>(tile, 6, tws, fp, ncols); }
-        else      { run_round<9, 3, DIF>(tile, 6, tws, fp, ncols); run_round<9, 3, DIF>(tile, 3, tws, fp, ncols); run_round<9, 3, DIF>(tile, 0, tws, fp, ncols); }
+        if (!DIF) { run_round<9, 3, DIF, LAZY>(tile, 0, tws, fp, ncols); run_round<9, 3, DIF, LAZY>(tile, 3, tws, fp, ncols); run_round<9, 3, DIF, LAZY>(tile, 6, tws, fp, ncols); }
+        else      { run_round<9, 3, DIF, LAZY>(tile, 6, tws, fp, ncols); run_round<9, 3, DIF, LAZY>(tile, 3, tws, fp, ncols); run_round<9, 3, DIF, LAZY>(tile, 0, tws, fp, ncols); }
     }
 }
 
@@ -287,6 +307,154 @@ void ntt_dif(stark_ctx* ctx, uint32_t* data, unsigned log_n, bool inverse_root, 
             dispatch_pass<true, true>(ctx, r, ps, batch * n / ((size_t)NTT_C << r));
         }
         hi = lo;
+    }
+    STARK_CUDA(cudaGetLastError());
+}
+
+// ---- blow-up-by-8 forward transform: one size-n NTT over 8 interleaved coset columns ------------------------
+// X[8k'+s] = sum_j c_j (g w_N^s)^j w_n^(j k'): the evaluation on the size-N = 8n coset is eight size-n
+// transforms (one per shift s) that share every butterfly twiddle and every inter-pass twiddle, and whose
+// outputs interleave into natural order.  Stored as D[n rows][8 columns] the eight columns of a row are 32
+// contiguous bytes: one twiddle is formed per ROW (not per element), global accesses are two 16-byte vectors
+// per row, and four adjacent rows make the 128-byte line.  Tile = 2^r rows x (4 row-groups x 8 columns).
+struct Lde8Pass {
+    const uint32_t* src;     // FIRST pass: coefficient source; later passes: unused (in place on dst)
+    uint32_t* dst;           // [n][8]
+    unsigned log_rows;       // n = 2^log_rows
+    unsigned lo;             // lowest row-index bit of this pass
+    unsigned src_len;        // FIRST: valid entries of src
+    int src_bitrev;          // FIRST: 1 = src is in bit-reversed row order (output of the DIF inverse), 0 = natural coefficients
+    int last;                // canonicalise on store
+    PowTable scale;          // FIRST: c0 * g^j
+    PowTable shift;          // FIRST: w_N^j  (N = 8n)
+    PowTable tw;             // later passes: w_n^e
+    const uint32_t* small;
+    unsigned small_log;
+};
+
+template <int R_LOG, bool FIRST>
+__global__ void lde8_pass_kernel(Lde8Pass ps, FieldParams fp) {
+    extern __shared__ uint32_t smem[];
+    constexpr int R = 1 << R_LOG;
+    uint32_t* tile = smem;                    // [R][33]: word g*8+s of row t
+    uint32_t* tws = smem + R * NTT_TS;
+    for (int k = threadIdx.x; k < (R >> 1); k += blockDim.x) tws[k] = ps.small[(size_t)k << (ps.small_log - R_LOG)];
+
+    const size_t tile_id = blockIdx.x;
+    size_t row_base;          // FIRST: first row of the tile; else row of (t = 0, g = 0)
+    uint32_t low0 = 0;
+    if (FIRST) {
+        row_base = tile_id * 4 * (size_t)R;
+    } else {
+        const size_t tiles_per_high = ((size_t)1 << ps.lo) / 4;
+        const size_t high = tile_id / tiles_per_high;
+        low0 = (uint32_t)(tile_id % tiles_per_high) * 4;
+        row_base = (high << (ps.lo + R_LOG)) | low0;
+    }
+    const unsigned tw_shift = ps.log_rows - ps.lo - R_LOG;
+
+    // ---- load: one work item = one row (8 columns) ----
+    for (int i = threadIdx.x; i < 4 * R; i += blockDim.x) {
+        uint32_t v[8];
+        int t, g;
+        if (FIRST) {
+            g = i >> R_LOG; t = i & (R - 1);
+            const uint32_t q = (uint32_t)(row_base + i);                    // row index = position in bit-reversed coefficient order
+            const uint32_t j = bitrev_bits(q, ps.log_rows);                 // the coefficient it holds
+            const uint32_t si = ps.src_bitrev ? q : j;
+            uint32_t c = si < ps.src_len ? ps.src[si] : 0u;
+            const uint32_t b = pow_lookup(ps.shift, j, fp);                 // w_N^j
+            v[0] = mont_mul(c, pow_lookup(ps.scale, j, fp), fp);            // c_j g^j
+#pragma unroll
+            for (int k = 1; k < 8; k++) v[k] = mont_mul(v[k - 1], b, fp);    // ... * w_N^(j s)
+        } else {
+            g = i & 3; t = i >> 2;
+            const size_t row = row_base + ((size_t)t << ps.lo) + g;
+            const uint4* p = reinterpret_cast<const uint4*>(ps.dst + row * 8);
+            uint4 a = p[0], bq = p[1];
+            const uint32_t e = bitrev_bits((uint32_t)t, R_LOG) * (low0 + (uint32_t)g);
+            const uint32_t tw = pow_lookup(ps.tw, e << tw_shift, fp);
+            v[0] = mont_mul(a.x, tw, fp); v[1] = mont_mul(a.y, tw, fp); v[2] = mont_mul(a.z, tw, fp); v[3] = mont_mul(a.w, tw, fp);
+            v[4] = mont_mul(bq.x, tw, fp); v[5] = mont_mul(bq.y, tw, fp); v[6] = mont_mul(bq.z, tw, fp); v[7] = mont_mul(bq.w, tw, fp);
+        }
+        uint32_t* o = tile + t * NTT_TS + g * 8;
+#pragma unroll
+        for (int k = 0; k < 8; k++) o[k] = v[k];
+    }
+    __syncthreads();
+
+    run_rounds<R_LOG, false, true>(tile, tws, fp, NTT_C);
+
+    // ---- store ----
+    for (int i = threadIdx.x; i < 4 * R; i += blockDim.x) {
+        int t, g;
+        size_t row;
+        if (FIRST) { g = i >> R_LOG; t = i & (R - 1); row = row_base + i; }
+        else { g = i & 3; t = i >> 2; row = row_base + ((size_t)t << ps.lo) + g; }
+        const uint32_t* o = tile + t * NTT_TS + g * 8;
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = ps.last ? canonical(o[k], fp) : o[k];
+        uint4* p = reinterpret_cast<uint4*>(ps.dst + row * 8);
+        p[0] = make_uint4(v[0], v[1], v[2], v[3]);
+        p[1] = make_uint4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+template <int R_LOG, bool FIRST>
+static void launch_lde8(stark_ctx* ctx, const Lde8Pass& ps, size_t tiles) {
+    constexpr int R = 1 << R_LOG;
+    int threads = (R * NTT_C) >> 4;
+    if (threads < 64) threads = 64;
+    if (threads > 1024) threads = 1024;
+    size_t smem = (size_t)(R * NTT_TS + (R >> 1) + 1) * sizeof(uint32_t);
+    auto kern = lde8_pass_kernel<R_LOG, FIRST>;
+    if (smem > 48 * 1024) STARK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)tiles, threads, smem, ctx->stream>>>(ps, ctx->fp);
+    ctx->launches++;
+}
+template <bool FIRST>
+static void dispatch_lde8(stark_ctx* ctx, unsigned r, const Lde8Pass& ps, size_t tiles) {
+    switch (r) {
+        case 5: launch_lde8<5, FIRST>(ctx, ps, tiles); break;
+        case 6: launch_lde8<6, FIRST>(ctx, ps, tiles); break;
+        case 7: launch_lde8<7, FIRST>(ctx, ps, tiles); break;
+        case 8: launch_lde8<8, FIRST>(ctx, ps, tiles); break;
+        case 9: launch_lde8<9, FIRST>(ctx, ps, tiles); break;
+        default: throw StarkError(ST_INTERNAL, "lde8: bad pass width");
+    }
+}
+
+bool lde8_supported(unsigned log_rows) { return log_rows >= 10; }
+
+// dst[8k'+s] = sum_j c_j (base w_N^s)^j w_n^(j k'), c_j = c0 * src[...]:
+//   src_bitrev = false: src holds natural-order coefficients (src_len of them, zero above)
+//   src_bitrev = true : src holds n values in bit-reversed coefficient order (the DIF inverse's output)
+void lde8_forward(stark_ctx* ctx, const uint32_t* src, size_t src_len, bool src_bitrev, uint32_t* dst, unsigned log_rows,
+                  uint64_t base, uint64_t c0) {
+    STARK_REQUIRE(lde8_supported(log_rows), "lde8: too small");
+    const unsigned log_N = log_rows + 3;
+    check_size(ctx, log_N);
+    const size_t n = (size_t)1 << log_rows;
+    const TwiddleSet& tw_rows = ctx->twiddles(log_rows);
+    const TwiddleSet& tw_N = ctx->twiddles(log_N);
+    ScaleTable st;
+    build_scale_table(ctx, base % ctx->modulus, c0 % ctx->modulus, log_rows, st);
+    std::vector<unsigned> bits = plan_bits(log_rows);       // every entry in [5, 9] for log_rows >= 10
+    KernelTimer kt(ctx, stark_ctx::CAT_NTT, 8.0 * (double)n + 8.0 * 8.0 * (double)n);
+    unsigned lo = 0;
+    for (size_t i = 0; i < bits.size(); i++) {
+        unsigned r = bits[i];
+        Lde8Pass ps{};
+        ps.src = src; ps.dst = dst; ps.log_rows = log_rows; ps.lo = lo;
+        ps.src_len = (unsigned)(src_len < n ? src_len : n); ps.src_bitrev = src_bitrev;
+        ps.last = (i + 1 == bits.size());
+        ps.scale = st.view; ps.shift = tw_N.fwd(); ps.tw = tw_rows.fwd();
+        ps.small = ctx->small_fwd.as<uint32_t>(); ps.small_log = ctx->small_log;
+        size_t tiles = n / ((size_t)4 << r);
+        if (i == 0) dispatch_lde8<true>(ctx, r, ps, tiles);
+        else dispatch_lde8<false>(ctx, r, ps, tiles);
+        lo += r;
     }
     STARK_CUDA(cudaGetLastError());
 }
