@@ -186,7 +186,9 @@ class FourStepLDE:
     exch. 1  all-to-all: rank s receives the rows k1 in its slice                        (NCCL / NVLink)
     phase C  batched size-N2 NTTs over n2 for the local rows                             (local kernels)
     exch. 2  all-to-all back to natural order: rank t receives k in [t*N/G, (t+1)*N/G)   (NCCL / NVLink)
-    Each exchange moves 4*N/G bytes per rank, (G-1)/G of it over NVLink.
+    Each exchange moves 4*N/G bytes per rank, (G-1)/G of it over NVLink.  The coefficients are taken from a
+    device vector that every rank holds (they are 1/blowup of the domain); the local transposes are strided
+    device copies straight into the vector the next kernel works on.
     """
 
     def __init__(self, sp, ctx, log_n: int, offset: int, rank: int, world: int):
@@ -194,53 +196,61 @@ class FourStepLDE:
         self.a, self.b = four_step_plan(log_n, world)
         self.n1, self.n2 = 1 << self.a, 1 << self.b
         self.omega = ctx.root_of_unity(log_n)
+        self._keep = []
 
-    def phase_a(self, coeffs: np.ndarray):
-        """-> torch int32 tensor [world (dest)][n2/G][n1/G] ready for the first exchange.
-        Only the rows of the [N1][N2] coefficient matrix that hold coefficients are uploaded (an LDE input is
-        zero above n = N/blowup); the column-major local layout [n2'][n1] is assembled on the device."""
+    def _handoff_to_lib(self):
         import torch
-        ctx, w = self.ctx, self.n2 // self.world
-        rows = -(-len(coeffs) // self.n2)                      # rows of the matrix that are not all zero
-        host = np.zeros((rows, w), dtype=np.uint64)
-        padded = np.zeros(rows * self.n2, dtype=np.uint64)
-        padded[: len(coeffs)] = coeffs
-        host[:, :] = padded.reshape(rows, self.n2)[:, self.rank * w:(self.rank + 1) * w]
-        up = ctx.upload(host.reshape(-1))                      # [rows][w]
-        v = ctx.zeros(w * self.n1)                             # [w][n1]
-        ctx.sync()
-        _as_torch(v).view(w, self.n1)[:, :rows] = _as_torch(up).view(rows, w).t()
         torch.cuda.current_stream().synchronize()
-        up.free()
+
+    def phase_a(self, coeffs):
+        """coeffs: host array or device Vec of the (<= N) coefficients -> torch int32 tensor
+        [world (dest)][n2/G][n1/G] ready for the first exchange."""
+        ctx, w = self.ctx, self.n2 // self.world
+        cv = coeffs if hasattr(coeffs, "device_ptr") else ctx.upload(coeffs)
+        n_c = len(cv)
+        rows = -(-n_c // self.n2)                              # rows of the [N1][N2] matrix that hold coefficients
+        v = ctx.zeros(w * self.n1)                             # [n2'][n1]
+        ctx.sync()
+        full = rows if rows * self.n2 == n_c else rows - 1    # complete rows
+        src = _as_torch(cv)
+        dst = _as_torch(v).view(w, self.n1)
+        if full:
+            dst[:, :full] = src[: full * self.n2].view(full, self.n2)[:, self.rank * w:(self.rank + 1) * w].t()
+        if full != rows:                                       # ragged last row
+            tail = src[full * self.n2:]
+            lo, hi = self.rank * w, min((self.rank + 1) * w, tail.numel())
+            if hi > lo:
+                dst[: hi - lo, full] = tail[lo:hi]
+        self._handoff_to_lib()
         if self.offset % ctx.modulus != 1:
             ctx.pow_mul_dev(v, self.n1, self.rank * w, False, self.n2, self.offset, 1, self.log_n)
         ctx.ntt_batch_dev(v, self.a)
         ctx.pow_mul_dev(v, self.n1, self.rank * w, True, 0, self.omega, 1, self.log_n)
         ctx.sync()
         t = _as_torch(v).view(w, self.world, self.n1 // self.world).permute(1, 0, 2).contiguous()
-        self._keep = v
+        self._keep = [v, cv]
         return t
 
     def phase_c(self, recv):
         """recv: [world (src)][n2/G][n1/G] == [n2][k1'] -> tensor [world (dest)][n1/G][n2/G] for the second exchange."""
-        import torch
         ctx = self.ctx
-        z = recv.reshape(self.n2, self.n1 // self.world).t().contiguous()           # [k1'][n2]
-        torch.cuda.current_stream().synchronize()
-        v = ctx.from_device(z.data_ptr(), z.numel())
+        v = ctx.zeros(self.n2 * (self.n1 // self.world))
+        ctx.sync()
+        _as_torch(v).view(self.n1 // self.world, self.n2).copy_(recv.reshape(self.n2, self.n1 // self.world).t())   # [k1'][n2]
+        self._handoff_to_lib()
         ctx.ntt_batch_dev(v, self.b)
         ctx.sync()
         t = _as_torch(v).view(self.n1 // self.world, self.world, self.n2 // self.world).permute(1, 0, 2).contiguous()
-        self._keep = v
+        self._keep = [v]
         return t
 
     def finish(self, recv):
         """recv: [world (src)][n1/G][n2/G] == [k1][k2'] -> Vec with this rank's natural-order block."""
-        import torch
-        nat = recv.reshape(self.n1, self.n2 // self.world).t().contiguous()        # [k2'][k1]: p = k1 + N1*k2'
-        torch.cuda.current_stream().synchronize()
-        out = self.ctx.from_device(nat.data_ptr(), nat.numel())
-        self._keep = None
+        out = self.ctx.zeros(self.n1 * (self.n2 // self.world))
+        self.ctx.sync()
+        _as_torch(out).view(self.n2 // self.world, self.n1).copy_(recv.reshape(self.n1, self.n2 // self.world).t())  # p = k1 + N1*k2'
+        self._handoff_to_lib()
+        self._keep = []
         return out
 
 

