@@ -282,7 +282,8 @@ def run_b200(args):
 
     line = {"metric": METRIC, "value": world * n / (ms_dev * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32 field arithmetic (p < 2^32, u64 at the ABI) + u32 SHA-256", "data": "synthetic",
+            "dtype": "u32", "dtype_note": "u32 Montgomery field arithmetic (p = 3221225473 < 2^32; u64 at the ABI) and 32-bit SHA-256 words",
+            "data": "synthetic",
             "config": {"workload": f"cfg3: fri_commit + decommit_fri, degree 2^{log_deg}-1 polynomial on the 2^{log_n} coset 5*<w>, "
                                    f"p=3221225473, {n_layers} layers, {QUERIES} queries; one column per GPU",
                        "log_domain": log_n, "blowup": 1 << args.log_blowup, "queries": QUERIES, "layers": n_layers,

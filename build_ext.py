@@ -29,6 +29,10 @@ def _deps(src: str) -> list[str]:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        if os.path.exists(OUT) and not force:      # a box without the toolkit: use the library that travelled with the tree
+            return OUT
+        raise RuntimeError("nvcc not found and no prebuilt libstark_b200.so in the tree")
     os.makedirs(BUILD, exist_ok=True)
     ccbin = _host_cxx()
     extra = os.environ.get("STARK_NVCC_DEFS", "").split()     # e.g. "-DSTARK_SHA_ADDS_ON_FMA=0" for kernel experiments
