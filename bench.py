@@ -113,6 +113,17 @@ def measured_peaks() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic() -> tuple:
+    """DRAM bytes per hashing launch from the committed ncu capture (profiles/rNN_traffic.json), or None."""
+    pdir = os.path.join(ROOT, "profiles")
+    try:
+        f = sorted(x for x in os.listdir(pdir) if x.endswith("_traffic.json"))[-1]
+        d = json.load(open(os.path.join(pdir, f)))
+        return d["hashing_dram_bytes_per_launch"], f"profiles/{f}: {d['hashing_dram_bytes_per_step'] / 1e9:.2f} GB over {d['hashing_launches']} launches per step"
+    except Exception:
+        return None, None
+
+
 def layer_sizes(log_n: int, log_deg: int) -> list[int]:
     return [1 << (log_n - k) for k in range(log_deg + 1)]
 
@@ -316,7 +327,8 @@ def run_b200(args):
                 "bound": "int", "achieved": achieved, "peak": alu_peak, "unit": "Tint-op/s", "frac": achieved / alu_peak,
                 "peak_source": "stark_measure_int_peak on this GPU: SHF+LOP3+IADD3 register chains (ALU pipe); "
                                f"with IMAD co-issue {mix_peak:.1f}",
-                "traffic": None, "launches_per_step": hash_launches, "kernel_ms_per_step": hash_ms,
+                "traffic": ncu_traffic()[0], "traffic_source": ncu_traffic()[1],
+                "launches_per_step": hash_launches, "kernel_ms_per_step": hash_ms,
                 "share_of_step": hash_ms / ms_instr,
                 "algorithmic": "1384 int-ops per SHA-256 compression; leaf = 1, node = 2 compressions (SURVEY.md 8d)",
                 "note": "achieved counts the ALGORITHMIC 1384 instructions per compression; the kernel executes fewer on the ALU pipe "

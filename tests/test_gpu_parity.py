@@ -402,3 +402,47 @@ def test_lde_roundtrip_2e24(sp, orc, ctx):
     assert np.array_equal(back.download(), c)
     lde = ctx.coset_lde_dev(ev, 5, 1, 7)           # same polynomial on a 2x larger coset
     assert int(lde.download(0, 1)[0]) == orc.poly_evaluate(c, 7, P)    # the reference's Horner at the first coset point (2^24 steps)
+
+
+# ---------------------------------------------------------------- error behaviour at the boundary
+def test_argument_errors(sp, orc, ctx):
+    v = ctx.upload(np.arange(10, dtype=np.uint64))
+    with pytest.raises(sp.StarkError) as e:
+        v.download(5, 10)                                    # range out of bounds
+    assert e.value.code == 1
+    with pytest.raises(sp.StarkError):
+        ctx.coset_interpolate_dev(v, 5)                      # length is not a power of two
+    t = sp.MerkleTree.new(ctx, np.arange(10, dtype=np.uint64))
+    with pytest.raises(sp.StarkError):
+        t.get_authentication_path(10)                        # no such leaf
+    with pytest.raises(sp.StarkError):
+        t.node(0, 0)                                         # level-0 digests are not stored
+    other = sp.Context(998244353, 3, 0)
+    try:
+        with pytest.raises(sp.StarkError):
+            other.batch_inverse_dev(v)                       # vector belongs to another context
+    finally:
+        other.close()
+    # the library is still healthy after the errors
+    assert sp.MerkleTree.new(ctx, [0, 1, 2]).root() == "07f15c470799d408152313c5b0e914969f00e954b6df62e826e235bd7d06d424"
+
+
+def test_two_contexts_interleaved(sp, orc):
+    """Contexts are independent (own stream, own reduction scratch and barrier counter)."""
+    a, b = sp.Context(P, 5, 0), sp.Context(P, 5, 0)
+    try:
+        c1, c2 = orc.synthetic_poly_exact_degree(1, 1 << 12), orc.synthetic_poly_exact_degree(2, 1 << 13)
+        p1, r1 = sp.fri_begin(a, c1, 15, 5)
+        p2, r2 = sp.fri_begin(b, c2, 16, 5)
+        for beta in (3, 5, 7, 11):
+            p1.fold(beta); p2.fold(beta + 1)
+        for pr, c, log_n, betas in ((p1, c1, 15, (3, 5, 7, 11)), (p2, c2, 16, (4, 6, 8, 12))):
+            e = orc.coset_evaluate(c, log_n, 5, orc.root_of_unity(log_n), P)
+            off, w = 5, orc.root_of_unity(log_n)
+            for k, beta in enumerate(betas):
+                e = orc.fri_fold_evals(e, beta, off, w, P)
+                off, w = off * off % P, w * w % P
+                assert np.array_equal(pr.layer(k + 1), e)
+                assert pr.tree(k + 1).root_bytes() == orc.merkle_root_only(e)
+    finally:
+        a.close(); b.close()
