@@ -183,6 +183,15 @@ const stark_tree* stark_fri_layer_tree(const stark_fri* f, size_t k);           
  *   BE8(evals[idx]) || path(idx) || BE8(evals[sib]) || path(sib),  idx = index % len_k, sib = (idx+len_k/2) % len_k
  * written back to back.  *len receives the total; call with out == NULL to size. */
 int stark_fri_open(const stark_fri* f, const uint64_t* indices, size_t n_idx, uint8_t* out, size_t cap, size_t* len);
+/* Multi-GPU layer 0: the evaluations were produced by the four-step NTT and hashed in leaf
+ * ranges on several GPUs.  stark_fri_begin_external adopts the gathered layer and its combined root (no
+ * evaluation, no hashing); the folds and later layers are stark_fri_fold as usual.  Layer-0 openings are made
+ * on the owning ranks (stark_merkle_open on their subtree + the top levels); stark_fri_open_layers returns the
+ * records of layers >= first_layer in the stark_fri_open format. */
+int stark_fri_begin_external(stark_ctx* ctx, const stark_vec* coeffs, unsigned log_n, uint64_t offset,
+                             const stark_vec* layer0, const uint8_t root0[32], stark_fri** out);
+int stark_fri_open_layers(const stark_fri* f, size_t first_layer, const uint64_t* indices, size_t n_idx, uint8_t* out,
+                          size_t cap, size_t* len);
 void stark_fri_destroy(stark_fri* f);
 
 int stark_fri_commit(stark_ctx* ctx, const uint64_t* coeffs, size_t n_coeffs, unsigned log_n, uint64_t offset,

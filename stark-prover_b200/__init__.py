@@ -123,6 +123,8 @@ def lib() -> C.CDLL:
     sig("stark_fri_layer_read", I, vp, szt, szt, szt, vp)
     sig("stark_fri_layer_tree", vp, vp, szt)
     sig("stark_fri_open", I, vp, vp, szt, vp, szt, C.POINTER(szt))
+    sig("stark_fri_begin_external", I, vp, vp, C.c_uint, u64, vp, vp, C.POINTER(vp))
+    sig("stark_fri_open_layers", I, vp, szt, vp, szt, vp, szt, C.POINTER(szt))
     sig("stark_fri_destroy", None, vp)
     sig("stark_fri_commit", I, vp, vp, szt, C.c_uint, u64, vp, C.POINTER(vp))
     sig("stark_fri_commit_dev", I, vp, vp, C.c_uint, u64, vp, C.POINTER(vp))
@@ -501,12 +503,12 @@ class FriProof:
         _check(lib().stark_fri_final(self.h, C.byref(v), C.byref(n)))
         return np.array([v.value] if n.value else [], dtype=np.uint64)
 
-    def open(self, indices: Sequence[int]) -> bytes:
+    def open(self, indices: Sequence[int], first_layer: int = 0) -> bytes:
         idx = _arr(list(indices))
         n = szt(0)
-        _check(lib().stark_fri_open(self.h, _ptr(idx), idx.size, None, 0, C.byref(n)))
+        _check(lib().stark_fri_open_layers(self.h, first_layer, _ptr(idx), idx.size, None, 0, C.byref(n)))
         out = np.zeros(max(n.value, 1), dtype=np.uint8)
-        _check(lib().stark_fri_open(self.h, _ptr(idx), idx.size, _ptr(out), out.size, C.byref(n)))
+        _check(lib().stark_fri_open_layers(self.h, first_layer, _ptr(idx), idx.size, _ptr(out), out.size, C.byref(n)))
         return out[: n.value].tobytes()
 
     def free(self):
@@ -531,6 +533,16 @@ def fri_begin(ctx: Context, coeffs, log_n: int, offset: int) -> tuple[FriProof, 
         c = _arr(coeffs)
         _check(lib().stark_fri_begin(ctx.h, _ptr(c), c.size, log_n, offset, C.byref(h), _ptr(root)))
     return FriProof(ctx, h), root.tobytes()
+
+
+def fri_begin_external(ctx: Context, coeffs: "Vec", log_n: int, offset: int, layer0: "Vec", root0: bytes) -> FriProof:
+    """Adopts a layer 0 that was evaluated and hashed in leaf ranges on several GPUs (multi_gpu.py)."""
+    h = vp()
+    r = np.frombuffer(root0, dtype=np.uint8).copy()
+    _check(lib().stark_fri_begin_external(ctx.h, coeffs.h, log_n, offset, layer0.h, _ptr(r), C.byref(h)))
+    pr = FriProof(ctx, h)
+    pr._layer0 = layer0            # the proof shares the vector's device memory
+    return pr
 
 
 def fri_commit(ctx: Context, poly, domain: CosetFri, channel: Channel) -> FriProof:

@@ -545,6 +545,7 @@ extern "C" int stark_merkle_open(const stark_tree* t, size_t idx, uint8_t* path,
     API_BEGIN
     STARK_REQUIRE(t && path_len, "merkle_open: null argument");
     STARK_REQUIRE(idx < t->shape.n, "merkle_open: leaf index out of range");
+    STARK_REQUIRE(!t->external, "merkle_open: this tree's levels are held by other ranks (leaf-range sharding); open on the owner");
     size_t pl = merkle_path_len(t->shape.n, idx);
     *path_len = pl;
     if (!path) return ST_OK;
@@ -561,6 +562,7 @@ extern "C" int stark_merkle_node(const stark_tree* t, size_t level, size_t j, ui
     API_BEGIN
     STARK_REQUIRE(t && out, "merkle_node: null argument");
     STARK_REQUIRE(level >= 1 && level <= t->shape.depth && j < t->shape.len[level], "merkle_node: no such node (level 0 digests are not stored)");
+    STARK_REQUIRE(!t->external, "merkle_node: this tree's levels are held by other ranks");
     CtxGuard g(t->ctx);
     uint32_t w[8];
     STARK_CUDA(cudaMemcpyAsync(w, t->nodes.as<uint32_t>() + 8 * (t->shape.off[level] + j), 32, cudaMemcpyDeviceToHost, t->ctx->stream));
@@ -748,9 +750,11 @@ extern "C" int stark_fri_layer_read(const stark_fri* f, size_t k, size_t offset,
 extern "C" const stark_tree* stark_fri_layer_tree(const stark_fri* f, size_t k) { return (f && k < f->trees.size()) ? f->trees[k].get() : nullptr; }
 
 // descriptors for one query index across all layers (fri_commit.rs:145-163)
-static size_t fri_query_descs(const stark_fri* f, size_t index, size_t out_off, std::vector<OpenDesc>& d) {
-    for (auto& tp : f->trees) {
-        const stark_tree* t = tp.get();
+static size_t fri_query_descs(const stark_fri* f, size_t index, size_t out_off, std::vector<OpenDesc>& d, size_t first_layer = 0) {
+    for (size_t k = first_layer; k < f->trees.size(); k++) {
+        const stark_tree* t = f->trees[k].get();
+        STARK_REQUIRE(!t->external, "fri open: layer 0 was committed in leaf ranges on several GPUs; open it on the owners "
+                                    "(stark_fri_open_layers with first_layer = 1 gives the rest)");
         size_t len = t->shape.n;
         size_t idx = index % len, sib = (idx + len / 2) % len;              // :152-153
         for (size_t which : {idx, sib}) {
@@ -772,6 +776,52 @@ extern "C" int stark_fri_open(const stark_fri* f, const uint64_t* indices, size_
     STARK_REQUIRE(cap >= total, "fri_open: buffer too small");
     CtxGuard g(f->ctx);
     open_records(f->ctx, d, total, out);
+    API_END
+}
+extern "C" int stark_fri_open_layers(const stark_fri* f, size_t first_layer, const uint64_t* indices, size_t n_idx, uint8_t* out,
+                                     size_t cap, size_t* len) {
+    API_BEGIN
+    STARK_REQUIRE(f && len && (indices || n_idx == 0) && first_layer <= f->trees.size(), "fri_open_layers: bad argument");
+    std::vector<OpenDesc> d;
+    size_t total = 0;
+    for (size_t q = 0; q < n_idx; q++) total = fri_query_descs(f, (size_t)indices[q], total, d, first_layer);
+    *len = total;
+    if (!out) return ST_OK;
+    STARK_REQUIRE(cap >= total, "fri_open_layers: buffer too small");
+    CtxGuard g(f->ctx);
+    open_records(f->ctx, d, total, out);
+    API_END
+}
+// Layer 0 was evaluated and hashed elsewhere (four-step LDE + leaf-range subtrees on several GPUs): adopt the
+// gathered evaluations and the combined root; folding and the later layers proceed as in stark_fri_begin.
+extern "C" int stark_fri_begin_external(stark_ctx* ctx, const stark_vec* coeffs, unsigned log_n, uint64_t offset,
+                                        const stark_vec* layer0, const uint8_t root0[32], stark_fri** out) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && out && coeffs && layer0 && root0 && coeffs->ctx == ctx && layer0->ctx == ctx, "fri_begin_external: bad argument");
+    CtxGuard g(ctx);
+    check_offset(ctx, offset);
+    STARK_REQUIRE(log_n <= 30 && log_n <= ctx->two_adicity && layer0->n == ((size_t)1 << log_n), "fri_begin_external: layer 0 must have 2^log_n evaluations");
+    size_t len = 0;
+    if (coeffs->n) {
+        poly_degree(ctx, coeffs->buf->as<uint32_t>(), coeffs->n, ctx->d_result);
+        STARK_CUDA(cudaStreamSynchronize(ctx->stream));
+        len = (size_t)ctx->h_result->degree_plus1;
+    }
+    STARK_REQUIRE(len <= layer0->n, "fri: polynomial has more coefficients than the domain has points");
+    std::unique_ptr<stark_fri> f(new stark_fri());
+    f->ctx = ctx; f->log_n = log_n; f->offset0 = offset % ctx->modulus;
+    f->cur_log = log_n; f->cur_offset = f->offset0;
+    size_t m = (size_t)1 << ceil_log2(std::max<size_t>(len, 1));
+    f->coeffs = make_buf(m * 4, ctx->stream);                 // private copy: folds replace it
+    STARK_CUDA(cudaMemsetAsync(f->coeffs->p, 0, m * 4, ctx->stream));
+    if (len) STARK_CUDA(cudaMemcpyAsync(f->coeffs->p, coeffs->buf->p, len * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    f->coeff_len = len;
+    std::unique_ptr<stark_tree> t(new stark_tree());
+    t->ctx = ctx; t->leaves = layer0->buf; t->shape = TreeShape::make(layer0->n); t->external = true;
+    for (int i = 0; i < 8; i++)
+        t->root_words[i] = ((uint32_t)root0[4 * i] << 24) | ((uint32_t)root0[4 * i + 1] << 16) | ((uint32_t)root0[4 * i + 2] << 8) | root0[4 * i + 3];
+    f->trees.push_back(std::move(t));
+    *out = f.release();
     API_END
 }
 extern "C" void stark_fri_destroy(stark_fri* f) {

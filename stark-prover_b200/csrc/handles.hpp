@@ -17,6 +17,7 @@ struct stark_tree {
     starkb200::TreeShape shape;
     starkb200::DevBuf nodes;
     uint32_t root_words[8] = {0};
+    bool external = false;           // levels live elsewhere (leaf ranges hashed on other GPUs): only leaves + root here
 };
 
 // FRIProof (reference src/fri/fri_commit.rs:9-13): trees[k]->leaves are fri_layers[k], trees[k] is

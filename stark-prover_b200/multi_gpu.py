@@ -282,3 +282,97 @@ def four_step_lde_emulated(sp, ctx, coeffs: np.ndarray, log_n: int, offset: int,
     send2 = [fs.phase_c(recv[r]).clone() for r, fs in enumerate(ranks)]
     recv2 = [torch.stack([send2[src][dst] for src in range(world)]) for dst in range(world)]
     return [fs.finish(recv2[r]) for r, fs in enumerate(ranks)]
+
+
+# ------------------------------------------------------------------------------------------------ cfg5: FRI commit with a sharded layer 0
+class MultiGpuFri:
+    """What `fri_commit_multi` leaves behind for `decommit_fri_multi`: the owner's leaf range and subtree on every
+    rank, the subtree roots, and (rank 0) the FRIProof whose layer 0 is the gathered evaluations."""
+
+    def __init__(self, log_n, block, subtree, subtree_roots, proof):
+        self.log_n, self.block, self.subtree, self.subtree_roots, self.proof = log_n, block, subtree, subtree_roots, proof
+
+
+def _bcast_int(value: int, group=None) -> int:
+    import torch
+    dist = _dist()
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.int64, device=_comm_device(group))
+    dist.broadcast(t, src=0, group=group)
+    return int(t.item())
+
+
+def fri_commit_multi(sp, ctx, coeffs, log_n: int, offset: int, channel, rank: int, world: int, group=None) -> MultiGpuFri:
+    """fri_commit (reference src/fri/fri_commit.rs:72-122) with layer 0 spread over `world` GPUs:
+    four-step LDE -> each rank hashes its contiguous leaf range -> subtree roots gathered -> the evaluations are
+    all-gathered and rank 0 runs the (unpartitioned) fold/commit loop against the channel.  The transcript is the
+    single-GPU one, byte for byte.  `channel` is only used on rank 0."""
+    import torch
+    dist = _dist()
+    cvec = coeffs if hasattr(coeffs, "device_ptr") else ctx.upload(coeffs)
+    block = four_step_lde(sp, ctx, cvec, log_n, offset, rank, world, group)
+    subtree = sp.MerkleTree.new(ctx, block)
+    root0, subs = commit_leaf_ranges(subtree.root_bytes, rank, world, group)
+    ctx.sync()
+    mine = _as_torch(block)
+    if world > 1:
+        full = torch.empty(mine.numel() * world, dtype=mine.dtype, device=mine.device)
+        dist.all_gather_into_tensor(full, mine, group=group)
+    else:
+        full = mine
+    proof = None
+    if rank == 0:
+        torch.cuda.current_stream().synchronize()
+        layer0 = ctx.from_device(full.data_ptr(), full.numel())
+        proof = sp.fri_begin_external(ctx, cvec, log_n, offset, layer0, root0)
+        channel.send(root0.hex().encode())                                   # fri_commit.rs:86
+        while proof.degree >= 1:                                             # :89
+            beta = channel.receive_random_field_element()                    # :91
+            channel.send(proof.fold(beta).hex().encode())                    # :94-100
+        fin = proof.final_poly()
+        channel.send(int(fin[0] if len(fin) else 0).to_bytes(8, "big"))      # :109-114
+    return MultiGpuFri(log_n, block, subtree, subs, proof)
+
+
+def feed_layer_records(channel, blob: bytes, layer_lens: Sequence[int], index: int) -> None:
+    """Sends the records of `stark_fri_open_layers` in the reference's order (fri_commit.rs:145-163)."""
+    off = 0
+    for n in layer_lens:
+        idx, depth = index % n, n.bit_length() - 1
+        if n == 1:
+            channel.send(blob[off:off + 8])                                  # :147-149, then falls through as written
+        for _ in (idx, (idx + n // 2) % n):
+            plen = 32 * depth
+            channel.send(blob[off:off + 8])
+            channel.send(blob[off + 8:off + 8 + plen])
+            off += 8 + plen
+    assert off == len(blob)
+
+
+def decommit_fri_multi(sp, mp: MultiGpuFri, num_queries: int, max_index: int, channel, rank: int, world: int, group=None) -> None:
+    """decommit_fri (fri_commit.rs:168-179) when layer 0's tree lives in leaf ranges on `world` GPUs: the index is
+    drawn on rank 0 and broadcast; the owners of idx and idx + N/2 open their subtree, rank 0 appends the top
+    levels and feeds the channel; the remaining layers are opened on rank 0."""
+    n = 1 << mp.log_n
+    blk = n // world
+    depth_local = blk.bit_length() - 1
+    for _ in range(num_queries):
+        idx = channel.receive_random_int(0, max_index, True) if rank == 0 else 0
+        idx = _bcast_int(idx, group)
+        i0 = idx % n
+        recs = []
+        for which in (i0, (i0 + n // 2) % n):
+            owner, local = which // blk, which % blk
+            payload = np.zeros(8 + 32 * depth_local, dtype=np.uint8)
+            if rank == owner:
+                val = int(mp.block.download(local, 1)[0])
+                payload[:] = np.frombuffer(val.to_bytes(8, "big") + mp.subtree.get_authentication_path(local), dtype=np.uint8)
+            allp = all_gather_bytes(payload, group)
+            recs.append((allp[owner, :8].tobytes(), allp[owner, 8:].tobytes() + top_path(mp.subtree_roots, owner)))
+        if rank == 0:
+            for elem, path in recs:                                          # layer 0: :156-163
+                channel.send(elem)
+                channel.send(path)
+            lens = [mp.proof.layer_len(k) for k in range(1, mp.proof.num_layers)]
+            feed_layer_records(channel, mp.proof.open([idx], first_layer=1), lens, idx)

@@ -53,3 +53,20 @@ def test_commit_columns_single_rank(sp, orc, ctx):
         lde = orc.coset_evaluate(coef, log_rows + log_blowup, 5, orc.root_of_unity(log_rows + log_blowup), P)
         assert roots[c] == orc.merkle_root_only(lde)
         assert np.array_equal(keep[c][0].download(0, 64), lde[:64])       # sampled rows
+
+
+def test_fri_commit_multi_degenerate_world1(sp, orc, ctx):
+    """The sharded-layer-0 protocol with one rank: adopts the four-step layer 0, transcript == fri_commit's."""
+    mg = _mg()
+    log_n = 14
+    c = orc.synthetic_poly_exact_degree(4, 1 << 11)
+    ch, ch1, och = sp.Channel(P), sp.Channel(P), orc.Channel(P)
+    mp = mg.fri_commit_multi(sp, ctx, c, log_n, 5, ch, 0, 1)
+    mg.decommit_fri_multi(sp, mp, 3, (1 << log_n) - 1, ch, 0, 1)
+    pr = sp.fri_commit(ctx, c, sp.CosetFri(ctx, 5, log_n), ch1)
+    sp.decommit_fri(3, (1 << log_n) - 1, pr, ch1)
+    opr = orc.fri_commit_fast(c, log_n, 5, orc.root_of_unity(log_n), och, P)
+    orc.decommit_fri(3, (1 << log_n) - 1, opr, och)
+    assert ch.state == ch1.state == och.state and ch.proof == ch1.proof == och.proof
+    with pytest.raises(sp.StarkError):
+        mp.proof.tree(0).get_authentication_path(0)          # layer 0's levels are not held by the proof object

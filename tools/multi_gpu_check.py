@@ -95,6 +95,21 @@ def main():
             n_blk = (1 << log_n) // world
             assert np.array_equal(blk.download(), want[:n_blk]), "cfg5 block differs from the oracle"
         print(json.dumps(out), flush=True)
+    # ---------------- cfg5 continued: the whole FRI commit + openings with the sharded layer 0
+    log_f = 24 if args.full else 18
+    cf = orc.synthetic_poly_exact_degree(43, 1 << (log_f - 3), P)
+    ch = sp.Channel(P)
+    barrier(); t0 = time.perf_counter()
+    mp = mg.fri_commit_multi(sp, ctx, cf, log_f, 5, ch, rank, world)
+    mg.decommit_fri_multi(sp, mp, 8, (1 << log_f) - 1, ch, rank, world)
+    barrier(); t_fri = time.perf_counter() - t0
+    if rank == 0:
+        ch1 = sp.Channel(P)
+        pr1 = sp.fri_commit(ctx, cf, sp.CosetFri(ctx, 5, log_f), ch1)
+        sp.decommit_fri(8, (1 << log_f) - 1, pr1, ch1)
+        assert ch.state == ch1.state and ch.proof == ch1.proof, "sharded-layer-0 transcript differs from the single-GPU transcript"
+        print(json.dumps({"world": world, "cfg5_fri": {"log_domain": log_f, "seconds": t_fri, "transcript_state": ch.state,
+                                                       "identical_to_single_gpu": True}}), flush=True)
     barrier()
     if world > 1:
         dist.destroy_process_group()
