@@ -100,3 +100,30 @@ def test_commit_columns_gloo_world2(orc):
         lde = orc.coset_evaluate(coef, 9, 5, orc.root_of_unity(9), P)
         assert roots0[c] == orc.Tree(lde).root_hex()
     assert top0 == orc.Tree(orc.synthetic_column(9, 256)).root_hex()
+
+
+def test_feed_layer_records_order(orc):
+    """The host-side assembly of a query's messages (layer 0 from the owners, later layers from rank 0) reproduces
+    decommit_fri_layers (fri_commit.rs:137-165), including the length-1 layer that falls through."""
+    mg = _mg()
+    for log_n, log_deg in ((8, 5), (5, 5)):          # the second case folds down to a one-point layer
+        w = orc.root_of_unity(log_n)
+        c = orc.synthetic_poly_exact_degree(7, 1 << log_deg)
+        ch_a, ch_b = orc.Channel(P), orc.Channel(P)
+        pr_a = orc.fri_commit_fast(c, log_n, 5, w, ch_a, P)
+        pr_b = orc.fri_commit_fast(c, log_n, 5, w, ch_b, P)
+        index = 77 % (1 << log_n)
+        orc.decommit_fri_layers(index, pr_a, ch_a)
+        # layer 0 by hand (what the owners send), then the blob format of stark_fri_open_layers for layers >= 1
+        n0 = 1 << log_n
+        for which in (index % n0, (index % n0 + n0 // 2) % n0):
+            ch_b.send(int(pr_b.layer(0)[which]).to_bytes(8, "big"))
+            ch_b.send(pr_b.tree(0).path(which))
+        blob, lens = b"", []
+        for k in range(1, pr_b.num_layers):
+            lay, n = pr_b.layer(k), len(pr_b.layer(k))
+            lens.append(n)
+            for which in (index % n, (index % n + n // 2) % n):
+                blob += int(lay[which]).to_bytes(8, "big") + pr_b.tree(k).path(which)
+        mg.feed_layer_records(ch_b, blob, lens, index)
+        assert ch_a.state == ch_b.state and ch_a.proof == ch_b.proof
