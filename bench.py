@@ -154,6 +154,7 @@ def run_reference(args):
         return
     from oracle import pyoracle as orc
     orc.build()
+    orc.set_num_threads(len(os.sched_getaffinity(0)))      # torchrun exports OMP_NUM_THREADS=1: use every host core we may run on
     log_n = args.cpu_log_n
     log_deg = log_n - args.log_blowup
     coeffs = orc.synthetic_poly_exact_degree(43, 1 << log_deg, P)
@@ -351,6 +352,7 @@ def run_b200(args):
         line["algorithmic"] = alg
         # ---- CPU baseline beside it (bounded sample, all host threads)
         if not args.no_cpu_baseline and world == 1:
+            orc.set_num_threads(len(os.sched_getaffinity(0)))
             cl = args.cpu_log_n
             cc = orc.synthetic_poly_exact_degree(43, 1 << (cl - args.log_blowup), P)
             cpu_step(orc, cc, cl, QUERIES)
