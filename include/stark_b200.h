@@ -122,6 +122,22 @@ int stark_ntt_batch_dev(stark_ctx* ctx, stark_vec* v, unsigned log_m, int invers
 int stark_pow_mul_dev(stark_ctx* ctx, stark_vec* v, size_t inner_len, size_t outer0, int product, size_t inner_stride,
                       uint64_t base, uint64_t c0, unsigned log_table);
 
+/* The same four-step NTT with the exchanges written straight into PEER memory over NVLink (fourstep.cu):
+ *   stark_peer_alloc   a cudaMalloc'ed, zero-filled vector plus its 64-byte CUDA IPC handle (send it to the peers)
+ *   stark_peer_open    maps a peer's handle into this process; the pointer is valid in this context's kernels
+ *   stark_fourstep_phase_a  coefficients -> column-batched transforms -> twiddle -> row stores into every peer's
+ *                           [N1/G][N2] buffer (peer_rows[s] = rank s's buffer; peer_rows[rank] = own buffer)
+ *   stark_fourstep_phase_c  row transforms on the own buffer -> 32x32 transpose -> 128-byte stores into every peer's
+ *                           natural-order block (peer_blocks[t])
+ * Both calls return after their stores are complete; the caller places one barrier between them. */
+int stark_peer_alloc(stark_ctx* ctx, size_t n, stark_vec** out, uint8_t handle[64]);
+int stark_peer_open(stark_ctx* ctx, const uint8_t handle[64], void** dptr);
+int stark_peer_close(stark_ctx* ctx, void* dptr);
+int stark_fourstep_phase_a(stark_ctx* ctx, const stark_vec* coeffs, unsigned log_n, uint64_t offset, unsigned world,
+                           unsigned rank, void* const* peer_rows);
+int stark_fourstep_phase_c(stark_ctx* ctx, stark_vec* rows, unsigned log_n, unsigned world, unsigned rank,
+                           void* const* peer_blocks);
+
 /* ---- merkle: src/merkle/mod.rs -------------------------------------------------------------------
  * stark_merkle_commit == MerkleTree::new(data)   :10-22   leaf = SHA-256(value.to_be_bytes()), rs_merkle tree
  * stark_merkle_root_hex == MerkleTree::root()    :24-26   64 lowercase hex chars + NUL

@@ -75,6 +75,11 @@ def lib() -> C.CDLL:
     sig("stark_vec_from_device", I, vp, vp, szt, C.POINTER(vp))
     sig("stark_ntt_batch_dev", I, vp, vp, C.c_uint, I)
     sig("stark_pow_mul_dev", I, vp, vp, szt, szt, I, szt, u64, u64, C.c_uint)
+    sig("stark_peer_alloc", I, vp, szt, C.POINTER(vp), vp)
+    sig("stark_peer_open", I, vp, vp, C.POINTER(vp))
+    sig("stark_peer_close", I, vp, vp)
+    sig("stark_fourstep_phase_a", I, vp, vp, C.c_uint, u64, C.c_uint, C.c_uint, C.POINTER(vp))
+    sig("stark_fourstep_phase_c", I, vp, vp, C.c_uint, C.c_uint, C.c_uint, C.POINTER(vp))
     sig("stark_vec_len", szt, vp)
     sig("stark_vec_device_ptr", vp, vp)
     sig("stark_vec_destroy", None, vp)
@@ -219,6 +224,30 @@ class Context:
     def pow_mul_dev(self, v: "Vec", inner_len: int, outer0: int, product: bool, inner_stride: int, base: int, c0: int,
                     log_table: int) -> None:
         _check(lib().stark_pow_mul_dev(self.h, v.h, inner_len, outer0, int(product), inner_stride, base, c0, log_table))
+
+    # ---- peer-visible buffers and the four-step phases that store into them (multi_gpu.FourStepP2P)
+    def peer_alloc(self, n: int) -> tuple["Vec", bytes]:
+        h = vp()
+        handle = np.zeros(64, dtype=np.uint8)
+        _check(lib().stark_peer_alloc(self.h, n, C.byref(h), _ptr(handle)))
+        return Vec(self, h), handle.tobytes()
+
+    def peer_open(self, handle: bytes) -> int:
+        p = vp()
+        hb = np.frombuffer(handle, dtype=np.uint8).copy()
+        _check(lib().stark_peer_open(self.h, _ptr(hb), C.byref(p)))
+        return p.value
+
+    def peer_close(self, ptr: int) -> None:
+        _check(lib().stark_peer_close(self.h, C.c_void_p(ptr)))
+
+    def fourstep_phase_a(self, coeffs: "Vec", log_n: int, offset: int, world: int, rank: int, peer_rows: Sequence[int]) -> None:
+        arr = (vp * world)(*[C.c_void_p(p) for p in peer_rows])
+        _check(lib().stark_fourstep_phase_a(self.h, coeffs.h, log_n, offset, world, rank, arr))
+
+    def fourstep_phase_c(self, rows: "Vec", log_n: int, world: int, rank: int, peer_blocks: Sequence[int]) -> None:
+        arr = (vp * world)(*[C.c_void_p(p) for p in peer_blocks])
+        _check(lib().stark_fourstep_phase_c(self.h, rows.h, log_n, world, rank, arr))
 
     def zeros(self, n: int) -> "Vec":
         h = vp()

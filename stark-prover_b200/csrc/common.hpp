@@ -39,20 +39,21 @@ struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
     cudaStream_t stream = nullptr;
+    bool plain = false;          // cudaMalloc'ed (exportable over CUDA IPC) instead of pool-allocated
     DevBuf() = default;
     DevBuf(size_t b, cudaStream_t s) : bytes(b), stream(s) {
         if (b) STARK_CUDA(cudaMallocAsync(&p, b, s));
     }
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes), stream(o.stream) { o.p = nullptr; o.bytes = 0; }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes), stream(o.stream), plain(o.plain) { o.p = nullptr; o.bytes = 0; }
     DevBuf& operator=(DevBuf&& o) noexcept {
-        if (this != &o) { release(); p = o.p; bytes = o.bytes; stream = o.stream; o.p = nullptr; o.bytes = 0; }
+        if (this != &o) { release(); p = o.p; bytes = o.bytes; stream = o.stream; plain = o.plain; o.p = nullptr; o.bytes = 0; }
         return *this;
     }
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFreeAsync(p, stream);
+        if (p) { if (plain) { cudaStreamSynchronize(stream); cudaFree(p); } else cudaFreeAsync(p, stream); }
         p = nullptr; bytes = 0;
     }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }

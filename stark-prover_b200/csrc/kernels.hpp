@@ -52,6 +52,8 @@ void ntt_dit(stark_ctx* ctx, const uint32_t* src, uint32_t* data, unsigned log_n
              const PowTable* scale, bool inverse_root, size_t batch = 1);
 // decimation-in-frequency: natural input -> bit-reversed output, in place.
 void ntt_dif(stark_ctx* ctx, uint32_t* data, unsigned log_n, bool inverse_root, size_t batch = 1);
+// column-batched DIF over data[2^log_n rows][2^col_bits columns] (col_bits >= 5): natural rows in, bit-reversed out
+void ntt_dif_columns(stark_ctx* ctx, uint32_t* data, unsigned log_n, unsigned col_bits, bool inverse_root);
 // Blow-up-by-8 forward transform (the LDE / evaluate hot path): dst[8k'+s] = sum_j c_j (base w_N^s)^j w_n^(j k'),
 // c_j = c0 * (natural coefficients src[j], or src in bit-reversed order when src_bitrev).  n = 2^log_rows >= 2^10.
 bool lde8_supported(unsigned log_rows);
@@ -83,6 +85,18 @@ void coset_domain(stark_ctx* ctx, uint64_t offset, unsigned log_n, uint32_t* out
 //   product mode: e = inner * outer (the four-step twiddle w_N^(n2*k1));  affine: e = inner * inner_stride + outer
 void pow_mul(stark_ctx* ctx, uint32_t* v, size_t n, size_t inner_len, size_t outer0, bool product, size_t inner_stride,
              const PowTable& table);
+// ---- multi-GPU four-step NTT over peer memory (fourstep.cu) ----
+constexpr int MAX_PEERS = 16;
+struct PeerPtrs { uint32_t* p[MAX_PEERS]; };
+// A[n1][n2'] = c[n1*N2 + rank*w + n2'] * offset^(n1*N2 + rank*w + n2')   (zero above `len`)
+void fourstep_stage_input(stark_ctx* ctx, const uint32_t* coeffs, size_t len, uint32_t* A, unsigned log_n1, unsigned log_n2,
+                          unsigned world, unsigned rank, uint64_t offset);
+// rows of A (slot q holds k1 = bitrev(q)) times w_N^(k1*n2), written to their owner: peers[k1 / (N1/G)][k1 % (N1/G)][rank*w + n2']
+void fourstep_twiddle_scatter_rows(stark_ctx* ctx, const uint32_t* A, unsigned log_n1, unsigned log_n2, unsigned world, unsigned rank,
+                                   const PeerPtrs& peers);
+// X[k1'][slot q2] (k2 = bitrev(q2)) -> natural-order blocks: peers[k2 / (N2/G)][(k2 % (N2/G))*N1 + rank*N1/G + k1']
+void fourstep_transpose_scatter(stark_ctx* ctx, const uint32_t* X, unsigned log_n1, unsigned log_n2, unsigned world, unsigned rank,
+                                const PeerPtrs& peers);
 // plain (unfused) evaluation-space fold of one layer
 void fri_fold(stark_ctx* ctx, const LeafSource& src);
 

@@ -23,7 +23,8 @@ struct NttPass {
     const uint32_t* src;
     uint32_t* dst;
     unsigned log_n;
-    unsigned lo;          // lowest bit of this pass (0: contiguous tile)
+    unsigned lo;          // lowest ADDRESS bit of this pass (0: contiguous tile)
+    unsigned col_bits;    // lowest address bits that index independent transforms (column-batched); 0 = one transform
     unsigned ncols;       // valid columns per tile
     unsigned log_pad;     // DIT/contiguous only: input is zero-padded by 2^log_pad
     unsigned log_m;       // log_n - log_pad
@@ -143,7 +144,7 @@ __global__ void ntt_pass_kernel(NttPass ps, FieldParams fp) {
     } else {
         gbase = tile_id * (size_t)R * ps.ncols;
     }
-    const unsigned tw_shift = ps.log_n - ps.lo - R_LOG;   // exponent scale into the size-2^log_n tables
+    const unsigned tw_shift = ps.log_n - (ps.lo - ps.col_bits) - R_LOG;   // exponent scale into the size-2^log_n tables
     const int total = R * (int)ps.ncols;
 
     // ---- load (coalesced) ----
@@ -165,7 +166,7 @@ __global__ void ntt_pass_kernel(NttPass ps, FieldParams fp) {
             if (!STRIDED && !DIF && ps.has_scale) x = mont_mul(x, pow_lookup(ps.scale, bitrev_bits((uint32_t)g, ps.log_n), fp), fp);
         }
         if (STRIDED && !DIF) {   // DIT inter-pass twiddle on the way in: w_{2^(lo+r)}^(bitrev(t) * low)
-            uint32_t e = bitrev_bits((uint32_t)t, R_LOG) * (low0 + (uint32_t)c);
+            uint32_t e = bitrev_bits((uint32_t)t, R_LOG) * ((low0 + (uint32_t)c) >> ps.col_bits);
             x = mont_mul(x, pow_lookup(ps.tw, e << tw_shift, fp), fp);
         }
         tile[t * NTT_TS + c] = x;
@@ -182,7 +183,7 @@ __global__ void ntt_pass_kernel(NttPass ps, FieldParams fp) {
         else         { c = i >> R_LOG; t = i & (R - 1); g = gbase + i; }
         uint32_t x = tile[t * NTT_TS + c];
         if (STRIDED && DIF) {    // DIF inter-pass twiddle on the way out
-            uint32_t e = bitrev_bits((uint32_t)t, R_LOG) * (low0 + (uint32_t)c);
+            uint32_t e = bitrev_bits((uint32_t)t, R_LOG) * ((low0 + (uint32_t)c) >> ps.col_bits);
             x = mont_mul(x, pow_lookup(ps.tw, e << tw_shift, fp), fp);
         }
         ps.dst[g] = x;
@@ -307,6 +308,35 @@ void ntt_dif(stark_ctx* ctx, uint32_t* data, unsigned log_n, bool inverse_root, 
             dispatch_pass<true, true>(ctx, r, ps, batch * n / ((size_t)NTT_C << r));
         }
         hi = lo;
+    }
+    STARK_CUDA(cudaGetLastError());
+}
+
+// ---- column-batched DIF: data[2^log_n rows][2^col_bits columns], every column an independent transform -----
+// (phase A of the multi-GPU four-step NTT: the columns are a rank's slice of n2, contiguous in memory, so the rows
+// it produces can be shipped to their owners as contiguous chunks).  Natural row order in, bit-reversed out.
+void ntt_dif_columns(stark_ctx* ctx, uint32_t* data, unsigned log_n, unsigned col_bits, bool inverse_root) {
+    check_size(ctx, log_n);
+    STARK_REQUIRE(col_bits >= 5 && log_n + col_bits <= 31, "ntt_dif_columns: needs >= 32 columns and < 2^31 elements");
+    if (log_n == 0) return;
+    const TwiddleSet& tws = ctx->twiddles(log_n);
+    const size_t total = (size_t)1 << (log_n + col_bits);
+    std::vector<unsigned> bits = plan_bits(log_n);
+    KernelTimer kt(ctx, stark_ctx::CAT_NTT, 16.0 * (double)total);
+    unsigned hi = log_n;
+    for (size_t ii = bits.size(); ii-- > 0;) {
+        unsigned r = bits[ii], tlo = hi - r;
+        if (r < 5) {   // tiny transforms: widen the pass so the strided kernel exists for it
+            throw StarkError(ST_UNSUPPORTED, "ntt_dif_columns: transform smaller than 2^5 rows");
+        }
+        NttPass ps{};
+        ps.src = data; ps.dst = data;
+        ps.log_n = log_n; ps.lo = tlo + col_bits; ps.col_bits = col_bits; ps.ncols = NTT_C;
+        ps.tw = inverse_root ? tws.inv() : tws.fwd();
+        ps.small = inverse_root ? ctx->small_inv.as<uint32_t>() : ctx->small_fwd.as<uint32_t>();
+        ps.small_log = ctx->small_log;
+        dispatch_pass<true, true>(ctx, r, ps, total / ((size_t)NTT_C << r));
+        hi = tlo;
     }
     STARK_CUDA(cudaGetLastError());
 }

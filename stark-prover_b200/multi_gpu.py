@@ -376,3 +376,71 @@ def decommit_fri_multi(sp, mp: MultiGpuFri, num_queries: int, max_index: int, ch
                 channel.send(path)
             lens = [mp.proof.layer_len(k) for k in range(1, mp.proof.num_layers)]
             feed_layer_records(channel, mp.proof.open([idx], first_layer=1), lens, idx)
+
+
+# ------------------------------------------------------------------------------------------------ four-step NTT over peer memory
+class FourStepP2P:
+    """The four-step LDE with both exchanges written straight into peer memory (NVLink P2P stores through CUDA-IPC
+    mapped pointers) by the kernels that produce the data — no pack / all-to-all / unpack passes (csrc/fourstep.cu).
+
+    Every rank owns two peer-visible buffers of N/G elements: `rows` ([N1/G][N2], filled by every rank's phase A) and
+    `block` (its natural-order slice of the result, filled by every rank's phase C).  Handles are exchanged once.
+    Two host barriers per transform separate the phases (a phase returns when its peer stores are complete)."""
+
+    def __init__(self, sp, ctx, log_n: int, rank: int, world: int, group=None):
+        self.sp, self.ctx, self.log_n, self.rank, self.world, self.group = sp, ctx, log_n, rank, world, group
+        n_loc = (1 << log_n) // world
+        self.rows, h_rows = ctx.peer_alloc(n_loc)
+        self.block, h_block = ctx.peer_alloc(n_loc)
+        ctx.sync()
+        self._opened = []
+        if world == 1:
+            self.peer_rows, self.peer_blocks = [self.rows.device_ptr], [self.block.device_ptr]
+        else:
+            hs = all_gather_bytes(np.frombuffer(h_rows + h_block, dtype=np.uint8), group)       # [world, 128]
+            self.peer_rows, self.peer_blocks = [], []
+            for r in range(world):
+                if r == rank:
+                    self.peer_rows.append(self.rows.device_ptr); self.peer_blocks.append(self.block.device_ptr)
+                else:
+                    pr, pb = ctx.peer_open(hs[r, :64].tobytes()), ctx.peer_open(hs[r, 64:].tobytes())
+                    self._opened += [pr, pb]
+                    self.peer_rows.append(pr); self.peer_blocks.append(pb)
+
+    def _barrier(self):
+        dist = _dist()
+        if self.world > 1 and dist.is_initialized():
+            dist.barrier(group=self.group)
+
+    def run(self, coeffs, offset: int):
+        """coeffs: device Vec (every rank holds the same coefficients).  Returns this rank's natural-order block
+        (the peer-visible `block` buffer: valid until the next run)."""
+        self._barrier()                                   # nobody still reads `rows` / `block` from a previous run
+        self.ctx.fourstep_phase_a(coeffs, self.log_n, offset, self.world, self.rank, self.peer_rows)
+        self._barrier()                                   # every rank's rows are complete
+        self.ctx.fourstep_phase_c(self.rows, self.log_n, self.world, self.rank, self.peer_blocks)
+        self._barrier()                                   # every rank's block is complete
+        return self.block
+
+    def close(self):
+        self._barrier()
+        for p in self._opened:
+            self.ctx.peer_close(p)
+        self._opened = []
+
+
+def four_step_p2p_emulated(sp, ctx, coeffs, log_n: int, offset: int, world: int) -> list:
+    """All ranks of FourStepP2P in ONE process on one GPU: the 'peer' pointers are plain device pointers of the
+    other emulated ranks' buffers, so the kernels and the index algebra run exactly as on `world` GPUs."""
+    n_loc = (1 << log_n) // world
+    rows = [ctx.peer_alloc(n_loc)[0] for _ in range(world)]
+    blocks = [ctx.peer_alloc(n_loc)[0] for _ in range(world)]
+    cvec = coeffs if hasattr(coeffs, "device_ptr") else ctx.upload(coeffs)
+    pr, pb = [v.device_ptr for v in rows], [v.device_ptr for v in blocks]
+    for r in range(world):
+        ctx.fourstep_phase_a(cvec, log_n, offset, world, r, pr)
+    for r in range(world):
+        ctx.fourstep_phase_c(rows[r], log_n, world, r, pb)
+    for v in rows:
+        v.free()
+    return blocks

@@ -70,3 +70,20 @@ def test_fri_commit_multi_degenerate_world1(sp, orc, ctx):
     assert ch.state == ch1.state == och.state and ch.proof == ch1.proof == och.proof
     with pytest.raises(sp.StarkError):
         mp.proof.tree(0).get_authentication_path(0)          # layer 0's levels are not held by the proof object
+
+
+@pytest.mark.parametrize("log_n,log_deg,world", [(10, 7, 1), (12, 9, 2), (14, 11, 4), (16, 13, 8), (16, 16, 2), (20, 17, 8), (21, 18, 4)])
+def test_four_step_peer_memory_emulated(sp, orc, ctx, log_n, log_deg, world):
+    """Fused twiddle+row-scatter and transpose+scatter kernels with every rank emulated on one GPU."""
+    mg = _mg()
+    coeffs = orc.synthetic_column(log_n * 3 + world, 1 << log_deg)
+    want = orc.coset_evaluate(coeffs, log_n, 5, orc.root_of_unity(log_n), P)
+    blocks = mg.four_step_p2p_emulated(sp, ctx, coeffs, log_n, 5, world)
+    got = np.concatenate([b.download() for b in blocks])
+    assert np.array_equal(got, want)
+
+
+def test_four_step_peer_memory_rejects_tiny(sp, orc, ctx):
+    mg = _mg()
+    with pytest.raises(sp.StarkError):
+        mg.four_step_p2p_emulated(sp, ctx, orc.synthetic_column(1, 64), 10, 5, 4)     # < 32 rows per rank

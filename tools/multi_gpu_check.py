@@ -95,6 +95,22 @@ def main():
             n_blk = (1 << log_n) // world
             assert np.array_equal(blk.download(), want[:n_blk]), "cfg5 block differs from the oracle"
         print(json.dumps(out), flush=True)
+    # ---------------- cfg5, exchanges over peer memory (CUDA IPC + NVLink P2P stores from the kernels)
+    fs = mg.FourStepP2P(sp, ctx, log_n, rank, world)
+    fs.run(cvec, 5)                                                            # warm-up
+    barrier(); t0 = time.perf_counter()
+    pblk = fs.run(cvec, 5)
+    barrier(); t_p2p = time.perf_counter() - t0
+    assert np.array_equal(pblk.download(0, 4096), blk.download(0, 4096)) and np.array_equal(pblk.download(len(pblk) - 4096, 4096), blk.download(len(blk) - 4096, 4096))
+    ptree = sp.MerkleTree.new(ctx, pblk)
+    proot, _ = mg.commit_leaf_ranges(ptree.root_bytes, rank, world)
+    assert proot == root, "peer-memory four-step differs from the NCCL path"
+    if rank == 0:
+        print(json.dumps({"world": world, "cfg5_p2p": {"log_domain": log_n, "lde_seconds_p2p": t_p2p, "lde_seconds_nccl": t_lde,
+                                                       "Melem_per_s_p2p": (1 << log_n) / t_p2p / 1e6}}), flush=True)
+    ptree.free()
+    fs.close()
+
     # ---------------- cfg5 continued: the whole FRI commit + openings with the sharded layer 0
     log_f = 24 if args.full else 18
     cf = orc.synthetic_poly_exact_degree(43, 1 << (log_f - 3), P)
