@@ -303,7 +303,8 @@ def _bcast_int(value: int, group=None) -> int:
     return int(t.item())
 
 
-def fri_commit_multi(sp, ctx, coeffs, log_n: int, offset: int, channel, rank: int, world: int, group=None) -> MultiGpuFri:
+def fri_commit_multi(sp, ctx, coeffs, log_n: int, offset: int, channel, rank: int, world: int, group=None,
+                     p2p: Optional["FourStepP2P"] = None) -> MultiGpuFri:
     """fri_commit (reference src/fri/fri_commit.rs:72-122) with layer 0 spread over `world` GPUs:
     four-step LDE -> each rank hashes its contiguous leaf range -> subtree roots gathered -> the evaluations are
     all-gathered and rank 0 runs the (unpartitioned) fold/commit loop against the channel.  The transcript is the
@@ -311,7 +312,8 @@ def fri_commit_multi(sp, ctx, coeffs, log_n: int, offset: int, channel, rank: in
     import torch
     dist = _dist()
     cvec = coeffs if hasattr(coeffs, "device_ptr") else ctx.upload(coeffs)
-    block = four_step_lde(sp, ctx, cvec, log_n, offset, rank, world, group)
+    # exchanges either over NCCL (all_to_all_single) or stored straight into peer memory by the kernels
+    block = p2p.run(cvec, offset) if p2p is not None else four_step_lde(sp, ctx, cvec, log_n, offset, rank, world, group)
     subtree = sp.MerkleTree.new(ctx, block)
     root0, subs = commit_leaf_ranges(subtree.root_bytes, rank, world, group)
     ctx.sync()
