@@ -197,13 +197,13 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     sp = importlib.import_module("stark-prover_b200")
-    from oracle import pyoracle as orc   # input generator + cpu_baseline leg only
+    synth = importlib.import_module("stark-prover_b200.synthetic")
 
     log_n, log_deg = args.log_n, args.log_n - args.log_blowup
     n = 1 << log_n
     ctx = sp.Context(P, sp.G_DEFAULT, local)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local)
-    coeffs = orc.synthetic_poly_exact_degree(43 + rank, 1 << log_deg, P)
+    coeffs = synth.synthetic_poly_exact_degree(43 + rank, 1 << log_deg, P)
     pinned = torch.empty(1 << log_deg, dtype=torch.int64).pin_memory()
     pinned_np = pinned.numpy().view(np.uint64)
     pinned_np[:] = coeffs
@@ -352,6 +352,8 @@ def run_b200(args):
         line["algorithmic"] = alg
         # ---- CPU baseline beside it (bounded sample, all host threads)
         if not args.no_cpu_baseline and world == 1:
+            from oracle import pyoracle as orc          # the CPU baseline leg is the only use of the oracle in this arm
+            orc.build()
             orc.set_num_threads(len(os.sched_getaffinity(0)))
             cl = args.cpu_log_n
             cc = orc.synthetic_poly_exact_degree(43, 1 << (cl - args.log_blowup), P)
