@@ -81,6 +81,7 @@ def lib() -> C.CDLL:
     sig("or_merkle_path", szt, C.c_void_p, szt, u8p)
     sig("or_merkle_verify", C.c_int, u8p, szt, szt, u64, u8p, szt)
     sig("or_merkle_root_only", None, u64p, szt, u8p)
+    sig("or_merkle_root_from_digests", None, u8p, szt, u8p)
     sig("or_channel_new", C.c_void_p, u64)
     sig("or_channel_free", None, C.c_void_p)
     sig("or_channel_send", None, C.c_void_p, C.c_char_p, szt)
@@ -262,6 +263,13 @@ def merkle_verify(root: bytes, n_leaves, idx, value, path: bytes) -> bool:
     r = np.frombuffer(root, dtype=np.uint8).copy()
     p = np.frombuffer(path, dtype=np.uint8).copy() if path else np.zeros(1, dtype=np.uint8)
     return bool(lib().or_merkle_verify(_b(r), n_leaves, idx, value, _b(p), len(path)))
+
+
+def merkle_root_from_digests(digests: list) -> bytes:
+    d = np.frombuffer(b"".join(digests), dtype=np.uint8).copy()
+    out = np.zeros(32, dtype=np.uint8)
+    lib().or_merkle_root_from_digests(_b(d), len(digests), _b(out))
+    return out.tobytes()
 
 
 def merkle_root_only(leaves) -> bytes:

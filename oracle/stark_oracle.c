@@ -377,6 +377,16 @@ int or_merkle_verify(const uint8_t root[32], size_t n_leaves, size_t idx, uint64
     }
     return used == path_len && memcmp(cur, root, 32) == 0;
 }
+void or_merkle_root_from_digests(const uint8_t* digests, size_t n, uint8_t out[32]) {
+    /* rs_merkle MerkleTree::from_leaves(&[[u8;32]]) + root(): the tree rule alone, for published rs_merkle vectors */
+    if (n == 0) { memset(out, 0, 32); return; }
+    uint8_t* a = (uint8_t*)malloc(n * 32); memcpy(a, digests, n * 32);
+    uint8_t* b = (uint8_t*)malloc(((n + 1) / 2) * 32 + 32);
+    size_t m = n;
+    while (m > 1) { level_up(a, m, b); m = (m + 1) / 2; uint8_t* t = a; a = b; b = t; }
+    memcpy(out, a, 32);
+    free(a); free(b);
+}
 void or_merkle_root_only(const uint64_t* leaves, size_t n, uint8_t out[32]) {
     if (n == 0) { memset(out, 0, 32); return; }
     if (g_accel < 0) accel_init();

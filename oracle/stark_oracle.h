@@ -24,8 +24,10 @@
  * alloy 0.11.1 / ruint 1.12.3) are not vendored under /root/reference.  Field and polynomial
  * results are pinned by the reference's own mod-7 known-answer tests (tests/golden/ref_kat.json,
  * each with its file:line).  SHA-256 is pinned by the FIPS 180-4 vectors and Python hashlib.
- * Merkle roots, channel states, FRI layers and openings have no reference test or fixture:
- * for those rows PARITY IS UNPINNED — the oracle is a restatement of the published rules.
+ * The rs_merkle tree rule (pairwise SHA-256, leaves not re-hashed, lone node promoted) is additionally checked
+ * against the root rs_merkle publishes for the leaves "a".."f" (tests/golden/spec_anchors.json).
+ * Merkle roots over field elements, channel states, FRI layers and openings have no reference test or
+ * fixture: for those rows PARITY IS UNPINNED — the oracle is a restatement of the published rules.
  */
 #ifndef STARK_ORACLE_H
 #define STARK_ORACLE_H
@@ -87,6 +89,8 @@ size_t   or_merkle_path(const or_tree* t, size_t idx, uint8_t* out /* >= 32*dept
 /* verify a path produced above (rs_merkle MerkleProof::verify for one leaf) */
 int      or_merkle_verify(const uint8_t root[32], size_t n_leaves, size_t idx, uint64_t value,
                           const uint8_t* path, size_t path_len);
+/* the tree rule alone over caller-supplied leaf digests (rs_merkle from_leaves + root), for published vectors */
+void     or_merkle_root_from_digests(const uint8_t* digests, size_t n, uint8_t out[32]);
 /* root only, multi-threaded, no retained tree (CPU baseline) */
 void     or_merkle_root_only(const uint64_t* leaves, size_t n, uint8_t out[32]);
 

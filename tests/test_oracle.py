@@ -107,6 +107,20 @@ def test_spec_anchors(orc, golden):
     assert int(orc.fibsq_trace(3141592, 1023)[1022]) == s["a_1022"]
 
 
+def test_rs_merkle_published_vector(orc, golden):
+    """The tree rule against the root rs_merkle publishes for the leaves "a".."f" (6 leaves: exercises promotion)."""
+    v = golden["spec_anchors"]["rs_merkle_published"]
+    digests = [hashlib.sha256(x.encode()).digest() for x in v["leaves_utf8"]]
+    assert orc.merkle_root_from_digests(digests).hex() == v["root_hex"]
+    lv = list(digests)                                   # and the hashlib twin's rule
+    while len(lv) > 1:
+        nxt = [hashlib.sha256(lv[i] + lv[i + 1]).digest() for i in range(0, len(lv) - 1, 2)]
+        if len(lv) & 1:
+            nxt.append(lv[-1])
+        lv = nxt
+    assert lv[0].hex() == v["root_hex"]
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 13, 64, 100, 257])
 def test_merkle_vs_hashlib(orc, n):
     vals = orc.synthetic_column(n, n).tolist()
