@@ -306,12 +306,14 @@ def test_stark101_other_sizes(sp, orc, ctx, log_trace, log_blowup, a1, q):
 
 
 # ---------------------------------------------------------------- other fields
-@pytest.mark.parametrize("modulus,gen", [(998244353, 3), (2013265921, 31), (17, 3), (7, 3), (257, 3)])
+# moduli that stress the arithmetic: just below 2^32 (every add can wrap), just above 2^31, tiny, low two-adicity
+@pytest.mark.parametrize("modulus,gen", [(998244353, 3), (2013265921, 31), (17, 3), (7, 3), (257, 3),
+                                         (4293918721, 19), (4294967291, 2), (3489660929, 3), (2281701377, 3), (469762049, 3)])
 def test_other_moduli(sp, orc, modulus, gen):
     c = sp.Context(modulus, gen, 0)
     try:
         adic = c.two_adicity
-        log_n = min(adic, 12)
+        log_n = min(adic, 16)
         w = orc.root_of_unity(log_n, modulus, gen)
         assert c.root_of_unity(log_n) == w
         coeffs = orc.synthetic_column(1, 1 << max(log_n - 2, 0), modulus)
@@ -446,3 +448,24 @@ def test_two_contexts_interleaved(sp, orc):
                 assert pr.tree(k + 1).root_bytes() == orc.merkle_root_only(e)
     finally:
         a.close(); b.close()
+
+
+@pytest.mark.parametrize("modulus,gen", [(4293918721, 19), (3489660929, 3)])
+def test_large_modulus_lde_and_fold_paths(sp, orc, modulus, gen):
+    """The blow-up-8 LDE kernel (weak/lazy arithmetic) and the fused fold with p close to 2^32."""
+    c = sp.Context(modulus, gen, 0)
+    try:
+        log_t, log_n = 13, 16
+        w_t, w_n = orc.root_of_unity(log_t, modulus, gen), orc.root_of_unity(log_n, modulus, gen)
+        col = orc.synthetic_column(3, 1 << log_t, modulus)
+        col[:8] = [modulus - 1, modulus - 2, 0, 1, modulus - 1, 0, modulus - 1, modulus - 1]
+        coef = orc.coset_interpolate(col, log_t, 1, w_t, modulus)
+        want = orc.coset_evaluate(coef, log_n, gen, w_n, modulus)
+        assert np.array_equal(c.coset_lde(col, log_t, 1, 3, gen), want)
+        assert np.array_equal(c.coset_evaluate(coef, log_n, gen), want)
+        pr, _ = sp.fri_begin(c, coef, log_n, gen)
+        beta = modulus - 1
+        pr.fold(beta)
+        assert np.array_equal(pr.layer(1), orc.fri_fold_evals(want, beta, gen, w_n, modulus))
+    finally:
+        c.close()
