@@ -40,7 +40,10 @@ size_t merkle_path_len(size_t n, size_t idx) {
 }
 
 constexpr int SUB = 3;            // levels advanced per launch (2^SUB items per thread)
-constexpr int MERKLE_THREADS = 128;
+#ifndef STARK_MERKLE_THREADS
+#define STARK_MERKLE_THREADS 128
+#endif
+constexpr int MERKLE_THREADS = STARK_MERKLE_THREADS;
 
 struct LevelPtrs { uint32_t* p[SUB + 1]; };   // p[l], l = 1..SUB: storage of the l-th level produced by this launch
 
