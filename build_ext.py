@@ -12,7 +12,7 @@ PKG = os.path.join(ROOT, "stark-prover_b200")
 CSRC = os.path.join(PKG, "csrc")
 OUT = os.path.join(PKG, "libstark_b200.so")
 BUILD = os.path.join(ROOT, "build")
-SOURCES = ["api.cu", "merkle.cu", "ntt.cu", "fri.cu", "stark101.cu", "peaks.cu", "fourstep.cu"]
+SOURCES = ["api.cu", "merkle.cu", "ntt.cu", "fri.cu", "stark101.cu", "peaks.cu", "fourstep.cu", "verify.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 

@@ -217,6 +217,18 @@ int stark_fri_commit_dev(stark_ctx* ctx, const stark_vec* coeffs, unsigned log_n
 int stark_decommit_fri_layers(const stark_fri* f, size_t index, stark_channel* ch);
 int stark_decommit_fri(const stark_fri* f, size_t num_queries, size_t max_index, stark_channel* ch);
 
+/* ---- verification (host side; completes what src/fri/fri_verify.rs sketches) ------------------------
+ * stark_merkle_verify == the `MerkleTree::validate` that fri_verify.rs:109,137 calls and the reference never defines
+ *                        (rs_merkle MerkleProof::verify for one leaf).
+ * stark_fri_verify    == verify_fri (fri_verify.rs:12-177) with the fold-consistency check that is commented out there
+ *                        (:153-170): replays the flattened proof (stark_channel_proof_flat) against a fresh channel.
+ * Both set *ok to 1/0 and return STARK_OK unless an argument is unusable; `reason` (>= 160 bytes, optional) gets
+ * the first failure. */
+int stark_merkle_verify(const uint8_t root[32], size_t n_leaves, size_t idx, uint64_t value, const uint8_t* path,
+                        size_t path_len, int* ok);
+int stark_fri_verify(const uint8_t* proof_flat, size_t proof_len, uint64_t modulus, uint64_t generator, unsigned log_n,
+                     uint64_t offset, size_t num_queries, size_t max_index, int* ok, char* reason);
+
 /* ---- prover (build-defined: src/prover, src/trace, src/composition are empty in the reference) ----
  * STARK-101 FibonacciSq statement a0 = 1, a1 = `a1`, a_{n+2} = a_{n+1}^2 + a_n^2 over 2^log_trace - 1 rows;
  * protocol and transcript order in DESIGN.md "cfg1". */

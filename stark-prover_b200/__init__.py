@@ -136,6 +136,8 @@ def lib() -> C.CDLL:
     sig("stark_decommit_fri_layers", I, vp, szt, vp)
     sig("stark_decommit_fri", I, vp, szt, szt, vp)
     sig("stark101_prove", I, vp, u64, C.c_uint, C.c_uint, szt, vp)
+    sig("stark_merkle_verify", I, vp, szt, szt, u64, vp, szt, C.POINTER(I))
+    sig("stark_fri_verify", I, vp, szt, u64, u64, C.c_uint, u64, szt, szt, C.POINTER(I), C.c_char_p)
     _lib = L
     return L
 
@@ -599,6 +601,24 @@ def stark101_prove(ctx: Context, channel: Channel, a1: int = 3141592, log_trace:
                    num_queries: int = 3) -> None:
     """Build-defined FibonacciSq prover."""
     _check(lib().stark101_prove(ctx.h, a1, log_trace, log_blowup, num_queries, channel.h))
+
+
+def merkle_validate(root: bytes, n_leaves: int, idx: int, value: int, path: bytes) -> bool:
+    """MerkleTree::validate (called at src/fri/fri_verify.rs:109, never defined in the reference)."""
+    r = np.frombuffer(root, dtype=np.uint8).copy()
+    p = np.frombuffer(path, dtype=np.uint8).copy() if path else np.zeros(1, dtype=np.uint8)
+    ok = C.c_int(0)
+    _check(lib().stark_merkle_verify(_ptr(r), n_leaves, idx, value, _ptr(p), len(path), C.byref(ok)))
+    return bool(ok.value)
+
+
+def verify_fri(proof_flat: bytes, log_n: int, offset: int, num_queries: int, max_index: int, modulus: int = P_DEFAULT,
+               generator: int = G_DEFAULT) -> tuple[bool, str]:
+    """verify_fri (src/fri/fri_verify.rs:12-177, completed): replays a flattened proof; host side, no GPU needed."""
+    buf = np.frombuffer(proof_flat, dtype=np.uint8).copy()
+    ok, reason = C.c_int(0), C.create_string_buffer(160)
+    _check(lib().stark_fri_verify(_ptr(buf), buf.size, modulus, generator, log_n, offset, num_queries, max_index, C.byref(ok), reason))
+    return bool(ok.value), reason.value.decode()
 
 
 def exported_symbols() -> list[str]:

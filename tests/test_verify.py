@@ -1,0 +1,67 @@
+"""The host-side verifier: accepts proofs made by the CPU oracle (CPU test) and by the
+GPU path (GPU test), rejects every single-byte corruption class."""
+import numpy as np
+import pytest
+
+P = 3221225473
+
+
+def _flat(msgs):
+    return b"".join(len(m).to_bytes(4, "little") + m for m in msgs)
+
+
+def _oracle_proof(orc, log_n, log_deg, q, seed=43):
+    c = orc.synthetic_poly_exact_degree(seed, 1 << log_deg)
+    ch = orc.Channel(P)
+    pr = orc.fri_commit_fast(c, log_n, 5, orc.root_of_unity(log_n), ch, P)
+    orc.decommit_fri(q, (1 << log_n) - 1, pr, ch)
+    return ch.proof
+
+
+@pytest.mark.parametrize("log_n,log_deg,q", [(10, 7, 3), (8, 8, 2), (6, 6, 2), (5, 0, 1)])
+def test_verifier_accepts_oracle_proofs(sp, orc, log_n, log_deg, q):
+    ok, why = sp.verify_fri(_flat(_oracle_proof(orc, log_n, log_deg, q)), log_n, 5, q, (1 << log_n) - 1)
+    assert ok, why
+
+
+def test_verifier_rejects_corruptions(sp, orc):
+    log_n, q = 10, 3
+    msgs = _oracle_proof(orc, log_n, 7, q)
+    n_layers = 8
+    first_query = 2 * n_layers                       # root0, (beta, root) x 7, final -> index at position 16
+    cases = {"root": 0, "beta": 1, "final": first_query - 1, "index": first_query, "element": first_query + 1,
+             "path": first_query + 2, "sibling element": first_query + 3, "deep path": len(msgs) - 1}
+    for name, pos in cases.items():
+        bad = [bytearray(m) for m in msgs]
+        bad[pos][len(bad[pos]) // 2] ^= 0x01
+        ok, why = sp.verify_fri(_flat([bytes(m) for m in bad]), log_n, 5, q, (1 << log_n) - 1)
+        assert not ok and why, name
+    ok, _ = sp.verify_fri(_flat(msgs[:-1]), log_n, 5, q, (1 << log_n) - 1)           # truncated
+    assert not ok
+    ok, _ = sp.verify_fri(_flat(msgs), log_n, 7, q, (1 << log_n) - 1)                # wrong coset offset: folds no longer match
+    assert not ok
+    ok, _ = sp.verify_fri(_flat(msgs), log_n, 5, q, (1 << log_n) - 2)                # wrong query range: indices no longer match
+    assert not ok
+
+
+def test_merkle_validate(sp, orc):
+    vals = orc.synthetic_column(1, 100)
+    t = orc.Tree(vals)
+    for idx in (0, 37, 99):
+        assert sp.merkle_validate(t.root(), 100, idx, int(vals[idx]), t.path(idx))
+        assert not sp.merkle_validate(t.root(), 100, idx, (int(vals[idx]) + 1) % P, t.path(idx))
+        assert not sp.merkle_validate(t.root(), 100, idx ^ 1, int(vals[idx]), t.path(idx))
+    assert not sp.merkle_validate(t.root(), 100, 5, int(vals[5]), t.path(5)[:-32])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("log_n,log_deg,q", [(12, 9, 4), (20, 17, 8)])
+def test_verifier_accepts_gpu_proofs(sp, orc, ctx, log_n, log_deg, q):
+    c = orc.synthetic_poly_exact_degree(43, 1 << log_deg)
+    ch = sp.Channel(P)
+    pr = sp.fri_commit(ctx, c, sp.CosetFri(ctx, 5, log_n), ch)
+    sp.decommit_fri(q, (1 << log_n) - 1, pr, ch)
+    ok, why = sp.verify_fri(ch.proof_flat(), log_n, 5, q, (1 << log_n) - 1)
+    assert ok, why
+    t = pr.tree(0)
+    assert sp.merkle_validate(t.root_bytes(), 1 << log_n, 5, int(pr.layer(0, 5, 1)[0]), t.get_authentication_path(5))
