@@ -17,8 +17,24 @@ struct Digest { uint32_t w[8]; };
 __device__ __forceinline__ uint32_t rotr32(uint32_t x, unsigned n) { return __funnelshift_r(x, x, n); }
 __device__ __forceinline__ uint32_t big_s0(uint32_t x) { return rotr32(x, 2) ^ rotr32(x, 13) ^ rotr32(x, 22); }
 __device__ __forceinline__ uint32_t big_s1(uint32_t x) { return rotr32(x, 6) ^ rotr32(x, 11) ^ rotr32(x, 25); }
-__device__ __forceinline__ uint32_t sml_s0(uint32_t x) { return rotr32(x, 7) ^ rotr32(x, 18) ^ (x >> 3); }
-__device__ __forceinline__ uint32_t sml_s1(uint32_t x) { return rotr32(x, 17) ^ rotr32(x, 19) ^ (x >> 10); }
+// Variant (off): the plain right shifts of the message schedule as the high word of x * 2^(32-n) with a factor
+// the compiler cannot see through, i.e. IMAD.HI on the FMA pipe instead of SHF on the ALU pipe (8 -> 6 ALU
+// instructions per schedule step).  Measured neutral on B200 (2^24-leaf tree 2.629 ms vs 2.627 ms), so the
+// plain shift stays.
+#ifndef STARK_SHA_SHR_ON_FMA
+#define STARK_SHA_SHR_ON_FMA 0
+#endif
+static __constant__ uint32_t c_sha_two29 = 1u << 29;
+static __constant__ uint32_t c_sha_two22 = 1u << 22;
+#if STARK_SHA_SHR_ON_FMA
+__device__ __forceinline__ uint32_t shr3(uint32_t x) { return __umulhi(x, c_sha_two29); }
+__device__ __forceinline__ uint32_t shr10(uint32_t x) { return __umulhi(x, c_sha_two22); }
+#else
+__device__ __forceinline__ uint32_t shr3(uint32_t x) { return x >> 3; }
+__device__ __forceinline__ uint32_t shr10(uint32_t x) { return x >> 10; }
+#endif
+__device__ __forceinline__ uint32_t sml_s0(uint32_t x) { return rotr32(x, 7) ^ rotr32(x, 18) ^ shr3(x); }
+__device__ __forceinline__ uint32_t sml_s1(uint32_t x) { return rotr32(x, 17) ^ rotr32(x, 19) ^ shr10(x); }
 __device__ __forceinline__ uint32_t ch(uint32_t e, uint32_t f, uint32_t g) { return (e & f) ^ (~e & g); }
 __device__ __forceinline__ uint32_t maj(uint32_t a, uint32_t b, uint32_t c) { return (a & b) ^ (a & c) ^ (b & c); }
 
