@@ -59,6 +59,36 @@ __global__ void fibsq_combine_kernel(FibSqDev q, PowTable tw, const uint32_t* f,
     cp[i] = fadd(r, mont_mul(p2, q.alpha_m[2], fp), fp);
 }
 
+// partial[b] = sum over block b of a[i] * w^i  (mod p): the device half of "choose the T-th trace value so that
+// the top coefficient of the interpolant vanishes"
+__global__ void dot_powers_kernel(const uint32_t* a, size_t n, PowTable tw, uint32_t* partial, FieldParams fp) {
+    unsigned long long acc = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        acc += mont_mul(a[i], pow_lookup(tw, (uint32_t)i, fp), fp);          // < p each; at most 2^32 terms fit
+    __shared__ unsigned long long sh[256];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = (uint32_t)(sh[0] % fp.p);
+}
+// sum_i a[i] * w_n^i over the first `count` entries of a device vector
+uint64_t dot_powers(stark_ctx* ctx, const uint32_t* a, size_t count, unsigned log_n) {
+    const unsigned blocks = 256;
+    DevBuf part(blocks * 4, ctx->stream);
+    dot_powers_kernel<<<blocks, 256, 0, ctx->stream>>>(a, count, ctx->twiddles(log_n).fwd(), part.as<uint32_t>(), ctx->fp);
+    ctx->launches++;
+    STARK_CUDA(cudaGetLastError());
+    uint32_t h[blocks];
+    STARK_CUDA(cudaMemcpyAsync(h, part.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    STARK_CUDA(cudaStreamSynchronize(ctx->stream));
+    uint64_t s = 0;
+    for (unsigned b = 0; b < blocks; b++) s = (s + h[b]) % ctx->modulus;
+    return s;
+}
+
 void fibsq_composition(stark_ctx* ctx, const uint32_t* f_eval, const FibSqParams& prm, uint32_t* cp_eval) {
     const uint64_t p = ctx->modulus;
     const unsigned log_N = prm.log_trace + prm.log_blowup;
@@ -117,16 +147,37 @@ extern "C" int stark101_prove(stark_ctx* ctx, uint64_t a1, unsigned log_trace, u
         const size_t T = (size_t)1 << log_trace, rows = T - 1, N = (size_t)1 << log_N, blow = (size_t)1 << log_blowup;
         const uint64_t g = ctx->root_of_unity(log_trace), w = ctx->generator;
         // ---- src/trace: the recurrence is sequential, it stays on the host ----
+        // (8M dependent steps at 2^23 rows: kept in 32-bit Montgomery form so a step is ~15 cycles, not two u128 divisions)
         std::vector<uint64_t> a(T);
-        a[0] = 1 % p; a[1] = a1 % p;
-        for (size_t i = 2; i < rows; i++) a[i] = (h_mul(a[i - 1], a[i - 1], p) + h_mul(a[i - 2], a[i - 2], p)) % p;
+        {
+            const uint32_t pp = (uint32_t)p, pinv = ctx->fp.pinv;
+            auto mm = [pp, pinv](uint32_t x, uint32_t y) {
+                uint64_t t = (uint64_t)x * y;
+                uint32_t q = (uint32_t)t * pinv, hq = (uint32_t)(((uint64_t)q * pp) >> 32), hi = (uint32_t)(t >> 32);
+                uint32_t r = hi - hq;
+                return hi < hq ? r + pp : r;
+            };
+            uint32_t x0 = ctx->to_mont(1), x1 = ctx->to_mont(a1);
+            a[0] = 1 % p; a[1] = a1 % p;
+            for (size_t i = 2; i < rows; i++) {
+                uint64_t sum = (uint64_t)mm(x1, x1) + mm(x0, x0);
+                uint32_t x2 = (uint32_t)(sum >= p ? sum - p : sum);
+                a[i] = mm(x2, 1u);                                 // out of Montgomery form (off the dependency chain)
+                x0 = x1; x1 = x2;
+            }
+            a[rows] = 0;
+        }
         // T-th value chosen so that the x^(T-1) coefficient of the size-T interpolant vanishes:
-        // the result is the unique degree <= T-2 interpolant through the T-1 rows (Polynomial::interpolate).
-        uint64_t s = 0, gi = 1;
-        for (size_t i = 0; i < rows; i++) { s = (s + h_mul(a[i], gi, p)) % p; gi = h_mul(gi, g, p); }
-        a[rows] = h_mul((p - s) % p, h_inv(gi, p), p);
-        // ---- LDE of the trace column and its commitment ----
+        // sum_{i<T} a_i g^i = 0  =>  the unique degree <= T-2 interpolant through the T-1 rows (Polynomial::interpolate).
         DevBufPtr tr = api_upload_u64(ctx, a.data(), T);
+        {
+            uint64_t s = dot_powers(ctx, tr->as<uint32_t>(), rows, log_trace);
+            a[rows] = h_mul((p - s) % p, h_inv(h_pow(g, rows, p), p), p);
+            uint32_t last32 = (uint32_t)a[rows];
+            STARK_CUDA(cudaMemcpyAsync(tr->as<uint32_t>() + rows, &last32, 4, cudaMemcpyHostToDevice, ctx->stream));
+            STARK_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        // ---- LDE of the trace column and its commitment ----
         DevBufPtr f_eval = api_lde_on_coset(ctx, tr->as<uint32_t>(), log_trace, 1, log_blowup, w);
         auto f_tree = api_tree_commit(ctx, f_eval, N);
         api_send_root(ch, f_tree.get());
