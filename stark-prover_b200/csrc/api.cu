@@ -888,14 +888,34 @@ static void send_query_records(const stark_fri* f, const uint8_t* rec, Channel& 
         }
     }
 }
+// One index, all layers: the layer table travels as kernel arguments, the records land in mapped host memory.
+static const uint8_t* open_one_index(const stark_fri* f, size_t index, size_t* total_out) {
+    stark_ctx* ctx = f->ctx;
+    STARK_REQUIRE(f->trees.size() <= (size_t)FRI_MAX_LAYERS, "fri: too many layers");
+    FriOpenArgs a{};
+    size_t total = 0;
+    for (size_t k = 0; k < f->trees.size(); k++) {
+        const stark_tree* t = f->trees[k].get();
+        STARK_REQUIRE(!t->external, "fri open: layer 0 was committed in leaf ranges on several GPUs; open it on the owners");
+        a.layers[k] = FriLayerDesc{t->leaves->as<uint32_t>(), t->nodes.as<uint32_t>(), t->shape.n};
+        size_t len = t->shape.n, idx = index % len, sib = (idx + len / 2) % len;
+        total += 16 + merkle_path_len(len, idx) + merkle_path_len(len, sib);
+    }
+    a.n_layers = (unsigned)f->trees.size(); a.first = 0; a.index = index;
+    ctx->pin_out.ensure(total);
+    a.out = static_cast<uint8_t*>(ctx->pin_out.d);
+    fri_open_one(ctx, a);
+    STARK_CUDA(cudaStreamSynchronize(ctx->stream));
+    *total_out = total;
+    return static_cast<const uint8_t*>(ctx->pin_out.h);
+}
 extern "C" int stark_decommit_fri_layers(const stark_fri* f, size_t index, stark_channel* ch) {
     API_BEGIN
     STARK_REQUIRE(f && ch, "decommit_fri_layers: null argument");
-    std::vector<OpenDesc> d;
-    size_t total = fri_query_descs(f, index, 0, d);
-    std::vector<uint8_t> rec(total);
-    { CtxGuard g(f->ctx); open_records(f->ctx, d, total, rec.data()); }
-    send_query_records(f, rec.data(), ch->ch, index);
+    CtxGuard g(f->ctx);
+    size_t total = 0;
+    const uint8_t* rec = open_one_index(f, index, &total);      // valid until the next opening on this context
+    send_query_records(f, rec, ch->ch, index);
     API_END
 }
 extern "C" int stark_decommit_fri(const stark_fri* f, size_t num_queries, size_t max_index, stark_channel* ch) {

@@ -41,6 +41,16 @@ struct OpenDesc {
     unsigned long long out_off;// byte offset of this record in the output: BE8(value) || path bytes
 };
 void merkle_open(stark_ctx* ctx, const OpenDesc* d_desc, size_t n_desc, uint8_t* d_out);
+// One query index across the layers of a FRI proof, descriptors passed by value as kernel arguments.
+constexpr int FRI_MAX_LAYERS = 40;
+struct FriLayerDesc { const uint32_t* vals; const uint32_t* nodes; unsigned long long n; };
+struct FriOpenArgs {
+    FriLayerDesc layers[FRI_MAX_LAYERS];
+    unsigned n_layers, first;
+    unsigned long long index;
+    uint8_t* out;            // records back to back: BE8(value) || path, layer by layer, idx then sibling
+};
+void fri_open_one(stark_ctx* ctx, const FriOpenArgs& a);
 // host-side: bytes of the path of leaf idx in a tree of n leaves (32 per level that has a sibling)
 size_t merkle_path_len(size_t n, size_t idx);
 

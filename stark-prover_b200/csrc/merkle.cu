@@ -370,6 +370,66 @@ __global__ void merkle_open_kernel(const OpenDesc* desc, size_t n_desc, uint8_t*
     }
 }
 
+// ---- one query index across the layers of a FRI proof: everything the kernel needs travels in its arguments
+// (no descriptor upload), the record offsets are computed on the device.  Warp w opens record w:
+// layer first + w/2, position idx (even w) or its sibling (odd w).
+__device__ __forceinline__ unsigned path_bytes(unsigned long long n, unsigned long long idx) {
+    unsigned bytes = 0;
+    for (unsigned long long m = n, j = idx; m > 1; m = (m + 1) >> 1, j >>= 1)
+        if ((j ^ 1ull) < m) bytes += 32;
+    return bytes;
+}
+__global__ void fri_open_one_kernel(FriOpenArgs a) {
+    const unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const unsigned n_rec = 2 * (a.n_layers - a.first);
+    if (w >= n_rec) return;
+    // byte offset of record w = sum of the sizes of records 0..w-1 (lanes take records lane, lane+32, ...)
+    unsigned before = 0;
+    for (unsigned r = lane; r < w; r += 32) {
+        const FriLayerDesc& L = a.layers[a.first + r / 2];
+        unsigned long long i = a.index % L.n;
+        if (r & 1) i = (i + L.n / 2) % L.n;
+        before += 8 + path_bytes(L.n, i);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    const FriLayerDesc& L = a.layers[a.first + w / 2];
+    unsigned long long idx = a.index % L.n;
+    if (w & 1) idx = (idx + L.n / 2) % L.n;
+    unsigned depth = 0;
+    for (unsigned long long m = L.n; m > 1; m = (m + 1) >> 1) depth++;
+    unsigned long long len_l = L.n, off_l = 0;
+    for (unsigned l = 0; l < lane && l < depth; l++) {
+        if (l >= 1) off_l += len_l;
+        len_l = (len_l + 1) >> 1;
+    }
+    unsigned long long j = (idx >> lane) ^ 1ull;
+    bool exists = lane < depth && j < len_l;
+    unsigned mask = __ballot_sync(0xffffffffu, exists);
+    uint32_t* rec = reinterpret_cast<uint32_t*>(a.out + before);
+    if (lane == 0) {
+        rec[0] = 0;
+        rec[1] = __byte_perm(L.vals[idx], 0, 0x0123);
+    }
+    if (exists) {
+        Digest dg;
+        if (lane == 0) sha256_leaf(0u, L.vals[j], dg);
+        else dg = load_digest(L.nodes + 8 * (off_l + j));
+        unsigned pos = __popc(mask & ((1u << lane) - 1u));
+        uint32_t* o = rec + 2 + 8 * pos;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o[i] = __byte_perm(dg.w[i], 0, 0x0123);
+    }
+}
+void fri_open_one(stark_ctx* ctx, const FriOpenArgs& a) {
+    unsigned n_rec = 2 * (a.n_layers - a.first);
+    if (!n_rec) return;
+    KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 0);
+    fri_open_one_kernel<<<(n_rec * 32 + 127) / 128, 128, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    STARK_CUDA(cudaGetLastError());
+}
+
 void merkle_open(stark_ctx* ctx, const OpenDesc* d_desc, size_t n_desc, uint8_t* d_out) {
     if (n_desc == 0) return;
     unsigned blocks = (unsigned)((n_desc * 32 + 127) / 128);
