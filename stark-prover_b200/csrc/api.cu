@@ -117,6 +117,7 @@ extern "C" void stark_ctx_destroy(stark_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     ctx->tw.clear();
     ctx->small_fwd.release(); ctx->small_inv.release(); ctx->tail_counter.release(); ctx->deg_scratch.release();
+    BlockCache::flush(ctx->stream);
     cudaStreamSynchronize(ctx->stream);
     for (int c = 0; c < stark_ctx::CAT_COUNT; c++) for (auto& pr : ctx->ev_used[c]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto e : ctx->ev_free) cudaEventDestroy(e);

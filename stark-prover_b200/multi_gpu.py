@@ -52,14 +52,30 @@ def all_gather_bytes(local: np.ndarray, group=None) -> np.ndarray:
     return out.cpu().numpy()
 
 
-def commit_columns(n_cols: int, commit_fn: Callable[[int], bytes], rank: int, world: int, group=None) -> list[bytes]:
+def commit_columns(n_cols: int, commit_fn, rank: int, world: int, group=None) -> list[bytes]:
     """Column-parallel commitment: `commit_fn(c)` returns the 32-byte Merkle root of column c (LDE + tree on
-    this rank's GPU).  Returns the roots of ALL columns, in column order, identical on every rank."""
+    this rank's GPU).  Returns the roots of ALL columns, in column order, identical on every rank.
+    `commit_fn` may be a list of callables (one per context/stream on this GPU): the rank's columns are then
+    pipelined over that many host threads, so one column's upload and tree tail overlap another's bulk hashing."""
     mine = shard_columns(n_cols, rank, world)
     per_rank = -(-n_cols // world)
     local = np.zeros((per_rank, 32), dtype=np.uint8)
-    for slot, c in enumerate(mine):
-        root = commit_fn(c)
+    fns = list(commit_fn) if isinstance(commit_fn, (list, tuple)) else [commit_fn]
+    if len(fns) == 1:
+        roots = [fns[0](c) for c in mine]
+    else:
+        import threading
+        roots = [None] * len(mine)
+
+        def run(k):
+            for slot in range(k, len(mine), len(fns)):
+                roots[slot] = fns[k](mine[slot])
+        ths = [threading.Thread(target=run, args=(k,)) for k in range(len(fns))]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+    for slot, root in enumerate(roots):
         assert len(root) == 32
         local[slot] = np.frombuffer(root, dtype=np.uint8)
     allr = all_gather_bytes(local, group)                       # [world, per_rank, 32]

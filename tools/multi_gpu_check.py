@@ -58,6 +58,17 @@ def main():
     barrier(); dt = time.perf_counter() - t0
     out["cfg4"] = {"columns": n_cols, "log_rows": log_rows, "log_lde": log_rows + 3, "seconds": dt,
                    "Melem_per_s": n_cols * (1 << (log_rows + 3)) / dt / 1e6, "root0": roots[0].hex()}
+    # the same with three contexts (streams) per GPU: columns pipelined over three host threads
+    ctxs = [ctx, sp.Context(P, 5, local), sp.Context(P, 5, local)]
+    commits = [mg.gpu_column_committer(sp, cx, lambda c: cols[c], 3, 1, 5) for cx in ctxs]
+    mg.commit_columns(n_cols, commits, rank, world)            # warm-up
+    barrier(); t0 = time.perf_counter()
+    roots3 = mg.commit_columns(n_cols, commits, rank, world)
+    barrier(); dt3 = time.perf_counter() - t0
+    assert roots3 == roots
+    out["cfg4"].update({"seconds_3_streams": dt3, "Melem_per_s_3_streams": n_cols * (1 << (log_rows + 3)) / dt3 / 1e6})
+    for cx in ctxs[1:]:
+        cx.close()
     if rank == 0 and not args.full:
         for c in (0, n_cols - 1):
             col = orc.synthetic_column(100 + c, 1 << log_rows)
