@@ -228,6 +228,11 @@ int stark_merkle_verify(const uint8_t root[32], size_t n_leaves, size_t idx, uin
                         size_t path_len, int* ok);
 int stark_fri_verify(const uint8_t* proof_flat, size_t proof_len, uint64_t modulus, uint64_t generator, unsigned log_n,
                      uint64_t offset, size_t num_queries, size_t max_index, int* ok, char* reason);
+/* Verifier of stark101_prove's transcript; public input = the claimed a_{T-2}.  Adds to the FRI checks: the three
+ * trace openings per query authenticate against the trace root and layer 0 of the FRI equals the composition
+ * polynomial computed from them. */
+int stark101_verify(const uint8_t* proof_flat, size_t proof_len, uint64_t modulus, uint64_t generator, uint64_t claimed_last,
+                    unsigned log_trace, unsigned log_blowup, size_t num_queries, int* ok, char* reason);
 
 /* ---- prover (build-defined: src/prover, src/trace, src/composition are empty in the reference) ----
  * STARK-101 FibonacciSq statement a0 = 1, a1 = `a1`, a_{n+2} = a_{n+1}^2 + a_n^2 over 2^log_trace - 1 rows;

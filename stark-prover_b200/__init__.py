@@ -138,6 +138,7 @@ def lib() -> C.CDLL:
     sig("stark101_prove", I, vp, u64, C.c_uint, C.c_uint, szt, vp)
     sig("stark_merkle_verify", I, vp, szt, szt, u64, vp, szt, C.POINTER(I))
     sig("stark_fri_verify", I, vp, szt, u64, u64, C.c_uint, u64, szt, szt, C.POINTER(I), C.c_char_p)
+    sig("stark101_verify", I, vp, szt, u64, u64, u64, C.c_uint, C.c_uint, szt, C.POINTER(I), C.c_char_p)
     _lib = L
     return L
 
@@ -618,6 +619,16 @@ def verify_fri(proof_flat: bytes, log_n: int, offset: int, num_queries: int, max
     buf = np.frombuffer(proof_flat, dtype=np.uint8).copy()
     ok, reason = C.c_int(0), C.create_string_buffer(160)
     _check(lib().stark_fri_verify(_ptr(buf), buf.size, modulus, generator, log_n, offset, num_queries, max_index, C.byref(ok), reason))
+    return bool(ok.value), reason.value.decode()
+
+
+def stark101_verify(proof_flat: bytes, claimed_last: int, log_trace: int = 10, log_blowup: int = 3, num_queries: int = 3,
+                    modulus: int = P_DEFAULT, generator: int = G_DEFAULT) -> tuple[bool, str]:
+    """Verifier of the FibonacciSq STARK transcript (public input: the claimed a_{T-2}); host side."""
+    buf = np.frombuffer(proof_flat, dtype=np.uint8).copy()
+    ok, reason = C.c_int(0), C.create_string_buffer(160)
+    _check(lib().stark101_verify(_ptr(buf), buf.size, modulus, generator, claimed_last, log_trace, log_blowup, num_queries,
+                                 C.byref(ok), reason))
     return bool(ok.value), reason.value.decode()
 
 

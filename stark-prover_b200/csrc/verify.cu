@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <array>
+#include <functional>
 
 #include "../../include/stark_b200.h"
 #include "handles.hpp"
@@ -74,48 +75,38 @@ bool parse_be8(const std::vector<uint8_t>& m, uint64_t* v) {
     return true;
 }
 
-}  // namespace
+using Msgs = std::vector<std::vector<uint8_t>>;
+// called once per query, after the index is drawn and before the FRI layers are read: may consume messages
+// (trace openings) and returns the value layer 0 must show at `idx` (or no constraint)
+using QueryHook = std::function<bool(size_t idx, const Msgs& msgs, size_t& pos, Channel& ch, uint64_t* expect0, bool* has_expect, std::string* why)>;
 
-extern "C" int stark_merkle_verify(const uint8_t root[32], size_t n_leaves, size_t idx, uint64_t value, const uint8_t* path,
-                                   size_t path_len, int* ok) {
-    if (!root || !ok || (!path && path_len)) { api_set_error("merkle_verify: null argument"); return ST_INVALID; }
-    *ok = merkle_verify(root, n_leaves, idx, value, path, path_len) ? 1 : 0;
-    return ST_OK;
-}
-
-// Replays a proof — the `proof` messages of a Channel that ran fri_commit + decommit_fri, flattened as
-// u32-LE length || bytes records (stark_channel_proof_flat) — against a fresh channel.
-// *ok = 1 iff every root/beta/index is the one the transcript dictates, every opened value authenticates
-// against its layer root, every layer is the fold of the previous one at the queried points, and the last
-// layer equals the final constant.  `reason` (optional, >= 160 bytes) receives the first failure.
-extern "C" int stark_fri_verify(const uint8_t* proof_flat, size_t proof_len, uint64_t modulus, uint64_t generator, unsigned log_n,
-                                uint64_t offset, size_t num_queries, size_t max_index, int* ok, char* reason) {
-    if (!proof_flat || !ok || modulus < 3) { api_set_error("fri_verify: bad argument"); return ST_INVALID; }
-    auto fail = [&](const std::string& why) { *ok = 0; if (reason) { strncpy(reason, why.c_str(), 159); reason[159] = 0; } return ST_OK; };
-    *ok = 0;
-    if (reason) reason[0] = 0;
-    std::vector<std::vector<uint8_t>> msgs;
-    for (size_t o = 0; o < proof_len;) {
-        if (o + 4 > proof_len) return fail("truncated record header");
-        size_t n = (size_t)proof_flat[o] | ((size_t)proof_flat[o + 1] << 8) | ((size_t)proof_flat[o + 2] << 16) | ((size_t)proof_flat[o + 3] << 24);
-        if (o + 4 + n > proof_len) return fail("truncated record");
-        msgs.emplace_back(proof_flat + o + 4, proof_flat + o + 4 + n);
+bool split_records(const uint8_t* flat, size_t len, Msgs& msgs, std::string* why) {
+    for (size_t o = 0; o < len;) {
+        if (o + 4 > len) { *why = "truncated record header"; return false; }
+        size_t n = (size_t)flat[o] | ((size_t)flat[o + 1] << 8) | ((size_t)flat[o + 2] << 16) | ((size_t)flat[o + 3] << 24);
+        if (o + 4 + n > len) { *why = "truncated record"; return false; }
+        msgs.emplace_back(flat + o + 4, flat + o + 4 + n);
         o += 4 + n;
     }
-    const Fp F{modulus};
+    return true;
+}
+
+// fri_commit + decommit_fri as seen by a verifier (fri_verify.rs:12-177, completed); starts at msgs[pos] with the
+// channel in the state the prover had when it called fri_commit
+bool verify_fri_core(const Msgs& msgs, size_t& pos, Channel& ch, const Fp& F, uint64_t generator, unsigned log_n, uint64_t offset,
+                     size_t num_queries, size_t max_index, const QueryHook& hook, std::string* why) {
+    auto fail = [&](const std::string& w) { *why = w; return false; };
     if (log_n > 40 || ((F.p - 1) & ((((uint64_t)1) << log_n) - 1)) != 0) return fail("2^log_n does not divide p-1");
     if (offset % F.p == 0) return fail("zero coset offset");
     const size_t n0 = (size_t)1 << log_n;
-    size_t pos = 0;
     auto next = [&]() -> const std::vector<uint8_t>* { return pos < msgs.size() ? &msgs[pos++] : nullptr; };
 
     // ---- commit phase: roots and betas (fri_commit.rs:86-103), then the final constant (:109-114)
-    Channel ch(F.p);
     std::vector<std::array<uint8_t, 32>> roots;
     std::vector<uint64_t> betas;
     const std::vector<uint8_t>* m = next();
     std::array<uint8_t, 32> r{};
-    if (!m || !parse_hex_root(*m, r.data())) return fail("first message is not a 64-character hex root");
+    if (!m || !parse_hex_root(*m, r.data())) return fail("first FRI message is not a 64-character hex root");
     roots.push_back(r);
     ch.send(m->data(), m->size());
     uint64_t final_value = 0;
@@ -152,6 +143,9 @@ extern "C" int stark_fri_verify(const uint8_t* proof_flat, size_t proof_len, uin
         m = next();
         uint64_t idx_msg;
         if (!m || !parse_be8(*m, &idx_msg) || idx_msg != idx_want) return fail("query index does not follow from the transcript");
+        uint64_t expect0 = 0;
+        bool has_expect = false;
+        if (hook && !hook((size_t)idx_want, msgs, pos, ch, &expect0, &has_expect, why)) return false;
         uint64_t prev_a = 0, prev_b = 0;      // opened pair of the previous layer, ordered (j, j + n/2)
         size_t prev_j = 0;
         uint64_t off_k = offset % F.p, w_k = w0;
@@ -176,12 +170,11 @@ extern "C" int stark_fri_verify(const uint8_t* proof_flat, size_t proof_len, uin
                 ch.send(me->data(), me->size());
                 ch.send(mp->data(), mp->size());
             }
+            if (k == 0 && has_expect && val[0] != expect0) return fail("layer 0 does not equal the composition polynomial at the queried point");
             const size_t j = i % (n / 2 ? n / 2 : 1);
             const uint64_t a = (i < n / 2 || n == 1) ? val[0] : val[1], b = (i < n / 2 || n == 1) ? val[1] : val[0];
             if (k > 0) {
                 // e_k[j'] == (a+b)/2 + beta_k (a-b) / (2 D_{k-1}[j]),  D_{k-1}[j] = off * w^j   (fri_verify.rs:153-170, completed)
-                const size_t np = n0 >> (k - 1);
-                (void)np;
                 uint64_t d = F.mul(off_k, h_pow(w_k, prev_j, F.p));
                 uint64_t folded = F.add(F.mul(F.add(prev_a, prev_b), inv2),
                                         F.mul(F.mul(betas[k - 1], F.sub(prev_a, prev_b)), F.inv(F.mul(2 % F.p, d))));
@@ -192,7 +185,92 @@ extern "C" int stark_fri_verify(const uint8_t* proof_flat, size_t proof_len, uin
             if (k + 1 == L && (val[0] != final_value || val[1] != final_value)) return fail("last layer does not equal the final constant");
         }
     }
-    if (pos != msgs.size()) return fail("trailing messages after the last query");
-    *ok = 1;
+    return true;
+}
+
+}  // namespace
+
+extern "C" int stark_merkle_verify(const uint8_t root[32], size_t n_leaves, size_t idx, uint64_t value, const uint8_t* path,
+                                   size_t path_len, int* ok) {
+    if (!root || !ok || (!path && path_len)) { api_set_error("merkle_verify: null argument"); return ST_INVALID; }
+    *ok = merkle_verify(root, n_leaves, idx, value, path, path_len) ? 1 : 0;
     return ST_OK;
+}
+
+static int finish(bool good, const std::string& why, int* ok, char* reason) {
+    *ok = good ? 1 : 0;
+    if (reason) { strncpy(reason, good ? "" : why.c_str(), 159); reason[159] = 0; }
+    return ST_OK;
+}
+
+// Replays a proof — the `proof` messages of a Channel that ran fri_commit + decommit_fri, flattened as
+// u32-LE length || bytes records (stark_channel_proof_flat) — against a fresh channel.
+// *ok = 1 iff every root/beta/index is the one the transcript dictates, every opened value authenticates
+// against its layer root, every layer is the fold of the previous one at the queried points, and the last
+// layer equals the final constant.  `reason` (optional, >= 160 bytes) receives the first failure.
+extern "C" int stark_fri_verify(const uint8_t* proof_flat, size_t proof_len, uint64_t modulus, uint64_t generator, unsigned log_n,
+                                uint64_t offset, size_t num_queries, size_t max_index, int* ok, char* reason) {
+    if (!proof_flat || !ok || modulus < 3) { api_set_error("fri_verify: bad argument"); return ST_INVALID; }
+    Msgs msgs;
+    std::string why;
+    if (!split_records(proof_flat, proof_len, msgs, &why)) return finish(false, why, ok, reason);
+    const Fp F{modulus};
+    Channel ch(F.p);
+    size_t pos = 0;
+    bool good = verify_fri_core(msgs, pos, ch, F, generator, log_n, offset, num_queries, max_index, nullptr, &why);
+    if (good && pos != msgs.size()) { good = false; why = "trailing messages after the last query"; }
+    return finish(good, why, ok, reason);
+}
+
+// Verifier of the build-defined FibonacciSq STARK (stark101_prove).  Public input: the claimed
+// a_{T-2} (`claimed_last`); the witness a1 is not needed.  On top of the FRI checks it authenticates f(x), f(gx),
+// f(g^2 x) against the trace root and requires layer 0 of the FRI to equal alpha0 p0 + alpha1 p1 + alpha2 p2
+// computed from them — the link between the trace commitment and the low-degree test.
+extern "C" int stark101_verify(const uint8_t* proof_flat, size_t proof_len, uint64_t modulus, uint64_t generator, uint64_t claimed_last,
+                               unsigned log_trace, unsigned log_blowup, size_t num_queries, int* ok, char* reason) {
+    if (!proof_flat || !ok || modulus < 3) { api_set_error("stark101_verify: bad argument"); return ST_INVALID; }
+    Msgs msgs;
+    std::string why;
+    if (!split_records(proof_flat, proof_len, msgs, &why)) return finish(false, why, ok, reason);
+    const Fp F{modulus};
+    const unsigned log_N = log_trace + log_blowup;
+    if (log_N > 40 || ((F.p - 1) & ((((uint64_t)1) << log_N) - 1)) != 0) return finish(false, "domain does not divide p-1", ok, reason);
+    const size_t T = (size_t)1 << log_trace, N = (size_t)1 << log_N, blow = (size_t)1 << log_blowup;
+    const uint64_t g = h_pow(generator % F.p, (F.p - 1) >> log_trace, F.p), h = h_pow(generator % F.p, (F.p - 1) >> log_N, F.p);
+    const uint64_t w = generator % F.p;
+    Channel ch(F.p);
+    size_t pos = 0;
+    std::array<uint8_t, 32> f_root{};
+    if (msgs.empty() || !parse_hex_root(msgs[0], f_root.data())) return finish(false, "first message is not the trace root", ok, reason);
+    ch.send(msgs[0].data(), msgs[0].size());
+    pos = 1;
+    uint64_t alpha[3];
+    for (int k = 0; k < 3; k++) {
+        uint64_t rec, want;
+        if (pos >= msgs.size() || !parse_be8(msgs[pos], &rec) || !ch.receive_random_field_element(&want) || want != rec % F.p)
+            return finish(false, "alpha does not follow from the transcript", ok, reason);
+        alpha[k] = want; pos++;
+    }
+    const uint64_t x_last = h_pow(g, T - 2, F.p), ex0 = h_pow(g, T - 3, F.p), ex2 = h_pow(g, T - 1, F.p);
+    QueryHook hook = [&](size_t idx, const Msgs& ms, size_t& p, Channel& c, uint64_t* expect0, bool* has, std::string* wy) {
+        uint64_t fv[3];
+        for (int t = 0; t < 3; t++) {                                       // f(x), f(g x), f(g^2 x): g = h^blow
+            if (p + 2 > ms.size() || !parse_be8(ms[p], &fv[t]) || fv[t] >= F.p) { *wy = "truncated trace opening"; return false; }
+            if (!merkle_verify(f_root.data(), N, idx + t * blow, fv[t], ms[p + 1].data(), ms[p + 1].size())) { *wy = "trace opening does not authenticate against the trace root"; return false; }
+            c.send(ms[p].data(), ms[p].size()); c.send(ms[p + 1].data(), ms[p + 1].size());
+            p += 2;
+        }
+        const uint64_t x = F.mul(w, h_pow(h, idx, F.p));
+        const uint64_t p0 = F.mul(F.sub(fv[0], 1 % F.p), F.inv(F.sub(x, 1 % F.p)));
+        const uint64_t p1 = F.mul(F.sub(fv[0], claimed_last % F.p), F.inv(F.sub(x, x_last)));
+        const uint64_t num = F.sub(F.sub(fv[2], F.mul(fv[1], fv[1])), F.mul(fv[0], fv[0]));
+        const uint64_t e3 = F.mul(F.mul(F.sub(x, ex0), F.sub(x, x_last)), F.sub(x, ex2));
+        const uint64_t p2 = F.mul(F.mul(num, e3), F.inv(F.sub(h_pow(x, T, F.p), 1 % F.p)));
+        *expect0 = F.add(F.add(F.mul(alpha[0], p0), F.mul(alpha[1], p1)), F.mul(alpha[2], p2));
+        *has = true;
+        return true;
+    };
+    bool good = verify_fri_core(msgs, pos, ch, F, generator, log_N, w, num_queries, N - 1 - 2 * blow, hook, &why);
+    if (good && pos != msgs.size()) { good = false; why = "trailing messages after the last query"; }
+    return finish(good, why, ok, reason);
 }

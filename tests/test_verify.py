@@ -65,3 +65,33 @@ def test_verifier_accepts_gpu_proofs(sp, orc, ctx, log_n, log_deg, q):
     assert ok, why
     t = pr.tree(0)
     assert sp.merkle_validate(t.root_bytes(), 1 << log_n, 5, int(pr.layer(0, 5, 1)[0]), t.get_authentication_path(5))
+
+
+def test_stark101_verifier_on_oracle_transcript(sp, orc):
+    """End-to-end soundness of the build-defined prover: the verifier links trace openings, composition polynomial
+    and FRI.  CPU only (oracle transcript)."""
+    ch = orc.Channel(P)
+    orc.stark101_prove(ch, literal=False)
+    claimed = int(orc.fibsq_trace(3141592, 1023)[1022])
+    ok, why = sp.stark101_verify(ch.proof_flat(), claimed)
+    assert ok, why
+    ok, why = sp.stark101_verify(ch.proof_flat(), claimed + 1)          # a false claim about a_1022
+    assert not ok and "composition" in why
+    msgs = ch.proof
+    for pos in (0, 1, 4, 20, 21, 22, 23, len(msgs) - 1):                 # trace root, alpha, CP root, final..., openings
+        bad = [bytearray(m) for m in msgs]
+        bad[pos][len(bad[pos]) // 2] ^= 0x04
+        ok, why = sp.stark101_verify(b"".join(len(m).to_bytes(4, "little") + bytes(m) for m in bad), claimed)
+        assert not ok and why, pos
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("log_trace,a1", [(10, 3141592), (14, 7)])
+def test_stark101_verifier_accepts_gpu_proof(sp, orc, ctx, log_trace, a1):
+    ch = sp.Channel(P)
+    sp.stark101_prove(ctx, ch, a1, log_trace, 3, 3)
+    claimed = int(orc.fibsq_trace(a1, (1 << log_trace) - 1)[(1 << log_trace) - 2])
+    ok, why = sp.stark101_verify(ch.proof_flat(), claimed, log_trace, 3, 3)
+    assert ok, why
+    ok, _ = sp.stark101_verify(ch.proof_flat(), (claimed + 5) % P, log_trace, 3, 3)
+    assert not ok
