@@ -141,6 +141,24 @@ def algorithmic_counts(log_n: int, log_deg: int) -> dict:
 
 
 # ------------------------------------------------------------------------------------------- reference arm
+def literal_tier(orc, log_n_full, log_blowup):
+    """the reference's LITERAL algorithm (Horner over every layer's domain, single thread like
+    the reference) timed where it finishes in about a second, with the analytic extrapolation to the full workload."""
+    ln = 13
+    c = orc.synthetic_poly_exact_degree(43, 1 << (ln - log_blowup), P)
+    dom = orc.coset_domain(OFFSET, orc.root_of_unity(ln, P), 1 << ln, P)
+    horner = lambda l: sum((1 << (l - k)) * (1 << (l - log_blowup - k)) for k in range(l - log_blowup + 1))
+    t0 = time.perf_counter()
+    pr = orc.fri_commit_literal(c, dom, orc.Channel(P), P)
+    dt = time.perf_counter() - t0
+    del pr
+    ns = dt * 1e9 / horner(ln)
+    return {"measured": f"fri_commit, literal tier, 2^{ln} domain, 1 thread: {dt * 1e3:.1f} ms", "ns_per_horner_step": ns,
+            "horner_steps_full_workload": horner(log_n_full),
+            "extrapolated_seconds_full_workload": ns * 1e-9 * horner(log_n_full),
+            "note": "upper-bounds the reference's speed: its field multiply is a u128 remainder (element.rs:106), the oracle's is u64"}
+
+
 def cpu_step(orc, coeffs, log_n, queries):
     """The reference's fri_commit + decommit_fri on the CPU (oracle port, NTT tier, retained trees)."""
     ch = orc.Channel(P)
@@ -175,7 +193,8 @@ def run_reference(args):
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": f"cfg3: FRI commit at 2^{args.log_n} domain, blowup 8, {QUERIES} queries (bounded CPU sample at 2^{log_n})",
                        "log_domain": args.log_n, "sample_log_domain": log_n},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "literal": literal_tier(orc, args.log_n, args.log_blowup)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "the reference is Rust nightly + un-vendored crates and cannot be built in this image; this is the C oracle port of its "
@@ -411,7 +430,8 @@ def run_b200(args):
             dt = (time.perf_counter() - t0) / reps
             line["cpu_baseline"] = {"value": (1 << cl) / dt / 1e6, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
                                     "sample": f"{reps} x fri_commit+decommit_fri at a 2^{cl} domain (1/{1 << (log_n - cl)} of the workload), "
-                                              f"oracle NTT tier + OpenMP, SHA-NI={bool(orc.lib().or_sha256_accel_active())}"}
+                                              f"oracle NTT tier + OpenMP, SHA-NI={bool(orc.lib().or_sha256_accel_active())}",
+                                    "literal": literal_tier(orc, log_n, args.log_blowup)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
