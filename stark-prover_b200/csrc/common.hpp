@@ -177,8 +177,7 @@ struct stark_ctx {
     starkb200::HostResult* d_result = nullptr;  // device alias of h_result
     starkb200::PinnedBuf pin_desc, pin_out;     // opening descriptors in, opening records out
     starkb200::DevBuf deg_scratch;              // DegScratch of coeff_fold_kernel
-    starkb200::DevBuf tail_counter;             // grid-barrier arrival counter of merkle_tail_kernel (monotone)
-    unsigned tail_count = 0;                    // its value once every launch issued so far has finished
+    starkb200::DevBuf tail_counter;             // "last CTA" ticket of merkle_tail_kernel (zero between launches)
     int sm_count = 148;
     unsigned long long launches = 0;            // kernels launched through this context
 

@@ -149,11 +149,14 @@ merkle_subtree_kernel(LeafSource src, const uint32_t* in_digests, size_t n, int 
 // ---- latency-bound part of every tree: one launch, one node per thread per level ------------------------
 // Below ~2^15 nodes a level no longer fills the machine and what matters is the length of the dependency
 // chain: 2 compressions per level.  Giving each thread 8 items (merkle_subtree_kernel) makes that chain 14
-// compressions per 3 levels.  This kernel instead walks the remaining levels with one parent per thread:
-// levels wider than a CTA are separated by a grid-wide barrier (cooperative launch: all CTAs are resident;
-// digests cross SMs through L2 with ld.global.cg), the last <= 128-parent levels run in CTA 0 alone.
-// 128-thread CTAs, at most 128 of them: every warp gets a scheduler (SM sub-partition) to itself, so the
-// ALU pipe (one warp instruction per 2 cycles) is never shared -- two warps per scheduler double the level time.
+// compressions per 3 levels.  This kernel instead walks the remaining levels with one parent per thread.
+// A CTA owns 256 consecutive items and reduces them 8 levels to one node, handing digests from level to
+// level through shared memory (word-major rows: a parent reads its two children as one conflict-free 64-bit
+// load per word); every node is also written to its place in the stored tree.  The CTA that finishes last
+// (an atomic ticket, no CTA ever waits for another) picks the <= 128 chunk roots out of L2 and walks the
+// remaining levels the same way.  128-thread CTAs: every warp gets a scheduler (SM sub-partition) to itself,
+// so the ALU pipe (one warp instruction per 2 cycles) is never shared -- two warps per scheduler double the
+// level time.
 constexpr int TAIL_THREADS = 128;
 constexpr int TAIL_MAX_CTAS = 128;
 constexpr int TAIL_MAX = 2 * TAIL_THREADS * TAIL_MAX_CTAS;      // 32768 items -> 16384 parents, one per thread
@@ -166,129 +169,121 @@ __device__ __forceinline__ Digest load_digest_cg(const uint32_t* p) {
     d.w[4] = b.x; d.w[5] = b.y; d.w[6] = b.z; d.w[7] = b.w;
     return d;
 }
-// monotone counter barrier: arrival k of a launch waits for base + k * gridDim.x
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
-        while ((int)(atomicAdd(counter, 0u) - target) < 0) { }
-        __threadfence();
-    }
-    __syncthreads();
-}
 
 struct TailArgs {
     LeafSource src;              // SRC_VALUES / SRC_FOLD: the items are leaf values
     const uint32_t* in_digests;  // SRC_DIGESTS: the items are stored digests
     int n_items;
     uint32_t* out;               // storage of the next level; the levels above follow contiguously
-    unsigned* barrier;
-    unsigned barrier_base;
+    unsigned* ticket;            // zero between launches (the last CTA resets it)
     HostResult* result;
     FieldParams fp;
 };
 
 template <int SRC>
 __global__ void __launch_bounds__(TAIL_THREADS) merkle_tail_kernel(TailArgs a) {
-    const int tid = blockIdx.x * TAIL_THREADS + threadIdx.x;
-    const int nthreads = gridDim.x * TAIL_THREADS;
-    int len = a.n_items;
-    const uint32_t* in = a.in_digests;
-    uint32_t* out = a.out;
-    unsigned arrivals = 0;
-    bool first = true;
+    __shared__ __align__(8) uint32_t sm[2][8][TAIL_THREADS + 2];
+    __shared__ int s_last;
+    const int t = threadIdx.x;
+    int len = a.n_items;                         // length of the level being consumed
+    uint32_t* out = a.out;                       // storage of the level being produced
     if (len == 1) {                              // one-leaf tree: the root is the leaf digest (slot 0)
-        if (tid == 0) {
+        if (blockIdx.x == 0 && t == 0) {
             Digest d;
-            if (SRC == SRC_DIGESTS) d = load_digest_cg(in);
+            if (SRC == SRC_DIGESTS) d = load_digest_cg(a.in_digests);
             else sha256_leaf(0u, SRC == SRC_FOLD ? fold_at(a.src, 0, a.fp) : a.src.vals[0], d);
             store_digest(out, d);
             if (a.result) for (int i = 0; i < 8; i++) a.result->root[i] = d.w[i];
         }
         return;
     }
-    while (len > 1) {
-        const int out_len = (len + 1) >> 1;
-        for (int j = tid; j < out_len; j += nthreads) {
-            Digest l, r, o;
-            const bool pair = 2 * j + 1 < len;
-            if (first && SRC != SRC_DIGESTS) {
-                sha256_leaf(0u, SRC == SRC_FOLD ? fold_at(a.src, 2 * (size_t)j, a.fp) : a.src.vals[2 * j], l);
-                if (pair) sha256_leaf(0u, SRC == SRC_FOLD ? fold_at(a.src, 2 * (size_t)j + 1, a.fp) : a.src.vals[2 * j + 1], r);
-            } else {
-                l = load_digest_cg(in + 16 * (size_t)j);
-                if (pair) r = load_digest_cg(in + 16 * (size_t)j + 8);
-            }
-            if (pair) sha256_node_fn(&l, &r, &o); else o = l;      // lone node promoted
-            store_digest(out + 8 * (size_t)j, o);
-        }
-        first = false;
-        in = out; out += 8 * (size_t)out_len; len = out_len;
-        if (len == 1) break;
-        if (gridDim.x > 1) {
-            // the next level has (len+1)/2 parents; while the grid is still needed every CTA arrives
-            arrivals++;
-            grid_barrier(a.barrier, a.barrier_base + arrivals * gridDim.x);
-            if (((len + 1) >> 1) <= TAIL_THREADS) {           // from here CTA 0 finishes alone
-                if (blockIdx.x != 0) return;
-                // fall through to the single-CTA loop below
-                while (len > 1) {
-                    const int ol = (len + 1) >> 1;
-                    for (int j = threadIdx.x; j < ol; j += TAIL_THREADS) {
-                        Digest l = load_digest_cg(in + 16 * (size_t)j), o;
-                        if (2 * j + 1 < len) { Digest r = load_digest_cg(in + 16 * (size_t)j + 8); sha256_node_fn(&l, &r, &o); }
-                        else o = l;
-                        store_digest(out + 8 * (size_t)j, o);
+    int base = blockIdx.x * 2 * TAIL_THREADS;    // the CTA's window of that level: `width` nodes from `base`
+    int width = 2 * TAIL_THREADS;
+    int buf = 0;                                 // sm[buf] holds the window (except for the first level)
+    bool first = true;
+    Digest o;
+    for (int phase = 0;; phase++) {
+        while (width > 1) {
+            const int out_len = (len + 1) >> 1;
+            const int j = (base >> 1) + t;       // parent index within its level
+            if (t < (width >> 1) && j < out_len) {
+                Digest l, r;
+                const bool pair = 2 * j + 1 < len;
+                if (first) {
+                    if (SRC == SRC_DIGESTS) {
+                        l = load_digest_cg(a.in_digests + 16 * (size_t)j);
+                        if (pair) r = load_digest_cg(a.in_digests + 16 * (size_t)j + 8);
+                    } else {
+                        sha256_leaf(0u, SRC == SRC_FOLD ? fold_at(a.src, 2 * (size_t)j, a.fp) : a.src.vals[2 * j], l);
+                        if (pair) sha256_leaf(0u, SRC == SRC_FOLD ? fold_at(a.src, 2 * (size_t)j + 1, a.fp) : a.src.vals[2 * j + 1], r);
                     }
-                    __syncthreads();
-                    in = out; out += 8 * (size_t)ol; len = ol;
+                } else {
+#pragma unroll
+                    for (int w = 0; w < 8; w++) {
+                        uint2 v = *reinterpret_cast<const uint2*>(&sm[buf][w][2 * t]);
+                        l.w[w] = v.x; r.w[w] = v.y;
+                    }
                 }
-                break;
+                if (pair) sha256_node_fn(&l, &r, &o); else o = l;      // lone node promoted
+                store_digest(out + 8 * (size_t)j, o);
+#pragma unroll
+                for (int w = 0; w < 8; w++) sm[buf ^ 1][w][t] = o.w[w];
             }
-        } else {
+            first = false;
+            out += 8 * (size_t)out_len; len = out_len; base >>= 1; width >>= 1;
+            if (len == 1) {                                            // that was the root (CTA 0, thread 0 holds it)
+                if (t == 0 && a.result) for (int i = 0; i < 8; i++) a.result->root[i] = o.w[i];
+                return;
+            }
             __syncthreads();
+            buf ^= 1;
         }
+        // the window is reduced to one node and the tree is not finished: more than one CTA took part
+        if (phase == 0) {
+            if (t == 0) {
+                __threadfence();                                       // this CTA's chunk root is visible before the ticket
+                unsigned tk = atomicAdd(a.ticket, 1u);
+                s_last = tk == gridDim.x - 1;
+                if (s_last) { *a.ticket = 0; __threadfence(); }        // every chunk root is in L2; re-arm for the next launch
+            }
+            __syncthreads();
+            if (!s_last) return;
+        }
+        // the last CTA continues with the level just produced (`len` nodes, stored right below `out`)
+        const uint32_t* in = out - 8 * (size_t)len;
+        while (len > TAIL_THREADS) {                                   // wider than a window (n_items > TAIL_MAX): via L2
+            const int out_len = (len + 1) >> 1;
+            for (int j = t; j < out_len; j += TAIL_THREADS) {
+                Digest l = load_digest_cg(in + 16 * (size_t)j), q;
+                if (2 * j + 1 < len) { Digest r = load_digest_cg(in + 16 * (size_t)j + 8); sha256_node_fn(&l, &r, &q); }
+                else q = l;
+                store_digest(out + 8 * (size_t)j, q);
+            }
+            __syncthreads();
+            in = out; out += 8 * (size_t)out_len; len = out_len;
+        }
+        if (t < len) {
+            Digest d = load_digest_cg(in + 8 * (size_t)t);
+#pragma unroll
+            for (int w = 0; w < 8; w++) sm[buf][w][t] = d.w[w];
+            o = d;
+        }
+        __syncthreads();
+        base = 0; width = TAIL_THREADS;
     }
-    if (tid == 0 && a.result) {
-        Digest d = load_digest_cg(in);
-        for (int i = 0; i < 8; i++) a.result->root[i] = d.w[i];
-    }
-}
-
-// number of grid-wide barrier arrivals the kernel above performs for (n_items, ctas): mirrors its control flow
-static unsigned tail_barriers(int n_items, int ctas) {
-    if (ctas <= 1 || n_items <= 1) return 0;
-    unsigned arrivals = 0;
-    int len = n_items;
-    while (len > 1) {
-        len = (len + 1) >> 1;
-        if (len == 1) break;
-        arrivals++;
-        if (((len + 1) >> 1) <= TAIL_THREADS) break;
-    }
-    return arrivals;
 }
 
 template <int SRC>
 static void launch_tail(stark_ctx* ctx, const LeafSource& src, const uint32_t* in_digests, size_t n_items, uint32_t* out,
                         HostResult* result) {
-    if (!ctx->tail_counter.p) {                      // one counter per context (= per stream): launches are ordered
+    if (!ctx->tail_counter.p) {                      // one ticket per context (= per stream): launches are ordered
         ctx->tail_counter = DevBuf(sizeof(unsigned), ctx->stream);
         STARK_CUDA(cudaMemsetAsync(ctx->tail_counter.p, 0, sizeof(unsigned), ctx->stream));
-        ctx->tail_count = 0;
     }
-    int parents = (int)((n_items + 1) / 2);
-    int ctas = (parents + TAIL_THREADS - 1) / TAIL_THREADS;
+    int ctas = (int)((n_items + 2 * TAIL_THREADS - 1) / (2 * TAIL_THREADS));
     if (ctas < 1) ctas = 1;
-    if (ctas > TAIL_MAX_CTAS) ctas = TAIL_MAX_CTAS;
-    TailArgs a{};
-    a.src = src; a.in_digests = in_digests; a.n_items = (int)n_items; a.out = out;
-    a.barrier = ctx->tail_counter.as<unsigned>(); a.barrier_base = ctx->tail_count; a.result = result; a.fp = ctx->fp;
-    ctx->tail_count += tail_barriers((int)n_items, ctas) * (unsigned)ctas;
-    void* args[] = {&a};
-    if (ctas > 1) STARK_CUDA(cudaLaunchCooperativeKernel((const void*)merkle_tail_kernel<SRC>, dim3(ctas), dim3(TAIL_THREADS), args, 0, ctx->stream));
-    else merkle_tail_kernel<SRC><<<1, TAIL_THREADS, 0, ctx->stream>>>(a);
+    TailArgs a{src, in_digests, (int)n_items, out, ctx->tail_counter.as<unsigned>(), result, ctx->fp};
+    merkle_tail_kernel<SRC><<<ctas, TAIL_THREADS, 0, ctx->stream>>>(a);
     ctx->launches++;
 }
 
