@@ -397,7 +397,15 @@ def run_b200(args):
             line["roofline_hbm"] = {
                 "ntt": {"bound": "hbm", "achieved": ntt_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ntt_gbs / hbm_peak if ntt_gbs else None,
                         "kernel_ms_per_step": ntt_ms, "launches_per_step": kt["ntt"]["launches"] // ksteps,
-                        "algorithmic": "8 B per coefficient read + 8 B per evaluation written (SURVEY.md 8d LDE n->N)"},
+                        "algorithmic": "8 B per coefficient read + 8 B per evaluation written (SURVEY.md 8d LDE n->N)",
+                        # (n/2) log2 n butterflies x (mul-mod + add-mod + sub-mod); 32-bit Montgomery product = 6
+                        # instructions, modular add / sub = 3 each; the blow-up is 2^b transforms of size n plus one product per
+                        # coefficient and shift for offset^j: in this 32-bit field the transform is integer-bound, not HBM-bound
+                        "int": (lambda ops: {"achieved": ops / (ntt_ms * 1e-3) / 1e12, "peak": mix_peak, "unit": "Tint-op/s",
+                                             "frac": ops / (ntt_ms * 1e-3) / 1e12 / mix_peak,
+                                             "algorithmic": "12 int-ops per butterfly, (n/2)*log2(n) butterflies per size-n transform, "
+                                                            "2^blowup transforms + 6 per point for the coset shift"})(
+                            (1 << args.log_blowup) * ((1 << log_deg) // 2 * log_deg * 12 + 6 * (1 << log_deg))) if ntt_ms else None},
                 "fold_and_hash": {"bound": "hbm", "achieved": leaf_bytes / (hash_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                   "frac": leaf_bytes / (hash_ms * 1e-3) / 1e9 / hbm_peak,
                                   "note": "same launches as `roofline`: integer-bound, HBM fraction shown for completeness"},

@@ -120,7 +120,7 @@ merkle_subtree_kernel(LeafSource src, const uint32_t* in_digests, size_t n, int 
 #pragma unroll 1
     for (int i = 0; i < cnt; i++) {
         if (SRC == SRC_DIGESTS) d = load_digest(in_digests + 8 * (base + i));
-        else sha256_leaf(0u, v[i], d);
+        else sha256_leaf32(v[i], d);
         int level = 0;
         unsigned idx = (unsigned)i;
         while (level < nlev && (idx & 1u)) {
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) merkle_tail_kernel(TailArgs a) {
         if (blockIdx.x == 0 && t == 0) {
             Digest d;
             if (SRC == SRC_DIGESTS) d = load_digest_cg(a.in_digests);
-            else sha256_leaf(0u, SRC == SRC_FOLD ? fold_at(a.src, 0, a.fp) : a.src.vals[0], d);
+            else sha256_leaf32(SRC == SRC_FOLD ? fold_at(a.src, 0, a.fp) : a.src.vals[0], d);
             store_digest(out, d);
             if (a.result) for (int i = 0; i < 8; i++) a.result->root[i] = d.w[i];
         }
@@ -214,8 +214,8 @@ __global__ void __launch_bounds__(TAIL_THREADS) merkle_tail_kernel(TailArgs a) {
                         l = load_digest_cg(a.in_digests + 16 * (size_t)j);
                         if (pair) r = load_digest_cg(a.in_digests + 16 * (size_t)j + 8);
                     } else {
-                        sha256_leaf(0u, SRC == SRC_FOLD ? fold_at(a.src, 2 * (size_t)j, a.fp) : a.src.vals[2 * j], l);
-                        if (pair) sha256_leaf(0u, SRC == SRC_FOLD ? fold_at(a.src, 2 * (size_t)j + 1, a.fp) : a.src.vals[2 * j + 1], r);
+                        sha256_leaf32(SRC == SRC_FOLD ? fold_at(a.src, 2 * (size_t)j, a.fp) : a.src.vals[2 * j], l);
+                        if (pair) sha256_leaf32(SRC == SRC_FOLD ? fold_at(a.src, 2 * (size_t)j + 1, a.fp) : a.src.vals[2 * j + 1], r);
                     }
                 } else {
 #pragma unroll
@@ -356,7 +356,7 @@ __global__ void merkle_open_kernel(const OpenDesc* desc, size_t n_desc, uint8_t*
     }
     if (exists) {
         Digest dg;
-        if (lane == 0) sha256_leaf(0u, d.vals[j], dg);
+        if (lane == 0) sha256_leaf32(d.vals[j], dg);
         else dg = load_digest(d.nodes + 8 * (off_l + j));
         unsigned pos = __popc(mask & ((1u << lane) - 1u));
         uint32_t* o = rec + 2 + 8 * pos;
@@ -408,7 +408,7 @@ __global__ void fri_open_one_kernel(FriOpenArgs a) {
     }
     if (exists) {
         Digest dg;
-        if (lane == 0) sha256_leaf(0u, L.vals[j], dg);
+        if (lane == 0) sha256_leaf32(L.vals[j], dg);
         else dg = load_digest(L.nodes + 8 * (off_l + j));
         unsigned pos = __popc(mask & ((1u << lane) - 1u));
         uint32_t* o = rec + 2 + 8 * pos;
