@@ -10,9 +10,9 @@
 // sibling digest from the sibling value.
 //
 // Work decomposition.  Each thread owns 2^S consecutive items of one level and reduces them to one
-// digest S levels up entirely in registers (no shared memory, no barriers), writing every
-// intermediate digest once.  One launch therefore advances the tree by S levels; a single-CTA kernel
-// finishes the last <= 9 levels.  The leaf launch can take its values from the FRI fold of the
+// digest S levels up on its own (no barriers; its stack of pending left siblings is a private column of
+// shared memory), writing every intermediate digest once.  One launch therefore advances the tree by S
+// levels; merkle_tail_kernel finishes the last <= 15 levels in one launch.  The leaf launch can take its values from the FRI fold of the
 // previous layer (fused fold-and-hash, reference src/fri/fri_commit.rs:94-97).
 #include "kernels.hpp"
 #include "sha256.cuh"
@@ -46,13 +46,18 @@ constexpr int SUB = 3;            // levels advanced per launch (2^SUB items per
 constexpr int MERKLE_THREADS = STARK_MERKLE_THREADS;
 
 struct LevelPtrs { uint32_t* p[SUB + 1]; };   // p[l], l = 1..SUB: storage of the l-th level produced by this launch
+// run-time level -> pointer without indexing the kernel parameter dynamically (that would copy it to local memory)
+__device__ __forceinline__ uint32_t* level_storage(const LevelPtrs& lv, int level) {
+    static_assert(SUB == 3, "level_storage spells out SUB levels");
+    return level == 1 ? lv.p[1] : level == 2 ? lv.p[2] : lv.p[3];
+}
 
 // One shared copy of the two-block parent hash: every call site in a kernel jumps here, so the code a
 // thread walks through stays a few tens of KB (see sha256_compress).
-__device__ __noinline__ void sha256_node_fn(const Digest* l, const Digest* r, Digest* out) {
-    Digest a = *l, b = *r, o;
-    sha256_node(a, b, o);
-    *out = o;
+__device__ __noinline__ Digest sha256_node_fn(Digest l, Digest r) {
+    Digest o;
+    sha256_node(l, r, o);
+    return o;
 }
 
 __device__ __forceinline__ uint32_t fold_one(uint32_t a, uint32_t b, uint32_t s_m, uint32_t inv2_m, const FieldParams& fp) {
@@ -115,20 +120,35 @@ merkle_subtree_kernel(LeafSource src, const uint32_t* in_digests, size_t n, int 
             for (int j = 0; j < (1 << SUB); j++) v[j] = j < cnt ? fold_at(src, base + j, fp) : 0u;
         }
     }
-    Digest stk[SUB + 1];
+    // pending left siblings, one per level, and the thread's 8 values: word-major in shared memory (the loops
+    // below index them with run-time levels / positions; in local memory they cost 190 MB of dead write-backs
+    // per 2^24-leaf launch)
+    __shared__ uint32_t s_stk[SUB][8][MERKLE_THREADS];
+    __shared__ uint32_t s_v[1 << SUB][MERKLE_THREADS];
+    const int tx = threadIdx.x;
+    if (SRC != SRC_DIGESTS) {
+#pragma unroll
+        for (int j = 0; j < (1 << SUB); j++) s_v[j][tx] = v[j];
+    }
     Digest d;
 #pragma unroll 1
     for (int i = 0; i < cnt; i++) {
         if (SRC == SRC_DIGESTS) d = load_digest(in_digests + 8 * (base + i));
-        else sha256_leaf32(v[i], d);
+        else sha256_leaf32(s_v[i][tx], d);
         int level = 0;
         unsigned idx = (unsigned)i;
         while (level < nlev && (idx & 1u)) {
-            sha256_node_fn(&stk[level], &d, &d);
+            Digest l;
+#pragma unroll
+            for (int w = 0; w < 8; w++) l.w[w] = s_stk[level][w][tx];
+            d = sha256_node_fn(l, d);
             level++; idx >>= 1;
-            store_digest(lv.p[level] + 8 * ((t << (SUB - level)) + idx), d);
+            store_digest(level_storage(lv, level) + 8 * ((t << (SUB - level)) + idx), d);
         }
-        if (level < nlev) stk[level] = d;
+        if (level < nlev) {
+#pragma unroll
+            for (int w = 0; w < 8; w++) s_stk[level][w][tx] = d.w[w];
+        }
     }
     if (nlev == 0) {                                    // one-leaf tree: the root is the leaf digest
         store_digest(lv.p[1], d);
@@ -136,10 +156,17 @@ merkle_subtree_kernel(LeafSource src, const uint32_t* in_digests, size_t n, int 
         bool have = false;
         for (int level = 0; level < nlev; level++) {
             bool pend = (cnt >> level) & 1;
-            if (have && pend) sha256_node_fn(&stk[level], &d, &d);
-            else if (pend) { d = stk[level]; have = true; }
-            else if (!have) continue;
-            store_digest(lv.p[level + 1] + 8 * ((t << (SUB - level - 1)) + (size_t)(cnt >> (level + 1))), d);
+            if (have && pend) {
+                Digest l;
+#pragma unroll
+                for (int w = 0; w < 8; w++) l.w[w] = s_stk[level][w][tx];
+                d = sha256_node_fn(l, d);
+            } else if (pend) {
+#pragma unroll
+                for (int w = 0; w < 8; w++) d.w[w] = s_stk[level][w][tx];
+                have = true;
+            } else if (!have) continue;
+            store_digest(level_storage(lv, level + 1) + 8 * ((t << (SUB - level - 1)) + (size_t)(cnt >> (level + 1))), d);
         }
     }
     if (last && t == 0 && result)
@@ -224,7 +251,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) merkle_tail_kernel(TailArgs a) {
                         l.w[w] = v.x; r.w[w] = v.y;
                     }
                 }
-                if (pair) sha256_node_fn(&l, &r, &o); else o = l;      // lone node promoted
+                if (pair) o = sha256_node_fn(l, r); else o = l;      // lone node promoted
                 store_digest(out + 8 * (size_t)j, o);
 #pragma unroll
                 for (int w = 0; w < 8; w++) sm[buf ^ 1][w][t] = o.w[w];
@@ -255,7 +282,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) merkle_tail_kernel(TailArgs a) {
             const int out_len = (len + 1) >> 1;
             for (int j = t; j < out_len; j += TAIL_THREADS) {
                 Digest l = load_digest_cg(in + 16 * (size_t)j), q;
-                if (2 * j + 1 < len) { Digest r = load_digest_cg(in + 16 * (size_t)j + 8); sha256_node_fn(&l, &r, &q); }
+                if (2 * j + 1 < len) { Digest r = load_digest_cg(in + 16 * (size_t)j + 8); q = sha256_node_fn(l, r); }
                 else q = l;
                 store_digest(out + 8 * (size_t)j, q);
             }

@@ -3,6 +3,7 @@
 
   python tools/ncu_summary.py launches gpurun_out/launches_r1d.csv profiles/r01_launches.md
   python tools/ncu_summary.py full gpurun_out/prof_merkle_r1c.ncu-rep profiles/r01_merkle_full.md
+  python tools/ncu_summary.py traffic gpurun_out/traffic_r1.csv profiles/r01_traffic.json
 """
 import collections
 import csv
@@ -33,7 +34,7 @@ def short(name: str) -> str:
 
 def launches(src, dst):
     lines = [l for l in open(src) if not l.startswith("==")]
-    rows = list(csv.DictReader(lines))
+    rows = [r for r in csv.DictReader(lines) if r["Metric Name"] == "gpu__time_duration.sum"]
     half = len(rows) // 2           # --profile-mode runs 1 warm-up step + 1 step: keep the second
     step = rows[half:]
     agg, tot = collections.OrderedDict(), 0.0
@@ -69,5 +70,33 @@ def full(src, dst):
     print("wrote", dst)
 
 
+def traffic(src, dst):
+    """DRAM bytes per kernel over the second (= measured) step of `bench.py --profile-mode --steps 1 --warmup 1` captured with
+    --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum."""
+    import json
+    lines = [l for l in open(src) if not l.startswith("==")]
+    per_id = collections.OrderedDict()
+    for r in csv.DictReader(lines):
+        d = per_id.setdefault(int(r["ID"]), {"kernel": short(r["Kernel Name"])})
+        d[r["Metric Name"]] = float(r["Metric Value"].replace(",", "")) * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r["Metric Unit"], 1.0)
+    rows = list(per_id.values())
+    step = rows[len(rows) // 2:]
+    per_kernel = collections.OrderedDict()
+    for r in step:
+        k = per_kernel.setdefault(r["kernel"], {"launches": 0, "dram_read": 0.0, "dram_write": 0.0, "us": 0.0})
+        k["launches"] += 1
+        k["dram_read"] += r.get("dram__bytes_read.sum", 0.0)
+        k["dram_write"] += r.get("dram__bytes_write.sum", 0.0)
+        k["us"] += r.get("gpu__time_duration.sum", 0.0) / 1e3
+    hashing = [v for k, v in per_kernel.items() if k.startswith("merkle_subtree_kernel") or k.startswith("merkle_tail_kernel")]
+    n = sum(v["launches"] for v in hashing)
+    b = sum(v["dram_read"] + v["dram_write"] for v in hashing)
+    json.dump({"source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none over one "
+                         f"step of bench.py --profile-mode ({src})",
+               "hashing_launches": n, "hashing_dram_bytes_per_step": b, "hashing_dram_bytes_per_launch": b / max(n, 1),
+               "per_kernel": per_kernel}, open(dst, "w"), indent=1)
+    print("wrote", dst)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
