@@ -26,6 +26,21 @@ def test_merkle_root_and_levels(sp, orc, ctx, n):
         assert t.get_authentication_path(idx) == ot.path(idx), idx
 
 
+@pytest.mark.parametrize("n", [255, 256, 258, 769, 32767, 32768, 32769, 65537, 100003])
+def test_merkle_every_node(sp, orc, ctx, n):
+    """Sizes around the chunk (256 items per CTA) and launch (2^15 items) boundaries of the tail kernel; ragged at many
+    levels; every stored node compared, not a sample."""
+    vals = orc.synthetic_column(1000 + n, n)
+    t = sp.MerkleTree.new(ctx, vals)
+    ot = orc.Tree(vals)
+    assert t.root() == ot.root_hex()
+    for l in range(1, t.depth + 1):
+        m = -(-n // (1 << l))
+        step = 1 if m <= 4096 else 7                      # all nodes of the upper levels, every 7th (+ the last) below
+        for j in list(range(0, m, step)) + [m - 1]:
+            assert t.node(l, j) == ot.node(l, j), (l, j)
+
+
 def test_merkle_anchors(sp, ctx, golden):
     a = golden["spec_anchors"]
     for v, h in a["leaf"].items():

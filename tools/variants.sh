@@ -1,8 +1,10 @@
 #!/bin/bash
-for defs in "" "-DSTARK_SHA_SHR_ON_FMA=0"; do
+# Kernel-variant sweep on the GPU box (nvcc is in the image): rebuilds merkle.cu with each -D set and times the tree alone.
+for defs in "" "-DSTARK_MERKLE_MIN_BLOCKS=9" "-DSTARK_MERKLE_MIN_BLOCKS=10" "-DSTARK_MERKLE_THREADS=256 -DSTARK_MERKLE_MIN_BLOCKS=4" \
+            "-DSTARK_MERKLE_THREADS=64" "-DSTARK_SHA_SHR_ON_FMA=1" "-DSTARK_SHA_ADDS_ON_FMA=0"; do
   export STARK_NVCC_DEFS="$defs"
   touch stark-prover_b200/csrc/merkle.cu
   python build_ext.py > /dev/null 2>&1 || { echo "build failed for $defs"; continue; }
   python tools/bench_merkle.py 24
-  python tools/bench_merkle.py 12
+  python tools/bench_merkle.py 24
 done
