@@ -379,9 +379,9 @@ def run_b200(args):
             line["roofline"] = {
                 "kernel": "merkle_subtree_kernel<VALUES|FOLD|DIGESTS> (fused fold + leaf hash, 3 levels per launch) + merkle_tail_kernel",
                 "bound": "int", "achieved": achieved, "peak": mix_peak, "unit": "Tint-op/s", "frac": achieved / mix_peak,
-                "peak_source": "stark_measure_int_peak on this GPU: register chains of SHF/LOP3 (ALU pipe) and IMAD (FMA pipe) "
-                               "issued 10:7, the mix one SHA-256 compression has (~784 rotate/logic ops + ~600 adds); "
-                               f"the ALU pipe alone peaks at {alu_peak:.1f}",
+                "peak_source": "stark_measure_int_peak on this GPU: register chains of SHF/LOP3/IADD3 (ALU pipe) and IMAD (FMA pipe) "
+                               "issued 3:1, the mix of the algorithmic count (1024 rotate/logic instructions : 360 adds per "
+                               f"compression); the ALU pipe alone peaks at {alu_peak:.1f}, and 1024 of the 1384 can only run there",
                 "alu_pipe_peak": alu_peak, "frac_of_alu_pipe_peak": achieved / alu_peak,
                 "traffic": ncu_traffic()[0], "traffic_source": ncu_traffic()[1],
                 "launches_per_step": hash_launches, "kernel_ms_per_step": hash_ms,

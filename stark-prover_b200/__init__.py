@@ -67,6 +67,7 @@ def lib() -> C.CDLL:
     sig("stark_ctx_launch_count", C.c_ulonglong, vp)
     sig("stark_ctx_stream", vp, vp)
     sig("stark_measure_int_peak", I, vp, C.POINTER(C.c_double))
+    sig("stark_measure_pipe_mix", I, vp, C.POINTER(C.c_double))
     sig("stark_ctx_set_timing", I, vp, I)
     sig("stark_ctx_read_timing", I, vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_ulonglong))
     sig("stark_vec_upload", I, vp, vp, szt, C.POINTER(vp))
@@ -199,6 +200,11 @@ class Context:
         t = (C.c_double * 2)()
         _check(lib().stark_measure_int_peak(self.h, t))
         return t[0], t[1]
+
+    def measure_pipe_mix(self) -> list[float]:
+        t = (C.c_double * 5)()
+        _check(lib().stark_measure_pipe_mix(self.h, t))
+        return list(t)
 
     def set_timing(self, on: bool): _check(lib().stark_ctx_set_timing(self.h, int(on)))
 

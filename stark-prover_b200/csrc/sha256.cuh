@@ -83,6 +83,19 @@ __device__ __forceinline__ uint32_t sha_add_imad(uint32_t a, uint32_t b) {
 #define SHA_ADD(x, y) ((x) + (y))
 #endif
 
+// Variant (off): some schedule steps do two of their three adds as ONE three-input IADD3 on the ALU pipe instead of two
+// IMADs (bit j of STARK_SHA_SCHED_IADD3 selects the form for schedule word j of each group of 16).  Motivation: a
+// register-chain micro-benchmark (tools/exp_pipe_mix.py) issues 3 ALU + 1 IMAD in the 6.0 cycles the ALU pipe needs, but
+// 3 ALU + 2 IMAD in 7.0 (IMAD.HI / IMAD.WIDE cost ~5 / ~3 issue cycles, which is why shifts and rotates stay on the ALU
+// pipe), and a compression is 1024 ALU : ~600 IMAD.  Measured on the 2^24-leaf tree: masks 0x0000 / 0x1111 / 0x5555 /
+// 0x7777 / 0xFFFF -> 2.831 / 2.868 / 2.865 / 2.858 / 2.893 ms, i.e. every instruction moved back to the ALU pipe costs
+// time and the all-IMAD form stays (profiles/r01_variants.txt).
+#ifndef STARK_SHA_SCHED_IADD3
+#define STARK_SHA_SCHED_IADD3 0x0000u
+#endif
+#define STARK_SHA_SCHED(w0, s0, w9, s1, j) \
+    (((STARK_SHA_SCHED_IADD3 >> (j)) & 1u) ? SHA_ADD(((w0) + (s0) + (w9)), (s1)) : SHA_ADD(SHA_ADD(SHA_ADD((w0), (s0)), (w9)), (s1)))
+
 // Operand order keeps the per-round dependency chain short: h + kw is known a round early, Ch needs one
 // LOP3 after the new e, Sigma1 two dependent ALU ops, so the new e is 4 dependent instructions after the old
 // one (SHF, LOP3, add, add) and the new a likewise.  Latency-bound launches (the top of every tree) run
@@ -130,7 +143,7 @@ __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16]) 
     for (int i = 16; i < 64; i += 16) {
 #pragma unroll
         for (int j = 0; j < 16; j++)
-            w[j] = SHA_ADD(SHA_ADD(SHA_ADD(w[j], sml_s0(w[(j + 1) & 15])), w[(j + 9) & 15]), sml_s1(w[(j + 14) & 15]));
+            w[j] = STARK_SHA_SCHED(w[j], sml_s0(w[(j + 1) & 15]), w[(j + 9) & 15], sml_s1(w[(j + 14) & 15]), j);
 #define KW_A(j) SHA_ADD(w[j], c_sha_k[i + j])
 #define KW_B(j) SHA_ADD(w[8 + j], c_sha_k[i + 8 + j])
         STARK_SHA_8ROUNDS(a, b, c, d, e, f, g, h, KW_A)
@@ -235,7 +248,7 @@ __device__ __forceinline__ void sha256_leaf32(uint32_t v, Digest& out) {
     for (int i = 32; i < 64; i += 16) {
 #pragma unroll
         for (int j = 0; j < 16; j++)
-            w[j] = SHA_ADD(SHA_ADD(SHA_ADD(w[j], sml_s0(w[(j + 1) & 15])), w[(j + 9) & 15]), sml_s1(w[(j + 14) & 15]));
+            w[j] = STARK_SHA_SCHED(w[j], sml_s0(w[(j + 1) & 15]), w[(j + 9) & 15], sml_s1(w[(j + 14) & 15]), j);
 #define KW_A(j) SHA_ADD(w[j], c_sha_k[i + j])
 #define KW_B(j) SHA_ADD(w[8 + j], c_sha_k[i + 8 + j])
         STARK_SHA_8ROUNDS(a, b, c, d, e, f, g, h, KW_A)
