@@ -126,31 +126,73 @@ void poly_degree(stark_ctx* ctx, const uint32_t* c, size_t len, HostResult* resu
 }
 
 // ---------------- zero-safe batched inverse (Montgomery trick), optional numerator ----------------
-constexpr int INV_K = 8;      // elements per Fermat exponentiation (K = 24 measured slower: registers, strided reach)
-constexpr int INV_THREADS = 256;
-__global__ void __launch_bounds__(INV_THREADS)
-batch_inverse_kernel(const uint32_t* a, const uint32_t* num, uint32_t* out, size_t n, FieldParams fp) {
+// One Fermat exponentiation (63 Montgomery products for this p) per CTA of 4096 elements instead of one per element
+// (element.rs:54-57) or one per thread: a thread multiplies its INV_K elements together, the 256 thread totals are
+// combined with warp-shuffle prefix and suffix product scans plus a pass over the 8 warp totals in shared memory, one
+// lane inverts the CTA total, and every thread gets the inverse of its own total as prefix * suffix * inverse-of-all
+// and unwinds it over its elements.  Integer-bound (a Montgomery product is ~18 issue cycles, two of its five
+// instructions are IMAD.HI): 3 products per element + ~2 per element of scan and inverse, against 13 per element with
+// a Fermat inverse per 8 elements (2^24 elements: 0.119 -> 0.070 ms; sweep of K / CTA size / register cap in
+// profiles/r01_variants.txt).
+// Raw inputs are used as the Montgomery forms of x/R, which keeps every product consistent without a to_mont pass; the
+// result then carries R^2 (R with a numerator), removed by one product with `fix` folded into the CTA inverse.
+// Zeros are skipped (factor 1) and map to 0, like FieldElement::inverse (element.rs:54-57: 0^(p-2) = 0).
+#ifndef STARK_INV_K
+#define STARK_INV_K 16
+#endif
+#ifndef STARK_INV_THREADS
+#define STARK_INV_THREADS 256
+#endif
+#ifndef STARK_INV_MINB
+#define STARK_INV_MINB 6          // resident CTAs per SM: the CTA-wide inversion is a ~1 us serial chain that only other CTAs hide
+#endif
+constexpr int INV_K = STARK_INV_K;
+constexpr int INV_THREADS = STARK_INV_THREADS;
+__global__ void __launch_bounds__(INV_THREADS, STARK_INV_MINB)
+batch_inverse_kernel(const uint32_t* a, const uint32_t* num, uint32_t* out, size_t n, FieldParams fp, uint32_t fix) {
+    __shared__ uint32_t s_tot[INV_THREADS / 32], s_pre[INV_THREADS / 32], s_suf[INV_THREADS / 32], s_inv;
     const size_t base = (size_t)blockIdx.x * (INV_THREADS * INV_K) + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t x[INV_K], pre[INV_K];
     uint32_t acc = fp.one;
 #pragma unroll
     for (int j = 0; j < INV_K; j++) {
         size_t i = base + (size_t)j * INV_THREADS;
-        uint32_t v = i < n ? a[i] : 0u;
-        x[j] = v ? to_mont(v, fp) : 0u;          // 0 marks "skip": zero (or out of range) contributes a factor 1
+        x[j] = i < n ? a[i] : 0u;                  // 0 marks "skip": zero (or out of range) contributes a factor 1
         pre[j] = acc;
-        if (v) acc = mont_mul(acc, x[j], fp);
+        if (x[j]) acc = mont_mul(acc, x[j], fp);
     }
-    uint32_t inv = mont_inv(acc, fp);            // one Fermat exponentiation per INV_K elements
+    // products of the thread totals before / after this thread within the warp
+    uint32_t pfx = acc, sfx = acc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t up = __shfl_up_sync(0xffffffffu, pfx, d), dn = __shfl_down_sync(0xffffffffu, sfx, d);
+        if (lane >= (unsigned)d) pfx = mont_mul(pfx, up, fp);
+        if (lane + d < 32) sfx = mont_mul(sfx, dn, fp);
+    }
+    if (lane == 31) s_tot[warp] = pfx;
+    uint32_t before = __shfl_up_sync(0xffffffffu, pfx, 1), after = __shfl_down_sync(0xffffffffu, sfx, 1);
+    if (lane == 0) before = fp.one;
+    if (lane == 31) after = fp.one;
+    __syncthreads();
+    if (threadIdx.x == 0) {                         // 8 warp totals: prefixes, suffixes, and the one inversion
+        uint32_t run = fp.one;
+        for (int w = 0; w < INV_THREADS / 32; w++) { s_pre[w] = run; run = mont_mul(run, s_tot[w], fp); }
+        s_inv = mont_mul(mont_inv(run, fp), fix, fp);
+        run = fp.one;
+        for (int w = INV_THREADS / 32 - 1; w >= 0; w--) { s_suf[w] = run; run = mont_mul(run, s_tot[w], fp); }
+    }
+    __syncthreads();
+    uint32_t inv = mont_mul(mont_mul(mont_mul(before, s_pre[warp], fp), mont_mul(after, s_suf[warp], fp), fp), s_inv, fp);
 #pragma unroll
     for (int j = INV_K - 1; j >= 0; j--) {
         size_t i = base + (size_t)j * INV_THREADS;
         if (i >= n) continue;
         uint32_t r = 0;
         if (x[j]) {
-            uint32_t r_m = mont_mul(inv, pre[j], fp);
+            r = mont_mul(inv, pre[j], fp);
             inv = mont_mul(inv, x[j], fp);
-            r = num ? mont_mul(r_m, num[i], fp) : from_mont(r_m, fp);
+            if (num) r = mont_mul(r, num[i], fp);
         }
         out[i] = r;
     }
@@ -159,7 +201,10 @@ void batch_inverse(stark_ctx* ctx, const uint32_t* a, const uint32_t* num, uint3
     KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 16.0 * n);
     if (!n) return;
     size_t per = (size_t)INV_THREADS * INV_K;
-    batch_inverse_kernel<<<(unsigned)((n + per - 1) / per), INV_THREADS, 0, ctx->stream>>>(a, num, out, n, ctx->fp);
+    // results come out as x^-1 * R^2: times R^-1 / R (plain output) or times 1 / R (then num / R in the last product)
+    const uint64_t p = ctx->modulus;
+    uint32_t fix = num ? 1u : (uint32_t)h_inv(((uint64_t)1 << 32) % p, p);
+    batch_inverse_kernel<<<(unsigned)((n + per - 1) / per), INV_THREADS, 0, ctx->stream>>>(a, num, out, n, ctx->fp, fix);
     ctx->launches++;
     STARK_CUDA(cudaGetLastError());
 }
