@@ -69,8 +69,9 @@ int stark_ctx_read_timing(stark_ctx* ctx, double ms[4], double units[4], unsigne
  * pipe only, what SHA-256's rotates and boolean functions are bound by), tops[1] = the same with one IMAD per
  * three ALU instructions (ALU + FMA pipes).  MEASURED_PEAKS.json has no integer figure. */
 int stark_measure_int_peak(stark_ctx* ctx, double tops[2]);
-/* Diagnostic: 1e12 chain steps/s of {3 ALU instructions} + {nothing, IMAD, FMA-pipe rotate (mul.wide + mad), mul.hi, 2 IMAD}. */
-int stark_measure_pipe_mix(stark_ctx* ctx, double steps_per_s[5]);
+/* Diagnostic: 1e12 chain steps/s of {3 ALU instructions} + {nothing, IMAD, FMA-pipe rotate (mul.wide + mad), mul.hi, 2 IMAD};
+ * entries 5..7: three IMAD / IMAD.HI / IMAD.WIDE per step with no ALU-pipe work. */
+int stark_measure_pipe_mix(stark_ctx* ctx, double steps_per_s[8]);
 
 /* ---- device vectors ------------------------------------------------------------------------------ */
 int stark_vec_upload(stark_ctx* ctx, const uint64_t* host, size_t n, stark_vec** out);

@@ -202,7 +202,7 @@ class Context:
         return t[0], t[1]
 
     def measure_pipe_mix(self) -> list[float]:
-        t = (C.c_double * 5)()
+        t = (C.c_double * 8)()
         _check(lib().stark_measure_pipe_mix(self.h, t))
         return list(t)
 

@@ -18,9 +18,17 @@ struct FieldParams {
 
 // a*b*2^-32 mod p.  Requires a*b < p*2^32 (true when one operand is < p); result in [0,p).
 // Signed form (t - q*p)/2^32 so that nothing overflows for p > 2^31.
+#ifndef STARK_MONT_WIDE
+#define STARK_MONT_WIDE 0
+#endif
 __device__ __forceinline__ uint32_t mont_mul(uint32_t a, uint32_t b, const FieldParams& f) {
+#if STARK_MONT_WIDE
+    uint64_t t = (uint64_t)a * b;                 // one IMAD.WIDE instead of IMAD + IMAD.HI
+    uint32_t lo = (uint32_t)t, hi = (uint32_t)(t >> 32);
+#else
     uint32_t lo = a * b;
     uint32_t hi = __umulhi(a, b);
+#endif
     uint32_t q = lo * f.pinv;
     uint32_t h = __umulhi(q, f.p);
     uint32_t r = hi - h;

@@ -45,10 +45,28 @@ __global__ void __launch_bounds__(256) pipe_mix_kernel(uint32_t* sink, int iters
         for (int r = 0; r < 4; r++) {
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                uint32_t t;
-                asm volatile("shf.r.wrap.b32 %0, %1, %1, 7;" : "=r"(t) : "r"(x[i]));
-                asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(t) : "r"(t), "r"(y), "r"(z));
-                asm volatile("{ .reg .u32 q; add.u32 q, %1, %2; add.u32 %0, q, %3; }" : "=r"(t) : "r"(t), "r"(y), "r"(z));
+                uint32_t t = x[i];
+                if (MODE < 5) {
+                    asm volatile("shf.r.wrap.b32 %0, %1, %1, 7;" : "=r"(t) : "r"(t));
+                    asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(t) : "r"(t), "r"(y), "r"(z));
+                    asm volatile("{ .reg .u32 q; add.u32 q, %1, %2; add.u32 %0, q, %3; }" : "=r"(t) : "r"(t), "r"(y), "r"(z));
+                }
+                if (MODE == 5) {                                   // FMA pipe alone: 3 IMAD
+#pragma unroll
+                    for (int k = 0; k < 3; k++) asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(t), "r"(mulc), "r"(z));
+                }
+                if (MODE == 6) {                                   // 3 IMAD.HI
+#pragma unroll
+                    for (int k = 0; k < 3; k++) asm volatile("mad.hi.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(t), "r"(y), "r"(z));
+                }
+                if (MODE == 7) {                                   // 3 IMAD.WIDE (the high word feeds the next one)
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        uint32_t lo;
+                        asm volatile("{ .reg .u64 w; mul.wide.u32 w, %2, %3; mov.b64 {%0, %1}, w; }" : "=r"(lo), "=r"(t) : "r"(t), "r"(y));
+                        z ^= lo & 0u;
+                    }
+                }
                 if (MODE == 1 || MODE == 4) asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(t), "r"(mulc), "r"(z));
                 if (MODE == 4) asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(t), "r"(mulc), "r"(y));
                 if (MODE == 2) {
@@ -71,9 +89,9 @@ __global__ void __launch_bounds__(256) pipe_mix_kernel(uint32_t* sink, int iters
 
 using namespace starkb200;
 
-// steps_per_s[m], m = 0..4: 1e12 chain steps per second for mode m (mode 0 = the three ALU instructions alone), so
+// steps_per_s[m], m = 0..7 (5..7 = three IMAD / IMAD.HI / IMAD.WIDE per step with no ALU-pipe work): 1e12 chain steps per second for mode m (mode 0 = the three ALU instructions alone), so
 // the ALU-pipe instruction rate is 3x the figure and the cost of the extra FMA-pipe work is read off the ratio to mode 0.
-extern "C" int stark_measure_pipe_mix(stark_ctx* ctx, double steps_per_s[5]) {
+extern "C" int stark_measure_pipe_mix(stark_ctx* ctx, double steps_per_s[8]) {
     if (!ctx || !steps_per_s) return ST_INVALID;
     try {
         std::lock_guard<std::recursive_mutex> lk(ctx->mu);
@@ -83,7 +101,7 @@ extern "C" int stark_measure_pipe_mix(stark_ctx* ctx, double steps_per_s[5]) {
         STARK_CUDA(cudaEventCreate(&e0)); STARK_CUDA(cudaEventCreate(&e1));
         const int iters = 512, blocks = ctx->sm_count * 16, threads = 256;
         const uint32_t mulc = 1u << 25;
-        for (int mode = 0; mode < 5; mode++) {
+        for (int mode = 0; mode < 8; mode++) {
             double best = 0;
             for (int rep = 0; rep < 4; rep++) {
                 STARK_CUDA(cudaEventRecord(e0, ctx->stream));
@@ -94,7 +112,10 @@ extern "C" int stark_measure_pipe_mix(stark_ctx* ctx, double steps_per_s[5]) {
                     case 1: pipe_mix_kernel<1><<<blocks, threads, 0, ctx->stream>>>(s, iters, seed, mulc); break;
                     case 2: pipe_mix_kernel<2><<<blocks, threads, 0, ctx->stream>>>(s, iters, seed, mulc); break;
                     case 3: pipe_mix_kernel<3><<<blocks, threads, 0, ctx->stream>>>(s, iters, seed, mulc); break;
-                    default: pipe_mix_kernel<4><<<blocks, threads, 0, ctx->stream>>>(s, iters, seed, mulc); break;
+                    case 4: pipe_mix_kernel<4><<<blocks, threads, 0, ctx->stream>>>(s, iters, seed, mulc); break;
+                    case 5: pipe_mix_kernel<5><<<blocks, threads, 0, ctx->stream>>>(s, iters, seed, mulc); break;
+                    case 6: pipe_mix_kernel<6><<<blocks, threads, 0, ctx->stream>>>(s, iters, seed, mulc); break;
+                    default: pipe_mix_kernel<7><<<blocks, threads, 0, ctx->stream>>>(s, iters, seed, mulc); break;
                 }
                 STARK_CUDA(cudaEventRecord(e1, ctx->stream));
                 STARK_CUDA(cudaEventSynchronize(e1));
