@@ -242,6 +242,13 @@ int stark101_verify(const uint8_t* proof_flat, size_t proof_len, uint64_t modulu
  * protocol and transcript order in DESIGN.md "cfg1". */
 int stark101_prove(stark_ctx* ctx, uint64_t a1, unsigned log_trace, unsigned log_blowup, size_t num_queries,
                    stark_channel* ch);
+/* Pieces of the same prover for callers that spread it over several GPUs (stark-prover_b200/multi_gpu.py,
+ * stark101_prove_multi): the T coefficients of the trace polynomial f (the top one is zero) together with a_{T-2};
+ * and the composition polynomial on the points start .. start+count-1 of the coset generator*<h>, where f_block
+ * holds f on that range followed by the next 2*blowup points (count == N: the whole coset, no halo). */
+int stark101_trace_poly(stark_ctx* ctx, uint64_t a1, unsigned log_trace, stark_vec** coeffs, uint64_t* last_value);
+int stark101_composition_range(stark_ctx* ctx, const stark_vec* f_block, size_t start, size_t count, const uint64_t alpha[3],
+                               uint64_t last_value, unsigned log_trace, unsigned log_blowup, stark_vec** cp_block);
 
 #ifdef __cplusplus
 }

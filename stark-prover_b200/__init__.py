@@ -137,6 +137,8 @@ def lib() -> C.CDLL:
     sig("stark_decommit_fri_layers", I, vp, szt, vp)
     sig("stark_decommit_fri", I, vp, szt, szt, vp)
     sig("stark101_prove", I, vp, u64, C.c_uint, C.c_uint, szt, vp)
+    sig("stark101_trace_poly", I, vp, u64, C.c_uint, C.POINTER(vp), C.POINTER(u64))
+    sig("stark101_composition_range", I, vp, vp, szt, szt, C.POINTER(u64), u64, C.c_uint, C.c_uint, C.POINTER(vp))
     sig("stark_merkle_verify", I, vp, szt, szt, u64, vp, szt, C.POINTER(I))
     sig("stark_fri_verify", I, vp, szt, u64, u64, C.c_uint, u64, szt, szt, C.POINTER(I), C.c_char_p)
     sig("stark101_verify", I, vp, szt, u64, u64, u64, C.c_uint, C.c_uint, szt, C.POINTER(I), C.c_char_p)
@@ -608,6 +610,22 @@ def stark101_prove(ctx: Context, channel: Channel, a1: int = 3141592, log_trace:
                    num_queries: int = 3) -> None:
     """Build-defined FibonacciSq prover."""
     _check(lib().stark101_prove(ctx.h, a1, log_trace, log_blowup, num_queries, channel.h))
+
+
+def stark101_trace_poly(ctx: Context, a1: int = 3141592, log_trace: int = 10) -> tuple["Vec", int]:
+    """(coefficients of the trace polynomial f as a device Vec of 2^log_trace entries, a_{T-2})."""
+    out, last = C.c_void_p(), C.c_uint64(0)
+    _check(lib().stark101_trace_poly(ctx.h, a1, log_trace, C.byref(out), C.byref(last)))
+    return Vec(ctx, out), int(last.value)
+
+
+def stark101_composition_range(ctx: Context, f_block: "Vec", start: int, count: int, alpha, last_value: int,
+                               log_trace: int, log_blowup: int) -> "Vec":
+    """CP on the points start .. start+count-1 of the coset; f_block = f on that range + the next 2*blowup points."""
+    al = (C.c_uint64 * 3)(*[int(x) for x in alpha])
+    out = C.c_void_p()
+    _check(lib().stark101_composition_range(ctx.h, f_block.h, start, count, al, last_value, log_trace, log_blowup, C.byref(out)))
+    return Vec(ctx, out)
 
 
 def merkle_validate(root: bytes, n_leaves: int, idx: int, value: int, path: bytes) -> bool:

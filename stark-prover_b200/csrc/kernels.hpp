@@ -117,6 +117,6 @@ struct FibSqParams {
     uint64_t alpha[3];
     uint64_t last_value;         // a[T-2]
 };
-void fibsq_composition(stark_ctx* ctx, const uint32_t* f_eval, const FibSqParams& prm, uint32_t* cp_eval);
+void fibsq_composition(stark_ctx* ctx, const uint32_t* f_eval, const FibSqParams& prm, uint32_t* cp_eval, size_t start, size_t count);
 
 }  // namespace starkb200

@@ -21,6 +21,15 @@ using namespace starkb200;
 
 namespace starkb200 {
 
+// helpers implemented in api.cu
+DevBufPtr api_upload_u64(stark_ctx* ctx, const uint64_t* host, size_t n);
+DevBufPtr api_lde_on_coset(stark_ctx* ctx, const uint32_t* evals, unsigned log_n, uint64_t offset_in, unsigned log_blowup, uint64_t offset_out);
+DevBufPtr api_interpolate_on_coset(stark_ctx* ctx, const uint32_t* evals, unsigned log_n, uint64_t offset);
+std::unique_ptr<stark_tree> api_tree_commit(stark_ctx* ctx, DevBufPtr leaves, size_t n);
+void api_send_root(Channel& ch, const stark_tree* t);
+void api_open_and_send(const stark_tree* t, size_t idx, Channel& ch);
+void api_set_error(const std::string& s);
+
 struct FibSqDev {
     uint32_t offset;          // w (canonical)
     uint32_t one;             // 1
@@ -30,13 +39,15 @@ struct FibSqDev {
     uint32_t alpha_m[3];      // Montgomery form
     uint32_t blow;            // 2^log_blowup
     const uint32_t* zinv_m;   // blow entries: (x^T - 1)^-1 for i mod blow, Montgomery form
+    uint32_t start;           // domain index of the first point handled (a multiple of blow); 0 for the whole coset
+    uint32_t f_mask;          // f is indexed (local + k*blow) & f_mask: N-1 for the whole coset (wraps), ~0 for a range with a halo
 };
 
 // d0[i] = x_i - 1, d1[i] = x_i - g^(T-2),  x_i = w h^i
 __global__ void fibsq_denoms_kernel(FibSqDev q, PowTable tw, uint32_t* d0, uint32_t* d1, size_t n, FieldParams fp) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t x = mont_mul(pow_lookup(tw, (uint32_t)i, fp), q.offset, fp);
+    uint32_t x = mont_mul(pow_lookup(tw, q.start + (uint32_t)i, fp), q.offset, fp);
     d0[i] = fsub(x, q.one, fp);
     d1[i] = fsub(x, q.x_last, fp);
 }
@@ -45,8 +56,8 @@ __global__ void fibsq_combine_kernel(FibSqDev q, PowTable tw, const uint32_t* f,
                                      uint32_t* cp, size_t n, FieldParams fp) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t x = mont_mul(pow_lookup(tw, (uint32_t)i, fp), q.offset, fp);
-    uint32_t fx = f[i], fgx = f[(i + q.blow) & (n - 1)], fg2x = f[(i + 2 * (size_t)q.blow) & (n - 1)];   // g = h^blow
+    uint32_t x = mont_mul(pow_lookup(tw, q.start + (uint32_t)i, fp), q.offset, fp);
+    uint32_t fx = f[i], fgx = f[(i + q.blow) & q.f_mask], fg2x = f[(i + 2 * (size_t)q.blow) & q.f_mask];   // g = h^blow
     uint32_t p0 = mont_mul(to_mont(fsub(fx, q.one, fp), fp), i0[i], fp);
     uint32_t p1 = mont_mul(to_mont(fsub(fx, q.last_value, fp), fp), i1[i], fp);
     uint32_t sq1 = mont_mul(to_mont(fgx, fp), fgx, fp), sq0 = mont_mul(to_mont(fx, fp), fx, fp);
@@ -54,7 +65,7 @@ __global__ void fibsq_combine_kernel(FibSqDev q, PowTable tw, const uint32_t* f,
     uint32_t e = mont_mul(to_mont(fsub(x, q.ex[0], fp), fp), fsub(x, q.ex[1], fp), fp);
     e = mont_mul(to_mont(e, fp), fsub(x, q.ex[2], fp), fp);
     uint32_t p2 = mont_mul(to_mont(num, fp), e, fp);
-    p2 = mont_mul(p2, __ldg(q.zinv_m + (i & (q.blow - 1))), fp);
+    p2 = mont_mul(p2, __ldg(q.zinv_m + ((q.start + i) & (q.blow - 1))), fp);
     uint32_t r = fadd(mont_mul(p0, q.alpha_m[0], fp), mont_mul(p1, q.alpha_m[1], fp), fp);
     cp[i] = fadd(r, mont_mul(p2, q.alpha_m[2], fp), fp);
 }
@@ -89,10 +100,18 @@ uint64_t dot_powers(stark_ctx* ctx, const uint32_t* a, size_t count, unsigned lo
     return s;
 }
 
-void fibsq_composition(stark_ctx* ctx, const uint32_t* f_eval, const FibSqParams& prm, uint32_t* cp_eval) {
+// CP on the points start .. start+count-1 of the coset.  Whole coset: start = 0, count = N, f_eval holds N values.
+// A range (several GPUs, each a contiguous block): f_eval holds count + 2*blow values, the block followed by the first
+// 2*blow values of the next block (f(g x), f(g^2 x) of the last points), and start is a multiple of blow.
+void fibsq_composition(stark_ctx* ctx, const uint32_t* f_eval, const FibSqParams& prm, uint32_t* cp_eval, size_t start, size_t count) {
     const uint64_t p = ctx->modulus;
     const unsigned log_N = prm.log_trace + prm.log_blowup;
-    const size_t T = (size_t)1 << prm.log_trace, N = (size_t)1 << log_N, blow = (size_t)1 << prm.log_blowup;
+    const size_t T = (size_t)1 << prm.log_trace, blow = (size_t)1 << prm.log_blowup;
+    size_t N = (size_t)1 << log_N;
+    if (count == 0) { start = 0; count = N; }
+    STARK_REQUIRE(start % blow == 0 && start + count <= N, "fibsq_composition: bad range");
+    const bool whole = count == N;
+    N = count;
     const uint64_t g = ctx->root_of_unity(prm.log_trace), h = ctx->root_of_unity(log_N), w = prm.offset % p;
     FibSqDev q{};
     q.offset = (uint32_t)w; q.one = (uint32_t)(1 % p);
@@ -101,6 +120,7 @@ void fibsq_composition(stark_ctx* ctx, const uint32_t* f_eval, const FibSqParams
     q.last_value = (uint32_t)(prm.last_value % p);
     for (int k = 0; k < 3; k++) q.alpha_m[k] = ctx->to_mont(prm.alpha[k]);
     q.blow = (uint32_t)blow;
+    q.start = (uint32_t)start; q.f_mask = whole ? (uint32_t)(N - 1) : 0xffffffffu;
     // x^T - 1 takes `blow` distinct values on the coset: w^T (h^T)^i
     std::vector<uint32_t> zinv(blow);
     uint64_t wT = h_pow(w, T, p), hT = h_pow(h, T, p), cur = wT;
@@ -122,71 +142,113 @@ void fibsq_composition(stark_ctx* ctx, const uint32_t* f_eval, const FibSqParams
 
 }  // namespace starkb200
 
-// helpers implemented in api.cu
-namespace starkb200 {
-DevBufPtr api_upload_u64(stark_ctx* ctx, const uint64_t* host, size_t n);
-DevBufPtr api_lde_on_coset(stark_ctx* ctx, const uint32_t* evals, unsigned log_n, uint64_t offset_in, unsigned log_blowup, uint64_t offset_out);
-DevBufPtr api_interpolate_on_coset(stark_ctx* ctx, const uint32_t* evals, unsigned log_n, uint64_t offset);
-std::unique_ptr<stark_tree> api_tree_commit(stark_ctx* ctx, DevBufPtr leaves, size_t n);
-void api_send_root(Channel& ch, const stark_tree* t);
-void api_open_and_send(const stark_tree* t, size_t idx, Channel& ch);
-void api_set_error(const std::string& s);
-}  // namespace starkb200
+
+// src/trace + the interpolation: the T values whose size-T interpolant over <g> is Polynomial::interpolate of the
+// T-1 trace rows (device buffer, canonical u32), and a_{T-2}
+static DevBufPtr fibsq_trace_column(stark_ctx* ctx, uint64_t a1, unsigned log_trace, uint64_t* last_value) {
+    const uint64_t p = ctx->modulus;
+    const size_t T = (size_t)1 << log_trace, rows = T - 1;
+    const uint64_t g = ctx->root_of_unity(log_trace);
+    // the recurrence is sequential, it stays on the host
+    // (8M dependent steps at 2^23 rows: kept in 32-bit Montgomery form so a step is ~15 cycles, not two u128 divisions)
+    std::vector<uint64_t> a(T);
+    {
+        const uint32_t pp = (uint32_t)p, pinv = ctx->fp.pinv;
+        auto mm = [pp, pinv](uint32_t x, uint32_t y) {
+            uint64_t t = (uint64_t)x * y;
+            uint32_t q = (uint32_t)t * pinv, hq = (uint32_t)(((uint64_t)q * pp) >> 32), hi = (uint32_t)(t >> 32);
+            uint32_t r = hi - hq;
+            return hi < hq ? r + pp : r;
+        };
+        uint32_t x0 = ctx->to_mont(1), x1 = ctx->to_mont(a1);
+        a[0] = 1 % p; a[1] = a1 % p;
+        for (size_t i = 2; i < rows; i++) {
+            uint64_t sum = (uint64_t)mm(x1, x1) + mm(x0, x0);
+            uint32_t x2 = (uint32_t)(sum >= p ? sum - p : sum);
+            a[i] = mm(x2, 1u);                                 // out of Montgomery form (off the dependency chain)
+            x0 = x1; x1 = x2;
+        }
+        a[rows] = 0;
+    }
+    // T-th value chosen so that the x^(T-1) coefficient of the size-T interpolant vanishes:
+    // sum_{i<T} a_i g^i = 0  =>  the unique degree <= T-2 interpolant through the T-1 rows (Polynomial::interpolate).
+    DevBufPtr tr = api_upload_u64(ctx, a.data(), T);
+    uint64_t s = dot_powers(ctx, tr->as<uint32_t>(), rows, log_trace);
+    a[rows] = h_mul((p - s) % p, h_inv(h_pow(g, rows, p), p), p);
+    uint32_t last32 = (uint32_t)a[rows];
+    STARK_CUDA(cudaMemcpyAsync(tr->as<uint32_t>() + rows, &last32, 4, cudaMemcpyHostToDevice, ctx->stream));
+    STARK_CUDA(cudaStreamSynchronize(ctx->stream));
+    *last_value = a[rows - 1];
+    return tr;
+}
+
+static void check_fibsq_sizes(stark_ctx* ctx, unsigned log_trace, unsigned log_blowup) {
+    STARK_REQUIRE(log_trace >= 2 && log_trace + log_blowup <= ctx->two_adicity && log_trace + log_blowup <= 30,
+                  "stark101: trace/blowup sizes not supported by this field");
+}
+
+// Building blocks of the prover for callers that spread the work over several GPUs (multi_gpu.py: stark101_prove_multi):
+// the coefficients of the trace polynomial f (T of them, the top one zero) with a_{T-2}, and the composition
+// polynomial on a contiguous range of the coset.
+extern "C" int stark101_trace_poly(stark_ctx* ctx, uint64_t a1, unsigned log_trace, stark_vec** coeffs, uint64_t* last_value) {
+    try {
+        STARK_REQUIRE(ctx && coeffs && last_value, "stark101_trace_poly: null argument");
+        check_fibsq_sizes(ctx, log_trace, 0);
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        STARK_CUDA(cudaSetDevice(ctx->device));
+        DevBufPtr tr = fibsq_trace_column(ctx, a1, log_trace, last_value);
+        DevBufPtr c = api_interpolate_on_coset(ctx, tr->as<uint32_t>(), log_trace, 1);
+        stark_vec* v = new stark_vec(); v->ctx = ctx; v->buf = c; v->n = (size_t)1 << log_trace;
+        *coeffs = v;
+        return ST_OK;
+    } catch (const StarkError& e) { api_set_error(e.what()); return e.code; }
+    catch (const std::exception& e) { api_set_error(e.what()); return ST_INTERNAL; }
+}
+extern "C" int stark101_composition_range(stark_ctx* ctx, const stark_vec* f_block, size_t start, size_t count, const uint64_t alpha[3],
+                                          uint64_t last_value, unsigned log_trace, unsigned log_blowup, stark_vec** cp_block) {
+    try {
+        STARK_REQUIRE(ctx && f_block && alpha && cp_block && f_block->ctx == ctx, "stark101_composition_range: bad argument");
+        check_fibsq_sizes(ctx, log_trace, log_blowup);
+        const size_t N = (size_t)1 << (log_trace + log_blowup), blow = (size_t)1 << log_blowup;
+        STARK_REQUIRE(count >= 1 && start + count <= N, "stark101_composition_range: range outside the domain");
+        STARK_REQUIRE(f_block->n == (count == N ? N : count + 2 * blow), "stark101_composition_range: f_block must hold the range plus 2*blowup halo values");
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        STARK_CUDA(cudaSetDevice(ctx->device));
+        FibSqParams prm{};
+        prm.log_trace = log_trace; prm.log_blowup = log_blowup; prm.offset = ctx->generator; prm.last_value = last_value;
+        for (int k = 0; k < 3; k++) prm.alpha[k] = alpha[k];
+        DevBufPtr out = make_buf(count * 4, ctx->stream);
+        fibsq_composition(ctx, f_block->buf->as<uint32_t>(), prm, out->as<uint32_t>(), start, count);
+        stark_vec* v = new stark_vec(); v->ctx = ctx; v->buf = out; v->n = count;
+        *cp_block = v;
+        return ST_OK;
+    } catch (const StarkError& e) { api_set_error(e.what()); return e.code; }
+    catch (const std::exception& e) { api_set_error(e.what()); return ST_INTERNAL; }
+}
 
 extern "C" int stark101_prove(stark_ctx* ctx, uint64_t a1, unsigned log_trace, unsigned log_blowup, size_t num_queries,
                               stark_channel* chan) {
     try {
         STARK_REQUIRE(ctx && chan, "stark101_prove: null argument");
-        STARK_REQUIRE(log_trace >= 2 && log_trace + log_blowup <= ctx->two_adicity && log_trace + log_blowup <= 30,
-                      "stark101_prove: trace/blowup sizes not supported by this field");
+        check_fibsq_sizes(ctx, log_trace, log_blowup);
         std::lock_guard<std::recursive_mutex> lk(ctx->mu);
         STARK_CUDA(cudaSetDevice(ctx->device));
         Channel& ch = chan->ch;
-        const uint64_t p = ctx->modulus;
         const unsigned log_N = log_trace + log_blowup;
-        const size_t T = (size_t)1 << log_trace, rows = T - 1, N = (size_t)1 << log_N, blow = (size_t)1 << log_blowup;
-        const uint64_t g = ctx->root_of_unity(log_trace), w = ctx->generator;
-        // ---- src/trace: the recurrence is sequential, it stays on the host ----
-        // (8M dependent steps at 2^23 rows: kept in 32-bit Montgomery form so a step is ~15 cycles, not two u128 divisions)
-        std::vector<uint64_t> a(T);
-        {
-            const uint32_t pp = (uint32_t)p, pinv = ctx->fp.pinv;
-            auto mm = [pp, pinv](uint32_t x, uint32_t y) {
-                uint64_t t = (uint64_t)x * y;
-                uint32_t q = (uint32_t)t * pinv, hq = (uint32_t)(((uint64_t)q * pp) >> 32), hi = (uint32_t)(t >> 32);
-                uint32_t r = hi - hq;
-                return hi < hq ? r + pp : r;
-            };
-            uint32_t x0 = ctx->to_mont(1), x1 = ctx->to_mont(a1);
-            a[0] = 1 % p; a[1] = a1 % p;
-            for (size_t i = 2; i < rows; i++) {
-                uint64_t sum = (uint64_t)mm(x1, x1) + mm(x0, x0);
-                uint32_t x2 = (uint32_t)(sum >= p ? sum - p : sum);
-                a[i] = mm(x2, 1u);                                 // out of Montgomery form (off the dependency chain)
-                x0 = x1; x1 = x2;
-            }
-            a[rows] = 0;
-        }
-        // T-th value chosen so that the x^(T-1) coefficient of the size-T interpolant vanishes:
-        // sum_{i<T} a_i g^i = 0  =>  the unique degree <= T-2 interpolant through the T-1 rows (Polynomial::interpolate).
-        DevBufPtr tr = api_upload_u64(ctx, a.data(), T);
-        {
-            uint64_t s = dot_powers(ctx, tr->as<uint32_t>(), rows, log_trace);
-            a[rows] = h_mul((p - s) % p, h_inv(h_pow(g, rows, p), p), p);
-            uint32_t last32 = (uint32_t)a[rows];
-            STARK_CUDA(cudaMemcpyAsync(tr->as<uint32_t>() + rows, &last32, 4, cudaMemcpyHostToDevice, ctx->stream));
-            STARK_CUDA(cudaStreamSynchronize(ctx->stream));
-        }
+        const size_t N = (size_t)1 << log_N, blow = (size_t)1 << log_blowup;
+        const uint64_t w = ctx->generator;
+        uint64_t last_value = 0;
+        DevBufPtr tr = fibsq_trace_column(ctx, a1, log_trace, &last_value);
         // ---- LDE of the trace column and its commitment ----
         DevBufPtr f_eval = api_lde_on_coset(ctx, tr->as<uint32_t>(), log_trace, 1, log_blowup, w);
         auto f_tree = api_tree_commit(ctx, f_eval, N);
         api_send_root(ch, f_tree.get());
         FibSqParams prm{};
-        prm.log_trace = log_trace; prm.log_blowup = log_blowup; prm.offset = w; prm.last_value = a[rows - 1];
+        prm.log_trace = log_trace; prm.log_blowup = log_blowup; prm.offset = w; prm.last_value = last_value;
         for (int k = 0; k < 3; k++) STARK_REQUIRE(ch.receive_random_field_element(&prm.alpha[k]), "channel: receive before send");
         // ---- src/composition: CP on the coset, then its coefficients ----
         DevBuf cp_eval(N * 4, ctx->stream);
-        fibsq_composition(ctx, f_eval->as<uint32_t>(), prm, cp_eval.as<uint32_t>());
+        fibsq_composition(ctx, f_eval->as<uint32_t>(), prm, cp_eval.as<uint32_t>(), 0, N);
         DevBufPtr cp_coef = api_interpolate_on_coset(ctx, cp_eval.as<uint32_t>(), log_N, w);
         stark_vec cpv; cpv.ctx = ctx; cpv.buf = cp_coef; cpv.n = N;
         // ---- src/fri ----

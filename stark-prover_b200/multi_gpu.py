@@ -396,6 +396,103 @@ def decommit_fri_multi(sp, mp: MultiGpuFri, num_queries: int, max_index: int, ch
             feed_layer_records(channel, mp.proof.open([idx], first_layer=1), lens, idx)
 
 
+# ------------------------------------------------------------------------------------------------ cfg5: the whole FibonacciSq prover
+def _open_leaf_range(block, subtree, subtree_roots, which: int, blk: int, rank: int, group=None) -> tuple[bytes, bytes]:
+    """(BE8(value), authentication path) of leaf `which` of a tree committed in leaf ranges: the owner opens its
+    subtree, everybody learns the record, the levels above the subtree roots are appended."""
+    owner, local = which // blk, which % blk
+    depth_local = blk.bit_length() - 1
+    payload = np.zeros(8 + 32 * depth_local, dtype=np.uint8)
+    if rank == owner:
+        val = int(block.download(local, 1)[0])
+        payload[:] = np.frombuffer(val.to_bytes(8, "big") + subtree.get_authentication_path(local), dtype=np.uint8)
+    allp = all_gather_bytes(payload, group)
+    return allp[owner, :8].tobytes(), allp[owner, 8:].tobytes() + top_path(subtree_roots, owner)
+
+
+def stark101_prove_multi(sp, ctx, channel, a1: int, log_trace: int, log_blowup: int, num_queries: int, rank: int, world: int,
+                         group=None) -> None:
+    """The build-defined FibonacciSq prover (csrc/stark101.cu, stark101_prove) with everything the north-star partitions
+    spread over `world` GPUs, and the same transcript byte for byte:
+      * trace LDE: four-step NTT, every rank ends up with a contiguous range of f on the coset;
+      * Merkle commitment of f: leaf-range subtrees, subtree roots gathered;
+      * composition polynomial: point-wise on the rank's own range (it needs f at i, i+blowup, i+2*blowup: a halo of
+        2*blowup values from the next rank);
+      * Merkle commitment of CP (FRI layer 0): leaf-range subtrees again;
+      * the rest of FRI (folds, smaller trees, channel) is not partitioned: rank 0, on the gathered layer 0.
+    `channel` is only used on rank 0."""
+    import torch
+    dist = _dist()
+    multi = world > 1 and dist.is_initialized()
+    log_n = log_trace + log_blowup
+    n, blow = 1 << log_n, 1 << log_blowup
+    blk = n // world
+    assert blk >= 2 * blow and blk % blow == 0, "stark101_prove_multi: ranges must hold at least 2*blowup points"
+    w = ctx.generator
+    # ---- src/trace: sequential recurrence, replicated (every rank needs all coefficients for the four-step LDE)
+    f_coef, last_value = sp.stark101_trace_poly(ctx, a1, log_trace)
+    f_block = four_step_lde(sp, ctx, f_coef, log_n, w, rank, world, group)
+    f_sub = sp.MerkleTree.new(ctx, f_block)
+    f_root, f_subs = commit_leaf_ranges(f_sub.root_bytes, rank, world, group)
+    alpha = [0, 0, 0]
+    if rank == 0:
+        channel.send(f_root.hex().encode())
+        alpha = [channel.receive_random_field_element() for _ in range(3)]
+    alpha = [_bcast_int(a, group) for a in alpha]
+    # ---- src/composition on the local range: block + halo from the next rank (wraps around)
+    ctx.sync()
+    mine = _as_torch(f_block)
+    if multi:
+        heads = torch.empty(world * 2 * blow, dtype=mine.dtype, device=mine.device)
+        dist.all_gather_into_tensor(heads, mine[: 2 * blow].contiguous(), group=group)
+        halo = heads.view(world, 2 * blow)[(rank + 1) % world]
+        ext = torch.cat([mine, halo])
+        torch.cuda.current_stream().synchronize()
+        f_ext = ctx.from_device(ext.data_ptr(), ext.numel())
+        cp_block = sp.stark101_composition_range(ctx, f_ext, rank * blk, blk, alpha, last_value, log_trace, log_blowup)
+        f_ext.free()
+    else:
+        cp_block = sp.stark101_composition_range(ctx, f_block, 0, n, alpha, last_value, log_trace, log_blowup)
+    cp_sub = sp.MerkleTree.new(ctx, cp_block)
+    cp_root, cp_subs = commit_leaf_ranges(cp_sub.root_bytes, rank, world, group)
+    # ---- src/fri on rank 0: layer 0 = the gathered CP evaluations, coefficients by interpolation (degree tracking)
+    ctx.sync()
+    cpm = _as_torch(cp_block)
+    if multi:
+        full = torch.empty(cpm.numel() * world, dtype=cpm.dtype, device=cpm.device)
+        dist.all_gather_into_tensor(full, cpm, group=group)
+    else:
+        full = cpm
+    proof = None
+    if rank == 0:
+        torch.cuda.current_stream().synchronize()
+        layer0 = ctx.from_device(full.data_ptr(), full.numel())
+        cp_coef = ctx.coset_interpolate_dev(layer0, w)
+        proof = sp.fri_begin_external(ctx, cp_coef, log_n, w, layer0, cp_root)
+        channel.send(cp_root.hex().encode())                                 # fri_commit.rs:86
+        while proof.degree >= 1:                                             # :89
+            beta = channel.receive_random_field_element()                    # :91
+            channel.send(proof.fold(beta).hex().encode())                    # :94-100
+        fin = proof.final_poly()
+        channel.send(int(fin[0] if len(fin) else 0).to_bytes(8, "big"))      # :109-114
+    # ---- queries: f(x), f(gx), f(g^2 x) from their owners, CP layer 0 from its owners, the other layers on rank 0
+    for _ in range(num_queries):
+        idx = channel.receive_random_int(0, n - 1 - 2 * blow, True) if rank == 0 else 0
+        idx = _bcast_int(idx, group)
+        recs = [_open_leaf_range(f_block, f_sub, f_subs, idx + k * blow, blk, rank, group) for k in range(3)]
+        recs += [_open_leaf_range(cp_block, cp_sub, cp_subs, which, blk, rank, group) for which in (idx, (idx + n // 2) % n)]
+        if rank == 0:
+            for elem, path in recs:
+                channel.send(elem)
+                channel.send(path)
+            lens = [proof.layer_len(k) for k in range(1, proof.num_layers)]
+            feed_layer_records(channel, proof.open([idx], first_layer=1), lens, idx)
+    if proof is not None:
+        proof.free()
+    for v in (f_sub, cp_sub):
+        v.free()
+
+
 # ------------------------------------------------------------------------------------------------ four-step NTT over peer memory
 class FourStepP2P:
     """The four-step LDE with both exchanges written straight into peer memory (NVLink P2P stores through CUDA-IPC

@@ -72,6 +72,37 @@ def test_fri_commit_multi_degenerate_world1(sp, orc, ctx):
         mp.proof.tree(0).get_authentication_path(0)          # layer 0's levels are not held by the proof object
 
 
+@pytest.mark.parametrize("log_trace,log_blowup,a1,q", [(10, 3, 3141592, 3), (13, 3, 77, 2), (9, 4, 5, 2)])
+def test_stark101_prove_multi_degenerate_world1(sp, orc, ctx, log_trace, log_blowup, a1, q):
+    """The sharded prover with one rank: four-step LDE, leaf-range commitment, range composition, adopted layer 0 --
+    the transcript is stark101_prove's (and the oracle's), and the verifier accepts it."""
+    mg = _mg()
+    ch, ch1, och = sp.Channel(P), sp.Channel(P), orc.Channel(P)
+    mg.stark101_prove_multi(sp, ctx, ch, a1, log_trace, log_blowup, q, 0, 1)
+    sp.stark101_prove(ctx, ch1, a1, log_trace, log_blowup, q)
+    orc.stark101_prove(och, a1, log_trace, log_blowup, sp.G_DEFAULT, q, literal=False)
+    assert ch.state == ch1.state == och.state and ch.proof == ch1.proof == och.proof
+    claimed = int(orc.fibsq_trace(a1, (1 << log_trace) - 1)[(1 << log_trace) - 2])
+    ok, why = sp.stark101_verify(ch.proof_flat(), claimed, log_trace, log_blowup, q)
+    assert ok, why
+
+
+def test_stark101_composition_range_matches_whole(sp, orc, ctx):
+    """CP on ranges with a halo == CP on the whole coset (the kernel the ranks of stark101_prove_multi run)."""
+    log_trace, log_blowup = 9, 3
+    n, blow = 1 << (log_trace + log_blowup), 1 << log_blowup
+    f_coef, last = sp.stark101_trace_poly(ctx, 3141592, log_trace)
+    f = ctx.coset_evaluate(f_coef.download(), log_trace + log_blowup, sp.G_DEFAULT)
+    alpha = [11, 22, 33]
+    whole = sp.stark101_composition_range(ctx, ctx.upload(f), 0, n, alpha, last, log_trace, log_blowup).download()
+    for world in (2, 8):
+        blk = n // world
+        for r in range(world):
+            ext = np.concatenate([f[r * blk:(r + 1) * blk], np.roll(f, -((r + 1) * blk) % n)[: 2 * blow]])
+            part = sp.stark101_composition_range(ctx, ctx.upload(ext), r * blk, blk, alpha, last, log_trace, log_blowup).download()
+            assert np.array_equal(part, whole[r * blk:(r + 1) * blk]), (world, r)
+
+
 @pytest.mark.parametrize("log_n,log_deg,world", [(10, 7, 1), (12, 9, 2), (14, 11, 4), (16, 13, 8), (16, 16, 2), (20, 17, 8), (21, 18, 4)])
 def test_four_step_peer_memory_emulated(sp, orc, ctx, log_n, log_deg, world):
     """Fused twiddle+row-scatter and transpose+scatter kernels with every rank emulated on one GPU."""
