@@ -71,8 +71,17 @@ def _worker(rank, world, port, n_cols, q):
             return orc.Tree(lde).root()
 
         roots = mg.commit_columns(n_cols, commit, rank, world)
-        top, subs = mg.commit_leaf_ranges(lambda: orc.Tree(orc.synthetic_column(9, 256)[rank * 128:(rank + 1) * 128]).root(), rank, world)
-        q.put((rank, calls, [r.hex() for r in roots], top.hex()))
+        big = orc.synthetic_column(9, 256)
+        mine = big[rank * 128:(rank + 1) * 128]
+        sub = orc.Tree(mine)
+        top, subs = mg.commit_leaf_ranges(sub.root, rank, world)
+
+        class Block:                                   # the two calls _open_leaf_range makes on a device Vec / MerkleTree
+            def download(self, off, n): return mine[off:off + n]
+        class Sub:
+            def get_authentication_path(self, i): return sub.path(i)
+        opened = [mg._open_leaf_range(Block(), Sub(), subs, which, 128, rank) for which in (3, 131, 255)]
+        q.put((rank, calls, [r.hex() for r in roots], top.hex(), [(e.hex(), pth.hex()) for e, pth in opened]))
     finally:
         dist.destroy_process_group()
 
@@ -91,7 +100,12 @@ def test_commit_columns_gloo_world2(orc):
     for p in procs:
         p.join(timeout=30)
         assert p.exitcode == 0
-    (r0, calls0, roots0, top0), (r1, calls1, roots1, top1) = res
+    (r0, calls0, roots0, top0, open0), (r1, calls1, roots1, top1, open1) = res
+    big = orc.synthetic_column(9, 256)
+    full = orc.Tree(big)
+    assert open0 == open1                                     # every rank learns the same opening, whoever owns the leaf
+    for (elem, pth), which in zip(open0, (3, 131, 255)):
+        assert elem == int(big[which]).to_bytes(8, "big").hex() and pth == full.path(which).hex()
     assert calls0 == [0, 2, 4] and calls1 == [1, 3]          # no column is computed twice
     assert roots0 == roots1 and top0 == top1                 # every rank ends with the same commitment
     for c in range(n_cols):                                   # and it is the single-process answer
