@@ -121,7 +121,7 @@ extern "C" void stark_ctx_destroy(stark_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (int c = 0; c < stark_ctx::CAT_COUNT; c++) for (auto& pr : ctx->ev_used[c]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto e : ctx->ev_free) cudaEventDestroy(e);
-    ctx->pin_desc.release(); ctx->pin_out.release();
+    ctx->pin_desc.release(); ctx->pin_out.release(); ctx->pin_stage.release();
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     cudaStreamDestroy(ctx->stream);
     delete ctx;

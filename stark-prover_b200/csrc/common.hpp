@@ -176,6 +176,7 @@ struct stark_ctx {
     starkb200::HostResult* h_result = nullptr;  // pinned + mapped
     starkb200::HostResult* d_result = nullptr;  // device alias of h_result
     starkb200::PinnedBuf pin_desc, pin_out;     // opening descriptors in, opening records out
+    starkb200::PinnedBuf pin_stage;             // host-produced columns on their way to HBM (the FibonacciSq trace)
     starkb200::DevBuf deg_scratch;              // DegScratch of coeff_fold_kernel
     starkb200::DevBuf tail_counter;             // "last CTA" ticket of merkle_tail_kernel (zero between launches)
     int sm_count = 148;

@@ -150,8 +150,11 @@ static DevBufPtr fibsq_trace_column(stark_ctx* ctx, uint64_t a1, unsigned log_tr
     const size_t T = (size_t)1 << log_trace, rows = T - 1;
     const uint64_t g = ctx->root_of_unity(log_trace);
     // the recurrence is sequential, it stays on the host
-    // (8M dependent steps at 2^23 rows: kept in 32-bit Montgomery form so a step is ~15 cycles, not two u128 divisions)
-    std::vector<uint64_t> a(T);
+    // (8M dependent steps at 2^23 rows: kept in 32-bit Montgomery form so a step is one Montgomery square on the
+    // dependency chain (~5 ns), not two u128 divisions; a_n^2 is carried over to the next step).  The values are written
+    // as canonical u32 straight into a pinned staging buffer the context keeps, and copied to HBM from there.
+    ctx->pin_stage.ensure(T * 4);
+    uint32_t* a = static_cast<uint32_t*>(ctx->pin_stage.h);
     {
         const uint32_t pp = (uint32_t)p, pinv = ctx->fp.pinv;
         auto mm = [pp, pinv](uint32_t x, uint32_t y) {
@@ -161,22 +164,24 @@ static DevBufPtr fibsq_trace_column(stark_ctx* ctx, uint64_t a1, unsigned log_tr
             return hi < hq ? r + pp : r;
         };
         uint32_t x0 = ctx->to_mont(1), x1 = ctx->to_mont(a1);
-        a[0] = 1 % p; a[1] = a1 % p;
+        a[0] = (uint32_t)(1 % p); a[1] = (uint32_t)(a1 % p);
+        uint32_t sq0 = mm(x0, x0);                                 // a_n^2 (Montgomery form)
         for (size_t i = 2; i < rows; i++) {
-            uint64_t sum = (uint64_t)mm(x1, x1) + mm(x0, x0);
+            uint32_t sq1 = mm(x1, x1);
+            uint64_t sum = (uint64_t)sq1 + sq0;
             uint32_t x2 = (uint32_t)(sum >= p ? sum - p : sum);
-            a[i] = mm(x2, 1u);                                 // out of Montgomery form (off the dependency chain)
-            x0 = x1; x1 = x2;
+            a[i] = mm(x2, 1u);                                     // out of Montgomery form (off the dependency chain)
+            x1 = x2; sq0 = sq1;
         }
         a[rows] = 0;
     }
     // T-th value chosen so that the x^(T-1) coefficient of the size-T interpolant vanishes:
     // sum_{i<T} a_i g^i = 0  =>  the unique degree <= T-2 interpolant through the T-1 rows (Polynomial::interpolate).
-    DevBufPtr tr = api_upload_u64(ctx, a.data(), T);
+    DevBufPtr tr = make_buf(T * 4, ctx->stream);
+    STARK_CUDA(cudaMemcpyAsync(tr->p, a, T * 4, cudaMemcpyHostToDevice, ctx->stream));
     uint64_t s = dot_powers(ctx, tr->as<uint32_t>(), rows, log_trace);
-    a[rows] = h_mul((p - s) % p, h_inv(h_pow(g, rows, p), p), p);
-    uint32_t last32 = (uint32_t)a[rows];
-    STARK_CUDA(cudaMemcpyAsync(tr->as<uint32_t>() + rows, &last32, 4, cudaMemcpyHostToDevice, ctx->stream));
+    a[rows] = (uint32_t)h_mul((p - s) % p, h_inv(h_pow(g, rows, p), p), p);
+    STARK_CUDA(cudaMemcpyAsync(tr->as<uint32_t>() + rows, &a[rows], 4, cudaMemcpyHostToDevice, ctx->stream));
     STARK_CUDA(cudaStreamSynchronize(ctx->stream));
     *last_value = a[rows - 1];
     return tr;

@@ -411,7 +411,7 @@ def _open_leaf_range(block, subtree, subtree_roots, which: int, blk: int, rank: 
 
 
 def stark101_prove_multi(sp, ctx, channel, a1: int, log_trace: int, log_blowup: int, num_queries: int, rank: int, world: int,
-                         group=None) -> None:
+                         group=None, timings: Optional[dict] = None) -> None:
     """The build-defined FibonacciSq prover (csrc/stark101.cu, stark101_prove) with everything the north-star partitions
     spread over `world` GPUs, and the same transcript byte for byte:
       * trace LDE: four-step NTT, every rank ends up with a contiguous range of f on the coset;
@@ -420,10 +420,19 @@ def stark101_prove_multi(sp, ctx, channel, a1: int, log_trace: int, log_blowup: 
         2*blowup values from the next rank);
       * Merkle commitment of CP (FRI layer 0): leaf-range subtrees again;
       * the rest of FRI (folds, smaller trees, channel) is not partitioned: rank 0, on the gathered layer 0.
-    `channel` is only used on rank 0."""
+    `channel` is only used on rank 0.  `timings` (optional dict) receives this rank's wall-clock seconds per phase."""
+    import time
     import torch
     dist = _dist()
     multi = world > 1 and dist.is_initialized()
+    t_last = [time.perf_counter()]
+
+    def lap(name):
+        if timings is not None:
+            ctx.sync()
+            now = time.perf_counter()
+            timings[name] = timings.get(name, 0.0) + now - t_last[0]
+            t_last[0] = now
     log_n = log_trace + log_blowup
     n, blow = 1 << log_n, 1 << log_blowup
     blk = n // world
@@ -431,9 +440,12 @@ def stark101_prove_multi(sp, ctx, channel, a1: int, log_trace: int, log_blowup: 
     w = ctx.generator
     # ---- src/trace: sequential recurrence, replicated (every rank needs all coefficients for the four-step LDE)
     f_coef, last_value = sp.stark101_trace_poly(ctx, a1, log_trace)
+    lap("trace_and_interpolate")
     f_block = four_step_lde(sp, ctx, f_coef, log_n, w, rank, world, group)
+    lap("four_step_lde")
     f_sub = sp.MerkleTree.new(ctx, f_block)
     f_root, f_subs = commit_leaf_ranges(f_sub.root_bytes, rank, world, group)
+    lap("commit_f")
     alpha = [0, 0, 0]
     if rank == 0:
         channel.send(f_root.hex().encode())
@@ -453,8 +465,10 @@ def stark101_prove_multi(sp, ctx, channel, a1: int, log_trace: int, log_blowup: 
         f_ext.free()
     else:
         cp_block = sp.stark101_composition_range(ctx, f_block, 0, n, alpha, last_value, log_trace, log_blowup)
+    lap("composition")
     cp_sub = sp.MerkleTree.new(ctx, cp_block)
     cp_root, cp_subs = commit_leaf_ranges(cp_sub.root_bytes, rank, world, group)
+    lap("commit_cp")
     # ---- src/fri on rank 0: layer 0 = the gathered CP evaluations, coefficients by interpolation (degree tracking)
     ctx.sync()
     cpm = _as_torch(cp_block)
@@ -464,10 +478,12 @@ def stark101_prove_multi(sp, ctx, channel, a1: int, log_trace: int, log_blowup: 
     else:
         full = cpm
     proof = None
+    lap("gather_layer0")
     if rank == 0:
         torch.cuda.current_stream().synchronize()
         layer0 = ctx.from_device(full.data_ptr(), full.numel())
         cp_coef = ctx.coset_interpolate_dev(layer0, w)
+        lap("interpolate_cp")
         proof = sp.fri_begin_external(ctx, cp_coef, log_n, w, layer0, cp_root)
         channel.send(cp_root.hex().encode())                                 # fri_commit.rs:86
         while proof.degree >= 1:                                             # :89
@@ -475,6 +491,7 @@ def stark101_prove_multi(sp, ctx, channel, a1: int, log_trace: int, log_blowup: 
             channel.send(proof.fold(beta).hex().encode())                    # :94-100
         fin = proof.final_poly()
         channel.send(int(fin[0] if len(fin) else 0).to_bytes(8, "big"))      # :109-114
+        lap("fri_layers_rank0")
     # ---- queries: f(x), f(gx), f(g^2 x) from their owners, CP layer 0 from its owners, the other layers on rank 0
     for _ in range(num_queries):
         idx = channel.receive_random_int(0, n - 1 - 2 * blow, True) if rank == 0 else 0
@@ -487,6 +504,7 @@ def stark101_prove_multi(sp, ctx, channel, a1: int, log_trace: int, log_blowup: 
                 channel.send(path)
             lens = [proof.layer_len(k) for k in range(1, proof.num_layers)]
             feed_layer_records(channel, proof.open([idx], first_layer=1), lens, idx)
+    lap("queries")
     if proof is not None:
         proof.free()
     for v in (f_sub, cp_sub):
