@@ -162,6 +162,23 @@ def test_batch_inverse(sp, orc, ctx, n):
         assert int(got[i]) == orc.fe_inverse(int(a[i]), P)
 
 
+@pytest.mark.parametrize("n", [4095, 4096, 4097, 8191, 12289])
+def test_batch_inverse_cta_boundaries_and_zero_patterns(sp, orc, ctx, n):
+    """The kernel inverts one product per CTA of 4096 elements (16 strided elements per thread, 256 threads): sizes
+    around that boundary, threads / warps / whole CTAs whose elements are all zero, and the values 1 and p-1."""
+    a = orc.synthetic_column(n, n)
+    a[5::256] = 0                      # every element of thread 5 of every CTA (element i belongs to thread i mod 256)
+    a[32:64] = 0                       # a whole warp's first element
+    a[1024:1024 + 7] = [1, P - 1, 2, P - 2, 0, 1, P - 1]
+    got = ctx.batch_inverse(a)
+    assert np.array_equal(got, orc.batch_inverse(a, P))
+    z = np.zeros(n, dtype=np.uint64)
+    assert not ctx.batch_inverse(z).any()                            # all zeros: every product is the empty product
+    if n > 4096:
+        a[:4096] = 0                                                 # first CTA entirely zero, the rest not
+        assert np.array_equal(ctx.batch_inverse(a), orc.batch_inverse(a, P))
+
+
 def test_quotient_pointwise(sp, orc, ctx):
     n = 5000
     num, den = orc.synthetic_column(1, n), orc.synthetic_column(2, n)
