@@ -21,7 +21,8 @@ class HostSha256 {
         uint32_t st[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
         size_t off = 0;
         const bool ni = have_sha_ni();
-        for (; off + 64 <= len; off += 64) ni ? block_ni(st, msg + off) : block(st, msg + off);
+        if (ni) { size_t nb = len / 64; blocks_ni(st, msg, nb); off = nb * 64; }
+        else for (; off + 64 <= len; off += 64) block(st, msg + off);
         uint8_t tail[128];
         size_t r = len - off;
         memset(tail, 0, sizeof tail);
@@ -45,7 +46,7 @@ class HostSha256 {
         uint64_t total = 0;
         bool ni = have_sha_ni();
         void blocks(const uint8_t* p, size_t nblk) {
-            if (ni) for (size_t i = 0; i < nblk; i++) block_ni(st, p + 64 * i);
+            if (ni) blocks_ni(st, p, nblk);
             else for (size_t i = 0; i < nblk; i++) block(st, p + 64 * i);
         }
         void update(const uint8_t* p, size_t n) {
@@ -133,8 +134,10 @@ class HostSha256 {
 #endif
     }
 #if defined(__x86_64__)
-    __attribute__((target("sha,sse4.1,ssse3"))) static void block_ni(uint32_t st[8], const uint8_t* p) {
-        static const uint32_t K[64] = {
+    // nblk consecutive blocks; the state stays in the (ABEF, CDGH) register layout of sha256rnds2 from the first block
+    // to the last, so the layout shuffles and the store/reload of st[] are off the per-block dependency chain
+    __attribute__((target("sha,sse4.1,ssse3"))) static void blocks_ni(uint32_t st[8], const uint8_t* p, size_t nblk) {
+        alignas(16) static const uint32_t K[64] = {
             0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
             0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
             0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
@@ -150,23 +153,25 @@ class HostSha256 {
         S1 = _mm_shuffle_epi32(S1, 0x1B);
         __m128i S0 = _mm_alignr_epi8(TMP, S1, 8);
         S1 = _mm_blend_epi16(S1, TMP, 0xF0);
-        const __m128i S0_SAVE = S0, S1_SAVE = S1;
-        __m128i M[4];
-        for (int i = 0; i < 4; i++) M[i] = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i*)(p + 16 * i)), MASK);
+        for (size_t blk = 0; blk < nblk; blk++, p += 64) {
+            const __m128i S0_SAVE = S0, S1_SAVE = S1;
+            __m128i M[4];
+            for (int i = 0; i < 4; i++) M[i] = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i*)(p + 16 * i)), MASK);
 #pragma GCC unroll 16
-        for (int r = 0; r < 16; r++) {
-            __m128i MSG = _mm_add_epi32(M[r & 3], _mm_loadu_si128((const __m128i*)&K[4 * r]));
-            S1 = _mm_sha256rnds2_epu32(S1, S0, MSG);
-            if (r >= 3 && r < 15) {
-                __m128i T = _mm_alignr_epi8(M[r & 3], M[(r + 3) & 3], 4);
-                M[(r + 1) & 3] = _mm_sha256msg2_epu32(_mm_add_epi32(M[(r + 1) & 3], T), M[r & 3]);
+            for (int r = 0; r < 16; r++) {
+                __m128i MSG = _mm_add_epi32(M[r & 3], _mm_load_si128((const __m128i*)&K[4 * r]));
+                S1 = _mm_sha256rnds2_epu32(S1, S0, MSG);
+                if (r >= 3 && r < 15) {
+                    __m128i T = _mm_alignr_epi8(M[r & 3], M[(r + 3) & 3], 4);
+                    M[(r + 1) & 3] = _mm_sha256msg2_epu32(_mm_add_epi32(M[(r + 1) & 3], T), M[r & 3]);
+                }
+                MSG = _mm_shuffle_epi32(MSG, 0x0E);
+                S0 = _mm_sha256rnds2_epu32(S0, S1, MSG);
+                if (r >= 1 && r < 13) M[(r + 3) & 3] = _mm_sha256msg1_epu32(M[(r + 3) & 3], M[r & 3]);
             }
-            MSG = _mm_shuffle_epi32(MSG, 0x0E);
-            S0 = _mm_sha256rnds2_epu32(S0, S1, MSG);
-            if (r >= 1 && r < 13) M[(r + 3) & 3] = _mm_sha256msg1_epu32(M[(r + 3) & 3], M[r & 3]);
+            S0 = _mm_add_epi32(S0, S0_SAVE);
+            S1 = _mm_add_epi32(S1, S1_SAVE);
         }
-        S0 = _mm_add_epi32(S0, S0_SAVE);
-        S1 = _mm_add_epi32(S1, S1_SAVE);
         TMP = _mm_shuffle_epi32(S0, 0x1B);
         S1 = _mm_shuffle_epi32(S1, 0xB1);
         S0 = _mm_blend_epi16(TMP, S1, 0xF0);
@@ -174,8 +179,10 @@ class HostSha256 {
         _mm_storeu_si128((__m128i*)&st[0], S0);
         _mm_storeu_si128((__m128i*)&st[4], S1);
     }
+    static void block_ni(uint32_t st[8], const uint8_t* p) { blocks_ni(st, p, 1); }
 #else
     static void block_ni(uint32_t st[8], const uint8_t* p) { block(st, p); }
+    static void blocks_ni(uint32_t st[8], const uint8_t* p, size_t nblk) { for (size_t i = 0; i < nblk; i++) block(st, p + 64 * i); }
 #endif
     static uint32_t ror(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
     static void block(uint32_t st[8], const uint8_t* p) {
