@@ -900,7 +900,10 @@ static const uint8_t* open_one_index(const stark_fri* f, size_t index, size_t* t
         STARK_REQUIRE(!t->external, "fri open: layer 0 was committed in leaf ranges on several GPUs; open it on the owners");
         a.layers[k] = FriLayerDesc{t->leaves->as<uint32_t>(), t->nodes.as<uint32_t>(), t->shape.n};
         size_t len = t->shape.n, idx = index % len, sib = (idx + len / 2) % len;
-        total += 16 + merkle_path_len(len, idx) + merkle_path_len(len, sib);
+        a.rec_off[2 * k] = (uint32_t)total;
+        total += 8 + merkle_path_len(len, idx);
+        a.rec_off[2 * k + 1] = (uint32_t)total;
+        total += 8 + merkle_path_len(len, sib);
     }
     a.n_layers = (unsigned)f->trees.size(); a.first = 0; a.index = index;
     ctx->pin_out.ensure(total);

@@ -49,6 +49,7 @@ struct FriOpenArgs {
     unsigned n_layers, first;
     unsigned long long index;
     uint8_t* out;            // records back to back: BE8(value) || path, layer by layer, idx then sibling
+    uint32_t rec_off[2 * FRI_MAX_LAYERS];   // byte offset of record r = 2*(layer - first) + (0: idx, 1: sibling), from the host
 };
 void fri_open_one(stark_ctx* ctx, const FriOpenArgs& a);
 // host-side: bytes of the path of leaf idx in a tree of n leaves (32 per level that has a sibling)

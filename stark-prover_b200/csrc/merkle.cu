@@ -393,28 +393,13 @@ __global__ void merkle_open_kernel(const OpenDesc* desc, size_t n_desc, uint8_t*
 }
 
 // ---- one query index across the layers of a FRI proof: everything the kernel needs travels in its arguments
-// (no descriptor upload), the record offsets are computed on the device.  Warp w opens record w:
+// (no descriptor upload), including the byte offset of every record.  Warp w opens record w:
 // layer first + w/2, position idx (even w) or its sibling (odd w).
-__device__ __forceinline__ unsigned path_bytes(unsigned long long n, unsigned long long idx) {
-    unsigned bytes = 0;
-    for (unsigned long long m = n, j = idx; m > 1; m = (m + 1) >> 1, j >>= 1)
-        if ((j ^ 1ull) < m) bytes += 32;
-    return bytes;
-}
 __global__ void fri_open_one_kernel(FriOpenArgs a) {
     const unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const unsigned n_rec = 2 * (a.n_layers - a.first);
     if (w >= n_rec) return;
-    // byte offset of record w = sum of the sizes of records 0..w-1 (lanes take records lane, lane+32, ...)
-    unsigned before = 0;
-    for (unsigned r = lane; r < w; r += 32) {
-        const FriLayerDesc& L = a.layers[a.first + r / 2];
-        unsigned long long i = a.index % L.n;
-        if (r & 1) i = (i + L.n / 2) % L.n;
-        before += 8 + path_bytes(L.n, i);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    const unsigned before = a.rec_off[w];          // computed by the host together with the total (api.cu: open_one_index)
     const FriLayerDesc& L = a.layers[a.first + w / 2];
     unsigned long long idx = a.index % L.n;
     if (w & 1) idx = (idx + L.n / 2) % L.n;
