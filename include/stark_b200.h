@@ -169,6 +169,7 @@ size_t stark_channel_proof_size(const stark_channel* ch);                       
 size_t stark_channel_compressed_proof_size(const stark_channel* ch);                            /* :93-95 */
 const char* stark_channel_state(const stark_channel* ch);
 size_t stark_channel_proof_len(const stark_channel* ch);
+/* message i: returns its length, *data points into the channel's log and stays valid until the next send/receive */
 size_t stark_channel_proof_msg(const stark_channel* ch, size_t i, const uint8_t** data);
 size_t stark_channel_compressed_len(const stark_channel* ch);
 size_t stark_channel_compressed_msg(const stark_channel* ch, size_t i, const uint8_t** data);

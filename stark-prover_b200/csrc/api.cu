@@ -609,22 +609,22 @@ extern "C" const char* stark_channel_state(const stark_channel* ch) { return ch 
 extern "C" size_t stark_channel_proof_len(const stark_channel* ch) { return ch ? ch->ch.proof.size() : 0; }
 extern "C" size_t stark_channel_proof_msg(const stark_channel* ch, size_t i, const uint8_t** data) {
     if (!ch || i >= ch->ch.proof.size()) return 0;
-    if (data) *data = ch->ch.proof[i].data();
-    return ch->ch.proof[i].size();
+    if (data) *data = ch->ch.proof.data(i);              // valid until the next message is appended
+    return ch->ch.proof.len(i);
 }
 extern "C" size_t stark_channel_compressed_len(const stark_channel* ch) { return ch ? ch->ch.compressed_idx.size() : 0; }
 extern "C" size_t stark_channel_compressed_msg(const stark_channel* ch, size_t i, const uint8_t** data) {
     if (!ch || i >= ch->ch.compressed_idx.size()) return 0;
-    const auto& m = ch->ch.compressed_msg(i);
-    if (data) *data = m.data();
-    return m.size();
+    const size_t k = ch->ch.compressed_idx[i];
+    if (data) *data = ch->ch.proof.data(k);
+    return ch->ch.proof.len(k);
 }
 extern "C" size_t stark_channel_proof_flat(const stark_channel* ch, uint8_t* out) {
     if (!ch) return 0;
     size_t w = 0;
-    for (auto& m : ch->ch.proof) {
-        uint32_t n = (uint32_t)m.size();
-        if (out) { out[w] = n & 255; out[w + 1] = (n >> 8) & 255; out[w + 2] = (n >> 16) & 255; out[w + 3] = n >> 24; if (n) memcpy(out + w + 4, m.data(), n); }
+    for (size_t i = 0; i < ch->ch.proof.size(); i++) {
+        uint32_t n = (uint32_t)ch->ch.proof.len(i);
+        if (out) { out[w] = n & 255; out[w + 1] = (n >> 8) & 255; out[w + 2] = (n >> 16) & 255; out[w + 3] = n >> 24; if (n) memcpy(out + w + 4, ch->ch.proof.data(i), n); }
         w += 4 + n;
     }
     return w;

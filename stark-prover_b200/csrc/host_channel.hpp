@@ -217,9 +217,24 @@ inline void be8(uint64_t v, uint8_t out[8]) {            // FieldElement::to_byt
     for (int i = 0; i < 8; i++) out[i] = (uint8_t)(v >> (56 - 8 * i));
 }
 
+// Vec<Vec<u8>> as one byte arena plus spans: a query appends ~90 messages, and a heap block per message costs more
+// than hashing the short ones.
+struct MessageLog {
+    std::vector<uint8_t> bytes;
+    std::vector<std::pair<size_t, size_t>> spans;         // (offset, length)
+    void push(const uint8_t* p, size_t n) {
+        spans.emplace_back(bytes.size(), n);
+        bytes.insert(bytes.end(), p, p + n);
+    }
+    size_t size() const { return spans.size(); }
+    const uint8_t* data(size_t i) const { return bytes.data() + spans[i].first; }
+    size_t len(size_t i) const { return spans[i].second; }
+    size_t total() const { return bytes.size(); }
+};
+
 // Channel<MODULUS> — channel.rs:14-95, field for field.
 struct Channel {
-    std::vector<std::vector<uint8_t>> proof;              // :16
+    MessageLog proof;                                      // :16
     std::vector<size_t> compressed_idx;                    // :17 compressed_proof: the same bytes as proof[i], stored once
     std::string state;                                     // :19, "" initially (:24-30)
     uint64_t modulus;
@@ -240,7 +255,7 @@ struct Channel {
         h.finish(dg);
         state.resize(64);
         HostSha256::hex_into(dg, 32, &state[0]);
-        proof.emplace_back(msg, msg + len);
+        proof.push(msg, len);
         compressed_idx.push_back(proof.size() - 1);      // compressed_proof.push(message.to_vec()), kept as an index
     }
     // :58-84.  Returns false where the reference would panic ("Channel state is not valid hex" on "").
@@ -256,7 +271,7 @@ struct Channel {
         }
         uint64_t num = (uint64_t)((acc + (unsigned __int128)(min % range)) % range);
         state = HostSha256::hex_digest(state);            // :75-76
-        if (show_in_proof) { uint8_t b[8]; be8(num, b); proof.emplace_back(b, b + 8); }   // :78-80
+        if (show_in_proof) { uint8_t b[8]; be8(num, b); proof.push(b, 8); }   // :78-80
         *out = num;                                        // :83
         return true;
     }
@@ -264,13 +279,12 @@ struct Channel {
         uint64_t num;
         if (!receive_random_int(0, modulus - 1, false, &num)) return false;
         uint8_t b[8]; be8(num, b);
-        proof.emplace_back(b, b + 8);
+        proof.push(b, 8);
         *out = num % modulus;
         return true;
     }
-    size_t proof_size() const { size_t s = 0; for (auto& m : proof) s += m.size(); return s; }                       // :88-90
-    size_t compressed_proof_size() const { size_t s = 0; for (size_t i : compressed_idx) s += proof[i].size(); return s; } // :93-95
-    const std::vector<uint8_t>& compressed_msg(size_t k) const { return proof[compressed_idx[k]]; }
+    size_t proof_size() const { return proof.total(); }                                                               // :88-90
+    size_t compressed_proof_size() const { size_t s = 0; for (size_t i : compressed_idx) s += proof.len(i); return s; } // :93-95
 };
 
 }  // namespace starkb200
