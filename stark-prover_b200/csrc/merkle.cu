@@ -174,19 +174,24 @@ merkle_subtree_kernel(LeafSource src, const uint32_t* in_digests, size_t n, int 
 }
 
 // ---- latency-bound part of every tree: one launch, one node per thread per level ------------------------
-// Below ~2^15 nodes a level no longer fills the machine and what matters is the length of the dependency
-// chain: 2 compressions per level.  Giving each thread 8 items (merkle_subtree_kernel) makes that chain 14
-// compressions per 3 levels.  This kernel instead walks the remaining levels with one parent per thread.
+// Below ~2^17 nodes a level no longer keeps the machine busy for long and what matters is the length of the
+// dependency chain: 2 compressions per level.  Giving each thread 8 items (merkle_subtree_kernel) makes that chain
+// 14 compressions per 3 levels.  This kernel instead walks the remaining levels with one parent per thread.
 // A CTA owns 256 consecutive items and reduces them 8 levels to one node, handing digests from level to
 // level through shared memory (word-major rows: a parent reads its two children as one conflict-free 64-bit
 // load per word); every node is also written to its place in the stored tree.  The CTA that finishes last
-// (an atomic ticket, no CTA ever waits for another) picks the <= 128 chunk roots out of L2 and walks the
-// remaining levels the same way.  128-thread CTAs: every warp gets a scheduler (SM sub-partition) to itself,
-// so the ALU pipe (one warp instruction per 2 cycles) is never shared -- two warps per scheduler double the
-// level time.
+// (an atomic ticket, no CTA ever waits for another) picks the chunk roots out of L2 (up to 512: two levels straight
+// from L2, then through shared memory again) and walks the remaining levels the same way.  128-thread CTAs: with up
+// to 148 of them every warp gets a scheduler (SM sub-partition) to itself, so the ALU pipe (one warp instruction per
+// 2 cycles) is not shared -- two warps per scheduler double the level time.
 constexpr int TAIL_THREADS = 128;
-constexpr int TAIL_MAX_CTAS = 128;
-constexpr int TAIL_MAX = 2 * TAIL_THREADS * TAIL_MAX_CTAS;      // 32768 items -> 16384 parents, one per thread
+// Where this kernel takes over from the 3-levels-per-launch kernel, in CTAs of 256 items.  Measured on the headline
+// step (tools/variants_tail.sh): 128 / 512 / 1024 / 2048 / 4096 CTAs -> commit phase 7.24 / 7.10 / 7.18 / 7.33 / 7.53 ms.
+#ifndef STARK_TAIL_MAX_CTAS
+#define STARK_TAIL_MAX_CTAS 512
+#endif
+constexpr int TAIL_MAX_CTAS = STARK_TAIL_MAX_CTAS;
+constexpr int TAIL_MAX = 2 * TAIL_THREADS * TAIL_MAX_CTAS;      // 2^17 items
 
 __device__ __forceinline__ Digest load_digest_cg(const uint32_t* p) {
     const uint4* q = reinterpret_cast<const uint4*>(p);
