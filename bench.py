@@ -66,7 +66,8 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "10", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", os.environ.get("BENCH_SMI_MS", "10"), "-i", str(self.device)],
+                                         stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -265,6 +266,8 @@ def run_b200(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
     roots_out = torch.zeros(world, 32, dtype=torch.uint8, device=f"cuda:{local}") if world > 1 else None
 
+    per_rank_ms = []
+
     def step(src):
         ch = sp.Channel(P)
         pr = sp.fri_commit(ctx, src, domain, ch)
@@ -302,6 +305,9 @@ def run_b200(args):
         ms = total / max(steps, 1)
         if world > 1:
             t = torch.tensor([ms], device=f"cuda:{local}")
+            every = torch.zeros(world, device=f"cuda:{local}")
+            dist.all_gather_into_tensor(every, t)
+            per_rank_ms[:] = [round(float(x), 3) for x in every.tolist()]
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms, pr, ch
@@ -314,12 +320,15 @@ def run_b200(args):
         ctx.close()
         return
     # ---- warm-up, then the device-resident timed region
+    # one sampler per job (rank 0's GPU): a polling nvidia-smi per rank perturbs the host-bound opening phase
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     timed(dev_coeffs, max(args.warmup, 3))
     l0 = ctx.launch_count
     sampler.mark_start()
     ms_dev, pr, ch = timed(dev_coeffs, args.steps)
+    per_rank_dev = list(per_rank_ms)
     sampler.mark_stop()
     launches = (ctx.launch_count - l0) // args.steps
     clocks = sampler.stop()
@@ -357,6 +366,7 @@ def run_b200(args):
             "e2e": {"value": world * n / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": 8 << log_deg, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "transcript_state": final_state,
+            "ms_per_rank": per_rank_dev if world > 1 else None,
             "host_breakdown_ms": host_breakdown}
 
     if rank == 0:
