@@ -35,8 +35,8 @@ struct NttPass {
     unsigned small_log;
 };
 
-// Lazy (DIT only): values are "weak" -- any u32 congruent to the element (2^32 < 2p, so canonical or
-// canonical + p).  A Montgomery product accepts a weak operand and returns a canonical one, so in
+// Lazy (DIT only, and only for p > 2^31 -- the launcher checks): values are "weak" -- any u32 congruent to the
+// element (2^32 < 2p, so canonical or canonical + p).  A Montgomery product accepts a weak operand and returns a canonical one, so in
 // a + w*b / a - w*b only `a` is weak; the sum wraps past 2^32 at most once and the difference goes negative
 // at most once, which makes the add 3 instructions instead of 6.  The last pass canonicalises on store.
 __device__ __forceinline__ uint32_t ladd(uint32_t a_weak, uint32_t b, const FieldParams& f) {
@@ -362,7 +362,7 @@ struct Lde8Pass {
     unsigned small_log;
 };
 
-template <int R_LOG, bool FIRST>
+template <int R_LOG, bool FIRST, bool LAZY>
 __global__ void lde8_pass_kernel(Lde8Pass ps, FieldParams fp) {
     extern __shared__ uint32_t smem[];
     constexpr int R = 1 << R_LOG;
@@ -413,7 +413,7 @@ __global__ void lde8_pass_kernel(Lde8Pass ps, FieldParams fp) {
     }
     __syncthreads();
 
-    run_rounds<R_LOG, false, true>(tile, tws, fp, NTT_C);
+    run_rounds<R_LOG, false, LAZY>(tile, tws, fp, NTT_C);
 
     // ---- store ----
     for (int i = threadIdx.x; i < 4 * R; i += blockDim.x) {
@@ -424,24 +424,30 @@ __global__ void lde8_pass_kernel(Lde8Pass ps, FieldParams fp) {
         const uint32_t* o = tile + t * NTT_TS + g * 8;
         uint32_t v[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = ps.last ? canonical(o[k], fp) : o[k];
+        for (int k = 0; k < 8; k++) v[k] = (LAZY && ps.last) ? canonical(o[k], fp) : o[k];
         uint4* p = reinterpret_cast<uint4*>(ps.dst + row * 8);
         p[0] = make_uint4(v[0], v[1], v[2], v[3]);
         p[1] = make_uint4(v[4], v[5], v[6], v[7]);
     }
 }
 
-template <int R_LOG, bool FIRST>
-static void launch_lde8(stark_ctx* ctx, const Lde8Pass& ps, size_t tiles) {
+template <int R_LOG, bool FIRST, bool LAZY>
+static void launch_lde8_impl(stark_ctx* ctx, const Lde8Pass& ps, size_t tiles) {
     constexpr int R = 1 << R_LOG;
     int threads = (R * NTT_C) >> 4;
     if (threads < 64) threads = 64;
     if (threads > 1024) threads = 1024;
     size_t smem = (size_t)(R * NTT_TS + (R >> 1) + 1) * sizeof(uint32_t);
-    auto kern = lde8_pass_kernel<R_LOG, FIRST>;
+    auto kern = lde8_pass_kernel<R_LOG, FIRST, LAZY>;
     if (smem > 48 * 1024) STARK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)tiles, threads, smem, ctx->stream>>>(ps, ctx->fp);
     ctx->launches++;
+}
+// weak (lazily reduced) butterfly values need 2^32 < 2p; smaller primes (BabyBear, 998244353, ...) take the strict form
+template <int R_LOG, bool FIRST>
+static void launch_lde8(stark_ctx* ctx, const Lde8Pass& ps, size_t tiles) {
+    if (ctx->fp.p >> 31) launch_lde8_impl<R_LOG, FIRST, true>(ctx, ps, tiles);
+    else launch_lde8_impl<R_LOG, FIRST, false>(ctx, ps, tiles);
 }
 template <bool FIRST>
 static void dispatch_lde8(stark_ctx* ctx, unsigned r, const Lde8Pass& ps, size_t tiles) {

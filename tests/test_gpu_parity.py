@@ -482,6 +482,28 @@ def test_two_contexts_interleaved(sp, orc):
         a.close(); b.close()
 
 
+@pytest.mark.parametrize("modulus,gen", [(2013265921, 31), (998244353, 3), (469762049, 3)])
+def test_small_modulus_blowup8_path(sp, orc, modulus, gen):
+    """p < 2^31: the blow-up-by-8 transform must not use lazily reduced ("weak") butterfly values, which need
+    2^32 < 2p (found by tools/soak.py: evaluations were off by multiples of p folded wrongly)."""
+    c = sp.Context(modulus, gen, 0)
+    try:
+        for log_n, nco in ((13, 14), (14, 31), (16, 602), (18, 1 << 15)):
+            w = orc.root_of_unity(log_n, modulus, gen)
+            coeffs = orc.synthetic_column(5 + log_n, nco, modulus)
+            off = 720954169 % modulus
+            assert np.array_equal(c.coset_evaluate(coeffs, log_n, off), orc.coset_evaluate(coeffs, log_n, off, w, modulus)), log_n
+        ch, och = sp.Channel(modulus), orc.Channel(modulus)
+        coeffs = orc.synthetic_column(9, 2731, modulus)
+        pr = sp.fri_commit(c, coeffs, sp.CosetFri(c, 267101690 % modulus, 15), ch)
+        sp.decommit_fri(2, (1 << 15) - 1, pr, ch)
+        opr = orc.fri_commit_fast(coeffs, 15, 267101690 % modulus, orc.root_of_unity(15, modulus, gen), och, modulus)
+        orc.decommit_fri(2, (1 << 15) - 1, opr, och)
+        assert ch.state == och.state and ch.proof == och.proof
+    finally:
+        c.close()
+
+
 @pytest.mark.parametrize("modulus,gen", [(4293918721, 19), (3489660929, 3)])
 def test_large_modulus_lde_and_fold_paths(sp, orc, modulus, gen):
     """The blow-up-8 LDE kernel (weak/lazy arithmetic) and the fused fold with p close to 2^32."""

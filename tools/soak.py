@@ -1,0 +1,110 @@
+#!/usr/bin/env python
+"""Randomised differential soak against the CPU oracle (test infrastructure, not product):
+    python tools/soak.py [seconds] [seed]
+Random tree sizes, transform sizes / offsets, polynomial degrees, inverse inputs with zero patterns and a few moduli;
+every result must equal the oracle's bit for bit.  Prints one line per failure and a summary; exit code 1 on any mismatch."""
+import importlib, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+sp = importlib.import_module("stark-prover_b200")
+from oracle import pyoracle as orc
+
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+seed = int(sys.argv[2]) if len(sys.argv) > 2 else 12345
+rng = np.random.default_rng(seed)
+MODULI = [(3221225473, 5), (2013265921, 31), (998244353, 3), (4293918721, 19), (469762049, 3)]
+ctxs = {}
+def ctx_for(m, g):
+    if m not in ctxs:
+        ctxs[m] = sp.Context(m, g, 0)
+    return ctxs[m]
+
+counts, fails = {}, 0
+def check(kind, ok, detail):
+    global fails
+    counts[kind] = counts.get(kind, 0) + 1
+    if not ok:
+        fails += 1
+        print(f"MISMATCH {kind}: {detail}", flush=True)
+
+t_end = time.time() + budget
+while time.time() < t_end:
+    m, g = MODULI[int(rng.integers(0, len(MODULI)))]
+    ctx = ctx_for(m, g)
+    two = (m - 1 & -(m - 1)).bit_length() - 1
+    kind = int(rng.integers(0, 5))
+    if kind == 0:                                   # Merkle: ragged sizes, every level's ends + random nodes + paths
+        n = int(rng.integers(1, 1 << int(rng.integers(1, 19))))
+        vals = orc.synthetic_column(int(rng.integers(1, 1 << 30)), n, m)
+        t, ot = sp.MerkleTree.new(ctx, vals), orc.Tree(vals)
+        ok = t.root() == ot.root_hex()
+        for l in range(1, t.depth + 1):
+            w = -(-n // (1 << l))
+            for j in {0, w - 1, int(rng.integers(0, w))}:
+                ok = ok and t.node(l, j) == ot.node(l, j)
+        for idx in {0, n - 1, int(rng.integers(0, n))}:
+            ok = ok and t.get_authentication_path(idx) == ot.path(idx)
+        check("merkle", ok, f"n={n} modulus={m}")
+        t.free()
+    elif kind == 1:                                 # coset evaluation / interpolation round trip against the oracle
+        log_n = int(rng.integers(0, min(two, 18) + 1))
+        log_d = int(rng.integers(0, log_n + 1))
+        nco = int(rng.integers(1, (1 << log_d) + 1))
+        off = int(rng.integers(1, m))
+        w = orc.root_of_unity(log_n, m, g)
+        c = orc.synthetic_column(int(rng.integers(1, 1 << 30)), nco, m)
+        ev = ctx.coset_evaluate(c, log_n, off)
+        want = orc.coset_evaluate(c, log_n, off, w, m)
+        back = ctx.coset_interpolate(ev, log_n, off)
+        ok = np.array_equal(ev, want) and np.array_equal(back[:nco], c) and not back[nco:].any()
+        check("coset_ntt", ok, f"log_n={log_n} coeffs={nco} offset={off} modulus={m}")
+    elif kind == 2:                                 # batched inverse / quotient with zero patterns
+        n = int(rng.integers(1, 1 << int(rng.integers(1, 17))))
+        a = orc.synthetic_column(int(rng.integers(1, 1 << 30)), n, m)
+        z = rng.random(n) < float(rng.choice([0.0, 0.01, 0.5, 0.99]))
+        a[z] = 0
+        got = ctx.batch_inverse(a)
+        ok = np.array_equal(got, orc.batch_inverse(a, m))
+        num = orc.synthetic_column(int(rng.integers(1, 1 << 30)), n, m)
+        q = ctx.quotient_pointwise(num, a)
+        inv = orc.batch_inverse(a, m)
+        want = np.array([int(x) * int(y) % m for x, y in zip(num[:2000], inv[:2000])], dtype=np.uint64)
+        ok = ok and np.array_equal(q[:2000], want)
+        check("inverse", ok, f"n={n} zeros={int(z.sum())} modulus={m}")
+    elif kind == 3:                                 # FRI commit + openings: whole transcript
+        log_n = int(rng.integers(1, min(two, 15) + 1))
+        log_d = int(rng.integers(0, log_n + 1))
+        nco = int(rng.integers(1, (1 << log_d) + 1))
+        off = int(rng.integers(1, m))
+        c = orc.synthetic_column(int(rng.integers(1, 1 << 30)), nco, m)
+        if rng.random() < 0.3:
+            c[-int(rng.integers(1, nco + 1)):] = 0  # trailing zeros: Polynomial::new trims (may become the zero polynomial)
+        q = int(rng.integers(0, 4))
+        ch, och = sp.Channel(m), orc.Channel(m)
+        try:
+            pr = sp.fri_commit(ctx, c, sp.CosetFri(ctx, off, log_n), ch)
+            sp.decommit_fri(q, (1 << log_n) - 1, pr, ch)
+            gpu_err = None
+        except sp.StarkError as e:
+            gpu_err = e
+        try:
+            opr = orc.fri_commit_fast(c, log_n, off, orc.root_of_unity(log_n, m, g), och, m)
+            orc.decommit_fri(q, (1 << log_n) - 1, opr, och)
+            cpu_err = None
+        except Exception as e:
+            cpu_err = e
+        ok = (gpu_err is None) == (cpu_err is None) and (gpu_err is not None or (ch.state == och.state and ch.proof == och.proof))
+        check("fri", ok, f"log_n={log_n} coeffs={nco} offset={off} q={q} modulus={m} gpu_err={gpu_err} cpu_err={cpu_err}")
+    else:                                           # the build-defined prover + its verifier (default field only)
+        ctx = ctx_for(*MODULI[0])
+        log_t, log_b = int(rng.integers(2, 13)), int(rng.integers(1, 5))
+        a1, q = int(rng.integers(0, MODULI[0][0])), int(rng.integers(1, 4))
+        ch, och = sp.Channel(MODULI[0][0]), orc.Channel(MODULI[0][0])
+        sp.stark101_prove(ctx, ch, a1, log_t, log_b, q)
+        orc.stark101_prove(och, a1, log_t, log_b, sp.G_DEFAULT, q, literal=False)
+        claimed = int(orc.fibsq_trace(a1, (1 << log_t) - 1)[(1 << log_t) - 2])
+        okv, why = sp.stark101_verify(ch.proof_flat(), claimed, log_t, log_b, q)
+        check("stark101", ch.state == och.state and ch.proof == och.proof and okv, f"log_trace={log_t} log_blowup={log_b} a1={a1} q={q} verifier={why}")
+print(f"soak: {sum(counts.values())} cases in {budget:.0f} s {counts}, mismatches: {fails} (seed {seed})")
+sys.exit(1 if fails else 0)
