@@ -239,6 +239,24 @@ static void check_size(stark_ctx* ctx, unsigned log_n) {
     STARK_REQUIRE(log_n <= 30, "ntt: log_n > 30 not supported");
 }
 
+// The contiguous pass over `cols` groups of 2^r points: tiles of 32 groups, and one narrower tile for what is left
+// (a batch whose group count is not a multiple of 32; a single transform has a power-of-two count).
+template <bool DIF>
+static void launch_contiguous(stark_ctx* ctx, unsigned r, NttPass ps, size_t cols) {
+    const size_t full = cols / NTT_C, rem = cols % NTT_C;
+    if (full) {
+        ps.ncols = NTT_C;
+        dispatch_pass<DIF, false>(ctx, r, ps, full);
+    }
+    if (rem) {
+        STARK_REQUIRE(full == 0 || (ps.log_pad == 0 && !ps.has_scale), "ntt: ragged batches take no padding/scale");
+        const size_t done = (full * NTT_C) << r;
+        ps.src += done; ps.dst += done;
+        ps.ncols = (unsigned)rem;
+        dispatch_pass<DIF, false>(ctx, r, ps, 1);
+    }
+}
+
 void ntt_dit(stark_ctx* ctx, const uint32_t* src, uint32_t* data, unsigned log_n, unsigned log_pad,
              const PowTable* scale, bool inverse_root, size_t batch) {
     check_size(ctx, log_n);
@@ -270,8 +288,7 @@ void ntt_dit(stark_ctx* ctx, const uint32_t* src, uint32_t* data, unsigned log_n
             ps.has_scale = scale != nullptr;
             if (scale) ps.scale = *scale;
             size_t cols = (n * batch) >> r;           // groups of 2^r contiguous points, across the whole batch
-            ps.ncols = (unsigned)(cols < (size_t)NTT_C ? cols : NTT_C);
-            dispatch_pass<false, false>(ctx, r, ps, cols / ps.ncols);
+            launch_contiguous<false>(ctx, r, ps, cols);
         } else {
             ps.ncols = NTT_C;
             dispatch_pass<false, true>(ctx, r, ps, batch * n / ((size_t)NTT_C << r));
@@ -301,8 +318,7 @@ void ntt_dif(stark_ctx* ctx, uint32_t* data, unsigned log_n, bool inverse_root, 
         ps.small_log = ctx->small_log;
         if (lo == 0) {
             size_t cols = (n * batch) >> r;
-            ps.ncols = (unsigned)(cols < (size_t)NTT_C ? cols : NTT_C);
-            dispatch_pass<true, false>(ctx, r, ps, cols / ps.ncols);
+            launch_contiguous<true>(ctx, r, ps, cols);
         } else {
             ps.ncols = NTT_C;
             dispatch_pass<true, true>(ctx, r, ps, batch * n / ((size_t)NTT_C << r));

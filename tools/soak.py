@@ -33,7 +33,7 @@ while time.time() < t_end:
     m, g = MODULI[int(rng.integers(0, len(MODULI)))]
     ctx = ctx_for(m, g)
     two = (m - 1 & -(m - 1)).bit_length() - 1
-    kind = int(rng.integers(0, 5))
+    kind = int(rng.integers(0, 9))
     if kind == 0:                                   # Merkle: ragged sizes, every level's ends + random nodes + paths
         n = int(rng.integers(1, 1 << int(rng.integers(1, 19))))
         vals = orc.synthetic_column(int(rng.integers(1, 1 << 30)), n, m)
@@ -96,7 +96,55 @@ while time.time() < t_end:
             cpu_err = e
         ok = (gpu_err is None) == (cpu_err is None) and (gpu_err is not None or (ch.state == och.state and ch.proof == och.proof))
         check("fri", ok, f"log_n={log_n} coeffs={nco} offset={off} q={q} modulus={m} gpu_err={gpu_err} cpu_err={cpu_err}")
-    else:                                           # the build-defined prover + its verifier (default field only)
+    elif kind == 5:                                 # LDE of evaluations: blow-ups 1..16 (8 takes its own kernel), both offsets random
+        log_t = int(rng.integers(0, min(two, 17) + 1))
+        log_b = int(rng.integers(0, min(4, two - log_t) + 1))
+        off_in, off_out = int(rng.integers(1, m)), int(rng.integers(1, m))
+        ev = orc.synthetic_column(int(rng.integers(1, 1 << 30)), 1 << log_t, m)
+        got = ctx.coset_lde(ev, log_t, off_in, log_b, off_out)
+        coef = orc.coset_interpolate(ev, log_t, off_in, orc.root_of_unity(log_t, m, g), m)
+        want = orc.coset_evaluate(coef, log_t + log_b, off_out, orc.root_of_unity(log_t + log_b, m, g), m)
+        check("coset_lde", np.array_equal(got, want), f"log_t={log_t} log_blowup={log_b} off_in={off_in} off_out={off_out} modulus={m}")
+    elif kind == 6:                                 # natural-order NTT / iNTT and the coset domain
+        log_n = int(rng.integers(0, min(two, 18) + 1))
+        w = orc.root_of_unity(log_n, m, g)
+        a = orc.synthetic_column(int(rng.integers(1, 1 << 30)), 1 << log_n, m)
+        f = ctx.ntt(a, log_n)
+        ok = np.array_equal(f, orc.ntt(a, log_n, w, m)) and np.array_equal(ctx.intt(f, log_n), a)
+        off = int(rng.integers(1, m))
+        ok = ok and np.array_equal(ctx.coset_domain(log_n, off), orc.coset_domain(off, w, 1 << log_n, m))
+        check("ntt_domain", ok, f"log_n={log_n} offset={off} modulus={m}")
+    elif kind == 7:                                 # four-step transform, all ranks emulated on this GPU (both exchange styles)
+        mg = importlib.import_module("stark-prover_b200.multi_gpu")
+        world = int(rng.choice([1, 2, 4, 8]))
+        log_n = int(rng.integers(max(10, 2 * (world.bit_length() - 1) + 4), min(two, 17) + 1))
+        nco = int(rng.integers(1, (1 << log_n) + 1))
+        off = int(rng.integers(1, m))
+        c = orc.synthetic_column(int(rng.integers(1, 1 << 30)), nco, m)
+        want = orc.coset_evaluate(c, log_n, off, orc.root_of_unity(log_n, m, g), m)
+        got = np.concatenate([b.download() for b in mg.four_step_lde_emulated(sp, ctx, c, log_n, off, world)])
+        ok, which = np.array_equal(got, want), "all-to-all style"
+        if ok:
+            try:
+                blocks = mg.four_step_p2p_emulated(sp, ctx, c, log_n, off, world)
+                ok, which = np.array_equal(np.concatenate([b.download() for b in blocks]), want), "peer-memory style"
+                for b in blocks: b.free()
+            except sp.StarkError as e:              # documented size limit of the peer-memory kernels (>= 32 rows and columns per rank)
+                ok = "every rank needs" in str(e)
+                which = f"peer-memory style raised {e}"
+        check("four_step", ok, f"{which}: log_n={log_n} coeffs={nco} world={world} offset={off} modulus={m}")
+    elif kind == 8:                                 # column-batched transforms (the four-step building block)
+        log_m = int(rng.integers(1, min(two, 12) + 1))
+        batch = int(rng.integers(1, 100))
+        a = orc.synthetic_column(int(rng.integers(1, 1 << 30)), batch << log_m, m)
+        v = ctx.upload(a)
+        inv = bool(rng.integers(0, 2))
+        ctx.ntt_batch_dev(v, log_m, inv)
+        w = orc.root_of_unity(log_m, m, g)
+        want = np.concatenate([(orc.intt if inv else orc.ntt)(a[i << log_m:(i + 1) << log_m], log_m, w, m) for i in range(batch)])
+        check("ntt_batch", np.array_equal(v.download(), want), f"log_m={log_m} batch={batch} inverse={inv} modulus={m}")
+        v.free()
+    else:                                           # kind 4: the build-defined prover + its verifier (default field only)
         ctx = ctx_for(*MODULI[0])
         log_t, log_b = int(rng.integers(2, 13)), int(rng.integers(1, 5))
         a1, q = int(rng.integers(0, MODULI[0][0])), int(rng.integers(1, 4))
