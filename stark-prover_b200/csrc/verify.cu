@@ -153,9 +153,10 @@ bool verify_fri_core(const Msgs& msgs, size_t& pos, Channel& ch, const Fp& F, ui
             const size_t n = n0 >> k;
             if (n == 0) return fail("layer of size zero");
             const size_t i = (size_t)idx_want % n, s = (i + n / 2) % n;
+            uint64_t lone = 0;
             if (n == 1) {                                                               // :147-149 sends the constant first
                 m = next();
-                if (!m || m->size() != 8) return fail("missing the length-1 layer element");
+                if (!m || !parse_be8(*m, &lone)) return fail("missing the length-1 layer element");
                 ch.send(m->data(), 8);
             }
             uint64_t val[2];
@@ -170,6 +171,7 @@ bool verify_fri_core(const Msgs& msgs, size_t& pos, Channel& ch, const Fp& F, ui
                 ch.send(me->data(), me->size());
                 ch.send(mp->data(), mp->size());
             }
+            if (n == 1 && lone != val[0]) return fail("the length-1 layer element differs from the opened value");
             if (k == 0 && has_expect && val[0] != expect0) return fail("layer 0 does not equal the composition polynomial at the queried point");
             const size_t j = i % (n / 2 ? n / 2 : 1);
             const uint64_t a = (i < n / 2 || n == 1) ? val[0] : val[1], b = (i < n / 2 || n == 1) ? val[1] : val[0];

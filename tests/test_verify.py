@@ -1,7 +1,11 @@
 """The host-side verifier: accepts proofs made by the CPU oracle (CPU test) and by the
 GPU path (GPU test), rejects every single-byte corruption class."""
+import os
+
 import numpy as np
 import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 P = 3221225473
 
@@ -95,3 +99,32 @@ def test_stark101_verifier_accepts_gpu_proof(sp, orc, ctx, log_trace, a1):
     assert ok, why
     ok, _ = sp.stark101_verify(ch.proof_flat(), (claimed + 5) % P, log_trace, 3, 3)
     assert not ok
+
+
+def test_fri_verifier_checks_the_length_one_layer_element(sp, orc):
+    """A FRI that folds down to a one-point layer sends that point once more before its openings (fri_commit.rs:147-149);
+    the verifier must compare it with the opened value -- in the LAST query nothing after it depends on the channel
+    state, so a flipped bit there was accepted (found by tools/soak_host.py)."""
+    log_n, off, q = 3, 1365814300, 2
+    c = orc.synthetic_poly_exact_degree(5, 7)
+    ch = orc.Channel(P)
+    pr = orc.fri_commit_fast(c, log_n, off, orc.root_of_unity(log_n), ch, P)
+    orc.decommit_fri(q, (1 << log_n) - 1, pr, ch)
+    assert len(pr.layer(pr.num_layers - 1)) == 1
+    msgs = ch.proof
+    flat = lambda ms: b"".join(len(m).to_bytes(4, "little") + bytes(m) for m in ms)
+    assert sp.verify_fri(flat(msgs), log_n, off, q, (1 << log_n) - 1)[0]
+    lone = len(msgs) - 5                      # ... lone element, elem, path, sibling elem, sibling path
+    assert len(msgs[lone]) == 8 and msgs[lone] == msgs[lone + 1]
+    bad = [bytearray(m) for m in msgs]
+    bad[lone][7] ^= 1
+    ok, why = sp.verify_fri(flat(bad), log_n, off, q, (1 << log_n) - 1)
+    assert not ok and "length-1" in why
+
+
+def test_host_soak_short():
+    """A few seconds of the randomised host-side differential run (channel op sequences, Merkle validation, verifiers
+    with bit flips); the long form is `python tools/soak_host.py 60`."""
+    import subprocess, sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "soak_host.py"), "4", "99"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
