@@ -33,7 +33,7 @@ while time.time() < t_end:
     m, g = MODULI[int(rng.integers(0, len(MODULI)))]
     ctx = ctx_for(m, g)
     two = (m - 1 & -(m - 1)).bit_length() - 1
-    kind = int(rng.integers(0, 9))
+    kind = int(rng.integers(0, 12))
     if kind == 0:                                   # Merkle: ragged sizes, every level's ends + random nodes + paths
         n = int(rng.integers(1, 1 << int(rng.integers(1, 19))))
         vals = orc.synthetic_column(int(rng.integers(1, 1 << 30)), n, m)
@@ -144,6 +144,45 @@ while time.time() < t_end:
         want = np.concatenate([(orc.intt if inv else orc.ntt)(a[i << log_m:(i + 1) << log_m], log_m, w, m) for i in range(batch)])
         check("ntt_batch", np.array_equal(v.download(), want), f"log_m={log_m} batch={batch} inverse={inv} modulus={m}")
         v.free()
+    elif kind == 9:                                 # occasionally large: 2^19..2^22 trees (root + a path) and transforms
+        if rng.random() < 0.85:
+            continue
+        n = int(rng.integers(1 << 19, (1 << 22) + 1))
+        vals = orc.synthetic_column(int(rng.integers(1, 1 << 30)), n, m)
+        t = sp.MerkleTree.new(ctx, vals)
+        ok = t.root_bytes() == orc.merkle_root_only(vals)
+        idx = int(rng.integers(0, n))
+        ok = ok and sp.merkle_validate(t.root_bytes(), n, idx, int(vals[idx]), t.get_authentication_path(idx))
+        t.free()
+        log_n = int(rng.integers(19, min(two, 22) + 1))
+        nco = int(rng.integers(1, (1 << log_n) + 1))
+        off = int(rng.integers(1, m))
+        c = orc.synthetic_column(int(rng.integers(1, 1 << 30)), nco, m)
+        ok = ok and np.array_equal(ctx.coset_evaluate(c, log_n, off), orc.coset_evaluate(c, log_n, off, orc.root_of_unity(log_n, m, g), m))
+        check("large", ok, f"leaves={n} log_n={log_n} coeffs={nco} offset={off} modulus={m}")
+    elif kind == 10:                                # FRI: one batched opening == per-index openings; the verifier accepts the transcript
+        log_n = int(rng.integers(2, min(two, 14) + 1))
+        nco = int(rng.integers(2, (1 << int(rng.integers(1, log_n + 1))) + 1))
+        off = int(rng.integers(1, m))
+        c = orc.synthetic_poly_exact_degree(int(rng.integers(1, 1 << 30)), nco, m)
+        q = int(rng.integers(1, 5))
+        ch = sp.Channel(m)
+        pr = sp.fri_commit(ctx, c, sp.CosetFri(ctx, off, log_n), ch)
+        idxs = [int(x) for x in rng.integers(0, 1 << log_n, 3)]
+        ok = pr.open(idxs) == b"".join(pr.open([i]) for i in idxs)
+        sp.decommit_fri(q, (1 << log_n) - 1, pr, ch)
+        good, why = sp.verify_fri(ch.proof_flat(), log_n, off, q, (1 << log_n) - 1, m, g)
+        check("fri_open_verify", ok and good, f"log_n={log_n} coeffs={nco} offset={off} q={q} modulus={m} verifier={why!r}")
+        pr.free()
+    elif kind == 11:                                # the sharded prover's code path with one rank == the plain prover
+        mg = importlib.import_module("stark-prover_b200.multi_gpu")
+        ctx = ctx_for(*MODULI[0])
+        log_t, log_b = int(rng.integers(7, 13)), 3
+        a1, q = int(rng.integers(0, MODULI[0][0])), int(rng.integers(1, 3))
+        ch, ch1 = sp.Channel(MODULI[0][0]), sp.Channel(MODULI[0][0])
+        mg.stark101_prove_multi(sp, ctx, ch, a1, log_t, log_b, q, 0, 1)
+        sp.stark101_prove(ctx, ch1, a1, log_t, log_b, q)
+        check("stark101_multi_world1", ch.state == ch1.state and ch.proof == ch1.proof, f"log_trace={log_t} a1={a1} q={q}")
     else:                                           # kind 4: the build-defined prover + its verifier (default field only)
         ctx = ctx_for(*MODULI[0])
         log_t, log_b = int(rng.integers(2, 13)), int(rng.integers(1, 5))
