@@ -250,10 +250,19 @@ static DevBufPtr evaluate_on_coset(stark_ctx* ctx, const uint32_t* coeffs_padded
         lde8_forward(ctx, coeffs_padded, m, false, out->as<uint32_t>(), log_n - 3, offset, 1);
         return out;
     }
-    DevBuf tmp(m * 4, ctx->stream);
     bool unit = (offset % ctx->modulus) == 1;
     ScaleTable st;
     if (!unit) build_scale_table(ctx, offset, 1, log_m, st);
+    if (log_n >= 10) {
+        // natural -> natural without a permutation sweep; the zero padding above m is never read
+        DevBuf work(n * 4, ctx->stream);
+        DevBufPtr out = make_buf(n * 4, ctx->stream);
+        if (ntt_natural_supported(log_n, coeffs_padded, work.p, out->p)) {
+            ntt_natural(ctx, coeffs_padded, m, work.as<uint32_t>(), out->as<uint32_t>(), log_n, false, unit ? nullptr : &st.view, nullptr);
+            return out;
+        }
+    }
+    DevBuf tmp(m * 4, ctx->stream);
     bitrev_permute(ctx, coeffs_padded, tmp.as<uint32_t>(), log_m, unit ? nullptr : &st.view, true);
     DevBufPtr out = make_buf(n * 4, ctx->stream);
     ntt_dit(ctx, tmp.as<uint32_t>(), out->as<uint32_t>(), log_n, log_n - log_m, nullptr, false);
@@ -264,11 +273,15 @@ static DevBufPtr interpolate_on_coset(stark_ctx* ctx, const uint32_t* evals, uns
     STARK_REQUIRE(log_n <= ctx->two_adicity, "interpolate: 2^log_n does not divide p-1");
     size_t n = (size_t)1 << log_n;
     DevBuf tmp(n * 4, ctx->stream);
-    STARK_CUDA(cudaMemcpyAsync(tmp.p, evals, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-    ntt_dif(ctx, tmp.as<uint32_t>(), log_n, true);
     ScaleTable st;   // c_j = n^-1 * offset^-j * raw_j
     build_scale_table(ctx, h_inv(offset % ctx->modulus, ctx->modulus), h_inv(n % ctx->modulus, ctx->modulus), log_n, st);
     DevBufPtr out = make_buf(n * 4, ctx->stream);
+    if (ntt_natural_supported(log_n, evals, tmp.p, out->p)) {      // three sweeps instead of copy + three + permutation
+        ntt_natural(ctx, evals, n, tmp.as<uint32_t>(), out->as<uint32_t>(), log_n, true, nullptr, &st.view);
+        return out;
+    }
+    STARK_CUDA(cudaMemcpyAsync(tmp.p, evals, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    ntt_dif(ctx, tmp.as<uint32_t>(), log_n, true);
     bitrev_permute(ctx, tmp.as<uint32_t>(), out->as<uint32_t>(), log_n, &st.view, false);
     return out;
 }

@@ -357,6 +357,239 @@ void ntt_dif_columns(stark_ctx* ctx, uint32_t* data, unsigned log_n, unsigned co
     STARK_CUDA(cudaGetLastError());
 }
 
+// ---- natural -> natural transform without a permutation sweep ------------------------------------------------
+// (Polynomial::evaluate over a whole domain, ops.rs:76-83 @ fri_commit.rs:78, and Polynomial::interpolate,
+// ops.rs:239-241: both take and return natural order.)  The index is split into digits n = [n1][n2]..[nm], n1 the
+// most significant; pass i transforms digit i.  Passes 1..m-1 are strided and in place: the element at
+// [k1..k(i-1)][n_i][low] is first multiplied by W^(K*n_i), W = w_{2^(log_n-lo_i)}, K = k1 + R1 k2 + .. the output
+// index accumulated so far -- a per-ROW scalar of the tile (K is fixed by the tile's high address bits), kept in
+// shared memory, so the inter-pass twiddle costs one product per element and no table look-up.  Rows go into the
+// tile in bit-reversed order so that the lazy decimation-in-time rounds leave digit k_i in natural row order.
+// The last pass transforms the contiguous digit and writes X[K + 2^(log_n-r_m) k_m]: a tile holds 32 consecutive
+// k1 (= 32 consecutive K) for every n_m, so both its reads (runs of 2^r_m words) and its writes (128-byte lines)
+// are coalesced and the digit reversal costs nothing.  16-byte global accesses throughout.
+struct NatPass {
+    const uint32_t* src;
+    uint32_t* dst;
+    unsigned log_n;
+    unsigned lo;             // lowest address bit of this pass's digit
+    unsigned src_len;        // FIRST: valid entries of src (zero above)
+    int has_scale;           // FIRST: x_j *= scale(j);  LAST: X_k *= scale(k)
+    PowTable scale;
+    PowTable tw;             // w_{2^log_n}^e
+    const uint32_t* small;
+    unsigned small_log;
+    unsigned nprev;          // digits already transformed (address bits above this digit), most significant first
+    unsigned prev_bits[4];   // their widths
+    unsigned prev_off[4];    // their positions in the output index: off[d] = r_1 + .. + r_(d-1)
+};
+
+// output index accumulated by the earlier passes from the address bits above this pass's digit
+__device__ __forceinline__ uint32_t nat_kacc(const NatPass& ps, uint32_t high) {
+    uint32_t k = 0;
+#pragma unroll
+    for (int d = 3; d >= 0; d--) {           // static indices: the parameter struct stays in constant memory
+        if (d < (int)ps.nprev) {
+            k |= (high & ((1u << ps.prev_bits[d]) - 1u)) << ps.prev_off[d];
+            high >>= ps.prev_bits[d];
+        }
+    }
+    return k;
+}
+
+constexpr int nat_threads(int r_log) { return (2 << r_log) < 64 ? 64 : ((2 << r_log) > 512 ? 512 : (2 << r_log)); }
+constexpr int nat_min_blocks(int r_log) { return 1536 / nat_threads(r_log) > 16 ? 16 : 1536 / nat_threads(r_log); }
+
+template <int R_LOG, bool FIRST, bool LAZY>
+__global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat_strided_kernel(NatPass ps, FieldParams fp) {
+    extern __shared__ uint32_t smem[];
+    constexpr int R = 1 << R_LOG;
+    uint32_t* tile = smem;                    // [R][33], row rho holds digit value bitrev(rho) until the rounds have run
+    uint32_t* tws = smem + R * NTT_TS;        // [R/2] twiddles of w_R
+    uint32_t* rowtw = tws + (R >> 1);         // [R] W^(K t)
+    for (int k = threadIdx.x; k < (R >> 1); k += blockDim.x) tws[k] = ps.small[(size_t)k << (ps.small_log - R_LOG)];
+
+    const size_t tiles_per_high = ((size_t)1 << ps.lo) / NTT_C;
+    const size_t high = blockIdx.x / tiles_per_high;
+    const uint32_t low0 = (uint32_t)(blockIdx.x % tiles_per_high) * NTT_C;
+    const size_t gbase = (high << (ps.lo + R_LOG)) | low0;
+    if (!FIRST) {
+        const uint32_t K = nat_kacc(ps, (uint32_t)high);
+        for (int t = threadIdx.x; t < R; t += blockDim.x) rowtw[t] = pow_lookup(ps.tw, (K * (uint32_t)t) << ps.lo, fp);
+        __syncthreads();
+    }
+    // ---- load: a warp covers 4 tile rows x 128 bytes ----
+    for (int i = threadIdx.x; i < R * 8; i += blockDim.x) {
+        const int g4 = i & 7, rho = i >> 3;
+        const uint32_t t = bitrev_bits((uint32_t)rho, R_LOG);
+        const size_t g = gbase + ((size_t)t << ps.lo) + 4 * g4;
+        uint32_t v[4];
+        if (FIRST) {
+            if (g + 3 < ps.src_len) {
+                uint4 a = *reinterpret_cast<const uint4*>(ps.src + g);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) v[k] = (g + k < ps.src_len) ? ps.src[g + k] : 0u;
+            }
+            if (ps.has_scale) {      // the table only covers the indices below src_len
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (g + k < ps.src_len) v[k] = mont_mul(v[k], pow_lookup(ps.scale, (uint32_t)g + k, fp), fp);
+            }
+        } else {
+            uint4 a = *reinterpret_cast<const uint4*>(ps.dst + g);
+            const uint32_t w = rowtw[t];
+            v[0] = mont_mul(a.x, w, fp); v[1] = mont_mul(a.y, w, fp); v[2] = mont_mul(a.z, w, fp); v[3] = mont_mul(a.w, w, fp);
+        }
+        uint32_t* o = tile + rho * NTT_TS + 4 * g4;
+#pragma unroll
+        for (int k = 0; k < 4; k++) o[k] = v[k];
+    }
+    __syncthreads();
+
+    run_rounds<R_LOG, false, LAZY>(tile, tws, fp, NTT_C);
+
+    // ---- store: digit k_i in natural row order, same addresses (weak values are fine: the next pass multiplies) ----
+    for (int i = threadIdx.x; i < R * 8; i += blockDim.x) {
+        const int g4 = i & 7, t = i >> 3;
+        const uint32_t* o = tile + t * NTT_TS + 4 * g4;
+        *reinterpret_cast<uint4*>(ps.dst + gbase + ((size_t)t << ps.lo) + 4 * g4) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+template <int R_LOG>
+__global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat_last_kernel(NatPass ps, FieldParams fp) {
+    extern __shared__ uint32_t smem[];
+    constexpr int R = 1 << R_LOG;
+    uint32_t* tile = smem;                    // [R rows = n_m][33: column j = k1 - k1_0]
+    uint32_t* tws = smem + R * NTT_TS;
+    uint32_t* coltw = tws + (R >> 1);         // [32] W^K(j), W = w_{2^log_n}
+    for (int k = threadIdx.x; k < (R >> 1); k += blockDim.x) tws[k] = ps.small[(size_t)k << (ps.small_log - R_LOG)];
+
+    // address bits above the digit: [k1][mid]; the tile takes 32 consecutive k1 at one mid
+    const unsigned high_bits = ps.log_n - R_LOG, mid_bits = high_bits - ps.prev_bits[0];
+    const uint32_t mid = blockIdx.x & ((1u << mid_bits) - 1u);
+    const uint32_t k1_0 = (blockIdx.x >> mid_bits) * NTT_C;
+    const uint32_t K0 = nat_kacc(ps, (k1_0 << mid_bits) | mid);     // K(j) = K0 + j  (k1 is the lowest digit of K)
+    if (threadIdx.x < NTT_C) coltw[threadIdx.x] = pow_lookup(ps.tw, K0 + threadIdx.x, fp);
+    __syncthreads();
+
+    // ---- load: 8 lanes read 128 contiguous bytes of one row; a warp covers 4 values of j ----
+    for (int i = threadIdx.x; i < R * 8; i += blockDim.x) {
+        const int q8 = i & 7, jj = (i >> 3) & 3, rest = i >> 5;
+        const int seg = rest & ((R >> 5) - 1), j = (rest >> (R_LOG - 5)) * 4 + jj;
+        const uint32_t n3 = (uint32_t)seg * 32 + 4 * q8;
+        const size_t row = ((size_t)(k1_0 + j) << mid_bits) | mid;
+        uint4 a = *reinterpret_cast<const uint4*>(ps.src + (row << R_LOG) + n3);
+        const uint32_t step = coltw[j];
+        uint32_t w = pow_lookup(ps.tw, n3 * (K0 + (uint32_t)j), fp);          // W^(n_m K)
+        uint32_t* o = tile + n3 * NTT_TS + j;
+        o[0] = mont_mul(a.x, w, fp); w = mont_mul(w, step, fp);
+        o[NTT_TS] = mont_mul(a.y, w, fp); w = mont_mul(w, step, fp);
+        o[2 * NTT_TS] = mont_mul(a.z, w, fp); w = mont_mul(w, step, fp);
+        o[3 * NTT_TS] = mont_mul(a.w, w, fp);
+    }
+    __syncthreads();
+
+    run_rounds<R_LOG, true>(tile, tws, fp, NTT_C);          // natural rows in, k_m = bitrev(row) out, canonical
+
+    // ---- store: X[K0 + j + 2^(log_n - r) k_m], four j per thread ----
+    for (int i = threadIdx.x; i < R * 8; i += blockDim.x) {
+        const int g4 = i & 7, rho = i >> 3;
+        const uint32_t km = bitrev_bits((uint32_t)rho, R_LOG);
+        const uint32_t* o = tile + rho * NTT_TS + 4 * g4;
+        const size_t k = ((size_t)km << high_bits) + K0 + 4 * g4;
+        uint32_t v[4] = {o[0], o[1], o[2], o[3]};
+        if (ps.has_scale) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) v[c] = mont_mul(v[c], pow_lookup(ps.scale, (uint32_t)k + c, fp), fp);
+        }
+        *reinterpret_cast<uint4*>(ps.dst + k) = make_uint4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+template <int R_LOG, bool FIRST>
+static void launch_nat_strided(stark_ctx* ctx, const NatPass& ps, size_t tiles) {
+    constexpr int R = 1 << R_LOG;
+    const int threads = nat_threads(R_LOG);
+    size_t smem = (size_t)(R * NTT_TS + (R >> 1) + R) * sizeof(uint32_t);
+    auto launch = [&](auto kern) {
+        if (smem > 48 * 1024) STARK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)tiles, threads, smem, ctx->stream>>>(ps, ctx->fp);
+    };
+    if (ctx->fp.p >> 31) launch(nat_strided_kernel<R_LOG, FIRST, true>);     // weak butterfly values need 2^32 < 2p
+    else launch(nat_strided_kernel<R_LOG, FIRST, false>);
+    ctx->launches++;
+}
+template <int R_LOG>
+static void launch_nat_last(stark_ctx* ctx, const NatPass& ps, size_t tiles) {
+    constexpr int R = 1 << R_LOG;
+    const int threads = nat_threads(R_LOG);
+    size_t smem = (size_t)(R * NTT_TS + (R >> 1) + NTT_C) * sizeof(uint32_t);
+    auto kern = nat_last_kernel<R_LOG>;
+    if (smem > 48 * 1024) STARK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)tiles, threads, smem, ctx->stream>>>(ps, ctx->fp);
+    ctx->launches++;
+}
+
+bool ntt_natural_supported(unsigned log_n, const void* src, const void* work, const void* dst) {
+    auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return log_n >= 10 && log_n <= 30 && aligned(src) && aligned(work) && aligned(dst);
+}
+
+void ntt_natural(stark_ctx* ctx, const uint32_t* src, size_t src_len, uint32_t* work, uint32_t* dst, unsigned log_n,
+                 bool inverse_root, const PowTable* in_scale, const PowTable* out_scale) {
+    check_size(ctx, log_n);
+    STARK_REQUIRE(ntt_natural_supported(log_n, src, work, dst), "ntt_natural: size or alignment not supported");
+    const TwiddleSet& tws = ctx->twiddles(log_n);
+    const size_t n = (size_t)1 << log_n;
+    if (src_len > n) src_len = n;
+    std::vector<unsigned> bits = plan_bits(log_n);         // >= 2 digits of 5..9 bits, most significant first
+    KernelTimer kt(ctx, stark_ctx::CAT_NTT, 8.0 * (double)src_len + 8.0 * (double)n);
+    NatPass ps{};
+    ps.log_n = log_n;
+    ps.tw = inverse_root ? tws.inv() : tws.fwd();
+    ps.small = inverse_root ? ctx->small_inv.as<uint32_t>() : ctx->small_fwd.as<uint32_t>();
+    ps.small_log = ctx->small_log;
+    unsigned hi = log_n, off = 0;
+    for (size_t i = 0; i < bits.size(); i++) {
+        const unsigned r = bits[i];
+        const bool first = (i == 0), last = (i + 1 == bits.size());
+        ps.lo = hi - r;
+        ps.nprev = (unsigned)i;
+        ps.src = first ? src : work;
+        ps.dst = last ? dst : work;
+        ps.src_len = (unsigned)src_len;
+        ps.has_scale = first ? (in_scale != nullptr) : (last ? (out_scale != nullptr) : 0);
+        if (first && in_scale) ps.scale = *in_scale;
+        if (last && out_scale) ps.scale = *out_scale;
+        const size_t tiles = n / ((size_t)NTT_C << r);
+        if (!last) {
+            switch (r) {
+                case 5: first ? launch_nat_strided<5, true>(ctx, ps, tiles) : launch_nat_strided<5, false>(ctx, ps, tiles); break;
+                case 6: first ? launch_nat_strided<6, true>(ctx, ps, tiles) : launch_nat_strided<6, false>(ctx, ps, tiles); break;
+                case 7: first ? launch_nat_strided<7, true>(ctx, ps, tiles) : launch_nat_strided<7, false>(ctx, ps, tiles); break;
+                case 8: first ? launch_nat_strided<8, true>(ctx, ps, tiles) : launch_nat_strided<8, false>(ctx, ps, tiles); break;
+                case 9: first ? launch_nat_strided<9, true>(ctx, ps, tiles) : launch_nat_strided<9, false>(ctx, ps, tiles); break;
+                default: throw StarkError(ST_INTERNAL, "ntt_natural: bad pass width");
+            }
+        } else {
+            switch (r) {
+                case 5: launch_nat_last<5>(ctx, ps, tiles); break;
+                case 6: launch_nat_last<6>(ctx, ps, tiles); break;
+                case 7: launch_nat_last<7>(ctx, ps, tiles); break;
+                case 8: launch_nat_last<8>(ctx, ps, tiles); break;
+                case 9: launch_nat_last<9>(ctx, ps, tiles); break;
+                default: throw StarkError(ST_INTERNAL, "ntt_natural: bad pass width");
+            }
+        }
+        ps.prev_bits[i] = r; ps.prev_off[i] = off;
+        off += r; hi -= r;
+    }
+    STARK_CUDA(cudaGetLastError());
+}
+
 // ---- blow-up-by-8 forward transform: one size-n NTT over 8 interleaved coset columns ------------------------
 // X[8k'+s] = sum_j c_j (g w_N^s)^j w_n^(j k'): the evaluation on the size-N = 8n coset is eight size-n
 // transforms (one per shift s) that share every butterfly twiddle and every inter-pass twiddle, and whose
