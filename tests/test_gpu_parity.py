@@ -125,6 +125,67 @@ def test_coset_lde(sp, orc, ctx, log_n, log_blowup, off_in, off_out):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("log_n", list(range(10, 21)))
+def test_natural_transform_every_size(sp, orc, ctx, log_n):
+    """The permutation-free natural-order transform (ntt.cu, ntt_natural): 2, 3 digits, coset scaling on the way in
+    (evaluate) and on the way out (interpolate), blow-ups 1, 2 and 4, coefficient counts that are not a multiple of 4."""
+    w = orc.root_of_unity(log_n)
+    n = 1 << log_n
+    for nco in (n, n - 1, n // 2, n // 2 + 3, n // 4, n // 4 - 5, 1):
+        c = orc.synthetic_column(31 * log_n + nco % 97, nco)
+        assert np.array_equal(ctx.coset_evaluate(c, log_n, 7), orc.coset_evaluate(c, log_n, 7, w, P)), nco
+    e = orc.synthetic_column(log_n, n)
+    e[:4] = [P - 1, 0, P - 1, 1]
+    got = ctx.coset_interpolate(e, log_n, 11)
+    assert np.array_equal(got, orc.coset_interpolate(e, log_n, 11, w, P))
+    assert np.array_equal(ctx.coset_evaluate(got, log_n, 11), e)
+
+
+@pytest.mark.parametrize("modulus,gen", [(2013265921, 31), (998244353, 3), (4293918721, 19), (3489660929, 3), (2281701377, 3)])
+def test_natural_transform_other_moduli(sp, orc, modulus, gen):
+    """strict butterflies for p < 2^31, weak ones above; values next to p."""
+    c = sp.Context(modulus, gen, 0)
+    try:
+        for log_n in (10, 13, 17, 19):
+            if log_n > c.two_adicity:
+                continue
+            w = orc.root_of_unity(log_n, modulus, gen)
+            a = orc.synthetic_column(log_n, 1 << log_n, modulus)
+            a[:6] = [modulus - 1, modulus - 1, 0, modulus - 2, 1, modulus - 1]
+            assert np.array_equal(c.coset_evaluate(a, log_n, gen), orc.coset_evaluate(a, log_n, gen, w, modulus)), log_n
+            assert np.array_equal(c.coset_interpolate(a, log_n, gen), orc.coset_interpolate(a, log_n, gen, w, modulus)), log_n
+            assert np.array_equal(c.ntt(a, log_n), orc.ntt(a, log_n, w, modulus)), log_n
+    finally:
+        c.close()
+
+
+def test_natural_transform_four_digits_2e28(sp, orc, ctx):
+    """2^28 points = four digits of 7 bits: a sparse polynomial evaluated on the coset, spot-checked with pow()."""
+    log_n, off = 28, 5
+    n = 1 << log_n
+    terms = {0: 17, 1: P - 1, 130: 99, (1 << 14) + 5: 123456789, (1 << 21) + 77: 3, n - 1: P - 2, n // 2: 42}
+    c = np.zeros(n, dtype=np.uint64)
+    for j, v in terms.items():
+        c[j] = v
+    cv = ctx.upload(c)
+    del c
+    ev = ctx.coset_evaluate_dev(cv, log_n, off)
+    w = orc.root_of_unity(log_n)
+    rng = np.random.default_rng(5)
+    idx = [0, 1, 127, 128, n - 1, n // 2, (1 << 21) + 1] + [int(i) for i in rng.integers(0, n, 40)]
+    for i in idx:
+        x = off * pow(w, i, P) % P
+        want = sum(v * pow(x, j, P) for j, v in terms.items()) % P
+        assert int(ev.download(i, 1)[0]) == want, i
+    back = ctx.coset_interpolate_dev(ev, off)
+    ev.free()
+    for j, v in terms.items():
+        assert int(back.download(j, 1)[0]) == v
+    blk = back.download(1 << 14, 1 << 12)
+    assert int(blk[5]) == 123456789 and np.count_nonzero(blk) == 1
+    back.free(); cv.free()
+
+
 def test_coset_domain(sp, orc, ctx):
     for log_n in (0, 1, 7, 13):
         assert np.array_equal(ctx.coset_domain(log_n, 5), orc.coset_domain(5, orc.root_of_unity(log_n), 1 << log_n, P))
