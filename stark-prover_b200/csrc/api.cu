@@ -290,10 +290,21 @@ static DevBufPtr lde_on_coset(stark_ctx* ctx, const uint32_t* evals, unsigned lo
     unsigned log_N = log_n + log_blowup;
     STARK_REQUIRE(log_N <= ctx->two_adicity, "lde: 2^(log_n+log_blowup) does not divide p-1");
     size_t n = (size_t)1 << log_n, N = (size_t)1 << log_N;
+    uint64_t p = ctx->modulus;
     DevBuf tmp(n * 4, ctx->stream);
+    if (log_blowup == 3 && lde8_supported(log_n)) {
+        DevBuf coef(n * 4, ctx->stream);
+        if (ntt_natural_supported(log_n, evals, tmp.p, coef.p)) {
+            // unscaled coefficients in natural order (three sweeps, no copy), gathered by the blow-up-by-8 transform's first pass
+            ntt_natural(ctx, evals, n, tmp.as<uint32_t>(), coef.as<uint32_t>(), log_n, true, nullptr, nullptr);
+            DevBufPtr out8 = make_buf(N * 4, ctx->stream);
+            lde8_forward(ctx, coef.as<uint32_t>(), n, false, out8->as<uint32_t>(), log_n,
+                         h_mul(offset_out % p, h_inv(offset_in % p, p), p), h_inv(n % p, p));
+            return out8;
+        }
+    }
     STARK_CUDA(cudaMemcpyAsync(tmp.p, evals, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     ntt_dif(ctx, tmp.as<uint32_t>(), log_n, true);                       // bit-reversed, unscaled coefficients
-    uint64_t p = ctx->modulus;
     if (log_blowup == 3 && lde8_supported(log_n)) {
         DevBufPtr out8 = make_buf(N * 4, ctx->stream);
         lde8_forward(ctx, tmp.as<uint32_t>(), n, true, out8->as<uint32_t>(), log_n,

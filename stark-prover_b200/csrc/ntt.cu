@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat
     constexpr int R = 1 << R_LOG;
     uint32_t* tile = smem;                    // [R][33], row rho holds digit value bitrev(rho) until the rounds have run
     uint32_t* tws = smem + R * NTT_TS;        // [R/2] twiddles of w_R
-    uint32_t* rowtw = tws + (R >> 1);         // [R] W^(K t)
+    uint32_t* rowtw = tws + (R >> 1);         // [R] W^(K t), t = bitrev(row)
     for (int k = threadIdx.x; k < (R >> 1); k += blockDim.x) tws[k] = ps.small[(size_t)k << (ps.small_log - R_LOG)];
 
     const size_t tiles_per_high = ((size_t)1 << ps.lo) / NTT_C;
@@ -415,7 +415,8 @@ __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat
     const size_t gbase = (high << (ps.lo + R_LOG)) | low0;
     if (!FIRST) {
         const uint32_t K = nat_kacc(ps, (uint32_t)high);
-        for (int t = threadIdx.x; t < R; t += blockDim.x) rowtw[t] = pow_lookup(ps.tw, (K * (uint32_t)t) << ps.lo, fp);
+        for (int rho = threadIdx.x; rho < R; rho += blockDim.x)      // indexed by tile row: consecutive words for a warp's 4 rows
+            rowtw[rho] = pow_lookup(ps.tw, (K * bitrev_bits((uint32_t)rho, R_LOG)) << ps.lo, fp);
         __syncthreads();
     }
     // ---- load: a warp covers 4 tile rows x 128 bytes ----
@@ -432,14 +433,15 @@ __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat
 #pragma unroll
                 for (int k = 0; k < 4; k++) v[k] = (g + k < ps.src_len) ? ps.src[g + k] : 0u;
             }
-            if (ps.has_scale) {      // the table only covers the indices below src_len
+            if (ps.has_scale && g < ps.src_len) {      // one look-up, then walk base^(g+k) (the table ends at src_len)
+                uint32_t sc = pow_lookup(ps.scale, (uint32_t)g, fp);
+                const uint32_t step = __ldg(ps.scale.lo + 1);
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (g + k < ps.src_len) v[k] = mont_mul(v[k], pow_lookup(ps.scale, (uint32_t)g + k, fp), fp);
+                for (int k = 0; k < 4; k++) { v[k] = mont_mul(v[k], sc, fp); if (k < 3) sc = mont_mul(sc, step, fp); }
             }
         } else {
             uint4 a = *reinterpret_cast<const uint4*>(ps.dst + g);
-            const uint32_t w = rowtw[t];
+            const uint32_t w = rowtw[rho];
             v[0] = mont_mul(a.x, w, fp); v[1] = mont_mul(a.y, w, fp); v[2] = mont_mul(a.z, w, fp); v[3] = mont_mul(a.w, w, fp);
         }
         uint32_t* o = tile + rho * NTT_TS + 4 * g4;
@@ -502,8 +504,10 @@ __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat
         const size_t k = ((size_t)km << high_bits) + K0 + 4 * g4;
         uint32_t v[4] = {o[0], o[1], o[2], o[3]};
         if (ps.has_scale) {
+            uint32_t sc = pow_lookup(ps.scale, (uint32_t)k, fp);
+            const uint32_t step = __ldg(ps.scale.lo + 1);
 #pragma unroll
-            for (int c = 0; c < 4; c++) v[c] = mont_mul(v[c], pow_lookup(ps.scale, (uint32_t)k + c, fp), fp);
+            for (int c = 0; c < 4; c++) { v[c] = mont_mul(v[c], sc, fp); if (c < 3) sc = mont_mul(sc, step, fp); }
         }
         *reinterpret_cast<uint4*>(ps.dst + k) = make_uint4(v[0], v[1], v[2], v[3]);
     }
