@@ -31,8 +31,18 @@ __device__ __forceinline__ uint32_t mont_mul(uint32_t a, uint32_t b, const Field
 #endif
     uint32_t q = lo * f.pinv;
     uint32_t h = __umulhi(q, f.p);
+#if defined(STARK_NTT_BFLY) && (STARK_NTT_BFLY & 4)
+    uint32_t r;      // experiment: predicated correction instead of compare + select + three-input add
+    asm("{ .reg .pred q;\n\t"
+        "setp.lt.u32 q, %1, %2;\n\t"
+        "sub.u32 %0, %1, %2;\n\t"
+        "@q add.u32 %0, %0, %3;\n\t}"
+        : "=&r"(r) : "r"(hi), "r"(h), "r"(f.p));
+    return r;
+#else
     uint32_t r = hi - h;
     return hi < h ? r + f.p : r;
+#endif
 }
 __device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b, const FieldParams& f) {
     uint32_t s = a + b;

@@ -39,13 +39,42 @@ struct NttPass {
 // element (2^32 < 2p, so canonical or canonical + p).  A Montgomery product accepts a weak operand and returns a canonical one, so in
 // a + w*b / a - w*b only `a` is weak; the sum wraps past 2^32 at most once and the difference goes negative
 // at most once, which makes the add 3 instructions instead of 6.  The last pass canonicalises on store.
+// STARK_NTT_BFLY (bit mask, kernel experiments): the conditional correction of a lazy add (bit 1) / subtract (bit 0)
+// as a PREDICATED multiply-add on the FMA pipe instead of compare + select + add on the ALU pipe; `one` is a 1 the
+// compiler cannot see through (same device as sha256.cuh).
+#ifndef STARK_NTT_BFLY
+#define STARK_NTT_BFLY 2
+#endif
+static __constant__ uint32_t c_ntt_one = 1;
 __device__ __forceinline__ uint32_t ladd(uint32_t a_weak, uint32_t b, const FieldParams& f) {
+#if STARK_NTT_BFLY & 2
+    uint32_t s;
+    const uint32_t one = c_ntt_one, np = 0u - f.p;
+    asm("{ .reg .pred q;\n\t"
+        "mad.lo.u32 %0, %1, %3, %2;\n\t"
+        "setp.lt.u32 q, %0, %1;\n\t"
+        "@q mad.lo.u32 %0, %4, %3, %0;\n\t}"
+        : "=&r"(s) : "r"(a_weak), "r"(b), "r"(one), "r"(np));
+    return s;
+#else
     uint32_t s = a_weak + b;
     return s < a_weak ? s - f.p : s;
+#endif
 }
 __device__ __forceinline__ uint32_t lsub(uint32_t a_weak, uint32_t b, const FieldParams& f) {
+#if STARK_NTT_BFLY & 1
+    uint32_t d;
+    const uint32_t one = c_ntt_one, mone = 0u - one;
+    asm("{ .reg .pred q;\n\t"
+        "setp.lt.u32 q, %1, %2;\n\t"
+        "mad.lo.u32 %0, %2, %4, %1;\n\t"
+        "@q mad.lo.u32 %0, %5, %3, %0;\n\t}"
+        : "=&r"(d) : "r"(a_weak), "r"(b), "r"(one), "r"(mone), "r"(f.p));
+    return d;
+#else
     uint32_t d = a_weak - b;
     return a_weak < b ? d + f.p : d;
+#endif
 }
 __device__ __forceinline__ uint32_t canonical(uint32_t x, const FieldParams& f) { return x >= f.p ? x - f.p : x; }
 
@@ -413,40 +442,58 @@ __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat
     const size_t high = blockIdx.x / tiles_per_high;
     const uint32_t low0 = (uint32_t)(blockIdx.x % tiles_per_high) * NTT_C;
     const size_t gbase = (high << (ps.lo + R_LOG)) | low0;
-    if (!FIRST) {
-        const uint32_t K = nat_kacc(ps, (uint32_t)high);
-        for (int rho = threadIdx.x; rho < R; rho += blockDim.x)      // indexed by tile row: consecutive words for a warp's 4 rows
-            rowtw[rho] = pow_lookup(ps.tw, (K * bitrev_bits((uint32_t)rho, R_LOG)) << ps.lo, fp);
-        __syncthreads();
-    }
-    // ---- load: a warp covers 4 tile rows x 128 bytes ----
-    for (int i = threadIdx.x; i < R * 8; i += blockDim.x) {
-        const int g4 = i & 7, rho = i >> 3;
-        const uint32_t t = bitrev_bits((uint32_t)rho, R_LOG);
-        const size_t g = gbase + ((size_t)t << ps.lo) + 4 * g4;
-        uint32_t v[4];
-        if (FIRST) {
-            if (g + 3 < ps.src_len) {
-                uint4 a = *reinterpret_cast<const uint4*>(ps.src + g);
-                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    // ---- load: a warp covers 4 tile rows x 128 bytes.  A thread's global loads are all issued before the row
+    // twiddles are looked up and before the first barrier, so that table and data latencies overlap. ----
+    constexpr int T = nat_threads(R_LOG), ITER = (R * 8) / T;     // 4 (8 for 2^9 rows)
+    static_assert(ITER % 4 == 0, "tile rows x 8 vectors must be a multiple of 4 per thread");
+#pragma unroll 1
+    for (int b = 0; b < ITER; b += 4) {
+        uint4 a[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = threadIdx.x + (b + u) * T;
+            const int g4 = i & 7, rho = i >> 3;
+            const size_t g = gbase + ((size_t)bitrev_bits((uint32_t)rho, R_LOG) << ps.lo) + 4 * g4;
+            if (FIRST) {
+                if (g + 3 < ps.src_len) a[u] = *reinterpret_cast<const uint4*>(ps.src + g);
+                else {
+                    a[u].x = (g < ps.src_len) ? ps.src[g] : 0u;
+                    a[u].y = (g + 1 < ps.src_len) ? ps.src[g + 1] : 0u;
+                    a[u].z = (g + 2 < ps.src_len) ? ps.src[g + 2] : 0u;
+                    a[u].w = 0u;
+                }
             } else {
-#pragma unroll
-                for (int k = 0; k < 4; k++) v[k] = (g + k < ps.src_len) ? ps.src[g + k] : 0u;
+                a[u] = *reinterpret_cast<const uint4*>(ps.dst + g);
             }
-            if (ps.has_scale && g < ps.src_len) {      // one look-up, then walk base^(g+k) (the table ends at src_len)
-                uint32_t sc = pow_lookup(ps.scale, (uint32_t)g, fp);
-                const uint32_t step = __ldg(ps.scale.lo + 1);
-#pragma unroll
-                for (int k = 0; k < 4; k++) { v[k] = mont_mul(v[k], sc, fp); if (k < 3) sc = mont_mul(sc, step, fp); }
-            }
-        } else {
-            uint4 a = *reinterpret_cast<const uint4*>(ps.dst + g);
-            const uint32_t w = rowtw[rho];
-            v[0] = mont_mul(a.x, w, fp); v[1] = mont_mul(a.y, w, fp); v[2] = mont_mul(a.z, w, fp); v[3] = mont_mul(a.w, w, fp);
         }
-        uint32_t* o = tile + rho * NTT_TS + 4 * g4;
+        if (!FIRST && b == 0) {
+            const uint32_t K = nat_kacc(ps, (uint32_t)high);
+            for (int rho = threadIdx.x; rho < R; rho += T)           // indexed by tile row: consecutive words for a warp's 4 rows
+                rowtw[rho] = pow_lookup(ps.tw, (K * bitrev_bits((uint32_t)rho, R_LOG)) << ps.lo, fp);
+            __syncthreads();
+        }
 #pragma unroll
-        for (int k = 0; k < 4; k++) o[k] = v[k];
+        for (int u = 0; u < 4; u++) {
+            const int i = threadIdx.x + (b + u) * T;
+            const int g4 = i & 7, rho = i >> 3;
+            uint32_t v[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
+            if (FIRST) {
+                const size_t g = gbase + ((size_t)bitrev_bits((uint32_t)rho, R_LOG) << ps.lo) + 4 * g4;
+                if (ps.has_scale && g < ps.src_len) {      // one look-up, then walk base^(g+k) (the table ends at src_len)
+                    uint32_t sc = pow_lookup(ps.scale, (uint32_t)g, fp);
+                    const uint32_t step = __ldg(ps.scale.lo + 1);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { v[k] = mont_mul(v[k], sc, fp); if (k < 3) sc = mont_mul(sc, step, fp); }
+                }
+            } else {
+                const uint32_t w = rowtw[rho];
+#pragma unroll
+                for (int k = 0; k < 4; k++) v[k] = mont_mul(v[k], w, fp);
+            }
+            uint32_t* o = tile + rho * NTT_TS + 4 * g4;
+#pragma unroll
+            for (int k = 0; k < 4; k++) o[k] = v[k];
+        }
     }
     __syncthreads();
 
@@ -474,23 +521,44 @@ __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat
     const uint32_t mid = blockIdx.x & ((1u << mid_bits) - 1u);
     const uint32_t k1_0 = (blockIdx.x >> mid_bits) * NTT_C;
     const uint32_t K0 = nat_kacc(ps, (k1_0 << mid_bits) | mid);     // K(j) = K0 + j  (k1 is the lowest digit of K)
-    if (threadIdx.x < NTT_C) coltw[threadIdx.x] = pow_lookup(ps.tw, K0 + threadIdx.x, fp);
-    __syncthreads();
-
-    // ---- load: 8 lanes read 128 contiguous bytes of one row; a warp covers 4 values of j ----
-    for (int i = threadIdx.x; i < R * 8; i += blockDim.x) {
-        const int q8 = i & 7, jj = (i >> 3) & 3, rest = i >> 5;
-        const int seg = rest & ((R >> 5) - 1), j = (rest >> (R_LOG - 5)) * 4 + jj;
-        const uint32_t n3 = (uint32_t)seg * 32 + 4 * q8;
-        const size_t row = ((size_t)(k1_0 + j) << mid_bits) | mid;
-        uint4 a = *reinterpret_cast<const uint4*>(ps.src + (row << R_LOG) + n3);
-        const uint32_t step = coltw[j];
-        uint32_t w = pow_lookup(ps.tw, n3 * (K0 + (uint32_t)j), fp);          // W^(n_m K)
-        uint32_t* o = tile + n3 * NTT_TS + j;
-        o[0] = mont_mul(a.x, w, fp); w = mont_mul(w, step, fp);
-        o[NTT_TS] = mont_mul(a.y, w, fp); w = mont_mul(w, step, fp);
-        o[2 * NTT_TS] = mont_mul(a.z, w, fp); w = mont_mul(w, step, fp);
-        o[3 * NTT_TS] = mont_mul(a.w, w, fp);
+    // ---- load: 8 lanes read 128 contiguous bytes of one row; a warp covers 4 values of j.  Data and table loads of
+    // four vectors are in flight together, ahead of the column-twiddle look-up and the first barrier. ----
+    constexpr int T = nat_threads(R_LOG), ITER = (R * 8) / T;
+    static_assert(ITER % 4 == 0, "tile rows x 8 vectors must be a multiple of 4 per thread");
+#pragma unroll 1
+    for (int b = 0; b < ITER; b += 4) {
+        uint4 a[4];
+        uint32_t wl[4], wh[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = threadIdx.x + (b + u) * T;
+            const int q8 = i & 7, jj = (i >> 3) & 3, rest = i >> 5;
+            const int seg = rest & ((R >> 5) - 1), j = (rest >> (R_LOG - 5)) * 4 + jj;
+            const uint32_t n3 = (uint32_t)seg * 32 + 4 * q8;
+            const size_t row = ((size_t)(k1_0 + j) << mid_bits) | mid;
+            a[u] = *reinterpret_cast<const uint4*>(ps.src + (row << R_LOG) + n3);
+            const uint32_t e = n3 * (K0 + (uint32_t)j);                        // W^(n_m K)
+            wl[u] = __ldg(ps.tw.lo + (e & ps.tw.mask));
+            wh[u] = __ldg(ps.tw.hi + (e >> ps.tw.shift));
+        }
+        if (b == 0) {
+            if (threadIdx.x < NTT_C) coltw[threadIdx.x] = pow_lookup(ps.tw, K0 + threadIdx.x, fp);
+            __syncthreads();
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = threadIdx.x + (b + u) * T;
+            const int q8 = i & 7, jj = (i >> 3) & 3, rest = i >> 5;
+            const int seg = rest & ((R >> 5) - 1), j = (rest >> (R_LOG - 5)) * 4 + jj;
+            const uint32_t n3 = (uint32_t)seg * 32 + 4 * q8;
+            const uint32_t step = coltw[j];
+            uint32_t w = mont_mul(wl[u], wh[u], fp);
+            uint32_t* o = tile + n3 * NTT_TS + j;
+            o[0] = mont_mul(a[u].x, w, fp); w = mont_mul(w, step, fp);
+            o[NTT_TS] = mont_mul(a[u].y, w, fp); w = mont_mul(w, step, fp);
+            o[2 * NTT_TS] = mont_mul(a[u].z, w, fp); w = mont_mul(w, step, fp);
+            o[3 * NTT_TS] = mont_mul(a[u].w, w, fp);
+        }
     }
     __syncthreads();
 
@@ -637,7 +705,31 @@ __global__ void lde8_pass_kernel(Lde8Pass ps, FieldParams fp) {
     const unsigned tw_shift = ps.log_rows - ps.lo - R_LOG;
 
     // ---- load: one work item = one row (8 columns) ----
-    for (int i = threadIdx.x; i < 4 * R; i += blockDim.x) {
+    if (!FIRST) {
+        // both rows of a thread (4R rows, 2R threads): data and twiddle-table loads in flight together
+        uint4 a[2], bq[2];
+        uint32_t wl[2], wh[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int i = threadIdx.x + u * 2 * R;
+            const int g = i & 3, t = i >> 2;
+            const uint4* p = reinterpret_cast<const uint4*>(ps.dst + (row_base + ((size_t)t << ps.lo) + g) * 8);
+            a[u] = p[0]; bq[u] = p[1];
+            const uint32_t e = (bitrev_bits((uint32_t)t, R_LOG) * (low0 + (uint32_t)g)) << tw_shift;
+            wl[u] = __ldg(ps.tw.lo + (e & ps.tw.mask));
+            wh[u] = __ldg(ps.tw.hi + (e >> ps.tw.shift));
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int i = threadIdx.x + u * 2 * R;
+            const int g = i & 3, t = i >> 2;
+            const uint32_t tw = mont_mul(wl[u], wh[u], fp);
+            uint32_t* o = tile + t * NTT_TS + g * 8;
+            o[0] = mont_mul(a[u].x, tw, fp); o[1] = mont_mul(a[u].y, tw, fp); o[2] = mont_mul(a[u].z, tw, fp); o[3] = mont_mul(a[u].w, tw, fp);
+            o[4] = mont_mul(bq[u].x, tw, fp); o[5] = mont_mul(bq[u].y, tw, fp); o[6] = mont_mul(bq[u].z, tw, fp); o[7] = mont_mul(bq[u].w, tw, fp);
+        }
+    }
+    for (int i = threadIdx.x; FIRST && i < 4 * R; i += blockDim.x) {
         uint32_t v[8];
         int t, g;
         if (FIRST) {
