@@ -11,7 +11,9 @@
 // inter-pass twiddle per element (two-level table, 2 loads + 1 multiply) and writes the tile back to the
 // addresses it came from.  Decimation-in-time consumes bit-reversed input and produces natural order;
 // decimation-in-frequency is its mirror.  The LDE chain  iNTT(DIF) -> coset scale -> NTT(DIT)  therefore
-// needs no permutation at all; natural->natural entry points add one bit-reversal gather.
+// needs no permutation at all.  Natural->natural entry points of size >= 2^10 use the digit-split transform further
+// down (ntt_natural: strided in-place passes + one transposing pass, no permutation sweep); smaller and batched ones
+// add one bit-reversal gather to the passes above.
 #include "kernels.hpp"
 
 namespace starkb200 {
