@@ -685,8 +685,18 @@ struct Lde8Pass {
     unsigned small_log;
 };
 
+// threads per tile of 2^r rows x 4 row-groups: 2R >> STARK_LDE8_TSHIFT (experiment knob: smaller CTAs = more
+// independent load / butterfly / store phases in flight per SM and a shorter last wave)
+#ifndef STARK_LDE8_TSHIFT
+#define STARK_LDE8_TSHIFT 1
+#endif
+constexpr int lde8_threads(int r_log) {
+    int t = (2 << r_log) >> STARK_LDE8_TSHIFT;
+    return t < 64 ? 64 : (t > 1024 ? 1024 : t);
+}
+
 template <int R_LOG, bool FIRST, bool LAZY>
-__global__ void lde8_pass_kernel(Lde8Pass ps, FieldParams fp) {
+__global__ void __launch_bounds__(lde8_threads(R_LOG), (1536 / lde8_threads(R_LOG) > 24 ? 24 : 1536 / lde8_threads(R_LOG))) lde8_pass_kernel(Lde8Pass ps, FieldParams fp) {
     extern __shared__ uint32_t smem[];
     constexpr int R = 1 << R_LOG;
     uint32_t* tile = smem;                    // [R][33]: word g*8+s of row t
@@ -708,12 +718,16 @@ __global__ void lde8_pass_kernel(Lde8Pass ps, FieldParams fp) {
 
     // ---- load: one work item = one row (8 columns) ----
     if (!FIRST) {
-        // both rows of a thread (4R rows, 2R threads): data and twiddle-table loads in flight together
+        // two rows of a thread at a time: data and twiddle-table loads in flight together
+        constexpr int T = lde8_threads(R_LOG);
+        static_assert((4 * R) % (2 * T) == 0, "rows per thread must be even");
+#pragma unroll 1
+        for (int b = 0; b < 4 * R; b += 2 * T) {
         uint4 a[2], bq[2];
         uint32_t wl[2], wh[2];
 #pragma unroll
         for (int u = 0; u < 2; u++) {
-            const int i = threadIdx.x + u * 2 * R;
+            const int i = b + threadIdx.x + u * T;
             const int g = i & 3, t = i >> 2;
             const uint4* p = reinterpret_cast<const uint4*>(ps.dst + (row_base + ((size_t)t << ps.lo) + g) * 8);
             a[u] = p[0]; bq[u] = p[1];
@@ -723,12 +737,13 @@ __global__ void lde8_pass_kernel(Lde8Pass ps, FieldParams fp) {
         }
 #pragma unroll
         for (int u = 0; u < 2; u++) {
-            const int i = threadIdx.x + u * 2 * R;
+            const int i = b + threadIdx.x + u * T;
             const int g = i & 3, t = i >> 2;
             const uint32_t tw = mont_mul(wl[u], wh[u], fp);
             uint32_t* o = tile + t * NTT_TS + g * 8;
             o[0] = mont_mul(a[u].x, tw, fp); o[1] = mont_mul(a[u].y, tw, fp); o[2] = mont_mul(a[u].z, tw, fp); o[3] = mont_mul(a[u].w, tw, fp);
             o[4] = mont_mul(bq[u].x, tw, fp); o[5] = mont_mul(bq[u].y, tw, fp); o[6] = mont_mul(bq[u].z, tw, fp); o[7] = mont_mul(bq[u].w, tw, fp);
+        }
         }
     }
     for (int i = threadIdx.x; FIRST && i < 4 * R; i += blockDim.x) {
@@ -781,9 +796,7 @@ __global__ void lde8_pass_kernel(Lde8Pass ps, FieldParams fp) {
 template <int R_LOG, bool FIRST, bool LAZY>
 static void launch_lde8_impl(stark_ctx* ctx, const Lde8Pass& ps, size_t tiles) {
     constexpr int R = 1 << R_LOG;
-    int threads = (R * NTT_C) >> 4;
-    if (threads < 64) threads = 64;
-    if (threads > 1024) threads = 1024;
+    const int threads = lde8_threads(R_LOG);
     size_t smem = (size_t)(R * NTT_TS + (R >> 1) + 1) * sizeof(uint32_t);
     auto kern = lde8_pass_kernel<R_LOG, FIRST, LAZY>;
     if (smem > 48 * 1024) STARK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
