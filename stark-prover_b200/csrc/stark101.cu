@@ -150,27 +150,35 @@ static DevBufPtr fibsq_trace_column(stark_ctx* ctx, uint64_t a1, unsigned log_tr
     const size_t T = (size_t)1 << log_trace, rows = T - 1;
     const uint64_t g = ctx->root_of_unity(log_trace);
     // the recurrence is sequential, it stays on the host
-    // (8M dependent steps at 2^23 rows: kept in 32-bit Montgomery form so a step is one Montgomery square on the
-    // dependency chain (~5 ns), not two u128 divisions; a_n^2 is carried over to the next step).  The values are written
-    // as canonical u32 straight into a pinned staging buffer the context keeps, and copied to HBM from there.
+    // (8M dependent steps at 2^23 rows.  Montgomery form with R = 2^64 and no correction on the dependency chain:
+    // REDC(x^2) = hi(x^2) + p - hi(m p) lies in (0, p + 16) for x < 2^33, so a_{n+2} = REDC(a_{n+1}^2) + REDC(a_n^2)
+    // stays below 2^33 unreduced and a step costs mul -> mul -> mulhi -> two adds (~12 cycles) instead of the 32-bit
+    // form's compare/select after both the square and the sum; a_n^2 is carried over from the previous step.  The
+    // canonical value leaves Montgomery form off the chain and is written as u32 straight into the pinned staging buffer
+    // the context keeps.)
     ctx->pin_stage.ensure(T * 4);
     uint32_t* a = static_cast<uint32_t*>(ctx->pin_stage.h);
     {
-        const uint32_t pp = (uint32_t)p, pinv = ctx->fp.pinv;
-        auto mm = [pp, pinv](uint32_t x, uint32_t y) {
-            uint64_t t = (uint64_t)x * y;
-            uint32_t q = (uint32_t)t * pinv, hq = (uint32_t)(((uint64_t)q * pp) >> 32), hi = (uint32_t)(t >> 32);
-            uint32_t r = hi - hq;
-            return hi < hq ? r + pp : r;
+        typedef unsigned __int128 u128;
+        uint64_t pinv = p;                                         // p^-1 mod 2^64 (Newton)
+        for (int i = 0; i < 6; i++) pinv *= 2 - p * pinv;
+        auto redc_sq = [p, pinv](uint64_t x) {                     // x^2 / R, in (0, p + hi(x^2)]
+            u128 t = (u128)x * x;
+            uint64_t m = (uint64_t)t * pinv;
+            return (uint64_t)(t >> 64) + p - (uint64_t)(((u128)m * p) >> 64);
         };
-        uint32_t x0 = ctx->to_mont(1), x1 = ctx->to_mont(a1);
+        auto out = [p, pinv](uint64_t x) {                         // x / R mod p, canonical (x < 2^64)
+            uint64_t m = x * pinv, u = (uint64_t)(((u128)m * p) >> 64);
+            return (uint32_t)(u ? p - u : 0);
+        };
+        auto to_m = [p](uint64_t v) { return (uint64_t)((((u128)(v % p)) << 64) % p); };
+        uint64_t x1 = to_m(a1);
         a[0] = (uint32_t)(1 % p); a[1] = (uint32_t)(a1 % p);
-        uint32_t sq0 = mm(x0, x0);                                 // a_n^2 (Montgomery form)
+        uint64_t sq0 = redc_sq(to_m(1));                           // a_n^2 (Montgomery form, lazily reduced)
         for (size_t i = 2; i < rows; i++) {
-            uint32_t sq1 = mm(x1, x1);
-            uint64_t sum = (uint64_t)sq1 + sq0;
-            uint32_t x2 = (uint32_t)(sum >= p ? sum - p : sum);
-            a[i] = mm(x2, 1u);                                     // out of Montgomery form (off the dependency chain)
+            uint64_t sq1 = redc_sq(x1);
+            uint64_t x2 = sq1 + sq0;                               // < 2p + 32
+            a[i] = out(x2);
             x1 = x2; sq0 = sq1;
         }
         a[rows] = 0;
