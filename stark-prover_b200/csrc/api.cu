@@ -253,14 +253,12 @@ static DevBufPtr evaluate_on_coset(stark_ctx* ctx, const uint32_t* coeffs_padded
     bool unit = (offset % ctx->modulus) == 1;
     ScaleTable st;
     if (!unit) build_scale_table(ctx, offset, 1, log_m, st);
-    if (log_n >= 10) {
+    if (ntt_natural_supported(log_n, coeffs_padded, nullptr, nullptr)) {     // pool blocks are always 16-byte aligned
         // natural -> natural without a permutation sweep; the zero padding above m is never read
         DevBuf work(n * 4, ctx->stream);
         DevBufPtr out = make_buf(n * 4, ctx->stream);
-        if (ntt_natural_supported(log_n, coeffs_padded, work.p, out->p)) {
-            ntt_natural(ctx, coeffs_padded, m, work.as<uint32_t>(), out->as<uint32_t>(), log_n, false, unit ? nullptr : &st.view, nullptr);
-            return out;
-        }
+        ntt_natural(ctx, coeffs_padded, m, work.as<uint32_t>(), out->as<uint32_t>(), log_n, false, unit ? nullptr : &st.view, nullptr);
+        return out;
     }
     DevBuf tmp(m * 4, ctx->stream);
     bitrev_permute(ctx, coeffs_padded, tmp.as<uint32_t>(), log_m, unit ? nullptr : &st.view, true);
@@ -276,7 +274,7 @@ static DevBufPtr interpolate_on_coset(stark_ctx* ctx, const uint32_t* evals, uns
     ScaleTable st;   // c_j = n^-1 * offset^-j * raw_j
     build_scale_table(ctx, h_inv(offset % ctx->modulus, ctx->modulus), h_inv(n % ctx->modulus, ctx->modulus), log_n, st);
     DevBufPtr out = make_buf(n * 4, ctx->stream);
-    if (ntt_natural_supported(log_n, evals, tmp.p, out->p)) {      // three sweeps instead of copy + three + permutation
+    if (ntt_natural_supported(log_n, evals, tmp.p, out->p)) {      // no staging copy, no permutation sweep
         ntt_natural(ctx, evals, n, tmp.as<uint32_t>(), out->as<uint32_t>(), log_n, true, nullptr, &st.view);
         return out;
     }
@@ -292,10 +290,10 @@ static DevBufPtr lde_on_coset(stark_ctx* ctx, const uint32_t* evals, unsigned lo
     size_t n = (size_t)1 << log_n, N = (size_t)1 << log_N;
     uint64_t p = ctx->modulus;
     DevBuf tmp(n * 4, ctx->stream);
-    if (log_blowup == 3 && lde8_supported(log_n)) {
-        DevBuf coef(n * 4, ctx->stream);
-        if (ntt_natural_supported(log_n, evals, tmp.p, coef.p)) {
-            // unscaled coefficients in natural order (three sweeps, no copy), gathered by the blow-up-by-8 transform's first pass
+    if (log_blowup == 3 && lde8_supported(log_n) && ntt_natural_supported(log_n, evals, tmp.p, nullptr)) {
+        {
+            DevBuf coef(n * 4, ctx->stream);
+            // unscaled coefficients in natural order (no staging copy), gathered by the blow-up-by-8 transform's first pass
             ntt_natural(ctx, evals, n, tmp.as<uint32_t>(), coef.as<uint32_t>(), log_n, true, nullptr, nullptr);
             DevBufPtr out8 = make_buf(N * 4, ctx->stream);
             lde8_forward(ctx, coef.as<uint32_t>(), n, false, out8->as<uint32_t>(), log_n,
