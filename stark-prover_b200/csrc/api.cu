@@ -472,6 +472,14 @@ extern "C" int stark_ntt_batch_dev(stark_ctx* ctx, stark_vec* v, unsigned log_m,
     STARK_REQUIRE(log_m <= ctx->two_adicity, "ntt_batch_dev: 2^log_m does not divide p-1");
     size_t batch = v->n / m;
     DevBuf tmp(v->n * 4, ctx->stream);
+    if (ntt_natural_supported(log_m, v->buf->p, tmp.p, v->buf->p) && v->n <= ((size_t)1 << 31)) {
+        // strided passes into tmp, transposing last pass back into v: no permutation sweep, no copy
+        ScaleTable st;
+        if (inverse) build_scale_table(ctx, 1, h_inv(m % ctx->modulus, ctx->modulus), log_m, st);
+        ntt_natural(ctx, v->buf->as<uint32_t>(), v->n, tmp.as<uint32_t>(), v->buf->as<uint32_t>(), log_m, inverse != 0, nullptr,
+                    inverse ? &st.view : nullptr, batch);
+        return ST_OK;
+    }
     if (!inverse) {
         bitrev_permute(ctx, v->buf->as<uint32_t>(), tmp.as<uint32_t>(), log_m, nullptr, false, batch);
         ntt_dit(ctx, tmp.as<uint32_t>(), v->buf->as<uint32_t>(), log_m, 0, nullptr, false, batch);

@@ -65,10 +65,12 @@ void ntt_dit(stark_ctx* ctx, const uint32_t* src, uint32_t* data, unsigned log_n
 void ntt_dif(stark_ctx* ctx, uint32_t* data, unsigned log_n, bool inverse_root, size_t batch = 1);
 // natural -> natural transform of size 2^log_n >= 2^10 with no permutation sweep (ntt.cu): dst = NTT(src zero-padded
 // above src_len), optionally x_j *= in_scale(j) on the way in and X_k *= out_scale(k) on the way out.  `work` is a
-// scratch array of 2^log_n words; src may equal neither work nor dst (it is only read).  All pointers 16-byte aligned.
+// scratch array of 2^log_n words (x batch); src must differ from work and may equal dst (it is consumed by the first pass).
+// All pointers 16-byte aligned.
 bool ntt_natural_supported(unsigned log_n, const void* src, const void* work, const void* dst);
+// batch > 1: `batch` transforms back to back (src_len = batch * 2^log_n, no input scale; out_scale is indexed inside each transform)
 void ntt_natural(stark_ctx* ctx, const uint32_t* src, size_t src_len, uint32_t* work, uint32_t* dst, unsigned log_n,
-                 bool inverse_root, const PowTable* in_scale, const PowTable* out_scale);
+                 bool inverse_root, const PowTable* in_scale, const PowTable* out_scale, size_t batch = 1);
 // column-batched DIF over data[2^log_n rows][2^col_bits columns] (col_bits >= 5): natural rows in, bit-reversed out
 void ntt_dif_columns(stark_ctx* ctx, uint32_t* data, unsigned log_n, unsigned col_bits, bool inverse_root);
 // Blow-up-by-8 forward transform (the LDE / evaluate hot path): dst[8k'+s] = sum_j c_j (base w_N^s)^j w_n^(j k'),

@@ -519,9 +519,15 @@ __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat
     for (int k = threadIdx.x; k < (R >> 1); k += blockDim.x) tws[k] = ps.small[(size_t)k << (ps.small_log - R_LOG)];
 
     // address bits above the digit: [k1][mid]; the tile takes 32 consecutive k1 at one mid
+    // (a batch of transforms: the tiles of one transform are consecutive, src / dst move on by 2^log_n per transform)
     const unsigned high_bits = ps.log_n - R_LOG, mid_bits = high_bits - ps.prev_bits[0];
-    const uint32_t mid = blockIdx.x & ((1u << mid_bits) - 1u);
-    const uint32_t k1_0 = (blockIdx.x >> mid_bits) * NTT_C;
+    const uint32_t tile_in = blockIdx.x & ((1u << (high_bits - 5)) - 1u);
+    {
+        const size_t shift = (size_t)(blockIdx.x >> (high_bits - 5)) << ps.log_n;
+        ps.src += shift; ps.dst += shift;
+    }
+    const uint32_t mid = tile_in & ((1u << mid_bits) - 1u);
+    const uint32_t k1_0 = (tile_in >> mid_bits) * NTT_C;
     const uint32_t K0 = nat_kacc(ps, (k1_0 << mid_bits) | mid);     // K(j) = K0 + j  (k1 is the lowest digit of K)
     // ---- load: 8 lanes read 128 contiguous bytes of one row; a warp covers 4 values of j.  Data and table loads of
     // four vectors are in flight together, ahead of the column-twiddle look-up and the first barrier. ----
@@ -613,14 +619,16 @@ bool ntt_natural_supported(unsigned log_n, const void* src, const void* work, co
 }
 
 void ntt_natural(stark_ctx* ctx, const uint32_t* src, size_t src_len, uint32_t* work, uint32_t* dst, unsigned log_n,
-                 bool inverse_root, const PowTable* in_scale, const PowTable* out_scale) {
+                 bool inverse_root, const PowTable* in_scale, const PowTable* out_scale, size_t batch) {
     check_size(ctx, log_n);
     STARK_REQUIRE(ntt_natural_supported(log_n, src, work, dst), "ntt_natural: size or alignment not supported");
     const TwiddleSet& tws = ctx->twiddles(log_n);
     const size_t n = (size_t)1 << log_n;
-    if (src_len > n) src_len = n;
+    STARK_REQUIRE(batch >= 1 && (batch == 1 || (src_len == n * batch && in_scale == nullptr)) && n * batch <= ((size_t)1 << 31),
+                  "ntt_natural: a batch takes full-length inputs, no input scale and < 2^31 elements");
+    if (batch == 1 && src_len > n) src_len = n;
     std::vector<unsigned> bits = plan_bits(log_n);         // >= 2 digits of 5..9 bits, most significant first
-    KernelTimer kt(ctx, stark_ctx::CAT_NTT, 8.0 * (double)src_len + 8.0 * (double)n);
+    KernelTimer kt(ctx, stark_ctx::CAT_NTT, 8.0 * (double)src_len + 8.0 * (double)n * (double)batch);
     NatPass ps{};
     ps.log_n = log_n;
     ps.tw = inverse_root ? tws.inv() : tws.fwd();
@@ -638,7 +646,7 @@ void ntt_natural(stark_ctx* ctx, const uint32_t* src, size_t src_len, uint32_t* 
         ps.has_scale = first ? (in_scale != nullptr) : (last ? (out_scale != nullptr) : 0);
         if (first && in_scale) ps.scale = *in_scale;
         if (last && out_scale) ps.scale = *out_scale;
-        const size_t tiles = n / ((size_t)NTT_C << r);
+        const size_t tiles = batch * (n / ((size_t)NTT_C << r));      // strided passes: the batch index is just more high address bits
         if (!last) {
             switch (r) {
                 case 5: first ? launch_nat_strided<5, true>(ctx, ps, tiles) : launch_nat_strided<5, false>(ctx, ps, tiles); break;

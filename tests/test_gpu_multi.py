@@ -14,7 +14,7 @@ def _mg():
 
 
 # (5, 37), (3, 37), (9, 38): group counts that are not a multiple of the 32-column tile (found by tools/soak.py)
-@pytest.mark.parametrize("log_m,batch", [(1, 8), (5, 3), (9, 64), (10, 7), (13, 16), (16, 2), (5, 37), (3, 37), (9, 38), (1, 99)])
+@pytest.mark.parametrize("log_m,batch", [(1, 8), (5, 3), (9, 64), (10, 7), (13, 16), (16, 2), (5, 37), (3, 37), (9, 38), (1, 99), (11, 5), (19, 3), (12, 33)])
 def test_ntt_batch(sp, orc, ctx, log_m, batch):
     m = 1 << log_m
     a = orc.synthetic_column(log_m * 10 + batch, m * batch)
