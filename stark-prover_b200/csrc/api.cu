@@ -986,4 +986,31 @@ void api_open_and_send(const stark_tree* t, size_t idx, Channel& ch) {
     ch.send(rec.data() + 8, pl);
 }
 void api_set_error(const std::string& s) { set_error(s); }
+// fri_commit for a polynomial whose evaluations on the FRI domain already exist (the composition polynomial of
+// stark101.cu is computed on the coset): layer 0 is `evals` as it stands -- no second transform, no copy of the
+// coefficients, which are consumed (the folds replace them anyway).  Same messages as stark_fri_commit_dev.
+int api_fri_commit_evaluated(stark_ctx* ctx, DevBufPtr coeffs, size_t n_coeffs, DevBufPtr evals, unsigned log_n, uint64_t offset,
+                             stark_channel* chan, stark_fri** out) {
+    STARK_REQUIRE(log_n <= ctx->two_adicity && log_n <= 30 && n_coeffs <= ((size_t)1 << log_n), "fri: bad sizes");
+    check_offset(ctx, offset);
+    size_t len = 0;
+    if (n_coeffs) {
+        poly_degree(ctx, coeffs->as<uint32_t>(), n_coeffs, ctx->d_result);
+        STARK_CUDA(cudaStreamSynchronize(ctx->stream));
+        len = (size_t)ctx->h_result->degree_plus1;
+    }
+    std::unique_ptr<stark_fri> f(new stark_fri());
+    f->ctx = ctx; f->log_n = log_n; f->offset0 = offset % ctx->modulus;
+    f->cur_log = log_n; f->cur_offset = f->offset0;
+    f->coeffs = std::move(coeffs); f->coeff_len = len;
+    LeafSource src; src.vals = evals->as<uint32_t>();
+    auto t = tree_launch(ctx, evals, (size_t)1 << log_n, src);
+    STARK_CUDA(cudaStreamSynchronize(ctx->stream));
+    tree_take_root(t.get());
+    f->trees.push_back(std::move(t));
+    int rc = fri_commit_loop(f.get(), chan);
+    if (rc != ST_OK) return rc;
+    *out = f.release();
+    return ST_OK;
+}
 }  // namespace starkb200

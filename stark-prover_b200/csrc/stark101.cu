@@ -29,6 +29,8 @@ std::unique_ptr<stark_tree> api_tree_commit(stark_ctx* ctx, DevBufPtr leaves, si
 void api_send_root(Channel& ch, const stark_tree* t);
 void api_open_and_send(const stark_tree* t, size_t idx, Channel& ch);
 void api_set_error(const std::string& s);
+int api_fri_commit_evaluated(stark_ctx* ctx, DevBufPtr coeffs, size_t n_coeffs, DevBufPtr evals, unsigned log_n, uint64_t offset,
+                             stark_channel* chan, stark_fri** out);
 
 struct FibSqDev {
     uint32_t offset;          // w (canonical)
@@ -260,13 +262,12 @@ extern "C" int stark101_prove(stark_ctx* ctx, uint64_t a1, unsigned log_trace, u
         prm.log_trace = log_trace; prm.log_blowup = log_blowup; prm.offset = w; prm.last_value = last_value;
         for (int k = 0; k < 3; k++) STARK_REQUIRE(ch.receive_random_field_element(&prm.alpha[k]), "channel: receive before send");
         // ---- src/composition: CP on the coset, then its coefficients ----
-        DevBuf cp_eval(N * 4, ctx->stream);
-        fibsq_composition(ctx, f_eval->as<uint32_t>(), prm, cp_eval.as<uint32_t>(), 0, N);
-        DevBufPtr cp_coef = api_interpolate_on_coset(ctx, cp_eval.as<uint32_t>(), log_N, w);
-        stark_vec cpv; cpv.ctx = ctx; cpv.buf = cp_coef; cpv.n = N;
-        // ---- src/fri ----
+        DevBufPtr cp_eval = make_buf(N * 4, ctx->stream);
+        fibsq_composition(ctx, f_eval->as<uint32_t>(), prm, cp_eval->as<uint32_t>(), 0, N);
+        DevBufPtr cp_coef = api_interpolate_on_coset(ctx, cp_eval->as<uint32_t>(), log_N, w);
+        // ---- src/fri: CP's evaluations on the coset ARE layer 0 of fri_commit(CP, domain, channel) ----
         stark_fri* fri = nullptr;
-        int rc = stark_fri_commit_dev(ctx, &cpv, log_N, w, chan, &fri);
+        int rc = api_fri_commit_evaluated(ctx, std::move(cp_coef), N, std::move(cp_eval), log_N, w, chan, &fri);
         if (rc != ST_OK) return rc;
         std::unique_ptr<stark_fri> fri_guard(fri);
         // ---- queries ----
