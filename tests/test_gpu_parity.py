@@ -186,6 +186,36 @@ def test_natural_transform_four_digits_2e28(sp, orc, ctx):
     back.free(); cv.free()
 
 
+def test_natural_transform_maximum_size_2e30(sp, orc, ctx):
+    """The largest domain this field has (2-adicity 30; digits 8+8+7+7): a sparse polynomial built on the device,
+    evaluated on the coset, spot-checked with pow(), and interpolated back."""
+    import torch
+    log_n, off = 30, 5
+    n = 1 << log_n
+    terms = {0: 5, 3: P - 1, (1 << 15) + 9: 77, (1 << 22) + 1: 1234567, (1 << 29) + 12345: 42, n - 1: P - 3}
+    t = torch.zeros(n, dtype=torch.int32, device="cuda")
+    for j, v in terms.items():
+        t[j] = v - (1 << 32) if v >= (1 << 31) else v          # the u32 bit pattern
+    torch.cuda.synchronize()
+    cv = ctx.from_device(t.data_ptr(), n)
+    del t
+    torch.cuda.empty_cache()
+    ev = ctx.coset_evaluate_dev(cv, log_n, off)
+    cv.free()
+    w = orc.root_of_unity(log_n)
+    rng = np.random.default_rng(30)
+    for i in [0, 1, 255, 256, n - 1, n // 2, (1 << 23) + 5] + [int(x) for x in rng.integers(0, n, 24)]:
+        x = off * pow(w, i, P) % P
+        assert int(ev.download(i, 1)[0]) == sum(v * pow(x, j, P) for j, v in terms.items()) % P, i
+    back = ctx.coset_interpolate_dev(ev, off)
+    ev.free()
+    for j, v in terms.items():
+        assert int(back.download(j, 1)[0]) == v, j
+    blk = back.download((1 << 29) + 12288, 1 << 12)
+    assert int(blk[12345 - 12288]) == 42 and np.count_nonzero(blk) == 1
+    back.free()
+
+
 def test_coset_domain(sp, orc, ctx):
     for log_n in (0, 1, 7, 13):
         assert np.array_equal(ctx.coset_domain(log_n, 5), orc.coset_domain(5, orc.root_of_unity(log_n), 1 << log_n, P))
