@@ -517,6 +517,35 @@ def test_fold_property_at_full_size(sp, orc, ctx):
         assert orc.merkle_verify(t.root_bytes(), n // 2, idx, int(pr.layer(1, idx, 1)[0]), t.get_authentication_path(idx))
 
 
+def test_fri_maximum_domain_2e30_verifies(sp, orc):
+    """The largest FRI domain this field admits (2^30 points, 28 layers, 2^31 leaves hashed): the verifier
+    (Merkle paths of every layer + fold consistency, fri_verify.rs:12-177 completed) accepts the transcript, and a
+    flipped bit is rejected.  Size-independent property; the CPU oracle does not go this far."""
+    c2 = sp.Context()
+    try:
+        log_n, q = 30, 4
+        coeffs = orc.synthetic_poly_exact_degree(30, 1 << (log_n - 3))
+        ch = sp.Channel(P)
+        pr = sp.fri_commit(c2, coeffs, sp.CosetFri(c2, 5, log_n), ch)
+        assert pr.num_layers == 28 and pr.layer_len(0) == 1 << log_n and pr.layer_len(27) == 8
+        sp.decommit_fri(q, (1 << log_n) - 1, pr, ch)
+        flat = ch.proof_flat()
+        ok, why = sp.verify_fri(flat, log_n, 5, q, (1 << log_n) - 1)
+        assert ok, why
+        bad = bytearray(flat)
+        bad[len(bad) // 2] ^= 0x10
+        ok2, _ = sp.verify_fri(bytes(bad), log_n, 5, q, (1 << log_n) - 1)
+        assert not ok2
+        # layer 0 against the reference's literal Horner evaluation (ops.rs:76-83) at a few points of the coset
+        w = orc.root_of_unity(log_n)
+        for i in (1, (1 << 29) + 3):                 # 2^27 Horner steps each on the host
+            x = 5 * pow(w, i, P) % P
+            assert int(pr.layer(0, i, 1)[0]) == orc.poly_evaluate(coeffs, x, P), i
+        pr.free()
+    finally:
+        c2.close()
+
+
 def test_lde_roundtrip_2e24(sp, orc, ctx):
     """interpolate(evaluate(c)) == c at 2^24 (idempotence), device resident."""
     log_n = 24
