@@ -313,6 +313,8 @@ def run_b200(args):
         return ms, pr, ch
 
     if args.profile_mode:
+        # (main() has set STARK_OPEN_SERVER=0: the resident opening server talks to the host while it runs, which a profiler
+        # that serialises and replays kernels cannot follow; under ncu the queries are one launch each, as before)
         timed(dev_coeffs, args.warmup, flush_l2=False)
         ms, pr, ch = timed(dev_coeffs, args.steps, flush_l2=False)
         print(json.dumps({"profile_mode": True, "ms_per_step_under_profiler": ms, "launches": ctx.launch_count}), flush=True)
@@ -459,6 +461,8 @@ def run_b200(args):
 
 def main():
     args = parse()
+    if args.profile_mode:
+        os.environ["STARK_OPEN_SERVER"] = "0"       # read once by the library when the first decommit runs
     if args.impl == "reference":
         run_reference(args)
     else:

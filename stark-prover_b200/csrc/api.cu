@@ -1,9 +1,11 @@
 // api.cu — the extern "C" boundary declared in include/stark_b200.h.
 // Everything here is host orchestration: argument checks, HBM allocation, kernel sequencing on the
 // context's stream, and the one sync per commitment that hands a root to the (host) Channel.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 
 #include "../../include/stark_b200.h"
 #include "handles.hpp"
@@ -952,9 +954,95 @@ extern "C" int stark_decommit_fri_layers(const stark_fri* f, size_t index, stark
     send_query_records(f, rec, ch->ch, index);
     API_END
 }
+// A run of queries on one proof through the resident opening server (merkle.cu): no launch and no stream
+// synchronisation per query, one 64-bit word each way in mapped pinned memory.
+#ifndef STARK_OPEN_SERVER
+#define STARK_OPEN_SERVER 1
+#endif
+struct FriOpenServer {
+    stark_ctx* ctx = nullptr;
+    FriServerBox* h_box = nullptr;
+    unsigned long long seq = 0;
+    bool running = false;
+    static bool usable(const stark_fri* f) {
+        // STARK_OPEN_SERVER=0 in the environment: one launch per query instead (a kernel that talks to the host cannot be
+        // replayed by a profiler; bench.py --profile-mode sets it)
+        static const bool enabled = [] { const char* e = getenv("STARK_OPEN_SERVER"); return STARK_OPEN_SERVER && !(e && e[0] == '0'); }();
+        if (!enabled || f->trees.empty() || f->trees.size() > (size_t)FRI_MAX_LAYERS) return false;
+        const size_t n0 = f->trees[0]->shape.n;
+        if (n0 > ((size_t)1 << 32)) return false;
+        for (auto& t : f->trees)
+            if (t->external || t->shape.n == 0 || n0 % t->shape.n != 0) return false;
+        return true;
+    }
+    void start(const stark_fri* f) {
+        ctx = f->ctx;
+        FriOpenArgs a{};
+        size_t cap = 0;
+        for (size_t k = 0; k < f->trees.size(); k++) {
+            const stark_tree* t = f->trees[k].get();
+            a.layers[k] = FriLayerDesc{t->leaves->as<uint32_t>(), t->nodes.as<uint32_t>(), t->shape.n};
+            cap += 2 * (8 + 32 * (size_t)t->shape.depth);
+        }
+        a.n_layers = (unsigned)f->trees.size(); a.first = 0;
+        ctx->pin_out.ensure(cap);
+        ctx->pin_desc.ensure(sizeof(FriServerBox));
+        a.out = static_cast<uint8_t*>(ctx->pin_out.d);
+        h_box = static_cast<FriServerBox*>(ctx->pin_desc.h);
+        __atomic_store_n(&h_box->req, 0ull, __ATOMIC_RELEASE);
+        __atomic_store_n(&h_box->done, 0ull, __ATOMIC_RELEASE);
+        fri_open_server_launch(ctx, a, static_cast<FriServerBox*>(ctx->pin_desc.d), 2000000000ull);
+        running = true;
+    }
+    const uint8_t* open(size_t index0, size_t* total) {
+        seq++;
+        __atomic_store_n(&h_box->req, (seq << 32) | (unsigned long long)index0, __ATOMIC_RELEASE);
+        const auto t0 = std::chrono::steady_clock::now();
+        unsigned long long d;
+        for (unsigned spin = 0;; spin++) {
+            d = __atomic_load_n(&h_box->done, __ATOMIC_ACQUIRE);
+            if ((d >> 32) == seq) break;
+            if ((spin & 0xfffu) == 0xfffu) {
+                // the kernel leaves by itself after 2 s without a request (a descheduled host thread): the caller falls
+                // back to one launch per query
+                if (cudaStreamQuery(ctx->stream) != cudaErrorNotReady) { running = false; STARK_CUDA(cudaStreamSynchronize(ctx->stream)); return nullptr; }
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5)) { stop(); throw StarkError(ST_CUDA, "opening server timed out"); }
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        *total = (size_t)(d & 0xffffffffull);
+        return static_cast<const uint8_t*>(ctx->pin_out.h);
+    }
+    void stop() {
+        if (!running) return;
+        running = false;
+        __atomic_store_n(&h_box->req, ~0ull, __ATOMIC_RELEASE);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    ~FriOpenServer() { stop(); }
+};
 extern "C" int stark_decommit_fri(const stark_fri* f, size_t num_queries, size_t max_index, stark_channel* ch) {
     API_BEGIN
     STARK_REQUIRE(f && ch, "decommit_fri: null argument");
+    if (num_queries >= 2 && FriOpenServer::usable(f)) {
+        CtxGuard g(f->ctx);
+        FriOpenServer srv;
+        srv.start(f);
+        const size_t n0 = f->trees[0]->shape.n;
+        for (size_t q = 0; q < num_queries; q++) {                           // :175-178
+            uint64_t idx;
+            STARK_REQUIRE(ch->ch.receive_random_int(0, max_index, true, &idx), "channel: receive before send");
+            size_t total = 0;
+            const uint8_t* rec = srv.running ? srv.open((size_t)idx % n0, &total) : nullptr;   // every layer length divides n0
+            if (!rec) rec = open_one_index(f, (size_t)idx, &total);
+            send_query_records(f, rec, ch->ch, (size_t)idx);
+        }
+        srv.stop();
+        STARK_CUDA(cudaGetLastError());
+        return ST_OK;
+    }
     for (size_t q = 0; q < num_queries; q++) {                               // :175-178
         uint64_t idx;
         STARK_REQUIRE(ch->ch.receive_random_int(0, max_index, true, &idx), "channel: receive before send");

@@ -52,6 +52,11 @@ struct FriOpenArgs {
     uint32_t rec_off[2 * FRI_MAX_LAYERS];   // byte offset of record r = 2*(layer - first) + (0: idx, 1: sibling), from the host
 };
 void fri_open_one(stark_ctx* ctx, const FriOpenArgs& a);
+// Resident opening server for a run of queries on one proof (merkle.cu): `req` = (sequence << 32) | index posted by the
+// host, `done` = (sequence << 32) | bytes written by the device; both live in mapped pinned host memory.  a.index and
+// a.rec_off are unused (the device computes the record offsets).  Every layer length must divide the first one's.
+struct FriServerBox { unsigned long long req; unsigned long long done; };
+void fri_open_server_launch(stark_ctx* ctx, const FriOpenArgs& a, FriServerBox* d_box, unsigned long long idle_ns);
 // host-side: bytes of the path of leaf idx in a tree of n leaves (32 per level that has a sibling)
 size_t merkle_path_len(size_t n, size_t idx);
 

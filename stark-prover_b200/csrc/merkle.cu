@@ -442,6 +442,110 @@ void fri_open_one(stark_ctx* ctx, const FriOpenArgs& a) {
     STARK_CUDA(cudaGetLastError());
 }
 
+// ---- opening server: decommit_fri draws every query index from the transcript state left by the previous query's
+// messages (fri_commit.rs:168-179), so the openings are a chain of host <-> device round trips.  One resident CTA
+// replaces the launch + stream synchronisation per query: the host posts (sequence, index) as ONE 64-bit word in mapped
+// pinned memory, thread 0 polls it, the CTA writes the records of all layers straight into the mapped output buffer
+// and answers with (sequence, bytes) after one system-scope fence.  Geometry per record is computed on the device
+// (sibling-exists mask per level, prefix sum of the record sizes); the sibling-leaf digests of all records are hashed
+// by neighbouring threads in lock step.  The kernel leaves when the host posts ~0 or nothing arrives for `idle_ns`.
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__global__ void __launch_bounds__(1024, 1) fri_open_server_kernel(FriOpenArgs a, FriServerBox* box, unsigned long long idle_ns) {
+    __shared__ unsigned long long s_req;
+    __shared__ uint32_t s_off[2 * FRI_MAX_LAYERS + 1], s_mask[2 * FRI_MAX_LAYERS];
+    const unsigned n_rec = 2 * (a.n_layers - a.first);
+    for (unsigned long long seq = 1;; seq++) {
+        if (threadIdx.x == 0) {
+            const unsigned long long t0 = global_timer_ns();
+            unsigned long long r;
+            for (;;) {
+                r = ld_sys_u64(&box->req);
+                if ((r >> 32) == seq || r == ~0ull) break;
+                if (global_timer_ns() - t0 > idle_ns) { r = ~0ull; break; }
+            }
+            s_req = r;
+        }
+        __syncthreads();
+        const unsigned long long req = s_req;
+        if (req == ~0ull) return;
+        const unsigned long long index = req & 0xffffffffull;
+        // record geometry: which levels have a sibling, and the record's size
+        if (threadIdx.x < n_rec) {
+            const FriLayerDesc& L = a.layers[a.first + threadIdx.x / 2];
+            unsigned long long idx = index % L.n;
+            if (threadIdx.x & 1) idx = (idx + L.n / 2) % L.n;
+            uint32_t mask = 0;
+            unsigned l = 0;
+            for (unsigned long long m = L.n, j = idx; m > 1; m = (m + 1) >> 1, j >>= 1, l++)
+                if ((j ^ 1ull) < m) mask |= 1u << l;
+            s_mask[threadIdx.x] = mask;
+            s_off[threadIdx.x + 1] = 8u + 32u * (unsigned)__popc(mask);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_off[0] = 0;
+            for (unsigned r = 0; r < n_rec; r++) s_off[r + 1] += s_off[r];
+        }
+        __syncthreads();
+        // value + level-0 sibling digest: one thread per record
+        if (threadIdx.x < n_rec) {
+            const FriLayerDesc& L = a.layers[a.first + threadIdx.x / 2];
+            unsigned long long idx = index % L.n;
+            if (threadIdx.x & 1) idx = (idx + L.n / 2) % L.n;
+            uint32_t* rec = reinterpret_cast<uint32_t*>(a.out + s_off[threadIdx.x]);
+            rec[0] = 0;
+            rec[1] = __byte_perm(L.vals[idx], 0, 0x0123);
+            if (s_mask[threadIdx.x] & 1u) {
+                Digest dg;
+                sha256_leaf32(L.vals[idx ^ 1ull], dg);
+#pragma unroll
+                for (int i = 0; i < 8; i++) rec[2 + i] = __byte_perm(dg.w[i], 0, 0x0123);
+            }
+        }
+        // stored levels: one thread per (record, level >= 1)
+        for (unsigned item = threadIdx.x; item < n_rec * 32; item += blockDim.x) {
+            const unsigned r = item >> 5, l = item & 31;
+            const uint32_t mask = s_mask[r];
+            if (l == 0 || !((mask >> l) & 1u)) continue;
+            const FriLayerDesc& L = a.layers[a.first + r / 2];
+            unsigned long long idx = index % L.n;
+            if (r & 1) idx = (idx + L.n / 2) % L.n;
+            unsigned long long len_l = L.n, off_l = 0;
+            for (unsigned m = 0; m < l; m++) {
+                if (m >= 1) off_l += len_l;
+                len_l = (len_l + 1) >> 1;
+            }
+            const unsigned long long j = (idx >> l) ^ 1ull;
+            const Digest dg = load_digest(L.nodes + 8 * (off_l + j));
+            uint32_t* o = reinterpret_cast<uint32_t*>(a.out + s_off[r]) + 2 + 8 * __popc(mask & ((1u << l) - 1u));
+#pragma unroll
+            for (int i = 0; i < 8; i++) o[i] = __byte_perm(dg.w[i], 0, 0x0123);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            st_sys_u64(&box->done, (seq << 32) | s_off[n_rec]);
+        }
+    }
+}
+void fri_open_server_launch(stark_ctx* ctx, const FriOpenArgs& a, FriServerBox* d_box, unsigned long long idle_ns) {
+    fri_open_server_kernel<<<1, 1024, 0, ctx->stream>>>(a, d_box, idle_ns);
+    ctx->launches++;
+    STARK_CUDA(cudaGetLastError());
+}
+
 void merkle_open(stark_ctx* ctx, const OpenDesc* d_desc, size_t n_desc, uint8_t* d_out) {
     if (n_desc == 0) return;
     unsigned blocks = (unsigned)((n_desc * 32 + 127) / 128);
