@@ -964,6 +964,9 @@ struct FriOpenServer {
     FriServerBox* h_box = nullptr;
     unsigned long long seq = 0;
     bool running = false;
+    // the kernel gives up after this long without a request (a descheduled host thread, or a profiler that runs the launch
+    // to completion before the host may post anything); open() then reports it and the caller launches per query
+    static constexpr unsigned long long kIdleNs = 250000000ull;
     static bool usable(const stark_fri* f) {
         // STARK_OPEN_SERVER=0 in the environment: one launch per query instead (a kernel that talks to the host cannot be
         // replayed by a profiler; bench.py --profile-mode sets it)
@@ -991,7 +994,7 @@ struct FriOpenServer {
         h_box = static_cast<FriServerBox*>(ctx->pin_desc.h);
         __atomic_store_n(&h_box->req, 0ull, __ATOMIC_RELEASE);
         __atomic_store_n(&h_box->done, 0ull, __ATOMIC_RELEASE);
-        fri_open_server_launch(ctx, a, static_cast<FriServerBox*>(ctx->pin_desc.d), 2000000000ull);
+        fri_open_server_launch(ctx, a, static_cast<FriServerBox*>(ctx->pin_desc.d), kIdleNs);
         running = true;
     }
     const uint8_t* open(size_t index0, size_t* total) {
@@ -1003,8 +1006,6 @@ struct FriOpenServer {
             d = __atomic_load_n(&h_box->done, __ATOMIC_ACQUIRE);
             if ((d >> 32) == seq) break;
             if ((spin & 0xfffu) == 0xfffu) {
-                // the kernel leaves by itself after 2 s without a request (a descheduled host thread): the caller falls
-                // back to one launch per query
                 if (cudaStreamQuery(ctx->stream) != cudaErrorNotReady) { running = false; STARK_CUDA(cudaStreamSynchronize(ctx->stream)); return nullptr; }
                 if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5)) { stop(); throw StarkError(ST_CUDA, "opening server timed out"); }
             }
