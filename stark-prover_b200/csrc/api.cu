@@ -994,7 +994,9 @@ struct FriOpenServer {
         h_box = static_cast<FriServerBox*>(ctx->pin_desc.h);
         __atomic_store_n(&h_box->req, 0ull, __ATOMIC_RELEASE);
         __atomic_store_n(&h_box->done, 0ull, __ATOMIC_RELEASE);
-        fri_open_server_launch(ctx, a, static_cast<FriServerBox*>(ctx->pin_desc.d), kIdleNs);
+        unsigned long long idle = kIdleNs;
+        if (const char* e = getenv("STARK_OPEN_SERVER_IDLE_NS")) { unsigned long long v = strtoull(e, nullptr, 10); if (v) idle = v; }   // tests
+        fri_open_server_launch(ctx, a, static_cast<FriServerBox*>(ctx->pin_desc.d), idle);
         running = true;
     }
     const uint8_t* open(size_t index0, size_t* total) {

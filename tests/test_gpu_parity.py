@@ -388,6 +388,26 @@ def test_fri_batched_open_matches_sequential(sp, orc, ctx):
     assert off == len(blob)
 
 
+def test_opening_server_falls_back_when_it_times_out(sp, orc, ctx, monkeypatch):
+    """decommit_fri runs its queries through a resident kernel that gives up when no request arrives in time; the host
+    must then finish with one launch per query and produce the same transcript.  A 1 us idle limit forces the hand-over."""
+    log_n, q = 14, 6
+    coeffs = orc.synthetic_poly_exact_degree(77, 1 << (log_n - 3))
+    och = orc.Channel(P)
+    opr = orc.fri_commit_fast(coeffs, log_n, 5, orc.root_of_unity(log_n), och, P)
+    orc.decommit_fri(q, (1 << log_n) - 1, opr, och)
+    for idle in ("1000", None):
+        if idle is None:
+            monkeypatch.delenv("STARK_OPEN_SERVER_IDLE_NS", raising=False)
+        else:
+            monkeypatch.setenv("STARK_OPEN_SERVER_IDLE_NS", idle)
+        ch = sp.Channel(P)
+        pr = sp.fri_commit(ctx, coeffs, sp.CosetFri(ctx, 5, log_n), ch)
+        sp.decommit_fri(q, (1 << log_n) - 1, pr, ch)
+        assert ch.state == och.state and ch.proof == och.proof, idle
+        pr.free()
+
+
 def test_fri_device_resident_input(sp, orc, ctx):
     log_n = 14
     c = orc.synthetic_poly_exact_degree(8, 1 << 11)
