@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 #if defined(__x86_64__)
@@ -33,6 +34,17 @@ class HostSha256 {
         for (int i = 0; i < 8; i++) tail[tl - 1 - i] = (uint8_t)(bits >> (8 * i));
         ni ? block_ni(st, tail) : block(st, tail);
         if (tl == 128) ni ? block_ni(st, tail + 64) : block(st, tail + 64);
+        for (int i = 0; i < 8; i++) {
+            out[4 * i] = (uint8_t)(st[i] >> 24); out[4 * i + 1] = (uint8_t)(st[i] >> 16);
+            out[4 * i + 2] = (uint8_t)(st[i] >> 8); out[4 * i + 3] = (uint8_t)st[i];
+        }
+    }
+    // nblk whole blocks that already carry their padding (Channel::send builds state || hex(msg) || padding in one
+    // buffer): one multi-block call, so the state never leaves the registers between the blocks of a message
+    static void digest_padded(const uint8_t* blocks, size_t nblk, uint8_t out[32]) {
+        uint32_t st[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+        if (have_sha_ni()) blocks_ni(st, blocks, nblk);
+        else for (size_t i = 0; i < nblk; i++) block(st, blocks + 64 * i);
         for (int i = 0; i < 8; i++) {
             out[4 * i] = (uint8_t)(st[i] >> 24); out[4 * i + 1] = (uint8_t)(st[i] >> 16);
             out[4 * i + 2] = (uint8_t)(st[i] >> 8); out[4 * i + 3] = (uint8_t)st[i];
@@ -219,10 +231,37 @@ inline void be8(uint64_t v, uint8_t out[8]) {            // FieldElement::to_byt
 
 // Vec<Vec<u8>> as one byte arena plus spans: a query appends ~90 messages, and a heap block per message costs more
 // than hashing the short ones.
+// The arena of a finished transcript goes back to a small pool and the next Channel starts on it: a proof logs ~0.6 MB,
+// and first-touch page faults on a fresh block every proof cost more than copying the bytes.
 struct MessageLog {
     std::vector<uint8_t> bytes;
     std::vector<std::pair<size_t, size_t>> spans;         // (offset, length)
+    MessageLog() = default;
+    MessageLog(const MessageLog&) = default;
+    MessageLog& operator=(const MessageLog&) = default;
+    MessageLog(MessageLog&&) = default;
+    MessageLog& operator=(MessageLog&&) = default;
+    ~MessageLog() { recycle(&bytes, false); }
+    // take == true: hands out a pooled arena (empty, capacity kept) if there is one; false: gives one back
+    static void recycle(std::vector<uint8_t>* v, bool take) {
+        static std::mutex mu;
+        static std::vector<std::vector<uint8_t>> pool;
+        std::lock_guard<std::mutex> g(mu);
+        if (take) {
+            if (!pool.empty()) { *v = std::move(pool.back()); pool.pop_back(); v->clear(); }
+        } else if (v->capacity() >= ((size_t)1 << 16) && v->capacity() <= ((size_t)64 << 20) && pool.size() < 8) {
+            pool.push_back(std::move(*v));
+        }
+    }
     void push(const uint8_t* p, size_t n) {
+        if (bytes.capacity() == 0) recycle(&bytes, true);
+        if (spans.size() == spans.capacity()) spans.reserve(spans.empty() ? 4096 : 2 * spans.size());
+        if (bytes.size() + n > bytes.capacity()) {           // a query appends ~20 KB: grow in big steps, few re-copies
+            size_t want = 2 * bytes.capacity();
+            if (want < bytes.size() + n) want = bytes.size() + n;
+            if (want < ((size_t)1 << 20)) want = (size_t)1 << 20;
+            bytes.reserve(want);
+        }
         spans.emplace_back(bytes.size(), n);
         bytes.insert(bytes.end(), p, p + n);
     }
@@ -238,21 +277,27 @@ struct Channel {
     std::vector<size_t> compressed_idx;                    // :17 compressed_proof: the same bytes as proof[i], stored once
     std::string state;                                     // :19, "" initially (:24-30)
     uint64_t modulus;
+    std::vector<uint8_t> scratch;                          // state || hex(message) || padding of the send in flight
 
     explicit Channel(uint64_t m) : modulus(m) {}
 
     void send(const uint8_t* msg, size_t len) {            // :35-44
-        // state = sha256::digest(old_state + hex::encode(message)), streamed in 2 KB pieces of hex text
-        HostSha256::Stream h;
-        h.update(reinterpret_cast<const uint8_t*>(state.data()), state.size());
-        char hx[2048];
-        for (size_t off = 0; off < len; off += 1024) {
-            size_t take = len - off < 1024 ? len - off : 1024;
-            HostSha256::hex_into(msg + off, take, hx);
-            h.update(reinterpret_cast<const uint8_t*>(hx), 2 * take);
-        }
+        // state = sha256::digest(old_state + hex::encode(message)): the text and its padding are laid out in one scratch
+        // buffer and hashed by ONE multi-block call, so the hash state stays in registers from the first block of a
+        // message to its last (a query sends ~90 messages of 2 .. 26 blocks; per-message set-up was a third of the time)
+        const size_t sl = state.size();                    // 0 before the first send, 64 afterwards
+        const size_t body = sl + 2 * len;
+        const size_t total = ((body + 9 + 63) / 64) * 64;
+        if (scratch.size() < total) scratch.resize(total < 4096 ? 4096 : total);
+        uint8_t* b = scratch.data();
+        memcpy(b, state.data(), sl);
+        HostSha256::hex_into(msg, len, reinterpret_cast<char*>(b + sl));
+        memset(b + body, 0, total - body);
+        b[body] = 0x80;
+        const uint64_t bits = (uint64_t)body * 8;
+        for (int i = 0; i < 8; i++) b[total - 1 - i] = (uint8_t)(bits >> (8 * i));
         uint8_t dg[32];
-        h.finish(dg);
+        HostSha256::digest_padded(b, total / 64, dg);
         state.resize(64);
         HostSha256::hex_into(dg, 32, &state[0]);
         proof.push(msg, len);
