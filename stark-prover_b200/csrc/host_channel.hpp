@@ -249,7 +249,7 @@ struct MessageLog {
         std::lock_guard<std::mutex> g(mu);
         if (take) {
             if (!pool.empty()) { *v = std::move(pool.back()); pool.pop_back(); v->clear(); }
-        } else if (v->capacity() >= ((size_t)1 << 16) && v->capacity() <= ((size_t)64 << 20) && pool.size() < 8) {
+        } else if (v->capacity() >= ((size_t)1 << 16) && v->capacity() <= ((size_t)8 << 20) && pool.size() < 8) {
             pool.push_back(std::move(*v));
         }
     }
