@@ -88,6 +88,25 @@ def test_host_channel_matches_oracle(sp, orc, golden):
     assert a.compressed_proof == b.compressed_proof
 
 
+def test_host_channel_block_boundaries_and_reuse(sp):
+    """Channel::send lays state || hex(message) || padding out in one buffer and hashes it in one call: every message
+    length around the 64-byte block boundaries (with and without a previous state), long messages, and transcripts that
+    reuse a recycled log arena, against hashlib (sha256 1.5.0 `digest` of the concatenated text, channel.rs:35-44)."""
+    import hashlib
+    lens = list(range(0, 70)) + [95, 96, 97, 127, 128, 129, 991, 992, 993, 1023, 1024, 1025, 5000, 70001]
+    for rnd in range(3):                       # later rounds start on an arena returned by the previous Channel
+        ch = sp.Channel(P)
+        state = ""
+        for n in lens:
+            m = bytes((7 * n + 3 * i + rnd) & 255 for i in range(n))
+            ch.send(m)
+            state = hashlib.sha256((state + m.hex()).encode()).hexdigest()
+            assert ch.state == state, (rnd, n)
+        assert ch.proof == [bytes((7 * n + 3 * i + rnd) & 255 for i in range(n)) for n in lens]
+        assert ch.proof_size() == sum(lens)
+        del ch
+
+
 def test_channel_receive_before_send_is_error(sp):
     ch = sp.Channel(P)
     with pytest.raises(sp.StarkError):
