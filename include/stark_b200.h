@@ -231,10 +231,17 @@ int stark_decommit_fri(const stark_fri* f, size_t num_queries, size_t max_index,
 int stark_merkle_verify(const uint8_t root[32], size_t n_leaves, size_t idx, uint64_t value, const uint8_t* path,
                         size_t path_len, int* ok);
 int stark_fri_verify(const uint8_t* proof_flat, size_t proof_len, uint64_t modulus, uint64_t generator, unsigned log_n,
-                     uint64_t offset, size_t num_queries, size_t max_index, int* ok, char* reason);
-/* Verifier of stark101_prove's transcript; public input = the claimed a_{T-2}.  Adds to the FRI checks: the three
- * trace openings per query authenticate against the trace root and layer 0 of the FRI equals the composition
- * polynomial computed from them. */
+                     uint64_t offset, size_t num_queries, size_t max_index, unsigned log_degree_bound, int* ok, char* reason);
+/* log_degree_bound: the committed polynomial is claimed to have at most 2^log_degree_bound coefficients (<= 2^log_n);
+ * a proof with more than log_degree_bound folds is rejected -- the layer count is the prover's choice, and without this
+ * cap any function folds down to a one-point layer that trivially "equals the final constant"
+ * (`expected_num_layers`, fri_verify.rs:15).
+ *
+ * Verifier of stark101_prove's transcript; public input = the claimed a_{T-2}.  The transcript opens with the statement
+ * (modulus, generator, log_trace, log_blowup, num_queries, claimed a_{T-2}: 8 big-endian bytes each) so that every
+ * challenge depends on it.  Adds to the FRI checks: the degree bound 2^log_trace that the statement implies for the
+ * composition polynomial, the three trace openings per query authenticate against the trace root, and layer 0 of the
+ * FRI equals the composition polynomial computed from them. */
 int stark101_verify(const uint8_t* proof_flat, size_t proof_len, uint64_t modulus, uint64_t generator, uint64_t claimed_last,
                     unsigned log_trace, unsigned log_blowup, size_t num_queries, int* ok, char* reason);
 

@@ -810,6 +810,12 @@ int or_stark101_prove(uint64_t a1, unsigned log_trace, unsigned log_blowup, uint
     if (literal) { for (size_t i = 0; i < N; i++) fe[i] = or_poly_evaluate(f, fl, D[i], M); }
     else or_coset_evaluate(f, fl, log_N, w, h, fe, M);
     or_tree* ft = or_merkle_new(fe, N);
+    {   /* the statement opens the transcript: modulus, generator, sizes, query count, claimed a_{T-2} (8 BE bytes each) */
+        uint8_t stmt[48];
+        or_fe_to_bytes(M, stmt); or_fe_to_bytes(or_fe_new(generator, M), stmt + 8); or_fe_to_bytes(log_trace, stmt + 16);
+        or_fe_to_bytes(log_blowup, stmt + 24); or_fe_to_bytes((uint64_t)num_queries, stmt + 32); or_fe_to_bytes(a[rows - 1], stmt + 40);
+        or_channel_send(ch, stmt, 48);
+    }
     send_root(ch, ft);
     uint64_t al[3];
     for (int k = 0; k < 3; k++) al[k] = or_channel_receive_random_field_element(ch);

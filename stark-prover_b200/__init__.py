@@ -140,7 +140,7 @@ def lib() -> C.CDLL:
     sig("stark101_trace_poly", I, vp, u64, C.c_uint, C.POINTER(vp), C.POINTER(u64))
     sig("stark101_composition_range", I, vp, vp, szt, szt, C.POINTER(u64), u64, C.c_uint, C.c_uint, C.POINTER(vp))
     sig("stark_merkle_verify", I, vp, szt, szt, u64, vp, szt, C.POINTER(I))
-    sig("stark_fri_verify", I, vp, szt, u64, u64, C.c_uint, u64, szt, szt, C.POINTER(I), C.c_char_p)
+    sig("stark_fri_verify", I, vp, szt, u64, u64, C.c_uint, u64, szt, szt, C.c_uint, C.POINTER(I), C.c_char_p)
     sig("stark101_verify", I, vp, szt, u64, u64, u64, C.c_uint, C.c_uint, szt, C.POINTER(I), C.c_char_p)
     _lib = L
     return L
@@ -637,13 +637,21 @@ def merkle_validate(root: bytes, n_leaves: int, idx: int, value: int, path: byte
     return bool(ok.value)
 
 
-def verify_fri(proof_flat: bytes, log_n: int, offset: int, num_queries: int, max_index: int, modulus: int = P_DEFAULT,
-               generator: int = G_DEFAULT) -> tuple[bool, str]:
-    """verify_fri (src/fri/fri_verify.rs:12-177, completed): replays a flattened proof; host side, no GPU needed."""
+def verify_fri(proof_flat: bytes, log_n: int, offset: int, num_queries: int, max_index: int, log_degree_bound: int,
+               modulus: int = P_DEFAULT, generator: int = G_DEFAULT) -> tuple[bool, str]:
+    """verify_fri (src/fri/fri_verify.rs:12-177, completed): replays a flattened proof; host side, no GPU needed.
+    `log_degree_bound`: the committed polynomial is claimed to have at most 2^log_degree_bound coefficients, so the
+    proof may hold at most that many folds (the reference's `expected_num_layers`, fri_verify.rs:15)."""
     buf = np.frombuffer(proof_flat, dtype=np.uint8).copy()
     ok, reason = C.c_int(0), C.create_string_buffer(160)
-    _check(lib().stark_fri_verify(_ptr(buf), buf.size, modulus, generator, log_n, offset, num_queries, max_index, C.byref(ok), reason))
+    _check(lib().stark_fri_verify(_ptr(buf), buf.size, modulus, generator, log_n, offset, num_queries, max_index, log_degree_bound,
+                                  C.byref(ok), reason))
     return bool(ok.value), reason.value.decode()
+
+
+def stark101_statement(modulus: int, generator: int, log_trace: int, log_blowup: int, num_queries: int, claimed_last: int) -> bytes:
+    """First transcript message of the FibonacciSq STARK: the public inputs, 8 big-endian bytes each."""
+    return b"".join(int(v).to_bytes(8, "big") for v in (modulus, generator % modulus, log_trace, log_blowup, num_queries, claimed_last % modulus))
 
 
 def stark101_verify(proof_flat: bytes, claimed_last: int, log_trace: int = 10, log_blowup: int = 3, num_queries: int = 3,

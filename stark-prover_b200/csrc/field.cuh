@@ -16,6 +16,94 @@ struct FieldParams {
     uint32_t one;    // 2^32 mod p  (1 in Montgomery form)
 };
 
+// ---- conditional corrections --------------------------------------------------------------------------------
+// Every modular add / subtract / Montgomery product ends in "add or subtract p if the 32-bit result went the wrong
+// way".  Written as compare + select + add that is three instructions on the ALU pipe, the contended one (the
+// rotates and boolean functions of SHA-256 and the compares of these corrections only run there).  The forms below
+// take the carry-out of the add / subtract itself as the predicate (IADD3 Rd, P0, ...) and apply the correction as a
+// predicated multiply-add on the FMA pipe (`one` is a 1 the compiler cannot see through, so it stays an IMAD):
+// one ALU + one FMA instruction per correction.  ptxas maps `add.cc / sub.cc ; addc c,0,0 ; setp c` onto the carry
+// predicate directly (checked in the SASS: IADD3 R, P0, PT, a, -b, RZ ; @!P0 IMAD R, one, p, R).
+// STARK_FIELD_CARRY=0 restores the compare + select forms (kernel experiments, tools/variants_ntt.sh).
+#ifndef STARK_FIELD_CARRY
+#define STARK_FIELD_CARRY 1
+#endif
+// which pipe applies the predicated +-p: bit 0 = Montgomery product, bit 1 = add, bit 2 = subtract; set = FMA pipe
+// (predicated IMAD), clear = ALU pipe (predicated IADD3).  Measured in profiles/r02_ntt.md.
+#ifndef STARK_CORR_FMA
+#define STARK_CORR_FMA 0
+#endif
+static __constant__ uint32_t c_field_one = 1;
+static __constant__ uint32_t c_field_zero = 0;
+// hi32(a * b).  With the carry forms on, the product is written as a multiply-add with an addend the compiler cannot see
+// through: ptxas otherwise folds the subtraction that follows into the multiply (IMAD.HI Rd, P0, a, b, {0, -h}), which
+// costs a negate, a register-pair move and a zeroing per product and takes its carry from hi + (2^32 - h) -- no carry for
+// h == 0, where a subtraction has one.
+__device__ __forceinline__ uint32_t mulhi_nofuse(uint32_t a, uint32_t b) {
+#if STARK_FIELD_CARRY
+    uint32_t hi;
+    const uint32_t zero = c_field_zero;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(hi) : "r"(a), "r"(b), "r"(zero));
+    return hi;
+#else
+    return __umulhi(a, b);
+#endif
+}
+// d = a - b, plus p when a < b.  Any u32 a, b: the result is congruent to a - b; canonical when both are.
+template <bool ON_FMA = ((STARK_CORR_FMA & 4) != 0)>
+__device__ __forceinline__ uint32_t sub_fix(uint32_t a, uint32_t b, uint32_t p) {
+#if STARK_FIELD_CARRY
+    uint32_t d;
+    if (ON_FMA) {
+        const uint32_t one = c_field_one;
+        asm("{ .reg .pred q; .reg .u32 c;\n\t"
+            "sub.cc.u32 %0, %1, %2;\n\t"
+            "addc.u32 c, 0, 0;\n\t"                  // the carry of a + ~b + 1: 1 when a >= b
+            "setp.eq.u32 q, c, 0;\n\t"
+            "@q mad.lo.u32 %0, %3, %4, %0;\n\t}"
+            : "=&r"(d) : "r"(a), "r"(b), "r"(one), "r"(p));
+    } else {
+        asm("{ .reg .pred q; .reg .u32 c;\n\t"
+            "sub.cc.u32 %0, %1, %2;\n\t"
+            "addc.u32 c, 0, 0;\n\t"
+            "setp.eq.u32 q, c, 0;\n\t"
+            "@q add.u32 %0, %0, %3;\n\t}"
+            : "=&r"(d) : "r"(a), "r"(b), "r"(p));
+    }
+    return d;
+#else
+    uint32_t d = a - b;
+    return a < b ? d + p : d;
+#endif
+}
+// s = a + b, minus p when the sum wrapped past 2^32 (a "weak" sum: congruent, not necessarily < p).
+__device__ __forceinline__ uint32_t add_wrap_fix(uint32_t a, uint32_t b, uint32_t p) {
+#if STARK_FIELD_CARRY
+    uint32_t s;
+    const uint32_t np = 0u - p;
+    if (STARK_CORR_FMA & 2) {
+        const uint32_t one = c_field_one;
+        asm("{ .reg .pred q; .reg .u32 c;\n\t"
+            "add.cc.u32 %0, %1, %2;\n\t"
+            "addc.u32 c, 0, 0;\n\t"
+            "setp.ne.u32 q, c, 0;\n\t"
+            "@q mad.lo.u32 %0, %3, %4, %0;\n\t}"
+            : "=&r"(s) : "r"(a), "r"(b), "r"(one), "r"(np));
+    } else {
+        asm("{ .reg .pred q; .reg .u32 c;\n\t"
+            "add.cc.u32 %0, %1, %2;\n\t"
+            "addc.u32 c, 0, 0;\n\t"
+            "setp.ne.u32 q, c, 0;\n\t"
+            "@q add.u32 %0, %0, %3;\n\t}"
+            : "=&r"(s) : "r"(a), "r"(b), "r"(np));
+    }
+    return s;
+#else
+    uint32_t s = a + b;
+    return s < a ? s - p : s;
+#endif
+}
+
 // a*b*2^-32 mod p.  Requires a*b < p*2^32 (true when one operand is < p); result in [0,p).
 // Signed form (t - q*p)/2^32 so that nothing overflows for p > 2^31.
 #ifndef STARK_MONT_WIDE
@@ -31,27 +119,38 @@ __device__ __forceinline__ uint32_t mont_mul(uint32_t a, uint32_t b, const Field
 #endif
     uint32_t q = lo * f.pinv;
     uint32_t h = __umulhi(q, f.p);
-#if defined(STARK_NTT_BFLY) && (STARK_NTT_BFLY & 4)
-    uint32_t r;      // experiment: predicated correction instead of compare + select + three-input add
-    asm("{ .reg .pred q;\n\t"
-        "setp.lt.u32 q, %1, %2;\n\t"
-        "sub.u32 %0, %1, %2;\n\t"
-        "@q add.u32 %0, %0, %3;\n\t}"
-        : "=&r"(r) : "r"(hi), "r"(h), "r"(f.p));
-    return r;
-#else
+    // compare + select here: the general product sits on long dependency chains (batched inverse, power walks), where the
+    // carry form measured slower (batch_inverse 2^24: 0.060 -> 0.068 ms, profiles/r02_ntt.md); the transform butterflies
+    // use mont_mul_tw below
     uint32_t r = hi - h;
     return hi < h ? r + f.p : r;
-#endif
 }
+// The same product when the second factor is a table constant stored with wp = w * p^-1 mod 2^32 next to it (the
+// transform twiddles): q = x * wp is one multiply, so the product is IMAD + 2 IMAD.HI + the correction.
+__device__ __forceinline__ uint32_t mont_mul_tw(uint32_t x, uint32_t w, uint32_t wp, const FieldParams& f) {
+    uint32_t q = x * wp;
+    uint32_t hi = mulhi_nofuse(x, w);
+    uint32_t h = __umulhi(q, f.p);
+    return sub_fix<(STARK_CORR_FMA & 1) != 0>(hi, h, f.p);
+}
+// canonical a, b -> canonical a + b:  a + (b - p) carries out of 32 bits exactly when a + b >= p
 __device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b, const FieldParams& f) {
+#if STARK_FIELD_CARRY
+    uint32_t s;
+    const uint32_t one = c_field_one, t = b - f.p;
+    asm("{ .reg .pred q; .reg .u32 c;\n\t"
+        "add.cc.u32 %0, %1, %2;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "setp.eq.u32 q, c, 0;\n\t"
+        "@q mad.lo.u32 %0, %3, %4, %0;\n\t}"
+        : "=&r"(s) : "r"(a), "r"(t), "r"(one), "r"(f.p));
+    return s;
+#else
     uint32_t s = a + b;
     return (s < a || s >= f.p) ? s - f.p : s;
+#endif
 }
-__device__ __forceinline__ uint32_t fsub(uint32_t a, uint32_t b, const FieldParams& f) {
-    uint32_t d = a - b;
-    return a < b ? d + f.p : d;
-}
+__device__ __forceinline__ uint32_t fsub(uint32_t a, uint32_t b, const FieldParams& f) { return sub_fix(a, b, f.p); }
 __device__ __forceinline__ uint32_t to_mont(uint32_t a, const FieldParams& f) { return mont_mul(a, f.r2, f); }
 __device__ __forceinline__ uint32_t from_mont(uint32_t a, const FieldParams& f) { return mont_mul(a, 1u, f); }
 

@@ -229,6 +229,15 @@ inline void be8(uint64_t v, uint8_t out[8]) {            // FieldElement::to_byt
     for (int i = 0; i < 8; i++) out[i] = (uint8_t)(v >> (56 - 8 * i));
 }
 
+// The statement of the build-defined FibonacciSq STARK as the FIRST transcript message: every
+// Fiat-Shamir challenge then depends on the modulus, the generator, the sizes, the query count and the claimed a_{T-2}.
+constexpr size_t STARK101_STATEMENT_BYTES = 48;
+inline void stark101_statement(uint64_t modulus, uint64_t generator, unsigned log_trace, unsigned log_blowup, size_t num_queries,
+                               uint64_t claimed_last, uint8_t out[STARK101_STATEMENT_BYTES]) {
+    be8(modulus, out); be8(generator, out + 8); be8(log_trace, out + 16); be8(log_blowup, out + 24);
+    be8((uint64_t)num_queries, out + 32); be8(claimed_last, out + 40);
+}
+
 // Vec<Vec<u8>> as one byte arena plus spans: a query appends ~90 messages, and a heap block per message costs more
 // than hashing the short ones.
 // The arena of a finished transcript goes back to a small pool and the next Channel starts on it: a proof logs ~0.6 MB,
@@ -244,8 +253,9 @@ struct MessageLog {
     ~MessageLog() { recycle(&bytes, false); }
     // take == true: hands out a pooled arena (empty, capacity kept) if there is one; false: gives one back
     static void recycle(std::vector<uint8_t>* v, bool take) {
-        static std::mutex mu;
-        static std::vector<std::vector<uint8_t>> pool;
+        // leaked on purpose: a Channel with static storage duration may be destroyed after any function-local static
+        static std::mutex& mu = *new std::mutex;
+        static std::vector<std::vector<uint8_t>>& pool = *new std::vector<std::vector<uint8_t>>;
         std::lock_guard<std::mutex> g(mu);
         if (take) {
             if (!pool.empty()) { *v = std::move(pool.back()); pool.pop_back(); v->clear(); }
@@ -254,6 +264,10 @@ struct MessageLog {
         }
     }
     void push(const uint8_t* p, size_t n) {
+        // the ABI hands out pointers into this arena (stark_channel_proof_msg): a caller re-sending one of those messages
+        // passes a pointer the reserve below may free -- remember where it points and re-derive it afterwards
+        const bool inside = n && !bytes.empty() && p >= bytes.data() && p < bytes.data() + bytes.size();
+        const size_t self_off = inside ? (size_t)(p - bytes.data()) : 0;
         if (bytes.capacity() == 0) recycle(&bytes, true);
         if (spans.size() == spans.capacity()) spans.reserve(spans.empty() ? 4096 : 2 * spans.size());
         if (bytes.size() + n > bytes.capacity()) {           // a query appends ~20 KB: grow in big steps, few re-copies
@@ -263,7 +277,13 @@ struct MessageLog {
             bytes.reserve(want);
         }
         spans.emplace_back(bytes.size(), n);
-        bytes.insert(bytes.end(), p, p + n);
+        if (inside) {                                        // capacity is already there: resize never reallocates here
+            const size_t at = bytes.size();
+            bytes.resize(at + n);
+            memmove(bytes.data() + at, bytes.data() + self_off, n);
+        } else {
+            bytes.insert(bytes.end(), p, p + n);
+        }
     }
     size_t size() const { return spans.size(); }
     const uint8_t* data(size_t i) const { return bytes.data() + spans[i].first; }

@@ -40,48 +40,25 @@ struct NttPass {
 // Lazy (DIT only, and only for p > 2^31 -- the launcher checks): values are "weak" -- any u32 congruent to the
 // element (2^32 < 2p, so canonical or canonical + p).  A Montgomery product accepts a weak operand and returns a canonical one, so in
 // a + w*b / a - w*b only `a` is weak; the sum wraps past 2^32 at most once and the difference goes negative
-// at most once, which makes the add 3 instructions instead of 6.  The last pass canonicalises on store.
-// STARK_NTT_BFLY (bit mask, kernel experiments): the conditional correction of a lazy add (bit 1) / subtract (bit 0)
-// as a PREDICATED multiply-add on the FMA pipe instead of compare + select + add on the ALU pipe; `one` is a 1 the
-// compiler cannot see through (same device as sha256.cuh).
-#ifndef STARK_NTT_BFLY
-#define STARK_NTT_BFLY 2
-#endif
-static __constant__ uint32_t c_ntt_one = 1;
-__device__ __forceinline__ uint32_t ladd(uint32_t a_weak, uint32_t b, const FieldParams& f) {
-#if STARK_NTT_BFLY & 2
-    uint32_t s;
-    const uint32_t one = c_ntt_one, np = 0u - f.p;
-    asm("{ .reg .pred q;\n\t"
-        "mad.lo.u32 %0, %1, %3, %2;\n\t"
-        "setp.lt.u32 q, %0, %1;\n\t"
-        "@q mad.lo.u32 %0, %4, %3, %0;\n\t}"
-        : "=&r"(s) : "r"(a_weak), "r"(b), "r"(one), "r"(np));
-    return s;
-#else
-    uint32_t s = a_weak + b;
-    return s < a_weak ? s - f.p : s;
-#endif
-}
-__device__ __forceinline__ uint32_t lsub(uint32_t a_weak, uint32_t b, const FieldParams& f) {
-#if STARK_NTT_BFLY & 1
-    uint32_t d;
-    const uint32_t one = c_ntt_one, mone = 0u - one;
-    asm("{ .reg .pred q;\n\t"
-        "setp.lt.u32 q, %1, %2;\n\t"
-        "mad.lo.u32 %0, %2, %4, %1;\n\t"
-        "@q mad.lo.u32 %0, %5, %3, %0;\n\t}"
-        : "=&r"(d) : "r"(a_weak), "r"(b), "r"(one), "r"(mone), "r"(f.p));
-    return d;
-#else
-    uint32_t d = a_weak - b;
-    return a_weak < b ? d + f.p : d;
-#endif
-}
+// at most once: one carry-predicated correction each (field.cuh: add_wrap_fix / sub_fix).  The last pass canonicalises
+// on store.  A butterfly is 9 instructions: the product (IMAD, 2 IMAD.HI, IADD3 with carry-out, predicated IMAD) and
+// two IADD3-with-carry + predicated-IMAD pairs -- 3 on the ALU pipe, 6 on the FMA pipe (was 7 + 5 with compare + select
+// corrections, profiles/r02_ntt.md).
+__device__ __forceinline__ uint32_t ladd(uint32_t a_weak, uint32_t b, const FieldParams& f) { return add_wrap_fix(a_weak, b, f.p); }
+__device__ __forceinline__ uint32_t lsub(uint32_t a_weak, uint32_t b, const FieldParams& f) { return sub_fix(a_weak, b, f.p); }
 __device__ __forceinline__ uint32_t canonical(uint32_t x, const FieldParams& f) { return x >= f.p ? x - f.p : x; }
 
+// In-tile twiddles travel as pairs {w, w * p^-1 mod 2^32} (mont_mul_tw): one 64-bit shared-memory load per distinct
+// twiddle of a register group instead of a load and a multiply.
+__device__ __forceinline__ void fill_tile_twiddles(uint2* tws, const uint32_t* small, unsigned small_log, int r_log, const FieldParams& fp) {
+    for (int k = threadIdx.x; k < (1 << r_log) >> 1; k += blockDim.x) {
+        const uint32_t w = small[(size_t)k << (small_log - r_log)];
+        tws[k] = make_uint2(w, w * fp.pinv);
+    }
+}
+
 template <int G, bool DIF, bool LAZY>
-__device__ __forceinline__ void butterfly_group(uint32_t* col, const int s, const int base, const uint32_t* tws,
+__device__ __forceinline__ void butterfly_group(uint32_t* col, const int s, const int base, const uint2* tws,
                                                 const int r_log, const FieldParams& fp) {
     uint32_t x[1 << G];
 #pragma unroll
@@ -96,18 +73,19 @@ __device__ __forceinline__ void butterfly_group(uint32_t* col, const int s, cons
             if (jj & (1 << u)) continue;
             const int k = bl + ((jj & ((1 << u) - 1)) << s);
             const bool unit = (s == 0 && u == 0);    // w_2^0 = 1: no multiplication in the span-1 stage
-            const uint32_t w = unit ? 0u : tws[k << (r_log - level)];
+            const uint2 w = unit ? make_uint2(0u, 0u) : tws[k << (r_log - level)];
             if (DIF) {
                 uint32_t a = x[jj], b = x[jj + (1 << u)];
                 x[jj] = fadd(a, b, fp);
                 uint32_t d = fsub(a, b, fp);
-                x[jj + (1 << u)] = unit ? d : mont_mul(d, w, fp);
+                x[jj + (1 << u)] = unit ? d : mont_mul_tw(d, w.x, w.y, fp);
             } else if (LAZY) {
-                uint32_t a = x[jj], b = unit ? x[jj + (1 << u)] : mont_mul(x[jj + (1 << u)], w, fp);
+                // (the span-1 stage is the first of a pass: its inputs come straight from a product, so `b` is canonical)
+                uint32_t a = x[jj], b = unit ? x[jj + (1 << u)] : mont_mul_tw(x[jj + (1 << u)], w.x, w.y, fp);
                 x[jj] = ladd(a, b, fp);
                 x[jj + (1 << u)] = lsub(a, b, fp);
             } else {
-                uint32_t a = x[jj], b = unit ? x[jj + (1 << u)] : mont_mul(x[jj + (1 << u)], w, fp);
+                uint32_t a = x[jj], b = unit ? x[jj + (1 << u)] : mont_mul_tw(x[jj + (1 << u)], w.x, w.y, fp);
                 x[jj] = fadd(a, b, fp);
                 x[jj + (1 << u)] = fsub(a, b, fp);
             }
@@ -118,7 +96,7 @@ __device__ __forceinline__ void butterfly_group(uint32_t* col, const int s, cons
 }
 
 template <int R_LOG, int G, bool DIF, bool LAZY>
-__device__ __forceinline__ void run_round(uint32_t* tile, const int s, const uint32_t* tws, const FieldParams& fp,
+__device__ __forceinline__ void run_round(uint32_t* tile, const int s, const uint2* tws, const FieldParams& fp,
                                           const unsigned ncols) {
     constexpr int items = ((1 << R_LOG) >> G) * NTT_C;
     for (int w = threadIdx.x; w < items; w += blockDim.x) {
@@ -131,7 +109,7 @@ __device__ __forceinline__ void run_round(uint32_t* tile, const int s, const uin
 }
 
 template <int R_LOG, bool DIF, bool LAZY = false>
-__device__ __forceinline__ void run_rounds(uint32_t* tile, const uint32_t* tws, const FieldParams& fp, unsigned ncols) {
+__device__ __forceinline__ void run_rounds(uint32_t* tile, const uint2* tws, const FieldParams& fp, unsigned ncols) {
     // stage groups (sum = R_LOG); DIT walks spans upward, DIF downward
     if constexpr (R_LOG <= 4) {
         run_round<R_LOG, R_LOG, DIF, LAZY>(tile, 0, tws, fp, ncols);
@@ -161,8 +139,8 @@ __global__ void ntt_pass_kernel(NttPass ps, FieldParams fp) {
     extern __shared__ uint32_t smem[];
     constexpr int R = 1 << R_LOG;
     uint32_t* tile = smem;                    // [R][33]
-    uint32_t* tws = smem + R * NTT_TS;        // [R/2] twiddles of w_R
-    for (int k = threadIdx.x; k < (R >> 1); k += blockDim.x) tws[k] = ps.small[(size_t)k << (ps.small_log - R_LOG)];
+    uint2* tws = reinterpret_cast<uint2*>(smem + R * NTT_TS);        // [R/2] twiddles of w_R
+    fill_tile_twiddles(tws, ps.small, ps.small_log, R_LOG, fp);
 
     const size_t tile_id = blockIdx.x;
     size_t gbase;
@@ -227,7 +205,7 @@ static void launch_pass(stark_ctx* ctx, const NttPass& ps, size_t tiles) {
     int threads = (R * NTT_C) >> 4;
     if (threads < 32) threads = 32;
     if (threads > 1024) threads = 1024;
-    size_t smem = (size_t)(R * NTT_TS + (R >> 1) + 1) * sizeof(uint32_t);
+    size_t smem = (size_t)(R * NTT_TS + R + 2) * sizeof(uint32_t);
     auto kern = ntt_pass_kernel<R_LOG, DIF, STRIDED>;
     if (smem > 48 * 1024)   // opt in per launch: the attribute is per device, contexts may live on several
         STARK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -429,16 +407,25 @@ __device__ __forceinline__ uint32_t nat_kacc(const NatPass& ps, uint32_t high) {
 }
 
 constexpr int nat_threads(int r_log) { return (2 << r_log) < 64 ? 64 : ((2 << r_log) > 512 ? 512 : (2 << r_log)); }
-constexpr int nat_min_blocks(int r_log) { return 1536 / nat_threads(r_log) > 16 ? 16 : 1536 / nat_threads(r_log); }
+// resident CTAs per SM the register allocation aims for: STARK_NTT_REGCAP = registers per thread the transforms may use
+#ifndef STARK_NTT_REGCAP
+#define STARK_NTT_REGCAP 48
+#endif
+constexpr int ntt_min_blocks(int threads, int cap) {
+    int by_regs = 65536 / (STARK_NTT_REGCAP * threads), by_threads = 1536 / threads;
+    int b = by_regs < by_threads ? by_regs : by_threads;
+    return b > cap ? cap : (b < 1 ? 1 : b);
+}
+constexpr int nat_min_blocks(int r_log) { return ntt_min_blocks(nat_threads(r_log), 16); }
 
 template <int R_LOG, bool FIRST, bool LAZY>
 __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat_strided_kernel(NatPass ps, FieldParams fp) {
     extern __shared__ uint32_t smem[];
     constexpr int R = 1 << R_LOG;
     uint32_t* tile = smem;                    // [R][33], row rho holds digit value bitrev(rho) until the rounds have run
-    uint32_t* tws = smem + R * NTT_TS;        // [R/2] twiddles of w_R
-    uint32_t* rowtw = tws + (R >> 1);         // [R] W^(K t), t = bitrev(row)
-    for (int k = threadIdx.x; k < (R >> 1); k += blockDim.x) tws[k] = ps.small[(size_t)k << (ps.small_log - R_LOG)];
+    uint2* tws = reinterpret_cast<uint2*>(smem + R * NTT_TS);        // [R/2] twiddles of w_R
+    uint2* rowtw = tws + (R >> 1);            // [R] W^(K t), t = bitrev(row), as {w, w * p^-1}
+    fill_tile_twiddles(tws, ps.small, ps.small_log, R_LOG, fp);
 
     const size_t tiles_per_high = ((size_t)1 << ps.lo) / NTT_C;
     const size_t high = blockIdx.x / tiles_per_high;
@@ -470,8 +457,10 @@ __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat
         }
         if (!FIRST && b == 0) {
             const uint32_t K = nat_kacc(ps, (uint32_t)high);
-            for (int rho = threadIdx.x; rho < R; rho += T)           // indexed by tile row: consecutive words for a warp's 4 rows
-                rowtw[rho] = pow_lookup(ps.tw, (K * bitrev_bits((uint32_t)rho, R_LOG)) << ps.lo, fp);
+            for (int rho = threadIdx.x; rho < R; rho += T) {         // indexed by tile row: consecutive words for a warp's 4 rows
+                const uint32_t w = pow_lookup(ps.tw, (K * bitrev_bits((uint32_t)rho, R_LOG)) << ps.lo, fp);
+                rowtw[rho] = make_uint2(w, w * fp.pinv);
+            }
             __syncthreads();
         }
 #pragma unroll
@@ -488,9 +477,9 @@ __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat
                     for (int k = 0; k < 4; k++) { v[k] = mont_mul(v[k], sc, fp); if (k < 3) sc = mont_mul(sc, step, fp); }
                 }
             } else {
-                const uint32_t w = rowtw[rho];
+                const uint2 w = rowtw[rho];
 #pragma unroll
-                for (int k = 0; k < 4; k++) v[k] = mont_mul(v[k], w, fp);
+                for (int k = 0; k < 4; k++) v[k] = mont_mul_tw(v[k], w.x, w.y, fp);
             }
             uint32_t* o = tile + rho * NTT_TS + 4 * g4;
 #pragma unroll
@@ -514,9 +503,9 @@ __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat
     extern __shared__ uint32_t smem[];
     constexpr int R = 1 << R_LOG;
     uint32_t* tile = smem;                    // [R rows = n_m][33: column j = k1 - k1_0]
-    uint32_t* tws = smem + R * NTT_TS;
-    uint32_t* coltw = tws + (R >> 1);         // [32] W^K(j), W = w_{2^log_n}
-    for (int k = threadIdx.x; k < (R >> 1); k += blockDim.x) tws[k] = ps.small[(size_t)k << (ps.small_log - R_LOG)];
+    uint2* tws = reinterpret_cast<uint2*>(smem + R * NTT_TS);
+    uint2* coltw = tws + (R >> 1);            // [32] W^K(j), W = w_{2^log_n}, as {w, w * p^-1}
+    fill_tile_twiddles(tws, ps.small, ps.small_log, R_LOG, fp);
 
     // address bits above the digit: [k1][mid]; the tile takes 32 consecutive k1 at one mid
     // (a batch of transforms: the tiles of one transform are consecutive, src / dst move on by 2^log_n per transform)
@@ -550,7 +539,10 @@ __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat
             wh[u] = __ldg(ps.tw.hi + (e >> ps.tw.shift));
         }
         if (b == 0) {
-            if (threadIdx.x < NTT_C) coltw[threadIdx.x] = pow_lookup(ps.tw, K0 + threadIdx.x, fp);
+            if (threadIdx.x < NTT_C) {
+                const uint32_t w = pow_lookup(ps.tw, K0 + threadIdx.x, fp);
+                coltw[threadIdx.x] = make_uint2(w, w * fp.pinv);
+            }
             __syncthreads();
         }
 #pragma unroll
@@ -559,12 +551,12 @@ __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat
             const int q8 = i & 7, jj = (i >> 3) & 3, rest = i >> 5;
             const int seg = rest & ((R >> 5) - 1), j = (rest >> (R_LOG - 5)) * 4 + jj;
             const uint32_t n3 = (uint32_t)seg * 32 + 4 * q8;
-            const uint32_t step = coltw[j];
+            const uint2 step = coltw[j];
             uint32_t w = mont_mul(wl[u], wh[u], fp);
             uint32_t* o = tile + n3 * NTT_TS + j;
-            o[0] = mont_mul(a[u].x, w, fp); w = mont_mul(w, step, fp);
-            o[NTT_TS] = mont_mul(a[u].y, w, fp); w = mont_mul(w, step, fp);
-            o[2 * NTT_TS] = mont_mul(a[u].z, w, fp); w = mont_mul(w, step, fp);
+            o[0] = mont_mul(a[u].x, w, fp); w = mont_mul_tw(w, step.x, step.y, fp);
+            o[NTT_TS] = mont_mul(a[u].y, w, fp); w = mont_mul_tw(w, step.x, step.y, fp);
+            o[2 * NTT_TS] = mont_mul(a[u].z, w, fp); w = mont_mul_tw(w, step.x, step.y, fp);
             o[3 * NTT_TS] = mont_mul(a[u].w, w, fp);
         }
     }
@@ -593,7 +585,7 @@ template <int R_LOG, bool FIRST>
 static void launch_nat_strided(stark_ctx* ctx, const NatPass& ps, size_t tiles) {
     constexpr int R = 1 << R_LOG;
     const int threads = nat_threads(R_LOG);
-    size_t smem = (size_t)(R * NTT_TS + (R >> 1) + R) * sizeof(uint32_t);
+    size_t smem = (size_t)(R * NTT_TS + R + 2 * R) * sizeof(uint32_t);
     auto launch = [&](auto kern) {
         if (smem > 48 * 1024) STARK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)tiles, threads, smem, ctx->stream>>>(ps, ctx->fp);
@@ -606,7 +598,7 @@ template <int R_LOG>
 static void launch_nat_last(stark_ctx* ctx, const NatPass& ps, size_t tiles) {
     constexpr int R = 1 << R_LOG;
     const int threads = nat_threads(R_LOG);
-    size_t smem = (size_t)(R * NTT_TS + (R >> 1) + NTT_C) * sizeof(uint32_t);
+    size_t smem = (size_t)(R * NTT_TS + R + 2 * NTT_C) * sizeof(uint32_t);
     auto kern = nat_last_kernel<R_LOG>;
     if (smem > 48 * 1024) STARK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)tiles, threads, smem, ctx->stream>>>(ps, ctx->fp);
@@ -704,12 +696,12 @@ constexpr int lde8_threads(int r_log) {
 }
 
 template <int R_LOG, bool FIRST, bool LAZY>
-__global__ void __launch_bounds__(lde8_threads(R_LOG), (1536 / lde8_threads(R_LOG) > 24 ? 24 : 1536 / lde8_threads(R_LOG))) lde8_pass_kernel(Lde8Pass ps, FieldParams fp) {
+__global__ void __launch_bounds__(lde8_threads(R_LOG), ntt_min_blocks(lde8_threads(R_LOG), 24)) lde8_pass_kernel(Lde8Pass ps, FieldParams fp) {
     extern __shared__ uint32_t smem[];
     constexpr int R = 1 << R_LOG;
     uint32_t* tile = smem;                    // [R][33]: word g*8+s of row t
-    uint32_t* tws = smem + R * NTT_TS;
-    for (int k = threadIdx.x; k < (R >> 1); k += blockDim.x) tws[k] = ps.small[(size_t)k << (ps.small_log - R_LOG)];
+    uint2* tws = reinterpret_cast<uint2*>(smem + R * NTT_TS);
+    fill_tile_twiddles(tws, ps.small, ps.small_log, R_LOG, fp);
 
     const size_t tile_id = blockIdx.x;
     size_t row_base;          // FIRST: first row of the tile; else row of (t = 0, g = 0)
@@ -747,10 +739,10 @@ __global__ void __launch_bounds__(lde8_threads(R_LOG), (1536 / lde8_threads(R_LO
         for (int u = 0; u < 2; u++) {
             const int i = b + threadIdx.x + u * T;
             const int g = i & 3, t = i >> 2;
-            const uint32_t tw = mont_mul(wl[u], wh[u], fp);
+            const uint32_t tw = mont_mul(wl[u], wh[u], fp), twp = tw * fp.pinv;
             uint32_t* o = tile + t * NTT_TS + g * 8;
-            o[0] = mont_mul(a[u].x, tw, fp); o[1] = mont_mul(a[u].y, tw, fp); o[2] = mont_mul(a[u].z, tw, fp); o[3] = mont_mul(a[u].w, tw, fp);
-            o[4] = mont_mul(bq[u].x, tw, fp); o[5] = mont_mul(bq[u].y, tw, fp); o[6] = mont_mul(bq[u].z, tw, fp); o[7] = mont_mul(bq[u].w, tw, fp);
+            o[0] = mont_mul_tw(a[u].x, tw, twp, fp); o[1] = mont_mul_tw(a[u].y, tw, twp, fp); o[2] = mont_mul_tw(a[u].z, tw, twp, fp); o[3] = mont_mul_tw(a[u].w, tw, twp, fp);
+            o[4] = mont_mul_tw(bq[u].x, tw, twp, fp); o[5] = mont_mul_tw(bq[u].y, tw, twp, fp); o[6] = mont_mul_tw(bq[u].z, tw, twp, fp); o[7] = mont_mul_tw(bq[u].w, tw, twp, fp);
         }
         }
     }
@@ -763,10 +755,10 @@ __global__ void __launch_bounds__(lde8_threads(R_LOG), (1536 / lde8_threads(R_LO
             const uint32_t j = bitrev_bits(q, ps.log_rows);                 // the coefficient it holds
             const uint32_t si = ps.src_bitrev ? q : j;
             uint32_t c = si < ps.src_len ? ps.src[si] : 0u;
-            const uint32_t b = pow_lookup(ps.shift, j, fp);                 // w_N^j
+            const uint32_t b = pow_lookup(ps.shift, j, fp), bp = b * fp.pinv;   // w_N^j
             v[0] = mont_mul(c, pow_lookup(ps.scale, j, fp), fp);            // c_j g^j
 #pragma unroll
-            for (int k = 1; k < 8; k++) v[k] = mont_mul(v[k - 1], b, fp);    // ... * w_N^(j s)
+            for (int k = 1; k < 8; k++) v[k] = mont_mul_tw(v[k - 1], b, bp, fp);    // ... * w_N^(j s)
         } else {
             g = i & 3; t = i >> 2;
             const size_t row = row_base + ((size_t)t << ps.lo) + g;
@@ -805,7 +797,7 @@ template <int R_LOG, bool FIRST, bool LAZY>
 static void launch_lde8_impl(stark_ctx* ctx, const Lde8Pass& ps, size_t tiles) {
     constexpr int R = 1 << R_LOG;
     const int threads = lde8_threads(R_LOG);
-    size_t smem = (size_t)(R * NTT_TS + (R >> 1) + 1) * sizeof(uint32_t);
+    size_t smem = (size_t)(R * NTT_TS + R + 2) * sizeof(uint32_t);
     auto kern = lde8_pass_kernel<R_LOG, FIRST, LAZY>;
     if (smem > 48 * 1024) STARK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)tiles, threads, smem, ctx->stream>>>(ps, ctx->fp);

@@ -254,6 +254,11 @@ extern "C" int stark101_prove(stark_ctx* ctx, uint64_t a1, unsigned log_trace, u
         const uint64_t w = ctx->generator;
         uint64_t last_value = 0;
         DevBufPtr tr = fibsq_trace_column(ctx, a1, log_trace, &last_value);
+        {   // the statement opens the transcript (host_channel.hpp: stark101_statement)
+            uint8_t stmt[STARK101_STATEMENT_BYTES];
+            stark101_statement(ctx->modulus, ctx->generator, log_trace, log_blowup, num_queries, last_value, stmt);
+            ch.send(stmt, sizeof stmt);
+        }
         // ---- LDE of the trace column and its commitment ----
         DevBufPtr f_eval = api_lde_on_coset(ctx, tr->as<uint32_t>(), log_trace, 1, log_blowup, w);
         auto f_tree = api_tree_commit(ctx, f_eval, N);

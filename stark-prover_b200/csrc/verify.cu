@@ -93,11 +93,19 @@ bool split_records(const uint8_t* flat, size_t len, Msgs& msgs, std::string* why
 
 // fri_commit + decommit_fri as seen by a verifier (fri_verify.rs:12-177, completed); starts at msgs[pos] with the
 // channel in the state the prover had when it called fri_commit
+//
+// Degree bound.  The number of layers is the prover's choice (fri_commit.rs:89 folds until the polynomial is constant),
+// so it is the VERIFIER that has to cap it: a polynomial with at most 2^log_degree_bound coefficients is constant after
+// log_degree_bound folds.  Without the cap a prover may fold any function down to a one-point layer, where "the last
+// layer equals the final constant" is vacuous, and every check passes (the reference's draft takes
+// `expected_num_layers`, fri_verify.rs:15, for the same reason).  With it the last layer keeps
+// 2^(log_n - log_degree_bound) points -- the blow-up -- that must all show the same constant.
 bool verify_fri_core(const Msgs& msgs, size_t& pos, Channel& ch, const Fp& F, uint64_t generator, unsigned log_n, uint64_t offset,
-                     size_t num_queries, size_t max_index, const QueryHook& hook, std::string* why) {
+                     size_t num_queries, size_t max_index, unsigned log_degree_bound, const QueryHook& hook, std::string* why) {
     auto fail = [&](const std::string& w) { *why = w; return false; };
     if (log_n > 40 || ((F.p - 1) & ((((uint64_t)1) << log_n) - 1)) != 0) return fail("2^log_n does not divide p-1");
     if (offset % F.p == 0) return fail("zero coset offset");
+    if (log_degree_bound > log_n) return fail("degree bound larger than the domain");
     const size_t n0 = (size_t)1 << log_n;
     auto next = [&]() -> const std::vector<uint8_t>* { return pos < msgs.size() ? &msgs[pos++] : nullptr; };
 
@@ -131,7 +139,8 @@ bool verify_fri_core(const Msgs& msgs, size_t& pos, Channel& ch, const Fp& F, ui
         }
     }
     const size_t L = roots.size();
-    if (L - 1 > log_n) return fail("more layers than the domain allows");
+    if (L - 1 > log_degree_bound) return fail("more FRI layers than the degree bound allows (" + std::to_string(L - 1) + " folds, bound " +
+                                              std::to_string(log_degree_bound) + ")");
     if (final_value >= F.p) return fail("final constant is not a canonical field element");
 
     // ---- query phase (fri_commit.rs:137-179)
@@ -211,7 +220,7 @@ static int finish(bool good, const std::string& why, int* ok, char* reason) {
 // against its layer root, every layer is the fold of the previous one at the queried points, and the last
 // layer equals the final constant.  `reason` (optional, >= 160 bytes) receives the first failure.
 extern "C" int stark_fri_verify(const uint8_t* proof_flat, size_t proof_len, uint64_t modulus, uint64_t generator, unsigned log_n,
-                                uint64_t offset, size_t num_queries, size_t max_index, int* ok, char* reason) {
+                                uint64_t offset, size_t num_queries, size_t max_index, unsigned log_degree_bound, int* ok, char* reason) {
     if (!proof_flat || !ok || modulus < 3) { api_set_error("fri_verify: bad argument"); return ST_INVALID; }
     Msgs msgs;
     std::string why;
@@ -219,7 +228,7 @@ extern "C" int stark_fri_verify(const uint8_t* proof_flat, size_t proof_len, uin
     const Fp F{modulus};
     Channel ch(F.p);
     size_t pos = 0;
-    bool good = verify_fri_core(msgs, pos, ch, F, generator, log_n, offset, num_queries, max_index, nullptr, &why);
+    bool good = verify_fri_core(msgs, pos, ch, F, generator, log_n, offset, num_queries, max_index, log_degree_bound, nullptr, &why);
     if (good && pos != msgs.size()) { good = false; why = "trailing messages after the last query"; }
     return finish(good, why, ok, reason);
 }
@@ -242,10 +251,16 @@ extern "C" int stark101_verify(const uint8_t* proof_flat, size_t proof_len, uint
     const uint64_t w = generator % F.p;
     Channel ch(F.p);
     size_t pos = 0;
-    std::array<uint8_t, 32> f_root{};
-    if (msgs.empty() || !parse_hex_root(msgs[0], f_root.data())) return finish(false, "first message is not the trace root", ok, reason);
+    // the statement is part of the transcript: every challenge depends on it (stark101_statement, host_channel.hpp)
+    uint8_t want_stmt[STARK101_STATEMENT_BYTES];
+    stark101_statement(F.p, generator % F.p, log_trace, log_blowup, num_queries, claimed_last % F.p, want_stmt);
+    if (msgs.empty() || msgs[0].size() != sizeof want_stmt || memcmp(msgs[0].data(), want_stmt, sizeof want_stmt) != 0)
+        return finish(false, "first message is not this statement (modulus, generator, sizes, queries, claimed a_{T-2})", ok, reason);
     ch.send(msgs[0].data(), msgs[0].size());
-    pos = 1;
+    std::array<uint8_t, 32> f_root{};
+    if (msgs.size() < 2 || !parse_hex_root(msgs[1], f_root.data())) return finish(false, "second message is not the trace root", ok, reason);
+    ch.send(msgs[1].data(), msgs[1].size());
+    pos = 2;
     uint64_t alpha[3];
     for (int k = 0; k < 3; k++) {
         uint64_t rec, want;
@@ -272,7 +287,8 @@ extern "C" int stark101_verify(const uint8_t* proof_flat, size_t proof_len, uint
         *has = true;
         return true;
     };
-    bool good = verify_fri_core(msgs, pos, ch, F, generator, log_N, w, num_queries, N - 1 - 2 * blow, hook, &why);
+    // deg CP <= T - 1 (p0, p1: deg f - 1 <= T - 3; p2: 2 (T - 2) + 3 - T): at most T coefficients, constant after log_trace folds
+    bool good = verify_fri_core(msgs, pos, ch, F, generator, log_N, w, num_queries, N - 1 - 2 * blow, log_trace, hook, &why);
     if (good && pos != msgs.size()) { good = false; why = "trailing messages after the last query"; }
     return finish(good, why, ok, reason);
 }

@@ -448,6 +448,7 @@ def stark101_prove_multi(sp, ctx, channel, a1: int, log_trace: int, log_blowup: 
     lap("commit_f")
     alpha = [0, 0, 0]
     if rank == 0:
+        channel.send(sp.stark101_statement(ctx.modulus, ctx.generator, log_trace, log_blowup, num_queries, last_value))
         channel.send(f_root.hex().encode())
         alpha = [channel.receive_random_field_element() for _ in range(3)]
     alpha = [_bcast_int(a, group) for a in alpha]

@@ -63,7 +63,7 @@ def main():
                        "final_state": ch.state, "proof_size": ch.proof_size(),
                        "compressed_proof_size": ch.compressed_proof_size(),
                        "proof_sha256": sha(ch.proof_flat()), "n_messages": len(ch.proof),
-                       "first_root": ch.proof[0].decode()}
+                       "statement": ch.proof[0].hex(), "first_root": ch.proof[1].decode()}
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "transcripts.json")
     json.dump(out, open(path, "w"), indent=1)
     print("wrote", path)

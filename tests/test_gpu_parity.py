@@ -550,11 +550,11 @@ def test_fri_maximum_domain_2e30_verifies(sp, orc):
         assert pr.num_layers == 28 and pr.layer_len(0) == 1 << log_n and pr.layer_len(27) == 8
         sp.decommit_fri(q, (1 << log_n) - 1, pr, ch)
         flat = ch.proof_flat()
-        ok, why = sp.verify_fri(flat, log_n, 5, q, (1 << log_n) - 1)
+        ok, why = sp.verify_fri(flat, log_n, 5, q, (1 << log_n) - 1, log_n - 3)
         assert ok, why
         bad = bytearray(flat)
         bad[len(bad) // 2] ^= 0x10
-        ok2, _ = sp.verify_fri(bytes(bad), log_n, 5, q, (1 << log_n) - 1)
+        ok2, _ = sp.verify_fri(bytes(bad), log_n, 5, q, (1 << log_n) - 1, log_n - 3)
         assert not ok2
         # layer 0 against the reference's literal Horner evaluation (ops.rs:76-83) at a few points of the coset
         w = orc.root_of_unity(log_n)

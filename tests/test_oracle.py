@@ -257,4 +257,5 @@ def test_golden_transcripts(orc, golden):
         orc.stark101_prove(ch, literal=literal)
         assert ch.state == s["final_state"] and ch.proof_size() == s["proof_size"]
         assert hashlib.sha256(ch.proof_flat()).hexdigest() == s["proof_sha256"]
-        assert ch.proof[0].decode() == s["first_root"]
+        assert ch.proof[0].hex() == s["statement"] and ch.proof[1].decode() == s["first_root"]
+        assert ch.proof[0] == b"".join(int(v).to_bytes(8, "big") for v in (P, 5, 10, 3, 3, int(orc.fibsq_trace(3141592, 1023)[1022])))

@@ -177,7 +177,7 @@ def run(budget: float, seed: int, tag: str = "") -> None:
             idxs = [int(x) for x in rng.integers(0, 1 << log_n, 3)]
             ok = pr.open(idxs) == b"".join(pr.open([i]) for i in idxs)
             sp.decommit_fri(q, (1 << log_n) - 1, pr, ch)
-            good, why = sp.verify_fri(ch.proof_flat(), log_n, off, q, (1 << log_n) - 1, m, g)
+            good, why = sp.verify_fri(ch.proof_flat(), log_n, off, q, (1 << log_n) - 1, (nco - 1).bit_length(), m, g)
             check("fri_open_verify", ok and good, f"log_n={log_n} coeffs={nco} offset={off} q={q} modulus={m} verifier={why!r}")
             pr.free()
         elif kind == 11:                                # the sharded prover's code path with one rank == the plain prover

@@ -73,13 +73,13 @@ while time.time() < t_end:
         pr = orc.fri_commit_fast(c, log_n, off, orc.root_of_unity(log_n), ch, P)
         orc.decommit_fri(q, (1 << log_n) - 1, pr, ch)
         msgs = ch.proof
-        good, why = sp.verify_fri(flat(msgs), log_n, off, q, (1 << log_n) - 1)
+        good, why = sp.verify_fri(flat(msgs), log_n, off, q, (1 << log_n) - 1, log_d)
         ok = good
         k = int(rng.integers(0, len(msgs)))
         if len(msgs[k]):
             bad = [bytearray(x) for x in msgs]
             bad[k][int(rng.integers(0, len(bad[k])))] ^= 1 << int(rng.integers(0, 8))
-            rej, why2 = sp.verify_fri(flat(bad), log_n, off, q, (1 << log_n) - 1)
+            rej, why2 = sp.verify_fri(flat(bad), log_n, off, q, (1 << log_n) - 1, log_d)
             ok = ok and not rej
         check("verify_fri", ok, f"log_n={log_n} coeffs={nco} off={off} q={q} why={why!r} flipped message {k}")
     else:                                           # STARK verifier on oracle transcripts + bit flip + wrong claim
