@@ -1,25 +1,33 @@
 #!/usr/bin/env python
-"""bench.py — LDE + Merkle + FRI-commit throughput (Melem/s) at a 2^24 domain on N B200s.
+"""bench.py — LDE + Merkle + FRI-commit throughput (Melem/s) and prove ms at a 2^24 domain on N B200s.
 
 A step = one pass of the hot path over one synthetic polynomial (BASELINE.json configs[2]):
 coset evaluation of a degree-(2^21-1) polynomial on the 2^24-point domain 5*<w>, 22 Merkle commitments,
 21 fused fold-and-hash layers driven by the host Fiat-Shamir channel, and the openings of 32 queries
 (`fri_commit` + `decommit_fri`, reference src/fri/fri_commit.rs:72-179).
 
-  value   device-timed (CUDA events on the library's stream), coefficients already resident in HBM
-  e2e     the same step through the host-buffer C ABI: pinned u64 coefficients -> stark_fri_commit (H2D
-          inside) -> roots/openings back in the host channel
-  N > 1   one process per GPU (torchrun); every rank commits its own column (weak scaling, no data-path
-          collective), then the 32-byte layer-0 roots are all-gathered (the root gather of SURVEY.md 8e)
-  --impl reference   the CPU oracle port of the reference algorithm (the Rust crate cannot be built here),
-          all host threads, on a bounded sample of the same workload
+  value     device-timed (CUDA events on the library's stream), coefficients already resident in HBM
+  e2e       the same step through the host-buffer C ABI: pinned u64 coefficients -> stark_fri_commit (H2D inside) ->
+            roots/openings back in the host channel;  e2e_full additionally copies every FRI layer back by value, as the
+            reference's FRIProof returns them (fri_commit.rs:9-13, :117-121)
+  prove     stark101_prove (trace -> LDE -> commit -> composition -> FRI -> queries) at a 2^24 domain, oracle beside it
+  N > 1     one process per GPU (torchrun).  `value`: every rank commits its own column (weak scaling, replicas: the FRI
+            loop is not partitioned, north-star).  `sharded`: the two configs that DO shard, at fixed total size (strong
+            scaling), asserted against committed oracle goldens inside the run:
+              cfg4  64 columns x 2^22 rows -> LDE 2^25 + Merkle commit per column, column c -> rank c mod N, roots gathered
+              cfg5  one 2^26-point column: four-step LDE (NCCL all-to-all and peer-memory stores), leaf-range commit,
+                    fri_commit with the sharded layer 0 + 8 openings
+  --impl reference   the CPU oracle port of the reference algorithm (the Rust crate cannot be built here), all host
+            threads, on the SAME 2^24 workload
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import importlib
 import json
 import os
+import socket
 import subprocess
 import sys
 import threading
@@ -43,10 +51,13 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log-n", type=int, default=24, help="log2 of the LDE/FRI domain (headline: 24)")
     ap.add_argument("--log-blowup", type=int, default=3)
-    ap.add_argument("--cpu-log-n", type=int, default=20, help="bounded CPU sample: domain 2^this")
+    ap.add_argument("--cpu-log-n", type=int, default=None, help="CPU arm domain (default: the same as --log-n)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
     ap.add_argument("--no-pipelined", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the cfg4 / cfg5 strong-scaling block")
+    ap.add_argument("--no-prove", action="store_true")
+    ap.add_argument("--sharded-small", action="store_true", help="cfg4 16 x 2^16, cfg5 2^22 (quick check of the sharded block)")
     ap.add_argument("--profile-mode", action="store_true",
                     help="for runs under ncu: exactly --warmup warm-up steps and --steps steps of the device-resident path, nothing else")
     return ap.parse_args()
@@ -115,15 +126,40 @@ def measured_peaks() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic() -> tuple:
-    """DRAM bytes per hashing launch from the committed ncu capture (profiles/rNN_traffic.json), or None."""
+def latest_profile(suffix: str):
     pdir = os.path.join(ROOT, "profiles")
     try:
-        f = sorted(x for x in os.listdir(pdir) if x.endswith("_traffic.json"))[-1]
-        d = json.load(open(os.path.join(pdir, f)))
-        return d["hashing_dram_bytes_per_launch"], f"profiles/{f}: {d['hashing_dram_bytes_per_step'] / 1e9:.2f} GB over {d['hashing_launches']} launches per step"
+        f = sorted(x for x in os.listdir(pdir) if x.endswith(suffix))[-1]
+        return json.load(open(os.path.join(pdir, f))), f"profiles/{f}"
     except Exception:
         return None, None
+
+
+def ncu_traffic() -> tuple:
+    """DRAM bytes per hashing launch from the committed ncu capture (profiles/rNN_traffic.json), or None."""
+    d, f = latest_profile("_traffic.json")
+    if not d:
+        return None, None
+    return d["hashing_dram_bytes_per_launch"], f"{f}: {d['hashing_dram_bytes_per_step'] / 1e9:.2f} GB over {d['hashing_launches']} launches per step"
+
+
+def build_record(sp) -> dict:
+    """Was the library this run loaded compiled on this machine, or did it travel with the tree?"""
+    rec = {"library": os.path.relpath(sp.LIB_PATH, ROOT), "host": socket.gethostname()}
+    try:
+        rec["sha256_16"] = hashlib.sha256(open(sp.LIB_PATH, "rb").read()).hexdigest()[:16]
+        info = json.load(open(sp.LIB_PATH.replace(".so", ".build.json")))
+        try:
+            boot = open("/proc/sys/kernel/random/boot_id").read().strip()
+        except Exception:
+            boot = ""
+        rec.update({"built_on": info.get("host"), "built_at": info.get("time"), "nvcc": info.get("nvcc"),
+                    "compiled_on_this_host": info.get("host") == rec["host"] and info.get("boot_id", "?") == boot})
+        if not rec["compiled_on_this_host"]:
+            rec["note"] = "prebuilt libstark_b200.so shipped with the tree (sm_100a cross-compiled by __graft_entry__.build())"
+    except Exception as e:
+        rec["note"] = f"no build record next to the library ({e})"
+    return rec
 
 
 def layer_sizes(log_n: int, log_deg: int) -> list[int]:
@@ -168,6 +204,21 @@ def cpu_step(orc, coeffs, log_n, queries):
     return ch
 
 
+def cpu_time_steps(orc, log_n, log_blowup, warm, steps=None, budget_s=None):
+    """ms per CPU step at a 2^log_n domain: `steps` timed steps, or as many as fit `budget_s` (at least 2)."""
+    coeffs = orc.synthetic_poly_exact_degree(43, 1 << (log_n - log_blowup), P)
+    for _ in range(warm):
+        cpu_step(orc, coeffs, log_n, QUERIES)
+    n, t0, state = 0, time.perf_counter(), None
+    while True:
+        state = cpu_step(orc, coeffs, log_n, QUERIES).state
+        n += 1
+        el = time.perf_counter() - t0
+        if (steps is not None and n >= steps) or (steps is None and n >= 2 and el >= budget_s) or el > 120.0:
+            break
+    return el / n * 1e3, n, state
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -175,29 +226,30 @@ def run_reference(args):
     from oracle import pyoracle as orc
     orc.build()
     orc.set_num_threads(len(os.sched_getaffinity(0)))      # torchrun exports OMP_NUM_THREADS=1: use every host core we may run on
-    log_n = args.cpu_log_n
+    log_n = args.cpu_log_n or args.log_n
     log_deg = log_n - args.log_blowup
-    coeffs = orc.synthetic_poly_exact_degree(43, 1 << log_deg, P)
-    for _ in range(max(args.warmup, 1)):
-        cpu_step(orc, coeffs, log_n, QUERIES)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_step(orc, coeffs, log_n, QUERIES)
-    dt = (time.perf_counter() - t0) / args.steps
-    val = (1 << log_n) / dt / 1e6
+    ms, n_steps, state = cpu_time_steps(orc, log_n, args.log_blowup, max(args.warmup, 1), steps=args.steps)
+    val = (1 << log_n) / (ms * 1e-3) / 1e6
     cores = orc.num_threads()
-    sample = (f"fri_commit+decommit_fri at a 2^{log_n} domain (degree 2^{log_deg}-1, blowup {1 << args.log_blowup}, {QUERIES} queries): "
-              f"1/{1 << (args.log_n - log_n)} of the 2^{args.log_n} workload per step; oracle NTT tier, OpenMP, SHA-NI="
-              f"{bool(orc.lib().or_sha256_accel_active())}")
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    same = log_n == args.log_n
+    sample = (f"{n_steps} x fri_commit+decommit_fri at a 2^{log_n} domain (degree 2^{log_deg}-1, blowup {1 << args.log_blowup}, {QUERIES} queries)"
+              + (": the full workload of the B200 arm" if same else f": 1/{1 << (args.log_n - log_n)} of the 2^{args.log_n} workload per step")
+              + f"; oracle NTT tier, OpenMP, SHA-NI={bool(orc.lib().or_sha256_accel_active())}")
+    extra = {}
+    if same and log_n > 20:                               # the cache-resident figure of round 1, kept for comparison
+        ms20, n20, _ = cpu_time_steps(orc, 20, args.log_blowup, 1, budget_s=3.0)
+        extra = {"sample_2e20": {"value": (1 << 20) / (ms20 * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms20, "steps": n20}}
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": n_steps,
+            "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"cfg3: FRI commit at 2^{args.log_n} domain, blowup 8, {QUERIES} queries (bounded CPU sample at 2^{log_n})",
-                       "log_domain": args.log_n, "sample_log_domain": log_n},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                             "literal": literal_tier(orc, args.log_n, args.log_blowup)},
+            "config": {"workload": f"cfg3: fri_commit + decommit_fri, degree 2^{log_deg}-1 polynomial on the 2^{log_n} coset 5*<w>, "
+                                   f"p=3221225473, {log_deg + 1} layers, {QUERIES} queries" + ("" if same else f" (bounded CPU sample of the 2^{args.log_n} workload)"),
+                       "log_domain": args.log_n, "sample_log_domain": log_n, "blowup": 1 << args.log_blowup, "queries": QUERIES,
+                       "same_config_as_b200_arm": same},
+            "cpu_baseline": dict({"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                  "literal": literal_tier(orc, args.log_n, args.log_blowup)}, **extra),
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
+            "gpu_launches": 0, "transcript_state": state,
             "note": "the reference is Rust nightly + un-vendored crates and cannot be built in this image; this is the C oracle port of its "
                     "algorithm (NTT tier: same bits as the literal Horner tier, which is O(N*d) and cannot reach this size)"}
     print(json.dumps(line), flush=True)
@@ -237,6 +289,225 @@ def pipelined_throughput(sp, synth, log_n, log_deg, n, device, instances=3, reps
             "note": "independent polynomials committed concurrently on one GPU from separate host threads / contexts / streams"}
 
 
+class Timer:
+    """CUDA events on the library's stream around a host-driven phase; max over ranks."""
+
+    def __init__(self, torch, dist, stream, world, local):
+        self.torch, self.dist, self.stream, self.world, self.local = torch, dist, stream, world, local
+
+    def sync_all(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def run(self, fn):
+        torch = self.torch
+        self.sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        out = fn()
+        e1.record(self.stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), out
+
+    def max_over_ranks(self, ms: float) -> float:
+        if self.world == 1:
+            return ms
+        t = self.torch.tensor([ms], device=f"cuda:{self.local}")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    @staticmethod
+    def _release(out):
+        for o in (out if isinstance(out, tuple) else (out,)):
+            if hasattr(o, "free"):
+                o.free()
+
+    def best(self, fn, reps: int, keep=None):
+        """min over `reps` of the max-over-ranks time; returns (ms, last result); earlier results are freed."""
+        best, last = None, None
+        for _ in range(reps):
+            if last is not None:
+                self._release(last)
+            ms, out = self.run(fn)
+            ms = self.max_over_ranks(ms)
+            best = ms if best is None else min(best, ms)
+            last = out
+        return best, last
+
+
+def sharded_block(args, sp, synth, ctx, tm: Timer, rank, world, local, mix_peak):
+    """The two BASELINE configs that shard, at fixed total size, asserted against the committed oracle goldens."""
+    import numpy as np
+    import torch
+    gold_path = os.path.join(ROOT, "tests", "golden", "sharded.json")
+    gold = json.load(open(gold_path))
+    g4, g5 = (gold["cfg4_small"], gold["cfg5_small"]) if args.sharded_small else (gold["cfg4"], gold["cfg5"])
+    mg = sp.MultiGpu.from_torch(ctx)
+    out = {"world": world, "scaling": "strong", "goldens": "tests/golden/sharded.json (CPU oracle, tests/golden/make_golden_sharded.py)",
+           "timing": "CUDA events on the library's stream around each phase, max over ranks, best of the repetitions"}
+
+    # ---------------- cfg4: 64 columns x 2^22 rows, column c -> rank c mod N
+    log_rows, n_cols, log_b = g4["log_rows"], g4["n_cols"], g4["log_blowup"]
+    n_rows, N4 = 1 << log_rows, 1 << (log_rows + log_b)
+    mine = list(range(rank, n_cols, world))
+    pin = torch.empty((max(len(mine), 1), n_rows), dtype=torch.int64).pin_memory()
+    pin_np = pin.numpy().view(np.uint64)
+    cols = {}
+    for k, c in enumerate(mine):
+        pin_np[k, :] = synth.synthetic_column(g4["seed_base"] + c, n_rows, P)
+        cols[c] = pin_np[k]
+    commit = lambda: mg.commit_columns(cols, n_cols, log_rows, g4["offset_in"], log_b, g4["offset_out"])
+    commit()                                                            # warm-up: twiddles, pool blocks
+    reps4 = 3 if world > 1 else 2
+    ms4, roots = tm.best(commit, reps4)
+    assert [r.hex() for r in roots] == g4["roots"], "cfg4: the gathered roots differ from the oracle's goldens"
+    comp4 = n_cols * (3 * N4 - 2)
+    out["cfg4"] = {"workload": f"{n_cols} columns x 2^{log_rows} rows -> coset LDE 2^{log_rows + log_b} + Merkle commit per column, column c -> rank c mod N, "
+                               f"{n_cols} roots all-gathered", "ms": ms4, "Melem_per_s": n_cols * N4 / (ms4 * 1e-3) / 1e6,
+                   "roots_equal_golden": True, "roots_sha256": g4["roots_sha256"], "columns_per_gpu": len(mine),
+                   "h2d_bytes_per_gpu": len(mine) * n_rows * 8, "collective": f"ncclAllGather of {32 * -(-n_cols // world)} bytes per rank",
+                   "roofline": {"bound": "int", "achieved": 1384.0 * comp4 / world / (ms4 * 1e-3) / 1e12, "peak": mix_peak, "unit": "Tint-op/s per GPU",
+                                "frac": (1384.0 * comp4 / world / (ms4 * 1e-3) / 1e12 / mix_peak) if mix_peak else None,
+                                "note": "hashing int-ops of the whole phase (upload, LDE and root gather included in the time) per GPU"}}
+    del cols, pin, pin_np
+
+    # ---------------- cfg5: one 2^26-point column
+    log_n, q5 = g5["log_n"], g5["queries"]
+    N5, blk = 1 << log_n, (1 << log_n) // world
+    cvec = ctx.upload(synth.synthetic_poly_exact_degree(g5["seed"], 1 << (log_n - 3), P))
+    exch_bytes = 2 * 4 * blk * (world - 1) // world                      # two exchanges, (G-1)/G of the rank's 4*N/G bytes each
+    c5 = {"workload": f"degree 2^{log_n - 3}-1 polynomial on the 2^{log_n} coset 5*<w>: four-step LDE, leaf-range commit, fri_commit with the sharded "
+                      f"layer 0 + {q5} openings", "exchange_bytes_per_gpu_per_transform": exch_bytes}
+    for name, transport in (("lde_nccl_all_to_all", 0), ("lde_peer_memory", 1)):
+        run = lambda: mg.fourstep_lde(cvec, log_n, g5["offset"], transport)
+        run().free()                                                    # warm-up (allocations, IPC mappings, NCCL channels)
+        ms, b = tm.best(run, 5, keep=lambda v: None)
+        tree, root, subs = mg.commit_leaf_ranges(b)
+        assert root.hex() == g5["roots"][0], f"cfg5 ({name}): the root of the distributed column differs from the oracle's golden"
+        tree.free()
+        c5[name] = {"ms": ms, "Melem_per_s": N5 / (ms * 1e-3) / 1e6, "root_equals_golden": True,
+                    "exchange_GBps_per_gpu": (exch_bytes / (ms * 1e-3) / 1e9) if world > 1 else None,
+                    "note": "GB/s = exchanged bytes / WHOLE transform time (both NTT phases included), a lower bound on the link rate"}
+    blkv = mg.fourstep_lde(cvec, log_n, g5["offset"], 1)
+
+    def commit_ranges():
+        t, root, subs = mg.commit_leaf_ranges(blkv)
+        t.free()
+        return root
+    commit_ranges()
+    ms_c, root = tm.best(commit_ranges, 3)
+    assert root.hex() == g5["roots"][0]
+    compl = 3 * N5 - 2
+    c5["leaf_range_commit"] = {"ms": ms_c, "Melem_per_s": N5 / (ms_c * 1e-3) / 1e6, "root_equals_golden": True,
+                               "roofline": {"bound": "int", "achieved": 1384.0 * compl / world / (ms_c * 1e-3) / 1e12, "peak": mix_peak,
+                                            "unit": "Tint-op/s per GPU", "frac": (1384.0 * compl / world / (ms_c * 1e-3) / 1e12 / mix_peak) if mix_peak else None}}
+    blkv.free()
+
+    def fri():
+        ch = sp.Channel(P) if rank == 0 else None
+        f = mg.fri_commit(cvec, log_n, g5["offset"], ch, 1)
+        mg.decommit_fri(f, q5, N5 - 1, ch)
+        return f, ch
+    f, ch = fri()
+    f.free()
+    ms_f, (f, ch) = tm.best(fri, 3, keep=None)
+    if rank == 0:
+        pr = f.proof
+        assert pr.num_layers == g5["num_layers"] and [pr.tree(k).root() for k in range(1, pr.num_layers)] == g5["roots"][1:]
+        assert ch.state == g5["final_state"] and hashlib.sha256(ch.proof_flat()).hexdigest() == g5["proof_sha256"], \
+            "cfg5: the transcript of the sharded fri_commit + decommit_fri differs from the oracle's golden"
+    f.free()
+    c5["fri_commit_and_openings"] = {"ms": ms_f, "Melem_per_s": N5 / (ms_f * 1e-3) / 1e6, "transcript_equals_golden": True,
+                                     "transcript_state": g5["final_state"], "layers": g5["num_layers"], "queries": q5,
+                                     "note": "four-step LDE + leaf-range commit + layer 0 collected on rank 0 + the unpartitioned fold/commit "
+                                             "loop and openings (rank 0; north-star: nothing else is partitioned)"}
+    # ---------------- the same workloads on ONE GPU, measured by rank 0 in this run (the other ranks wait): strong-scaling reference
+    tm.sync_all()
+    if world > 1:
+        single = {}
+        if rank == 0:
+            solo = Timer(torch, None, tm.stream, 1, local)
+            g1 = sp.MultiGpu(ctx, 0, 1)
+            ev = lambda: ctx.coset_evaluate_dev(cvec, log_n, g5["offset"])
+            ev().free()
+            single["lde_ms"], e = solo.best(ev, 3, keep=lambda v: None)
+            mk = lambda: sp.MerkleTree.new(ctx, e)
+            mk().free()
+            single["commit_ms"], t = solo.best(mk, 2, keep=lambda v: None)
+            assert t.root_bytes().hex() == g5["roots"][0]
+            t.free(); e.free()
+
+            def fri1():
+                ch1 = sp.Channel(P)
+                pr1 = sp.fri_commit(ctx, cvec, sp.CosetFri(ctx, g5["offset"], log_n), ch1)
+                sp.decommit_fri(q5, N5 - 1, pr1, ch1)
+                return pr1, ch1
+            fri1()[0].free()
+            single["fri_ms"], (pr1, ch1) = solo.best(fri1, 2, keep=None)
+            assert ch1.state == g5["final_state"]
+            pr1.free()
+            # one cfg4 column on one GPU x n_cols (columns are independent: the single-GPU time of the whole config)
+            colp = torch.empty(n_rows, dtype=torch.int64).pin_memory()
+            colp_np = colp.numpy().view(np.uint64)
+            colp_np[:] = synth.synthetic_column(g4["seed_base"], n_rows, P)
+            one = lambda: g1.commit_columns({0: colp_np}, 1, log_rows, g4["offset_in"], log_b, g4["offset_out"])
+            one()
+            ms1, r1 = solo.best(one, 3)
+            assert r1[0].hex() == g4["roots"][0]
+            single["cfg4_ms"] = ms1 * n_cols
+            single["cfg4_note"] = f"{n_cols} x the measured time of one column ({ms1:.3f} ms) on one GPU"
+            g1.close()
+        tm.sync_all()
+        if rank == 0:
+            out["single_gpu_reference"] = single
+            out["cfg4"]["speedup_vs_1gpu"] = single["cfg4_ms"] / ms4
+            out["cfg4"]["efficiency"] = single["cfg4_ms"] / ms4 / world
+            c5["lde_peer_memory"]["speedup_vs_1gpu"] = single["lde_ms"] / c5["lde_peer_memory"]["ms"]
+            c5["lde_nccl_all_to_all"]["speedup_vs_1gpu"] = single["lde_ms"] / c5["lde_nccl_all_to_all"]["ms"]
+            c5["leaf_range_commit"]["speedup_vs_1gpu"] = single["commit_ms"] / ms_c
+            c5["leaf_range_commit"]["efficiency"] = single["commit_ms"] / ms_c / world
+            c5["fri_commit_and_openings"]["speedup_vs_1gpu"] = single["fri_ms"] / ms_f
+    out["cfg5"] = c5
+    cvec.free()
+    mg.close()
+    return out
+
+
+def prove_block(sp, ctx, tm: Timer, log_n, log_blowup, with_oracle: bool):
+    """`prove ms at a 2^24 domain` (BASELINE.json metric): stark101_prove, the build-defined FibonacciSq prover of DESIGN.md
+    cfg1 scaled to a 2^(log_n - log_blowup) - 1 row trace, 3 queries; transcript asserted equal to the CPU oracle's."""
+    log_trace, q = log_n - log_blowup, 3
+
+    def prove():
+        ch = sp.Channel(P)
+        sp.stark101_prove(ctx, ch, 3141592, log_trace, log_blowup, q)
+        return ch
+    prove()
+    ms, ch = tm.best(prove, 3)
+    t0 = time.perf_counter()
+    prove()
+    wall = (time.perf_counter() - t0) * 1e3
+    out = {"what": f"stark101_prove: FibonacciSq trace of 2^{log_trace}-1 rows, LDE/FRI domain 2^{log_n}, {q} queries (trace generation on the host included)",
+           "ms": ms, "wall_ms": wall, "transcript_state": ch.state, "proof_bytes": ch.proof_size()}
+    if with_oracle:
+        from oracle import pyoracle as orc
+        orc.build()
+        orc.set_num_threads(len(os.sched_getaffinity(0)))
+        och = orc.Channel(P)
+        t0 = time.perf_counter()
+        orc.stark101_prove(och, 3141592, log_trace, log_blowup, sp.G_DEFAULT, q, literal=False)
+        out["oracle_ms"] = (time.perf_counter() - t0) * 1e3
+        out["oracle_cores"] = orc.num_threads()
+        assert och.state == ch.state and och.proof_flat() == ch.proof_flat(), "stark101_prove: GPU transcript differs from the oracle's"
+        out["transcript_equals_oracle"] = True
+        claimed = int.from_bytes(ch.proof[0][40:48], "big")
+        ok, why = sp.stark101_verify(ch.proof_flat(), claimed, log_trace, log_blowup, q)
+        assert ok, why
+        out["verifier_accepts"] = True
+    return out
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -257,6 +528,7 @@ def run_b200(args):
     n = 1 << log_n
     ctx = sp.Context(P, sp.G_DEFAULT, local)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local)
+    tm = Timer(torch, dist, stream, world, local)
     coeffs = synth.synthetic_poly_exact_degree(43 + rank, 1 << log_deg, P)
     pinned = torch.empty(1 << log_deg, dtype=torch.int64).pin_memory()
     pinned_np = pinned.numpy().view(np.uint64)
@@ -280,8 +552,9 @@ def run_b200(args):
         mine = torch.frombuffer(bytearray(pr.tree(0).root_bytes()), dtype=torch.uint8).to(f"cuda:{local}")
         dist.all_gather_into_tensor(roots_out.view(-1), mine)
 
-    def timed(src, steps, flush_l2=True):
-        """max-over-ranks device time per step (ms) and the last step's artefacts."""
+    def timed(src, steps, flush_l2=True, after=None):
+        """max-over-ranks device time per step (ms) and the last step's artefacts.  `after(pr)`: extra work inside the
+        timed region (e2e_full: the layers copied back by value)."""
         total = 0.0
         pr = ch = None
         for _ in range(steps):
@@ -296,6 +569,8 @@ def run_b200(args):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             pr, ch = step(src)
+            if after is not None:
+                after(pr)
             gather_roots(pr)
             if world > 1:
                 stream.wait_stream(torch.cuda.current_stream())
@@ -337,6 +612,7 @@ def run_b200(args):
     final_state = ch.state
     n_layers = pr.num_layers
     d2h = 32 * n_layers + 8 * n_layers + len(pr.open([0])) * QUERIES
+    layer_lens = [pr.layer_len(k) for k in range(n_layers)]
     pr.free()
 
     # ---- where the step's wall time goes on the host side (one extra, untimed-for-the-metric step)
@@ -355,102 +631,136 @@ def run_b200(args):
     ms_e2e, pr2, ch2 = timed(pinned_np, args.steps)
     assert ch2.state == final_state, "device-resident and host-buffer paths disagree"
     pr2.free()
+    # ---- end to end with FRIProof BY VALUE: every layer copied back as u64 (fri_commit.rs:117-121 returns Vec<Vec<FieldElement>>)
+    layers_pin = torch.empty(sum(layer_lens), dtype=torch.int64).pin_memory()
+    layers_np = layers_pin.numpy().view(np.uint64)
+
+    def copy_layers_back(p):
+        off = 0
+        for k, ln in enumerate(layer_lens):
+            p.layer(k, 0, ln, out=layers_np[off:off + ln])
+            off += ln
+    timed(pinned_np, 1, after=copy_layers_back)
+    ms_full, pr4, _ = timed(pinned_np, max(2, min(args.steps, 5)), after=copy_layers_back)
+    assert int(layers_np[0]) == int(pr4.layer(0, 0, 1)[0])
+    pr4.free()
+    del layers_pin, layers_np
 
     line = {"metric": METRIC, "value": world * n / (ms_dev * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "dtype_note": "u32 Montgomery field arithmetic (p = 3221225473 < 2^32; u64 at the ABI) and 32-bit SHA-256 words",
             "data": "synthetic",
             "config": {"workload": f"cfg3: fri_commit + decommit_fri, degree 2^{log_deg}-1 polynomial on the 2^{log_n} coset 5*<w>, "
-                                   f"p=3221225473, {n_layers} layers, {QUERIES} queries; one column per GPU",
+                                   f"p=3221225473, {n_layers} layers, {QUERIES} queries; one column per GPU (replicas: the FRI loop is not partitioned)",
                        "log_domain": log_n, "blowup": 1 << args.log_blowup, "queries": QUERIES, "layers": n_layers,
                        "l2": "256 MiB buffer written between timed iterations; layer 0 + its tree = 576 MiB > L2",
-                       "prove_ms": ms_dev},
+                       "fri_commit_decommit_ms": ms_dev,
+                       "fri_layers": "device-resident handles (stark_fri_layer_read copies ranges on demand); e2e_full copies all of them back by value"},
             "e2e": {"value": world * n / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": 8 << log_deg, "d2h_bytes_per_step": d2h},
+            "e2e_full": {"value": world * n / (ms_full * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_full,
+                         "h2d_bytes_per_step": 8 << log_deg, "d2h_bytes_per_step": d2h + 8 * sum(layer_lens),
+                         "note": "e2e plus every FRI layer copied to pinned host memory as u64, i.e. FRIProof.fri_layers by value"},
             "gpu_launches": int(launches), "clocks": clocks, "transcript_state": final_state,
             "ms_per_rank": per_rank_dev if world > 1 else None,
             "host_breakdown_ms": host_breakdown}
 
+    # ---- per-kernel durations, live, CUDA events on the launching stream (separate instrumented steps; every rank runs
+    # them so that the collectives inside `timed` stay matched, rank 0 reports)
+    hbm_peak, peak_src = measured_peaks()
+    alg = algorithmic_counts(log_n, log_deg)
+    mix_peak = None
+    if not args.no_kernel_timing:
+        ctx.set_timing(True)
+        ctx.read_timing()
+        ksteps = max(2, min(args.steps, 5))
+        ms_instr, pr3, _ = timed(dev_coeffs, ksteps)
+        kt = ctx.read_timing()
+        ctx.set_timing(False)
+        pr3.free()
+        alu_peak, mix_peak = ctx.measure_int_peak()
+        hash_ms = (kt["merkle_leaf"]["ms"] + kt["merkle_node"]["ms"]) / ksteps
+        hash_ops = (kt["merkle_leaf"]["units"] + kt["merkle_node"]["units"]) / ksteps
+        hash_launches = (kt["merkle_leaf"]["launches"] + kt["merkle_node"]["launches"]) // ksteps
+        achieved = hash_ops / (hash_ms * 1e-3) / 1e12
+        pipe, pipe_src = latest_profile("_pipe_util.json")
+        line["roofline"] = {
+            "kernel": "merkle_subtree_kernel<VALUES|FOLD|DIGESTS> (fused fold + leaf hash, 3 levels per launch) + merkle_tail_kernel",
+            "bound": "int", "achieved": achieved, "peak": mix_peak, "unit": "Tint-op/s", "frac": achieved / mix_peak,
+            "peak_source": "stark_measure_int_peak on this GPU: register chains of SHF/LOP3/IADD3 (ALU pipe) and IMAD (FMA pipe) "
+                           "issued 3:1, the mix of the algorithmic count (1024 rotate/logic instructions : 360 adds per "
+                           f"compression); the ALU pipe alone peaks at {alu_peak:.1f}, and 1024 of the 1384 can only run there",
+            "alu_pipe_peak": alu_peak, "frac_of_alu_pipe_peak": achieved / alu_peak,
+            "executed_alu_pipe_pct": pipe, "executed_alu_pipe_pct_source": pipe_src,
+            "traffic": ncu_traffic()[0], "traffic_source": ncu_traffic()[1],
+            "launches_per_step": hash_launches, "kernel_ms_per_step": hash_ms,
+            "share_of_step": hash_ms / ms_instr, "rank": rank,
+            "algorithmic": "1384 int-ops per SHA-256 compression; leaf = 1, node = 2 compressions (SURVEY.md 8d)",
+            "note": "achieved counts the ALGORITHMIC 1384 instructions per compression against the two-pipe issue peak; the kernel "
+                    "executes fewer on the leaf launches (specialised leaf block) and more on node launches (1384 + 904 per parent); "
+                    "`executed_alu_pipe_pct` is ncu's sm__pipe_alu_cycles_active per launch class, the executed-instruction view"}
+        ntt_ms = kt["ntt"]["ms"] / ksteps
+        ntt_gbs = kt["ntt"]["units"] / ksteps / (ntt_ms * 1e-3) / 1e9 if ntt_ms else None
+        # the fused fold+hash launches also stream every layer once: algorithmic bytes of those launches
+        leaf_bytes = alg["bytes_fused_min"] - (8 * (1 << log_deg) + 8 * n)
+        ntt_ops = (1 << args.log_blowup) * ((1 << log_deg) // 2 * log_deg * 12 + 6 * (1 << log_deg))
+        line["roofline_hbm"] = {
+            "ntt": {"bound": "hbm", "achieved": ntt_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ntt_gbs / hbm_peak if ntt_gbs else None,
+                    "kernel_ms_per_step": ntt_ms, "launches_per_step": kt["ntt"]["launches"] // ksteps,
+                    "algorithmic": "8 B per coefficient read + 8 B per evaluation written (SURVEY.md 8d LDE n->N)",
+                    # (n/2) log2 n butterflies x (mul-mod + add-mod + sub-mod); counted as 12 int-ops per butterfly
+                    # (the round-1 instruction count; the carry-predicated butterfly of round 2 executes 9): in this 32-bit field
+                    # the transform is integer-bound, not HBM-bound
+                    "int": {"achieved": ntt_ops / (ntt_ms * 1e-3) / 1e12, "peak": mix_peak, "unit": "Tint-op/s",
+                            "frac": ntt_ops / (ntt_ms * 1e-3) / 1e12 / mix_peak,
+                            "algorithmic": "12 int-ops per butterfly, (n/2)*log2(n) butterflies per size-n transform, "
+                                           "2^blowup transforms + 6 per point for the coset shift"} if ntt_ms else None},
+            "fold_and_hash": {"bound": "hbm", "achieved": leaf_bytes / (hash_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                              "frac": leaf_bytes / (hash_ms * 1e-3) / 1e9 / hbm_peak,
+                              "note": "same launches as `roofline`: integer-bound, HBM fraction shown for completeness"},
+            "peak_source": peak_src}
+        line["kernel_ms"] = {k: v["ms"] / ksteps for k, v in kt.items()}
+        line["instrumented_ms_per_step"] = ms_instr
+    line["algorithmic"] = alg
+    line["build"] = build_record(sp)
+
+    # ---- the configs that shard (strong scaling), every N including 1
+    if not args.no_sharded:
+        line["sharded"] = sharded_block(args, sp, synth, ctx, tm, rank, world, local, mix_peak)
+
     if rank == 0:
-        # ---- per-kernel durations, live, CUDA events on the launching stream (separate instrumented steps)
-        hbm_peak, peak_src = measured_peaks()
-        alg = algorithmic_counts(log_n, log_deg)
-        if not args.no_kernel_timing and world == 1:
-            ctx.set_timing(True)
-            ctx.read_timing()
-            ksteps = max(2, min(args.steps, 5))
-            ms_instr, pr3, _ = timed(dev_coeffs, ksteps)
-            kt = ctx.read_timing()
-            ctx.set_timing(False)
-            pr3.free()
-            alu_peak, mix_peak = ctx.measure_int_peak()
-            hash_ms = (kt["merkle_leaf"]["ms"] + kt["merkle_node"]["ms"]) / ksteps
-            hash_ops = (kt["merkle_leaf"]["units"] + kt["merkle_node"]["units"]) / ksteps
-            hash_launches = (kt["merkle_leaf"]["launches"] + kt["merkle_node"]["launches"]) // ksteps
-            achieved = hash_ops / (hash_ms * 1e-3) / 1e12
-            line["roofline"] = {
-                "kernel": "merkle_subtree_kernel<VALUES|FOLD|DIGESTS> (fused fold + leaf hash, 3 levels per launch) + merkle_tail_kernel",
-                "bound": "int", "achieved": achieved, "peak": mix_peak, "unit": "Tint-op/s", "frac": achieved / mix_peak,
-                "peak_source": "stark_measure_int_peak on this GPU: register chains of SHF/LOP3/IADD3 (ALU pipe) and IMAD (FMA pipe) "
-                               "issued 3:1, the mix of the algorithmic count (1024 rotate/logic instructions : 360 adds per "
-                               f"compression); the ALU pipe alone peaks at {alu_peak:.1f}, and 1024 of the 1384 can only run there",
-                "alu_pipe_peak": alu_peak, "frac_of_alu_pipe_peak": achieved / alu_peak,
-                "traffic": ncu_traffic()[0], "traffic_source": ncu_traffic()[1],
-                "launches_per_step": hash_launches, "kernel_ms_per_step": hash_ms,
-                "share_of_step": hash_ms / ms_instr,
-                "algorithmic": "1384 int-ops per SHA-256 compression; leaf = 1, node = 2 compressions (SURVEY.md 8d)",
-                "note": "achieved counts the ALGORITHMIC 1384 instructions per compression against the two-pipe issue peak; the kernel "
-                        "executes fewer (the padding block of a parent hash needs no message schedule), which is why the "
-                        "ALU-pipe-only fraction can pass 1.0 while ncu shows that pipe ~85% active (profiles/)"}
-            ntt_ms = kt["ntt"]["ms"] / ksteps
-            ntt_gbs = kt["ntt"]["units"] / ksteps / (ntt_ms * 1e-3) / 1e9 if ntt_ms else None
-            # the fused fold+hash launches also stream every layer once: algorithmic bytes of those launches
-            leaf_bytes = alg["bytes_fused_min"] - (8 * (1 << log_deg) + 8 * n)
-            line["roofline_hbm"] = {
-                "ntt": {"bound": "hbm", "achieved": ntt_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ntt_gbs / hbm_peak if ntt_gbs else None,
-                        "kernel_ms_per_step": ntt_ms, "launches_per_step": kt["ntt"]["launches"] // ksteps,
-                        "algorithmic": "8 B per coefficient read + 8 B per evaluation written (SURVEY.md 8d LDE n->N)",
-                        # (n/2) log2 n butterflies x (mul-mod + add-mod + sub-mod); 32-bit Montgomery product = 6
-                        # instructions, modular add / sub = 3 each; the blow-up is 2^b transforms of size n plus one product per
-                        # coefficient and shift for offset^j: in this 32-bit field the transform is integer-bound, not HBM-bound
-                        "int": (lambda ops: {"achieved": ops / (ntt_ms * 1e-3) / 1e12, "peak": mix_peak, "unit": "Tint-op/s",
-                                             "frac": ops / (ntt_ms * 1e-3) / 1e12 / mix_peak,
-                                             "algorithmic": "12 int-ops per butterfly, (n/2)*log2(n) butterflies per size-n transform, "
-                                                            "2^blowup transforms + 6 per point for the coset shift"})(
-                            (1 << args.log_blowup) * ((1 << log_deg) // 2 * log_deg * 12 + 6 * (1 << log_deg))) if ntt_ms else None},
-                "fold_and_hash": {"bound": "hbm", "achieved": leaf_bytes / (hash_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                  "frac": leaf_bytes / (hash_ms * 1e-3) / 1e9 / hbm_peak,
-                                  "note": "same launches as `roofline`: integer-bound, HBM fraction shown for completeness"},
-                "peak_source": peak_src}
-            line["kernel_ms"] = {k: v["ms"] / ksteps for k, v in kt.items()}
-            line["instrumented_ms_per_step"] = ms_instr
-        line["algorithmic"] = alg
+        # ---- prove ms at the headline domain (BASELINE.json metric), oracle beside it
+        if not args.no_prove:
+            try:
+                line["prove"] = prove_block(sp, ctx, Timer(torch, None, stream, 1, local), log_n, args.log_blowup,
+                                            with_oracle=(not args.no_cpu_baseline) and world == 1)
+            except AssertionError:
+                raise
+            except Exception as e:
+                line["prove"] = {"error": str(e)}
         # ---- saturated throughput: independent instances from separate host threads/contexts on the same GPU
         # (one instance's host-bound openings overlap another's device-bound commit); informational, `value` stays
-        # the single-instance figure that `prove_ms` describes
+        # the single-instance figure
         if world == 1 and not args.no_pipelined:
             try:
                 line["pipelined"] = pipelined_throughput(sp, synth, log_n, log_deg, n, local, instances=3, reps=max(3, min(args.steps, 6)))
             except Exception as e:                                   # never let the extra measurement break the line
                 line["pipelined"] = {"error": str(e)}
-        # ---- CPU baseline beside it (bounded sample, all host threads)
+        # ---- CPU baseline beside it: the SAME workload, all host threads, 10-30 s of CPU work
         if not args.no_cpu_baseline and world == 1:
             from oracle import pyoracle as orc          # the CPU baseline leg is the only use of the oracle in this arm
             orc.build()
             orc.set_num_threads(len(os.sched_getaffinity(0)))
-            cl = args.cpu_log_n
-            cc = orc.synthetic_poly_exact_degree(43, 1 << (cl - args.log_blowup), P)
-            cpu_step(orc, cc, cl, QUERIES)
-            reps, t0 = 0, time.perf_counter()
-            while reps < 3 or time.perf_counter() - t0 < 10.0:
-                cpu_step(orc, cc, cl, QUERIES)
-                reps += 1
-                if time.perf_counter() - t0 > 30.0:
-                    break
-            dt = (time.perf_counter() - t0) / reps
-            line["cpu_baseline"] = {"value": (1 << cl) / dt / 1e6, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
-                                    "sample": f"{reps} x fri_commit+decommit_fri at a 2^{cl} domain (1/{1 << (log_n - cl)} of the workload), "
-                                              f"oracle NTT tier + OpenMP, SHA-NI={bool(orc.lib().or_sha256_accel_active())}",
+            cl = args.cpu_log_n or log_n
+            ms_cpu, reps, cstate = cpu_time_steps(orc, cl, args.log_blowup, 1, budget_s=10.0)
+            if cl == log_n:
+                assert cstate == final_state, "the CPU oracle's transcript of the benchmark workload differs from the GPU's"
+            line["cpu_baseline"] = {"value": (1 << cl) / (ms_cpu * 1e-3) / 1e6, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+                                    "ms_per_step": ms_cpu, "same_config": cl == log_n,
+                                    "transcript_equals_gpu": (cstate == final_state) if cl == log_n else None,
+                                    "sample": f"{reps} x fri_commit+decommit_fri at a 2^{cl} domain"
+                                              + (" (the full workload)" if cl == log_n else f" (1/{1 << (log_n - cl)} of the workload)")
+                                              + f", oracle NTT tier + OpenMP, SHA-NI={bool(orc.lib().or_sha256_accel_active())}",
                                     "literal": literal_tier(orc, log_n, args.log_blowup)}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -11,8 +11,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "stark-prover_b200")
 CSRC = os.path.join(PKG, "csrc")
 OUT = os.path.join(PKG, "libstark_b200.so")
+INFO = os.path.join(PKG, "libstark_b200.build.json")
 BUILD = os.path.join(ROOT, "build")
-SOURCES = ["api.cu", "merkle.cu", "ntt.cu", "fri.cu", "stark101.cu", "peaks.cu", "fourstep.cu", "verify.cu"]
+SOURCES = ["api.cu", "merkle.cu", "ntt.cu", "fri.cu", "stark101.cu", "peaks.cu", "fourstep.cu", "verify.cu", "multi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 
@@ -20,6 +21,13 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 def _host_cxx() -> str | None:
     # the image's /opt/gcc wrapper lacks some spec files; prefer the distro compiler
     return "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else None
+
+
+def _boot_id() -> str:
+    try:
+        return open("/proc/sys/kernel/random/boot_id").read().strip()
+    except Exception:
+        return ""
 
 
 def _deps(src: str) -> list[str]:
@@ -63,9 +71,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
         list(ex.map(compile_one, jobs))
     if jobs or force or not os.path.exists(OUT):
-        r = subprocess.run(base + ["-shared", "-o", OUT] + objs + ["-lcudart"], capture_output=True, text=True)
+        r = subprocess.run(base + ["-shared", "-o", OUT] + objs + ["-lcudart", "-ldl"], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        # provenance of the binary (bench.py reports whether the library it ran was compiled on the box or travelled with the tree)
+        import json, socket, time
+        ver = subprocess.run([nvcc, "--version"], capture_output=True, text=True).stdout.strip().splitlines()
+        with open(INFO, "w") as fh:
+            json.dump({"host": socket.gethostname(), "boot_id": _boot_id(), "time": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()), "nvcc": ver[-2] if len(ver) >= 2 else "",
+                       "flags": NVCC_FLAGS + extra, "recompiled": [os.path.basename(j[0]) for j in jobs]}, fh)
     return OUT
 
 

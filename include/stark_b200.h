@@ -40,6 +40,8 @@ typedef struct stark_vec stark_vec;         /* device-resident Vec<FieldElement<
 typedef struct stark_tree stark_tree;       /* MerkleTree<M>            (src/merkle/mod.rs:5-7) */
 typedef struct stark_fri stark_fri;         /* FRIProof                 (src/fri/fri_commit.rs:9-13) */
 typedef struct stark_channel stark_channel; /* Channel<M>               (src/channel/channel.rs:14-20) */
+typedef struct stark_mg stark_mg;           /* a group of ranks, one GPU each (multi-GPU entry points below) */
+typedef struct stark_mg_fri stark_mg_fri;   /* FRIProof whose layer 0 is spread over the group */
 
 const char* stark_last_error(void);
 const char* stark_version(void);
@@ -132,14 +134,19 @@ int stark_pow_mul_dev(stark_ctx* ctx, stark_vec* v, size_t inner_len, size_t out
  *                           [N1/G][N2] buffer (peer_rows[s] = rank s's buffer; peer_rows[rank] = own buffer)
  *   stark_fourstep_phase_c  row transforms on the own buffer -> 32x32 transpose -> 128-byte stores into every peer's
  *                           natural-order block (peer_blocks[t])
- * Both calls return after their stores are complete; the caller places one barrier between them. */
+ * Hand-over between the phases.  peer_flags == NULL: both calls return after their stores are complete and the caller
+ * places one barrier between them.  peer_flags[s] = rank s's flag array (stark_peer_alloc of 2 * 16 words, zero-filled,
+ * opened on every rank): nothing is synchronised on the host -- phase A publishes `epoch` (1, 2, 3, ... per transform) to
+ * every peer when its stores are complete, phase C starts with a device-side wait for all peers' phase-A epochs and
+ * publishes its own, and stark_fourstep_wait(own flags, 1, ...) enqueues the wait for the block. */
 int stark_peer_alloc(stark_ctx* ctx, size_t n, stark_vec** out, uint8_t handle[64]);
 int stark_peer_open(stark_ctx* ctx, const uint8_t handle[64], void** dptr);
 int stark_peer_close(stark_ctx* ctx, void* dptr);
 int stark_fourstep_phase_a(stark_ctx* ctx, const stark_vec* coeffs, unsigned log_n, uint64_t offset, unsigned world,
-                           unsigned rank, void* const* peer_rows);
+                           unsigned rank, void* const* peer_rows, void* const* peer_flags, uint32_t epoch);
 int stark_fourstep_phase_c(stark_ctx* ctx, stark_vec* rows, unsigned log_n, unsigned world, unsigned rank,
-                           void* const* peer_blocks);
+                           void* const* peer_blocks, void* const* peer_flags, uint32_t epoch);
+int stark_fourstep_wait(stark_ctx* ctx, const void* own_flags, unsigned slot, unsigned world, uint32_t epoch);
 
 /* ---- merkle: src/merkle/mod.rs -------------------------------------------------------------------
  * stark_merkle_commit == MerkleTree::new(data)   :10-22   leaf = SHA-256(value.to_be_bytes()), rs_merkle tree
@@ -220,6 +227,45 @@ int stark_fri_commit_dev(stark_ctx* ctx, const stark_vec* coeffs, unsigned log_n
                          stark_channel* ch, stark_fri** out);
 int stark_decommit_fri_layers(const stark_fri* f, size_t index, stark_channel* ch);
 int stark_decommit_fri(const stark_fri* f, size_t num_queries, size_t max_index, stark_channel* ch);
+
+/* ---- multi-GPU: one process per GPU, one stark_mg per process ------------------------------------
+ * What shards: independent trace columns (cfg4), and one big column through the four-step NTT + contiguous leaf ranges
+ * (cfg5); the FRI folds, the smaller trees, the channel and the openings of layers >= 1 stay on rank 0 (north-star:
+ * "nothing else is partitioned").  The group owns an NCCL communicator (bound at run time, libnccl.so.2): rank 0 calls
+ * stark_mg_unique_id, hands the 128 bytes to the other ranks by whatever means the host program has (MPI, a file, its
+ * own RPC), and every rank calls stark_mg_create; stark_mg_adopt takes an existing ncclComm_t instead.  Calls on a group
+ * are collective: every rank makes the same calls in the same order.  world must be a power of two <= 16 for the
+ * four-step entry points. */
+int stark_mg_unique_id(uint8_t id[128]);
+int stark_mg_create(stark_ctx* ctx, const uint8_t id[128], unsigned rank, unsigned world, stark_mg** out);
+int stark_mg_adopt(stark_ctx* ctx, void* nccl_comm, unsigned rank, unsigned world, stark_mg** out);
+void stark_mg_destroy(stark_mg* mg);
+unsigned stark_mg_rank(const stark_mg* mg);
+unsigned stark_mg_world(const stark_mg* mg);
+int stark_mg_barrier(stark_mg* mg);
+/* cfg4.  Column c = columns[c][0 .. 2^log_rows) (host memory, read only on rank c % world; pinned memory lets the next
+ * upload run under the current column's hashing): trace column on offset_in*<g> -> coset LDE on offset_out*<h>
+ * (interpolate + evaluate, ops.rs:239 / :76) -> MerkleTree::new (merkle/mod.rs:10).  roots: n_cols * 32 bytes, all
+ * columns, identical on every rank.  ldes / trees (optional arrays of n_cols entries): the owner's device-resident LDE
+ * and tree of each of its columns (NULL for the others), to be destroyed by the caller. */
+int stark_mg_commit_columns(stark_mg* mg, size_t n_cols, const uint64_t* const* columns, unsigned log_rows, uint64_t offset_in,
+                            unsigned log_blowup, uint64_t offset_out, uint8_t* roots, stark_vec** ldes, stark_tree** trees);
+/* cfg5.  Evaluations of `coeffs` (held by every rank) on offset*<w_{2^log_n}> through the four-step NTT:
+ * transport 0 = all-to-all over NCCL, 1 = the producing kernels store into peer memory over NVLink with device-side epoch
+ * flags between the phases (no host synchronisation inside the transform).  *block = this rank's natural-order range
+ * [rank*N/G, (rank+1)*N/G); it aliases a buffer of the group that the next transform of the same size overwrites. */
+int stark_mg_fourstep_lde(stark_mg* mg, const stark_vec* coeffs, unsigned log_n, uint64_t offset, int transport, stark_vec** block);
+/* MerkleTree::new over a column held in contiguous leaf ranges: each rank hashes its range (an exact subtree), the
+ * subtree roots are gathered and the top levels finished on every rank.  subtree_roots: optional, world * 32 bytes. */
+int stark_mg_commit_leaf_ranges(stark_mg* mg, const stark_vec* block, stark_tree** subtree, uint8_t root[32], uint8_t* subtree_roots);
+/* fri_commit (fri_commit.rs:72-122) / decommit_fri (:168-179) with layer 0 distributed that way; `ch` is used on rank 0
+ * only and receives the single-GPU transcript byte for byte. */
+int stark_mg_fri_commit(stark_mg* mg, const stark_vec* coeffs, unsigned log_n, uint64_t offset, int transport, stark_channel* ch,
+                        stark_mg_fri** out);
+int stark_mg_decommit_fri(stark_mg_fri* f, size_t num_queries, size_t max_index, stark_channel* ch);
+const stark_fri* stark_mg_fri_proof(const stark_mg_fri* f);      /* rank 0: layers >= 1 live here (borrowed); NULL elsewhere */
+const stark_tree* stark_mg_fri_subtree(const stark_mg_fri* f);   /* this rank's subtree of layer 0 (borrowed) */
+void stark_mg_fri_destroy(stark_mg_fri* f);
 
 /* ---- verification (host side; completes what src/fri/fri_verify.rs sketches) ------------------------
  * stark_merkle_verify == the `MerkleTree::validate` that fri_verify.rs:109,137 calls and the reference never defines

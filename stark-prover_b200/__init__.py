@@ -79,8 +79,24 @@ def lib() -> C.CDLL:
     sig("stark_peer_alloc", I, vp, szt, C.POINTER(vp), vp)
     sig("stark_peer_open", I, vp, vp, C.POINTER(vp))
     sig("stark_peer_close", I, vp, vp)
-    sig("stark_fourstep_phase_a", I, vp, vp, C.c_uint, u64, C.c_uint, C.c_uint, C.POINTER(vp))
-    sig("stark_fourstep_phase_c", I, vp, vp, C.c_uint, C.c_uint, C.c_uint, C.POINTER(vp))
+    sig("stark_fourstep_phase_a", I, vp, vp, C.c_uint, u64, C.c_uint, C.c_uint, C.POINTER(vp), C.POINTER(vp), C.c_uint32)
+    sig("stark_fourstep_phase_c", I, vp, vp, C.c_uint, C.c_uint, C.c_uint, C.POINTER(vp), C.POINTER(vp), C.c_uint32)
+    sig("stark_fourstep_wait", I, vp, vp, C.c_uint, C.c_uint, C.c_uint32)
+    sig("stark_mg_unique_id", I, vp)
+    sig("stark_mg_create", I, vp, vp, C.c_uint, C.c_uint, C.POINTER(vp))
+    sig("stark_mg_adopt", I, vp, vp, C.c_uint, C.c_uint, C.POINTER(vp))
+    sig("stark_mg_destroy", None, vp)
+    sig("stark_mg_rank", C.c_uint, vp)
+    sig("stark_mg_world", C.c_uint, vp)
+    sig("stark_mg_barrier", I, vp)
+    sig("stark_mg_commit_columns", I, vp, szt, C.POINTER(vp), C.c_uint, u64, C.c_uint, u64, vp, C.POINTER(vp), C.POINTER(vp))
+    sig("stark_mg_fourstep_lde", I, vp, vp, C.c_uint, u64, I, C.POINTER(vp))
+    sig("stark_mg_commit_leaf_ranges", I, vp, vp, C.POINTER(vp), vp, vp)
+    sig("stark_mg_fri_commit", I, vp, vp, C.c_uint, u64, I, vp, C.POINTER(vp))
+    sig("stark_mg_decommit_fri", I, vp, szt, szt, vp)
+    sig("stark_mg_fri_proof", vp, vp)
+    sig("stark_mg_fri_subtree", vp, vp)
+    sig("stark_mg_fri_destroy", None, vp)
     sig("stark_vec_len", szt, vp)
     sig("stark_vec_device_ptr", vp, vp)
     sig("stark_vec_destroy", None, vp)
@@ -178,8 +194,9 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
-            for child in list(self._children):
-                child.free()
+            kids = list(self._children)
+            for child in [c for c in kids if not isinstance(c, MultiGpu)] + [c for c in kids if isinstance(c, MultiGpu)]:
+                child.free()                     # groups last: their proofs and buffers refer to them
             lib().stark_ctx_destroy(self.h)
             self.h = None
 
@@ -252,13 +269,22 @@ class Context:
     def peer_close(self, ptr: int) -> None:
         _check(lib().stark_peer_close(self.h, C.c_void_p(ptr)))
 
-    def fourstep_phase_a(self, coeffs: "Vec", log_n: int, offset: int, world: int, rank: int, peer_rows: Sequence[int]) -> None:
+    def fourstep_phase_a(self, coeffs: "Vec", log_n: int, offset: int, world: int, rank: int, peer_rows: Sequence[int],
+                         peer_flags: Optional[Sequence[int]] = None, epoch: int = 0) -> None:
+        """peer_flags None: returns when the peer stores are complete (host barrier before phase C).  With the peers' flag
+        arrays: nothing is synchronised, the hand-over happens on the device (epoch = 1, 2, 3, ... per transform)."""
         arr = (vp * world)(*[C.c_void_p(p) for p in peer_rows])
-        _check(lib().stark_fourstep_phase_a(self.h, coeffs.h, log_n, offset, world, rank, arr))
+        fl = (vp * world)(*[C.c_void_p(p) for p in peer_flags]) if peer_flags is not None else None
+        _check(lib().stark_fourstep_phase_a(self.h, coeffs.h, log_n, offset, world, rank, arr, fl, epoch))
 
-    def fourstep_phase_c(self, rows: "Vec", log_n: int, world: int, rank: int, peer_blocks: Sequence[int]) -> None:
+    def fourstep_phase_c(self, rows: "Vec", log_n: int, world: int, rank: int, peer_blocks: Sequence[int],
+                         peer_flags: Optional[Sequence[int]] = None, epoch: int = 0) -> None:
         arr = (vp * world)(*[C.c_void_p(p) for p in peer_blocks])
-        _check(lib().stark_fourstep_phase_c(self.h, rows.h, log_n, world, rank, arr))
+        fl = (vp * world)(*[C.c_void_p(p) for p in peer_flags]) if peer_flags is not None else None
+        _check(lib().stark_fourstep_phase_c(self.h, rows.h, log_n, world, rank, arr, fl, epoch))
+
+    def fourstep_wait(self, own_flags: int, slot: int, world: int, epoch: int) -> None:
+        _check(lib().stark_fourstep_wait(self.h, C.c_void_p(own_flags), slot, world, epoch))
 
     def zeros(self, n: int) -> "Vec":
         h = vp()
@@ -518,11 +544,14 @@ class FriProof:
     def num_layers(self) -> int: return lib().stark_fri_num_layers(self.h)
     def layer_len(self, k: int) -> int: return lib().stark_fri_layer_len(self.h, k)
 
-    def layer(self, k: int, offset: int = 0, n: Optional[int] = None) -> np.ndarray:
+    def layer(self, k: int, offset: int = 0, n: Optional[int] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """fri_layers[k] by value (u64 per element, as fri_commit.rs:117-121 returns them); `out` may be pinned memory"""
         n = self.layer_len(k) - offset if n is None else n
-        out = np.empty(n, dtype=np.uint64)
+        if out is None:
+            out = np.empty(n, dtype=np.uint64)
+        assert out.dtype == np.uint64 and out.size >= n and out.flags["C_CONTIGUOUS"]
         _check(lib().stark_fri_layer_read(self.h, k, offset, n, _ptr(out)))
-        return out
+        return out[:n]
 
     def tree(self, k: int) -> MerkleTree:
         return MerkleTree(self.ctx, lib().stark_fri_layer_tree(self.h, k), owned=False, keep=self)
@@ -553,7 +582,8 @@ class FriProof:
 
     def free(self):
         if getattr(self, "h", None):
-            lib().stark_fri_destroy(self.h)
+            if not getattr(self, "_borrowed", False):
+                lib().stark_fri_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -662,6 +692,120 @@ def stark101_verify(proof_flat: bytes, claimed_last: int, log_trace: int = 10, l
     _check(lib().stark101_verify(_ptr(buf), buf.size, modulus, generator, claimed_last, log_trace, log_blowup, num_queries,
                                  C.byref(ok), reason))
     return bool(ok.value), reason.value.decode()
+
+
+class MgFri:
+    """FRIProof whose layer 0 is spread over a MultiGpu group (stark_mg_fri)."""
+
+    def __init__(self, mg: "MultiGpu", h):
+        self.mg, self.h = mg, h
+        mg.ctx._adopt(self)
+
+    @property
+    def proof(self) -> Optional[FriProof]:
+        """rank 0: the layers >= 1 (and the adopted layer 0), borrowed; None on the other ranks"""
+        h = lib().stark_mg_fri_proof(self.h)
+        if not h:
+            return None
+        pr = FriProof.__new__(FriProof)
+        pr.ctx, pr.h, pr._borrowed = self.mg.ctx, h, True
+        return pr
+
+    def free(self):
+        if getattr(self, "h", None):
+            lib().stark_mg_fri_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class MultiGpu:
+    """One group of ranks, one GPU each (stark_mg): the C-level multi-GPU entry points of SURVEY.md 8(e).
+    The library owns its NCCL communicator; only the 128-byte unique id travels through the host program."""
+
+    def __init__(self, ctx: Context, rank: int, world: int, unique_id: Optional[bytes] = None):
+        h = vp()
+        uid = np.frombuffer(unique_id, dtype=np.uint8).copy() if unique_id is not None else np.zeros(128, dtype=np.uint8)
+        _check(lib().stark_mg_create(ctx.h, _ptr(uid), rank, world, C.byref(h)))
+        self.ctx, self.h, self.rank, self.world = ctx, h, rank, world
+        ctx._adopt(self)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        out = np.zeros(128, dtype=np.uint8)
+        _check(lib().stark_mg_unique_id(_ptr(out)))
+        return out.tobytes()
+
+    @classmethod
+    def from_torch(cls, ctx: Context, group=None) -> "MultiGpu":
+        """Bootstraps the group over an initialised torch.distributed process group (any backend): rank 0 makes the id,
+        the others receive it."""
+        import torch.distributed as dist
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return cls(ctx, 0, 1)
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        return cls(ctx, rank, world, box[0])
+
+    def barrier(self): _check(lib().stark_mg_barrier(self.h))
+
+    def commit_columns(self, columns, n_cols: int, log_rows: int, offset_in: int, log_blowup: int, offset_out: int, keep: bool = False):
+        """columns: {c: uint64 array} or a list indexed by column holding at least this rank's columns (c % world == rank).
+        Returns the roots of all columns (list of 32-byte strings); with keep=True also {c: (Vec, MerkleTree)} for the
+        rank's own columns."""
+        get = (lambda c: columns.get(c)) if isinstance(columns, dict) else (lambda c: columns[c] if c < len(columns) else None)
+        arrs = {c: _arr(get(c)) for c in range(self.rank, n_cols, self.world)}
+        ptrs = (vp * n_cols)(*[C.c_void_p(arrs[c].ctypes.data) if c in arrs else None for c in range(n_cols)])
+        roots = np.zeros(n_cols * 32, dtype=np.uint8)
+        ldes = (vp * n_cols)() if keep else None
+        trees = (vp * n_cols)() if keep else None
+        _check(lib().stark_mg_commit_columns(self.h, n_cols, ptrs, log_rows, offset_in, log_blowup, offset_out, _ptr(roots), ldes, trees))
+        out = [roots[32 * c:32 * c + 32].tobytes() for c in range(n_cols)]
+        if not keep:
+            return out
+        kept = {c: (Vec(self.ctx, C.c_void_p(ldes[c])), MerkleTree(self.ctx, C.c_void_p(trees[c]))) for c in arrs}
+        return out, kept
+
+    def fourstep_lde(self, coeffs: "Vec", log_n: int, offset: int, transport: int = 1) -> "Vec":
+        """This rank's natural-order block of the evaluations; transport 0 = NCCL all-to-all, 1 = peer-memory stores.
+        The block aliases a buffer the next transform of the same size overwrites."""
+        h = vp()
+        _check(lib().stark_mg_fourstep_lde(self.h, coeffs.h, log_n, offset, transport, C.byref(h)))
+        return Vec(self.ctx, h)
+
+    def commit_leaf_ranges(self, block: "Vec") -> tuple["MerkleTree", bytes, list[bytes]]:
+        h = vp()
+        root = np.zeros(32, dtype=np.uint8)
+        subs = np.zeros(32 * self.world, dtype=np.uint8)
+        _check(lib().stark_mg_commit_leaf_ranges(self.h, block.h, C.byref(h), _ptr(root), _ptr(subs)))
+        return MerkleTree(self.ctx, h, keep=block), root.tobytes(), [subs[32 * r:32 * r + 32].tobytes() for r in range(self.world)]
+
+    def fri_commit(self, coeffs: "Vec", log_n: int, offset: int, channel: Optional[Channel], transport: int = 1) -> MgFri:
+        h = vp()
+        _check(lib().stark_mg_fri_commit(self.h, coeffs.h, log_n, offset, transport, channel.h if channel is not None else None, C.byref(h)))
+        return MgFri(self, h)
+
+    def decommit_fri(self, f: MgFri, num_queries: int, max_index: int, channel: Optional[Channel]) -> None:
+        _check(lib().stark_mg_decommit_fri(f.h, num_queries, max_index, channel.h if channel is not None else None))
+
+    def free(self):
+        if getattr(self, "h", None):
+            lib().stark_mg_destroy(self.h)
+            self.h = None
+
+    def close(self):
+        self.free()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def exported_symbols() -> list[str]:

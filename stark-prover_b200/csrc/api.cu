@@ -118,7 +118,7 @@ extern "C" void stark_ctx_destroy(stark_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ctx->tw.clear();
-    ctx->small_fwd.release(); ctx->small_inv.release(); ctx->tail_counter.release(); ctx->deg_scratch.release();
+    ctx->small_fwd.release(); ctx->small_inv.release(); ctx->tail_counter.release(); ctx->fs_ticket.release(); ctx->deg_scratch.release();
     BlockCache::flush(ctx->stream);
     cudaStreamSynchronize(ctx->stream);
     for (int c = 0; c < stark_ctx::CAT_COUNT; c++) for (auto& pr : ctx->ev_used[c]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -511,12 +511,12 @@ static void words_to_bytes(const uint32_t w[8], uint8_t out[32]) {
     for (int i = 0; i < 8; i++) { out[4 * i] = (uint8_t)(w[i] >> 24); out[4 * i + 1] = (uint8_t)(w[i] >> 16); out[4 * i + 2] = (uint8_t)(w[i] >> 8); out[4 * i + 3] = (uint8_t)w[i]; }
 }
 // Builds the tree over `src` on the stream (no sync); the root lands in ctx->h_result.
-static std::unique_ptr<stark_tree> tree_launch(stark_ctx* ctx, DevBufPtr leaves, size_t n, const LeafSource& src) {
+static std::unique_ptr<stark_tree> tree_launch(stark_ctx* ctx, DevBufPtr leaves, size_t n, const LeafSource& src, HostResult* result = nullptr) {
     std::unique_ptr<stark_tree> t(new stark_tree());
     t->ctx = ctx; t->leaves = std::move(leaves);
     t->shape = TreeShape::make(n);
     t->nodes = DevBuf(t->shape.total * 32, ctx->stream);
-    merkle_build(ctx, src, t->shape, t->nodes.as<uint32_t>(), ctx->d_result);
+    merkle_build(ctx, src, t->shape, t->nodes.as<uint32_t>(), result ? result : ctx->d_result);
     return t;
 }
 static void tree_take_root(stark_tree* t) {   // after a stream sync
@@ -907,9 +907,10 @@ extern "C" int stark_fri_commit_dev(stark_ctx* ctx, const stark_vec* coeffs, uns
     API_END
 }
 // feeds one query's records to the channel in the reference's order (fri_commit.rs:145-163)
-static void send_query_records(const stark_fri* f, const uint8_t* rec, Channel& ch, size_t index) {
+static void send_query_records(const stark_fri* f, const uint8_t* rec, Channel& ch, size_t index, size_t first_layer = 0) {
     size_t off = 0;
-    for (auto& tp : f->trees) {
+    for (size_t k = first_layer; k < f->trees.size(); k++) {
+        auto& tp = f->trees[k];
         size_t len = tp->shape.n;
         size_t idx = index % len, sib = (idx + len / 2) % len;
         if (len == 1) ch.send(rec + off, 8);                                 // :147-149 (then falls through, as written)
@@ -1077,6 +1078,16 @@ void api_open_and_send(const stark_tree* t, size_t idx, Channel& ch) {
     ch.send(rec.data() + 8, pl);
 }
 void api_set_error(const std::string& s) { set_error(s); }
+// multi.cu: a tree over leaf values whose root lands in `result` (device alias of mapped host memory) -- no sync here
+std::unique_ptr<stark_tree> api_tree_launch_values(stark_ctx* ctx, DevBufPtr leaves, size_t n, HostResult* result) {
+    STARK_REQUIRE(n >= 1 && n <= ((size_t)1 << 32), "merkle: leaf count out of range");
+    LeafSource src; src.vals = leaves->as<uint32_t>();
+    return tree_launch(ctx, std::move(leaves), n, src, result);
+}
+int api_fri_commit_loop(stark_fri* f, stark_channel* chan) { return fri_commit_loop(f, chan); }
+void api_send_query_records(const stark_fri* f, const uint8_t* rec, Channel& ch, size_t index, size_t first_layer) {
+    send_query_records(f, rec, ch, index, first_layer);
+}
 // fri_commit for a polynomial whose evaluations on the FRI domain already exist (the composition polynomial of
 // stark101.cu is computed on the coset): layer 0 is `evals` as it stands -- no second transform, no copy of the
 // coefficients, which are consumed (the folds replace them anyway).  Same messages as stark_fri_commit_dev.

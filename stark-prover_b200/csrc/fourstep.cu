@@ -41,33 +41,115 @@ void fourstep_stage_input(stark_ctx* ctx, const uint32_t* coeffs, size_t len, ui
     STARK_CUDA(cudaGetLastError());
 }
 
-__global__ void fourstep_rows_kernel(const uint32_t* __restrict__ A, unsigned log_n1, unsigned log_n2, unsigned log_w, unsigned log_g,
-                                     unsigned rank, PeerPtrs peers, PowTable tw, FieldParams fp) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >> (log_n1 + log_w)) return;
-    uint32_t q = (uint32_t)(i >> log_w), c = (uint32_t)(i & (((size_t)1 << log_w) - 1));
-    uint32_t k1 = brev_bits(q, log_n1);
-    uint32_t n2 = (rank << log_w) + c;
-    uint32_t v = mont_mul(A[i], pow_lookup(tw, k1 * n2, fp), fp);            // k1*n2 < N
-    unsigned rows_per = log_n1 - log_g;
-    uint32_t owner = k1 >> rows_per, row = k1 & ((1u << rows_per) - 1);
-    peers.p[owner][((size_t)row << log_n2) + n2] = v;
+// ---- device-side hand-over between the phases (no host barrier, no stream synchronisation) ---------------------
+// Every rank owns a small peer-visible array of epoch words: flags[slot * MAX_PEERS + r] = the last transform for which
+// rank r has finished storing into THIS rank's buffer (slot 0: the rows of exchange 1, slot 1: the block of exchange 2).
+// A scatter kernel ends with: every thread fences its peer stores at system scope, the CTAs take a ticket, and the last
+// one publishes the epoch to all peers (st.release.sys).  The consumer runs a one-warp kernel in front of its next phase
+// that spins with ld.acquire.sys until all `world` words have reached the epoch; stream order does the rest.
+struct FlagPtrs { uint32_t* p[MAX_PEERS]; };
+struct FsSignal {
+    FlagPtrs flags;          // flags.p[s] = rank s's flag array (null pointers: no signalling, the host synchronises)
+    unsigned* ticket;        // zero between launches
+    unsigned slot, rank, world;
+    uint32_t epoch;
+};
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// tail of a scatter kernel; `first` = this CTA's thread that takes the ticket, `n_ctas` = CTAs in the grid
+__device__ __forceinline__ void fs_publish(const FsSignal& sg, bool first, unsigned n_ctas) {
+    if (!sg.ticket) return;
+    __threadfence_system();                      // this thread's peer stores are performed before anything that follows
+    __syncthreads();
+    if (first) {
+        const unsigned t = atomicAdd(sg.ticket, 1u);
+        if (t == n_ctas - 1) {
+            *sg.ticket = 0;                      // re-armed for the next launch on this stream
+            __threadfence_system();
+            for (unsigned s = 0; s < sg.world; s++) st_release_sys_u32(sg.flags.p[s] + sg.slot * MAX_PEERS + sg.rank, sg.epoch);
+        }
+    }
+}
+// Spins until every peer's epoch word of `slot` has reached `epoch` (wrap-safe compare).  After `timeout_ns` it gives up
+// and raises result->flag so that the host reports a lost peer instead of hanging.
+__global__ void fourstep_wait_kernel(const uint32_t* flags, unsigned slot, unsigned world, uint32_t epoch, HostResult* result,
+                                     unsigned long long timeout_ns) {
+    const unsigned r = threadIdx.x;
+    if (r >= world) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        const uint32_t v = ld_acquire_sys_u32(flags + slot * MAX_PEERS + r);
+        if ((int32_t)(v - epoch) >= 0) break;
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > timeout_ns) { if (result) result->flag = 0xdead0000u | (slot << 8) | r; break; }
+        __nanosleep(200);
+    }
+}
+
+// Four columns per thread: one 16-byte load, four twiddles, one 16-byte store into the owner (a warp covers 512 contiguous
+// bytes of a row).  dst = base[owner] + row * row_pitch + col_off + c, c the column inside this rank's slice:
+// peer memory: row_pitch = N2, col_off = rank * w (the owner's [N1/G][N2] matrix);  staging for NCCL: row_pitch = w, col_off = 0.
+__global__ void fourstep_rows_kernel(const uint32_t* __restrict__ A, unsigned log_n1, unsigned log_w, unsigned log_g,
+                                     unsigned rank, PeerPtrs peers, size_t row_pitch, size_t col_off, PowTable tw, FieldParams fp, FsSignal sg) {
+    const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (!(i4 >> (log_n1 + log_w))) {
+        const uint32_t q = (uint32_t)(i4 >> log_w), c = (uint32_t)(i4 & (((size_t)1 << log_w) - 1));
+        const uint32_t k1 = brev_bits(q, log_n1);
+        const uint32_t n2 = (rank << log_w) + c;
+        const uint4 a = *reinterpret_cast<const uint4*>(A + i4);
+        uint4 v;
+        v.x = mont_mul(a.x, pow_lookup(tw, k1 * n2, fp), fp);                // k1 * n2 < N
+        v.y = mont_mul(a.y, pow_lookup(tw, k1 * (n2 + 1), fp), fp);
+        v.z = mont_mul(a.z, pow_lookup(tw, k1 * (n2 + 2), fp), fp);
+        v.w = mont_mul(a.w, pow_lookup(tw, k1 * (n2 + 3), fp), fp);
+        const unsigned rows_per = log_n1 - log_g;
+        const uint32_t owner = k1 >> rows_per, row = k1 & ((1u << rows_per) - 1);
+        *reinterpret_cast<uint4*>(peers.p[owner] + (size_t)row * row_pitch + col_off + c) = v;
+    }
+    fs_publish(sg, threadIdx.x == 0, gridDim.x);
+}
+static unsigned* fs_ticket(stark_ctx* ctx) {
+    if (!ctx->fs_ticket.p) {
+        ctx->fs_ticket = DevBuf(sizeof(unsigned), ctx->stream);
+        STARK_CUDA(cudaMemsetAsync(ctx->fs_ticket.p, 0, sizeof(unsigned), ctx->stream));
+    }
+    return ctx->fs_ticket.as<unsigned>();
+}
+static FsSignal make_signal(stark_ctx* ctx, void* const* peer_flags, unsigned slot, unsigned rank, unsigned world, uint32_t epoch) {
+    FsSignal sg{};
+    if (!peer_flags) return sg;
+    for (unsigned s = 0; s < world; s++) sg.flags.p[s] = static_cast<uint32_t*>(peer_flags[s]);
+    sg.ticket = fs_ticket(ctx); sg.slot = slot; sg.rank = rank; sg.world = world; sg.epoch = epoch;
+    return sg;
 }
 void fourstep_twiddle_scatter_rows(stark_ctx* ctx, const uint32_t* A, unsigned log_n1, unsigned log_n2, unsigned world, unsigned rank,
-                                   const PeerPtrs& peers) {
+                                   const PeerPtrs& peers, bool staged, void* const* peer_flags, uint32_t epoch) {
     unsigned log_g = 0; while ((1u << log_g) < world) log_g++;
     unsigned log_w = log_n2 - log_g;
+    STARK_REQUIRE(log_w >= 2, "fourstep: every rank needs >= 4 columns");
     size_t total = (size_t)1 << (log_n1 + log_w);
     const TwiddleSet& tws = ctx->twiddles(log_n1 + log_n2);
+    const size_t w = (size_t)1 << log_w;
     KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 16.0 * total);
-    fourstep_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(A, log_n1, log_n2, log_w, log_g, rank, peers, tws.fwd(), ctx->fp);
+    fourstep_rows_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, ctx->stream>>>(
+        A, log_n1, log_w, log_g, rank, peers, staged ? w : ((size_t)1 << log_n2), staged ? 0 : (size_t)rank * w, tws.fwd(), ctx->fp,
+        make_signal(ctx, peer_flags, 0, rank, world, epoch));
     ctx->launches++;
     STARK_CUDA(cudaGetLastError());
 }
 
-// tile: 32 rows (k1') x 32 slots (q2); block (32, 8)
-__global__ void fourstep_transpose_kernel(const uint32_t* __restrict__ X, unsigned log_r, unsigned log_n1, unsigned log_n2, unsigned log_g,
-                                          unsigned rank, PeerPtrs peers) {
+// tile: 32 rows (k1') x 32 slots (q2); block (32, 8).  dst = base[owner] + col * col_pitch + k1_off + k1':
+// peer memory: col_pitch = N1, k1_off = rank * N1/G (the owner's natural-order block);  staging: col_pitch = N1/G, k1_off = 0.
+__global__ void fourstep_transpose_kernel(const uint32_t* __restrict__ X, unsigned log_n2, unsigned log_g, PeerPtrs peers,
+                                          size_t col_pitch, size_t k1_off, FsSignal sg) {
     __shared__ uint32_t tile[32][33];
     const size_t n2 = (size_t)1 << log_n2;
     const uint32_t q0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -79,20 +161,47 @@ __global__ void fourstep_transpose_kernel(const uint32_t* __restrict__ X, unsign
     for (int j = threadIdx.y; j < 32; j += 8) {
         uint32_t k2 = brev_bits(q0 + j, log_n2);
         uint32_t owner = k2 >> cols_per, col = k2 & ((1u << cols_per) - 1);
-        size_t k1 = ((size_t)rank << log_r) + r0 + threadIdx.x;
-        peers.p[owner][((size_t)col << log_n1) + k1] = tile[threadIdx.x][j];
+        peers.p[owner][(size_t)col * col_pitch + k1_off + r0 + threadIdx.x] = tile[threadIdx.x][j];
     }
+    fs_publish(sg, threadIdx.x == 0 && threadIdx.y == 0, gridDim.x * gridDim.y);
 }
 void fourstep_transpose_scatter(stark_ctx* ctx, const uint32_t* X, unsigned log_n1, unsigned log_n2, unsigned world, unsigned rank,
-                                const PeerPtrs& peers) {
+                                const PeerPtrs& peers, bool staged, void* const* peer_flags, uint32_t epoch) {
     unsigned log_g = 0; while ((1u << log_g) < world) log_g++;
     unsigned log_r = log_n1 - log_g;
     STARK_REQUIRE(log_r >= 5 && log_n2 >= 5, "fourstep: tiles need >= 32 rows and columns per rank");
     dim3 grid(1u << (log_n2 - 5), 1u << (log_r - 5));
     KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 16.0 * (double)((size_t)1 << (log_r + log_n2)));
-    fourstep_transpose_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(X, log_r, log_n1, log_n2, log_g, rank, peers);
+    fourstep_transpose_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(
+        X, log_n2, log_g, peers, staged ? ((size_t)1 << log_r) : ((size_t)1 << log_n1), staged ? 0 : ((size_t)rank << log_r),
+        make_signal(ctx, peer_flags, 1, rank, world, epoch));
     ctx->launches++;
     STARK_CUDA(cudaGetLastError());
+}
+void fourstep_wait(stark_ctx* ctx, const void* own_flags, unsigned slot, unsigned world, uint32_t epoch) {
+    KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 0);
+    fourstep_wait_kernel<<<1, 32, 0, ctx->stream>>>(static_cast<const uint32_t*>(own_flags), slot, world, epoch, ctx->d_result, 5000000000ull);
+    ctx->launches++;
+    STARK_CUDA(cudaGetLastError());
+}
+
+// the two compute phases, shared by the C entry points below and by the NCCL-staged transport of multi.cu
+void fourstep_phase_a_launch(stark_ctx* ctx, const uint32_t* coeffs, size_t n_coeffs, unsigned log_n, uint64_t offset, unsigned world,
+                             unsigned rank, const PeerPtrs& dst, bool staged, void* const* peer_flags, uint32_t epoch) {
+    unsigned a = log_n / 2, b = log_n - a, log_g = 0;
+    while ((1u << log_g) < world) log_g++;
+    const unsigned log_w = b - log_g;
+    DevBuf A(((size_t)4) << (a + log_w), ctx->stream);
+    fourstep_stage_input(ctx, coeffs, n_coeffs, A.as<uint32_t>(), a, b, world, rank, offset);
+    ntt_dif_columns(ctx, A.as<uint32_t>(), a, log_w, false);
+    fourstep_twiddle_scatter_rows(ctx, A.as<uint32_t>(), a, b, world, rank, dst, staged, peer_flags, epoch);
+}
+void fourstep_phase_c_launch(stark_ctx* ctx, uint32_t* rows, unsigned log_n, unsigned world, unsigned rank, const PeerPtrs& dst,
+                             bool staged, void* const* peer_flags, uint32_t epoch) {
+    unsigned a = log_n / 2, b = log_n - a, log_g = 0;
+    while ((1u << log_g) < world) log_g++;
+    ntt_dif(ctx, rows, b, false, (size_t)1 << (a - log_g));
+    fourstep_transpose_scatter(ctx, rows, a, b, world, rank, dst, staged, peer_flags, epoch);
 }
 
 }  // namespace starkb200
@@ -161,8 +270,10 @@ static void fs_dims(stark_ctx* ctx, unsigned log_n, unsigned world, unsigned& a,
 }
 
 // Phase A + exchange 1: coefficients (device, every rank holds them) -> rows of the [N1/G][N2] matrix of each peer.
+// peer_flags == NULL: returns after the stores are complete (the caller places a barrier before phase C).
+// peer_flags != NULL: nothing is synchronised -- the scatter kernel publishes `epoch` into slot 0 of every peer's flags.
 extern "C" int stark_fourstep_phase_a(stark_ctx* ctx, const stark_vec* coeffs, unsigned log_n, uint64_t offset, unsigned world,
-                                      unsigned rank, void* const* peer_rows) {
+                                      unsigned rank, void* const* peer_rows, void* const* peer_flags, uint32_t epoch) {
     FS_BEGIN
     STARK_REQUIRE(ctx && coeffs && coeffs->ctx == ctx && peer_rows && rank < world, "fourstep_phase_a: bad argument");
     FsGuard g(ctx);
@@ -170,25 +281,32 @@ extern "C" int stark_fourstep_phase_a(stark_ctx* ctx, const stark_vec* coeffs, u
     unsigned a, b, log_g; fs_dims(ctx, log_n, world, a, b, log_g);
     STARK_REQUIRE(coeffs->n <= ((size_t)1 << log_n), "fourstep: more coefficients than domain points");
     PeerPtrs peers = make_peers(peer_rows, world);
-    unsigned log_w = b - log_g;
-    DevBuf A(((size_t)4) << (a + log_w), ctx->stream);
-    fourstep_stage_input(ctx, coeffs->buf->as<uint32_t>(), coeffs->n, A.as<uint32_t>(), a, b, world, rank, offset);
-    ntt_dif_columns(ctx, A.as<uint32_t>(), a, log_w, false);
-    fourstep_twiddle_scatter_rows(ctx, A.as<uint32_t>(), a, b, world, rank, peers);
-    STARK_CUDA(cudaStreamSynchronize(ctx->stream));      // the stores into the peers are complete when this returns
+    if (peer_flags) make_peers(peer_flags, world);
+    fourstep_phase_a_launch(ctx, coeffs->buf->as<uint32_t>(), coeffs->n, log_n, offset, world, rank, peers, false, peer_flags, epoch);
+    if (!peer_flags) STARK_CUDA(cudaStreamSynchronize(ctx->stream));      // the stores into the peers are complete when this returns
     FS_END
 }
 // Phase C + exchange 2: this rank's [N1/G][N2] rows (all peers have written them) -> natural-order blocks of each peer.
+// With flags: first waits (on the device) until every peer's phase-A epoch has arrived, and publishes `epoch` into slot 1
+// of every peer's flags when its own stores are done.
 extern "C" int stark_fourstep_phase_c(stark_ctx* ctx, stark_vec* rows, unsigned log_n, unsigned world, unsigned rank,
-                                      void* const* peer_blocks) {
+                                      void* const* peer_blocks, void* const* peer_flags, uint32_t epoch) {
     FS_BEGIN
     STARK_REQUIRE(ctx && rows && rows->ctx == ctx && peer_blocks && rank < world, "fourstep_phase_c: bad argument");
     FsGuard g(ctx);
     unsigned a, b, log_g; fs_dims(ctx, log_n, world, a, b, log_g);
     STARK_REQUIRE(rows->n == ((size_t)1 << (log_n - log_g)), "fourstep_phase_c: rows vector has the wrong size");
     PeerPtrs peers = make_peers(peer_blocks, world);
-    ntt_dif(ctx, rows->buf->as<uint32_t>(), b, false, (size_t)1 << (a - log_g));
-    fourstep_transpose_scatter(ctx, rows->buf->as<uint32_t>(), a, b, world, rank, peers);
-    STARK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (peer_flags) { make_peers(peer_flags, world); fourstep_wait(ctx, peer_flags[rank], 0, world, epoch); }
+    fourstep_phase_c_launch(ctx, rows->buf->as<uint32_t>(), log_n, world, rank, peers, false, peer_flags, epoch);
+    if (!peer_flags) STARK_CUDA(cudaStreamSynchronize(ctx->stream));
+    FS_END
+}
+// Enqueues the device-side wait for slot (0: rows, 1: block) of this rank's own flag array.
+extern "C" int stark_fourstep_wait(stark_ctx* ctx, const void* own_flags, unsigned slot, unsigned world, uint32_t epoch) {
+    FS_BEGIN
+    STARK_REQUIRE(ctx && own_flags && slot < 2 && world >= 1 && world <= (unsigned)MAX_PEERS, "fourstep_wait: bad argument");
+    FsGuard g(ctx);
+    fourstep_wait(ctx, own_flags, slot, world, epoch);
     FS_END
 }

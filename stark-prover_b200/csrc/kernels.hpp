@@ -116,11 +116,21 @@ struct PeerPtrs { uint32_t* p[MAX_PEERS]; };
 void fourstep_stage_input(stark_ctx* ctx, const uint32_t* coeffs, size_t len, uint32_t* A, unsigned log_n1, unsigned log_n2,
                           unsigned world, unsigned rank, uint64_t offset);
 // rows of A (slot q holds k1 = bitrev(q)) times w_N^(k1*n2), written to their owner: peers[k1 / (N1/G)][k1 % (N1/G)][rank*w + n2']
+// (staged: into per-destination chunks [N1/G][w] of a local send buffer instead, for the NCCL transport).
+// peer_flags != null: the kernel publishes `epoch` to slot 0 of every peer's flag array when its stores are complete.
 void fourstep_twiddle_scatter_rows(stark_ctx* ctx, const uint32_t* A, unsigned log_n1, unsigned log_n2, unsigned world, unsigned rank,
-                                   const PeerPtrs& peers);
+                                   const PeerPtrs& peers, bool staged, void* const* peer_flags, uint32_t epoch);
 // X[k1'][slot q2] (k2 = bitrev(q2)) -> natural-order blocks: peers[k2 / (N2/G)][(k2 % (N2/G))*N1 + rank*N1/G + k1']
+// (staged: chunks [N2/G][N1/G]); publishes `epoch` to slot 1 when peer_flags != null.
 void fourstep_transpose_scatter(stark_ctx* ctx, const uint32_t* X, unsigned log_n1, unsigned log_n2, unsigned world, unsigned rank,
-                                const PeerPtrs& peers);
+                                const PeerPtrs& peers, bool staged, void* const* peer_flags, uint32_t epoch);
+// one-warp kernel that spins until all `world` epoch words of `slot` in this rank's flag array have reached `epoch`
+void fourstep_wait(stark_ctx* ctx, const void* own_flags, unsigned slot, unsigned world, uint32_t epoch);
+// phase A = stage + column-batched DIF + twiddle/scatter; phase C = row-batched DIF + transpose/scatter
+void fourstep_phase_a_launch(stark_ctx* ctx, const uint32_t* coeffs, size_t n_coeffs, unsigned log_n, uint64_t offset, unsigned world,
+                             unsigned rank, const PeerPtrs& dst, bool staged, void* const* peer_flags, uint32_t epoch);
+void fourstep_phase_c_launch(stark_ctx* ctx, uint32_t* rows, unsigned log_n, unsigned world, unsigned rank, const PeerPtrs& dst,
+                             bool staged, void* const* peer_flags, uint32_t epoch);
 // plain (unfused) evaluation-space fold of one layer
 void fri_fold(stark_ctx* ctx, const LeafSource& src);
 

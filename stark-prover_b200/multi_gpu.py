@@ -518,28 +518,36 @@ class FourStepP2P:
     mapped pointers) by the kernels that produce the data — no pack / all-to-all / unpack passes (csrc/fourstep.cu).
 
     Every rank owns two peer-visible buffers of N/G elements: `rows` ([N1/G][N2], filled by every rank's phase A) and
-    `block` (its natural-order slice of the result, filled by every rank's phase C).  Handles are exchanged once.
-    Two host barriers per transform separate the phases (a phase returns when its peer stores are complete)."""
+    `block` (its natural-order slice of the result, filled by every rank's phase C), plus a small array of epoch flags.
+    Handles are exchanged once.  The phases hand over ON THE DEVICE: a scatter kernel publishes its epoch to every peer
+    when its stores are complete, the consumer's next phase starts with a one-warp wait kernel — no host barrier and no
+    stream synchronisation inside a transform (`host_barriers=True` restores the two-barrier form for comparison).
+    The product path for non-Python callers is `stark_mg_fourstep_lde` (csrc/multi.cu), which does the same with its own
+    NCCL communicator; this class drives the phase entry points from Python over torch.distributed."""
 
-    def __init__(self, sp, ctx, log_n: int, rank: int, world: int, group=None):
+    def __init__(self, sp, ctx, log_n: int, rank: int, world: int, group=None, host_barriers: bool = False):
         self.sp, self.ctx, self.log_n, self.rank, self.world, self.group = sp, ctx, log_n, rank, world, group
+        self.host_barriers, self.epoch = host_barriers, 0
         n_loc = (1 << log_n) // world
         self.rows, h_rows = ctx.peer_alloc(n_loc)
         self.block, h_block = ctx.peer_alloc(n_loc)
+        self.flags, h_flags = ctx.peer_alloc(32)
         ctx.sync()
         self._opened = []
         if world == 1:
-            self.peer_rows, self.peer_blocks = [self.rows.device_ptr], [self.block.device_ptr]
+            self.peer_rows, self.peer_blocks, self.peer_flags = [self.rows.device_ptr], [self.block.device_ptr], [self.flags.device_ptr]
         else:
-            hs = all_gather_bytes(np.frombuffer(h_rows + h_block, dtype=np.uint8), group)       # [world, 128]
-            self.peer_rows, self.peer_blocks = [], []
+            hs = all_gather_bytes(np.frombuffer(h_rows + h_block + h_flags, dtype=np.uint8), group)       # [world, 192]
+            self.peer_rows, self.peer_blocks, self.peer_flags = [], [], []
             for r in range(world):
                 if r == rank:
                     self.peer_rows.append(self.rows.device_ptr); self.peer_blocks.append(self.block.device_ptr)
+                    self.peer_flags.append(self.flags.device_ptr)
                 else:
-                    pr, pb = ctx.peer_open(hs[r, :64].tobytes()), ctx.peer_open(hs[r, 64:].tobytes())
-                    self._opened += [pr, pb]
-                    self.peer_rows.append(pr); self.peer_blocks.append(pb)
+                    ptrs = [ctx.peer_open(hs[r, 64 * k:64 * k + 64].tobytes()) for k in range(3)]
+                    self._opened += ptrs
+                    self.peer_rows.append(ptrs[0]); self.peer_blocks.append(ptrs[1]); self.peer_flags.append(ptrs[2])
+            self._barrier()                               # every buffer exists and is zeroed before anyone stores into it
 
     def _barrier(self):
         dist = _dist()
@@ -548,33 +556,51 @@ class FourStepP2P:
 
     def run(self, coeffs, offset: int):
         """coeffs: device Vec (every rank holds the same coefficients).  Returns this rank's natural-order block
-        (the peer-visible `block` buffer: valid until the next run)."""
-        self._barrier()                                   # nobody still reads `rows` / `block` from a previous run
-        self.ctx.fourstep_phase_a(coeffs, self.log_n, offset, self.world, self.rank, self.peer_rows)
-        self._barrier()                                   # every rank's rows are complete
-        self.ctx.fourstep_phase_c(self.rows, self.log_n, self.world, self.rank, self.peer_blocks)
-        self._barrier()                                   # every rank's block is complete
+        (the peer-visible `block` buffer: valid until the next run; work that reads it must be enqueued on this context
+        before the next run)."""
+        ctx = self.ctx
+        if self.host_barriers:
+            self._barrier()                                   # nobody still reads `rows` / `block` from a previous run
+            ctx.fourstep_phase_a(coeffs, self.log_n, offset, self.world, self.rank, self.peer_rows)
+            self._barrier()                                   # every rank's rows are complete
+            ctx.fourstep_phase_c(self.rows, self.log_n, self.world, self.rank, self.peer_blocks)
+            self._barrier()                                   # every rank's block is complete
+            return self.block
+        self.epoch += 1
+        ctx.fourstep_phase_a(coeffs, self.log_n, offset, self.world, self.rank, self.peer_rows, self.peer_flags, self.epoch)
+        ctx.fourstep_phase_c(self.rows, self.log_n, self.world, self.rank, self.peer_blocks, self.peer_flags, self.epoch)
+        ctx.fourstep_wait(self.peer_flags[self.rank], 1, self.world, self.epoch)
         return self.block
 
     def close(self):
+        self.ctx.sync()
         self._barrier()
         for p in self._opened:
             self.ctx.peer_close(p)
         self._opened = []
 
 
-def four_step_p2p_emulated(sp, ctx, coeffs, log_n: int, offset: int, world: int) -> list:
+def four_step_p2p_emulated(sp, ctx, coeffs, log_n: int, offset: int, world: int, flags: bool = True) -> list:
     """All ranks of FourStepP2P in ONE process on one GPU: the 'peer' pointers are plain device pointers of the
-    other emulated ranks' buffers, so the kernels and the index algebra run exactly as on `world` GPUs."""
+    other emulated ranks' buffers, so the kernels, the index algebra and (flags=True) the epoch hand-over run exactly as
+    on `world` GPUs.  One stream: every rank's phase A is enqueued before any rank's phase C, whose wait kernel would
+    otherwise spin for a producer queued behind it."""
     n_loc = (1 << log_n) // world
     rows = [ctx.peer_alloc(n_loc)[0] for _ in range(world)]
     blocks = [ctx.peer_alloc(n_loc)[0] for _ in range(world)]
+    fl = [ctx.peer_alloc(32)[0] for _ in range(world)] if flags else None
     cvec = coeffs if hasattr(coeffs, "device_ptr") else ctx.upload(coeffs)
     pr, pb = [v.device_ptr for v in rows], [v.device_ptr for v in blocks]
-    for r in range(world):
-        ctx.fourstep_phase_a(cvec, log_n, offset, world, r, pr)
-    for r in range(world):
-        ctx.fourstep_phase_c(rows[r], log_n, world, r, pb)
-    for v in rows:
+    pf = [v.device_ptr for v in fl] if flags else None
+    for epoch in ((1, 2) if flags else (0,)):           # twice with flags: the second run exercises the re-armed ticket and epoch 2
+        for r in range(world):
+            ctx.fourstep_phase_a(cvec, log_n, offset, world, r, pr, pf, epoch)
+        for r in range(world):
+            ctx.fourstep_phase_c(rows[r], log_n, world, r, pb, pf, epoch)
+        if flags:
+            for r in range(world):
+                ctx.fourstep_wait(pf[r], 1, world, epoch)
+    ctx.sync()
+    for v in rows + (fl or []):
         v.free()
     return blocks

@@ -119,3 +119,109 @@ def test_four_step_peer_memory_rejects_tiny(sp, orc, ctx):
     mg = _mg()
     with pytest.raises(sp.StarkError):
         mg.four_step_p2p_emulated(sp, ctx, orc.synthetic_column(1, 64), 10, 5, 4)     # < 32 rows per rank
+
+
+@pytest.mark.parametrize("log_n,log_deg,world", [(12, 9, 2), (16, 13, 8)])
+def test_four_step_peer_memory_host_barrier_form(sp, orc, ctx, log_n, log_deg, world):
+    """The same kernels without the epoch flags (every phase call returns after its stores: the two-barrier form)."""
+    mg = _mg()
+    coeffs = orc.synthetic_column(log_n * 5 + world, 1 << log_deg)
+    want = orc.coset_evaluate(coeffs, log_n, 5, orc.root_of_unity(log_n), P)
+    blocks = mg.four_step_p2p_emulated(sp, ctx, coeffs, log_n, 5, world, flags=False)
+    assert np.array_equal(np.concatenate([b.download() for b in blocks]), want)
+
+
+# ---- the C-level group (csrc/multi.cu) with one rank: every entry point, no NCCL involved --------------------------
+def test_mg_commit_columns_world1(sp, orc, ctx):
+    g = sp.MultiGpu(ctx, 0, 1)
+    log_rows, log_blowup, n_cols = 12, 3, 5
+    cols = [orc.synthetic_column(100 + c, 1 << log_rows) for c in range(n_cols)]
+    roots, kept = g.commit_columns(cols, n_cols, log_rows, 1, log_blowup, 5, keep=True)
+    for c in range(n_cols):
+        coef = orc.coset_interpolate(cols[c], log_rows, 1, orc.root_of_unity(log_rows), P)
+        lde = orc.coset_evaluate(coef, log_rows + log_blowup, 5, orc.root_of_unity(log_rows + log_blowup), P)
+        assert roots[c] == orc.merkle_root_only(lde), c
+        vec, tree = kept[c]
+        assert np.array_equal(vec.download(), lde) and tree.root_bytes() == roots[c]
+        assert orc.merkle_verify(roots[c], len(lde), 77, int(lde[77]), tree.get_authentication_path(77))
+    assert g.commit_columns(cols, n_cols, log_rows, 1, log_blowup, 5) == roots      # without retained trees
+    g.close()
+
+
+@pytest.mark.parametrize("transport", [0, 1])
+@pytest.mark.parametrize("log_n,log_deg", [(10, 7), (15, 15), (20, 17)])
+def test_mg_fourstep_and_leaf_ranges_world1(sp, orc, ctx, log_n, log_deg, transport):
+    g = sp.MultiGpu(ctx, 0, 1)
+    coeffs = orc.synthetic_column(log_n + 7 * transport, 1 << log_deg)
+    want = orc.coset_evaluate(coeffs, log_n, 5, orc.root_of_unity(log_n), P)
+    cv = ctx.upload(coeffs)
+    for _ in range(2):                                   # twice: epochs / staging buffers are reused
+        blk = g.fourstep_lde(cv, log_n, 5, transport)
+        assert np.array_equal(blk.download(), want)
+    tree, root, subs = g.commit_leaf_ranges(blk)
+    assert root == orc.merkle_root_only(want) and subs == [root] and tree.root_bytes() == root
+    g.close()
+
+
+@pytest.mark.parametrize("transport", [0, 1])
+def test_mg_fri_commit_world1(sp, orc, ctx, transport):
+    """stark_mg_fri_commit / stark_mg_decommit_fri with one rank: the transcript is fri_commit's and the oracle's."""
+    g = sp.MultiGpu(ctx, 0, 1)
+    log_n, q = 14, 3
+    c = orc.synthetic_poly_exact_degree(4, 1 << 11)
+    ch, ch1, och = sp.Channel(P), sp.Channel(P), orc.Channel(P)
+    f = g.fri_commit(ctx.upload(c), log_n, 5, ch, transport)
+    g.decommit_fri(f, q, (1 << log_n) - 1, ch)
+    pr = sp.fri_commit(ctx, c, sp.CosetFri(ctx, 5, log_n), ch1)
+    sp.decommit_fri(q, (1 << log_n) - 1, pr, ch1)
+    opr = orc.fri_commit_fast(c, log_n, 5, orc.root_of_unity(log_n), och, P)
+    orc.decommit_fri(q, (1 << log_n) - 1, opr, och)
+    assert ch.state == ch1.state == och.state and ch.proof == ch1.proof == och.proof
+    assert f.proof.num_layers == pr.num_layers
+    ok, why = sp.verify_fri(ch.proof_flat(), log_n, 5, q, (1 << log_n) - 1, 11)
+    assert ok, why
+    f.free(); g.close()
+
+
+# ---- full-size parity for the sharded configs on one GPU (VERDICT r1: cfg4 / cfg5 were never oracle-checked at size) ----
+def test_cfg4_one_column_full_size(sp, orc, ctx):
+    """One cfg4 column at BASELINE size: 2^22 rows -> coset LDE 2^25 -> root == the oracle's, 64 sampled rows equal."""
+    log_rows, c = 22, 17
+    col = orc.synthetic_column(100 + c, 1 << log_rows)
+    g = sp.MultiGpu(ctx, 0, 1)
+    roots, kept = g.commit_columns({0: col}, 1, log_rows, 1, 3, 5, keep=True)
+    coef = orc.coset_interpolate(col, log_rows, 1, orc.root_of_unity(log_rows), P)
+    lde = orc.coset_evaluate(coef, log_rows + 3, 5, orc.root_of_unity(log_rows + 3), P)
+    assert roots[0] == orc.merkle_root_only(lde)
+    vec, tree = kept[0]
+    rng = np.random.default_rng(4)
+    for i in rng.integers(0, 1 << 25, 64):
+        assert int(vec.download(int(i), 1)[0]) == int(lde[int(i)])
+    assert np.array_equal(vec.download(0, 1 << 16), lde[: 1 << 16])
+    # the committed golden of the full 64-column run holds the same root for this column
+    import json, os
+    gpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sharded.json")
+    gold = json.load(open(gpath)).get("cfg4")
+    if gold:
+        assert gold["roots"][c] == roots[0].hex()
+    vec.free(); tree.free(); g.close()
+
+
+@pytest.mark.parametrize("kind", ["nccl_flow", "peer_memory"])
+def test_four_step_eight_emulated_ranks_2e24(sp, orc, ctx, kind):
+    """8 emulated ranks at a 2^24 domain, both exchange flavours, against the oracle's root and sampled blocks."""
+    mg = _mg()
+    log_n, world = 24, 8
+    coeffs = orc.synthetic_poly_exact_degree(43, 1 << (log_n - 3))
+    want = orc.coset_evaluate(coeffs, log_n, 5, orc.root_of_unity(log_n), P)
+    cv = ctx.upload(coeffs)
+    blocks = mg.four_step_lde_emulated(sp, ctx, cv, log_n, 5, world) if kind == "nccl_flow" else mg.four_step_p2p_emulated(sp, ctx, cv, log_n, 5, world)
+    blk = (1 << log_n) // world
+    subs = []
+    for r, b in enumerate(blocks):
+        assert np.array_equal(b.download(0, 4096), want[r * blk:r * blk + 4096]), r
+        assert np.array_equal(b.download(blk - 4096, 4096), want[(r + 1) * blk - 4096:(r + 1) * blk]), r
+        subs.append(sp.MerkleTree.new(ctx, b).root_bytes())
+    assert mg.combine_subtree_roots(subs) == orc.merkle_root_only(want)
+    for b in blocks:
+        b.free()
