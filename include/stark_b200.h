@@ -263,6 +263,12 @@ int stark_mg_commit_leaf_ranges(stark_mg* mg, const stark_vec* block, stark_tree
 int stark_mg_fri_commit(stark_mg* mg, const stark_vec* coeffs, unsigned log_n, uint64_t offset, int transport, stark_channel* ch,
                         stark_mg_fri** out);
 int stark_mg_decommit_fri(stark_mg_fri* f, size_t num_queries, size_t max_index, stark_channel* ch);
+/* stark101_prove over the group (BASELINE cfg5, "end-to-end prove ... using four-step NTT"): trace LDE through the
+ * four-step transform, commitments of f and of the composition polynomial in leaf ranges, the composition polynomial on
+ * each rank's own range (a halo of 2 * blowup values from the next rank), FRI layers >= 1 and the channel on rank 0.
+ * The transcript in `ch` (rank 0) is stark101_prove's, byte for byte. */
+int stark_mg_stark101_prove(stark_mg* mg, uint64_t a1, unsigned log_trace, unsigned log_blowup, size_t num_queries, int transport,
+                            stark_channel* ch);
 const stark_fri* stark_mg_fri_proof(const stark_mg_fri* f);      /* rank 0: layers >= 1 live here (borrowed); NULL elsewhere */
 const stark_tree* stark_mg_fri_subtree(const stark_mg_fri* f);   /* this rank's subtree of layer 0 (borrowed) */
 void stark_mg_fri_destroy(stark_mg_fri* f);

@@ -112,6 +112,7 @@ extern "C" {
     pub fn stark_mg_commit_leaf_ranges(mg: *mut stark_mg, block: *const stark_vec, subtree: *mut *mut stark_tree, root: *mut u8, subtree_roots: *mut u8) -> c_int;
     pub fn stark_mg_fri_commit(mg: *mut stark_mg, coeffs: *const stark_vec, log_n: c_uint, offset: u64, transport: c_int, ch: *mut stark_channel, out: *mut *mut stark_mg_fri) -> c_int;
     pub fn stark_mg_decommit_fri(f: *mut stark_mg_fri, num_queries: usize, max_index: usize, ch: *mut stark_channel) -> c_int;
+    pub fn stark_mg_stark101_prove(mg: *mut stark_mg, a1: u64, log_trace: c_uint, log_blowup: c_uint, num_queries: usize, transport: c_int, ch: *mut stark_channel) -> c_int;
     pub fn stark_mg_fri_proof(f: *const stark_mg_fri) -> *const stark_fri;
     pub fn stark_mg_fri_subtree(f: *const stark_mg_fri) -> *const stark_tree;
     pub fn stark_mg_fri_destroy(f: *mut stark_mg_fri);

@@ -94,6 +94,7 @@ def lib() -> C.CDLL:
     sig("stark_mg_commit_leaf_ranges", I, vp, vp, C.POINTER(vp), vp, vp)
     sig("stark_mg_fri_commit", I, vp, vp, C.c_uint, u64, I, vp, C.POINTER(vp))
     sig("stark_mg_decommit_fri", I, vp, szt, szt, vp)
+    sig("stark_mg_stark101_prove", I, vp, u64, C.c_uint, C.c_uint, szt, I, vp)
     sig("stark_mg_fri_proof", vp, vp)
     sig("stark_mg_fri_subtree", vp, vp)
     sig("stark_mg_fri_destroy", None, vp)
@@ -789,6 +790,12 @@ class MultiGpu:
         h = vp()
         _check(lib().stark_mg_fri_commit(self.h, coeffs.h, log_n, offset, transport, channel.h if channel is not None else None, C.byref(h)))
         return MgFri(self, h)
+
+    def stark101_prove(self, channel: Optional[Channel], a1: int = 3141592, log_trace: int = 10, log_blowup: int = 3, num_queries: int = 3,
+                       transport: int = 1) -> None:
+        """The FibonacciSq prover over the group (collective; `channel` on rank 0 only): stark101_prove's transcript."""
+        _check(lib().stark_mg_stark101_prove(self.h, a1, log_trace, log_blowup, num_queries, transport,
+                                             channel.h if channel is not None else None))
 
     def decommit_fri(self, f: MgFri, num_queries: int, max_index: int, channel: Optional[Channel]) -> None:
         _check(lib().stark_mg_decommit_fri(f.h, num_queries, max_index, channel.h if channel is not None else None))

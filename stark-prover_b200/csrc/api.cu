@@ -115,6 +115,11 @@ extern "C" int stark_ctx_create(uint64_t modulus, uint64_t generator, int device
 }
 extern "C" void stark_ctx_destroy(stark_ctx* ctx) {
     if (!ctx) return;
+    ctx->destroy_requested.store(true);
+    if (ctx->handles.load() > 0) return;         // the last handle released tears the context down (CtxRef, common.hpp)
+    stark_ctx_teardown(ctx);
+}
+void stark_ctx_teardown(stark_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ctx->tw.clear();
@@ -321,6 +326,7 @@ static DevBufPtr lde_on_coset(stark_ctx* ctx, const uint32_t* evals, unsigned lo
 extern "C" int stark_ntt(stark_ctx* ctx, uint64_t* inout, unsigned log_n) {
     API_BEGIN
     STARK_REQUIRE(ctx && inout, "ntt: null argument");
+    STARK_REQUIRE(log_n <= 30 && log_n <= ctx->two_adicity, "ntt: 2^log_n does not divide p-1 (or log_n > 30)");
     CtxGuard g(ctx);
     size_t n = (size_t)1 << log_n;
     DevBufPtr c = upload_u64(ctx, inout, n);
@@ -331,6 +337,7 @@ extern "C" int stark_ntt(stark_ctx* ctx, uint64_t* inout, unsigned log_n) {
 extern "C" int stark_intt(stark_ctx* ctx, uint64_t* inout, unsigned log_n) {
     API_BEGIN
     STARK_REQUIRE(ctx && inout, "intt: null argument");
+    STARK_REQUIRE(log_n <= 30 && log_n <= ctx->two_adicity, "intt: 2^log_n does not divide p-1 (or log_n > 30)");
     CtxGuard g(ctx);
     size_t n = (size_t)1 << log_n;
     DevBufPtr e = upload_u64(ctx, inout, n);
@@ -343,7 +350,8 @@ extern "C" int stark_coset_evaluate(stark_ctx* ctx, const uint64_t* coeffs, size
     STARK_REQUIRE(ctx && out && (coeffs || n_coeffs == 0), "coset_evaluate: null argument");
     CtxGuard g(ctx);
     check_offset(ctx, offset);
-    STARK_REQUIRE(log_n <= 30 && n_coeffs <= ((size_t)1 << log_n), "coset_evaluate: more coefficients than domain points");
+    STARK_REQUIRE(log_n <= 30 && log_n <= ctx->two_adicity, "coset_evaluate: 2^log_n does not divide p-1 (or log_n > 30)");
+    STARK_REQUIRE(n_coeffs <= ((size_t)1 << log_n), "coset_evaluate: more coefficients than domain points");
     unsigned log_m = ceil_log2(std::max<size_t>(n_coeffs, 1));
     DevBufPtr c = upload_u64(ctx, coeffs, n_coeffs, (size_t)1 << log_m);
     DevBufPtr e = evaluate_on_coset(ctx, c->as<uint32_t>(), log_m, log_n, offset);
@@ -355,7 +363,7 @@ extern "C" int stark_coset_interpolate(stark_ctx* ctx, const uint64_t* evals, un
     STARK_REQUIRE(ctx && evals && coeffs_out, "coset_interpolate: null argument");
     CtxGuard g(ctx);
     check_offset(ctx, offset);
-    STARK_REQUIRE(log_n <= 30, "coset_interpolate: log_n too large");
+    STARK_REQUIRE(log_n <= 30 && log_n <= ctx->two_adicity, "coset_interpolate: 2^log_n does not divide p-1 (or log_n > 30)");
     size_t n = (size_t)1 << log_n;
     DevBufPtr e = upload_u64(ctx, evals, n);
     DevBufPtr c = interpolate_on_coset(ctx, e->as<uint32_t>(), log_n, offset);
@@ -368,7 +376,8 @@ extern "C" int stark_coset_lde(stark_ctx* ctx, const uint64_t* evals, unsigned l
     STARK_REQUIRE(ctx && evals && out, "coset_lde: null argument");
     CtxGuard g(ctx);
     check_offset(ctx, offset_in); check_offset(ctx, offset_out);
-    STARK_REQUIRE(log_n + log_blowup <= 30, "coset_lde: domain too large");
+    STARK_REQUIRE(log_n <= 30 && log_blowup <= 30 && log_n + log_blowup <= 30 && log_n + log_blowup <= ctx->two_adicity,
+                  "coset_lde: 2^(log_n+log_blowup) does not divide p-1 (or exceeds 2^30)");
     size_t n = (size_t)1 << log_n;
     DevBufPtr e = upload_u64(ctx, evals, n);
     DevBufPtr r = lde_on_coset(ctx, e->as<uint32_t>(), log_n, offset_in, log_blowup, offset_out);
@@ -499,6 +508,12 @@ extern "C" int stark_pow_mul_dev(stark_ctx* ctx, stark_vec* v, size_t inner_len,
     API_BEGIN
     STARK_REQUIRE(ctx && v && v->ctx == ctx && inner_len >= 1, "pow_mul_dev: bad argument");
     STARK_REQUIRE(log_table <= 31, "pow_mul_dev: table too large");
+    {   // every exponent the kernel forms must index inside the 2^log_table table
+        const size_t n = v->n, outer_max = outer0 + (n ? (n - 1) / inner_len : 0), inner_max = std::min(inner_len, n ? n : 1) - 1;
+        const unsigned __int128 e_max = product ? (unsigned __int128)inner_max * outer_max
+                                                : (unsigned __int128)inner_max * inner_stride + outer_max;
+        STARK_REQUIRE(e_max < ((unsigned __int128)1 << log_table), "pow_mul_dev: an exponent would fall outside the 2^log_table table");
+    }
     CtxGuard g(ctx);
     ScaleTable st;
     build_scale_table(ctx, base % ctx->modulus, c0 % ctx->modulus, log_table, st);
@@ -965,12 +980,15 @@ struct FriOpenServer {
     FriServerBox* h_box = nullptr;
     unsigned long long seq = 0;
     bool running = false;
-    // the kernel gives up after this long without a request (a descheduled host thread, or a profiler that runs the launch
-    // to completion before the host may post anything); open() then reports it and the caller launches per query
-    static constexpr unsigned long long kIdleNs = 250000000ull;
+    // The kernel leaves after this long without a request.  The first request is posted BEFORE the launch, so a kernel
+    // that only starts once the host is blocked inside the launch call (CUDA_LAUNCH_BLOCKING=1, a profiler or debugger that
+    // serialises launches) still answers it and then idles for this long at most -- 2 ms, ~40x the host's time between two
+    // queries (transcript hashing, ~45 us) -- before the host falls back to one launch per query.  (Round 1 waited 250 ms
+    // here: 99.8 % of a profiled smoke run)
+    static constexpr unsigned long long kIdleNs = 2000000ull;
     static bool usable(const stark_fri* f) {
-        // STARK_OPEN_SERVER=0 in the environment: one launch per query instead (a kernel that talks to the host cannot be
-        // replayed by a profiler; bench.py --profile-mode sets it)
+        // STARK_OPEN_SERVER=0 in the environment: one launch per query instead (bench.py --profile-mode sets it so that the
+        // committed launch list shows every opening)
         static const bool enabled = [] { const char* e = getenv("STARK_OPEN_SERVER"); return STARK_OPEN_SERVER && !(e && e[0] == '0'); }();
         if (!enabled || f->trees.empty() || f->trees.size() > (size_t)FRI_MAX_LAYERS) return false;
         const size_t n0 = f->trees[0]->shape.n;
@@ -979,7 +997,8 @@ struct FriOpenServer {
             if (t->external || t->shape.n == 0 || n0 % t->shape.n != 0) return false;
         return true;
     }
-    void start(const stark_fri* f) {
+    // launches the server with request 1 = `index0` already posted
+    void start(const stark_fri* f, size_t index0) {
         ctx = f->ctx;
         FriOpenArgs a{};
         size_t cap = 0;
@@ -989,27 +1008,34 @@ struct FriOpenServer {
             cap += 2 * (8 + 32 * (size_t)t->shape.depth);
         }
         a.n_layers = (unsigned)f->trees.size(); a.first = 0;
+        STARK_CUDA(cudaStreamSynchronize(ctx->stream));            // the pinned buffers may still be in use by an earlier opening
         ctx->pin_out.ensure(cap);
         ctx->pin_desc.ensure(sizeof(FriServerBox));
         a.out = static_cast<uint8_t*>(ctx->pin_out.d);
         h_box = static_cast<FriServerBox*>(ctx->pin_desc.h);
-        __atomic_store_n(&h_box->req, 0ull, __ATOMIC_RELEASE);
+        seq = 1;
         __atomic_store_n(&h_box->done, 0ull, __ATOMIC_RELEASE);
+        __atomic_store_n(&h_box->req, (seq << 32) | (unsigned long long)index0, __ATOMIC_RELEASE);
         unsigned long long idle = kIdleNs;
         if (const char* e = getenv("STARK_OPEN_SERVER_IDLE_NS")) { unsigned long long v = strtoull(e, nullptr, 10); if (v) idle = v; }   // tests
         fri_open_server_launch(ctx, a, static_cast<FriServerBox*>(ctx->pin_desc.d), idle);
         running = true;
     }
-    const uint8_t* open(size_t index0, size_t* total) {
-        seq++;
-        __atomic_store_n(&h_box->req, (seq << 32) | (unsigned long long)index0, __ATOMIC_RELEASE);
+    // waits for the answer to the request in flight; nullptr = the server has left (the caller launches per query)
+    const uint8_t* wait(size_t* total) {
         const auto t0 = std::chrono::steady_clock::now();
         unsigned long long d;
         for (unsigned spin = 0;; spin++) {
             d = __atomic_load_n(&h_box->done, __ATOMIC_ACQUIRE);
             if ((d >> 32) == seq) break;
-            if ((spin & 0xfffu) == 0xfffu) {
-                if (cudaStreamQuery(ctx->stream) != cudaErrorNotReady) { running = false; STARK_CUDA(cudaStreamSynchronize(ctx->stream)); return nullptr; }
+            if ((spin & 0x3ffu) == 0x3ffu) {
+                if (cudaStreamQuery(ctx->stream) != cudaErrorNotReady) {
+                    running = false;
+                    STARK_CUDA(cudaStreamSynchronize(ctx->stream));
+                    d = __atomic_load_n(&h_box->done, __ATOMIC_ACQUIRE);          // it may have answered on its way out
+                    if ((d >> 32) == seq) break;
+                    return nullptr;
+                }
                 if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5)) { stop(); throw StarkError(ST_CUDA, "opening server timed out"); }
             }
 #if defined(__x86_64__)
@@ -1018,6 +1044,11 @@ struct FriOpenServer {
         }
         *total = (size_t)(d & 0xffffffffull);
         return static_cast<const uint8_t*>(ctx->pin_out.h);
+    }
+    const uint8_t* open(size_t index0, size_t* total) {
+        seq++;
+        __atomic_store_n(&h_box->req, (seq << 32) | (unsigned long long)index0, __ATOMIC_RELEASE);
+        return wait(total);
     }
     void stop() {
         if (!running) return;
@@ -1033,13 +1064,14 @@ extern "C" int stark_decommit_fri(const stark_fri* f, size_t num_queries, size_t
     if (num_queries >= 2 && FriOpenServer::usable(f)) {
         CtxGuard g(f->ctx);
         FriOpenServer srv;
-        srv.start(f);
         const size_t n0 = f->trees[0]->shape.n;
         for (size_t q = 0; q < num_queries; q++) {                           // :175-178
             uint64_t idx;
             STARK_REQUIRE(ch->ch.receive_random_int(0, max_index, true, &idx), "channel: receive before send");
             size_t total = 0;
-            const uint8_t* rec = srv.running ? srv.open((size_t)idx % n0, &total) : nullptr;   // every layer length divides n0
+            const uint8_t* rec = nullptr;
+            if (q == 0) { srv.start(f, (size_t)idx % n0); rec = srv.wait(&total); }      // every layer length divides n0
+            else if (srv.running) rec = srv.open((size_t)idx % n0, &total);
             if (!rec) rec = open_one_index(f, (size_t)idx, &total);
             send_query_records(f, rec, ch->ch, (size_t)idx);
         }
@@ -1078,6 +1110,10 @@ void api_open_and_send(const stark_tree* t, size_t idx, Channel& ch) {
     ch.send(rec.data() + 8, pl);
 }
 void api_set_error(const std::string& s) { set_error(s); }
+void api_send_root_bytes(Channel& ch, const uint8_t root[32]) {
+    std::string h = HostSha256::hex(root, 32);
+    ch.send(reinterpret_cast<const uint8_t*>(h.data()), 64);
+}
 // multi.cu: a tree over leaf values whose root lands in `result` (device alias of mapped host memory) -- no sync here
 std::unique_ptr<stark_tree> api_tree_launch_values(stark_ctx* ctx, DevBufPtr leaves, size_t n, HostResult* result) {
     STARK_REQUIRE(n >= 1 && n <= ((size_t)1 << 32), "merkle: leaf count out of range");

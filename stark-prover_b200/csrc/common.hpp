@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -41,34 +42,55 @@ struct StarkError : std::runtime_error {
 // 64-column commit showed 10-200 ms allocation spikes once three sizes interleaved).
 struct BlockCache {
     static std::mutex& mu() { static std::mutex m; return m; }
-    static std::map<cudaStream_t, std::multimap<size_t, void*>>& lists() { static std::map<cudaStream_t, std::multimap<size_t, void*>> l; return l; }
-    static std::map<cudaStream_t, size_t>& held() { static std::map<cudaStream_t, size_t> h; return h; }
+    struct PerStream { std::multimap<size_t, void*> blocks; size_t held = 0; int device = -1; };
+    static std::map<cudaStream_t, PerStream>& lists() { static std::map<cudaStream_t, PerStream> l; return l; }
     static constexpr size_t kMinBytes = (size_t)1 << 20;
     static constexpr size_t kMaxHeld = (size_t)24 << 30;          // per stream
     static void* take(cudaStream_t s, size_t bytes) {
         if (bytes < kMinBytes) return nullptr;
         std::lock_guard<std::mutex> g(mu());
         auto& l = lists()[s];
-        auto it = l.find(bytes);
-        if (it == l.end()) return nullptr;
+        auto it = l.blocks.find(bytes);
+        if (it == l.blocks.end()) return nullptr;
         void* p = it->second;
-        l.erase(it);
-        held()[s] -= bytes;
+        l.blocks.erase(it);
+        l.held -= bytes;
         return p;
     }
     static bool give(cudaStream_t s, size_t bytes, void* p) {
         if (bytes < kMinBytes) return false;
         std::lock_guard<std::mutex> g(mu());
-        if (held()[s] + bytes > kMaxHeld) return false;
-        lists()[s].emplace(bytes, p);
-        held()[s] += bytes;
+        auto& l = lists()[s];
+        if (l.held + bytes > kMaxHeld) return false;
+        if (l.device < 0) cudaGetDevice(&l.device);
+        l.blocks.emplace(bytes, p);
+        l.held += bytes;
         return true;
     }
     static void flush(cudaStream_t s) {                           // context teardown
         std::lock_guard<std::mutex> g(mu());
-        for (auto& kv : lists()[s]) cudaFreeAsync(kv.second, s);
-        lists().erase(s);
-        held().erase(s);
+        auto it = lists().find(s);
+        if (it == lists().end()) return;
+        for (auto& kv : it->second.blocks) cudaFreeAsync(kv.second, s);
+        lists().erase(it);
+    }
+    // An allocation failed: hand every parked block of EVERY stream on the current device back to the driver's pool
+    // (other contexts' lists may be holding the memory this one needs), wait for the frees, and let the caller retry.
+    static void flush_device() {
+        int dev = -1;
+        cudaGetDevice(&dev);
+        {
+            std::lock_guard<std::mutex> g(mu());
+            for (auto& kv : lists()) {
+                if (kv.second.device != dev) continue;
+                for (auto& b : kv.second.blocks) cudaFreeAsync(b.second, kv.first);
+                kv.second.blocks.clear();
+                kv.second.held = 0;
+            }
+        }
+        cudaDeviceSynchronize();
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
     }
 };
 
@@ -81,7 +103,15 @@ struct DevBuf {
     DevBuf(size_t b, cudaStream_t s) : bytes(b), stream(s) {
         if (!b) return;
         p = BlockCache::take(s, b);
-        if (!p) STARK_CUDA(cudaMallocAsync(&p, b, s));
+        if (!p) {
+            cudaError_t e = cudaMallocAsync(&p, b, s);
+            if (e == cudaErrorMemoryAllocation) {                 // free memory may be sitting in the recycling lists
+                cudaGetLastError();
+                BlockCache::flush_device();
+                e = cudaMallocAsync(&p, b, s);
+            }
+            if (e != cudaSuccess) { p = nullptr; throw StarkError(ST_CUDA, std::string("cudaMallocAsync(") + std::to_string(b) + " bytes): " + cudaGetErrorString(e)); }
+        }
     }
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
@@ -153,7 +183,19 @@ inline uint64_t h_inv(uint64_t a, uint64_t m) { return h_pow(a, m - 2, m); }
 }  // namespace starkb200
 
 struct stark_ctx;
+void stark_ctx_teardown(stark_ctx* ctx);        // api.cu: what stark_ctx_destroy does once no handle is left
 namespace starkb200 {
+// The context pointer inside a handle: counts the handle in, and out again when the handle dies.
+struct CtxRef {
+    stark_ctx* p = nullptr;
+    CtxRef() = default;
+    CtxRef(const CtxRef&) = delete;
+    CtxRef& operator=(const CtxRef&) = delete;
+    CtxRef& operator=(stark_ctx* c);
+    ~CtxRef() { *this = nullptr; }
+    stark_ctx* operator->() const { return p; }
+    operator stark_ctx*() const { return p; }
+};
 // RAII: brackets the launches issued in its scope with a CUDA-event pair when ctx->timing is on.
 struct KernelTimer {
     stark_ctx* ctx; int cat; cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -182,6 +224,10 @@ struct stark_ctx {
     starkb200::DevBuf fs_ticket;                // the same for the four-step exchange kernels (fourstep.cu)
     int sm_count = 148;
     unsigned long long launches = 0;            // kernels launched through this context
+    // Handles (vectors, trees, FRI proofs, groups) keep their context alive: stark_ctx_destroy with handles outstanding
+    // only marks the context, and the last handle to go tears it down (a C or Rust caller has no _children list).
+    std::atomic<long> handles{0};
+    std::atomic<bool> destroy_requested{false};
 
     // optional per-category kernel timing (CUDA events on `stream`); see KernelTimer
     enum { CAT_MERKLE_LEAF = 0, CAT_MERKLE_NODE = 1, CAT_NTT = 2, CAT_OTHER = 3, CAT_COUNT = 4 };
@@ -194,3 +240,12 @@ struct stark_ctx {
     uint64_t root_of_unity(unsigned log_n) const { return starkb200::h_pow(generator, (modulus - 1) >> log_n, modulus); }
     const starkb200::TwiddleSet& twiddles(unsigned log_n);
 };
+
+inline starkb200::CtxRef& starkb200::CtxRef::operator=(stark_ctx* c) {
+    if (p == c) return *this;
+    stark_ctx* old = p;
+    p = c;
+    if (p) p->handles.fetch_add(1);
+    if (old && old->handles.fetch_sub(1) == 1 && old->destroy_requested.load()) stark_ctx_teardown(old);
+    return *this;
+}

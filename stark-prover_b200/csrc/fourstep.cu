@@ -15,6 +15,21 @@
 namespace starkb200 {
 
 __device__ __forceinline__ uint32_t brev_bits(uint32_t x, unsigned bits) { return bits ? (__brev(x) >> (32 - bits)) : 0u; }
+// output index held by slot q (kernels.hpp: SlotMap)
+__device__ __forceinline__ uint32_t slot_index(const SlotMap& m, uint32_t q) {
+    if (m.mode == 0) return brev_bits(q, m.total_bits);
+    if (m.mode == 2) return q;
+    uint32_t k = 0, off = 0, pos = m.total_bits;
+#pragma unroll
+    for (int d = 0; d < 4; d++) {            // digit d sits at address bits [pos - bits[d], pos) and is worth 2^off
+        if (d < (int)m.nd) {
+            pos -= m.bits[d];
+            k |= ((q >> pos) & ((1u << m.bits[d]) - 1u)) << off;
+            off += m.bits[d];
+        }
+    }
+    return k;
+}
 
 __global__ void fourstep_stage_kernel(const uint32_t* __restrict__ c, size_t len, uint32_t* __restrict__ A, unsigned log_n1,
                                       unsigned log_n2, unsigned log_w, unsigned rank, int has_scale, PowTable scale, FieldParams fp) {
@@ -62,12 +77,16 @@ __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// tail of a scatter kernel; `first` = this CTA's thread that takes the ticket, `n_ctas` = CTAs in the grid
+// tail of a scatter kernel; `first` = this CTA's thread that takes the ticket, `n_ctas` = CTAs in the grid.
+// One system-scope fence per CTA, after the barrier: the barrier orders every thread's peer stores before thread 0's
+// fence (causality is transitive through bar.sync -- the pattern of a cooperative-groups grid sync), and the fence is
+// cumulative over them.  A fence.sys in EVERY thread made these kernels 5x slower (91 / 113 us instead of ~20 us for
+// 2^23 elements, profiles/r02_fourstep.md).
 __device__ __forceinline__ void fs_publish(const FsSignal& sg, bool first, unsigned n_ctas) {
     if (!sg.ticket) return;
-    __threadfence_system();                      // this thread's peer stores are performed before anything that follows
     __syncthreads();
     if (first) {
+        __threadfence_system();                  // the CTA's peer stores are performed before the ticket
         const unsigned t = atomicAdd(sg.ticket, 1u);
         if (t == n_ctas - 1) {
             *sg.ticket = 0;                      // re-armed for the next launch on this stream
@@ -94,27 +113,51 @@ __global__ void fourstep_wait_kernel(const uint32_t* flags, unsigned slot, unsig
     }
 }
 
-// Four columns per thread: one 16-byte load, four twiddles, one 16-byte store into the owner (a warp covers 512 contiguous
-// bytes of a row).  dst = base[owner] + row * row_pitch + col_off + c, c the column inside this rank's slice:
+// The peers' base pointers travel as a kernel-parameter array; indexing that array with a run-time owner makes the
+// compiler copy all 16 pointers to every thread's local memory (a 128-byte stack frame: 268 MB of local stores for 2^21
+// threads -- 75-82 us instead of ~20 for these kernels, profiles/r02_fourstep.md).  Staged once per CTA in shared memory
+// with compile-time indices instead.
+__device__ __forceinline__ void stage_peers(uint32_t** s_peer, const PeerPtrs& peers, unsigned tid) {
+    if (tid != 0) return;
+#pragma unroll
+    for (int i = 0; i < MAX_PEERS; i++) s_peer[i] = peers.p[i];
+}
+
+// One CTA per (row, segment of up to 1024 columns); four consecutive columns per thread: one 16-byte load, one 16-byte
+// store into the owner.  The twiddle of column c of row k1 is w_N^(k1 (n2_0 + c)): with c = 32 h + j it factors into
+// Rhi[h] = w_N^(k1 (n2_0 + 32 h)) and Rlo[j] = w_N^(k1 j) -- 64 table look-ups per CTA, kept in shared memory, instead
+// of two scattered global look-ups per ELEMENT (whose 32 different L1 lines per warp instruction bound the round-1 kernel).
+// dst = base[owner] + row * row_pitch + col_off + c:
 // peer memory: row_pitch = N2, col_off = rank * w (the owner's [N1/G][N2] matrix);  staging for NCCL: row_pitch = w, col_off = 0.
 __global__ void fourstep_rows_kernel(const uint32_t* __restrict__ A, unsigned log_n1, unsigned log_w, unsigned log_g,
-                                     unsigned rank, PeerPtrs peers, size_t row_pitch, size_t col_off, PowTable tw, FieldParams fp, FsSignal sg) {
-    const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (!(i4 >> (log_n1 + log_w))) {
-        const uint32_t q = (uint32_t)(i4 >> log_w), c = (uint32_t)(i4 & (((size_t)1 << log_w) - 1));
-        const uint32_t k1 = brev_bits(q, log_n1);
-        const uint32_t n2 = (rank << log_w) + c;
-        const uint4 a = *reinterpret_cast<const uint4*>(A + i4);
+                                     unsigned rank, PeerPtrs peers, size_t row_pitch, size_t col_off, PowTable tw, FieldParams fp, FsSignal sg,
+                                     SlotMap map) {
+    __shared__ uint32_t* s_peer[MAX_PEERS];
+    __shared__ uint32_t s_lo[32], s_hi[32];
+    const unsigned tid = threadIdx.x, seg_len = blockDim.x * 4;          // columns of this CTA's segment
+    const uint32_t q = blockIdx.y, c0 = blockIdx.x * seg_len;            // slot (row of A), first column of the segment
+    const uint32_t k1 = slot_index(map, q);
+    const uint32_t n2_0 = (rank << log_w) + c0;
+    stage_peers(s_peer, peers, tid);
+    for (unsigned i = tid; i < 64; i += blockDim.x) {                                     // (a segment may have fewer than 64 threads)
+        if (i < 32) s_lo[i] = pow_lookup(tw, k1 * i, fp);                                   // k1 * 31 < N
+        else if ((i - 32) * 32 < seg_len) s_hi[i - 32] = pow_lookup(tw, k1 * (n2_0 + (i - 32) * 32), fp);   // k1 * n2 < N
+    }
+    __syncthreads();
+    {
+        const uint32_t c = c0 + tid * 4;
+        const uint4 a = *reinterpret_cast<const uint4*>(A + ((size_t)q << log_w) + c);
+        const uint32_t hi = s_hi[tid >> 3], j = (tid & 7) * 4;
         uint4 v;
-        v.x = mont_mul(a.x, pow_lookup(tw, k1 * n2, fp), fp);                // k1 * n2 < N
-        v.y = mont_mul(a.y, pow_lookup(tw, k1 * (n2 + 1), fp), fp);
-        v.z = mont_mul(a.z, pow_lookup(tw, k1 * (n2 + 2), fp), fp);
-        v.w = mont_mul(a.w, pow_lookup(tw, k1 * (n2 + 3), fp), fp);
+        v.x = mont_mul(a.x, mont_mul(s_lo[j], hi, fp), fp);
+        v.y = mont_mul(a.y, mont_mul(s_lo[j + 1], hi, fp), fp);
+        v.z = mont_mul(a.z, mont_mul(s_lo[j + 2], hi, fp), fp);
+        v.w = mont_mul(a.w, mont_mul(s_lo[j + 3], hi, fp), fp);
         const unsigned rows_per = log_n1 - log_g;
         const uint32_t owner = k1 >> rows_per, row = k1 & ((1u << rows_per) - 1);
-        *reinterpret_cast<uint4*>(peers.p[owner] + (size_t)row * row_pitch + col_off + c) = v;
+        *reinterpret_cast<uint4*>(s_peer[owner] + (size_t)row * row_pitch + col_off + c) = v;
     }
-    fs_publish(sg, threadIdx.x == 0, gridDim.x);
+    fs_publish(sg, tid == 0, gridDim.x * gridDim.y);
 }
 static unsigned* fs_ticket(stark_ctx* ctx) {
     if (!ctx->fs_ticket.p) {
@@ -131,17 +174,20 @@ static FsSignal make_signal(stark_ctx* ctx, void* const* peer_flags, unsigned sl
     return sg;
 }
 void fourstep_twiddle_scatter_rows(stark_ctx* ctx, const uint32_t* A, unsigned log_n1, unsigned log_n2, unsigned world, unsigned rank,
-                                   const PeerPtrs& peers, bool staged, void* const* peer_flags, uint32_t epoch) {
+                                   const PeerPtrs& peers, bool staged, void* const* peer_flags, uint32_t epoch, const SlotMap& map) {
     unsigned log_g = 0; while ((1u << log_g) < world) log_g++;
     unsigned log_w = log_n2 - log_g;
     STARK_REQUIRE(log_w >= 2, "fourstep: every rank needs >= 4 columns");
     size_t total = (size_t)1 << (log_n1 + log_w);
     const TwiddleSet& tws = ctx->twiddles(log_n1 + log_n2);
     const size_t w = (size_t)1 << log_w;
+    STARK_REQUIRE(log_w >= 5, "fourstep: every rank needs >= 32 columns");
     KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 16.0 * total);
-    fourstep_rows_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, ctx->stream>>>(
+    const unsigned seg = w < 1024 ? (unsigned)w : 1024u;                       // columns per CTA, 4 per thread
+    STARK_REQUIRE(((size_t)1 << log_n1) <= 65535, "fourstep: too many rows for one grid dimension");
+    fourstep_rows_kernel<<<dim3((unsigned)(w / seg), 1u << log_n1), seg / 4, 0, ctx->stream>>>(
         A, log_n1, log_w, log_g, rank, peers, staged ? w : ((size_t)1 << log_n2), staged ? 0 : (size_t)rank * w, tws.fwd(), ctx->fp,
-        make_signal(ctx, peer_flags, 0, rank, world, epoch));
+        make_signal(ctx, peer_flags, 0, rank, world, epoch), map);
     ctx->launches++;
     STARK_CUDA(cudaGetLastError());
 }
@@ -149,8 +195,10 @@ void fourstep_twiddle_scatter_rows(stark_ctx* ctx, const uint32_t* A, unsigned l
 // tile: 32 rows (k1') x 32 slots (q2); block (32, 8).  dst = base[owner] + col * col_pitch + k1_off + k1':
 // peer memory: col_pitch = N1, k1_off = rank * N1/G (the owner's natural-order block);  staging: col_pitch = N1/G, k1_off = 0.
 __global__ void fourstep_transpose_kernel(const uint32_t* __restrict__ X, unsigned log_n2, unsigned log_g, PeerPtrs peers,
-                                          size_t col_pitch, size_t k1_off, FsSignal sg) {
+                                          size_t col_pitch, size_t k1_off, FsSignal sg, SlotMap map) {
     __shared__ uint32_t tile[32][33];
+    __shared__ uint32_t* s_peer[MAX_PEERS];
+    stage_peers(s_peer, peers, threadIdx.y * 32 + threadIdx.x);
     const size_t n2 = (size_t)1 << log_n2;
     const uint32_t q0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
 #pragma unroll
@@ -159,14 +207,14 @@ __global__ void fourstep_transpose_kernel(const uint32_t* __restrict__ X, unsign
     const unsigned cols_per = log_n2 - log_g;
 #pragma unroll
     for (int j = threadIdx.y; j < 32; j += 8) {
-        uint32_t k2 = brev_bits(q0 + j, log_n2);
+        uint32_t k2 = slot_index(map, q0 + j);
         uint32_t owner = k2 >> cols_per, col = k2 & ((1u << cols_per) - 1);
-        peers.p[owner][(size_t)col * col_pitch + k1_off + r0 + threadIdx.x] = tile[threadIdx.x][j];
+        s_peer[owner][(size_t)col * col_pitch + k1_off + r0 + threadIdx.x] = tile[threadIdx.x][j];
     }
     fs_publish(sg, threadIdx.x == 0 && threadIdx.y == 0, gridDim.x * gridDim.y);
 }
 void fourstep_transpose_scatter(stark_ctx* ctx, const uint32_t* X, unsigned log_n1, unsigned log_n2, unsigned world, unsigned rank,
-                                const PeerPtrs& peers, bool staged, void* const* peer_flags, uint32_t epoch) {
+                                const PeerPtrs& peers, bool staged, void* const* peer_flags, uint32_t epoch, const SlotMap& map) {
     unsigned log_g = 0; while ((1u << log_g) < world) log_g++;
     unsigned log_r = log_n1 - log_g;
     STARK_REQUIRE(log_r >= 5 && log_n2 >= 5, "fourstep: tiles need >= 32 rows and columns per rank");
@@ -174,7 +222,7 @@ void fourstep_transpose_scatter(stark_ctx* ctx, const uint32_t* X, unsigned log_
     KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 16.0 * (double)((size_t)1 << (log_r + log_n2)));
     fourstep_transpose_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(
         X, log_n2, log_g, peers, staged ? ((size_t)1 << log_r) : ((size_t)1 << log_n1), staged ? 0 : ((size_t)rank << log_r),
-        make_signal(ctx, peer_flags, 1, rank, world, epoch));
+        make_signal(ctx, peer_flags, 1, rank, world, epoch), map);
     ctx->launches++;
     STARK_CUDA(cudaGetLastError());
 }
@@ -186,6 +234,7 @@ void fourstep_wait(stark_ctx* ctx, const void* own_flags, unsigned slot, unsigne
 }
 
 // the two compute phases, shared by the C entry points below and by the NCCL-staged transport of multi.cu
+static SlotMap bitrev_map(unsigned bits) { SlotMap m{}; m.mode = 0; m.total_bits = bits; return m; }
 void fourstep_phase_a_launch(stark_ctx* ctx, const uint32_t* coeffs, size_t n_coeffs, unsigned log_n, uint64_t offset, unsigned world,
                              unsigned rank, const PeerPtrs& dst, bool staged, void* const* peer_flags, uint32_t epoch) {
     unsigned a = log_n / 2, b = log_n - a, log_g = 0;
@@ -193,15 +242,33 @@ void fourstep_phase_a_launch(stark_ctx* ctx, const uint32_t* coeffs, size_t n_co
     const unsigned log_w = b - log_g;
     DevBuf A(((size_t)4) << (a + log_w), ctx->stream);
     fourstep_stage_input(ctx, coeffs, n_coeffs, A.as<uint32_t>(), a, b, world, rank, offset);
-    ntt_dif_columns(ctx, A.as<uint32_t>(), a, log_w, false);
-    fourstep_twiddle_scatter_rows(ctx, A.as<uint32_t>(), a, b, world, rank, dst, staged, peer_flags, epoch);
+    SlotMap map = bitrev_map(a);
+    if (a >= 10 && a + log_w <= 31) {
+        // the strided passes of the natural-order transform (lazy 9-instruction butterflies, 16-byte accesses, one
+        // row twiddle per tile row); they leave digit-reversed slots, which the scatter below undoes for free
+        std::vector<unsigned> bits = ntt_columns_digitrev(ctx, A.as<uint32_t>(), a, log_w, false);
+        map.mode = 1; map.nd = (unsigned)bits.size();
+        for (size_t i = 0; i < bits.size(); i++) map.bits[i] = bits[i];
+    } else {
+        ntt_dif_columns(ctx, A.as<uint32_t>(), a, log_w, false);
+    }
+    fourstep_twiddle_scatter_rows(ctx, A.as<uint32_t>(), a, b, world, rank, dst, staged, peer_flags, epoch, map);
 }
 void fourstep_phase_c_launch(stark_ctx* ctx, uint32_t* rows, unsigned log_n, unsigned world, unsigned rank, const PeerPtrs& dst,
                              bool staged, void* const* peer_flags, uint32_t epoch) {
     unsigned a = log_n / 2, b = log_n - a, log_g = 0;
     while ((1u << log_g) < world) log_g++;
-    ntt_dif(ctx, rows, b, false, (size_t)1 << (a - log_g));
-    fourstep_transpose_scatter(ctx, rows, a, b, world, rank, dst, staged, peer_flags, epoch);
+    const size_t batch = (size_t)1 << (a - log_g), total = batch << b;
+    SlotMap map = bitrev_map(b);
+    if (ntt_natural_supported(b, rows, rows, rows) && total <= ((size_t)1 << 31)) {
+        // natural -> natural row transforms (strided passes into a scratch array, transposing last pass back into `rows`)
+        DevBuf work(total * 4, ctx->stream);
+        ntt_natural(ctx, rows, total, work.as<uint32_t>(), rows, b, false, nullptr, nullptr, batch);
+        map.mode = 2;
+    } else {
+        ntt_dif(ctx, rows, b, false, batch);
+    }
+    fourstep_transpose_scatter(ctx, rows, a, b, world, rank, dst, staged, peer_flags, epoch, map);
 }
 
 }  // namespace starkb200

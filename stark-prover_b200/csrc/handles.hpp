@@ -3,8 +3,10 @@
 #include "host_channel.hpp"
 #include "kernels.hpp"
 
+// (the context reference is the FIRST member of every handle: members die in reverse order, so the buffers go back to the
+// context's stream before the reference that may tear the context down is dropped)
 struct stark_vec {
-    stark_ctx* ctx = nullptr;
+    starkb200::CtxRef ctx;
     starkb200::DevBufPtr buf;        // n canonical u32 values
     size_t n = 0;
 };
@@ -12,7 +14,7 @@ struct stark_vec {
 // MerkleTree<M> (reference src/merkle/mod.rs:5-7): the leaf values it was built over (shared with the
 // FRI layer or vector that owns them) plus levels 1..depth of digests.
 struct stark_tree {
-    stark_ctx* ctx = nullptr;
+    starkb200::CtxRef ctx;
     starkb200::DevBufPtr leaves;
     starkb200::TreeShape shape;
     starkb200::DevBuf nodes;
@@ -24,7 +26,7 @@ struct stark_tree {
 // fri_merkles[k]; `coeffs` tracks the folded polynomial so that its exact degree and the final
 // constant are the reference's.
 struct stark_fri {
-    stark_ctx* ctx = nullptr;
+    starkb200::CtxRef ctx;
     unsigned log_n = 0;
     uint64_t offset0 = 1;
     unsigned cur_log = 0;

@@ -76,6 +76,10 @@ bool ntt_natural_supported(unsigned log_n, const void* src, const void* work, co
 // batch > 1: `batch` transforms back to back (src_len = batch * 2^log_n, no input scale; out_scale is indexed inside each transform)
 void ntt_natural(stark_ctx* ctx, const uint32_t* src, size_t src_len, uint32_t* work, uint32_t* dst, unsigned log_n,
                  bool inverse_root, const PowTable* in_scale, const PowTable* out_scale, size_t batch = 1);
+// column-batched transform over data[2^log_n rows][2^col_bits columns] with the strided passes of ntt_natural (log_n >= 10,
+// col_bits >= 5): natural rows in, DIGIT-reversed slots out (slot [k_1]..[k_m] holds X[k_1 + R_1 k_2 + ..]), weak values;
+// returns the digit widths R_i = 2^bits[i], most significant address digit first
+std::vector<unsigned> ntt_columns_digitrev(stark_ctx* ctx, uint32_t* data, unsigned log_n, unsigned col_bits, bool inverse_root);
 // column-batched DIF over data[2^log_n rows][2^col_bits columns] (col_bits >= 5): natural rows in, bit-reversed out
 void ntt_dif_columns(stark_ctx* ctx, uint32_t* data, unsigned log_n, unsigned col_bits, bool inverse_root);
 // Blow-up-by-8 forward transform (the LDE / evaluate hot path): dst[8k'+s] = sum_j c_j (base w_N^s)^j w_n^(j k'),
@@ -112,6 +116,14 @@ void pow_mul(stark_ctx* ctx, uint32_t* v, size_t n, size_t inner_len, size_t out
 // ---- multi-GPU four-step NTT over peer memory (fourstep.cu) ----
 constexpr int MAX_PEERS = 16;
 struct PeerPtrs { uint32_t* p[MAX_PEERS]; };
+// how a transform left its outputs in its slots: index(slot) = bit reversal (DIF passes), digit reversal (strided
+// natural-order passes without the final transposition), or the slot itself (natural order)
+struct SlotMap {
+    int mode;                // 0: bit reversal, 1: digit reversal, 2: identity
+    unsigned total_bits;
+    unsigned nd;
+    unsigned bits[4];        // digit widths, most significant address digit first
+};
 // A[n1][n2'] = c[n1*N2 + rank*w + n2'] * offset^(n1*N2 + rank*w + n2')   (zero above `len`)
 void fourstep_stage_input(stark_ctx* ctx, const uint32_t* coeffs, size_t len, uint32_t* A, unsigned log_n1, unsigned log_n2,
                           unsigned world, unsigned rank, uint64_t offset);
@@ -119,11 +131,11 @@ void fourstep_stage_input(stark_ctx* ctx, const uint32_t* coeffs, size_t len, ui
 // (staged: into per-destination chunks [N1/G][w] of a local send buffer instead, for the NCCL transport).
 // peer_flags != null: the kernel publishes `epoch` to slot 0 of every peer's flag array when its stores are complete.
 void fourstep_twiddle_scatter_rows(stark_ctx* ctx, const uint32_t* A, unsigned log_n1, unsigned log_n2, unsigned world, unsigned rank,
-                                   const PeerPtrs& peers, bool staged, void* const* peer_flags, uint32_t epoch);
+                                   const PeerPtrs& peers, bool staged, void* const* peer_flags, uint32_t epoch, const SlotMap& map);
 // X[k1'][slot q2] (k2 = bitrev(q2)) -> natural-order blocks: peers[k2 / (N2/G)][(k2 % (N2/G))*N1 + rank*N1/G + k1']
 // (staged: chunks [N2/G][N1/G]); publishes `epoch` to slot 1 when peer_flags != null.
 void fourstep_transpose_scatter(stark_ctx* ctx, const uint32_t* X, unsigned log_n1, unsigned log_n2, unsigned world, unsigned rank,
-                                const PeerPtrs& peers, bool staged, void* const* peer_flags, uint32_t epoch);
+                                const PeerPtrs& peers, bool staged, void* const* peer_flags, uint32_t epoch, const SlotMap& map);
 // one-warp kernel that spins until all `world` epoch words of `slot` in this rank's flag array have reached `epoch`
 void fourstep_wait(stark_ctx* ctx, const void* own_flags, unsigned slot, unsigned world, uint32_t epoch);
 // phase A = stage + column-batched DIF + twiddle/scatter; phase C = row-batched DIF + transpose/scatter

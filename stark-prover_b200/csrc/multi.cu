@@ -30,6 +30,8 @@ DevBufPtr api_lde_on_coset(stark_ctx* ctx, const uint32_t* evals, unsigned log_n
 std::unique_ptr<stark_tree> api_tree_launch_values(stark_ctx* ctx, DevBufPtr leaves, size_t n, HostResult* result);
 int api_fri_commit_loop(stark_fri* f, stark_channel* chan);
 void api_send_query_records(const stark_fri* f, const uint8_t* rec, Channel& ch, size_t index, size_t first_layer);
+DevBufPtr api_interpolate_on_coset(stark_ctx* ctx, const uint32_t* evals, unsigned log_n, uint64_t offset);
+void api_send_root_bytes(Channel& ch, const uint8_t root[32]);
 }  // namespace starkb200
 
 namespace {
@@ -139,7 +141,7 @@ struct StagedState {                    // NCCL transport: send / receive stagin
 }  // namespace
 
 struct stark_mg {
-    stark_ctx* ctx = nullptr;
+    CtxRef ctx;
     unsigned rank = 0, world = 1;
     nccl_comm_t comm = nullptr;
     bool own_comm = false;
@@ -338,6 +340,37 @@ std::unique_ptr<stark_tree> commit_leaf_range(stark_mg* mg, DevBufPtr block, siz
     combine_roots(all.data(), mg->world, root);
     if (subtree_roots) memcpy(subtree_roots, all.data(), all.size());
     return t;
+}
+
+// Openings of `count` leaves of a column committed in leaf ranges: each owner opens its subtree, everybody learns the
+// records, rank 0 appends the levels above the subtree roots and feeds (element, path) pairs to the channel in order.
+void open_leaf_ranges(stark_mg* mg, const stark_vec* block, const stark_tree* subtree, const uint8_t* subtree_roots, const size_t* which,
+                      size_t count, size_t n_total, Channel* ch) {
+    const unsigned world = mg->world, rank = mg->rank;
+    const size_t blk = n_total / world, depth_local = ilog2(blk), rec_len = 8 + 32 * depth_local;
+    std::vector<uint8_t> payload(count * rec_len, 0), all((size_t)world * count * rec_len), top(32 * 8);
+    for (size_t t = 0; t < count; t++) {
+        if (which[t] / blk != rank) continue;
+        const size_t local = which[t] % blk;
+        uint64_t v;
+        int rc = stark_vec_download(block, local, 1, &v);
+        if (rc != ST_OK) throw StarkError(rc, stark_last_error());
+        be8(v, payload.data() + t * rec_len);
+        size_t pl = 0;
+        rc = stark_merkle_open(subtree, local, payload.data() + t * rec_len + 8, 32 * depth_local, &pl);
+        if (rc != ST_OK) throw StarkError(rc, stark_last_error());
+    }
+    gather_bytes(mg, payload.data(), payload.size(), all.data());
+    if (rank != 0) return;
+    for (size_t t = 0; t < count; t++) {
+        const unsigned owner = (unsigned)(which[t] / blk);
+        const uint8_t* rec = all.data() + (size_t)owner * count * rec_len + t * rec_len;
+        std::vector<uint8_t> path(rec + 8, rec + rec_len);
+        const size_t tl = top_path(subtree_roots, world, owner, top.data());
+        path.insert(path.end(), top.begin(), top.begin() + tl);
+        ch->send(rec, 8);
+        ch->send(path.data(), path.size());
+    }
 }
 
 stark_vec* wrap_vec(stark_ctx* ctx, DevBufPtr b, size_t n) {
@@ -574,36 +607,15 @@ extern "C" int stark_mg_decommit_fri(stark_mg_fri* f, size_t num_queries, size_t
     MgGuard g(mg);
     const unsigned world = mg->world, rank = mg->rank;
     const size_t N = (size_t)1 << f->log_n, blk = N / world;
-    const size_t depth_local = ilog2(blk), rec_len = 8 + 32 * depth_local;
-    std::vector<uint8_t> payload(2 * rec_len), all((size_t)world * 2 * rec_len), top(32 * 8), blob;
+    std::vector<uint8_t> blob;
+    (void)blk;
     for (size_t q = 0; q < num_queries; q++) {
         uint64_t idx = 0;
         if (rank == 0) STARK_REQUIRE(ch->ch.receive_random_int(0, max_index, true, &idx), "channel: receive before send");
         idx = bcast_u64(mg, idx);
         const size_t i0 = (size_t)idx % N, which[2] = {i0, (i0 + N / 2) % N};
-        std::fill(payload.begin(), payload.end(), 0);
-        for (int t = 0; t < 2; t++) {
-            if (which[t] / blk != rank) continue;
-            const size_t local = which[t] % blk;
-            uint64_t v;
-            int rc = stark_vec_download(f->block, local, 1, &v);
-            if (rc != ST_OK) return rc;
-            be8(v, payload.data() + t * rec_len);
-            size_t pl = 0;
-            rc = stark_merkle_open(f->subtree, local, payload.data() + t * rec_len + 8, 32 * depth_local, &pl);
-            if (rc != ST_OK) return rc;
-        }
-        gather_bytes(mg, payload.data(), payload.size(), all.data());
+        open_leaf_ranges(mg, f->block, f->subtree, f->subtree_roots.data(), which, 2, N, rank == 0 ? &ch->ch : nullptr);   // layer 0: :156-163
         if (rank != 0) continue;
-        for (int t = 0; t < 2; t++) {                                             // layer 0: fri_commit.rs:156-163
-            const unsigned owner = (unsigned)(which[t] / blk);
-            const uint8_t* rec = all.data() + (size_t)owner * 2 * rec_len + t * rec_len;
-            std::vector<uint8_t> path(rec + 8, rec + rec_len);
-            const size_t tl = top_path(f->subtree_roots.data(), world, owner, top.data());
-            path.insert(path.end(), top.begin(), top.begin() + tl);
-            ch->ch.send(rec, 8);
-            ch->ch.send(path.data(), path.size());
-        }
         size_t len = 0;
         const uint64_t i64 = idx;
         int rc = stark_fri_open_layers(f->proof, 1, &i64, 1, nullptr, 0, &len);
@@ -614,6 +626,116 @@ extern "C" int stark_mg_decommit_fri(stark_mg_fri* f, size_t num_queries, size_t
             if (rc != ST_OK) return rc;
         }
         api_send_query_records(f->proof, blob.data(), ch->ch, (size_t)idx, 1);
+    }
+    MG_END
+}
+
+// ======================================================================================= cfg5: the whole FibonacciSq prover
+// stark101_prove (stark101.cu) with everything the north-star partitions spread over the group, and the
+// same transcript byte for byte: the trace LDE through the four-step NTT, the commitments of f and of the composition
+// polynomial in leaf ranges, the composition polynomial point-wise on each rank's own range (it needs f at i, i + blow,
+// i + 2 blow: a halo of 2 blow values from the next rank).  The sequential trace recurrence is replicated; the FRI
+// layers >= 1, the channel and their openings stay on rank 0.  `ch` is used on rank 0 only.  Collective.
+extern "C" int stark_mg_stark101_prove(stark_mg* mg, uint64_t a1, unsigned log_trace, unsigned log_blowup, size_t num_queries, int transport,
+                                       stark_channel* ch) {
+    MG_BEGIN
+    STARK_REQUIRE(mg && (ch || mg->rank != 0), "mg_stark101_prove: bad argument");
+    MgGuard g(mg);
+    stark_ctx* ctx = mg->ctx;
+    const unsigned world = mg->world, rank = mg->rank;
+    const unsigned log_n = log_trace + log_blowup;
+    STARK_REQUIRE(log_trace >= 2 && log_n <= ctx->two_adicity && log_n <= 30, "stark101: trace/blowup sizes not supported by this field");
+    const size_t N = (size_t)1 << log_n, blow = (size_t)1 << log_blowup, blk = N / world;
+    STARK_REQUIRE(blk >= 2 * blow && blk % blow == 0, "mg_stark101_prove: every rank's range must hold at least 2 * blowup points");
+    const uint64_t w = ctx->generator;
+    Channel* chan = rank == 0 ? &ch->ch : nullptr;
+    // ---- src/trace: sequential recurrence + interpolation, replicated (every rank needs all coefficients)
+    stark_vec* f_coef = nullptr;
+    uint64_t last_value = 0;
+    int rc = stark101_trace_poly(ctx, a1, log_trace, &f_coef, &last_value);
+    if (rc != ST_OK) return rc;
+    std::unique_ptr<stark_vec> f_coef_guard(f_coef);
+    // ---- trace LDE (four-step) and its commitment in leaf ranges
+    DevBufPtr f_alias = fourstep_lde(mg, f_coef, log_n, w, transport);
+    DevBufPtr f_block = make_buf(blk * 4, ctx->stream);                       // private copy: the transport's buffer is reused
+    STARK_CUDA(cudaMemcpyAsync(f_block->p, f_alias->p, blk * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    std::vector<uint8_t> f_subs((size_t)world * 32), cp_subs((size_t)world * 32);
+    uint8_t f_root[32], cp_root[32];
+    auto f_sub = commit_leaf_range(mg, f_block, blk, f_root, f_subs.data());
+    uint64_t alpha[3] = {0, 0, 0};
+    if (rank == 0) {
+        uint8_t stmt[STARK101_STATEMENT_BYTES];
+        stark101_statement(ctx->modulus, ctx->generator, log_trace, log_blowup, num_queries, last_value, stmt);
+        chan->send(stmt, sizeof stmt);
+        api_send_root_bytes(*chan, f_root);
+        for (int k = 0; k < 3; k++) STARK_REQUIRE(chan->receive_random_field_element(&alpha[k]), "channel: receive before send");
+    }
+    for (int k = 0; k < 3; k++) alpha[k] = bcast_u64(mg, alpha[k]);
+    // ---- src/composition on the local range: block + halo from the next rank (wraps around)
+    stark_vec f_vec; f_vec.ctx = ctx; f_vec.buf = f_block; f_vec.n = blk;
+    stark_vec* cp_vec = nullptr;
+    if (world == 1) {
+        rc = stark101_composition_range(ctx, &f_vec, 0, N, alpha, last_value, log_trace, log_blowup, &cp_vec);
+    } else {
+        DevBuf heads((size_t)world * 2 * blow * 4, ctx->stream);
+        STARK_NCCL(nccl().AllGather(f_block->p, heads.p, 2 * blow, NCCL_UINT32, mg->comm, ctx->stream));
+        stark_vec ext; ext.ctx = ctx; ext.n = blk + 2 * blow;
+        ext.buf = make_buf(ext.n * 4, ctx->stream);
+        STARK_CUDA(cudaMemcpyAsync(ext.buf->p, f_block->p, blk * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        STARK_CUDA(cudaMemcpyAsync(ext.buf->as<uint32_t>() + blk, heads.as<uint32_t>() + (size_t)((rank + 1) % world) * 2 * blow, 2 * blow * 4,
+                                   cudaMemcpyDeviceToDevice, ctx->stream));
+        rc = stark101_composition_range(ctx, &ext, rank * blk, blk, alpha, last_value, log_trace, log_blowup, &cp_vec);
+    }
+    if (rc != ST_OK) return rc;
+    std::unique_ptr<stark_vec> cp_guard(cp_vec);
+    auto cp_sub = commit_leaf_range(mg, cp_vec->buf, blk, cp_root, cp_subs.data());
+    // ---- src/fri on rank 0: layer 0 = the collected CP evaluations, its coefficients by interpolation (degree tracking)
+    std::unique_ptr<stark_fri> proof;
+    if (world == 1 || rank == 0) {
+        DevBufPtr layer0;
+        if (world == 1) layer0 = cp_vec->buf;
+        else {
+            Nccl& n = nccl();
+            layer0 = make_buf(N * 4, ctx->stream);
+            STARK_CUDA(cudaMemcpyAsync(layer0->p, cp_vec->buf->p, blk * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            STARK_NCCL(n.GroupStart());
+            for (unsigned p = 1; p < world; p++) STARK_NCCL(n.Recv(layer0->as<uint32_t>() + p * blk, blk, NCCL_UINT32, (int)p, mg->comm, ctx->stream));
+            STARK_NCCL(n.GroupEnd());
+        }
+        stark_vec l0; l0.ctx = ctx; l0.buf = layer0; l0.n = N;
+        stark_vec cc; cc.ctx = ctx; cc.n = N;
+        cc.buf = api_interpolate_on_coset(ctx, layer0->as<uint32_t>(), log_n, w);
+        stark_fri* pf = nullptr;
+        rc = stark_fri_begin_external(ctx, &cc, log_n, w, &l0, cp_root, &pf);
+        if (rc != ST_OK) return rc;
+        proof.reset(pf);
+        rc = api_fri_commit_loop(pf, ch);
+        if (rc != ST_OK) return rc;
+    } else {
+        STARK_NCCL(nccl().Send(cp_vec->buf->p, blk, NCCL_UINT32, 0, mg->comm, ctx->stream));
+        STARK_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    // ---- queries: f(x), f(gx), f(g^2 x) and layer 0 of the FRI from their owners, the other layers on rank 0
+    std::vector<uint8_t> blob;
+    for (size_t q = 0; q < num_queries; q++) {
+        uint64_t idx = 0;
+        if (rank == 0) STARK_REQUIRE(chan->receive_random_int(0, N - 1 - 2 * blow, true, &idx), "channel: receive before send");
+        idx = bcast_u64(mg, idx);
+        const size_t fw[3] = {(size_t)idx, (size_t)idx + blow, (size_t)idx + 2 * blow};
+        open_leaf_ranges(mg, &f_vec, f_sub.get(), f_subs.data(), fw, 3, N, chan);
+        const size_t cw[2] = {(size_t)idx % N, ((size_t)idx + N / 2) % N};
+        open_leaf_ranges(mg, cp_vec, cp_sub.get(), cp_subs.data(), cw, 2, N, chan);
+        if (rank != 0) continue;
+        size_t len = 0;
+        const uint64_t i64 = idx;
+        rc = stark_fri_open_layers(proof.get(), 1, &i64, 1, nullptr, 0, &len);
+        if (rc != ST_OK) return rc;
+        blob.resize(len);
+        if (len) {
+            rc = stark_fri_open_layers(proof.get(), 1, &i64, 1, blob.data(), blob.size(), &len);
+            if (rc != ST_OK) return rc;
+        }
+        api_send_query_records(proof.get(), blob.data(), *chan, (size_t)idx, 1);
     }
     MG_END
 }

@@ -14,6 +14,10 @@
 // needs no permutation at all.  Natural->natural entry points of size >= 2^10 use the digit-split transform further
 // down (ntt_natural: strided in-place passes + one transposing pass, no permutation sweep); smaller and batched ones
 // add one bit-reversal gather to the passes above.
+#include <stdlib.h>
+
+#include <string>
+
 #include "kernels.hpp"
 
 namespace starkb200 {
@@ -235,8 +239,39 @@ __global__ void point_scale_kernel(const uint32_t* src, uint32_t* dst, int has_s
     dst[0] = x;
 }
 
+// experiment knob (tools/variants_plan.sh): STARK_NTT_PLAN="21:8,7,6;24:8,8,8" overrides the pass widths for those sizes
+static bool plan_override(unsigned log_n, std::vector<unsigned>& out) {
+    const char* e = getenv("STARK_NTT_PLAN");
+    if (!e) return false;
+    std::string s(e);
+    size_t pos = 0;
+    while (pos < s.size()) {
+        size_t end = s.find(';', pos);
+        if (end == std::string::npos) end = s.size();
+        std::string item = s.substr(pos, end - pos);
+        size_t colon = item.find(':');
+        if (colon != std::string::npos && (unsigned)atoi(item.substr(0, colon).c_str()) == log_n) {
+            std::vector<unsigned> v;
+            unsigned sum = 0;
+            size_t q = colon + 1;
+            while (q < item.size()) {
+                size_t comma = item.find(',', q);
+                if (comma == std::string::npos) comma = item.size();
+                unsigned b = (unsigned)atoi(item.substr(q, comma - q).c_str());
+                if (b < 5 || b > 9) return false;
+                v.push_back(b); sum += b;
+                q = comma + 1;
+            }
+            if (sum == log_n && v.size() >= 2 && v.size() <= 4) { out = v; return true; }
+            return false;
+        }
+        pos = end + 1;
+    }
+    return false;
+}
 static std::vector<unsigned> plan_bits(unsigned log_n) {
     if (log_n <= 9) return {log_n};
+    { std::vector<unsigned> o; if (plan_override(log_n, o)) return o; }
     unsigned k = (log_n + 8) / 9, base = log_n / k, rem = log_n % k;
     std::vector<unsigned> v;
     for (unsigned i = 0; i < k; i++) v.push_back(base + (i < rem ? 1u : 0u));
@@ -388,6 +423,7 @@ struct NatPass {
     PowTable tw;             // w_{2^log_n}^e
     const uint32_t* small;
     unsigned small_log;
+    unsigned col_bits;       // column-batched data: the lowest address bits index independent transforms (0 otherwise)
     unsigned nprev;          // digits already transformed (address bits above this digit), most significant first
     unsigned prev_bits[4];   // their widths
     unsigned prev_off[4];    // their positions in the output index: off[d] = r_1 + .. + r_(d-1)
@@ -458,7 +494,7 @@ __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat
         if (!FIRST && b == 0) {
             const uint32_t K = nat_kacc(ps, (uint32_t)high);
             for (int rho = threadIdx.x; rho < R; rho += T) {         // indexed by tile row: consecutive words for a warp's 4 rows
-                const uint32_t w = pow_lookup(ps.tw, (K * bitrev_bits((uint32_t)rho, R_LOG)) << ps.lo, fp);
+                const uint32_t w = pow_lookup(ps.tw, (K * bitrev_bits((uint32_t)rho, R_LOG)) << (ps.lo - ps.col_bits), fp);
                 rowtw[rho] = make_uint2(w, w * fp.pinv);
             }
             __syncthreads();
@@ -662,6 +698,47 @@ void ntt_natural(stark_ctx* ctx, const uint32_t* src, size_t src_len, uint32_t* 
         off += r; hi -= r;
     }
     STARK_CUDA(cudaGetLastError());
+}
+
+// ---- column-batched transform with the same strided passes: data[2^log_n rows][2^col_bits columns], every column an
+// independent transform (phase A of the multi-GPU four-step NTT).  Every digit is strided here, so all passes are
+// nat_strided passes, in place; natural rows in, and slot [k_1][k_2]..[k_m] (digit k_1 in the most significant address
+// bits) holds X[k_1 + R_1 k_2 + R_1 R_2 k_3 + ..]: digit-reversed, which the caller undoes for free when it scatters the
+// rows to their owners.  Values are weak after the last pass (the consumer multiplies).  Returns the digit widths.
+std::vector<unsigned> ntt_columns_digitrev(stark_ctx* ctx, uint32_t* data, unsigned log_n, unsigned col_bits, bool inverse_root) {
+    check_size(ctx, log_n);
+    STARK_REQUIRE(log_n >= 10 && col_bits >= 5 && log_n + col_bits <= 31, "ntt_columns_digitrev: needs >= 2^10 rows, >= 32 columns, < 2^31 elements");
+    STARK_REQUIRE((reinterpret_cast<uintptr_t>(data) & 15) == 0, "ntt_columns_digitrev: unaligned buffer");
+    const TwiddleSet& tws = ctx->twiddles(log_n);
+    const size_t total = (size_t)1 << (log_n + col_bits);
+    std::vector<unsigned> bits = plan_bits(log_n);
+    KernelTimer kt(ctx, stark_ctx::CAT_NTT, 16.0 * (double)total);
+    NatPass ps{};
+    ps.log_n = log_n; ps.col_bits = col_bits;
+    ps.tw = inverse_root ? tws.inv() : tws.fwd();
+    ps.small = inverse_root ? ctx->small_inv.as<uint32_t>() : ctx->small_fwd.as<uint32_t>();
+    ps.small_log = ctx->small_log;
+    ps.src = data; ps.dst = data; ps.src_len = (unsigned)total; ps.has_scale = 0;
+    unsigned hi = log_n, off = 0;
+    for (size_t i = 0; i < bits.size(); i++) {
+        const unsigned r = bits[i];
+        ps.lo = hi - r + col_bits;
+        ps.nprev = (unsigned)i;
+        const size_t tiles = total / ((size_t)NTT_C << r);
+        const bool first = (i == 0);
+        switch (r) {
+            case 5: first ? launch_nat_strided<5, true>(ctx, ps, tiles) : launch_nat_strided<5, false>(ctx, ps, tiles); break;
+            case 6: first ? launch_nat_strided<6, true>(ctx, ps, tiles) : launch_nat_strided<6, false>(ctx, ps, tiles); break;
+            case 7: first ? launch_nat_strided<7, true>(ctx, ps, tiles) : launch_nat_strided<7, false>(ctx, ps, tiles); break;
+            case 8: first ? launch_nat_strided<8, true>(ctx, ps, tiles) : launch_nat_strided<8, false>(ctx, ps, tiles); break;
+            case 9: first ? launch_nat_strided<9, true>(ctx, ps, tiles) : launch_nat_strided<9, false>(ctx, ps, tiles); break;
+            default: throw StarkError(ST_INTERNAL, "ntt_columns_digitrev: bad pass width");
+        }
+        ps.prev_bits[i] = r; ps.prev_off[i] = off;
+        off += r; hi -= r;
+    }
+    STARK_CUDA(cudaGetLastError());
+    return bits;
 }
 
 // ---- blow-up-by-8 forward transform: one size-n NTT over 8 interleaved coset columns ------------------------

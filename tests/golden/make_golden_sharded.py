@@ -3,6 +3,7 @@ that `bench.py --gpus N` can assert its multi-GPU results inside the run (the or
   cfg4  64 columns x 2^22 rows (seeds 100+c), trace domain <g>, LDE on the coset 5*<h> of size 2^25: the 64 Merkle roots
   cfg5  one polynomial of degree 2^23-1 (seed 43) on the coset 5*<w> of size 2^26: root of layer 0, every later root,
         the final constant and the transcript after fri_commit + 8 openings
+  prove5  the FibonacciSq prover (stark101_prove) with a 2^23-1 row trace, LDE/FRI domain 2^26, 3 queries: the transcript
 Run from the repo root:  python tests/golden/make_golden_sharded.py   (~10 minutes on 8 cores, ~12 GB of RAM)"""
 import hashlib
 import json
@@ -42,13 +43,21 @@ def cfg5(log_n=26, queries=8):
             "proof_size": ch.proof_size(), "proof_sha256": hashlib.sha256(ch.proof_flat()).hexdigest()}
 
 
+def prove(log_trace=23, log_blowup=3, queries=3, a1=3141592):
+    ch = o.Channel(P)
+    o.stark101_prove(ch, a1, log_trace, log_blowup, o.G_DEFAULT, queries, literal=False)
+    return {"a1": a1, "log_trace": log_trace, "log_blowup": log_blowup, "queries": queries, "statement": ch.proof[0].hex(),
+            "trace_root": ch.proof[1].decode(), "final_state": ch.state, "proof_size": ch.proof_size(), "n_messages": len(ch.proof),
+            "proof_sha256": hashlib.sha256(ch.proof_flat()).hexdigest()}
+
+
 def main():
     o.build()
     o.set_num_threads(len(os.sched_getaffinity(0)))
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "sharded.json")
     out = json.load(open(path)) if os.path.exists(path) else {}
     out["_comment"] = __doc__
-    which = sys.argv[1:] or ["cfg5", "cfg5_small", "cfg4", "cfg4_small"]
+    which = sys.argv[1:] or ["cfg5", "cfg5_small", "prove5", "prove5_small", "cfg4", "cfg4_small"]
     for w in which:
         t0 = time.time()
         if w == "cfg4":
@@ -59,6 +68,10 @@ def main():
             out[w] = cfg5()
         elif w == "cfg5_small":
             out[w] = cfg5(22)
+        elif w == "prove5":
+            out[w] = prove()
+        elif w == "prove5_small":
+            out[w] = prove(15)
         print(w, "done in", round(time.time() - t0, 1), "s", flush=True)
         json.dump(out, open(path, "w"), indent=1)
     print("wrote", path)

@@ -183,6 +183,21 @@ def test_mg_fri_commit_world1(sp, orc, ctx, transport):
     f.free(); g.close()
 
 
+@pytest.mark.parametrize("log_trace,log_blowup,a1,q,transport", [(8, 3, 3141592, 3, 1), (12, 3, 99, 4, 0), (15, 3, 3141592, 3, 1)])
+def test_mg_stark101_prove_world1(sp, orc, ctx, log_trace, log_blowup, a1, q, transport):
+    """The C-level sharded prover with one rank: stark101_prove's transcript (and the oracle's); the verifier accepts it."""
+    g = sp.MultiGpu(ctx, 0, 1)
+    ch, ch1, och = sp.Channel(P), sp.Channel(P), orc.Channel(P)
+    g.stark101_prove(ch, a1, log_trace, log_blowup, q, transport)
+    sp.stark101_prove(ctx, ch1, a1, log_trace, log_blowup, q)
+    orc.stark101_prove(och, a1, log_trace, log_blowup, sp.G_DEFAULT, q, literal=False)
+    assert ch.state == ch1.state == och.state and ch.proof == ch1.proof == och.proof
+    claimed = int(orc.fibsq_trace(a1, (1 << log_trace) - 1)[(1 << log_trace) - 2])
+    ok, why = sp.stark101_verify(ch.proof_flat(), claimed, log_trace, log_blowup, q)
+    assert ok, why
+    g.close()
+
+
 # ---- full-size parity for the sharded configs on one GPU (VERDICT r1: cfg4 / cfg5 were never oracle-checked at size) ----
 def test_cfg4_one_column_full_size(sp, orc, ctx):
     """One cfg4 column at BASELINE size: 2^22 rows -> coset LDE 2^25 -> root == the oracle's, 64 sampled rows equal."""

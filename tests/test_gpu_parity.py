@@ -408,6 +408,41 @@ def test_opening_server_falls_back_when_it_times_out(sp, orc, ctx, monkeypatch):
         pr.free()
 
 
+def test_opening_server_when_launches_are_serialised(orc):
+    """CUDA_LAUNCH_BLOCKING=1 (like a profiler or a debugger) keeps the host inside the launch call until the resident
+    opening kernel has left: the first request is already posted, so it is answered; the kernel then idles for 2 ms at most
+    (250 ms in round 1) and the remaining queries are one launch each.  Same transcript, and no quarter second lost."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import importlib, sys, time
+sys.path.insert(0, %r)
+sp = importlib.import_module("stark-prover_b200")
+from oracle import pyoracle as orc
+P = sp.P_DEFAULT
+log_n, q = 14, 16
+coeffs = orc.synthetic_poly_exact_degree(78, 1 << (log_n - 3))
+och = orc.Channel(P)
+opr = orc.fri_commit_fast(coeffs, log_n, 5, orc.root_of_unity(log_n), och, P)
+orc.decommit_fri(q, (1 << log_n) - 1, opr, och)
+ctx = sp.Context()
+best = 1e9
+for rep in range(3):
+    ch = sp.Channel(P)
+    pr = sp.fri_commit(ctx, coeffs, sp.CosetFri(ctx, 5, log_n), ch)
+    t0 = time.perf_counter()
+    sp.decommit_fri(q, (1 << log_n) - 1, pr, ch)
+    best = min(best, time.perf_counter() - t0)
+    assert ch.state == och.state and ch.proof == och.proof
+    pr.free()
+print("decommit_seconds", best)
+""" % root
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CUDA_LAUNCH_BLOCKING="1"), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    secs = float(r.stdout.split("decommit_seconds")[1].split()[0])
+    assert secs < 0.1, f"decommit_fri of 16 queries took {secs:.3f} s with serialised launches"
+
+
 def test_fri_device_resident_input(sp, orc, ctx):
     log_n = 14
     c = orc.synthetic_poly_exact_degree(8, 1 << 11)
@@ -446,6 +481,20 @@ def test_stark101_other_sizes(sp, orc, ctx, log_trace, log_blowup, a1, q):
     sp.stark101_prove(ctx, ch, a1, log_trace, log_blowup, q)
     orc.stark101_prove(och, a1=a1, log_trace=log_trace, log_blowup=log_blowup, num_queries=q, literal=False)
     assert ch.proof == och.proof and ch.state == och.state
+
+
+@pytest.mark.parametrize("log_trace", [18, 20])
+def test_stark101_large_domains_vs_oracle(sp, orc, ctx, log_trace):
+    """the whole prover against the oracle's NTT tier at 2^21 and 2^23 domains (0.8 s / 3 s of CPU), message by
+    message, and the verifier accepts the GPU proof."""
+    q = 3
+    ch, och = sp.Channel(P), orc.Channel(P)
+    sp.stark101_prove(ctx, ch, 3141592, log_trace, 3, q)
+    orc.stark101_prove(och, a1=3141592, log_trace=log_trace, log_blowup=3, num_queries=q, literal=False)
+    assert ch.state == och.state and ch.proof == och.proof
+    claimed = int.from_bytes(ch.proof[0][40:48], "big")
+    ok, why = sp.stark101_verify(ch.proof_flat(), claimed, log_trace, 3, q)
+    assert ok, why
 
 
 # ---------------------------------------------------------------- other fields
@@ -663,3 +712,38 @@ def test_large_modulus_lde_and_fold_paths(sp, orc, modulus, gen):
         assert np.array_equal(pr.layer(1), orc.fri_fold_evals(want, beta, gen, w_n, modulus))
     finally:
         c.close()
+
+
+def test_context_destroyed_before_its_handles(sp, orc):
+    """a C or Rust caller may drop the context first.  stark_ctx_destroy with handles outstanding only marks
+    the context; the last handle released tears it down -- no use-after-free, and the handles stay usable until then."""
+    import ctypes as C
+    L = sp.lib()
+    h = C.c_void_p()
+    assert L.stark_ctx_create(P, 5, 0, C.byref(h)) == 0
+    vals = orc.synthetic_column(3, 1 << 12)
+    v, t = C.c_void_p(), C.c_void_p()
+    assert L.stark_vec_upload(h, vals.ctypes.data_as(C.c_void_p), vals.size, C.byref(v)) == 0
+    assert L.stark_merkle_commit_dev(h, v, C.byref(t)) == 0
+    L.stark_ctx_destroy(h)                                   # handles outstanding: deferred
+    out = np.zeros(16, dtype=np.uint64)
+    assert L.stark_vec_download(v, 0, 16, out.ctypes.data_as(C.c_void_p)) == 0 and np.array_equal(out, vals[:16])
+    root = np.zeros(32, dtype=np.uint8)
+    assert L.stark_merkle_root(t, root.ctypes.data_as(C.c_void_p)) == 0 and root.tobytes() == orc.merkle_root_only(vals)
+    L.stark_vec_destroy(v)
+    L.stark_tree_destroy(t)                                  # last handle: the context goes with it
+
+
+def test_oversized_log_n_is_rejected_before_any_read(sp, ctx):
+    """stark_ntt / stark_intt / stark_coset_interpolate sized and uploaded before checking log_n."""
+    import ctypes as C
+    L = sp.lib()
+    tiny = np.zeros(4, dtype=np.uint64)
+    for fn in (L.stark_ntt, L.stark_intt):
+        for bad in (31, 40, 64, 200):
+            assert fn(ctx.h, tiny.ctypes.data_as(C.c_void_p), bad) != 0
+    assert L.stark_coset_interpolate(ctx.h, tiny.ctypes.data_as(C.c_void_p), 31, 5, tiny.ctypes.data_as(C.c_void_p)) != 0
+    v = ctx.upload(np.arange(64, dtype=np.uint64))
+    with pytest.raises(sp.StarkError):
+        ctx.pow_mul_dev(v, 8, 0, True, 0, 5, 1, 4)         # exponents up to 7*7 = 49 >= 2^4
+    ctx.pow_mul_dev(v, 8, 0, True, 0, 5, 1, 6)             # 49 < 2^6: fine

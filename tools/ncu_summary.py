@@ -98,5 +98,35 @@ def traffic(src, dst):
     print("wrote", dst)
 
 
+def pipe(srcs, dst):
+    """ALU / FMA pipe utilisation per launch class from one or more --set full captures (comma-separated .ncu-rep files):
+    the executed-instruction view printed next to bench.py's algorithmic roofline fractions.  Time-weighted per class."""
+    import json
+    CLASS = {"merkle_subtree_kernel<0>": "merkle_subtree_kernel<VALUES>", "merkle_subtree_kernel<1>": "merkle_subtree_kernel<FOLD>",
+             "merkle_subtree_kernel<2>": "merkle_subtree_kernel<DIGESTS>"}
+    acc = collections.OrderedDict()
+    for src in srcs.split(","):
+        raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(raw)))
+        hdr = rows[0]
+        col = lambda name: hdr.index(name)
+        for r in rows[2:]:
+            k = short(r[col("Kernel Name")])
+            k = CLASS.get(k, re.sub(r"<.*", "", k) if k.startswith(("merkle_tail", "fri_")) else k)
+            t = float(r[col("gpu__time_duration.sum")].replace(",", ""))
+            a = acc.setdefault(k, {"t": 0.0, "alu": 0.0, "fma": 0.0, "issue": 0.0, "n": 0})
+            a["t"] += t; a["n"] += 1
+            a["alu"] += t * float(r[col("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active")])
+            a["fma"] += t * float(r[col("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active")])
+            a["issue"] += t * float(r[col("smsp__issue_active.avg.pct_of_peak_sustained_active")])
+    out = {"_source": f"ncu --set full --clock-control none: {srcs}; sm__pipe_alu_cycles_active / sm__pipe_fma_cycles_active / "
+                      "smsp__issue_active .avg.pct_of_peak_sustained_active, time-weighted over the captured launches of each class"}
+    for k, a in acc.items():
+        out[k] = {"alu_pipe_pct": round(a["alu"] / a["t"], 1), "fma_pipe_pct": round(a["fma"] / a["t"], 1),
+                  "issue_active_pct": round(a["issue"] / a["t"], 1), "launches_captured": a["n"]}
+    json.dump(out, open(dst, "w"), indent=1)
+    print("wrote", dst)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic, "pipe": pipe}[sys.argv[1]](sys.argv[2], sys.argv[3])
