@@ -123,7 +123,7 @@ void stark_ctx_teardown(stark_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ctx->tw.clear();
-    ctx->small_fwd.release(); ctx->small_inv.release(); ctx->tail_counter.release(); ctx->fs_ticket.release(); ctx->deg_scratch.release();
+    ctx->small_fwd.release(); ctx->small_inv.release(); ctx->tail_counter.release(); ctx->deg_scratch.release();
     BlockCache::flush(ctx->stream);
     cudaStreamSynchronize(ctx->stream);
     for (int c = 0; c < stark_ctx::CAT_COUNT; c++) for (auto& pr : ctx->ev_used[c]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }

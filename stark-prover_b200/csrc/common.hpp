@@ -221,7 +221,6 @@ struct stark_ctx {
     starkb200::PinnedBuf pin_stage;             // host-produced columns on their way to HBM (the FibonacciSq trace)
     starkb200::DevBuf deg_scratch;              // DegScratch of coeff_fold_kernel
     starkb200::DevBuf tail_counter;             // "last CTA" ticket of merkle_tail_kernel (zero between launches)
-    starkb200::DevBuf fs_ticket;                // the same for the four-step exchange kernels (fourstep.cu)
     int sm_count = 148;
     unsigned long long launches = 0;            // kernels launched through this context
     // Handles (vectors, trees, FRI proofs, groups) keep their context alive: stark_ctx_destroy with handles outstanding

@@ -9,6 +9,10 @@
 //   exch. 2            32x32 shared-memory transpose, then 128-byte stores into the peer that owns k2:
 //                      natural-order block of rank t: position (k2 % (N2/G))*N1 + k1      (fused transpose + exchange)
 // No bit-reversal pass and no separate pack/unpack pass exists anywhere in this pipeline.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "../../include/stark_b200.h"
 #include "handles.hpp"
 
@@ -59,16 +63,10 @@ void fourstep_stage_input(stark_ctx* ctx, const uint32_t* coeffs, size_t len, ui
 // ---- device-side hand-over between the phases (no host barrier, no stream synchronisation) ---------------------
 // Every rank owns a small peer-visible array of epoch words: flags[slot * MAX_PEERS + r] = the last transform for which
 // rank r has finished storing into THIS rank's buffer (slot 0: the rows of exchange 1, slot 1: the block of exchange 2).
-// A scatter kernel ends with: every thread fences its peer stores at system scope, the CTAs take a ticket, and the last
-// one publishes the epoch to all peers (st.release.sys).  The consumer runs a one-warp kernel in front of its next phase
-// that spins with ld.acquire.sys until all `world` words have reached the epoch; stream order does the rest.
+// A one-warp kernel behind each scatter kernel publishes the epoch to all peers (st.release.sys); the consumer runs a
+// one-warp kernel in front of its next phase that spins with ld.acquire.sys until all `world` words have reached the
+// epoch; stream order does the rest.
 struct FlagPtrs { uint32_t* p[MAX_PEERS]; };
-struct FsSignal {
-    FlagPtrs flags;          // flags.p[s] = rank s's flag array (null pointers: no signalling, the host synchronises)
-    unsigned* ticket;        // zero between launches
-    unsigned slot, rank, world;
-    uint32_t epoch;
-};
 __device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -77,23 +75,18 @@ __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// tail of a scatter kernel; `first` = this CTA's thread that takes the ticket, `n_ctas` = CTAs in the grid.
-// One system-scope fence per CTA, after the barrier: the barrier orders every thread's peer stores before thread 0's
-// fence (causality is transitive through bar.sync -- the pattern of a cooperative-groups grid sync), and the fence is
-// cumulative over them.  A fence.sys in EVERY thread made these kernels 5x slower (91 / 113 us instead of ~20 us for
-// 2^23 elements, profiles/r02_fourstep.md).
-__device__ __forceinline__ void fs_publish(const FsSignal& sg, bool first, unsigned n_ctas) {
-    if (!sg.ticket) return;
-    __syncthreads();
-    if (first) {
-        __threadfence_system();                  // the CTA's peer stores are performed before the ticket
-        const unsigned t = atomicAdd(sg.ticket, 1u);
-        if (t == n_ctas - 1) {
-            *sg.ticket = 0;                      // re-armed for the next launch on this stream
-            __threadfence_system();
-            for (unsigned s = 0; s < sg.world; s++) st_release_sys_u32(sg.flags.p[s] + sg.slot * MAX_PEERS + sg.rank, sg.epoch);
-        }
-    }
+// Hand-over: a ONE-WARP kernel enqueued right behind a scatter kernel publishes the epoch to every peer.  Stream order
+// makes it start only when the scatter kernel's grid has completed, i.e. when all of its stores -- the peer stores over
+// NVLink included -- have been performed; the fence + st.release.sys pair then orders the flag behind them for the
+// peer's ld.acquire.sys.  (Measured alternatives, profiles/r02_fourstep.md: a system-scope fence in every thread of the
+// scatter kernel: 91 / 113 us instead of 23 / 31 us for 2^23 elements; one fence per CTA + "last CTA publishes": still
+// +23 us per kernel, with 8192 CTAs or with 1184 persistent ones -- a fence.sys stalls behind every outstanding peer
+// store of its SM.  The extra launch costs ~3 us.)
+__global__ void fourstep_publish_kernel(FlagPtrs flags, unsigned slot, unsigned rank, unsigned world, uint32_t epoch) {
+    const unsigned s = threadIdx.x;
+    if (s >= world) return;
+    __threadfence_system();
+    st_release_sys_u32(flags.p[s] + slot * MAX_PEERS + rank, epoch);
 }
 // Spins until every peer's epoch word of `slot` has reached `epoch` (wrap-safe compare).  After `timeout_ns` it gives up
 // and raises result->flag so that the host reports a lost peer instead of hanging.
@@ -130,8 +123,7 @@ __device__ __forceinline__ void stage_peers(uint32_t** s_peer, const PeerPtrs& p
 // dst = base[owner] + row * row_pitch + col_off + c:
 // peer memory: row_pitch = N2, col_off = rank * w (the owner's [N1/G][N2] matrix);  staging for NCCL: row_pitch = w, col_off = 0.
 __global__ void fourstep_rows_kernel(const uint32_t* __restrict__ A, unsigned log_n1, unsigned log_w, unsigned log_g,
-                                     unsigned rank, PeerPtrs peers, size_t row_pitch, size_t col_off, PowTable tw, FieldParams fp, FsSignal sg,
-                                     SlotMap map) {
+                                     unsigned rank, PeerPtrs peers, size_t row_pitch, size_t col_off, PowTable tw, FieldParams fp, SlotMap map) {
     __shared__ uint32_t* s_peer[MAX_PEERS];
     __shared__ uint32_t s_lo[32], s_hi[32];
     const unsigned tid = threadIdx.x, seg_len = blockDim.x * 4;          // columns of this CTA's segment
@@ -139,39 +131,29 @@ __global__ void fourstep_rows_kernel(const uint32_t* __restrict__ A, unsigned lo
     const uint32_t k1 = slot_index(map, q);
     const uint32_t n2_0 = (rank << log_w) + c0;
     stage_peers(s_peer, peers, tid);
-    for (unsigned i = tid; i < 64; i += blockDim.x) {                                     // (a segment may have fewer than 64 threads)
+    for (unsigned i = tid; i < 64; i += blockDim.x) {                     // (a segment may have fewer than 64 threads)
         if (i < 32) s_lo[i] = pow_lookup(tw, k1 * i, fp);                                   // k1 * 31 < N
         else if ((i - 32) * 32 < seg_len) s_hi[i - 32] = pow_lookup(tw, k1 * (n2_0 + (i - 32) * 32), fp);   // k1 * n2 < N
     }
+    const uint32_t c = c0 + tid * 4;
+    const uint4 a = *reinterpret_cast<const uint4*>(A + ((size_t)q << log_w) + c);          // in flight across the barrier
     __syncthreads();
-    {
-        const uint32_t c = c0 + tid * 4;
-        const uint4 a = *reinterpret_cast<const uint4*>(A + ((size_t)q << log_w) + c);
-        const uint32_t hi = s_hi[tid >> 3], j = (tid & 7) * 4;
-        uint4 v;
-        v.x = mont_mul(a.x, mont_mul(s_lo[j], hi, fp), fp);
-        v.y = mont_mul(a.y, mont_mul(s_lo[j + 1], hi, fp), fp);
-        v.z = mont_mul(a.z, mont_mul(s_lo[j + 2], hi, fp), fp);
-        v.w = mont_mul(a.w, mont_mul(s_lo[j + 3], hi, fp), fp);
-        const unsigned rows_per = log_n1 - log_g;
-        const uint32_t owner = k1 >> rows_per, row = k1 & ((1u << rows_per) - 1);
-        *reinterpret_cast<uint4*>(s_peer[owner] + (size_t)row * row_pitch + col_off + c) = v;
-    }
-    fs_publish(sg, tid == 0, gridDim.x * gridDim.y);
+    const uint32_t hi = s_hi[tid >> 3], j = (tid & 7) * 4;
+    uint4 v;
+    v.x = mont_mul(a.x, mont_mul(s_lo[j], hi, fp), fp);
+    v.y = mont_mul(a.y, mont_mul(s_lo[j + 1], hi, fp), fp);
+    v.z = mont_mul(a.z, mont_mul(s_lo[j + 2], hi, fp), fp);
+    v.w = mont_mul(a.w, mont_mul(s_lo[j + 3], hi, fp), fp);
+    const unsigned rows_per = log_n1 - log_g;
+    const uint32_t owner = k1 >> rows_per, row = k1 & ((1u << rows_per) - 1);
+    *reinterpret_cast<uint4*>(s_peer[owner] + (size_t)row * row_pitch + col_off + c) = v;
 }
-static unsigned* fs_ticket(stark_ctx* ctx) {
-    if (!ctx->fs_ticket.p) {
-        ctx->fs_ticket = DevBuf(sizeof(unsigned), ctx->stream);
-        STARK_CUDA(cudaMemsetAsync(ctx->fs_ticket.p, 0, sizeof(unsigned), ctx->stream));
-    }
-    return ctx->fs_ticket.as<unsigned>();
-}
-static FsSignal make_signal(stark_ctx* ctx, void* const* peer_flags, unsigned slot, unsigned rank, unsigned world, uint32_t epoch) {
-    FsSignal sg{};
-    if (!peer_flags) return sg;
-    for (unsigned s = 0; s < world; s++) sg.flags.p[s] = static_cast<uint32_t*>(peer_flags[s]);
-    sg.ticket = fs_ticket(ctx); sg.slot = slot; sg.rank = rank; sg.world = world; sg.epoch = epoch;
-    return sg;
+static void fs_publish(stark_ctx* ctx, void* const* peer_flags, unsigned slot, unsigned rank, unsigned world, uint32_t epoch) {
+    if (!peer_flags) return;
+    FlagPtrs f{};
+    for (unsigned s = 0; s < world; s++) f.p[s] = static_cast<uint32_t*>(peer_flags[s]);
+    fourstep_publish_kernel<<<1, 32, 0, ctx->stream>>>(f, slot, rank, world, epoch);
+    ctx->launches++;
 }
 void fourstep_twiddle_scatter_rows(stark_ctx* ctx, const uint32_t* A, unsigned log_n1, unsigned log_n2, unsigned world, unsigned rank,
                                    const PeerPtrs& peers, bool staged, void* const* peer_flags, uint32_t epoch, const SlotMap& map) {
@@ -186,16 +168,16 @@ void fourstep_twiddle_scatter_rows(stark_ctx* ctx, const uint32_t* A, unsigned l
     const unsigned seg = w < 1024 ? (unsigned)w : 1024u;                       // columns per CTA, 4 per thread
     STARK_REQUIRE(((size_t)1 << log_n1) <= 65535, "fourstep: too many rows for one grid dimension");
     fourstep_rows_kernel<<<dim3((unsigned)(w / seg), 1u << log_n1), seg / 4, 0, ctx->stream>>>(
-        A, log_n1, log_w, log_g, rank, peers, staged ? w : ((size_t)1 << log_n2), staged ? 0 : (size_t)rank * w, tws.fwd(), ctx->fp,
-        make_signal(ctx, peer_flags, 0, rank, world, epoch), map);
+        A, log_n1, log_w, log_g, rank, peers, staged ? w : ((size_t)1 << log_n2), staged ? 0 : (size_t)rank * w, tws.fwd(), ctx->fp, map);
     ctx->launches++;
+    fs_publish(ctx, peer_flags, 0, rank, world, epoch);
     STARK_CUDA(cudaGetLastError());
 }
 
 // tile: 32 rows (k1') x 32 slots (q2); block (32, 8).  dst = base[owner] + col * col_pitch + k1_off + k1':
 // peer memory: col_pitch = N1, k1_off = rank * N1/G (the owner's natural-order block);  staging: col_pitch = N1/G, k1_off = 0.
 __global__ void fourstep_transpose_kernel(const uint32_t* __restrict__ X, unsigned log_n2, unsigned log_g, PeerPtrs peers,
-                                          size_t col_pitch, size_t k1_off, FsSignal sg, SlotMap map) {
+                                          size_t col_pitch, size_t k1_off, SlotMap map) {
     __shared__ uint32_t tile[32][33];
     __shared__ uint32_t* s_peer[MAX_PEERS];
     stage_peers(s_peer, peers, threadIdx.y * 32 + threadIdx.x);
@@ -211,7 +193,6 @@ __global__ void fourstep_transpose_kernel(const uint32_t* __restrict__ X, unsign
         uint32_t owner = k2 >> cols_per, col = k2 & ((1u << cols_per) - 1);
         s_peer[owner][(size_t)col * col_pitch + k1_off + r0 + threadIdx.x] = tile[threadIdx.x][j];
     }
-    fs_publish(sg, threadIdx.x == 0 && threadIdx.y == 0, gridDim.x * gridDim.y);
 }
 void fourstep_transpose_scatter(stark_ctx* ctx, const uint32_t* X, unsigned log_n1, unsigned log_n2, unsigned world, unsigned rank,
                                 const PeerPtrs& peers, bool staged, void* const* peer_flags, uint32_t epoch, const SlotMap& map) {
@@ -221,9 +202,9 @@ void fourstep_transpose_scatter(stark_ctx* ctx, const uint32_t* X, unsigned log_
     dim3 grid(1u << (log_n2 - 5), 1u << (log_r - 5));
     KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 16.0 * (double)((size_t)1 << (log_r + log_n2)));
     fourstep_transpose_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(
-        X, log_n2, log_g, peers, staged ? ((size_t)1 << log_r) : ((size_t)1 << log_n1), staged ? 0 : ((size_t)rank << log_r),
-        make_signal(ctx, peer_flags, 1, rank, world, epoch), map);
+        X, log_n2, log_g, peers, staged ? ((size_t)1 << log_r) : ((size_t)1 << log_n1), staged ? 0 : ((size_t)rank << log_r), map);
     ctx->launches++;
+    fs_publish(ctx, peer_flags, 1, rank, world, epoch);
     STARK_CUDA(cudaGetLastError());
 }
 void fourstep_wait(stark_ctx* ctx, const void* own_flags, unsigned slot, unsigned world, uint32_t epoch) {
@@ -241,15 +222,20 @@ void fourstep_phase_a_launch(stark_ctx* ctx, const uint32_t* coeffs, size_t n_co
     while ((1u << log_g) < world) log_g++;
     const unsigned log_w = b - log_g;
     DevBuf A(((size_t)4) << (a + log_w), ctx->stream);
-    fourstep_stage_input(ctx, coeffs, n_coeffs, A.as<uint32_t>(), a, b, world, rank, offset);
     SlotMap map = bitrev_map(a);
-    if (a >= 10 && a + log_w <= 31) {
+    if (a >= 10 && a + log_w <= 31 && (reinterpret_cast<uintptr_t>(coeffs) & 15) == 0) {
         // the strided passes of the natural-order transform (lazy 9-instruction butterflies, 16-byte accesses, one
-        // row twiddle per tile row); they leave digit-reversed slots, which the scatter below undoes for free
-        std::vector<unsigned> bits = ntt_columns_digitrev(ctx, A.as<uint32_t>(), a, log_w, false);
+        // row twiddle per tile row); the first pass gathers this rank's columns of the coefficient matrix and applies the
+        // coset scale on the way in (no staging sweep); they leave digit-reversed slots, which the scatter below undoes for free
+        const bool unit = offset % ctx->modulus == 1;
+        ScaleTable st;
+        if (!unit) build_scale_table(ctx, offset % ctx->modulus, 1, a + b, st);
+        ColumnSource from{coeffs, n_coeffs, b, (unsigned)(rank << log_w), unit ? nullptr : &st.view};
+        std::vector<unsigned> bits = ntt_columns_digitrev(ctx, A.as<uint32_t>(), a, log_w, false, &from);
         map.mode = 1; map.nd = (unsigned)bits.size();
         for (size_t i = 0; i < bits.size(); i++) map.bits[i] = bits[i];
     } else {
+        fourstep_stage_input(ctx, coeffs, n_coeffs, A.as<uint32_t>(), a, b, world, rank, offset);
         ntt_dif_columns(ctx, A.as<uint32_t>(), a, log_w, false);
     }
     fourstep_twiddle_scatter_rows(ctx, A.as<uint32_t>(), a, b, world, rank, dst, staged, peer_flags, epoch, map);

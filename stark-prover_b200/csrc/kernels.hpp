@@ -79,7 +79,11 @@ void ntt_natural(stark_ctx* ctx, const uint32_t* src, size_t src_len, uint32_t* 
 // column-batched transform over data[2^log_n rows][2^col_bits columns] with the strided passes of ntt_natural (log_n >= 10,
 // col_bits >= 5): natural rows in, DIGIT-reversed slots out (slot [k_1]..[k_m] holds X[k_1 + R_1 k_2 + ..]), weak values;
 // returns the digit widths R_i = 2^bits[i], most significant address digit first
-std::vector<unsigned> ntt_columns_digitrev(stark_ctx* ctx, uint32_t* data, unsigned log_n, unsigned col_bits, bool inverse_root);
+// `from` (optional): the first pass reads element (row, col) from from->src[(row << row_log) + col_off + col] (zero beyond
+// src_len) and multiplies it by scale(that index) -- a column slice of a larger row-major array, no staging copy
+struct ColumnSource { const uint32_t* src; size_t src_len; unsigned row_log, col_off; const PowTable* scale; };
+std::vector<unsigned> ntt_columns_digitrev(stark_ctx* ctx, uint32_t* data, unsigned log_n, unsigned col_bits, bool inverse_root,
+                                           const ColumnSource* from = nullptr);
 // column-batched DIF over data[2^log_n rows][2^col_bits columns] (col_bits >= 5): natural rows in, bit-reversed out
 void ntt_dif_columns(stark_ctx* ctx, uint32_t* data, unsigned log_n, unsigned col_bits, bool inverse_root);
 // Blow-up-by-8 forward transform (the LDE / evaluate hot path): dst[8k'+s] = sum_j c_j (base w_N^s)^j w_n^(j k'),

@@ -424,11 +424,20 @@ struct NatPass {
     const uint32_t* small;
     unsigned small_log;
     unsigned col_bits;       // column-batched data: the lowest address bits index independent transforms (0 otherwise)
+    // FIRST pass of a column-batched transform reading a slice of a larger row-major array (phase A of the four-step
+    // NTT reads its columns of the coefficient matrix directly: no staging sweep): element (row, col) of the working array
+    // comes from src[(row << src_row_log) + src_col_off + col]; src_len and the input scale are indexed the same way
+    int src_map;
+    unsigned src_row_log, src_col_off;
     unsigned nprev;          // digits already transformed (address bits above this digit), most significant first
     unsigned prev_bits[4];   // their widths
     unsigned prev_off[4];    // their positions in the output index: off[d] = r_1 + .. + r_(d-1)
 };
 
+__device__ __forceinline__ size_t nat_src_index(const NatPass& ps, size_t g) {
+    if (!ps.src_map) return g;
+    return ((g >> ps.col_bits) << ps.src_row_log) + ps.src_col_off + (g & (((size_t)1 << ps.col_bits) - 1));
+}
 // output index accumulated by the earlier passes from the address bits above this pass's digit
 __device__ __forceinline__ uint32_t nat_kacc(const NatPass& ps, uint32_t high) {
     uint32_t k = 0;
@@ -480,11 +489,12 @@ __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat
             const int g4 = i & 7, rho = i >> 3;
             const size_t g = gbase + ((size_t)bitrev_bits((uint32_t)rho, R_LOG) << ps.lo) + 4 * g4;
             if (FIRST) {
-                if (g + 3 < ps.src_len) a[u] = *reinterpret_cast<const uint4*>(ps.src + g);
+                const size_t gs = nat_src_index(ps, g);
+                if (gs + 3 < ps.src_len) a[u] = *reinterpret_cast<const uint4*>(ps.src + gs);
                 else {
-                    a[u].x = (g < ps.src_len) ? ps.src[g] : 0u;
-                    a[u].y = (g + 1 < ps.src_len) ? ps.src[g + 1] : 0u;
-                    a[u].z = (g + 2 < ps.src_len) ? ps.src[g + 2] : 0u;
+                    a[u].x = (gs < ps.src_len) ? ps.src[gs] : 0u;
+                    a[u].y = (gs + 1 < ps.src_len) ? ps.src[gs + 1] : 0u;
+                    a[u].z = (gs + 2 < ps.src_len) ? ps.src[gs + 2] : 0u;
                     a[u].w = 0u;
                 }
             } else {
@@ -505,7 +515,7 @@ __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat
             const int g4 = i & 7, rho = i >> 3;
             uint32_t v[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
             if (FIRST) {
-                const size_t g = gbase + ((size_t)bitrev_bits((uint32_t)rho, R_LOG) << ps.lo) + 4 * g4;
+                const size_t g = nat_src_index(ps, gbase + ((size_t)bitrev_bits((uint32_t)rho, R_LOG) << ps.lo) + 4 * g4);
                 if (ps.has_scale && g < ps.src_len) {      // one look-up, then walk base^(g+k) (the table ends at src_len)
                     uint32_t sc = pow_lookup(ps.scale, (uint32_t)g, fp);
                     const uint32_t step = __ldg(ps.scale.lo + 1);
@@ -705,7 +715,8 @@ void ntt_natural(stark_ctx* ctx, const uint32_t* src, size_t src_len, uint32_t* 
 // nat_strided passes, in place; natural rows in, and slot [k_1][k_2]..[k_m] (digit k_1 in the most significant address
 // bits) holds X[k_1 + R_1 k_2 + R_1 R_2 k_3 + ..]: digit-reversed, which the caller undoes for free when it scatters the
 // rows to their owners.  Values are weak after the last pass (the consumer multiplies).  Returns the digit widths.
-std::vector<unsigned> ntt_columns_digitrev(stark_ctx* ctx, uint32_t* data, unsigned log_n, unsigned col_bits, bool inverse_root) {
+std::vector<unsigned> ntt_columns_digitrev(stark_ctx* ctx, uint32_t* data, unsigned log_n, unsigned col_bits, bool inverse_root,
+                                           const ColumnSource* from) {
     check_size(ctx, log_n);
     STARK_REQUIRE(log_n >= 10 && col_bits >= 5 && log_n + col_bits <= 31, "ntt_columns_digitrev: needs >= 2^10 rows, >= 32 columns, < 2^31 elements");
     STARK_REQUIRE((reinterpret_cast<uintptr_t>(data) & 15) == 0, "ntt_columns_digitrev: unaligned buffer");
@@ -719,6 +730,14 @@ std::vector<unsigned> ntt_columns_digitrev(stark_ctx* ctx, uint32_t* data, unsig
     ps.small = inverse_root ? ctx->small_inv.as<uint32_t>() : ctx->small_fwd.as<uint32_t>();
     ps.small_log = ctx->small_log;
     ps.src = data; ps.dst = data; ps.src_len = (unsigned)total; ps.has_scale = 0;
+    if (from) {           // the first pass gathers the working array from a slice of `from->src` and scales it on the way in
+        STARK_REQUIRE((reinterpret_cast<uintptr_t>(from->src) & 15) == 0 && from->col_off % 4 == 0 && from->src_len <= 0xffffffffull,
+                      "ntt_columns_digitrev: unaligned source slice");
+        ps.src = from->src; ps.src_len = (unsigned)from->src_len; ps.src_map = 1;
+        ps.src_row_log = from->row_log; ps.src_col_off = from->col_off;
+        ps.has_scale = from->scale != nullptr;
+        if (from->scale) ps.scale = *from->scale;
+    }
     unsigned hi = log_n, off = 0;
     for (size_t i = 0; i < bits.size(); i++) {
         const unsigned r = bits[i];

@@ -525,9 +525,12 @@ class FourStepP2P:
     The product path for non-Python callers is `stark_mg_fourstep_lde` (csrc/multi.cu), which does the same with its own
     NCCL communicator; this class drives the phase entry points from Python over torch.distributed."""
 
-    def __init__(self, sp, ctx, log_n: int, rank: int, world: int, group=None, host_barriers: bool = False):
+    def __init__(self, sp, ctx, log_n: int, rank: int, world: int, group=None, host_barriers: bool = False, gather=None, barrier=None):
+        """gather(bytes array) -> [world, n] and barrier(): the plumbing between the ranks; default torch.distributed."""
         self.sp, self.ctx, self.log_n, self.rank, self.world, self.group = sp, ctx, log_n, rank, world, group
         self.host_barriers, self.epoch = host_barriers, 0
+        self._gather = gather or (lambda a: all_gather_bytes(a, group))
+        self._barrier_fn = barrier
         n_loc = (1 << log_n) // world
         self.rows, h_rows = ctx.peer_alloc(n_loc)
         self.block, h_block = ctx.peer_alloc(n_loc)
@@ -537,7 +540,7 @@ class FourStepP2P:
         if world == 1:
             self.peer_rows, self.peer_blocks, self.peer_flags = [self.rows.device_ptr], [self.block.device_ptr], [self.flags.device_ptr]
         else:
-            hs = all_gather_bytes(np.frombuffer(h_rows + h_block + h_flags, dtype=np.uint8), group)       # [world, 192]
+            hs = self._gather(np.frombuffer(h_rows + h_block + h_flags, dtype=np.uint8))       # [world, 192]
             self.peer_rows, self.peer_blocks, self.peer_flags = [], [], []
             for r in range(world):
                 if r == rank:
@@ -550,6 +553,8 @@ class FourStepP2P:
             self._barrier()                               # every buffer exists and is zeroed before anyone stores into it
 
     def _barrier(self):
+        if self._barrier_fn is not None:
+            return self._barrier_fn()
         dist = _dist()
         if self.world > 1 and dist.is_initialized():
             dist.barrier(group=self.group)
