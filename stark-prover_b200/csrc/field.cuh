@@ -10,11 +10,22 @@
 namespace starkb200 {
 
 struct FieldParams {
+    static constexpr bool is_ref = false;
     uint32_t p;      // modulus
     uint32_t pinv;   // p^-1 mod 2^32
     uint32_t r2;     // 2^64 mod p  (to Montgomery form: mont_mul(a, r2))
     uint32_t one;    // 2^32 mod p  (1 in Montgomery form)
 };
+// The reference's own field, p = 3 * 2^30 + 1 (the crate's MODULUS, src/fields/element.rs), as compile-time constants.
+// The device functions below are templates over the field description: with FieldRef the modulus, its negation and
+// p^-1 = 2^30 + 1 are instruction immediates; every other modulus passes the run-time FieldParams.
+struct FieldRef {
+    static constexpr bool is_ref = true;
+    static constexpr uint32_t p = 0xC0000001u, pinv = 0x40000001u, r2 = 0x6AAAAAADu, one = 0x3FFFFFFFu;
+};
+static_assert((uint32_t)(FieldRef::p * FieldRef::pinv) == 1u, "p^-1 mod 2^32");
+static_assert((((uint64_t)1 << 32) % FieldRef::p) == FieldRef::one && ((uint64_t)FieldRef::one * FieldRef::one) % FieldRef::p == FieldRef::r2,
+              "Montgomery constants of the reference field");
 
 // ---- conditional corrections --------------------------------------------------------------------------------
 // Every modular add / subtract / Montgomery product ends in "add or subtract p if the 32-bit result went the wrong
@@ -39,8 +50,11 @@ static __constant__ uint32_t c_field_zero = 0;
 // through: ptxas otherwise folds the subtraction that follows into the multiply (IMAD.HI Rd, P0, a, b, {0, -h}), which
 // costs a negate, a register-pair move and a zeroing per product and takes its carry from hi + (2^32 - h) -- no carry for
 // h == 0, where a subtraction has one.
+#ifndef STARK_MULHI_PLAIN
+#define STARK_MULHI_PLAIN 0
+#endif
 __device__ __forceinline__ uint32_t mulhi_nofuse(uint32_t a, uint32_t b) {
-#if STARK_FIELD_CARRY
+#if STARK_FIELD_CARRY && !STARK_MULHI_PLAIN
     uint32_t hi;
     const uint32_t zero = c_field_zero;
     asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(hi) : "r"(a), "r"(b), "r"(zero));
@@ -109,7 +123,8 @@ __device__ __forceinline__ uint32_t add_wrap_fix(uint32_t a, uint32_t b, uint32_
 #ifndef STARK_MONT_WIDE
 #define STARK_MONT_WIDE 0
 #endif
-__device__ __forceinline__ uint32_t mont_mul(uint32_t a, uint32_t b, const FieldParams& f) {
+template <class F>
+__device__ __forceinline__ uint32_t mont_mul(uint32_t a, uint32_t b, const F& f) {
 #if STARK_MONT_WIDE
     uint64_t t = (uint64_t)a * b;                 // one IMAD.WIDE instead of IMAD + IMAD.HI
     uint32_t lo = (uint32_t)t, hi = (uint32_t)(t >> 32);
@@ -127,14 +142,34 @@ __device__ __forceinline__ uint32_t mont_mul(uint32_t a, uint32_t b, const Field
 }
 // The same product when the second factor is a table constant stored with wp = w * p^-1 mod 2^32 next to it (the
 // transform twiddles): q = x * wp is one multiply, so the product is IMAD + 2 IMAD.HI + the correction.
-__device__ __forceinline__ uint32_t mont_mul_tw(uint32_t x, uint32_t w, uint32_t wp, const FieldParams& f) {
+#ifndef STARK_MONT_TW_WIDE
+#define STARK_MONT_TW_WIDE 1
+#endif
+template <class F>
+__device__ __forceinline__ uint32_t mont_mul_tw(uint32_t x, uint32_t w, uint32_t wp, const F& f) {
+#if STARK_MONT_TW_WIDE
+    // x * w as ONE 64-bit product whose low word feeds q: the subtraction below cannot be folded into a multiply whose
+    // own low half it depends on, so no opaque addend (and none of the register-pair moves it cost) is needed
+    (void)wp;
+    const uint64_t t = (uint64_t)x * w;
+    uint32_t qw;
+    if constexpr (F::is_ref) {
+        // p = 3 * 2^30 + 1: p^-1 = 2^30 + 1 mod 2^32, so q = lo + (lo << 30) -- one shift-add on the ALU pipe instead of a
+        // multiply on the FMA pipe (written in PTX: the front end turns the C shift-add back into a multiply by the constant)
+        asm("{ .reg .u32 s; shl.b32 s, %1, 30; add.u32 %0, s, %1; }" : "=r"(qw) : "r"((uint32_t)t));
+    } else {
+        qw = (uint32_t)t * f.pinv;
+    }
+    return sub_fix<(STARK_CORR_FMA & 1) != 0>((uint32_t)(t >> 32), __umulhi(qw, f.p), f.p);
+#endif
     uint32_t q = x * wp;
     uint32_t hi = mulhi_nofuse(x, w);
     uint32_t h = __umulhi(q, f.p);
     return sub_fix<(STARK_CORR_FMA & 1) != 0>(hi, h, f.p);
 }
 // canonical a, b -> canonical a + b:  a + (b - p) carries out of 32 bits exactly when a + b >= p
-__device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b, const FieldParams& f) {
+template <class F>
+__device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b, const F& f) {
 #if STARK_FIELD_CARRY
     uint32_t s;
     const uint32_t one = c_field_one, t = b - f.p;
@@ -150,12 +185,16 @@ __device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b, const FieldPara
     return (s < a || s >= f.p) ? s - f.p : s;
 #endif
 }
-__device__ __forceinline__ uint32_t fsub(uint32_t a, uint32_t b, const FieldParams& f) { return sub_fix(a, b, f.p); }
-__device__ __forceinline__ uint32_t to_mont(uint32_t a, const FieldParams& f) { return mont_mul(a, f.r2, f); }
-__device__ __forceinline__ uint32_t from_mont(uint32_t a, const FieldParams& f) { return mont_mul(a, 1u, f); }
+template <class F>
+__device__ __forceinline__ uint32_t fsub(uint32_t a, uint32_t b, const F& f) { return sub_fix(a, b, f.p); }
+template <class F>
+__device__ __forceinline__ uint32_t to_mont(uint32_t a, const F& f) { return mont_mul(a, f.r2, f); }
+template <class F>
+__device__ __forceinline__ uint32_t from_mont(uint32_t a, const F& f) { return mont_mul(a, 1u, f); }
 
 // base^e with base in Montgomery form; result in Montgomery form.
-__device__ __forceinline__ uint32_t mont_pow(uint32_t base, uint64_t e, const FieldParams& f) {
+template <class F>
+__device__ __forceinline__ uint32_t mont_pow(uint32_t base, uint64_t e, const F& f) {
     uint32_t r = f.one;
     while (e) {
         if (e & 1) r = mont_mul(r, base, f);
@@ -165,7 +204,8 @@ __device__ __forceinline__ uint32_t mont_pow(uint32_t base, uint64_t e, const Fi
     return r;
 }
 // Fermat inverse in Montgomery form; inverse(0) == 0 like element.rs:54-57.
-__device__ __forceinline__ uint32_t mont_inv(uint32_t a, const FieldParams& f) {
+template <class F>
+__device__ __forceinline__ uint32_t mont_inv(uint32_t a, const F& f) {
     return mont_pow(a, (uint64_t)f.p - 2, f);
 }
 
@@ -176,7 +216,8 @@ struct PowTable {
     uint32_t shift;
     uint32_t mask;
 };
-__device__ __forceinline__ uint32_t pow_lookup(const PowTable& t, uint32_t e, const FieldParams& f) {
+template <class F>
+__device__ __forceinline__ uint32_t pow_lookup(const PowTable& t, uint32_t e, const F& f) {
     return mont_mul(__ldg(t.lo + (e & t.mask)), __ldg(t.hi + (e >> t.shift)), f);
 }
 

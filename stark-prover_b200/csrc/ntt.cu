@@ -25,6 +25,12 @@ namespace starkb200 {
 constexpr int NTT_C = 32;
 constexpr int NTT_TS = NTT_C + 1;
 
+// The hot transform kernels are instantiated once more for the reference's own field (FieldRef, field.cuh), where the
+// modulus is an immediate and q = lo * p^-1 is a shift-add; every other modulus runs the same kernels on FieldParams.
+template <bool PREF> struct FieldOf { using type = FieldParams; __device__ static FieldParams make(const FieldParams& fp) { return fp; } };
+template <> struct FieldOf<true> { using type = FieldRef; __device__ static FieldRef make(const FieldParams&) { return FieldRef{}; } };
+static bool is_ref_field(const stark_ctx* ctx) { return ctx->fp.p == FieldRef::p; }
+
 struct NttPass {
     const uint32_t* src;
     uint32_t* dst;
@@ -48,22 +54,26 @@ struct NttPass {
 // on store.  A butterfly is 9 instructions: the product (IMAD, 2 IMAD.HI, IADD3 with carry-out, predicated IMAD) and
 // two IADD3-with-carry + predicated-IMAD pairs -- 3 on the ALU pipe, 6 on the FMA pipe (was 7 + 5 with compare + select
 // corrections, profiles/r02_ntt.md).
-__device__ __forceinline__ uint32_t ladd(uint32_t a_weak, uint32_t b, const FieldParams& f) { return add_wrap_fix(a_weak, b, f.p); }
-__device__ __forceinline__ uint32_t lsub(uint32_t a_weak, uint32_t b, const FieldParams& f) { return sub_fix(a_weak, b, f.p); }
-__device__ __forceinline__ uint32_t canonical(uint32_t x, const FieldParams& f) { return x >= f.p ? x - f.p : x; }
+template <class F>
+__device__ __forceinline__ uint32_t ladd(uint32_t a_weak, uint32_t b, const F& f) { return add_wrap_fix(a_weak, b, f.p); }
+template <class F>
+__device__ __forceinline__ uint32_t lsub(uint32_t a_weak, uint32_t b, const F& f) { return sub_fix(a_weak, b, f.p); }
+template <class F>
+__device__ __forceinline__ uint32_t canonical(uint32_t x, const F& f) { return x >= f.p ? x - f.p : x; }
 
 // In-tile twiddles travel as pairs {w, w * p^-1 mod 2^32} (mont_mul_tw): one 64-bit shared-memory load per distinct
 // twiddle of a register group instead of a load and a multiply.
-__device__ __forceinline__ void fill_tile_twiddles(uint2* tws, const uint32_t* small, unsigned small_log, int r_log, const FieldParams& fp) {
+template <class F>
+__device__ __forceinline__ void fill_tile_twiddles(uint2* tws, const uint32_t* small, unsigned small_log, int r_log, const F& fp) {
     for (int k = threadIdx.x; k < (1 << r_log) >> 1; k += blockDim.x) {
         const uint32_t w = small[(size_t)k << (small_log - r_log)];
         tws[k] = make_uint2(w, w * fp.pinv);
     }
 }
 
-template <int G, bool DIF, bool LAZY>
+template <int G, bool DIF, bool LAZY, class F>
 __device__ __forceinline__ void butterfly_group(uint32_t* col, const int s, const int base, const uint2* tws,
-                                                const int r_log, const FieldParams& fp) {
+                                                const int r_log, const F& fp) {
     uint32_t x[1 << G];
 #pragma unroll
     for (int j = 0; j < (1 << G); j++) x[j] = col[(base + (j << s)) * NTT_TS];
@@ -99,8 +109,8 @@ __device__ __forceinline__ void butterfly_group(uint32_t* col, const int s, cons
     for (int j = 0; j < (1 << G); j++) col[(base + (j << s)) * NTT_TS] = x[j];
 }
 
-template <int R_LOG, int G, bool DIF, bool LAZY>
-__device__ __forceinline__ void run_round(uint32_t* tile, const int s, const uint2* tws, const FieldParams& fp,
+template <int R_LOG, int G, bool DIF, bool LAZY, class F>
+__device__ __forceinline__ void run_round(uint32_t* tile, const int s, const uint2* tws, const F& fp,
                                           const unsigned ncols) {
     constexpr int items = ((1 << R_LOG) >> G) * NTT_C;
     for (int w = threadIdx.x; w < items; w += blockDim.x) {
@@ -112,8 +122,8 @@ __device__ __forceinline__ void run_round(uint32_t* tile, const int s, const uin
     __syncthreads();
 }
 
-template <int R_LOG, bool DIF, bool LAZY = false>
-__device__ __forceinline__ void run_rounds(uint32_t* tile, const uint2* tws, const FieldParams& fp, unsigned ncols) {
+template <int R_LOG, bool DIF, bool LAZY = false, class F = FieldParams>
+__device__ __forceinline__ void run_rounds(uint32_t* tile, const uint2* tws, const F& fp, unsigned ncols) {
     // stage groups (sum = R_LOG); DIT walks spans upward, DIF downward
     if constexpr (R_LOG <= 4) {
         run_round<R_LOG, R_LOG, DIF, LAZY>(tile, 0, tws, fp, ncols);
@@ -463,8 +473,9 @@ constexpr int ntt_min_blocks(int threads, int cap) {
 }
 constexpr int nat_min_blocks(int r_log) { return ntt_min_blocks(nat_threads(r_log), 16); }
 
-template <int R_LOG, bool FIRST, bool LAZY>
-__global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat_strided_kernel(NatPass ps, FieldParams fp) {
+template <int R_LOG, bool FIRST, bool LAZY, bool PREF>
+__global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat_strided_kernel(NatPass ps, FieldParams fp_arg) {
+    const typename FieldOf<PREF>::type fp = FieldOf<PREF>::make(fp_arg);
     extern __shared__ uint32_t smem[];
     constexpr int R = 1 << R_LOG;
     uint32_t* tile = smem;                    // [R][33], row rho holds digit value bitrev(rho) until the rounds have run
@@ -544,8 +555,9 @@ __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat
     }
 }
 
-template <int R_LOG>
-__global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat_last_kernel(NatPass ps, FieldParams fp) {
+template <int R_LOG, bool PREF>
+__global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat_last_kernel(NatPass ps, FieldParams fp_arg) {
+    const typename FieldOf<PREF>::type fp = FieldOf<PREF>::make(fp_arg);
     extern __shared__ uint32_t smem[];
     constexpr int R = 1 << R_LOG;
     uint32_t* tile = smem;                    // [R rows = n_m][33: column j = k1 - k1_0]
@@ -636,8 +648,9 @@ static void launch_nat_strided(stark_ctx* ctx, const NatPass& ps, size_t tiles) 
         if (smem > 48 * 1024) STARK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)tiles, threads, smem, ctx->stream>>>(ps, ctx->fp);
     };
-    if (ctx->fp.p >> 31) launch(nat_strided_kernel<R_LOG, FIRST, true>);     // weak butterfly values need 2^32 < 2p
-    else launch(nat_strided_kernel<R_LOG, FIRST, false>);
+    if (is_ref_field(ctx)) launch(nat_strided_kernel<R_LOG, FIRST, true, true>);
+    else if (ctx->fp.p >> 31) launch(nat_strided_kernel<R_LOG, FIRST, true, false>);     // weak butterfly values need 2^32 < 2p
+    else launch(nat_strided_kernel<R_LOG, FIRST, false, false>);
     ctx->launches++;
 }
 template <int R_LOG>
@@ -645,7 +658,7 @@ static void launch_nat_last(stark_ctx* ctx, const NatPass& ps, size_t tiles) {
     constexpr int R = 1 << R_LOG;
     const int threads = nat_threads(R_LOG);
     size_t smem = (size_t)(R * NTT_TS + R + 2 * NTT_C) * sizeof(uint32_t);
-    auto kern = nat_last_kernel<R_LOG>;
+    auto kern = is_ref_field(ctx) ? nat_last_kernel<R_LOG, true> : nat_last_kernel<R_LOG, false>;
     if (smem > 48 * 1024) STARK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)tiles, threads, smem, ctx->stream>>>(ps, ctx->fp);
     ctx->launches++;
@@ -791,8 +804,9 @@ constexpr int lde8_threads(int r_log) {
     return t < 64 ? 64 : (t > 1024 ? 1024 : t);
 }
 
-template <int R_LOG, bool FIRST, bool LAZY>
-__global__ void __launch_bounds__(lde8_threads(R_LOG), ntt_min_blocks(lde8_threads(R_LOG), 24)) lde8_pass_kernel(Lde8Pass ps, FieldParams fp) {
+template <int R_LOG, bool FIRST, bool LAZY, bool PREF>
+__global__ void __launch_bounds__(lde8_threads(R_LOG), ntt_min_blocks(lde8_threads(R_LOG), 24)) lde8_pass_kernel(Lde8Pass ps, FieldParams fp_arg) {
+    const typename FieldOf<PREF>::type fp = FieldOf<PREF>::make(fp_arg);
     extern __shared__ uint32_t smem[];
     constexpr int R = 1 << R_LOG;
     uint32_t* tile = smem;                    // [R][33]: word g*8+s of row t
@@ -889,12 +903,12 @@ __global__ void __launch_bounds__(lde8_threads(R_LOG), ntt_min_blocks(lde8_threa
     }
 }
 
-template <int R_LOG, bool FIRST, bool LAZY>
+template <int R_LOG, bool FIRST, bool LAZY, bool PREF>
 static void launch_lde8_impl(stark_ctx* ctx, const Lde8Pass& ps, size_t tiles) {
     constexpr int R = 1 << R_LOG;
     const int threads = lde8_threads(R_LOG);
     size_t smem = (size_t)(R * NTT_TS + R + 2) * sizeof(uint32_t);
-    auto kern = lde8_pass_kernel<R_LOG, FIRST, LAZY>;
+    auto kern = lde8_pass_kernel<R_LOG, FIRST, LAZY, PREF>;
     if (smem > 48 * 1024) STARK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)tiles, threads, smem, ctx->stream>>>(ps, ctx->fp);
     ctx->launches++;
@@ -902,8 +916,9 @@ static void launch_lde8_impl(stark_ctx* ctx, const Lde8Pass& ps, size_t tiles) {
 // weak (lazily reduced) butterfly values need 2^32 < 2p; smaller primes (BabyBear, 998244353, ...) take the strict form
 template <int R_LOG, bool FIRST>
 static void launch_lde8(stark_ctx* ctx, const Lde8Pass& ps, size_t tiles) {
-    if (ctx->fp.p >> 31) launch_lde8_impl<R_LOG, FIRST, true>(ctx, ps, tiles);
-    else launch_lde8_impl<R_LOG, FIRST, false>(ctx, ps, tiles);
+    if (is_ref_field(ctx)) launch_lde8_impl<R_LOG, FIRST, true, true>(ctx, ps, tiles);
+    else if (ctx->fp.p >> 31) launch_lde8_impl<R_LOG, FIRST, true, false>(ctx, ps, tiles);
+    else launch_lde8_impl<R_LOG, FIRST, false, false>(ctx, ps, tiles);
 }
 template <bool FIRST>
 static void dispatch_lde8(stark_ctx* ctx, unsigned r, const Lde8Pass& ps, size_t tiles) {
