@@ -817,7 +817,7 @@ __global__ void __launch_bounds__(lde8_threads(R_LOG), ntt_min_blocks(lde8_threa
     size_t row_base;          // FIRST: first row of the tile; else row of (t = 0, g = 0)
     uint32_t low0 = 0;
     if (FIRST) {
-        row_base = tile_id * 4 * (size_t)R;
+        row_base = tile_id * (size_t)R;          // rows row_base + t + (g << (log_rows - 2))
     } else {
         const size_t tiles_per_high = ((size_t)1 << ps.lo) / 4;
         const size_t high = tile_id / tiles_per_high;
@@ -856,32 +856,43 @@ __global__ void __launch_bounds__(lde8_threads(R_LOG), ntt_min_blocks(lde8_threa
         }
         }
     }
-    for (int i = threadIdx.x; FIRST && i < 4 * R; i += blockDim.x) {
-        uint32_t v[8];
-        int t, g;
-        if (FIRST) {
-            g = i >> R_LOG; t = i & (R - 1);
-            const uint32_t q = (uint32_t)(row_base + i);                    // row index = position in bit-reversed coefficient order
-            const uint32_t j = bitrev_bits(q, ps.log_rows);                 // the coefficient it holds
-            const uint32_t si = ps.src_bitrev ? q : j;
-            uint32_t c = si < ps.src_len ? ps.src[si] : 0u;
-            const uint32_t b = pow_lookup(ps.shift, j, fp), bp = b * fp.pinv;   // w_N^j
-            v[0] = mont_mul(c, pow_lookup(ps.scale, j, fp), fp);            // c_j g^j
+    // FIRST: the tile holds all 2^r values of the lowest row digit t for four values g of the TOP two row bits, i.e. rows
+    // q = t | tile << r | g << (log_rows - 2).  Row q holds coefficient bitrev(q), so the four rows of one t are four
+    // ADJACENT coefficients (one aligned 16-byte load of natural-order input; the 32-byte sectors of the gather are used
+    // in full by two neighbouring tiles instead of one word in eight), and their scale / shift factors are one table
+    // look-up each plus a walk.  The rows of one g are 2^r consecutive rows of the output: stores stay contiguous.
+    if (FIRST) {
+        const unsigned top = ps.log_rows - 2, mid_bits = top - R_LOG;
+        const uint32_t jmid = bitrev_bits((uint32_t)tile_id, mid_bits) << 2;
+        const bool vec = !ps.src_bitrev && (reinterpret_cast<uintptr_t>(ps.src) & 15) == 0;
+        for (int t = threadIdx.x; t < R; t += blockDim.x) {
+            const uint32_t j0 = (bitrev_bits((uint32_t)t, R_LOG) << (ps.log_rows - R_LOG)) | jmid;     // coefficients j0 .. j0 + 3
+            const uint32_t q0 = (uint32_t)t | ((uint32_t)tile_id << R_LOG);
+            uint32_t c[4];
+            if (vec && j0 + 3 < ps.src_len) {
+                const uint4 x = *reinterpret_cast<const uint4*>(ps.src + j0);
+                c[0] = x.x; c[1] = x.y; c[2] = x.z; c[3] = x.w;
+            } else {
 #pragma unroll
-            for (int k = 1; k < 8; k++) v[k] = mont_mul_tw(v[k - 1], b, bp, fp);    // ... * w_N^(j s)
-        } else {
-            g = i & 3; t = i >> 2;
-            const size_t row = row_base + ((size_t)t << ps.lo) + g;
-            const uint4* p = reinterpret_cast<const uint4*>(ps.dst + row * 8);
-            uint4 a = p[0], bq = p[1];
-            const uint32_t e = bitrev_bits((uint32_t)t, R_LOG) * (low0 + (uint32_t)g);
-            const uint32_t tw = pow_lookup(ps.tw, e << tw_shift, fp);
-            v[0] = mont_mul(a.x, tw, fp); v[1] = mont_mul(a.y, tw, fp); v[2] = mont_mul(a.z, tw, fp); v[3] = mont_mul(a.w, tw, fp);
-            v[4] = mont_mul(bq.x, tw, fp); v[5] = mont_mul(bq.y, tw, fp); v[6] = mont_mul(bq.z, tw, fp); v[7] = mont_mul(bq.w, tw, fp);
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t si = ps.src_bitrev ? (q0 | (bitrev_bits((uint32_t)k, 2) << top)) : j0 + k;
+                    c[k] = si < ps.src_len ? ps.src[si] : 0u;
+                }
+            }
+            uint32_t sc = pow_lookup(ps.scale, j0, fp), b = pow_lookup(ps.shift, j0, fp);      // c0 g^j0, w_N^j0
+            const uint32_t sc_step = __ldg(ps.scale.lo + 1), b_step = __ldg(ps.shift.lo + 1);  // g, w_N
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int g = (int)bitrev_bits((uint32_t)k, 2);
+                const uint32_t bp = b * fp.pinv;
+                uint32_t v = mont_mul(c[k], sc, fp);                                           // c_j g^j
+                uint32_t* o = tile + t * NTT_TS + g * 8;
+                o[0] = v;
+#pragma unroll
+                for (int e = 1; e < 8; e++) { v = mont_mul_tw(v, b, bp, fp); o[e] = v; }       // ... * w_N^(j s)
+                if (k < 3) { sc = mont_mul(sc, sc_step, fp); b = mont_mul(b, b_step, fp); }
+            }
         }
-        uint32_t* o = tile + t * NTT_TS + g * 8;
-#pragma unroll
-        for (int k = 0; k < 8; k++) o[k] = v[k];
     }
     __syncthreads();
 
@@ -891,7 +902,7 @@ __global__ void __launch_bounds__(lde8_threads(R_LOG), ntt_min_blocks(lde8_threa
     for (int i = threadIdx.x; i < 4 * R; i += blockDim.x) {
         int t, g;
         size_t row;
-        if (FIRST) { g = i >> R_LOG; t = i & (R - 1); row = row_base + i; }
+        if (FIRST) { g = i >> R_LOG; t = i & (R - 1); row = row_base + t + ((size_t)g << (ps.log_rows - 2)); }
         else { g = i & 3; t = i >> 2; row = row_base + ((size_t)t << ps.lo) + g; }
         const uint32_t* o = tile + t * NTT_TS + g * 8;
         uint32_t v[8];
