@@ -745,13 +745,7 @@ extern "C" int stark_fri_fold(stark_fri* f, uint64_t beta, uint8_t root[32]) {
                                    "MerkleTree::root() would panic (fri_commit.rs:97-100, merkle/mod.rs:25)");
     const uint64_t p = ctx->modulus;
     const size_t n = (size_t)1 << f->cur_log, half = n >> 1;
-    // coefficient space: exact degree of even + beta*odd (fri_commit.rs:32-50)
-    if (f->coeff_len > 0) {
-        size_t out_len = (f->coeff_len + 1) / 2;
-        DevBufPtr nc = make_buf(out_len * 4, ctx->stream);
-        coeff_fold(ctx, f->coeffs->as<uint32_t>(), f->coeff_len, ctx->to_mont(beta), nc->as<uint32_t>(), ctx->d_result);
-        f->coeffs = nc;
-    }
+    DevBufPtr old_coeffs;
     // evaluation space fused with the next tree (fri_commit.rs:53-65, :97)
     const stark_tree* prev = f->trees.back().get();
     DevBufPtr ev = make_buf(half * 4, ctx->stream);
@@ -761,6 +755,15 @@ extern "C" int stark_fri_fold(stark_fri* f, uint64_t beta, uint8_t root[32]) {
     src.inv2_m = ctx->to_mont(inv2);
     src.sb_m = ctx->to_mont(h_mul(h_mul(beta % p, inv2, p), h_inv(f->cur_offset, p), p));
     src.winv = ctx->twiddles(f->cur_log).inv();
+    // coefficient space: exact degree of even + beta*odd (fri_commit.rs:32-50) -- a few CTAs of the tree's first launch
+    if (f->coeff_len > 0) {
+        size_t out_len = (f->coeff_len + 1) / 2;
+        DevBufPtr nc = make_buf(out_len * 4, ctx->stream);
+        coeff_fold_job(ctx, f->coeffs->as<uint32_t>(), f->coeff_len, ctx->to_mont(beta), nc->as<uint32_t>(), ctx->d_result,
+                       merkle_first_launch_threads(half), src.job);
+        old_coeffs = f->coeffs;              // read by the launch below: its stream-ordered release must come after it
+        f->coeffs = nc;
+    }
     auto t = tree_launch(ctx, ev, half, src);
     STARK_CUDA(cudaStreamSynchronize(ctx->stream));
     tree_take_root(t.get());

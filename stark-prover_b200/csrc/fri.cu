@@ -61,6 +61,7 @@ void fill_zero(stark_ctx* ctx, uint32_t* p, size_t n) {
 }
 
 // ---------------- coefficient-space fold + exact degree ----------------
+DegScratch* deg_scratch(stark_ctx* ctx);
 // {running max, ticket}: lives in the context (zeroed once); the last block of every launch resets it
 
 template <bool FOLD>
@@ -102,7 +103,7 @@ __global__ void coeff_fold_kernel(const uint32_t* c, size_t len, uint32_t beta_m
         }
     }
 }
-static DegScratch* deg_scratch(stark_ctx* ctx) {
+DegScratch* deg_scratch(stark_ctx* ctx) {
     if (!ctx->deg_scratch.p) {
         ctx->deg_scratch = DevBuf(sizeof(DegScratch), ctx->stream);
         STARK_CUDA(cudaMemsetAsync(ctx->deg_scratch.p, 0, sizeof(DegScratch), ctx->stream));
@@ -116,6 +117,14 @@ void coeff_fold(stark_ctx* ctx, const uint32_t* c, size_t len, uint32_t beta_m, 
     coeff_fold_kernel<true><<<(unsigned)((out_len + 255) / 256), 256, 0, ctx->stream>>>(c, len, beta_m, out, out_len, result, deg_scratch(ctx), ctx->fp);
     ctx->launches++;
     STARK_CUDA(cudaGetLastError());
+}
+void coeff_fold_job(stark_ctx* ctx, const uint32_t* c, size_t len, uint32_t beta_m, uint32_t* out, HostResult* result, unsigned cta_threads, CoeffJob& job) {
+    const size_t out_len = (len + 1) / 2;
+    STARK_REQUIRE(out_len >= 1 && len <= 0x7fffffffu, "coeff_fold: empty or oversized polynomial");
+    job.c = c; job.out = out; job.len = (uint32_t)len; job.out_len = (uint32_t)out_len; job.beta_m = beta_m;
+    const size_t want = (out_len + cta_threads - 1) / cta_threads;
+    job.ctas = (unsigned)(want < COEFF_JOB_MAX_CTAS ? want : COEFF_JOB_MAX_CTAS);
+    job.result = result; job.scratch = deg_scratch(ctx);
 }
 void poly_degree(stark_ctx* ctx, const uint32_t* c, size_t len, HostResult* result) {
     KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 8.0 * len);

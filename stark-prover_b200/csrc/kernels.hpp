@@ -14,6 +14,21 @@ struct TreeShape {
     static TreeShape make(size_t n);
 };
 
+// Coefficient-space fold of a FRI layer (fri_commit.rs:32-50: even + beta * odd, with the exact degree the loop condition
+// at :89 needs) riding in the FIRST launch of that layer's tree: the lowest `ctas` block indices of the launch run it, the
+// rest hash.  It is a few microseconds of memory work beside an ALU-bound launch; as a launch of its own it cost ~6 us of
+// launch latency per layer (21 of them per proof).
+struct CoeffJob {
+    const uint32_t* c = nullptr;       // len coefficients
+    uint32_t* out = nullptr;           // out_len = (len + 1) / 2 folded coefficients
+    uint32_t len = 0, out_len = 0;
+    uint32_t beta_m = 0;               // beta, Montgomery form
+    unsigned ctas = 0;                 // 0 = no job
+    HostResult* result = nullptr;      // degree + 1 of the folded polynomial lands in result->degree_plus1
+    DegScratch* scratch = nullptr;
+};
+constexpr unsigned COEFF_JOB_MAX_CTAS = 296;
+
 // Source of the leaf VALUES of a tree: either an existing layer, or the FRI fold of the previous layer
 // computed on the fly (and written to `fold_out`) — the fused fold-and-hash of fri_commit.rs:94-97.
 struct LeafSource {
@@ -25,7 +40,12 @@ struct LeafSource {
     uint32_t inv2_m = 0;               // 1/2, Montgomery form
     uint32_t sb_m = 0;                 // beta/(2*offset), Montgomery form
     PowTable winv{};                   // w^-i for this layer's size
+    CoeffJob job{};                    // fold launches only
 };
+// threads per CTA of the first launch merkle_build makes for a tree of n leaves (what a CoeffJob CTA will have)
+unsigned merkle_first_launch_threads(size_t n);
+// fills src.job (fri.cu): c -> out with beta, degree to `result`
+void coeff_fold_job(stark_ctx* ctx, const uint32_t* c, size_t len, uint32_t beta_m, uint32_t* out, HostResult* result, unsigned cta_threads, CoeffJob& job);
 
 // Builds levels 1..depth into `nodes` (TreeShape layout); when `result` is non-null the root's 8 state
 // words are also written there (mapped host memory).  Leaf digests are not stored.

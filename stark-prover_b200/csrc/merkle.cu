@@ -16,6 +16,7 @@
 // previous layer (fused fold-and-hash, reference src/fri/fri_commit.rs:94-97).
 #include "kernels.hpp"
 #include "sha256.cuh"
+#include "coeff_job.cuh"
 
 namespace starkb200 {
 
@@ -85,7 +86,12 @@ template <int SRC>
 __global__ void __launch_bounds__(MERKLE_THREADS, STARK_MERKLE_MIN_BLOCKS)
 merkle_subtree_kernel(LeafSource src, const uint32_t* in_digests, size_t n, int nlev, LevelPtrs lv, FieldParams fp,
                       HostResult* result, int last) {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned bid = blockIdx.x;
+    if (SRC == SRC_FOLD && src.job.ctas) {              // the layer's coefficient-space fold rides in the lowest block indices
+        if (bid < src.job.ctas) { coeff_job_run(src.job, bid, fp); return; }
+        bid -= src.job.ctas;
+    }
+    const size_t t = (size_t)bid * blockDim.x + threadIdx.x;
     const size_t base = t << SUB;
     if (base >= n) return;
     const int cnt = (n - base) < (size_t)(1 << SUB) ? (int)(n - base) : (1 << SUB);
@@ -217,10 +223,15 @@ __global__ void __launch_bounds__(TAIL_THREADS) merkle_tail_kernel(TailArgs a) {
     __shared__ __align__(8) uint32_t sm[2][8][TAIL_THREADS + 2];
     __shared__ int s_last;
     const int t = threadIdx.x;
+    unsigned bid = blockIdx.x, nblk = gridDim.x;
+    if (SRC == SRC_FOLD && a.src.job.ctas) {     // the layer's coefficient-space fold rides in the lowest block indices
+        if (bid < a.src.job.ctas) { coeff_job_run(a.src.job, bid, a.fp); return; }
+        bid -= a.src.job.ctas; nblk -= a.src.job.ctas;
+    }
     int len = a.n_items;                         // length of the level being consumed
     uint32_t* out = a.out;                       // storage of the level being produced
     if (len == 1) {                              // one-leaf tree: the root is the leaf digest (slot 0)
-        if (blockIdx.x == 0 && t == 0) {
+        if (bid == 0 && t == 0) {
             Digest d;
             if (SRC == SRC_DIGESTS) d = load_digest_cg(a.in_digests);
             else sha256_leaf32(SRC == SRC_FOLD ? fold_at(a.src, 0, a.fp) : a.src.vals[0], d);
@@ -229,7 +240,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) merkle_tail_kernel(TailArgs a) {
         }
         return;
     }
-    int base = blockIdx.x * 2 * TAIL_THREADS;    // the CTA's window of that level: `width` nodes from `base`
+    int base = (int)bid * 2 * TAIL_THREADS;      // the CTA's window of that level: `width` nodes from `base`
     int width = 2 * TAIL_THREADS;
     int buf = 0;                                 // sm[buf] holds the window (except for the first level)
     bool first = true;
@@ -275,7 +286,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) merkle_tail_kernel(TailArgs a) {
             if (t == 0) {
                 __threadfence();                                       // this CTA's chunk root is visible before the ticket
                 unsigned tk = atomicAdd(a.ticket, 1u);
-                s_last = tk == gridDim.x - 1;
+                s_last = tk == nblk - 1;
                 if (s_last) { *a.ticket = 0; __threadfence(); }        // every chunk root is in L2; re-arm for the next launch
             }
             __syncthreads();
@@ -315,9 +326,12 @@ static void launch_tail(stark_ctx* ctx, const LeafSource& src, const uint32_t* i
     int ctas = (int)((n_items + 2 * TAIL_THREADS - 1) / (2 * TAIL_THREADS));
     if (ctas < 1) ctas = 1;
     TailArgs a{src, in_digests, (int)n_items, out, ctx->tail_counter.as<unsigned>(), result, ctx->fp};
+    if (SRC == SRC_FOLD) ctas += (int)src.job.ctas;
     merkle_tail_kernel<SRC><<<ctas, TAIL_THREADS, 0, ctx->stream>>>(a);
     ctx->launches++;
 }
+
+unsigned merkle_first_launch_threads(size_t n) { return n <= (size_t)TAIL_MAX ? TAIL_THREADS : MERKLE_THREADS; }
 
 void merkle_build(stark_ctx* ctx, const LeafSource& src, const TreeShape& shape, uint32_t* nodes, HostResult* result) {
     const size_t n = shape.n;
@@ -341,7 +355,7 @@ void merkle_build(stark_ctx* ctx, const LeafSource& src, const TreeShape& shape,
         size_t threads = (n + (1 << SUB) - 1) >> SUB;
         unsigned blocks = (unsigned)((threads + MERKLE_THREADS - 1) / MERKLE_THREADS);
         KernelTimer kt(ctx, stark_ctx::CAT_MERKLE_LEAF, 1384.0 * ((double)n + comp_levels(1, SUB)));
-        if (fold) merkle_subtree_kernel<SRC_FOLD><<<blocks, MERKLE_THREADS, 0, ctx->stream>>>(src, nullptr, n, SUB, lv, ctx->fp, result, 0);
+        if (fold) merkle_subtree_kernel<SRC_FOLD><<<blocks + src.job.ctas, MERKLE_THREADS, 0, ctx->stream>>>(src, nullptr, n, SUB, lv, ctx->fp, result, 0);
         else merkle_subtree_kernel<SRC_VALUES><<<blocks, MERKLE_THREADS, 0, ctx->stream>>>(src, nullptr, n, SUB, lv, ctx->fp, result, 0);
         ctx->launches++;
         cur = SUB;
