@@ -46,23 +46,6 @@ static_assert((((uint64_t)1 << 32) % FieldRef::p) == FieldRef::one && ((uint64_t
 #endif
 static __constant__ uint32_t c_field_one = 1;
 static __constant__ uint32_t c_field_zero = 0;
-// hi32(a * b).  With the carry forms on, the product is written as a multiply-add with an addend the compiler cannot see
-// through: ptxas otherwise folds the subtraction that follows into the multiply (IMAD.HI Rd, P0, a, b, {0, -h}), which
-// costs a negate, a register-pair move and a zeroing per product and takes its carry from hi + (2^32 - h) -- no carry for
-// h == 0, where a subtraction has one.
-#ifndef STARK_MULHI_PLAIN
-#define STARK_MULHI_PLAIN 0
-#endif
-__device__ __forceinline__ uint32_t mulhi_nofuse(uint32_t a, uint32_t b) {
-#if STARK_FIELD_CARRY && !STARK_MULHI_PLAIN
-    uint32_t hi;
-    const uint32_t zero = c_field_zero;
-    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(hi) : "r"(a), "r"(b), "r"(zero));
-    return hi;
-#else
-    return __umulhi(a, b);
-#endif
-}
 // d = a - b, plus p when a < b.  Any u32 a, b: the result is congruent to a - b; canonical when both are.
 template <bool ON_FMA = ((STARK_CORR_FMA & 4) != 0)>
 __device__ __forceinline__ uint32_t sub_fix(uint32_t a, uint32_t b, uint32_t p) {
@@ -140,32 +123,24 @@ __device__ __forceinline__ uint32_t mont_mul(uint32_t a, uint32_t b, const F& f)
     uint32_t r = hi - h;
     return hi < h ? r + f.p : r;
 }
-// The same product when the second factor is a table constant stored with wp = w * p^-1 mod 2^32 next to it (the
-// transform twiddles): q = x * wp is one multiply, so the product is IMAD + 2 IMAD.HI + the correction.
-#ifndef STARK_MONT_TW_WIDE
-#define STARK_MONT_TW_WIDE 1
-#endif
+// The product of the transform butterflies (second factor = a twiddle in Montgomery form), with the carry-predicated
+// correction.  x * w is formed as ONE 64-bit multiply whose low word feeds q: ptxas cannot fold the subtraction below into
+// a multiply whose own low half it depends on (with separate mul.lo / mul.hi it folds `hi - h` into IMAD.HI with a
+// negated register-pair addend -- a negate, a pair move and a zeroing per product, and a carry that is wrong for h == 0;
+// round 2 first avoided that with an opaque addend and a second table word w * p^-1, which cost ~1.4 register moves per
+// product on the FMA-heavy pipe, the pipe that bounds these kernels: profiles/r02_ubench_pipes.txt, r02_ntt.md).
 template <class F>
-__device__ __forceinline__ uint32_t mont_mul_tw(uint32_t x, uint32_t w, uint32_t wp, const F& f) {
-#if STARK_MONT_TW_WIDE
-    // x * w as ONE 64-bit product whose low word feeds q: the subtraction below cannot be folded into a multiply whose
-    // own low half it depends on, so no opaque addend (and none of the register-pair moves it cost) is needed
-    (void)wp;
+__device__ __forceinline__ uint32_t mont_mul_tw(uint32_t x, uint32_t w, const F& f) {
     const uint64_t t = (uint64_t)x * w;
-    uint32_t qw;
+    uint32_t q;
     if constexpr (F::is_ref) {
-        // p = 3 * 2^30 + 1: p^-1 = 2^30 + 1 mod 2^32, so q = lo + (lo << 30) -- one shift-add on the ALU pipe instead of a
-        // multiply on the FMA pipe (written in PTX: the front end turns the C shift-add back into a multiply by the constant)
-        asm("{ .reg .u32 s; shl.b32 s, %1, 30; add.u32 %0, s, %1; }" : "=r"(qw) : "r"((uint32_t)t));
+        // p = 3 * 2^30 + 1: p^-1 = 2^30 + 1 mod 2^32, q = lo + (lo << 30) (ptxas picks a shift-add or a multiply by the
+        // immediate as its pipe balance sees fit)
+        asm("{ .reg .u32 s; shl.b32 s, %1, 30; add.u32 %0, s, %1; }" : "=r"(q) : "r"((uint32_t)t));
     } else {
-        qw = (uint32_t)t * f.pinv;
+        q = (uint32_t)t * f.pinv;
     }
-    return sub_fix<(STARK_CORR_FMA & 1) != 0>((uint32_t)(t >> 32), __umulhi(qw, f.p), f.p);
-#endif
-    uint32_t q = x * wp;
-    uint32_t hi = mulhi_nofuse(x, w);
-    uint32_t h = __umulhi(q, f.p);
-    return sub_fix<(STARK_CORR_FMA & 1) != 0>(hi, h, f.p);
+    return sub_fix<(STARK_CORR_FMA & 1) != 0>((uint32_t)(t >> 32), __umulhi(q, f.p), f.p);
 }
 // canonical a, b -> canonical a + b:  a + (b - p) carries out of 32 bits exactly when a + b >= p
 template <class F>

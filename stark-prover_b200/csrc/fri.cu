@@ -64,32 +64,15 @@ void fill_zero(stark_ctx* ctx, uint32_t* p, size_t n) {
 DegScratch* deg_scratch(stark_ctx* ctx);
 // {running max, ticket}: lives in the context (zeroed once); the last block of every launch resets it
 
-template <bool FOLD>
-__global__ void coeff_fold_kernel(const uint32_t* c, size_t len, uint32_t beta_m, uint32_t* out, size_t out_len,
-                                  HostResult* result, DegScratch* scratch, FieldParams fp) {
+// exact degree of a coefficient vector (ops.rs:19-37: trailing zeros trimmed): block max -> atomic max -> last block publishes
+__global__ void poly_degree_kernel(const uint32_t* c, size_t len, HostResult* result, DegScratch* scratch) {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int mine = 0;
-    if (j < out_len) {
-        uint32_t v;
-        if (FOLD) {
-            uint32_t e = c[2 * j];
-            uint32_t o = (2 * j + 1 < len) ? mont_mul(c[2 * j + 1], beta_m, fp) : 0u;
-            v = fadd(o, e, fp);
-            out[j] = v;
-        } else {
-            v = c[j];
-        }
-        if (v != 0) mine = (int)(j + 1);
-    }
-    // block max -> global max -> last block publishes
+    int mine = (j < len && c[j] != 0) ? (int)(j + 1) : 0;
     __shared__ int smax;
     if (threadIdx.x == 0) smax = 0;
     __syncthreads();
-    mine = max(mine, __shfl_xor_sync(0xffffffffu, mine, 16));
-    mine = max(mine, __shfl_xor_sync(0xffffffffu, mine, 8));
-    mine = max(mine, __shfl_xor_sync(0xffffffffu, mine, 4));
-    mine = max(mine, __shfl_xor_sync(0xffffffffu, mine, 2));
-    mine = max(mine, __shfl_xor_sync(0xffffffffu, mine, 1));
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) mine = max(mine, __shfl_xor_sync(0xffffffffu, mine, d));
     if ((threadIdx.x & 31) == 0 && mine) atomicMax(&smax, mine);
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -110,14 +93,6 @@ DegScratch* deg_scratch(stark_ctx* ctx) {
     }
     return ctx->deg_scratch.as<DegScratch>();
 }
-void coeff_fold(stark_ctx* ctx, const uint32_t* c, size_t len, uint32_t beta_m, uint32_t* out, HostResult* result) {
-    KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 12.0 * len);
-    size_t out_len = (len + 1) / 2;
-    if (out_len == 0) { throw StarkError(ST_INTERNAL, "coeff_fold: empty polynomial"); }
-    coeff_fold_kernel<true><<<(unsigned)((out_len + 255) / 256), 256, 0, ctx->stream>>>(c, len, beta_m, out, out_len, result, deg_scratch(ctx), ctx->fp);
-    ctx->launches++;
-    STARK_CUDA(cudaGetLastError());
-}
 void coeff_fold_job(stark_ctx* ctx, const uint32_t* c, size_t len, uint32_t beta_m, uint32_t* out, HostResult* result, unsigned cta_threads, CoeffJob& job) {
     const size_t out_len = (len + 1) / 2;
     STARK_REQUIRE(out_len >= 1 && len <= 0x7fffffffu, "coeff_fold: empty or oversized polynomial");
@@ -129,7 +104,7 @@ void coeff_fold_job(stark_ctx* ctx, const uint32_t* c, size_t len, uint32_t beta
 void poly_degree(stark_ctx* ctx, const uint32_t* c, size_t len, HostResult* result) {
     KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 8.0 * len);
     STARK_REQUIRE(len > 0, "poly_degree: empty");
-    coeff_fold_kernel<false><<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>(c, len, 0, nullptr, len, result, deg_scratch(ctx), ctx->fp);
+    poly_degree_kernel<<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>(c, len, result, deg_scratch(ctx));
     ctx->launches++;
     STARK_CUDA(cudaGetLastError());
 }

@@ -126,7 +126,6 @@ void narrow_u64(stark_ctx* ctx, const uint64_t* in, uint32_t* out, size_t n);   
 void widen_u32(stark_ctx* ctx, const uint32_t* in, uint64_t* out, size_t n);
 void fill_zero(stark_ctx* ctx, uint32_t* p, size_t n);
 // c'[j] = c[2j] + beta*c[2j+1]; result->degree_plus1 = 1 + max{j : c'[j] != 0} (0 for the zero poly)
-void coeff_fold(stark_ctx* ctx, const uint32_t* c, size_t len, uint32_t beta_m, uint32_t* out, HostResult* result);
 void poly_degree(stark_ctx* ctx, const uint32_t* c, size_t len, HostResult* result);
 // a[i] <- a[i]^-1 (0 stays 0); if num != null: out[i] = num[i] * a[i]^-1
 void batch_inverse(stark_ctx* ctx, const uint32_t* a, const uint32_t* num, uint32_t* out, size_t n);

@@ -61,18 +61,14 @@ __device__ __forceinline__ uint32_t lsub(uint32_t a_weak, uint32_t b, const F& f
 template <class F>
 __device__ __forceinline__ uint32_t canonical(uint32_t x, const F& f) { return x >= f.p ? x - f.p : x; }
 
-// In-tile twiddles travel as pairs {w, w * p^-1 mod 2^32} (mont_mul_tw): one 64-bit shared-memory load per distinct
-// twiddle of a register group instead of a load and a multiply.
-template <class F>
-__device__ __forceinline__ void fill_tile_twiddles(uint2* tws, const uint32_t* small, unsigned small_log, int r_log, const F& fp) {
-    for (int k = threadIdx.x; k < (1 << r_log) >> 1; k += blockDim.x) {
-        const uint32_t w = small[(size_t)k << (small_log - r_log)];
-        tws[k] = make_uint2(w, w * fp.pinv);
-    }
+// In-tile twiddles w_R^k, k < R/2 (Montgomery form), in shared memory: a warp's lanes are columns of one butterfly, so
+// every twiddle load of a register group is a broadcast.
+__device__ __forceinline__ void fill_tile_twiddles(uint32_t* tws, const uint32_t* small, unsigned small_log, int r_log) {
+    for (int k = threadIdx.x; k < (1 << r_log) >> 1; k += blockDim.x) tws[k] = small[(size_t)k << (small_log - r_log)];
 }
 
 template <int G, bool DIF, bool LAZY, class F>
-__device__ __forceinline__ void butterfly_group(uint32_t* col, const int s, const int base, const uint2* tws,
+__device__ __forceinline__ void butterfly_group(uint32_t* col, const int s, const int base, const uint32_t* tws,
                                                 const int r_log, const F& fp) {
     uint32_t x[1 << G];
 #pragma unroll
@@ -87,19 +83,19 @@ __device__ __forceinline__ void butterfly_group(uint32_t* col, const int s, cons
             if (jj & (1 << u)) continue;
             const int k = bl + ((jj & ((1 << u) - 1)) << s);
             const bool unit = (s == 0 && u == 0);    // w_2^0 = 1: no multiplication in the span-1 stage
-            const uint2 w = unit ? make_uint2(0u, 0u) : tws[k << (r_log - level)];
+            const uint32_t w = unit ? 0u : tws[k << (r_log - level)];
             if (DIF) {
                 uint32_t a = x[jj], b = x[jj + (1 << u)];
                 x[jj] = fadd(a, b, fp);
                 uint32_t d = fsub(a, b, fp);
-                x[jj + (1 << u)] = unit ? d : mont_mul_tw(d, w.x, w.y, fp);
+                x[jj + (1 << u)] = unit ? d : mont_mul_tw(d, w, fp);
             } else if (LAZY) {
                 // (the span-1 stage is the first of a pass: its inputs come straight from a product, so `b` is canonical)
-                uint32_t a = x[jj], b = unit ? x[jj + (1 << u)] : mont_mul_tw(x[jj + (1 << u)], w.x, w.y, fp);
+                uint32_t a = x[jj], b = unit ? x[jj + (1 << u)] : mont_mul_tw(x[jj + (1 << u)], w, fp);
                 x[jj] = ladd(a, b, fp);
                 x[jj + (1 << u)] = lsub(a, b, fp);
             } else {
-                uint32_t a = x[jj], b = unit ? x[jj + (1 << u)] : mont_mul_tw(x[jj + (1 << u)], w.x, w.y, fp);
+                uint32_t a = x[jj], b = unit ? x[jj + (1 << u)] : mont_mul_tw(x[jj + (1 << u)], w, fp);
                 x[jj] = fadd(a, b, fp);
                 x[jj + (1 << u)] = fsub(a, b, fp);
             }
@@ -110,7 +106,7 @@ __device__ __forceinline__ void butterfly_group(uint32_t* col, const int s, cons
 }
 
 template <int R_LOG, int G, bool DIF, bool LAZY, class F>
-__device__ __forceinline__ void run_round(uint32_t* tile, const int s, const uint2* tws, const F& fp,
+__device__ __forceinline__ void run_round(uint32_t* tile, const int s, const uint32_t* tws, const F& fp,
                                           const unsigned ncols) {
     constexpr int items = ((1 << R_LOG) >> G) * NTT_C;
     for (int w = threadIdx.x; w < items; w += blockDim.x) {
@@ -123,7 +119,7 @@ __device__ __forceinline__ void run_round(uint32_t* tile, const int s, const uin
 }
 
 template <int R_LOG, bool DIF, bool LAZY = false, class F = FieldParams>
-__device__ __forceinline__ void run_rounds(uint32_t* tile, const uint2* tws, const F& fp, unsigned ncols) {
+__device__ __forceinline__ void run_rounds(uint32_t* tile, const uint32_t* tws, const F& fp, unsigned ncols) {
     // stage groups (sum = R_LOG); DIT walks spans upward, DIF downward
     if constexpr (R_LOG <= 4) {
         run_round<R_LOG, R_LOG, DIF, LAZY>(tile, 0, tws, fp, ncols);
@@ -153,8 +149,8 @@ __global__ void ntt_pass_kernel(NttPass ps, FieldParams fp) {
     extern __shared__ uint32_t smem[];
     constexpr int R = 1 << R_LOG;
     uint32_t* tile = smem;                    // [R][33]
-    uint2* tws = reinterpret_cast<uint2*>(smem + R * NTT_TS);        // [R/2] twiddles of w_R
-    fill_tile_twiddles(tws, ps.small, ps.small_log, R_LOG, fp);
+    uint32_t* tws = smem + R * NTT_TS;        // [R/2] twiddles of w_R
+    fill_tile_twiddles(tws, ps.small, ps.small_log, R_LOG);
 
     const size_t tile_id = blockIdx.x;
     size_t gbase;
@@ -219,7 +215,7 @@ static void launch_pass(stark_ctx* ctx, const NttPass& ps, size_t tiles) {
     int threads = (R * NTT_C) >> 4;
     if (threads < 32) threads = 32;
     if (threads > 1024) threads = 1024;
-    size_t smem = (size_t)(R * NTT_TS + R + 2) * sizeof(uint32_t);
+    size_t smem = (size_t)(R * NTT_TS + (R >> 1) + 2) * sizeof(uint32_t);
     auto kern = ntt_pass_kernel<R_LOG, DIF, STRIDED>;
     if (smem > 48 * 1024)   // opt in per launch: the attribute is per device, contexts may live on several
         STARK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -479,9 +475,9 @@ __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat
     extern __shared__ uint32_t smem[];
     constexpr int R = 1 << R_LOG;
     uint32_t* tile = smem;                    // [R][33], row rho holds digit value bitrev(rho) until the rounds have run
-    uint2* tws = reinterpret_cast<uint2*>(smem + R * NTT_TS);        // [R/2] twiddles of w_R
-    uint2* rowtw = tws + (R >> 1);            // [R] W^(K t), t = bitrev(row), as {w, w * p^-1}
-    fill_tile_twiddles(tws, ps.small, ps.small_log, R_LOG, fp);
+    uint32_t* tws = smem + R * NTT_TS;        // [R/2] twiddles of w_R
+    uint32_t* rowtw = tws + (R >> 1);         // [R] W^(K t), t = bitrev(row)
+    fill_tile_twiddles(tws, ps.small, ps.small_log, R_LOG);
 
     const size_t tiles_per_high = ((size_t)1 << ps.lo) / NTT_C;
     const size_t high = blockIdx.x / tiles_per_high;
@@ -515,8 +511,7 @@ __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat
         if (!FIRST && b == 0) {
             const uint32_t K = nat_kacc(ps, (uint32_t)high);
             for (int rho = threadIdx.x; rho < R; rho += T) {         // indexed by tile row: consecutive words for a warp's 4 rows
-                const uint32_t w = pow_lookup(ps.tw, (K * bitrev_bits((uint32_t)rho, R_LOG)) << (ps.lo - ps.col_bits), fp);
-                rowtw[rho] = make_uint2(w, w * fp.pinv);
+                rowtw[rho] = pow_lookup(ps.tw, (K * bitrev_bits((uint32_t)rho, R_LOG)) << (ps.lo - ps.col_bits), fp);
             }
             __syncthreads();
         }
@@ -534,9 +529,9 @@ __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat
                     for (int k = 0; k < 4; k++) { v[k] = mont_mul(v[k], sc, fp); if (k < 3) sc = mont_mul(sc, step, fp); }
                 }
             } else {
-                const uint2 w = rowtw[rho];
+                const uint32_t w = rowtw[rho];
 #pragma unroll
-                for (int k = 0; k < 4; k++) v[k] = mont_mul_tw(v[k], w.x, w.y, fp);
+                for (int k = 0; k < 4; k++) v[k] = mont_mul_tw(v[k], w, fp);
             }
             uint32_t* o = tile + rho * NTT_TS + 4 * g4;
 #pragma unroll
@@ -561,9 +556,9 @@ __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat
     extern __shared__ uint32_t smem[];
     constexpr int R = 1 << R_LOG;
     uint32_t* tile = smem;                    // [R rows = n_m][33: column j = k1 - k1_0]
-    uint2* tws = reinterpret_cast<uint2*>(smem + R * NTT_TS);
-    uint2* coltw = tws + (R >> 1);            // [32] W^K(j), W = w_{2^log_n}, as {w, w * p^-1}
-    fill_tile_twiddles(tws, ps.small, ps.small_log, R_LOG, fp);
+    uint32_t* tws = smem + R * NTT_TS;
+    uint32_t* coltw = tws + (R >> 1);         // [32] W^K(j), W = w_{2^log_n}
+    fill_tile_twiddles(tws, ps.small, ps.small_log, R_LOG);
 
     // address bits above the digit: [k1][mid]; the tile takes 32 consecutive k1 at one mid
     // (a batch of transforms: the tiles of one transform are consecutive, src / dst move on by 2^log_n per transform)
@@ -598,8 +593,7 @@ __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat
         }
         if (b == 0) {
             if (threadIdx.x < NTT_C) {
-                const uint32_t w = pow_lookup(ps.tw, K0 + threadIdx.x, fp);
-                coltw[threadIdx.x] = make_uint2(w, w * fp.pinv);
+                coltw[threadIdx.x] = pow_lookup(ps.tw, K0 + threadIdx.x, fp);
             }
             __syncthreads();
         }
@@ -609,12 +603,12 @@ __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat
             const int q8 = i & 7, jj = (i >> 3) & 3, rest = i >> 5;
             const int seg = rest & ((R >> 5) - 1), j = (rest >> (R_LOG - 5)) * 4 + jj;
             const uint32_t n3 = (uint32_t)seg * 32 + 4 * q8;
-            const uint2 step = coltw[j];
+            const uint32_t step = coltw[j];
             uint32_t w = mont_mul(wl[u], wh[u], fp);
             uint32_t* o = tile + n3 * NTT_TS + j;
-            o[0] = mont_mul(a[u].x, w, fp); w = mont_mul_tw(w, step.x, step.y, fp);
-            o[NTT_TS] = mont_mul(a[u].y, w, fp); w = mont_mul_tw(w, step.x, step.y, fp);
-            o[2 * NTT_TS] = mont_mul(a[u].z, w, fp); w = mont_mul_tw(w, step.x, step.y, fp);
+            o[0] = mont_mul(a[u].x, w, fp); w = mont_mul_tw(w, step, fp);
+            o[NTT_TS] = mont_mul(a[u].y, w, fp); w = mont_mul_tw(w, step, fp);
+            o[2 * NTT_TS] = mont_mul(a[u].z, w, fp); w = mont_mul_tw(w, step, fp);
             o[3 * NTT_TS] = mont_mul(a[u].w, w, fp);
         }
     }
@@ -643,7 +637,7 @@ template <int R_LOG, bool FIRST>
 static void launch_nat_strided(stark_ctx* ctx, const NatPass& ps, size_t tiles) {
     constexpr int R = 1 << R_LOG;
     const int threads = nat_threads(R_LOG);
-    size_t smem = (size_t)(R * NTT_TS + R + 2 * R) * sizeof(uint32_t);
+    size_t smem = (size_t)(R * NTT_TS + (R >> 1) + R) * sizeof(uint32_t);
     auto launch = [&](auto kern) {
         if (smem > 48 * 1024) STARK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)tiles, threads, smem, ctx->stream>>>(ps, ctx->fp);
@@ -657,7 +651,7 @@ template <int R_LOG>
 static void launch_nat_last(stark_ctx* ctx, const NatPass& ps, size_t tiles) {
     constexpr int R = 1 << R_LOG;
     const int threads = nat_threads(R_LOG);
-    size_t smem = (size_t)(R * NTT_TS + R + 2 * NTT_C) * sizeof(uint32_t);
+    size_t smem = (size_t)(R * NTT_TS + (R >> 1) + NTT_C) * sizeof(uint32_t);
     auto kern = is_ref_field(ctx) ? nat_last_kernel<R_LOG, true> : nat_last_kernel<R_LOG, false>;
     if (smem > 48 * 1024) STARK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)tiles, threads, smem, ctx->stream>>>(ps, ctx->fp);
@@ -810,8 +804,8 @@ __global__ void __launch_bounds__(lde8_threads(R_LOG), ntt_min_blocks(lde8_threa
     extern __shared__ uint32_t smem[];
     constexpr int R = 1 << R_LOG;
     uint32_t* tile = smem;                    // [R][33]: word g*8+s of row t
-    uint2* tws = reinterpret_cast<uint2*>(smem + R * NTT_TS);
-    fill_tile_twiddles(tws, ps.small, ps.small_log, R_LOG, fp);
+    uint32_t* tws = smem + R * NTT_TS;
+    fill_tile_twiddles(tws, ps.small, ps.small_log, R_LOG);
 
     const size_t tile_id = blockIdx.x;
     size_t row_base;          // FIRST: first row of the tile; else row of (t = 0, g = 0)
@@ -849,10 +843,10 @@ __global__ void __launch_bounds__(lde8_threads(R_LOG), ntt_min_blocks(lde8_threa
         for (int u = 0; u < 2; u++) {
             const int i = b + threadIdx.x + u * T;
             const int g = i & 3, t = i >> 2;
-            const uint32_t tw = mont_mul(wl[u], wh[u], fp), twp = tw * fp.pinv;
+            const uint32_t tw = mont_mul(wl[u], wh[u], fp);
             uint32_t* o = tile + t * NTT_TS + g * 8;
-            o[0] = mont_mul_tw(a[u].x, tw, twp, fp); o[1] = mont_mul_tw(a[u].y, tw, twp, fp); o[2] = mont_mul_tw(a[u].z, tw, twp, fp); o[3] = mont_mul_tw(a[u].w, tw, twp, fp);
-            o[4] = mont_mul_tw(bq[u].x, tw, twp, fp); o[5] = mont_mul_tw(bq[u].y, tw, twp, fp); o[6] = mont_mul_tw(bq[u].z, tw, twp, fp); o[7] = mont_mul_tw(bq[u].w, tw, twp, fp);
+            o[0] = mont_mul_tw(a[u].x, tw, fp); o[1] = mont_mul_tw(a[u].y, tw, fp); o[2] = mont_mul_tw(a[u].z, tw, fp); o[3] = mont_mul_tw(a[u].w, tw, fp);
+            o[4] = mont_mul_tw(bq[u].x, tw, fp); o[5] = mont_mul_tw(bq[u].y, tw, fp); o[6] = mont_mul_tw(bq[u].z, tw, fp); o[7] = mont_mul_tw(bq[u].w, tw, fp);
         }
         }
     }
@@ -884,12 +878,11 @@ __global__ void __launch_bounds__(lde8_threads(R_LOG), ntt_min_blocks(lde8_threa
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int g = (int)bitrev_bits((uint32_t)k, 2);
-                const uint32_t bp = b * fp.pinv;
                 uint32_t v = mont_mul(c[k], sc, fp);                                           // c_j g^j
                 uint32_t* o = tile + t * NTT_TS + g * 8;
                 o[0] = v;
 #pragma unroll
-                for (int e = 1; e < 8; e++) { v = mont_mul_tw(v, b, bp, fp); o[e] = v; }       // ... * w_N^(j s)
+                for (int e = 1; e < 8; e++) { v = mont_mul_tw(v, b, fp); o[e] = v; }       // ... * w_N^(j s)
                 if (k < 3) { sc = mont_mul(sc, sc_step, fp); b = mont_mul(b, b_step, fp); }
             }
         }
@@ -918,7 +911,7 @@ template <int R_LOG, bool FIRST, bool LAZY, bool PREF>
 static void launch_lde8_impl(stark_ctx* ctx, const Lde8Pass& ps, size_t tiles) {
     constexpr int R = 1 << R_LOG;
     const int threads = lde8_threads(R_LOG);
-    size_t smem = (size_t)(R * NTT_TS + R + 2) * sizeof(uint32_t);
+    size_t smem = (size_t)(R * NTT_TS + (R >> 1) + 2) * sizeof(uint32_t);
     auto kern = lde8_pass_kernel<R_LOG, FIRST, LAZY, PREF>;
     if (smem > 48 * 1024) STARK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)tiles, threads, smem, ctx->stream>>>(ps, ctx->fp);

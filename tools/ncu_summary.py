@@ -15,6 +15,7 @@ import sys
 KEYS = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__occupancy_limit_registers",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
         "sm__inst_executed_pipe_alu.sum", "sm__inst_executed_pipe_fma.sum", "smsp__inst_executed.sum",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
@@ -114,15 +115,20 @@ def pipe(srcs, dst):
             k = short(r[col("Kernel Name")])
             k = CLASS.get(k, re.sub(r"<.*", "", k) if k.startswith(("merkle_tail", "fri_")) else k)
             t = float(r[col("gpu__time_duration.sum")].replace(",", ""))
-            a = acc.setdefault(k, {"t": 0.0, "alu": 0.0, "fma": 0.0, "issue": 0.0, "n": 0})
+            a = acc.setdefault(k, {"t": 0.0, "alu": 0.0, "fma": 0.0, "fmaheavy": 0.0, "lsu": 0.0, "issue": 0.0, "n": 0})
             a["t"] += t; a["n"] += 1
             a["alu"] += t * float(r[col("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active")])
             a["fma"] += t * float(r[col("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active")])
             a["issue"] += t * float(r[col("smsp__issue_active.avg.pct_of_peak_sustained_active")])
+            # the integer multiplies (IMAD, half-rate IMAD.HI / IMAD.WIDE, and ptxas' VIADD / IMAD.IADD adds) all run on the
+            # FMA-HEAVY half of the FMA pipe: the combined fma figure above averages it with the idle FMA-lite half
+            a["fmaheavy"] += t * float(r[col("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed")])
+            a["lsu"] += t * float(r[col("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed")])
     out = {"_source": f"ncu --set full --clock-control none: {srcs}; sm__pipe_alu_cycles_active / sm__pipe_fma_cycles_active / "
                       "smsp__issue_active .avg.pct_of_peak_sustained_active, time-weighted over the captured launches of each class"}
     for k, a in acc.items():
         out[k] = {"alu_pipe_pct": round(a["alu"] / a["t"], 1), "fma_pipe_pct": round(a["fma"] / a["t"], 1),
+                  "fmaheavy_pipe_pct": round(a["fmaheavy"] / a["t"], 1), "lsu_wavefront_pct": round(a["lsu"] / a["t"], 1),
                   "issue_active_pct": round(a["issue"] / a["t"], 1), "launches_captured": a["n"]}
     json.dump(out, open(dst, "w"), indent=1)
     print("wrote", dst)
