@@ -29,12 +29,14 @@ static_assert((((uint64_t)1 << 32) % FieldRef::p) == FieldRef::one && ((uint64_t
 
 // ---- conditional corrections --------------------------------------------------------------------------------
 // Every modular add / subtract / Montgomery product ends in "add or subtract p if the 32-bit result went the wrong
-// way".  Written as compare + select + add that is three instructions on the ALU pipe, the contended one (the
-// rotates and boolean functions of SHA-256 and the compares of these corrections only run there).  The forms below
-// take the carry-out of the add / subtract itself as the predicate (IADD3 Rd, P0, ...) and apply the correction as a
-// predicated multiply-add on the FMA pipe (`one` is a 1 the compiler cannot see through, so it stays an IMAD):
-// one ALU + one FMA instruction per correction.  ptxas maps `add.cc / sub.cc ; addc c,0,0 ; setp c` onto the carry
-// predicate directly (checked in the SASS: IADD3 R, P0, PT, a, -b, RZ ; @!P0 IMAD R, one, p, R).
+// way".  Written as compare + select + add that is three instructions.  The forms below take the carry-out of the
+// add / subtract itself as the predicate (IADD3 Rd, P0, ...) and apply the correction as ONE predicated add: ptxas maps
+// `add.cc / sub.cc ; addc c,0,0 ; setp c` onto the carry predicate directly (checked in the SASS).  Which pipe the
+// predicated add lands on is ptxas' choice: IADD3 (ALU pipe) or VIADD / IMAD.IADD (FMA-heavy pipe, measured in
+// tools/ubench/pipes.cu) -- it alternates to balance instruction counts and cannot be steered from PTX (a predicated
+// three-input add comes back as VIADD + IADD3, a predicated add-with-carry as IADD3.X + SEL).  STARK_CORR_FMA forces
+// corrections onto the FMA pipe as predicated multiply-adds (`one` is a 1 the compiler cannot see through); every such
+// variant measured slower (profiles/r02_ntt.md), the multiplier pipe being the one the transforms saturate.
 // STARK_FIELD_CARRY=0 restores the compare + select forms (kernel experiments, tools/variants_ntt.sh).
 #ifndef STARK_FIELD_CARRY
 #define STARK_FIELD_CARRY 1

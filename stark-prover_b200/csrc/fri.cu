@@ -9,6 +9,8 @@
 //   degree        src/polynomial/ops.rs:19-37 (trailing zeros trimmed) drives `while poly.degree >= 1`
 //                 (fri_commit.rs:89), so the exact degree of the folded polynomial is tracked
 //   inverse       src/fields/element.rs:54-57: a^(p-2), hence inverse(0) == 0
+#include <stdlib.h>
+
 #include "kernels.hpp"
 
 namespace starkb200 {
@@ -66,8 +68,9 @@ DegScratch* deg_scratch(stark_ctx* ctx);
 
 // exact degree of a coefficient vector (ops.rs:19-37: trailing zeros trimmed): block max -> atomic max -> last block publishes
 __global__ void poly_degree_kernel(const uint32_t* c, size_t len, HostResult* result, DegScratch* scratch) {
-    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int mine = (j < len && c[j] != 0) ? (int)(j + 1) : 0;
+    int mine = 0;
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < len; j += (size_t)gridDim.x * blockDim.x)
+        if (c[j] != 0) mine = (int)(j + 1);
     __shared__ int smax;
     if (threadIdx.x == 0) smax = 0;
     __syncthreads();
@@ -98,13 +101,14 @@ void coeff_fold_job(stark_ctx* ctx, const uint32_t* c, size_t len, uint32_t beta
     STARK_REQUIRE(out_len >= 1 && len <= 0x7fffffffu, "coeff_fold: empty or oversized polynomial");
     job.c = c; job.out = out; job.len = (uint32_t)len; job.out_len = (uint32_t)out_len; job.beta_m = beta_m;
     const size_t want = (out_len + cta_threads - 1) / cta_threads;
-    job.ctas = (unsigned)(want < COEFF_JOB_MAX_CTAS ? want : COEFF_JOB_MAX_CTAS);
+    static const unsigned cap = [] { const char* e = getenv("STARK_COEFF_JOB_CTAS"); unsigned v = e ? (unsigned)atoi(e) : 0; return v ? v : COEFF_JOB_MAX_CTAS; }();
+    job.ctas = (unsigned)(want < cap ? want : cap);
     job.result = result; job.scratch = deg_scratch(ctx);
 }
 void poly_degree(stark_ctx* ctx, const uint32_t* c, size_t len, HostResult* result) {
     KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 8.0 * len);
     STARK_REQUIRE(len > 0, "poly_degree: empty");
-    poly_degree_kernel<<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>(c, len, result, deg_scratch(ctx));
+    poly_degree_kernel<<<(unsigned)std::min<size_t>((len + 255) / 256, 592), 256, 0, ctx->stream>>>(c, len, result, deg_scratch(ctx));
     ctx->launches++;
     STARK_CUDA(cudaGetLastError());
 }

@@ -15,9 +15,10 @@ struct TreeShape {
 };
 
 // Coefficient-space fold of a FRI layer (fri_commit.rs:32-50: even + beta * odd, with the exact degree the loop condition
-// at :89 needs) riding in the FIRST launch of that layer's tree: the lowest `ctas` block indices of the launch run it, the
-// rest hash.  It is a few microseconds of memory work beside an ALU-bound launch; as a launch of its own it cost ~6 us of
-// launch latency per layer (21 of them per proof).
+// at :89 needs) riding in the FIRST launch of that layer's tree.  Throughput-bound launches (merkle_subtree_kernel): the
+// first `ctas` CTAs do a slice each before they hash.  The latency-bound one-launch trees (merkle_tail_kernel, one warp per
+// scheduler): `ctas` EXTRA CTAs at the end of the grid.  It is a few microseconds of memory work beside ALU-bound hashing; as
+// a launch of its own it cost ~6-14 us per layer (21 of them per proof).
 struct CoeffJob {
     const uint32_t* c = nullptr;       // len coefficients
     uint32_t* out = nullptr;           // out_len = (len + 1) / 2 folded coefficients
@@ -27,7 +28,7 @@ struct CoeffJob {
     HostResult* result = nullptr;      // degree + 1 of the folded polynomial lands in result->degree_plus1
     DegScratch* scratch = nullptr;
 };
-constexpr unsigned COEFF_JOB_MAX_CTAS = 296;
+constexpr unsigned COEFF_JOB_MAX_CTAS = 96;      // measured: 8 / 32 / 96 / 296 -> commit phase 7.82 / 7.17 / 7.07 / 7.13 ms
 
 // Source of the leaf VALUES of a tree: either an existing layer, or the FRI fold of the previous layer
 // computed on the fly (and written to `fold_out`) — the fused fold-and-hash of fri_commit.rs:94-97.

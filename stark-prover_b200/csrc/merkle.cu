@@ -86,11 +86,10 @@ template <int SRC>
 __global__ void __launch_bounds__(MERKLE_THREADS, STARK_MERKLE_MIN_BLOCKS)
 merkle_subtree_kernel(LeafSource src, const uint32_t* in_digests, size_t n, int nlev, LevelPtrs lv, FieldParams fp,
                       HostResult* result, int last) {
-    unsigned bid = blockIdx.x;
-    if (SRC == SRC_FOLD && src.job.ctas) {              // the layer's coefficient-space fold rides in the lowest block indices
-        if (bid < src.job.ctas) { coeff_job_run(src.job, bid, fp); return; }
-        bid -= src.job.ctas;
-    }
+    const unsigned bid = blockIdx.x;
+    // the layer's coefficient-space fold: the first job.ctas CTAs do a slice of it each BEFORE they hash (extra CTAs beside an
+    // ALU-bound grid that fits one wave cost it 12 %: the 2^20-leaf launch went 176 -> 197 us whatever their number or position)
+    if (SRC == SRC_FOLD && bid < src.job.ctas) coeff_job_run(src.job, bid, fp);
     const size_t t = (size_t)bid * blockDim.x + threadIdx.x;
     const size_t base = t << SUB;
     if (base >= n) return;
@@ -223,10 +222,11 @@ __global__ void __launch_bounds__(TAIL_THREADS) merkle_tail_kernel(TailArgs a) {
     __shared__ __align__(8) uint32_t sm[2][8][TAIL_THREADS + 2];
     __shared__ int s_last;
     const int t = threadIdx.x;
-    unsigned bid = blockIdx.x, nblk = gridDim.x;
-    if (SRC == SRC_FOLD && a.src.job.ctas) {     // the layer's coefficient-space fold rides in the lowest block indices
-        if (bid < a.src.job.ctas) { coeff_job_run(a.src.job, bid, a.fp); return; }
-        bid -= a.src.job.ctas; nblk -= a.src.job.ctas;
+    const unsigned bid = blockIdx.x;
+    unsigned nblk = gridDim.x;
+    if (SRC == SRC_FOLD && a.src.job.ctas) {     // the layer's coefficient-space fold rides in the highest block indices
+        nblk -= a.src.job.ctas;
+        if (bid >= nblk) { coeff_job_run(a.src.job, bid - nblk, a.fp); return; }
     }
     int len = a.n_items;                         // length of the level being consumed
     uint32_t* out = a.out;                       // storage of the level being produced
@@ -355,7 +355,11 @@ void merkle_build(stark_ctx* ctx, const LeafSource& src, const TreeShape& shape,
         size_t threads = (n + (1 << SUB) - 1) >> SUB;
         unsigned blocks = (unsigned)((threads + MERKLE_THREADS - 1) / MERKLE_THREADS);
         KernelTimer kt(ctx, stark_ctx::CAT_MERKLE_LEAF, 1384.0 * ((double)n + comp_levels(1, SUB)));
-        if (fold) merkle_subtree_kernel<SRC_FOLD><<<blocks + src.job.ctas, MERKLE_THREADS, 0, ctx->stream>>>(src, nullptr, n, SUB, lv, ctx->fp, result, 0);
+        if (fold) {
+            LeafSource s2 = src;
+            if (s2.job.ctas > blocks) s2.job.ctas = blocks;          // grid-stride: any number of CTAs covers the job
+            merkle_subtree_kernel<SRC_FOLD><<<blocks, MERKLE_THREADS, 0, ctx->stream>>>(s2, nullptr, n, SUB, lv, ctx->fp, result, 0);
+        }
         else merkle_subtree_kernel<SRC_VALUES><<<blocks, MERKLE_THREADS, 0, ctx->stream>>>(src, nullptr, n, SUB, lv, ctx->fp, result, 0);
         ctx->launches++;
         cur = SUB;

@@ -51,9 +51,10 @@ struct NttPass {
 // element (2^32 < 2p, so canonical or canonical + p).  A Montgomery product accepts a weak operand and returns a canonical one, so in
 // a + w*b / a - w*b only `a` is weak; the sum wraps past 2^32 at most once and the difference goes negative
 // at most once: one carry-predicated correction each (field.cuh: add_wrap_fix / sub_fix).  The last pass canonicalises
-// on store.  A butterfly is 9 instructions: the product (IMAD, 2 IMAD.HI, IADD3 with carry-out, predicated IMAD) and
-// two IADD3-with-carry + predicated-IMAD pairs -- 3 on the ALU pipe, 6 on the FMA pipe (was 7 + 5 with compare + select
-// corrections, profiles/r02_ntt.md).
+// on store.  A butterfly is 9 instructions: the product (IMAD.WIDE, IMAD, IMAD.HI, IADD3 with carry-out, predicated add)
+// and two IADD3-with-carry + predicated-add pairs.  The multiplies can only run on the FMA-heavy pipe (2 / 4 / 4 cycles per
+// warp instruction) and ptxas places about half of the predicated adds there too (as VIADD / IMAD.IADD): that pipe, not
+// the ALU pipe, bounds these kernels (profiles/r02_ntt.md, tools/ubench/pipes.cu).
 template <class F>
 __device__ __forceinline__ uint32_t ladd(uint32_t a_weak, uint32_t b, const F& f) { return add_wrap_fix(a_weak, b, f.p); }
 template <class F>
@@ -460,7 +461,7 @@ __device__ __forceinline__ uint32_t nat_kacc(const NatPass& ps, uint32_t high) {
 constexpr int nat_threads(int r_log) { return (2 << r_log) < 64 ? 64 : ((2 << r_log) > 512 ? 512 : (2 << r_log)); }
 // resident CTAs per SM the register allocation aims for: STARK_NTT_REGCAP = registers per thread the transforms may use
 #ifndef STARK_NTT_REGCAP
-#define STARK_NTT_REGCAP 48
+#define STARK_NTT_REGCAP 42
 #endif
 constexpr int ntt_min_blocks(int threads, int cap) {
     int by_regs = 65536 / (STARK_NTT_REGCAP * threads), by_threads = 1536 / threads;

@@ -693,6 +693,34 @@ def test_small_modulus_blowup8_path(sp, orc, modulus, gen):
         c.close()
 
 
+@pytest.mark.parametrize("modulus,gen", [(3221225473, 5), (4293918721, 19), (998244353, 3)])
+def test_blowup8_first_pass_ragged_coefficients(sp, orc, modulus, gen):
+    """First pass of the blow-up-by-8 transform: a tile takes the lowest row digit x the TOP two row bits, so one thread
+    reads FOUR adjacent coefficients with one 16-byte load and walks their scale / shift factors.  Coefficient counts
+    around every multiple of 4, at the ends of the tables, below one tile row and above -- for the reference field (the
+    kernels instantiated with the modulus as an immediate), a modulus close to 2^32 (run-time modulus, weak values) and one
+    below 2^31 (strict values)."""
+    c = sp.Context(modulus, gen, 0)
+    try:
+        for log_n in (13, 14, 17):
+            w = orc.root_of_unity(log_n, modulus, gen)
+            top = 1 << (log_n - 3)
+            for nco in (1, 2, 3, 4, 5, 6, 7, 8, 9, 127, 129, 1021, 1023, 1024, top - 3, top - 1, top):
+                coeffs = orc.synthetic_column(nco + log_n, nco, modulus)
+                off = (5 + 977 * nco) % modulus or 7
+                got = c.coset_evaluate(coeffs, log_n, off)
+                assert np.array_equal(got, orc.coset_evaluate(coeffs, log_n, off, w, modulus)), (log_n, nco)
+        # the LDE chain (natural iNTT -> first pass reads its unscaled coefficients with c0 = 1/n folded into the walk)
+        for log_n in (10, 12, 15):
+            vals = orc.synthetic_column(77 + log_n, 1 << log_n, modulus)
+            w, W = orc.root_of_unity(log_n, modulus, gen), orc.root_of_unity(log_n + 3, modulus, gen)
+            co = orc.coset_interpolate(vals, log_n, 1, w, modulus)
+            want = orc.coset_evaluate(co, log_n + 3, 11, W, modulus)
+            assert np.array_equal(c.coset_lde(vals, log_n, 1, 3, 11), want), log_n
+    finally:
+        c.close()
+
+
 @pytest.mark.parametrize("modulus,gen", [(4293918721, 19), (3489660929, 3)])
 def test_large_modulus_lde_and_fold_paths(sp, orc, modulus, gen):
     """The blow-up-8 LDE kernel (weak/lazy arithmetic) and the fused fold with p close to 2^32."""
