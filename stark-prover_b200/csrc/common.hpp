@@ -162,7 +162,7 @@ struct PinnedBuf {
     }
 };
 
-struct DegScratch { int maxv; unsigned ticket; };     // coeff_fold_kernel's cross-block reduction state
+struct DegScratch { int maxv; unsigned ticket; };     // cross-block reduction state of the coefficient fold job / poly_degree_kernel
 
 // What the host reads after each commit without issuing a copy (mapped pinned memory).
 struct HostResult {
@@ -219,7 +219,7 @@ struct stark_ctx {
     starkb200::HostResult* d_result = nullptr;  // device alias of h_result
     starkb200::PinnedBuf pin_desc, pin_out;     // opening descriptors in, opening records out
     starkb200::PinnedBuf pin_stage;             // host-produced columns on their way to HBM (the FibonacciSq trace)
-    starkb200::DevBuf deg_scratch;              // DegScratch of coeff_fold_kernel
+    starkb200::DevBuf deg_scratch;              // DegScratch of the coefficient fold job (coeff_job.cuh)
     starkb200::DevBuf tail_counter;             // "last CTA" ticket of merkle_tail_kernel (zero between launches)
     int sm_count = 148;
     unsigned long long launches = 0;            // kernels launched through this context
