@@ -35,8 +35,10 @@ struct StarkError : std::runtime_error {
         if (!(cond)) throw ::starkb200::StarkError(::starkb200::ST_INVALID, msg);                     \
     } while (0)
 
-// Stream-ordered device allocation.  Large blocks (>= 1 MiB) are recycled through an exact-size free list per
-// stream before falling back to the cudaMallocAsync pool: a prover allocates the same few sizes over and over
+// Stream-ordered device allocation.  Blocks of >= 4 KiB are recycled through an exact-size free list per
+// stream before falling back to the cudaMallocAsync pool (small ones too since round 2: three cudaMallocAsync calls per FRI
+// layer sat between a layer's root and the next launch, ~0.05 ms per proof; their number is capped so that a workload of
+// ever-changing sizes cannot pile up entries): a prover allocates the same few sizes over and over
 // (layer, tree levels, staging), and reusing the very same block on the very same stream is always ordered
 // correctly and never depends on how the driver's pool splits and coalesces (measured: without the list a
 // 64-column commit showed 10-200 ms allocation spikes once three sizes interleaved).
@@ -44,8 +46,9 @@ struct BlockCache {
     static std::mutex& mu() { static std::mutex m; return m; }
     struct PerStream { std::multimap<size_t, void*> blocks; size_t held = 0; int device = -1; };
     static std::map<cudaStream_t, PerStream>& lists() { static std::map<cudaStream_t, PerStream> l; return l; }
-    static constexpr size_t kMinBytes = (size_t)1 << 20;
+    static constexpr size_t kMinBytes = (size_t)1 << 12;          // smaller blocks: the driver pool is as fast as these lists
     static constexpr size_t kMaxHeld = (size_t)24 << 30;          // per stream
+    static constexpr size_t kMaxBlocks = 4096;                    // per stream
     static void* take(cudaStream_t s, size_t bytes) {
         if (bytes < kMinBytes) return nullptr;
         std::lock_guard<std::mutex> g(mu());
@@ -61,7 +64,7 @@ struct BlockCache {
         if (bytes < kMinBytes) return false;
         std::lock_guard<std::mutex> g(mu());
         auto& l = lists()[s];
-        if (l.held + bytes > kMaxHeld) return false;
+        if (l.held + bytes > kMaxHeld || l.blocks.size() >= kMaxBlocks) return false;
         if (l.device < 0) cudaGetDevice(&l.device);
         l.blocks.emplace(bytes, p);
         l.held += bytes;

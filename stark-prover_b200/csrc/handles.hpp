@@ -31,6 +31,7 @@ struct stark_fri {
     uint64_t offset0 = 1;
     unsigned cur_log = 0;
     uint64_t cur_offset = 1;
+    uint64_t half_over_offset = 0;   // 1 / (2 * cur_offset) mod p, squared-and-doubled along with cur_offset (0 = not formed yet)
     starkb200::DevBufPtr coeffs;
     size_t coeff_len = 0;            // degree + 1 (0 = zero polynomial)
     std::vector<std::unique_ptr<stark_tree>> trees;
