@@ -24,6 +24,13 @@ namespace starkb200 {
 
 constexpr int NTT_C = 32;
 constexpr int NTT_TS = NTT_C + 1;
+// Row stride of the tiles whose load / store phases move whole 16-byte groups of a row (blow-up-by-8 passes, strided
+// natural-order passes): 36 words keeps every row 16-byte aligned, so those phases are STS.128 / LDS.128 (4x fewer
+// shared-memory instructions; ncu's source view had 57 % of all warp samples in the load phase of a pass, a third of them
+// on the MIO queue and issue slots of its 32 scalar stores per thread) and stays conflict-free: a quarter warp's eight
+// 16-byte accesses fall on rows t, t+1 (banks 4t + 8g and 4t + 4 + 8g) or on one row (banks 4 rho + 4 g4); the butterfly
+// rounds read one row per warp instruction whatever the stride.
+constexpr int NTT_TS16 = NTT_C + 4;
 
 // The hot transform kernels are instantiated once more for the reference's own field (FieldRef, field.cuh), where the
 // modulus is an immediate and q = lo * p^-1 is a shift-add; every other modulus runs the same kernels on FieldParams.
@@ -68,12 +75,12 @@ __device__ __forceinline__ void fill_tile_twiddles(uint32_t* tws, const uint32_t
     for (int k = threadIdx.x; k < (1 << r_log) >> 1; k += blockDim.x) tws[k] = small[(size_t)k << (small_log - r_log)];
 }
 
-template <int G, bool DIF, bool LAZY, class F>
+template <int G, bool DIF, bool LAZY, int TS, class F>
 __device__ __forceinline__ void butterfly_group(uint32_t* col, const int s, const int base, const uint32_t* tws,
                                                 const int r_log, const F& fp) {
     uint32_t x[1 << G];
 #pragma unroll
-    for (int j = 0; j < (1 << G); j++) x[j] = col[(base + (j << s)) * NTT_TS];
+    for (int j = 0; j < (1 << G); j++) x[j] = col[(base + (j << s)) * TS];
     const int bl = base & ((1 << s) - 1);
 #pragma unroll
     for (int uu = 0; uu < G; uu++) {
@@ -103,10 +110,10 @@ __device__ __forceinline__ void butterfly_group(uint32_t* col, const int s, cons
         }
     }
 #pragma unroll
-    for (int j = 0; j < (1 << G); j++) col[(base + (j << s)) * NTT_TS] = x[j];
+    for (int j = 0; j < (1 << G); j++) col[(base + (j << s)) * TS] = x[j];
 }
 
-template <int R_LOG, int G, bool DIF, bool LAZY, class F>
+template <int R_LOG, int G, bool DIF, bool LAZY, int TS, class F>
 __device__ __forceinline__ void run_round(uint32_t* tile, const int s, const uint32_t* tws, const F& fp,
                                           const unsigned ncols) {
     constexpr int items = ((1 << R_LOG) >> G) * NTT_C;
@@ -114,32 +121,32 @@ __device__ __forceinline__ void run_round(uint32_t* tile, const int s, const uin
         const int c = w % NTT_C, bi = w / NTT_C;
         if ((unsigned)c >= ncols) continue;
         const int base = ((bi >> s) << (s + G)) | (bi & ((1 << s) - 1));
-        butterfly_group<G, DIF, LAZY>(tile + c, s, base, tws, R_LOG, fp);
+        butterfly_group<G, DIF, LAZY, TS>(tile + c, s, base, tws, R_LOG, fp);
     }
     __syncthreads();
 }
 
-template <int R_LOG, bool DIF, bool LAZY = false, class F = FieldParams>
+template <int R_LOG, bool DIF, bool LAZY = false, int TS = NTT_TS, class F = FieldParams>
 __device__ __forceinline__ void run_rounds(uint32_t* tile, const uint32_t* tws, const F& fp, unsigned ncols) {
     // stage groups (sum = R_LOG); DIT walks spans upward, DIF downward
     if constexpr (R_LOG <= 4) {
-        run_round<R_LOG, R_LOG, DIF, LAZY>(tile, 0, tws, fp, ncols);
+        run_round<R_LOG, R_LOG, DIF, LAZY, TS>(tile, 0, tws, fp, ncols);
     } else if constexpr (R_LOG == 5) {
-        if (!DIF) { run_round<5, 3, DIF, LAZY>(tile, 0, tws, fp, ncols); run_round<5, 2, DIF, LAZY>(tile, 3, tws, fp, ncols); }
-        else      { run_round<5, 2, DIF, LAZY>(tile, 3, tws, fp, ncols); run_round<5, 3, DIF, LAZY>(tile, 0, tws, fp, ncols); }
+        if (!DIF) { run_round<5, 3, DIF, LAZY, TS>(tile, 0, tws, fp, ncols); run_round<5, 2, DIF, LAZY, TS>(tile, 3, tws, fp, ncols); }
+        else      { run_round<5, 2, DIF, LAZY, TS>(tile, 3, tws, fp, ncols); run_round<5, 3, DIF, LAZY, TS>(tile, 0, tws, fp, ncols); }
     } else if constexpr (R_LOG == 6) {
-        if (!DIF) { run_round<6, 3, DIF, LAZY>(tile, 0, tws, fp, ncols); run_round<6, 3, DIF, LAZY>(tile, 3, tws, fp, ncols); }
-        else      { run_round<6, 3, DIF, LAZY>(tile, 3, tws, fp, ncols); run_round<6, 3, DIF, LAZY>(tile, 0, tws, fp, ncols); }
+        if (!DIF) { run_round<6, 3, DIF, LAZY, TS>(tile, 0, tws, fp, ncols); run_round<6, 3, DIF, LAZY, TS>(tile, 3, tws, fp, ncols); }
+        else      { run_round<6, 3, DIF, LAZY, TS>(tile, 3, tws, fp, ncols); run_round<6, 3, DIF, LAZY, TS>(tile, 0, tws, fp, ncols); }
     } else if constexpr (R_LOG == 7) {
-        if (!DIF) { run_round<7, 4, DIF, LAZY>(tile, 0, tws, fp, ncols); run_round<7, 3, DIF, LAZY>(tile, 4, tws, fp, ncols); }
-        else      { run_round<7, 3, DIF, LAZY>(tile, 4, tws, fp, ncols); run_round<7, 4, DIF, LAZY>(tile, 0, tws, fp, ncols); }
+        if (!DIF) { run_round<7, 4, DIF, LAZY, TS>(tile, 0, tws, fp, ncols); run_round<7, 3, DIF, LAZY, TS>(tile, 4, tws, fp, ncols); }
+        else      { run_round<7, 3, DIF, LAZY, TS>(tile, 4, tws, fp, ncols); run_round<7, 4, DIF, LAZY, TS>(tile, 0, tws, fp, ncols); }
     } else if constexpr (R_LOG == 8) {
-        if (!DIF) { run_round<8, 4, DIF, LAZY>(tile, 0, tws, fp, ncols); run_round<8, 4, DIF, LAZY>(tile, 4, tws, fp, ncols); }
-        else      { run_round<8, 4, DIF, LAZY>(tile, 4, tws, fp, ncols); run_round<8, 4, DIF, LAZY>(tile, 0, tws, fp, ncols); }
+        if (!DIF) { run_round<8, 4, DIF, LAZY, TS>(tile, 0, tws, fp, ncols); run_round<8, 4, DIF, LAZY, TS>(tile, 4, tws, fp, ncols); }
+        else      { run_round<8, 4, DIF, LAZY, TS>(tile, 4, tws, fp, ncols); run_round<8, 4, DIF, LAZY, TS>(tile, 0, tws, fp, ncols); }
     } else {
         static_assert(R_LOG == 9, "pass width");
-        if (!DIF) { run_round<9, 3, DIF, LAZY>(tile, 0, tws, fp, ncols); run_round<9, 3, DIF, LAZY>(tile, 3, tws, fp, ncols); run_round<9, 3, DIF, LAZY>(tile, 6, tws, fp, ncols); }
-        else      { run_round<9, 3, DIF, LAZY>(tile, 6, tws, fp, ncols); run_round<9, 3, DIF, LAZY>(tile, 3, tws, fp, ncols); run_round<9, 3, DIF, LAZY>(tile, 0, tws, fp, ncols); }
+        if (!DIF) { run_round<9, 3, DIF, LAZY, TS>(tile, 0, tws, fp, ncols); run_round<9, 3, DIF, LAZY, TS>(tile, 3, tws, fp, ncols); run_round<9, 3, DIF, LAZY, TS>(tile, 6, tws, fp, ncols); }
+        else      { run_round<9, 3, DIF, LAZY, TS>(tile, 6, tws, fp, ncols); run_round<9, 3, DIF, LAZY, TS>(tile, 3, tws, fp, ncols); run_round<9, 3, DIF, LAZY, TS>(tile, 0, tws, fp, ncols); }
     }
 }
 
@@ -475,8 +482,9 @@ __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat
     const typename FieldOf<PREF>::type fp = FieldOf<PREF>::make(fp_arg);
     extern __shared__ uint32_t smem[];
     constexpr int R = 1 << R_LOG;
-    uint32_t* tile = smem;                    // [R][33], row rho holds digit value bitrev(rho) until the rounds have run
-    uint32_t* tws = smem + R * NTT_TS;        // [R/2] twiddles of w_R
+    constexpr int TS = NTT_TS16;
+    uint32_t* tile = smem;                    // [R][TS], row rho holds digit value bitrev(rho) until the rounds have run
+    uint32_t* tws = smem + R * TS;        // [R/2] twiddles of w_R
     uint32_t* rowtw = tws + (R >> 1);         // [R] W^(K t), t = bitrev(row)
     fill_tile_twiddles(tws, ps.small, ps.small_log, R_LOG);
 
@@ -534,20 +542,17 @@ __global__ void __launch_bounds__(nat_threads(R_LOG), nat_min_blocks(R_LOG)) nat
 #pragma unroll
                 for (int k = 0; k < 4; k++) v[k] = mont_mul_tw(v[k], w, fp);
             }
-            uint32_t* o = tile + rho * NTT_TS + 4 * g4;
-#pragma unroll
-            for (int k = 0; k < 4; k++) o[k] = v[k];
+            *reinterpret_cast<uint4*>(tile + rho * TS + 4 * g4) = make_uint4(v[0], v[1], v[2], v[3]);
         }
     }
     __syncthreads();
 
-    run_rounds<R_LOG, false, LAZY>(tile, tws, fp, NTT_C);
+    run_rounds<R_LOG, false, LAZY, TS>(tile, tws, fp, NTT_C);
 
     // ---- store: digit k_i in natural row order, same addresses (weak values are fine: the next pass multiplies) ----
     for (int i = threadIdx.x; i < R * 8; i += blockDim.x) {
         const int g4 = i & 7, t = i >> 3;
-        const uint32_t* o = tile + t * NTT_TS + 4 * g4;
-        *reinterpret_cast<uint4*>(ps.dst + gbase + ((size_t)t << ps.lo) + 4 * g4) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(ps.dst + gbase + ((size_t)t << ps.lo) + 4 * g4) = *reinterpret_cast<const uint4*>(tile + t * TS + 4 * g4);
     }
 }
 
@@ -638,7 +643,7 @@ template <int R_LOG, bool FIRST>
 static void launch_nat_strided(stark_ctx* ctx, const NatPass& ps, size_t tiles) {
     constexpr int R = 1 << R_LOG;
     const int threads = nat_threads(R_LOG);
-    size_t smem = (size_t)(R * NTT_TS + (R >> 1) + R) * sizeof(uint32_t);
+    size_t smem = (size_t)(R * NTT_TS16 + (R >> 1) + R) * sizeof(uint32_t);
     auto launch = [&](auto kern) {
         if (smem > 48 * 1024) STARK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)tiles, threads, smem, ctx->stream>>>(ps, ctx->fp);
@@ -804,8 +809,9 @@ __global__ void __launch_bounds__(lde8_threads(R_LOG), ntt_min_blocks(lde8_threa
     const typename FieldOf<PREF>::type fp = FieldOf<PREF>::make(fp_arg);
     extern __shared__ uint32_t smem[];
     constexpr int R = 1 << R_LOG;
-    uint32_t* tile = smem;                    // [R][33]: word g*8+s of row t
-    uint32_t* tws = smem + R * NTT_TS;
+    constexpr int TS = NTT_TS16;
+    uint32_t* tile = smem;                    // [R][TS]: word g*8+s of row t
+    uint32_t* tws = smem + R * TS;
     fill_tile_twiddles(tws, ps.small, ps.small_log, R_LOG);
 
     const size_t tile_id = blockIdx.x;
@@ -845,9 +851,9 @@ __global__ void __launch_bounds__(lde8_threads(R_LOG), ntt_min_blocks(lde8_threa
             const int i = b + threadIdx.x + u * T;
             const int g = i & 3, t = i >> 2;
             const uint32_t tw = mont_mul(wl[u], wh[u], fp);
-            uint32_t* o = tile + t * NTT_TS + g * 8;
-            o[0] = mont_mul_tw(a[u].x, tw, fp); o[1] = mont_mul_tw(a[u].y, tw, fp); o[2] = mont_mul_tw(a[u].z, tw, fp); o[3] = mont_mul_tw(a[u].w, tw, fp);
-            o[4] = mont_mul_tw(bq[u].x, tw, fp); o[5] = mont_mul_tw(bq[u].y, tw, fp); o[6] = mont_mul_tw(bq[u].z, tw, fp); o[7] = mont_mul_tw(bq[u].w, tw, fp);
+            uint4* o = reinterpret_cast<uint4*>(tile + t * TS + g * 8);
+            o[0] = make_uint4(mont_mul_tw(a[u].x, tw, fp), mont_mul_tw(a[u].y, tw, fp), mont_mul_tw(a[u].z, tw, fp), mont_mul_tw(a[u].w, tw, fp));
+            o[1] = make_uint4(mont_mul_tw(bq[u].x, tw, fp), mont_mul_tw(bq[u].y, tw, fp), mont_mul_tw(bq[u].z, tw, fp), mont_mul_tw(bq[u].w, tw, fp));
         }
         }
     }
@@ -879,18 +885,20 @@ __global__ void __launch_bounds__(lde8_threads(R_LOG), ntt_min_blocks(lde8_threa
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int g = (int)bitrev_bits((uint32_t)k, 2);
-                uint32_t v = mont_mul(c[k], sc, fp);                                           // c_j g^j
-                uint32_t* o = tile + t * NTT_TS + g * 8;
-                o[0] = v;
+                uint32_t v[8];
+                v[0] = mont_mul(c[k], sc, fp);                                                 // c_j g^j
 #pragma unroll
-                for (int e = 1; e < 8; e++) { v = mont_mul_tw(v, b, fp); o[e] = v; }       // ... * w_N^(j s)
+                for (int e = 1; e < 8; e++) v[e] = mont_mul_tw(v[e - 1], b, fp);               // ... * w_N^(j s)
+                uint4* o = reinterpret_cast<uint4*>(tile + t * TS + g * 8);
+                o[0] = make_uint4(v[0], v[1], v[2], v[3]);
+                o[1] = make_uint4(v[4], v[5], v[6], v[7]);
                 if (k < 3) { sc = mont_mul(sc, sc_step, fp); b = mont_mul(b, b_step, fp); }
             }
         }
     }
     __syncthreads();
 
-    run_rounds<R_LOG, false, LAZY>(tile, tws, fp, NTT_C);
+    run_rounds<R_LOG, false, LAZY, TS>(tile, tws, fp, NTT_C);
 
     // ---- store ----
     for (int i = threadIdx.x; i < 4 * R; i += blockDim.x) {
@@ -898,7 +906,9 @@ __global__ void __launch_bounds__(lde8_threads(R_LOG), ntt_min_blocks(lde8_threa
         size_t row;
         if (FIRST) { g = i >> R_LOG; t = i & (R - 1); row = row_base + t + ((size_t)g << (ps.log_rows - 2)); }
         else { g = i & 3; t = i >> 2; row = row_base + ((size_t)t << ps.lo) + g; }
-        const uint32_t* o = tile + t * NTT_TS + g * 8;
+        const uint4* o4 = reinterpret_cast<const uint4*>(tile + t * TS + g * 8);
+        const uint4 lo4 = o4[0], hi4 = o4[1];
+        const uint32_t o[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
         uint32_t v[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) v[k] = (LAZY && ps.last) ? canonical(o[k], fp) : o[k];
@@ -912,7 +922,7 @@ template <int R_LOG, bool FIRST, bool LAZY, bool PREF>
 static void launch_lde8_impl(stark_ctx* ctx, const Lde8Pass& ps, size_t tiles) {
     constexpr int R = 1 << R_LOG;
     const int threads = lde8_threads(R_LOG);
-    size_t smem = (size_t)(R * NTT_TS + (R >> 1) + 2) * sizeof(uint32_t);
+    size_t smem = (size_t)(R * NTT_TS16 + (R >> 1) + 2) * sizeof(uint32_t);
     auto kern = lde8_pass_kernel<R_LOG, FIRST, LAZY, PREF>;
     if (smem > 48 * 1024) STARK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)tiles, threads, smem, ctx->stream>>>(ps, ctx->fp);
