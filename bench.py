@@ -429,8 +429,23 @@ def sharded_block(args, sp, synth, ctx, tm: Timer, rank, world, local, mix_peak)
     f.free()
     c5["fri_commit_and_openings"] = {"ms": ms_f, "Melem_per_s": N5 / (ms_f * 1e-3) / 1e6, "transcript_equals_golden": True,
                                      "transcript_state": g5["final_state"], "layers": g5["num_layers"], "queries": q5,
-                                     "note": "four-step LDE + leaf-range commit + layer 0 collected on rank 0 + the unpartitioned fold/commit "
-                                             "loop and openings (rank 0; north-star: nothing else is partitioned)"}
+                                     "note": "four-step LDE + leaf-range commit of layer 0; at N > 1 layer 0 is all-gathered, every rank replicates "
+                                             "the folds (HBM-bound, cheap) and the layers of >= 2^21 leaves are hashed in leaf ranges too (32-byte "
+                                             "subtree roots gathered, beta broadcast); the smaller layers, the channel and their openings stay on "
+                                             "rank 0; one exchange per query for every leaf-range opening"}
+    if world > 1:
+        # the same call with the leaf hashing of layers >= 1 left on rank 0 (round 1 / first half of round 2), for comparison
+        os.environ["STARK_MG_FRI_SHARD"] = "0"
+        try:
+            f, ch = fri()
+            f.free()
+            ms_f0, (f, ch) = tm.best(fri, 2, keep=None)
+            if rank == 0:
+                assert ch.state == g5["final_state"], "cfg5: transcript with the layers >= 1 on rank 0 differs from the golden"
+            f.free()
+        finally:
+            del os.environ["STARK_MG_FRI_SHARD"]
+        c5["fri_commit_and_openings"]["ms_with_layers_ge1_on_rank0"] = ms_f0
     # ---------------- cfg5, the whole prover: FibonacciSq trace of 2^23 - 1 rows, domain 2^26, 3 queries
     gp = gold.get("prove5_small" if args.sharded_small else "prove5")
     if gp:
@@ -444,7 +459,7 @@ def sharded_block(args, sp, synth, ctx, tm: Timer, rank, world, local, mix_peak)
             assert chp.state == gp["final_state"] and hashlib.sha256(chp.proof_flat()).hexdigest() == gp["proof_sha256"], \
                 "cfg5: the transcript of the sharded prover differs from the oracle's golden"
         c5["prove"] = {"ms": ms_p, "what": f"stark_mg_stark101_prove: trace of 2^{gp['log_trace']}-1 rows (sequential recurrence on the host, replicated), "
-                                           f"four-step LDE, leaf-range commitments of f and CP, composition on the local range, FRI layers >= 1 on rank 0, "
+                                           f"four-step LDE, leaf-range commitments of f and CP, composition on the local range, large FRI layers hashed in leaf ranges, "
                                            f"{gp['queries']} queries", "transcript_equals_golden": True, "transcript_state": gp["final_state"]}
     # ---------------- the same workloads on ONE GPU, measured by rank 0 in this run (the other ranks wait): strong-scaling reference
     tm.sync_all()
@@ -576,9 +591,9 @@ def run_b200(args):
 
     per_rank_ms = []
 
-    def step(src):
+    def step(src, layers_out=None):
         ch = sp.Channel(P)
-        pr = sp.fri_commit(ctx, src, domain, ch)
+        pr = sp.fri_commit(ctx, src, domain, ch, layers_out=layers_out)
         sp.decommit_fri(QUERIES, n - 1, pr, ch)
         return pr, ch
 
@@ -588,9 +603,10 @@ def run_b200(args):
         mine = torch.frombuffer(bytearray(pr.tree(0).root_bytes()), dtype=torch.uint8).to(f"cuda:{local}")
         dist.all_gather_into_tensor(roots_out.view(-1), mine)
 
-    def timed(src, steps, flush_l2=True, after=None):
+    def timed(src, steps, flush_l2=True, after=None, layers_out=None):
         """max-over-ranks device time per step (ms) and the last step's artefacts.  `after(pr)`: extra work inside the
-        timed region (e2e_full: the layers copied back by value)."""
+        timed region (the layers copied back by value after the step); `layers_out`: the layers streamed to that pinned
+        buffer during the commit (e2e_full)."""
         total = 0.0
         pr = ch = None
         for _ in range(steps):
@@ -604,7 +620,7 @@ def run_b200(args):
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            pr, ch = step(src)
+            pr, ch = step(src, layers_out)
             if after is not None:
                 after(pr)
             gather_roots(pr)
@@ -677,9 +693,18 @@ def run_b200(args):
             p.layer(k, 0, ln, out=layers_np[off:off + ln])
             off += ln
     timed(pinned_np, 1, after=copy_layers_back)
-    ms_full, pr4, _ = timed(pinned_np, max(2, min(args.steps, 5)), after=copy_layers_back)
+    ms_full_after, pr4, _ = timed(pinned_np, max(2, min(args.steps, 5)), after=copy_layers_back)
     assert int(layers_np[0]) == int(pr4.layer(0, 0, 1)[0])
     pr4.free()
+    # the same by-value result with the copies issued DURING the commit: stark_fri_commit_to_host widens and copies every layer
+    # on a second, high-priority stream while the main stream hashes the following layers; complete when fri_commit returns
+    check = hashlib.sha256(layers_np.tobytes()).hexdigest()
+    layers_np[:] = 0
+    timed(pinned_np, 1, layers_out=layers_np)
+    ms_full, pr5, ch5 = timed(pinned_np, max(2, min(args.steps, 5)), layers_out=layers_np)
+    assert ch5.state == final_state, "the by-value path changed the transcript"
+    assert hashlib.sha256(layers_np.tobytes()).hexdigest() == check, "streamed layers differ from stark_fri_layer_read"
+    pr5.free()
     del layers_pin, layers_np
 
     line = {"metric": METRIC, "value": world * n / (ms_dev * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -691,12 +716,14 @@ def run_b200(args):
                        "log_domain": log_n, "blowup": 1 << args.log_blowup, "queries": QUERIES, "layers": n_layers,
                        "l2": "256 MiB buffer written between timed iterations; layer 0 + its tree = 576 MiB > L2",
                        "fri_commit_decommit_ms": ms_dev,
-                       "fri_layers": "device-resident handles (stark_fri_layer_read copies ranges on demand); e2e_full copies all of them back by value"},
+                       "fri_layers": "device-resident handles (stark_fri_layer_read copies ranges on demand); e2e_full returns all of them by value (streamed during the commit)"},
             "e2e": {"value": world * n / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": 8 << log_deg, "d2h_bytes_per_step": d2h},
             "e2e_full": {"value": world * n / (ms_full * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_full,
                          "h2d_bytes_per_step": 8 << log_deg, "d2h_bytes_per_step": d2h + 8 * sum(layer_lens),
-                         "note": "e2e plus every FRI layer copied to pinned host memory as u64, i.e. FRIProof.fri_layers by value"},
+                         "note": "e2e plus every FRI layer in pinned host memory as u64 when fri_commit returns, i.e. FRIProof.fri_layers by "
+                                 "value: stark_fri_commit_to_host streams them on a second stream under the hashing of the following layers",
+                         "ms_per_step_copied_after_the_step": ms_full_after},
             "gpu_launches": int(launches), "clocks": clocks, "transcript_state": final_state,
             "ms_per_rank": per_rank_dev if world > 1 else None,
             "host_breakdown_ms": host_breakdown}

@@ -220,6 +220,21 @@ int stark_fri_begin_external(stark_ctx* ctx, const stark_vec* coeffs, unsigned l
 int stark_fri_open_layers(const stark_fri* f, size_t first_layer, const uint64_t* indices, size_t n_idx, uint8_t* out,
                           size_t cap, size_t* len);
 void stark_fri_destroy(stark_fri* f);
+/* FRIProof.fri_layers BY VALUE (fri_commit.rs:9-13, :117-121 return Vec<Vec<FieldElement>>) without paying for the copy
+ * after the commit.  stark_fri_begin_to_host is stark_fri_begin with a host destination: layer 0, and every layer a later
+ * stark_fri_fold produces, is also written to layers_out as u64 -- layer k at element offset
+ * stark_fri_layer_host_offset(f, k) = the sum of the earlier layers' lengths -- by a second, high-priority stream (widening
+ * kernel + copy engine) while the main stream hashes the following layers.  cap = capacity of layers_out in elements
+ * (2^(log_n+1) hold every layer).  stark_fri_layers_wait blocks until every copy issued so far has landed;
+ * stark_fri_destroy waits as well.  With pinned memory (cudaHostAlloc / cudaHostRegister) the copies are asynchronous;
+ * pageable memory works but blocks the calling thread for each copy.  stark_fri_commit_to_host = the whole loop with the
+ * library's Channel, complete on return. */
+int stark_fri_begin_to_host(stark_ctx* ctx, const uint64_t* coeffs, size_t n_coeffs, unsigned log_n, uint64_t offset,
+                            uint64_t* layers_out, size_t cap, stark_fri** out, uint8_t root[32]);
+int stark_fri_layers_wait(const stark_fri* f);
+size_t stark_fri_layer_host_offset(const stark_fri* f, size_t k);               /* (size_t)-1: no such layer / no host copy */
+int stark_fri_commit_to_host(stark_ctx* ctx, const uint64_t* coeffs, size_t n_coeffs, unsigned log_n, uint64_t offset,
+                             stark_channel* ch, uint64_t* layers_out, size_t cap, stark_fri** out);
 
 int stark_fri_commit(stark_ctx* ctx, const uint64_t* coeffs, size_t n_coeffs, unsigned log_n, uint64_t offset,
                      stark_channel* ch, stark_fri** out);

@@ -96,6 +96,10 @@ extern "C" {
     pub fn stark_fri_begin_external(ctx: *mut stark_ctx, coeffs: *const stark_vec, log_n: c_uint, offset: u64, layer0: *const stark_vec, root0: *const u8, out: *mut *mut stark_fri) -> c_int;
     pub fn stark_fri_open_layers(f: *const stark_fri, first_layer: usize, indices: *const u64, n_idx: usize, out: *mut u8, cap: usize, len: *mut usize) -> c_int;
     pub fn stark_fri_destroy(f: *mut stark_fri);
+    pub fn stark_fri_begin_to_host(ctx: *mut stark_ctx, coeffs: *const u64, n_coeffs: usize, log_n: c_uint, offset: u64, layers_out: *mut u64, cap: usize, out: *mut *mut stark_fri, root: *mut u8) -> c_int;
+    pub fn stark_fri_layers_wait(f: *const stark_fri) -> c_int;
+    pub fn stark_fri_layer_host_offset(f: *const stark_fri, k: usize) -> usize;
+    pub fn stark_fri_commit_to_host(ctx: *mut stark_ctx, coeffs: *const u64, n_coeffs: usize, log_n: c_uint, offset: u64, ch: *mut stark_channel, layers_out: *mut u64, cap: usize, out: *mut *mut stark_fri) -> c_int;
     pub fn stark_fri_commit(ctx: *mut stark_ctx, coeffs: *const u64, n_coeffs: usize, log_n: c_uint, offset: u64, ch: *mut stark_channel, out: *mut *mut stark_fri) -> c_int;
     pub fn stark_fri_commit_dev(ctx: *mut stark_ctx, coeffs: *const stark_vec, log_n: c_uint, offset: u64, ch: *mut stark_channel, out: *mut *mut stark_fri) -> c_int;
     pub fn stark_decommit_fri_layers(f: *const stark_fri, index: usize, ch: *mut stark_channel) -> c_int;

@@ -38,6 +38,11 @@ impl<const M: u64> FRIProof<M> {
         ffi::check(unsafe { ffi::stark_fri_layer_read(self.handle, k, offset, n, ffi::as_u64_mut_ptr(&mut out)) });
         out
     }
+    /// Element offset of layer k in the buffer given to `fri_commit_into` (`None`: the proof was not streamed to the host).
+    pub fn layer_host_offset(&self, k: usize) -> Option<usize> {
+        let o = unsafe { ffi::stark_fri_layer_host_offset(self.handle, k) };
+        if o == usize::MAX { None } else { Some(o) }
+    }
     pub(crate) fn raw(&self) -> *const ffi::stark_fri {
         self.handle
     }
@@ -62,7 +67,8 @@ fn hex_lower(bytes: &[u8; 32]) -> String {
     s
 }
 
-fn commit_loop<const M: u64>(poly: Polynomial<M>, domain: &CosetFri<M>, channel: &mut Channel<M>) -> (*mut ffi::stark_fri, Polynomial<M>) {
+fn commit_loop<const M: u64>(poly: Polynomial<M>, domain: &CosetFri<M>, channel: &mut Channel<M>,
+                             sink: Option<&mut [FieldElement<M>]>) -> (*mut ffi::stark_fri, Polynomial<M>) {
     assert!(domain.domain_size.is_power_of_two(), "FRI domain size must be a power of two");
     let log_n = domain.domain_size.trailing_zeros();
     let c = ffi::ctx::<M>();
@@ -70,11 +76,18 @@ fn commit_loop<const M: u64>(poly: Polynomial<M>, domain: &CosetFri<M>, channel:
                "the domain generator must be the library's root of unity (CosetFri::with_library_root)");
     let mut handle: *mut ffi::stark_fri = std::ptr::null_mut();
     let mut root = [0u8; 32];
-    // :78-79  evaluate on the coset, build the tree
-    ffi::check(unsafe {
-        ffi::stark_fri_begin(c, ffi::as_u64_ptr(&poly.coefficients), poly.coefficients.len(), log_n, domain.offset.value(), &mut handle,
-                             root.as_mut_ptr())
-    });
+    // :78-79  evaluate on the coset, build the tree (with a sink: every layer also streams to it on the copy stream)
+    let streaming = sink.is_some();
+    match sink {
+        None => ffi::check(unsafe {
+            ffi::stark_fri_begin(c, ffi::as_u64_ptr(&poly.coefficients), poly.coefficients.len(), log_n, domain.offset.value(), &mut handle,
+                                 root.as_mut_ptr())
+        }),
+        Some(buf) => ffi::check(unsafe {
+            ffi::stark_fri_begin_to_host(c, ffi::as_u64_ptr(&poly.coefficients), poly.coefficients.len(), log_n, domain.offset.value(),
+                                         ffi::as_u64_mut_ptr(buf), buf.len(), &mut handle, root.as_mut_ptr())
+        }),
+    }
     channel.send(hex_lower(&root).as_bytes()); // :86
     let mut degree: i64 = 0;
     loop {
@@ -91,6 +104,9 @@ fn commit_loop<const M: u64>(poly: Polynomial<M>, domain: &CosetFri<M>, channel:
     let final_value = FieldElement::<M>::new(value); // zero when the polynomial is zero (:109-113)
     channel.send(&final_value.to_bytes()); // :114
     let final_poly = if len == 0 { Polynomial::zero() } else { Polynomial::new(vec![final_value]) };
+    if streaming {
+        ffi::check(unsafe { ffi::stark_fri_layers_wait(handle) }); // the caller's buffer is complete when we return
+    }
     (handle, final_poly)
 }
 
@@ -101,7 +117,7 @@ fn borrow_trees<const M: u64>(handle: *mut ffi::stark_fri) -> Vec<MerkleTree<M>>
 
 /// fri_commit (reference :72-122), layers returned by value like the reference does.
 pub fn fri_commit<const M: u64>(poly: Polynomial<M>, domain: &CosetFri<M>, channel: &mut Channel<M>) -> FRIProof<M> {
-    let (handle, final_poly) = commit_loop(poly, domain, channel);
+    let (handle, final_poly) = commit_loop(poly, domain, channel, None);
     let layers = unsafe { ffi::stark_fri_num_layers(handle) };
     let mut fri_layers = Vec::with_capacity(layers);
     for k in 0..layers {
@@ -116,7 +132,17 @@ pub fn fri_commit<const M: u64>(poly: Polynomial<M>, domain: &CosetFri<M>, chann
 /// The same commit phase with the layers left in HBM (`fri_layers` empty; `read_layer` copies ranges on demand): what a
 /// prover that only opens a few dozen positions wants -- copying 2N elements back costs more than the whole commit.
 pub fn fri_commit_resident<const M: u64>(poly: Polynomial<M>, domain: &CosetFri<M>, channel: &mut Channel<M>) -> FRIProof<M> {
-    let (handle, final_poly) = commit_loop(poly, domain, channel);
+    let (handle, final_poly) = commit_loop(poly, domain, channel, None);
+    FRIProof { fri_layers: Vec::new(), fri_merkles: borrow_trees(handle), final_poly, handle }
+}
+
+/// The commit phase with every layer ALSO written by value into `layers` (layer k at `proof.layer_host_offset(k)`, u64 per
+/// element; `2 * domain_size` elements hold every layer), copied by the library's second stream while the following layers
+/// are hashed: the by-value `FRIProof` of the reference at (almost) the cost of `fri_commit_resident`, provided `layers` is
+/// page-locked (`cudaHostRegister` / `cudaHostAlloc`); `fri_layers` stays empty, the slice is the caller's.
+pub fn fri_commit_into<const M: u64>(poly: Polynomial<M>, domain: &CosetFri<M>, channel: &mut Channel<M>,
+                                     layers: &mut [FieldElement<M>]) -> FRIProof<M> {
+    let (handle, final_poly) = commit_loop(poly, domain, channel, Some(layers));
     FRIProof { fri_layers: Vec::new(), fri_merkles: borrow_trees(handle), final_poly, handle }
 }
 

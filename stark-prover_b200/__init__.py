@@ -151,6 +151,10 @@ def lib() -> C.CDLL:
     sig("stark_fri_destroy", None, vp)
     sig("stark_fri_commit", I, vp, vp, szt, C.c_uint, u64, vp, C.POINTER(vp))
     sig("stark_fri_commit_dev", I, vp, vp, C.c_uint, u64, vp, C.POINTER(vp))
+    sig("stark_fri_begin_to_host", I, vp, vp, szt, C.c_uint, u64, vp, szt, C.POINTER(vp), vp)
+    sig("stark_fri_layers_wait", I, vp)
+    sig("stark_fri_layer_host_offset", szt, vp, szt)
+    sig("stark_fri_commit_to_host", I, vp, vp, szt, C.c_uint, u64, vp, vp, szt, C.POINTER(vp))
     sig("stark_decommit_fri_layers", I, vp, szt, vp)
     sig("stark_decommit_fri", I, vp, szt, szt, vp)
     sig("stark101_prove", I, vp, u64, C.c_uint, C.c_uint, szt, vp)
@@ -554,6 +558,15 @@ class FriProof:
         _check(lib().stark_fri_layer_read(self.h, k, offset, n, _ptr(out)))
         return out[:n]
 
+    def layers_wait(self) -> None:
+        """Blocks until every layer copy issued so far by a *_to_host commit has landed in the host buffer."""
+        _check(lib().stark_fri_layers_wait(self.h))
+
+    def layer_host_offset(self, k: int) -> int:
+        """Element offset of layer k in the host buffer of a *_to_host commit (-1: none)."""
+        o = lib().stark_fri_layer_host_offset(self.h, k)
+        return -1 if o == (1 << (8 * C.sizeof(szt))) - 1 else int(o)
+
     def tree(self, k: int) -> MerkleTree:
         return MerkleTree(self.ctx, lib().stark_fri_layer_tree(self.h, k), owned=False, keep=self)
 
@@ -594,10 +607,18 @@ class FriProof:
             pass
 
 
-def fri_begin(ctx: Context, coeffs, log_n: int, offset: int) -> tuple[FriProof, bytes]:
-    """Layer 0 only (fri_commit.rs:78-86 without the send): returns the proof object and the root."""
+def fri_begin(ctx: Context, coeffs, log_n: int, offset: int, layers_out: Optional[np.ndarray] = None) -> tuple[FriProof, bytes]:
+    """Layer 0 only (fri_commit.rs:78-86 without the send): returns the proof object and the root.  `layers_out`: as in
+    fri_commit -- layer 0 and every later fold's layer stream to that host buffer; call `layers_wait()` before reading."""
     h = vp()
     root = np.zeros(32, dtype=np.uint8)
+    if layers_out is not None:
+        assert not isinstance(coeffs, Vec) and layers_out.dtype == np.uint64 and layers_out.flags["C_CONTIGUOUS"]
+        c = _arr(coeffs)
+        _check(lib().stark_fri_begin_to_host(ctx.h, _ptr(c), c.size, log_n, offset, _ptr(layers_out), layers_out.size, C.byref(h), _ptr(root)))
+        pr = FriProof(ctx, h)
+        pr._keep_layers = layers_out
+        return pr, root.tobytes()
     if isinstance(coeffs, Vec):
         _check(lib().stark_fri_begin_dev(ctx.h, coeffs.h, log_n, offset, C.byref(h), _ptr(root)))
     else:
@@ -616,9 +637,20 @@ def fri_begin_external(ctx: Context, coeffs: "Vec", log_n: int, offset: int, lay
     return pr
 
 
-def fri_commit(ctx: Context, poly, domain: CosetFri, channel: Channel) -> FriProof:
-    """fri_commit(poly, domain, &mut channel) (src/fri/fri_commit.rs:72-122)."""
+def fri_commit(ctx: Context, poly, domain: CosetFri, channel: Channel, layers_out: Optional[np.ndarray] = None) -> FriProof:
+    """fri_commit(poly, domain, &mut channel) (src/fri/fri_commit.rs:72-122).  With `layers_out` (uint64, >= 2^(log_size+1)
+    elements always suffice; pinned memory keeps the copies asynchronous) every layer is also returned BY VALUE, layer k at
+    `proof.layer_host_offset(k)`, copied on a second stream under the hashing of the following layers."""
     h = vp()
+    if layers_out is not None:
+        assert not isinstance(poly, Vec), "fri_commit(layers_out=...): host coefficients"
+        assert layers_out.dtype == np.uint64 and layers_out.flags["C_CONTIGUOUS"]
+        c = _arr(poly)
+        _check(lib().stark_fri_commit_to_host(ctx.h, _ptr(c), c.size, domain.log_size, domain.offset, channel.h,
+                                              _ptr(layers_out), layers_out.size, C.byref(h)))
+        pr = FriProof(ctx, h)
+        pr._keep_layers = layers_out
+        return pr
     if isinstance(poly, Vec):
         _check(lib().stark_fri_commit_dev(ctx.h, poly.h, domain.log_size, domain.offset, channel.h, C.byref(h)))
     else:

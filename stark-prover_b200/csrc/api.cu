@@ -126,6 +126,13 @@ void stark_ctx_teardown(stark_ctx* ctx) {
     ctx->small_fwd.release(); ctx->small_inv.release(); ctx->tail_counter.release(); ctx->deg_scratch.release();
     BlockCache::flush(ctx->stream);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        BlockCache::flush(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+        cudaEventDestroy(ctx->copy_event);
+    }
     for (int c = 0; c < stark_ctx::CAT_COUNT; c++) for (auto& pr : ctx->ev_used[c]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto e : ctx->ev_free) cudaEventDestroy(e);
     ctx->pin_desc.release(); ctx->pin_out.release(); ctx->pin_stage.release();
@@ -678,15 +685,53 @@ extern "C" size_t stark_channel_proof_flat(const stark_channel* ch, uint8_t* out
 }
 
 // ======================================================================================= FRI
+// ---- FRIProof.fri_layers by value: the layers stream to the host while the following ones are hashed ----
+// The copy stream has the highest priority, so the widening kernel's CTAs are placed as soon as hashing CTAs retire; each
+// layer is ~0.02 ms of HBM-bound widening and 8 B per element over PCIe, against 1384 integer instructions per leaf on the
+// main stream -- the copies of a 2^24-domain proof (269 MB) end before its commit phase does.
+static void ensure_copy_stream(stark_ctx* ctx) {
+    if (ctx->copy_stream) return;
+    int lo = 0, hi = 0;
+    STARK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    STARK_CUDA(cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, hi));
+    STARK_CUDA(cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming));
+}
+static std::unique_ptr<stark_fri::LayerSink> make_sink(stark_ctx* ctx, unsigned log_n, uint64_t* host, size_t cap) {
+    STARK_REQUIRE(host && cap >= ((size_t)1 << log_n), "fri: the host buffer must hold at least layer 0 (2^(log_n+1) elements hold every layer)");
+    ensure_copy_stream(ctx);
+    std::unique_ptr<stark_fri::LayerSink> s(new stark_fri::LayerSink());
+    s->stream = ctx->copy_stream; s->host = host; s->cap = cap;
+    s->stage = DevBuf(((size_t)8) << log_n, ctx->copy_stream);
+    return s;
+}
+// `vals` is complete in main-stream order at the time of the call (after_main: the copy stream waits for that point;
+// otherwise the caller has synchronised the main stream)
+static void sink_push(stark_fri* f, const uint32_t* vals, size_t n, bool after_main) {
+    stark_fri::LayerSink* s = f->sink.get();
+    if (!s) return;
+    stark_ctx* ctx = f->ctx;
+    STARK_REQUIRE(n <= s->cap - s->off, "fri: the host buffer for the layers is full (2^(log_n+1) elements hold every layer)");
+    if (after_main) {
+        STARK_CUDA(cudaEventRecord(ctx->copy_event, ctx->stream));
+        STARK_CUDA(cudaStreamWaitEvent(s->stream, ctx->copy_event, 0));
+    }
+    widen_u32_on(ctx, s->stream, vals, s->stage.as<uint64_t>(), n);
+    STARK_CUDA(cudaMemcpyAsync(s->host + s->off, s->stage.p, n * 8, cudaMemcpyDeviceToHost, s->stream));
+    s->offs.push_back(s->off);
+    s->off += n;
+}
+
 static void fri_begin_impl(stark_ctx* ctx, DevBufPtr coeffs_padded, size_t len, unsigned log_m, unsigned log_n,
-                           uint64_t offset, stark_fri** out, uint8_t root[32]) {
+                           uint64_t offset, stark_fri** out, uint8_t root[32], uint64_t* layers_out = nullptr, size_t layers_cap = 0) {
     STARK_REQUIRE(log_n <= ctx->two_adicity && log_n <= 30, "fri: 2^log_n does not divide p-1");
     STARK_REQUIRE(log_m <= log_n, "fri: polynomial has more coefficients than the domain has points");
     std::unique_ptr<stark_fri> f(new stark_fri());
     f->ctx = ctx; f->log_n = log_n; f->offset0 = offset % ctx->modulus;
     f->cur_log = log_n; f->cur_offset = f->offset0;
     f->coeffs = coeffs_padded; f->coeff_len = len;
+    if (layers_out || layers_cap) f->sink = make_sink(ctx, log_n, layers_out, layers_cap);
     DevBufPtr ev = evaluate_on_coset(ctx, f->coeffs->as<uint32_t>(), log_m, log_n, offset);          // fri_commit.rs:78
+    sink_push(f.get(), ev->as<uint32_t>(), (size_t)1 << log_n, true);     // ahead of the tree's launches: its CTAs go first
     LeafSource src; src.vals = ev->as<uint32_t>();
     auto t = tree_launch(ctx, ev, (size_t)1 << log_n, src);                                          // :79
     STARK_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -708,6 +753,32 @@ extern "C" int stark_fri_begin(stark_ctx* ctx, const uint64_t* coeffs, size_t n_
     DevBufPtr c = upload_u64(ctx, coeffs, len, (size_t)1 << log_m);
     fri_begin_impl(ctx, c, len, log_m, log_n, offset, out, root);
     API_END
+}
+extern "C" int stark_fri_begin_to_host(stark_ctx* ctx, const uint64_t* coeffs, size_t n_coeffs, unsigned log_n, uint64_t offset,
+                                       uint64_t* layers_out, size_t cap, stark_fri** out, uint8_t root[32]) {
+    API_BEGIN
+    STARK_REQUIRE(ctx && out && layers_out && (coeffs || n_coeffs == 0), "fri_begin_to_host: null argument");
+    CtxGuard g(ctx);
+    check_offset(ctx, offset);
+    size_t len = n_coeffs;
+    while (len > 0 && coeffs[len - 1] % ctx->modulus == 0) len--;
+    STARK_REQUIRE(log_n <= 30 && len <= ((size_t)1 << log_n), "fri: polynomial has more coefficients than the domain has points");
+    unsigned log_m = ceil_log2(std::max<size_t>(len, 1));
+    DevBufPtr c = upload_u64(ctx, coeffs, len, (size_t)1 << log_m);
+    fri_begin_impl(ctx, c, len, log_m, log_n, offset, out, root, layers_out, cap);
+    API_END
+}
+extern "C" int stark_fri_layers_wait(const stark_fri* f) {
+    API_BEGIN
+    STARK_REQUIRE(f, "fri_layers_wait: null argument");
+    if (f->sink) {
+        CtxGuard g(f->ctx);
+        STARK_CUDA(cudaStreamSynchronize(f->sink->stream));
+    }
+    API_END
+}
+extern "C" size_t stark_fri_layer_host_offset(const stark_fri* f, size_t k) {
+    return (f && f->sink && k < f->sink->offs.size()) ? f->sink->offs[k] : (size_t)-1;
 }
 extern "C" int stark_fri_begin_dev(stark_ctx* ctx, const stark_vec* coeffs, unsigned log_n, uint64_t offset, stark_fri** out,
                                    uint8_t root[32]) {
@@ -772,6 +843,7 @@ extern "C" int stark_fri_fold(stark_fri* f, uint64_t beta, uint8_t root[32]) {
     tree_take_root(t.get());
     if (f->coeff_len > 0) f->coeff_len = (size_t)ctx->h_result->degree_plus1;
     if (root) words_to_bytes(t->root_words, root);
+    sink_push(f, t->leaves->as<uint32_t>(), half, false);
     f->trees.push_back(std::move(t));
     f->cur_log -= 1;
     f->cur_offset = h_mul(f->cur_offset, f->cur_offset, p);
@@ -891,9 +963,9 @@ static void send_root(Channel& ch, const stark_tree* t) {
     std::string h = HostSha256::hex(r, 32);
     ch.send(reinterpret_cast<const uint8_t*>(h.data()), 64);    // root().as_bytes(): 64 ASCII hex chars (fri_verify.rs:24-25)
 }
-static int fri_commit_loop(stark_fri* f, stark_channel* chan) {
+static int fri_commit_loop(stark_fri* f, stark_channel* chan, bool send_first = true) {
     Channel& ch = chan->ch;
-    send_root(ch, f->trees[0].get());                                        // fri_commit.rs:86
+    if (send_first) send_root(ch, f->trees[0].get());                        // fri_commit.rs:86
     while ((long long)f->coeff_len - 1 >= 1) {                               // :89
         uint64_t beta;
         STARK_REQUIRE(ch.receive_random_field_element(&beta), "channel: receive before send");   // :91
@@ -915,6 +987,17 @@ extern "C" int stark_fri_commit(stark_ctx* ctx, const uint64_t* coeffs, size_t n
     if (rc != ST_OK) return rc;
     API_BEGIN
     rc = fri_commit_loop(*out, ch);
+    if (rc != ST_OK) { stark_fri_destroy(*out); *out = nullptr; return rc; }
+    API_END
+}
+extern "C" int stark_fri_commit_to_host(stark_ctx* ctx, const uint64_t* coeffs, size_t n_coeffs, unsigned log_n, uint64_t offset,
+                                        stark_channel* ch, uint64_t* layers_out, size_t cap, stark_fri** out) {
+    STARK_API_GUARD_NULL(ctx && ch && out && layers_out);
+    int rc = stark_fri_begin_to_host(ctx, coeffs, n_coeffs, log_n, offset, layers_out, cap, out, nullptr);
+    if (rc != ST_OK) return rc;
+    API_BEGIN
+    rc = fri_commit_loop(*out, ch);
+    if (rc == ST_OK) rc = stark_fri_layers_wait(*out);                       // by value: complete on return
     if (rc != ST_OK) { stark_fri_destroy(*out); *out = nullptr; return rc; }
     API_END
 }
@@ -1128,6 +1211,50 @@ std::unique_ptr<stark_tree> api_tree_launch_values(stark_ctx* ctx, DevBufPtr lea
     return tree_launch(ctx, std::move(leaves), n, src, result);
 }
 int api_fri_commit_loop(stark_fri* f, stark_channel* chan) { return fri_commit_loop(f, chan); }
+int api_fri_commit_loop_resume(stark_fri* f, stark_channel* chan) { return fri_commit_loop(f, chan, false); }
+// One fold whose tree is built elsewhere (leaf ranges of the new layer hashed on several GPUs, multi.cu): the evaluation-space
+// fold of the WHOLE layer and the coefficient-space fold with its exact degree are enqueued here; the caller hashes its
+// range, synchronises the stream, and hands the layer back with the combined root through api_fri_adopt_layer.
+DevBufPtr api_fri_fold_values(stark_fri* f, uint64_t beta) {
+    stark_ctx* ctx = f->ctx;
+    STARK_REQUIRE(f->cur_log >= 1, "fri_fold: the domain has one point left");
+    const uint64_t p = ctx->modulus;
+    const size_t half = ((size_t)1 << f->cur_log) >> 1;
+    DevBufPtr ev = make_buf(half * 4, ctx->stream);
+    LeafSource src;
+    src.prev = f->trees.back()->leaves->as<uint32_t>(); src.fold_out = ev->as<uint32_t>(); src.half = half;
+    const uint64_t inv2 = (p + 1) / 2;
+    if (f->half_over_offset == 0) f->half_over_offset = h_mul(inv2, h_inv(f->cur_offset, p), p);
+    src.inv2_m = ctx->to_mont(inv2);
+    src.sb_m = ctx->to_mont(h_mul(beta % p, f->half_over_offset, p));
+    src.winv = ctx->twiddles(f->cur_log).inv();
+    fri_fold(ctx, src);
+    if (f->coeff_len > 0) {
+        const size_t out_len = (f->coeff_len + 1) / 2;
+        DevBufPtr nc = make_buf(out_len * 4, ctx->stream);
+        coeff_fold(ctx, f->coeffs->as<uint32_t>(), f->coeff_len, ctx->to_mont(beta), nc->as<uint32_t>(), ctx->d_result);
+        f->coeffs = nc;            // (the old block goes back to the same stream: its release is ordered after the launch)
+    }
+    return ev;
+}
+// after a stream synchronisation: the degree the coefficient fold published, and the layer as a tree whose levels live elsewhere
+void api_fri_adopt_layer(stark_fri* f, DevBufPtr layer, const uint8_t root[32]) {
+    stark_ctx* ctx = f->ctx;
+    const uint64_t p = ctx->modulus;
+    if (f->coeff_len > 0) f->coeff_len = (size_t)ctx->h_result->degree_plus1;
+    std::unique_ptr<stark_tree> t(new stark_tree());
+    t->ctx = ctx; t->shape = TreeShape::make(((size_t)1 << f->cur_log) >> 1); t->leaves = std::move(layer); t->external = true;
+    for (int i = 0; i < 8; i++)
+        t->root_words[i] = ((uint32_t)root[4 * i] << 24) | ((uint32_t)root[4 * i + 1] << 16) | ((uint32_t)root[4 * i + 2] << 8) | root[4 * i + 3];
+    f->trees.push_back(std::move(t));
+    f->cur_log -= 1;
+    f->cur_offset = h_mul(f->cur_offset, f->cur_offset, p);
+    f->half_over_offset = h_mul(2 % p, h_mul(f->half_over_offset, f->half_over_offset, p), p);
+}
+// a batch of (element, path) records in one launch (BE8(value) || path each)
+void api_open_records(stark_ctx* ctx, const std::vector<OpenDesc>& descs, size_t total_bytes, uint8_t* host_out) {
+    open_records(ctx, descs, total_bytes, host_out);
+}
 void api_send_query_records(const stark_fri* f, const uint8_t* rec, Channel& ch, size_t index, size_t first_layer) {
     send_query_records(f, rec, ch, index, first_layer);
 }

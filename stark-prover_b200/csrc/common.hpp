@@ -211,6 +211,8 @@ struct KernelTimer {
 struct stark_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;         // created on first use (ensure_copy_stream): FRI layers on their way to the host
+    cudaEvent_t copy_event = nullptr;           //   while `stream` hashes the following layers (stark_fri_begin_to_host)
     uint64_t modulus = 0, generator = 0;
     unsigned two_adicity = 0;       // largest k with 2^k | p-1
     unsigned small_log = 0;         // size (log2) of the in-tile twiddle table

@@ -12,6 +12,7 @@
 #include <stdlib.h>
 
 #include "kernels.hpp"
+#include "coeff_job.cuh"
 
 namespace starkb200 {
 
@@ -55,6 +56,23 @@ void widen_u32(stark_ctx* ctx, const uint32_t* in, uint64_t* out, size_t n) {
     KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 12.0 * n);
     if (!n) return;
     widen_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(in, out, n);
+    ctx->launches++;
+    STARK_CUDA(cudaGetLastError());
+}
+// the same conversion on another stream (FRI layers streamed to the host under the hashing, api.cu: sink_push)
+__global__ void widen4_kernel(const uint4* in, ulonglong2* out, size_t n4) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const uint4 v = in[i];
+    out[2 * i] = make_ulonglong2(v.x, v.y);
+    out[2 * i + 1] = make_ulonglong2(v.z, v.w);
+}
+void widen_u32_on(stark_ctx* ctx, cudaStream_t s, const uint32_t* in, uint64_t* out, size_t n) {
+    if (!n) return;
+    if (n % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+        widen4_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<ulonglong2*>(out), n / 4);
+    else
+        widen_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, n);
     ctx->launches++;
     STARK_CUDA(cudaGetLastError());
 }
@@ -104,6 +122,15 @@ void coeff_fold_job(stark_ctx* ctx, const uint32_t* c, size_t len, uint32_t beta
     static const unsigned cap = [] { const char* e = getenv("STARK_COEFF_JOB_CTAS"); unsigned v = e ? (unsigned)atoi(e) : 0; return v ? v : COEFF_JOB_MAX_CTAS; }();
     job.ctas = (unsigned)(want < cap ? want : cap);
     job.result = result; job.scratch = deg_scratch(ctx);
+}
+// the coefficient fold as a launch of its own (a fold whose tree is built elsewhere has no hashing launch to ride in)
+__global__ void coeff_fold_kernel(CoeffJob job, FieldParams fp) { coeff_job_run(job, blockIdx.x, fp); }
+void coeff_fold(stark_ctx* ctx, const uint32_t* c, size_t len, uint32_t beta_m, uint32_t* out, HostResult* result) {
+    CoeffJob job{};
+    coeff_fold_job(ctx, c, len, beta_m, out, result, 256, job);
+    coeff_fold_kernel<<<job.ctas, 256, 0, ctx->stream>>>(job, ctx->fp);
+    ctx->launches++;
+    STARK_CUDA(cudaGetLastError());
 }
 void poly_degree(stark_ctx* ctx, const uint32_t* c, size_t len, HostResult* result) {
     KernelTimer kt(ctx, stark_ctx::CAT_OTHER, 8.0 * len);

@@ -35,6 +35,18 @@ struct stark_fri {
     starkb200::DevBufPtr coeffs;
     size_t coeff_len = 0;            // degree + 1 (0 = zero polynomial)
     std::vector<std::unique_ptr<stark_tree>> trees;
+    // FRIProof.fri_layers by value (fri_commit.rs:117-121): every layer is also widened to u64 and copied to host memory on
+    // the context's copy stream while the main stream hashes the following layers (stark_fri_begin_to_host).  Declared
+    // after `trees`: it dies first and waits for its copies, so no layer is released under a copy in flight.
+    struct LayerSink {
+        cudaStream_t stream = nullptr;
+        uint64_t* host = nullptr;
+        size_t cap = 0, off = 0;
+        std::vector<size_t> offs;        // element offset of layer k in `host`
+        starkb200::DevBuf stage;         // u64 staging for one layer (the largest); reused in copy-stream order
+        ~LayerSink() { if (stream) cudaStreamSynchronize(stream); }
+    };
+    std::unique_ptr<LayerSink> sink;
 };
 
 struct stark_channel {

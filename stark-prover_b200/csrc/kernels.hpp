@@ -47,6 +47,8 @@ struct LeafSource {
 unsigned merkle_first_launch_threads(size_t n);
 // fills src.job (fri.cu): c -> out with beta, degree to `result`
 void coeff_fold_job(stark_ctx* ctx, const uint32_t* c, size_t len, uint32_t beta_m, uint32_t* out, HostResult* result, unsigned cta_threads, CoeffJob& job);
+// the same fold as a launch of its own
+void coeff_fold(stark_ctx* ctx, const uint32_t* c, size_t len, uint32_t beta_m, uint32_t* out, HostResult* result);
 
 // Builds levels 1..depth into `nodes` (TreeShape layout); when `result` is non-null the root's 8 state
 // words are also written there (mapped host memory).  Leaf digests are not stored.
@@ -125,6 +127,7 @@ void build_scale_table(stark_ctx* ctx, uint64_t base, uint64_t c0, unsigned log_
 // ---------------- element-wise / FRI helpers (fri.cu) ----------------
 void narrow_u64(stark_ctx* ctx, const uint64_t* in, uint32_t* out, size_t n);      // v % p  (FieldElement::new)
 void widen_u32(stark_ctx* ctx, const uint32_t* in, uint64_t* out, size_t n);
+void widen_u32_on(stark_ctx* ctx, cudaStream_t s, const uint32_t* in, uint64_t* out, size_t n);
 void fill_zero(stark_ctx* ctx, uint32_t* p, size_t n);
 // c'[j] = c[2j] + beta*c[2j+1]; result->degree_plus1 = 1 + max{j : c'[j] != 0} (0 for the zero poly)
 void poly_degree(stark_ctx* ctx, const uint32_t* c, size_t len, HostResult* result);

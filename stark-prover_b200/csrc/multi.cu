@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <array>
+#include <deque>
 
 #include "../../include/stark_b200.h"
 #include "handles.hpp"
@@ -29,6 +30,10 @@ DevBufPtr api_upload_u64(stark_ctx* ctx, const uint64_t* host, size_t n);
 DevBufPtr api_lde_on_coset(stark_ctx* ctx, const uint32_t* evals, unsigned log_n, uint64_t offset_in, unsigned log_blowup, uint64_t offset_out);
 std::unique_ptr<stark_tree> api_tree_launch_values(stark_ctx* ctx, DevBufPtr leaves, size_t n, HostResult* result);
 int api_fri_commit_loop(stark_fri* f, stark_channel* chan);
+int api_fri_commit_loop_resume(stark_fri* f, stark_channel* chan);
+DevBufPtr api_fri_fold_values(stark_fri* f, uint64_t beta);
+void api_fri_adopt_layer(stark_fri* f, DevBufPtr layer, const uint8_t root[32]);
+void api_open_records(stark_ctx* ctx, const std::vector<OpenDesc>& descs, size_t total_bytes, uint8_t* host_out);
 void api_send_query_records(const stark_fri* f, const uint8_t* rec, Channel& ch, size_t index, size_t first_layer);
 DevBufPtr api_interpolate_on_coset(stark_ctx* ctx, const uint32_t* evals, unsigned log_n, uint64_t offset);
 void api_send_root_bytes(Channel& ch, const uint8_t root[32]);
@@ -151,13 +156,22 @@ struct stark_mg {
     std::map<unsigned, std::unique_ptr<P2PState>> p2p;
     std::map<unsigned, std::unique_ptr<StagedState>> staged;
 };
+// One FRI layer >= 1 hashed in leaf ranges: this rank's range of the values (a private copy), its subtree, all subtree roots.
+struct ShardedLayer {
+    std::unique_ptr<stark_vec> block;
+    std::unique_ptr<stark_tree> subtree;
+    std::vector<uint8_t> subtree_roots;  // world * 32
+    size_t n = 0;                        // leaves of the whole layer
+};
 struct stark_mg_fri {
     stark_mg* mg = nullptr;
     unsigned log_n = 0;
     stark_vec* block = nullptr;          // this rank's leaf range of layer 0 (borrowed from the transport when owned == false)
     stark_tree* subtree = nullptr;       // its tree
     std::vector<uint8_t> subtree_roots;  // world * 32
-    stark_fri* proof = nullptr;          // rank 0: layer 0 adopted, layers >= 1 built here
+    std::vector<ShardedLayer> sharded;   // layers 1 .. S, hashed in leaf ranges as well (sharded_fri_layers)
+    stark_fri* proof = nullptr;          // rank 0 (every rank when layers >= 1 are sharded: the folds are replicated):
+                                         // layers 0 .. S adopted, the later ones built here on rank 0
 };
 
 namespace {
@@ -174,9 +188,9 @@ struct MgGuard {
     catch (const std::exception& e) { api_set_error(e.what()); return ST_INTERNAL; }        \
     return ST_OK;
 
-constexpr size_t SMALL_BYTES = (size_t)1 << 16;
+constexpr size_t SMALL_BYTES = (size_t)1 << 20;
 
-// every rank contributes `bytes` (<= 64 KiB / world): out = world * bytes, identical on every rank
+// every rank contributes `bytes` (<= 512 KiB / (world + 1)): out = world * bytes, identical on every rank
 void gather_bytes(stark_mg* mg, const void* in, size_t bytes, void* out) {
     if (mg->world == 1) { memcpy(out, in, bytes); return; }
     STARK_REQUIRE(bytes * (mg->world + 1) <= SMALL_BYTES / 2, "gather_bytes: payload too large");
@@ -342,39 +356,121 @@ std::unique_ptr<stark_tree> commit_leaf_range(stark_mg* mg, DevBufPtr block, siz
     return t;
 }
 
-// Openings of `count` leaves of a column committed in leaf ranges: each owner opens its subtree, everybody learns the
-// records, rank 0 appends the levels above the subtree roots and feeds (element, path) pairs to the channel in order.
-void open_leaf_ranges(stark_mg* mg, const stark_vec* block, const stark_tree* subtree, const uint8_t* subtree_roots, const size_t* which,
-                      size_t count, size_t n_total, Channel* ch) {
+// Openings of leaves of columns committed in leaf ranges, any number of columns / layers in ONE exchange: each owner opens
+// its records with one launch, one all-gather tells everybody, rank 0 appends the levels above the subtree roots and
+// feeds (element, path) pairs to the channel in the order of `items`.
+struct LeafRangeSet {
+    const stark_vec* block;            // this rank's range of the values
+    const stark_tree* subtree;         // its tree
+    const uint8_t* subtree_roots;      // world * 32
+    size_t n_total;                    // leaves of the whole column
+};
+struct OpenItem { const LeafRangeSet* set; size_t which; };
+void open_leaf_ranges_batch(stark_mg* mg, const std::vector<OpenItem>& items, Channel* ch) {
     const unsigned world = mg->world, rank = mg->rank;
-    const size_t blk = n_total / world, depth_local = ilog2(blk), rec_len = 8 + 32 * depth_local;
-    std::vector<uint8_t> payload(count * rec_len, 0), all((size_t)world * count * rec_len), top(32 * 8);
-    for (size_t t = 0; t < count; t++) {
-        if (which[t] / blk != rank) continue;
-        const size_t local = which[t] % blk;
-        uint64_t v;
-        int rc = stark_vec_download(block, local, 1, &v);
-        if (rc != ST_OK) throw StarkError(rc, stark_last_error());
-        be8(v, payload.data() + t * rec_len);
-        size_t pl = 0;
-        rc = stark_merkle_open(subtree, local, payload.data() + t * rec_len + 8, 32 * depth_local, &pl);
-        if (rc != ST_OK) throw StarkError(rc, stark_last_error());
+    std::vector<size_t> off(items.size() + 1, 0);
+    std::vector<OpenDesc> mine;
+    for (size_t t = 0; t < items.size(); t++) {
+        const LeafRangeSet& s = *items[t].set;
+        const size_t blk = s.n_total / world;
+        STARK_REQUIRE(items[t].which < s.n_total, "open_leaf_ranges: leaf index out of range");
+        off[t + 1] = off[t] + 8 + 32 * ilog2(blk);
+        if (items[t].which / blk == rank)
+            mine.push_back(OpenDesc{s.block->buf->as<uint32_t>(), s.subtree->nodes.as<uint32_t>(), blk, items[t].which % blk, off[t]});
     }
-    gather_bytes(mg, payload.data(), payload.size(), all.data());
+    const size_t bytes = off.back();
+    std::vector<uint8_t> payload(bytes, 0), all((size_t)world * bytes), top(32 * 8);
+    if (!mine.empty()) api_open_records(mg->ctx, mine, bytes, payload.data());
+    gather_bytes(mg, payload.data(), bytes, all.data());
     if (rank != 0) return;
-    for (size_t t = 0; t < count; t++) {
-        const unsigned owner = (unsigned)(which[t] / blk);
-        const uint8_t* rec = all.data() + (size_t)owner * count * rec_len + t * rec_len;
-        std::vector<uint8_t> path(rec + 8, rec + rec_len);
-        const size_t tl = top_path(subtree_roots, world, owner, top.data());
+    std::vector<uint8_t> path;
+    for (size_t t = 0; t < items.size(); t++) {
+        const LeafRangeSet& s = *items[t].set;
+        const unsigned owner = (unsigned)(items[t].which / (s.n_total / world));
+        const uint8_t* rec = all.data() + (size_t)owner * bytes + off[t];
+        path.assign(rec + 8, rec + (off[t + 1] - off[t]));
+        const size_t tl = top_path(s.subtree_roots, world, owner, top.data());
         path.insert(path.end(), top.begin(), top.begin() + tl);
         ch->send(rec, 8);
         ch->send(path.data(), path.size());
     }
 }
+void open_leaf_ranges(stark_mg* mg, const stark_vec* block, const stark_tree* subtree, const uint8_t* subtree_roots, const size_t* which,
+                      size_t count, size_t n_total, Channel* ch) {
+    LeafRangeSet set{block, subtree, subtree_roots, n_total};
+    std::vector<OpenItem> items;
+    for (size_t t = 0; t < count; t++) items.push_back(OpenItem{&set, which[t]});
+    open_leaf_ranges_batch(mg, items, ch);
+}
+// idx and its FRI sibling in every layer hashed in leaf ranges (fri_commit.rs:152-153)
+void sharded_layer_items(const std::vector<ShardedLayer>& layers, std::deque<LeafRangeSet>& sets, size_t index, std::vector<OpenItem>& items) {
+    const size_t first = sets.size();
+    for (const ShardedLayer& l : layers) sets.push_back(LeafRangeSet{l.block.get(), l.subtree.get(), l.subtree_roots.data(), l.n});
+    for (size_t k = 0; k < layers.size(); k++) {
+        const size_t len = layers[k].n, idx = index % len;
+        items.push_back(OpenItem{&sets[first + k], idx});
+        items.push_back(OpenItem{&sets[first + k], (idx + len / 2) % len});
+    }
+}
 
 stark_vec* wrap_vec(stark_ctx* ctx, DevBufPtr b, size_t n) {
     stark_vec* v = new stark_vec(); v->ctx = ctx; v->buf = std::move(b); v->n = n; return v;
+}
+
+stark_vec* wrap_vec(stark_ctx* ctx, DevBufPtr b, size_t n);
+std::unique_ptr<stark_tree> commit_leaf_range(stark_mg* mg, DevBufPtr block, size_t n_loc, uint8_t root[32], uint8_t* subtree_roots);
+// ---- FRI layers >= 1 while they are large: leaf hashing in ranges, everything else replicated -------------------------
+// The north-star partitions leaf hashing and nothing else.  A FRI layer is 12 bytes of HBM traffic per point to fold and
+// 1384 integer instructions per leaf (plus the nodes) to commit, so the fold is replicated -- every rank holds layer 0 (one
+// all-gather instead of the gather on rank 0), folds the WHOLE next layer and the coefficients itself, and no data-path
+// exchange follows -- while the tree is hashed in leaf ranges: 32 bytes of subtree root per rank travel to everybody, the
+// top log2(world) levels are finished on the host, rank 0 feeds the channel and beta (8 bytes) travels back.  Layers below
+// 2^STARK_MG_FRI_SHARD_MIN_LOG leaves (default 2^21: a layer costs ~0.16 ns per leaf to hash against ~0.12 ms for the two
+// small collectives and the extra launches) are left to rank 0's ordinary loop.
+unsigned shard_min_log() {
+    const char* e = getenv("STARK_MG_FRI_SHARD_MIN_LOG");
+    const int v = e ? atoi(e) : 0;
+    return v >= 6 && v <= 30 ? (unsigned)v : 21u;
+}
+bool shard_forced() { const char* e = getenv("STARK_MG_FRI_SHARD_FORCE"); return e && atoi(e) != 0; }      // tests: one rank takes the sharded path
+bool shard_wanted(const stark_mg* mg, unsigned log_n) {
+    if (mg->world == 1 && !shard_forced()) return false;
+    const char* off = getenv("STARK_MG_FRI_SHARD");
+    if (off && atoi(off) == 0) return false;
+    return log_n >= 1 && log_n - 1 >= shard_min_log() && (((size_t)1 << (log_n - 1)) / mg->world) >= 2;
+}
+// Every rank holds `proof` with identical layers and coefficients; `chan` on rank 0 only.  Collective.
+void sharded_fri_layers(stark_mg* mg, stark_fri* proof, Channel* chan, std::vector<ShardedLayer>& out) {
+    stark_ctx* ctx = mg->ctx;
+    const unsigned world = mg->world, rank = mg->rank;
+    const size_t min_len = (size_t)1 << shard_min_log();
+    while ((long long)proof->coeff_len - 1 >= 1 && proof->cur_log >= 1) {                     // fri_commit.rs:89
+        const size_t half = ((size_t)1 << proof->cur_log) >> 1, blk = half / world;
+        if (half < min_len || blk < 2) break;
+        uint64_t beta = 0;
+        if (rank == 0) STARK_REQUIRE(chan->receive_random_field_element(&beta), "channel: receive before send");     // :91
+        beta = bcast_u64(mg, beta);
+        DevBufPtr layer = api_fri_fold_values(proof, beta);                                    // :94, whole layer, every rank
+        DevBufPtr mine = make_buf(blk * 4, ctx->stream);
+        STARK_CUDA(cudaMemcpyAsync(mine->p, layer->as<uint32_t>() + (size_t)rank * blk, blk * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        ShardedLayer sl;
+        sl.n = half;
+        sl.subtree_roots.resize((size_t)world * 32);
+        uint8_t root[32];
+        sl.subtree = commit_leaf_range(mg, mine, blk, root, sl.subtree_roots.data());           // :97 (synchronises: the degree is in too)
+        api_fri_adopt_layer(proof, layer, root);
+        if (rank == 0) api_send_root_bytes(*chan, root);                                       // :100
+        sl.block.reset(wrap_vec(ctx, mine, blk));
+        out.push_back(std::move(sl));
+    }
+}
+// layer 0 of a sharded proof on every rank: this rank's block + everybody else's
+DevBufPtr allgather_layer(stark_mg* mg, const DevBufPtr& block, size_t blk) {
+    stark_ctx* ctx = mg->ctx;
+    if (mg->world == 1) return block;
+    DevBufPtr all = make_buf(blk * mg->world * 4, ctx->stream);
+    STARK_NCCL(nccl().AllGather(block->p, all->p, blk, NCCL_UINT32, mg->comm, ctx->stream));
+    return all;
 }
 
 }  // namespace
@@ -554,9 +650,11 @@ extern "C" int stark_mg_fri_commit(stark_mg* mg, const stark_vec* coeffs, unsign
     f->subtree_roots.resize((size_t)world * 32);
     uint8_t root0[32];
     auto sub = commit_leaf_range(mg, b, blk, root0, f->subtree_roots.data());
-    // collect layer 0 on rank 0
+    // layer 0: on every rank when the following layers are hashed in leaf ranges too (the folds are replicated), else on rank 0
+    const bool shard = shard_wanted(mg, log_n);
     DevBufPtr layer0;
     if (world == 1) layer0 = b;
+    else if (shard) layer0 = allgather_layer(mg, b, blk);
     else {
         Nccl& n = nccl();
         if (rank == 0) {
@@ -575,14 +673,18 @@ extern "C" int stark_mg_fri_commit(stark_mg* mg, const stark_vec* coeffs, unsign
     sub->leaves = keep;
     f->block = wrap_vec(ctx, keep, blk);
     f->subtree = sub.release();
-    if (rank == 0) {
+    if (rank == 0 || shard) {
         stark_vec l0; l0.ctx = ctx; l0.buf = layer0; l0.n = N;
         int rc = stark_fri_begin_external(ctx, coeffs, log_n, offset, &l0, root0, &f->proof);
-        if (rc == ST_OK) rc = api_fri_commit_loop(f->proof, ch);
+        if (rc == ST_OK && !shard) rc = api_fri_commit_loop(f->proof, ch);
+        if (rc == ST_OK && shard) {
+            if (rank == 0) api_send_root_bytes(ch->ch, root0);                                 // fri_commit.rs:86
+            sharded_fri_layers(mg, f->proof, rank == 0 ? &ch->ch : nullptr, f->sharded);
+            if (rank == 0) rc = api_fri_commit_loop_resume(f->proof, ch);                      // the small layers and the final constant
+        }
         if (rc != ST_OK) { stark_mg_fri_destroy(f.release()); return rc; }
-    } else {
-        STARK_CUDA(cudaStreamSynchronize(ctx->stream));
     }
+    STARK_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = f.release();
     MG_END
 }
@@ -613,19 +715,26 @@ extern "C" int stark_mg_decommit_fri(stark_mg_fri* f, size_t num_queries, size_t
         uint64_t idx = 0;
         if (rank == 0) STARK_REQUIRE(ch->ch.receive_random_int(0, max_index, true, &idx), "channel: receive before send");
         idx = bcast_u64(mg, idx);
-        const size_t i0 = (size_t)idx % N, which[2] = {i0, (i0 + N / 2) % N};
-        open_leaf_ranges(mg, f->block, f->subtree, f->subtree_roots.data(), which, 2, N, rank == 0 ? &ch->ch : nullptr);   // layer 0: :156-163
+        const size_t i0 = (size_t)idx % N;
+        std::deque<LeafRangeSet> sets;
+        std::vector<OpenItem> items;
+        sets.push_back(LeafRangeSet{f->block, f->subtree, f->subtree_roots.data(), N});
+        items.push_back(OpenItem{&sets[0], i0});                                               // layer 0: :156-163
+        items.push_back(OpenItem{&sets[0], (i0 + N / 2) % N});
+        sharded_layer_items(f->sharded, sets, (size_t)idx, items);                             // layers 1 .. S, same exchange
+        open_leaf_ranges_batch(mg, items, rank == 0 ? &ch->ch : nullptr);
         if (rank != 0) continue;
+        const size_t first = 1 + f->sharded.size();
         size_t len = 0;
         const uint64_t i64 = idx;
-        int rc = stark_fri_open_layers(f->proof, 1, &i64, 1, nullptr, 0, &len);
+        int rc = stark_fri_open_layers(f->proof, first, &i64, 1, nullptr, 0, &len);
         if (rc != ST_OK) return rc;
         blob.resize(len);
         if (len) {
-            rc = stark_fri_open_layers(f->proof, 1, &i64, 1, blob.data(), blob.size(), &len);
+            rc = stark_fri_open_layers(f->proof, first, &i64, 1, blob.data(), blob.size(), &len);
             if (rc != ST_OK) return rc;
         }
-        api_send_query_records(f->proof, blob.data(), ch->ch, (size_t)idx, 1);
+        api_send_query_records(f->proof, blob.data(), ch->ch, (size_t)idx, first);
     }
     MG_END
 }
@@ -689,11 +798,15 @@ extern "C" int stark_mg_stark101_prove(stark_mg* mg, uint64_t a1, unsigned log_t
     if (rc != ST_OK) return rc;
     std::unique_ptr<stark_vec> cp_guard(cp_vec);
     auto cp_sub = commit_leaf_range(mg, cp_vec->buf, blk, cp_root, cp_subs.data());
-    // ---- src/fri on rank 0: layer 0 = the collected CP evaluations, its coefficients by interpolation (degree tracking)
+    // ---- src/fri: layer 0 = the CP evaluations, its coefficients by interpolation (degree tracking).  With the large layers
+    // >= 1 hashed in leaf ranges every rank holds layer 0 and replicates the folds (sharded_fri_layers); otherwise rank 0 alone
+    const bool shard = shard_wanted(mg, log_n);
     std::unique_ptr<stark_fri> proof;
-    if (world == 1 || rank == 0) {
+    std::vector<ShardedLayer> sharded;
+    if (world == 1 || rank == 0 || shard) {
         DevBufPtr layer0;
         if (world == 1) layer0 = cp_vec->buf;
+        else if (shard) layer0 = allgather_layer(mg, cp_vec->buf, blk);
         else {
             Nccl& n = nccl();
             layer0 = make_buf(N * 4, ctx->stream);
@@ -709,33 +822,45 @@ extern "C" int stark_mg_stark101_prove(stark_mg* mg, uint64_t a1, unsigned log_t
         rc = stark_fri_begin_external(ctx, &cc, log_n, w, &l0, cp_root, &pf);
         if (rc != ST_OK) return rc;
         proof.reset(pf);
-        rc = api_fri_commit_loop(pf, ch);
+        if (!shard) rc = api_fri_commit_loop(pf, ch);
+        else {
+            if (rank == 0) api_send_root_bytes(*chan, cp_root);
+            sharded_fri_layers(mg, pf, chan, sharded);
+            if (rank == 0) rc = api_fri_commit_loop_resume(pf, ch);
+        }
         if (rc != ST_OK) return rc;
     } else {
         STARK_NCCL(nccl().Send(cp_vec->buf->p, blk, NCCL_UINT32, 0, mg->comm, ctx->stream));
         STARK_CUDA(cudaStreamSynchronize(ctx->stream));
     }
-    // ---- queries: f(x), f(gx), f(g^2 x) and layer 0 of the FRI from their owners, the other layers on rank 0
+    // ---- queries: f(x), f(gx), f(g^2 x), layer 0 of the FRI and its layers hashed in leaf ranges from their owners in one
+    // exchange per query, the other layers on rank 0
     std::vector<uint8_t> blob;
     for (size_t q = 0; q < num_queries; q++) {
         uint64_t idx = 0;
         if (rank == 0) STARK_REQUIRE(chan->receive_random_int(0, N - 1 - 2 * blow, true, &idx), "channel: receive before send");
         idx = bcast_u64(mg, idx);
-        const size_t fw[3] = {(size_t)idx, (size_t)idx + blow, (size_t)idx + 2 * blow};
-        open_leaf_ranges(mg, &f_vec, f_sub.get(), f_subs.data(), fw, 3, N, chan);
-        const size_t cw[2] = {(size_t)idx % N, ((size_t)idx + N / 2) % N};
-        open_leaf_ranges(mg, cp_vec, cp_sub.get(), cp_subs.data(), cw, 2, N, chan);
+        std::deque<LeafRangeSet> sets;
+        std::vector<OpenItem> items;
+        sets.push_back(LeafRangeSet{&f_vec, f_sub.get(), f_subs.data(), N});
+        sets.push_back(LeafRangeSet{cp_vec, cp_sub.get(), cp_subs.data(), N});
+        for (size_t k = 0; k < 3; k++) items.push_back(OpenItem{&sets[0], (size_t)idx + k * blow});
+        items.push_back(OpenItem{&sets[1], (size_t)idx % N});
+        items.push_back(OpenItem{&sets[1], ((size_t)idx + N / 2) % N});
+        sharded_layer_items(sharded, sets, (size_t)idx, items);
+        open_leaf_ranges_batch(mg, items, chan);
         if (rank != 0) continue;
+        const size_t first = 1 + sharded.size();
         size_t len = 0;
         const uint64_t i64 = idx;
-        rc = stark_fri_open_layers(proof.get(), 1, &i64, 1, nullptr, 0, &len);
+        rc = stark_fri_open_layers(proof.get(), first, &i64, 1, nullptr, 0, &len);
         if (rc != ST_OK) return rc;
         blob.resize(len);
         if (len) {
-            rc = stark_fri_open_layers(proof.get(), 1, &i64, 1, blob.data(), blob.size(), &len);
+            rc = stark_fri_open_layers(proof.get(), first, &i64, 1, blob.data(), blob.size(), &len);
             if (rc != ST_OK) return rc;
         }
-        api_send_query_records(proof.get(), blob.data(), *chan, (size_t)idx, 1);
+        api_send_query_records(proof.get(), blob.data(), *chan, (size_t)idx, first);
     }
     MG_END
 }

@@ -183,6 +183,72 @@ def test_mg_fri_commit_world1(sp, orc, ctx, transport):
     f.free(); g.close()
 
 
+@pytest.fixture
+def forced_sharding(monkeypatch):
+    """One rank takes the path that hashes the large FRI layers >= 1 in leaf ranges (on N > 1 GPUs it is the default)."""
+    monkeypatch.setenv("STARK_MG_FRI_SHARD_FORCE", "1")
+    monkeypatch.setenv("STARK_MG_FRI_SHARD_MIN_LOG", "8")
+
+
+@pytest.mark.parametrize("log_n,log_deg,q", [(14, 11, 3), (16, 13, 5), (12, 12, 2), (10, 3, 2)])
+def test_mg_fri_commit_sharded_layers_world1(sp, orc, ctx, forced_sharding, log_n, log_deg, q):
+    """stark_mg_fri_commit with the FRI layers >= 1 hashed in leaf ranges too (replicated folds + stand-alone coefficient
+    fold, trees adopted from their combined roots, every leaf-range opening of a query in one exchange): with one rank the
+    transcript is fri_commit's and the oracle's, byte for byte, and the verifier accepts it."""
+    g = sp.MultiGpu(ctx, 0, 1)
+    c = orc.synthetic_poly_exact_degree(40 + log_n, 1 << log_deg)
+    ch, ch1, och = sp.Channel(P), sp.Channel(P), orc.Channel(P)
+    f = g.fri_commit(ctx.upload(c), log_n, 5, ch, 1)
+    g.decommit_fri(f, q, (1 << log_n) - 1, ch)
+    pr = sp.fri_commit(ctx, c, sp.CosetFri(ctx, 5, log_n), ch1)
+    sp.decommit_fri(q, (1 << log_n) - 1, pr, ch1)
+    opr = orc.fri_commit_fast(c, log_n, 5, orc.root_of_unity(log_n), och, P)
+    orc.decommit_fri(q, (1 << log_n) - 1, opr, och)
+    assert ch.state == ch1.state == och.state and ch.proof == ch1.proof == och.proof
+    mp = f.proof
+    assert mp.num_layers == pr.num_layers
+    for k in range(mp.num_layers):
+        assert mp.tree(k).root() == pr.tree(k).root() and np.array_equal(mp.layer(k), pr.layer(k)), f"layer {k}"
+    if log_n >= 10 and log_deg >= 8:
+        with pytest.raises(sp.StarkError):
+            mp.tree(1).get_authentication_path(0)        # layer 1's levels live in the leaf-range subtree, not in the proof object
+    ok, why = sp.verify_fri(ch.proof_flat(), log_n, 5, q, (1 << log_n) - 1, log_deg)
+    assert ok, why
+    f.free(); g.close()
+
+
+def test_mg_fri_sharded_sparse_polynomial_world1(sp, orc, ctx, forced_sharding):
+    """The loop condition of the sharded layers is the exact degree (fri_commit.rs:89), tracked by the stand-alone
+    coefficient fold: a sparse polynomial (powers of x^4 only, trailing zeros trimmed by Polynomial::new) takes the
+    reference's number of layers."""
+    log_n = 12
+    c = np.zeros(1 << 9, dtype=np.uint64)
+    c[::4] = orc.synthetic_column(3, 1 << 7)
+    c[-4] = 0                                         # the top power present is x^500
+    g = sp.MultiGpu(ctx, 0, 1)
+    ch, och = sp.Channel(P), orc.Channel(P)
+    f = g.fri_commit(ctx.upload(c), log_n, 5, ch, 1)
+    g.decommit_fri(f, 2, (1 << log_n) - 1, ch)
+    opr = orc.fri_commit_fast(c, log_n, 5, orc.root_of_unity(log_n), och, P)
+    orc.decommit_fri(2, (1 << log_n) - 1, opr, och)
+    assert f.proof.num_layers == opr.num_layers
+    assert ch.state == och.state and ch.proof == och.proof
+    f.free(); g.close()
+
+
+@pytest.mark.parametrize("log_trace,log_blowup,a1,q", [(8, 3, 3141592, 3), (13, 3, 99, 4)])
+def test_mg_stark101_prove_sharded_layers_world1(sp, orc, ctx, forced_sharding, log_trace, log_blowup, a1, q):
+    g = sp.MultiGpu(ctx, 0, 1)
+    ch, och = sp.Channel(P), orc.Channel(P)
+    g.stark101_prove(ch, a1, log_trace, log_blowup, q, 1)
+    orc.stark101_prove(och, a1, log_trace, log_blowup, sp.G_DEFAULT, q, literal=False)
+    assert ch.state == och.state and ch.proof == och.proof
+    claimed = int(orc.fibsq_trace(a1, (1 << log_trace) - 1)[(1 << log_trace) - 2])
+    ok, why = sp.stark101_verify(ch.proof_flat(), claimed, log_trace, log_blowup, q)
+    assert ok, why
+    g.close()
+
+
 @pytest.mark.parametrize("log_trace,log_blowup,a1,q,transport", [(8, 3, 3141592, 3, 1), (12, 3, 99, 4, 0), (15, 3, 3141592, 3, 1)])
 def test_mg_stark101_prove_world1(sp, orc, ctx, log_trace, log_blowup, a1, q, transport):
     """The C-level sharded prover with one rank: stark101_prove's transcript (and the oracle's); the verifier accepts it."""

@@ -454,6 +454,61 @@ def test_fri_device_resident_input(sp, orc, ctx):
     assert np.array_equal(v.download(), c)
 
 
+def test_fri_layers_by_value_streamed_to_host(sp, orc, ctx):
+    """FRIProof.fri_layers by value (fri_commit.rs:117-121): the layers a *_to_host commit streams to host memory on the
+    copy stream equal the oracle's layers and what stark_fri_layer_read returns; same transcript as the resident commit;
+    pageable and pinned destinations, the step API, a destination that is too small."""
+    import torch
+    for log_n, log_deg, pinned in ((12, 9, False), (16, 13, True), (20, 17, True), (5, 5, False), (4, 0, False)):
+        c = orc.synthetic_poly_exact_degree(77 + log_n, 1 << log_deg)
+        cap = 2 << log_n
+        keep = torch.empty(cap, dtype=torch.int64).pin_memory() if pinned else None
+        buf = keep.numpy().view(np.uint64) if pinned else np.empty(cap, dtype=np.uint64)
+        buf[:] = np.uint64(0xDEADBEEFDEADBEEF)
+        ch, ch0, och = sp.Channel(P), sp.Channel(P), orc.Channel(P)
+        pr = sp.fri_commit(ctx, c, sp.CosetFri(ctx, 5, log_n), ch, layers_out=buf)
+        p0 = sp.fri_commit(ctx, c, sp.CosetFri(ctx, 5, log_n), ch0)
+        opr = orc.fri_commit_fast(c, log_n, 5, orc.root_of_unity(log_n), och, P)
+        assert ch.state == ch0.state == och.state and pr.num_layers == opr.num_layers
+        off = 0
+        for k in range(pr.num_layers):
+            ln = pr.layer_len(k)
+            assert pr.layer_host_offset(k) == off
+            assert np.array_equal(buf[off:off + ln], opr.layer(k)), f"log_n {log_n} layer {k}"
+            assert np.array_equal(buf[off:off + ln], pr.layer(k))
+            off += ln
+        assert pr.layer_host_offset(pr.num_layers) == -1 and p0.layer_host_offset(0) == -1
+        assert np.all(buf[off:] == np.uint64(0xDEADBEEFDEADBEEF))
+        sp.decommit_fri(3, (1 << log_n) - 1, pr, ch)
+        orc.decommit_fri(3, (1 << log_n) - 1, opr, och)
+        assert ch.state == och.state
+        pr.free(); p0.free()
+    # step API: the folds keep streaming; layers_wait before reading
+    log_n = 10
+    c = orc.synthetic_poly_exact_degree(5, 1 << 7)
+    buf = np.zeros(2 << log_n, dtype=np.uint64)
+    pr, root = sp.fri_begin(ctx, c, log_n, 5, layers_out=buf)
+    betas = [3, 1234567, 99]
+    for b in betas:
+        pr.fold(b)
+    pr.layers_wait()
+    ev = orc.coset_evaluate(c, log_n, 5, orc.root_of_unity(log_n), P)
+    assert np.array_equal(buf[:1 << log_n], ev)
+    off = 0
+    for k in range(pr.num_layers):
+        assert np.array_equal(buf[off:off + pr.layer_len(k)], pr.layer(k))
+        off += pr.layer_len(k)
+    pr.free()
+    # a destination that cannot hold layer 0 is refused up front; one that fills up later fails in the fold that overflows it
+    with pytest.raises(sp.StarkError):
+        sp.fri_begin(ctx, c, log_n, 5, layers_out=np.zeros((1 << log_n) - 1, dtype=np.uint64))
+    small = np.zeros((1 << log_n) + 100, dtype=np.uint64)
+    with pytest.raises(sp.StarkError):
+        sp.fri_commit(ctx, c, sp.CosetFri(ctx, 5, log_n), sp.Channel(P), layers_out=small)
+    # the context is still usable afterwards
+    _check_fri(sp, orc, ctx, c, log_n, 5, 2)
+
+
 def test_fri_too_many_folds_is_error(sp, orc, ctx):
     # degree >= domain size: the reference would reach an empty layer and panic in MerkleTree::root()
     pr, _ = sp.fri_begin(ctx, orc.synthetic_poly_exact_degree(1, 4), 2, 5)
