@@ -151,6 +151,7 @@ struct stark_mg {
     nccl_comm_t comm = nullptr;
     bool own_comm = false;
     cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_done = nullptr;   // main stream -> copy stream -> main stream (allgather_layer_begin / _end)
     DevBuf d_small;                     // device scratch of the small collectives
     PinnedBuf h_small;                  // their pinned host side; also the per-column root slots of commit_columns
     std::map<unsigned, std::unique_ptr<P2PState>> p2p;
@@ -238,6 +239,8 @@ void mg_common_init(stark_mg* mg) {
     stark_ctx* ctx = mg->ctx;
     STARK_REQUIRE(mg->world >= 1 && mg->world <= (unsigned)MAX_PEERS && mg->rank < mg->world, "stark_mg: rank / world out of range");
     STARK_CUDA(cudaStreamCreateWithFlags(&mg->copy_stream, cudaStreamNonBlocking));
+    STARK_CUDA(cudaEventCreateWithFlags(&mg->ev_ready, cudaEventDisableTiming));
+    STARK_CUDA(cudaEventCreateWithFlags(&mg->ev_done, cudaEventDisableTiming));
     mg->d_small = DevBuf(SMALL_BYTES, ctx->stream);
     mg->h_small.ensure(SMALL_BYTES);
 }
@@ -425,12 +428,13 @@ std::unique_ptr<stark_tree> commit_leaf_range(stark_mg* mg, DevBufPtr block, siz
 // all-gather instead of the gather on rank 0), folds the WHOLE next layer and the coefficients itself, and no data-path
 // exchange follows -- while the tree is hashed in leaf ranges: 32 bytes of subtree root per rank travel to everybody, the
 // top log2(world) levels are finished on the host, rank 0 feeds the channel and beta (8 bytes) travels back.  Layers below
-// 2^STARK_MG_FRI_SHARD_MIN_LOG leaves (default 2^21: a layer costs ~0.16 ns per leaf to hash against ~0.12 ms for the two
-// small collectives and the extra launches) are left to rank 0's ordinary loop.
+// 2^STARK_MG_FRI_SHARD_MIN_LOG leaves (default 2^20: a layer costs ~0.16 ns per leaf to hash against ~0.1 ms for the two
+// small collectives and the extra launches; measured on 8 GPUs at a 2^26 domain, thresholds 2^25 / 23 / 22 / 21 / 20 / 19 / 18 /
+// 17 -> 11.5 / 8.30 / 7.81 / 7.53 / 7.45 / 7.43 / 7.48 / 7.53 ms) are left to rank 0's ordinary loop.
 unsigned shard_min_log() {
     const char* e = getenv("STARK_MG_FRI_SHARD_MIN_LOG");
     const int v = e ? atoi(e) : 0;
-    return v >= 6 && v <= 30 ? (unsigned)v : 21u;
+    return v >= 6 && v <= 30 ? (unsigned)v : 20u;
 }
 bool shard_forced() { const char* e = getenv("STARK_MG_FRI_SHARD_FORCE"); return e && atoi(e) != 0; }      // tests: one rank takes the sharded path
 bool shard_wanted(const stark_mg* mg, unsigned log_n) {
@@ -464,13 +468,21 @@ void sharded_fri_layers(stark_mg* mg, stark_fri* proof, Channel* chan, std::vect
         out.push_back(std::move(sl));
     }
 }
-// layer 0 of a sharded proof on every rank: this rank's block + everybody else's
-DevBufPtr allgather_layer(stark_mg* mg, const DevBufPtr& block, size_t blk) {
+// Layer 0 of a sharded proof on every rank: this rank's block + everybody else's.  The all-gather (4 N bytes per rank over
+// NVLink) is issued on the copy stream BEFORE the leaf-range hashing of the same block is launched on the main stream, so
+// the two overlap (the collective's few CTAs are placed first); allgather_layer_end makes the main stream wait for it.
+DevBufPtr allgather_layer_begin(stark_mg* mg, const DevBufPtr& block, size_t blk) {
     stark_ctx* ctx = mg->ctx;
     if (mg->world == 1) return block;
     DevBufPtr all = make_buf(blk * mg->world * 4, ctx->stream);
-    STARK_NCCL(nccl().AllGather(block->p, all->p, blk, NCCL_UINT32, mg->comm, ctx->stream));
+    STARK_CUDA(cudaEventRecord(mg->ev_ready, ctx->stream));
+    STARK_CUDA(cudaStreamWaitEvent(mg->copy_stream, mg->ev_ready, 0));
+    STARK_NCCL(nccl().AllGather(block->p, all->p, blk, NCCL_UINT32, mg->comm, mg->copy_stream));
+    STARK_CUDA(cudaEventRecord(mg->ev_done, mg->copy_stream));
     return all;
+}
+void allgather_layer_end(stark_mg* mg) {
+    if (mg->world > 1) STARK_CUDA(cudaStreamWaitEvent(mg->ctx->stream, mg->ev_done, 0));
 }
 
 }  // namespace
@@ -525,6 +537,8 @@ extern "C" void stark_mg_destroy(stark_mg* mg) {
     mg->p2p.clear(); mg->staged.clear();
     mg->d_small.release(); mg->h_small.release();
     if (mg->copy_stream) cudaStreamDestroy(mg->copy_stream);
+    if (mg->ev_ready) cudaEventDestroy(mg->ev_ready);
+    if (mg->ev_done) cudaEventDestroy(mg->ev_done);
     if (mg->own_comm && mg->comm) nccl().CommDestroy(mg->comm);
     delete mg;
 }
@@ -649,12 +663,13 @@ extern "C" int stark_mg_fri_commit(stark_mg* mg, const stark_vec* coeffs, unsign
     DevBufPtr b = fourstep_lde(mg, coeffs, log_n, offset, transport);
     f->subtree_roots.resize((size_t)world * 32);
     uint8_t root0[32];
-    auto sub = commit_leaf_range(mg, b, blk, root0, f->subtree_roots.data());
     // layer 0: on every rank when the following layers are hashed in leaf ranges too (the folds are replicated), else on rank 0
     const bool shard = shard_wanted(mg, log_n);
     DevBufPtr layer0;
+    if (world > 1 && shard) layer0 = allgather_layer_begin(mg, b, blk);        // runs under the hashing below
+    auto sub = commit_leaf_range(mg, b, blk, root0, f->subtree_roots.data());
     if (world == 1) layer0 = b;
-    else if (shard) layer0 = allgather_layer(mg, b, blk);
+    else if (shard) allgather_layer_end(mg);
     else {
         Nccl& n = nccl();
         if (rank == 0) {
@@ -797,16 +812,18 @@ extern "C" int stark_mg_stark101_prove(stark_mg* mg, uint64_t a1, unsigned log_t
     }
     if (rc != ST_OK) return rc;
     std::unique_ptr<stark_vec> cp_guard(cp_vec);
+    const bool shard = shard_wanted(mg, log_n);
+    DevBufPtr cp_all;
+    if (world > 1 && shard) cp_all = allgather_layer_begin(mg, cp_vec->buf, blk);          // runs under the hashing below
     auto cp_sub = commit_leaf_range(mg, cp_vec->buf, blk, cp_root, cp_subs.data());
     // ---- src/fri: layer 0 = the CP evaluations, its coefficients by interpolation (degree tracking).  With the large layers
     // >= 1 hashed in leaf ranges every rank holds layer 0 and replicates the folds (sharded_fri_layers); otherwise rank 0 alone
-    const bool shard = shard_wanted(mg, log_n);
     std::unique_ptr<stark_fri> proof;
     std::vector<ShardedLayer> sharded;
     if (world == 1 || rank == 0 || shard) {
         DevBufPtr layer0;
         if (world == 1) layer0 = cp_vec->buf;
-        else if (shard) layer0 = allgather_layer(mg, cp_vec->buf, blk);
+        else if (shard) { layer0 = cp_all; allgather_layer_end(mg); }
         else {
             Nccl& n = nccl();
             layer0 = make_buf(N * 4, ctx->stream);
