@@ -245,8 +245,9 @@ int stark_decommit_fri(const stark_fri* f, size_t num_queries, size_t max_index,
 
 /* ---- multi-GPU: one process per GPU, one stark_mg per process ------------------------------------
  * What shards: independent trace columns (cfg4), and one big column through the four-step NTT + contiguous leaf ranges
- * (cfg5); the FRI folds, the smaller trees, the channel and the openings of layers >= 1 stay on rank 0 (north-star:
- * "nothing else is partitioned").  The group owns an NCCL communicator (bound at run time, libnccl.so.2): rank 0 calls
+ * (cfg5) -- layer 0 of a FRI proof and, on more than one GPU, every later layer of >= 2^20 leaves (each rank folds the
+ * whole layer itself, hashes its leaf range, 32-byte subtree roots are gathered); the smaller trees and the channel
+ * stay on rank 0, and no data is partitioned except for leaf hashing (north-star: "nothing else is partitioned").  The group owns an NCCL communicator (bound at run time, libnccl.so.2): rank 0 calls
  * stark_mg_unique_id, hands the 128 bytes to the other ranks by whatever means the host program has (MPI, a file, its
  * own RPC), and every rank calls stark_mg_create; stark_mg_adopt takes an existing ncclComm_t instead.  Calls on a group
  * are collective: every rank makes the same calls in the same order.  world must be a power of two <= 16 for the
@@ -273,18 +274,19 @@ int stark_mg_fourstep_lde(stark_mg* mg, const stark_vec* coeffs, unsigned log_n,
 /* MerkleTree::new over a column held in contiguous leaf ranges: each rank hashes its range (an exact subtree), the
  * subtree roots are gathered and the top levels finished on every rank.  subtree_roots: optional, world * 32 bytes. */
 int stark_mg_commit_leaf_ranges(stark_mg* mg, const stark_vec* block, stark_tree** subtree, uint8_t root[32], uint8_t* subtree_roots);
-/* fri_commit (fri_commit.rs:72-122) / decommit_fri (:168-179) with layer 0 distributed that way; `ch` is used on rank 0
- * only and receives the single-GPU transcript byte for byte. */
+/* fri_commit (fri_commit.rs:72-122) / decommit_fri (:168-179) with layer 0 -- and the later large layers -- hashed in
+ * leaf ranges; `ch` is used on rank 0 only and receives the single-GPU transcript byte for byte.  Environment:
+ * STARK_MG_FRI_SHARD=0 leaves the layers >= 1 on rank 0, STARK_MG_FRI_SHARD_MIN_LOG (default 20) moves the threshold. */
 int stark_mg_fri_commit(stark_mg* mg, const stark_vec* coeffs, unsigned log_n, uint64_t offset, int transport, stark_channel* ch,
                         stark_mg_fri** out);
 int stark_mg_decommit_fri(stark_mg_fri* f, size_t num_queries, size_t max_index, stark_channel* ch);
 /* stark101_prove over the group (BASELINE cfg5, "end-to-end prove ... using four-step NTT"): trace LDE through the
  * four-step transform, commitments of f and of the composition polynomial in leaf ranges, the composition polynomial on
- * each rank's own range (a halo of 2 * blowup values from the next rank), FRI layers >= 1 and the channel on rank 0.
+ * each rank's own range (a halo of 2 * blowup values from the next rank), the FRI layers as in stark_mg_fri_commit.
  * The transcript in `ch` (rank 0) is stark101_prove's, byte for byte. */
 int stark_mg_stark101_prove(stark_mg* mg, uint64_t a1, unsigned log_trace, unsigned log_blowup, size_t num_queries, int transport,
                             stark_channel* ch);
-const stark_fri* stark_mg_fri_proof(const stark_mg_fri* f);      /* rank 0: layers >= 1 live here (borrowed); NULL elsewhere */
+const stark_fri* stark_mg_fri_proof(const stark_mg_fri* f);      /* rank 0: every layer's values, the small layers' trees (borrowed); elsewhere NULL or the replicated large layers */
 const stark_tree* stark_mg_fri_subtree(const stark_mg_fri* f);   /* this rank's subtree of layer 0 (borrowed) */
 void stark_mg_fri_destroy(stark_mg_fri* f);
 

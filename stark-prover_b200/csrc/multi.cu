@@ -7,8 +7,10 @@
 //     (ncclSend/ncclRecv groups) or stored straight into peer memory over NVLink by the kernels that produce the data,
 //     handed over with device-side epoch flags (fourstep.cu) -- then contiguous leaf ranges hashed per rank and the
 //     subtree roots gathered (stark_mg_fourstep_lde, stark_mg_commit_leaf_ranges);
-//   * fri_commit / decommit_fri with layer 0 distributed that way; the folds, the smaller trees and the channel stay
-//     on rank 0 (stark_mg_fri_commit, stark_mg_decommit_fri, BASELINE cfg5).
+//   * fri_commit / decommit_fri with layer 0 distributed that way, and the leaf hashing of the later LARGE layers too:
+//     the folds are replicated on every rank, each rank hashes its leaf range of the new layer, subtree roots are
+//     gathered (sharded_fri_layers); the smaller trees and the channel stay on rank 0 (stark_mg_fri_commit,
+//     stark_mg_decommit_fri, BASELINE cfg5).
 //
 // NCCL is resolved at run time (dlopen of libnccl.so.2: the copy a host framework has already loaded, or the system
 // one), so the library has no link-time dependency on it and single-GPU users never touch it.
