@@ -396,6 +396,92 @@ def decommit_fri_multi(sp, mp: MultiGpuFri, num_queries: int, max_index: int, ch
             feed_layer_records(channel, mp.proof.open([idx], first_layer=1), lens, idx)
 
 
+# ------------------------------------------------------------------------------------------------ cfg5: the large FRI layers in leaf ranges
+# Host protocol of csrc/multi.cu (sharded_fri_layers, open_leaf_ranges_batch) with the compute injected, so that it runs
+# over a real multi-process group on CPU (gloo; tests/test_multi_gpu_cpu.py injects the oracle): every rank holds layer 0,
+# replicates the folds, hashes its own leaf range of each large layer, subtree roots are gathered, rank 0 feeds the channel
+# and beta travels back; the small layers stay with rank 0; a query's leaf-range openings travel in ONE exchange.
+class LeafRangeLayer:
+    def __init__(self, n, block, subtree, subtree_roots):
+        self.n, self.block, self.subtree, self.subtree_roots = n, block, subtree, subtree_roots
+
+
+def fri_commit_leaf_range_layers(engine, coeffs, log_n: int, offset: int, modulus: int, channel, rank: int, world: int,
+                                 min_len: int, group=None):
+    """fri_commit (fri_commit.rs:72-122).  `engine`: evaluate(coeffs, log_n, offset) -> layer 0, fold(evals, beta, offset,
+    log_len) -> next layer, fold_poly(coeffs, beta) -> trimmed coefficients, tree(values) -> object with root() / path(i).
+    Returns (layers hashed in leaf ranges, [(values, tree)] of the small layers on rank 0)."""
+    def commit(values):
+        blk = len(values) // world
+        mine = values[rank * blk:(rank + 1) * blk]
+        sub = engine.tree(mine)
+        root, subs = commit_leaf_ranges(sub.root, rank, world, group)
+        if rank == 0:
+            channel.send(root.hex().encode())                                 # :86 / :100
+        return LeafRangeLayer(len(values), mine, sub, subs)
+
+    poly = np.asarray(coeffs, dtype=np.uint64)
+    while len(poly) and poly[-1] == 0:
+        poly = poly[:-1]
+    cur = engine.evaluate(poly, log_n, offset)
+    ranged, cur_log, cur_off = [commit(cur)], log_n, offset % modulus
+    while len(poly) - 1 >= 1:                                                  # :89, identical on every rank
+        half = (1 << cur_log) >> 1
+        if half < min_len or half // world < 2:
+            break
+        beta = channel.receive_random_field_element() if rank == 0 else 0     # :91
+        beta = _bcast_int(beta, group)
+        cur = engine.fold(cur, beta, cur_off, cur_log)                         # replicated
+        poly = engine.fold_poly(poly, beta)
+        ranged.append(commit(cur))
+        cur_log, cur_off = cur_log - 1, cur_off * cur_off % modulus
+    tail = []
+    if rank == 0:
+        while len(poly) - 1 >= 1:
+            beta = channel.receive_random_field_element()
+            cur = engine.fold(cur, beta, cur_off, cur_log)
+            poly = engine.fold_poly(poly, beta)
+            t = engine.tree(cur)
+            channel.send(t.root().hex().encode())
+            tail.append((cur, t))
+            cur_log, cur_off = cur_log - 1, cur_off * cur_off % modulus
+        channel.send(int(poly[0] if len(poly) else 0).to_bytes(8, "big"))      # :109-114
+    return ranged, tail
+
+
+def decommit_fri_leaf_range_layers(ranged, tail, num_queries: int, max_index: int, channel, rank: int, world: int, group=None) -> None:
+    """decommit_fri (fri_commit.rs:168-179): one broadcast of the index and ONE gather per query for every layer hashed in ranges."""
+    for _ in range(num_queries):
+        idx = channel.receive_random_int(0, max_index, True) if rank == 0 else 0
+        idx = _bcast_int(idx, group)
+        items, off = [], [0]
+        for lay in ranged:
+            blk = lay.n // world
+            for which in (idx % lay.n, (idx % lay.n + lay.n // 2) % lay.n):
+                items.append((lay, which, blk))
+                off.append(off[-1] + 8 + 32 * (blk.bit_length() - 1))
+        payload = np.zeros(off[-1], dtype=np.uint8)
+        for t, (lay, which, blk) in enumerate(items):
+            if which // blk == rank:
+                rec = int(lay.block[which % blk]).to_bytes(8, "big") + lay.subtree.path(which % blk)
+                payload[off[t]:off[t + 1]] = np.frombuffer(rec, dtype=np.uint8)
+        allp = all_gather_bytes(payload, group)
+        if rank != 0:
+            continue
+        for t, (lay, which, blk) in enumerate(items):                          # :156-163, layer by layer
+            rec = allp[which // blk, off[t]:off[t + 1]].tobytes()
+            channel.send(rec[:8])
+            channel.send(rec[8:] + top_path(lay.subtree_roots, which // blk))
+        for values, tree in tail:
+            n = len(values)
+            i = idx % n
+            if n == 1:
+                channel.send(int(values[i]).to_bytes(8, "big"))               # :147-149, then falls through as written
+            for which in (i, (i + n // 2) % n):
+                channel.send(int(values[which]).to_bytes(8, "big"))
+                channel.send(tree.path(which))
+
+
 # ------------------------------------------------------------------------------------------------ cfg5: the whole FibonacciSq prover
 def _open_leaf_range(block, subtree, subtree_roots, which: int, blk: int, rank: int, group=None) -> tuple[bytes, bytes]:
     """(BE8(value), authentication path) of leaf `which` of a tree committed in leaf ranges: the owner opens its

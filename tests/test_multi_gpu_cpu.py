@@ -141,3 +141,58 @@ def test_feed_layer_records_order(orc):
                 blob += int(lay[which]).to_bytes(8, "big") + pr_b.tree(k).path(which)
         mg.feed_layer_records(ch_b, blob, lens, index)
         assert ch_a.state == ch_b.state and ch_a.proof == ch_b.proof
+
+
+# ---- the large FRI layers hashed in leaf ranges (csrc/multi.cu: sharded_fri_layers / open_leaf_ranges_batch) -----------------
+class _OracleEngine:
+    """The compute of the protocol, from the oracle."""
+    def __init__(self, orc):
+        self.orc = orc
+    def evaluate(self, c, log_n, offset): return self.orc.coset_evaluate(c, log_n, offset, self.orc.root_of_unity(log_n), P)
+    def fold(self, e, beta, offset, log_len): return self.orc.fri_fold_evals(e, beta, offset, self.orc.root_of_unity(log_len), P)
+    def fold_poly(self, c, beta): return self.orc.poly_trim(self.orc.next_fri_polynomial(c, beta, P))
+    def tree(self, values): return self.orc.Tree(values)
+
+
+def _fri_worker(rank, world, port, q, log_n, log_deg, queries, min_len):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from oracle import pyoracle as orc
+    mg = importlib.import_module("stark-prover_b200.multi_gpu")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        c = orc.synthetic_poly_exact_degree(11, 1 << log_deg)
+        ch = orc.Channel(P) if rank == 0 else None
+        ranged, tail = mg.fri_commit_leaf_range_layers(_OracleEngine(orc), c, log_n, 5, P, ch, rank, world, min_len)
+        mg.decommit_fri_leaf_range_layers(ranged, tail, queries, (1 << log_n) - 1, ch, rank, world)
+        q.put((rank, len(ranged), len(tail), ch.state if ch else None, [m.hex() for m in ch.proof] if ch else None))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("world,log_n,log_deg,min_len", [(2, 9, 6, 16), (2, 7, 7, 4), (4, 10, 5, 64)])
+def test_fri_leaf_range_layers_gloo(orc, world, log_n, log_deg, min_len):
+    """world_size-2 and -4 gloo groups run the protocol of the sharded FRI layers (replicated folds, leaf-range hashing, root
+    gathers, beta broadcast, one exchange per query); rank 0's transcript is the single-process oracle's, byte for byte."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() * 7 + world * 13 + log_n) % 2000
+    queries = 3
+    procs = [ctx.Process(target=_fri_worker, args=(r, world, port, q, log_n, log_deg, queries, min_len)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=150) for _ in procs)
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    och = orc.Channel(P)
+    c = orc.synthetic_poly_exact_degree(11, 1 << log_deg)
+    opr = orc.fri_commit_fast(c, log_n, 5, orc.root_of_unity(log_n), och, P)
+    orc.decommit_fri(queries, (1 << log_n) - 1, opr, och)
+    _, n_ranged, n_tail, state, proof = res[0]
+    assert n_ranged >= 2 and n_ranged + n_tail == opr.num_layers          # at least one layer >= 1 went through the ranges
+    assert all(r[1] == n_ranged for r in res)                             # every rank took the same number of sharded layers
+    assert state == och.state and proof == [m.hex() for m in och.proof]
