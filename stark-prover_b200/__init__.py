@@ -736,7 +736,8 @@ class MgFri:
 
     @property
     def proof(self) -> Optional[FriProof]:
-        """rank 0: the layers >= 1 (and the adopted layer 0), borrowed; None on the other ranks"""
+        """rank 0: every layer's values and the small layers' trees, borrowed.  On the other ranks None, or -- when the
+        large layers >= 1 are hashed in leaf ranges (more than one GPU) -- the replicated large layers"""
         h = lib().stark_mg_fri_proof(self.h)
         if not h:
             return None

@@ -39,7 +39,7 @@ def run(budget: float, seed: int, tag: str = "") -> None:
         m, g = MODULI[int(rng.integers(0, len(MODULI)))]
         ctx = ctx_for(m, g)
         two = (m - 1 & -(m - 1)).bit_length() - 1
-        kind = int(rng.integers(0, 12))
+        kind = int(rng.integers(0, 14))
         if kind == 0:                                   # Merkle: ragged sizes, every level's ends + random nodes + paths
             n = int(rng.integers(1, 1 << int(rng.integers(1, 19))))
             vals = orc.synthetic_column(int(rng.integers(1, 1 << 30)), n, m)
@@ -189,6 +189,44 @@ def run(budget: float, seed: int, tag: str = "") -> None:
             mg.stark101_prove_multi(sp, ctx, ch, a1, log_t, log_b, q, 0, 1)
             sp.stark101_prove(ctx, ch1, a1, log_t, log_b, q)
             check("stark101_multi_world1", ch.state == ch1.state and ch.proof == ch1.proof, f"log_trace={log_t} a1={a1} q={q}")
+        elif kind == 12:                                # C-level group of one rank, the large FRI layers hashed in leaf ranges (forced) at a random threshold
+            ctx = ctx_for(*MODULI[0])
+            m0 = MODULI[0][0]
+            log_n = int(rng.integers(9, 17))
+            nco = int(rng.integers(2, (1 << (log_n - 1)) + 1))
+            q = int(rng.integers(1, 4))
+            os.environ["STARK_MG_FRI_SHARD_FORCE"] = "1"
+            os.environ["STARK_MG_FRI_SHARD_MIN_LOG"] = str(int(rng.integers(6, log_n + 1)))
+            try:
+                c = orc.synthetic_poly_exact_degree(int(rng.integers(1, 1 << 30)), nco, m0)
+                grp = sp.MultiGpu(ctx, 0, 1)
+                ch, och = sp.Channel(m0), orc.Channel(m0)
+                f = grp.fri_commit(ctx.upload(c), log_n, 5, ch, int(rng.integers(0, 2)))
+                grp.decommit_fri(f, q, (1 << log_n) - 1, ch)
+                opr = orc.fri_commit_fast(c, log_n, 5, orc.root_of_unity(log_n), och, m0)
+                orc.decommit_fri(q, (1 << log_n) - 1, opr, och)
+                check("mg_fri_leaf_range_layers", ch.state == och.state and ch.proof == och.proof,
+                      f"log_n={log_n} coeffs={nco} q={q} min_log={os.environ['STARK_MG_FRI_SHARD_MIN_LOG']}")
+                f.free(); grp.close()
+            finally:
+                os.environ.pop("STARK_MG_FRI_SHARD_FORCE", None); os.environ.pop("STARK_MG_FRI_SHARD_MIN_LOG", None)
+        elif kind == 13:                                # FRI layers by value, streamed to the host during the commit
+            log_n = int(rng.integers(2, min(two, 18) + 1))
+            nco = int(rng.integers(1, (1 << log_n) + 1))
+            off = int(rng.integers(1, m))
+            c = orc.synthetic_column(int(rng.integers(1, 1 << 30)), nco, m)
+            buf = np.full(2 << log_n, 0xABCDABCDABCDABCD, dtype=np.uint64)
+            ch, ch1 = sp.Channel(m), sp.Channel(m)
+            pr = sp.fri_commit(ctx, c, sp.CosetFri(ctx, off, log_n), ch, layers_out=buf)
+            p1 = sp.fri_commit(ctx, c, sp.CosetFri(ctx, off, log_n), ch1)
+            ok, o = ch.state == ch1.state and pr.num_layers == p1.num_layers, 0
+            for k in range(p1.num_layers):
+                ln = p1.layer_len(k)
+                ok = ok and pr.layer_host_offset(k) == o and np.array_equal(buf[o:o + ln], p1.layer(k))
+                o += ln
+            ok = ok and bool(np.all(buf[o:] == np.uint64(0xABCDABCDABCDABCD)))
+            check("fri_layers_by_value", ok, f"log_n={log_n} coeffs={nco} offset={off} modulus={m}")
+            pr.free(); p1.free()
         else:                                           # kind 4: the build-defined prover + its verifier (default field only)
             ctx = ctx_for(*MODULI[0])
             log_t, log_b = int(rng.integers(2, 13)), int(rng.integers(1, 5))
