@@ -591,10 +591,12 @@ def run_b200(args):
 
     per_rank_ms = []
 
-    def step(src, layers_out=None):
+    def step(src, layers_out=None, wait=True):
         ch = sp.Channel(P)
-        pr = sp.fri_commit(ctx, src, domain, ch, layers_out=layers_out)
+        pr = sp.fri_commit(ctx, src, domain, ch, layers_out=layers_out, wait=wait)
         sp.decommit_fri(QUERIES, n - 1, pr, ch)
+        if layers_out is not None and not wait:
+            pr.layers_wait()                     # the last layer copies ran under the openings
         return pr, ch
 
     def gather_roots(pr):
@@ -603,7 +605,7 @@ def run_b200(args):
         mine = torch.frombuffer(bytearray(pr.tree(0).root_bytes()), dtype=torch.uint8).to(f"cuda:{local}")
         dist.all_gather_into_tensor(roots_out.view(-1), mine)
 
-    def timed(src, steps, flush_l2=True, after=None, layers_out=None):
+    def timed(src, steps, flush_l2=True, after=None, layers_out=None, wait=True):
         """max-over-ranks device time per step (ms) and the last step's artefacts.  `after(pr)`: extra work inside the
         timed region (the layers copied back by value after the step); `layers_out`: the layers streamed to that pinned
         buffer during the commit (e2e_full)."""
@@ -620,7 +622,7 @@ def run_b200(args):
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            pr, ch = step(src, layers_out)
+            pr, ch = step(src, layers_out, wait)
             if after is not None:
                 after(pr)
             gather_roots(pr)
@@ -701,7 +703,14 @@ def run_b200(args):
     check = hashlib.sha256(layers_np.tobytes()).hexdigest()
     layers_np[:] = 0
     timed(pinned_np, 1, layers_out=layers_np)
-    ms_full, pr5, ch5 = timed(pinned_np, max(2, min(args.steps, 5)), layers_out=layers_np)
+    ms_full_sync, pr5, ch5 = timed(pinned_np, max(2, min(args.steps, 5)), layers_out=layers_np)
+    assert ch5.state == final_state, "the by-value path changed the transcript"
+    assert hashlib.sha256(layers_np.tobytes()).hexdigest() == check, "streamed layers differ from stark_fri_layer_read"
+    pr5.free()
+    # ... and with the wait moved behind the openings (stark_fri_commit_to_host_async + stark_fri_layers_wait): the layers are
+    # complete when the STEP ends, the tail of the copies runs under decommit_fri
+    layers_np[:] = 0
+    ms_full, pr5, ch5 = timed(pinned_np, max(2, min(args.steps, 5)), layers_out=layers_np, wait=False)
     assert ch5.state == final_state, "the by-value path changed the transcript"
     assert hashlib.sha256(layers_np.tobytes()).hexdigest() == check, "streamed layers differ from stark_fri_layer_read"
     pr5.free()
@@ -721,8 +730,10 @@ def run_b200(args):
                     "h2d_bytes_per_step": 8 << log_deg, "d2h_bytes_per_step": d2h},
             "e2e_full": {"value": world * n / (ms_full * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_full,
                          "h2d_bytes_per_step": 8 << log_deg, "d2h_bytes_per_step": d2h + 8 * sum(layer_lens),
-                         "note": "e2e plus every FRI layer in pinned host memory as u64 when fri_commit returns, i.e. FRIProof.fri_layers by "
-                                 "value: stark_fri_commit_to_host streams them on a second stream under the hashing of the following layers",
+                         "note": "e2e plus every FRI layer in pinned host memory as u64 when the step ends, i.e. FRIProof.fri_layers by "
+                                 "value: stark_fri_commit_to_host_async streams them on a second stream under the hashing of the following "
+                                 "layers and the openings (stark_fri_layers_wait at the end of the step)",
+                         "ms_per_step_layers_complete_when_fri_commit_returns": ms_full_sync,
                          "ms_per_step_copied_after_the_step": ms_full_after},
             "gpu_launches": int(launches), "clocks": clocks, "transcript_state": final_state,
             "ms_per_rank": per_rank_dev if world > 1 else None,

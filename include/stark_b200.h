@@ -228,13 +228,16 @@ void stark_fri_destroy(stark_fri* f);
  * (2^(log_n+1) hold every layer).  stark_fri_layers_wait blocks until every copy issued so far has landed;
  * stark_fri_destroy waits as well.  With pinned memory (cudaHostAlloc / cudaHostRegister) the copies are asynchronous;
  * pageable memory works but blocks the calling thread for each copy.  stark_fri_commit_to_host = the whole loop with the
- * library's Channel, complete on return. */
+ * library's Channel, complete on return; stark_fri_commit_to_host_async returns as soon as the transcript is complete, the
+ * last copies may still be in flight (they finish under the caller's query phase: stark_fri_layers_wait before reading). */
 int stark_fri_begin_to_host(stark_ctx* ctx, const uint64_t* coeffs, size_t n_coeffs, unsigned log_n, uint64_t offset,
                             uint64_t* layers_out, size_t cap, stark_fri** out, uint8_t root[32]);
 int stark_fri_layers_wait(const stark_fri* f);
 size_t stark_fri_layer_host_offset(const stark_fri* f, size_t k);               /* (size_t)-1: no such layer / no host copy */
 int stark_fri_commit_to_host(stark_ctx* ctx, const uint64_t* coeffs, size_t n_coeffs, unsigned log_n, uint64_t offset,
                              stark_channel* ch, uint64_t* layers_out, size_t cap, stark_fri** out);
+int stark_fri_commit_to_host_async(stark_ctx* ctx, const uint64_t* coeffs, size_t n_coeffs, unsigned log_n, uint64_t offset,
+                                   stark_channel* ch, uint64_t* layers_out, size_t cap, stark_fri** out);
 
 int stark_fri_commit(stark_ctx* ctx, const uint64_t* coeffs, size_t n_coeffs, unsigned log_n, uint64_t offset,
                      stark_channel* ch, stark_fri** out);

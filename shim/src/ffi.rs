@@ -100,6 +100,7 @@ extern "C" {
     pub fn stark_fri_layers_wait(f: *const stark_fri) -> c_int;
     pub fn stark_fri_layer_host_offset(f: *const stark_fri, k: usize) -> usize;
     pub fn stark_fri_commit_to_host(ctx: *mut stark_ctx, coeffs: *const u64, n_coeffs: usize, log_n: c_uint, offset: u64, ch: *mut stark_channel, layers_out: *mut u64, cap: usize, out: *mut *mut stark_fri) -> c_int;
+    pub fn stark_fri_commit_to_host_async(ctx: *mut stark_ctx, coeffs: *const u64, n_coeffs: usize, log_n: c_uint, offset: u64, ch: *mut stark_channel, layers_out: *mut u64, cap: usize, out: *mut *mut stark_fri) -> c_int;
     pub fn stark_fri_commit(ctx: *mut stark_ctx, coeffs: *const u64, n_coeffs: usize, log_n: c_uint, offset: u64, ch: *mut stark_channel, out: *mut *mut stark_fri) -> c_int;
     pub fn stark_fri_commit_dev(ctx: *mut stark_ctx, coeffs: *const stark_vec, log_n: c_uint, offset: u64, ch: *mut stark_channel, out: *mut *mut stark_fri) -> c_int;
     pub fn stark_decommit_fri_layers(f: *const stark_fri, index: usize, ch: *mut stark_channel) -> c_int;

@@ -155,6 +155,7 @@ def lib() -> C.CDLL:
     sig("stark_fri_layers_wait", I, vp)
     sig("stark_fri_layer_host_offset", szt, vp, szt)
     sig("stark_fri_commit_to_host", I, vp, vp, szt, C.c_uint, u64, vp, vp, szt, C.POINTER(vp))
+    sig("stark_fri_commit_to_host_async", I, vp, vp, szt, C.c_uint, u64, vp, vp, szt, C.POINTER(vp))
     sig("stark_decommit_fri_layers", I, vp, szt, vp)
     sig("stark_decommit_fri", I, vp, szt, szt, vp)
     sig("stark101_prove", I, vp, u64, C.c_uint, C.c_uint, szt, vp)
@@ -637,17 +638,19 @@ def fri_begin_external(ctx: Context, coeffs: "Vec", log_n: int, offset: int, lay
     return pr
 
 
-def fri_commit(ctx: Context, poly, domain: CosetFri, channel: Channel, layers_out: Optional[np.ndarray] = None) -> FriProof:
+def fri_commit(ctx: Context, poly, domain: CosetFri, channel: Channel, layers_out: Optional[np.ndarray] = None,
+               wait: bool = True) -> FriProof:
     """fri_commit(poly, domain, &mut channel) (src/fri/fri_commit.rs:72-122).  With `layers_out` (uint64, >= 2^(log_size+1)
     elements always suffice; pinned memory keeps the copies asynchronous) every layer is also returned BY VALUE, layer k at
-    `proof.layer_host_offset(k)`, copied on a second stream under the hashing of the following layers."""
+    `proof.layer_host_offset(k)`, copied on a second stream under the hashing of the following layers; complete on return,
+    or -- with wait=False -- once `proof.layers_wait()` has been called (the last copies then run under the query phase)."""
     h = vp()
     if layers_out is not None:
         assert not isinstance(poly, Vec), "fri_commit(layers_out=...): host coefficients"
         assert layers_out.dtype == np.uint64 and layers_out.flags["C_CONTIGUOUS"]
         c = _arr(poly)
-        _check(lib().stark_fri_commit_to_host(ctx.h, _ptr(c), c.size, domain.log_size, domain.offset, channel.h,
-                                              _ptr(layers_out), layers_out.size, C.byref(h)))
+        fn = lib().stark_fri_commit_to_host if wait else lib().stark_fri_commit_to_host_async
+        _check(fn(ctx.h, _ptr(c), c.size, domain.log_size, domain.offset, channel.h, _ptr(layers_out), layers_out.size, C.byref(h)))
         pr = FriProof(ctx, h)
         pr._keep_layers = layers_out
         return pr

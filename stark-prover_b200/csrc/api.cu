@@ -990,16 +990,24 @@ extern "C" int stark_fri_commit(stark_ctx* ctx, const uint64_t* coeffs, size_t n
     if (rc != ST_OK) { stark_fri_destroy(*out); *out = nullptr; return rc; }
     API_END
 }
-extern "C" int stark_fri_commit_to_host(stark_ctx* ctx, const uint64_t* coeffs, size_t n_coeffs, unsigned log_n, uint64_t offset,
-                                        stark_channel* ch, uint64_t* layers_out, size_t cap, stark_fri** out) {
+static int fri_commit_to_host_impl(stark_ctx* ctx, const uint64_t* coeffs, size_t n_coeffs, unsigned log_n, uint64_t offset,
+                                   stark_channel* ch, uint64_t* layers_out, size_t cap, stark_fri** out, bool wait) {
     STARK_API_GUARD_NULL(ctx && ch && out && layers_out);
     int rc = stark_fri_begin_to_host(ctx, coeffs, n_coeffs, log_n, offset, layers_out, cap, out, nullptr);
     if (rc != ST_OK) return rc;
     API_BEGIN
     rc = fri_commit_loop(*out, ch);
-    if (rc == ST_OK) rc = stark_fri_layers_wait(*out);                       // by value: complete on return
+    if (rc == ST_OK && wait) rc = stark_fri_layers_wait(*out);               // by value: complete on return
     if (rc != ST_OK) { stark_fri_destroy(*out); *out = nullptr; return rc; }
     API_END
+}
+extern "C" int stark_fri_commit_to_host(stark_ctx* ctx, const uint64_t* coeffs, size_t n_coeffs, unsigned log_n, uint64_t offset,
+                                        stark_channel* ch, uint64_t* layers_out, size_t cap, stark_fri** out) {
+    return fri_commit_to_host_impl(ctx, coeffs, n_coeffs, log_n, offset, ch, layers_out, cap, out, true);
+}
+extern "C" int stark_fri_commit_to_host_async(stark_ctx* ctx, const uint64_t* coeffs, size_t n_coeffs, unsigned log_n, uint64_t offset,
+                                              stark_channel* ch, uint64_t* layers_out, size_t cap, stark_fri** out) {
+    return fri_commit_to_host_impl(ctx, coeffs, n_coeffs, log_n, offset, ch, layers_out, cap, out, false);
 }
 extern "C" int stark_fri_commit_dev(stark_ctx* ctx, const stark_vec* coeffs, unsigned log_n, uint64_t offset,
                                     stark_channel* ch, stark_fri** out) {

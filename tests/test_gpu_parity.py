@@ -483,6 +483,22 @@ def test_fri_layers_by_value_streamed_to_host(sp, orc, ctx):
         orc.decommit_fri(3, (1 << log_n) - 1, opr, och)
         assert ch.state == och.state
         pr.free(); p0.free()
+    # the asynchronous form: the transcript is complete on return, the copies after layers_wait (here: under the openings)
+    log_n = 18
+    c = orc.synthetic_poly_exact_degree(91, 1 << 15)
+    keep = torch.empty(2 << log_n, dtype=torch.int64).pin_memory()
+    buf = keep.numpy().view(np.uint64)
+    ch, ch0 = sp.Channel(P), sp.Channel(P)
+    pr = sp.fri_commit(ctx, c, sp.CosetFri(ctx, 5, log_n), ch, layers_out=buf, wait=False)
+    sp.decommit_fri(4, (1 << log_n) - 1, pr, ch)
+    pr.layers_wait()
+    p0 = sp.fri_commit(ctx, c, sp.CosetFri(ctx, 5, log_n), ch0)
+    sp.decommit_fri(4, (1 << log_n) - 1, p0, ch0)
+    assert ch.state == ch0.state
+    for k in range(p0.num_layers):
+        o = pr.layer_host_offset(k)
+        assert np.array_equal(buf[o:o + p0.layer_len(k)], p0.layer(k)), f"async layer {k}"
+    pr.free(); p0.free()
     # step API: the folds keep streaming; layers_wait before reading
     log_n = 10
     c = orc.synthetic_poly_exact_degree(5, 1 << 7)

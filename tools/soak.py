@@ -192,7 +192,7 @@ def run(budget: float, seed: int, tag: str = "") -> None:
         elif kind == 12:                                # C-level group of one rank, the large FRI layers hashed in leaf ranges (forced) at a random threshold
             ctx = ctx_for(*MODULI[0])
             m0 = MODULI[0][0]
-            log_n = int(rng.integers(9, 17))
+            log_n = int(rng.integers(10, 17))
             nco = int(rng.integers(2, (1 << (log_n - 1)) + 1))
             q = int(rng.integers(1, 4))
             os.environ["STARK_MG_FRI_SHARD_FORCE"] = "1"
