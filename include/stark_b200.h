@@ -225,7 +225,8 @@ void stark_fri_destroy(stark_fri* f);
  * stark_fri_fold produces, is also written to layers_out as u64 -- layer k at element offset
  * stark_fri_layer_host_offset(f, k) = the sum of the earlier layers' lengths -- by a second, high-priority stream (widening
  * kernel + copy engine) while the main stream hashes the following layers.  cap = capacity of layers_out in elements
- * (2^(log_n+1) hold every layer).  stark_fri_layers_wait blocks until every copy issued so far has landed;
+ * (2^(log_n+1) hold every layer).  A layer's copy is enqueued while the main stream works on the next one (the last layer's
+ * with stark_fri_final); stark_fri_layers_wait blocks until every layer produced so far has landed;
  * stark_fri_destroy waits as well.  With pinned memory (cudaHostAlloc / cudaHostRegister) the copies are asynchronous;
  * pageable memory works but blocks the calling thread for each copy.  stark_fri_commit_to_host = the whole loop with the
  * library's Channel, complete on return; stark_fri_commit_to_host_async returns as soon as the transcript is complete, the

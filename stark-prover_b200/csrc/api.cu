@@ -720,6 +720,17 @@ static void sink_push(stark_fri* f, const uint32_t* vals, size_t n, bool after_m
     s->offs.push_back(s->off);
     s->off += n;
 }
+// every finished layer that has not been sent yet.  Called while the main stream is busy with the NEXT layer's launches
+// (stark_fri_fold, between its launches and its synchronisation), so that the two enqueues per layer cost no time between a
+// layer's root and the next launch; the last layer goes out with stark_fri_final / stark_fri_layers_wait.
+static void sink_flush(stark_fri* f) {
+    stark_fri::LayerSink* s = f->sink.get();
+    if (!s) return;
+    while (s->offs.size() < f->trees.size()) {
+        const stark_tree* t = f->trees[s->offs.size()].get();
+        sink_push(f, t->leaves->as<uint32_t>(), t->shape.n, false);
+    }
+}
 
 static void fri_begin_impl(stark_ctx* ctx, DevBufPtr coeffs_padded, size_t len, unsigned log_m, unsigned log_n,
                            uint64_t offset, stark_fri** out, uint8_t root[32], uint64_t* layers_out = nullptr, size_t layers_cap = 0) {
@@ -773,6 +784,7 @@ extern "C" int stark_fri_layers_wait(const stark_fri* f) {
     STARK_REQUIRE(f, "fri_layers_wait: null argument");
     if (f->sink) {
         CtxGuard g(f->ctx);
+        sink_flush(const_cast<stark_fri*>(f));
         STARK_CUDA(cudaStreamSynchronize(f->sink->stream));
     }
     API_END
@@ -839,11 +851,11 @@ extern "C" int stark_fri_fold(stark_fri* f, uint64_t beta, uint8_t root[32]) {
         f->coeffs = nc;
     }
     auto t = tree_launch(ctx, ev, half, src);
+    sink_flush(f);                           // the previous layer on its way to the host, enqueued under this layer's launches
     STARK_CUDA(cudaStreamSynchronize(ctx->stream));
     tree_take_root(t.get());
     if (f->coeff_len > 0) f->coeff_len = (size_t)ctx->h_result->degree_plus1;
     if (root) words_to_bytes(t->root_words, root);
-    sink_push(f, t->leaves->as<uint32_t>(), half, false);
     f->trees.push_back(std::move(t));
     f->cur_log -= 1;
     f->cur_offset = h_mul(f->cur_offset, f->cur_offset, p);
@@ -854,6 +866,7 @@ extern "C" int stark_fri_final(const stark_fri* f, uint64_t* value, size_t* fina
     API_BEGIN
     STARK_REQUIRE(f && value, "fri_final: null argument");
     CtxGuard g(f->ctx);
+    sink_flush(const_cast<stark_fri*>(f));
     uint32_t c0 = 0;
     if (f->coeff_len > 0) {
         STARK_CUDA(cudaMemcpyAsync(&c0, f->coeffs->p, 4, cudaMemcpyDeviceToHost, f->ctx->stream));
