@@ -715,8 +715,10 @@ static void sink_push(stark_fri* f, const uint32_t* vals, size_t n, bool after_m
         STARK_CUDA(cudaEventRecord(ctx->copy_event, ctx->stream));
         STARK_CUDA(cudaStreamWaitEvent(s->stream, ctx->copy_event, 0));
     }
-    widen_u32_on(ctx, s->stream, vals, s->stage.as<uint64_t>(), n);
-    STARK_CUDA(cudaMemcpyAsync(s->host + s->off, s->stage.p, n * 8, cudaMemcpyDeviceToHost, s->stream));
+    // experiment knob (tools/exp_by_value.py): 1 = no copy to the host, 2 = neither the widening kernel nor the copy
+    static const int dbg = [] { const char* e = getenv("STARK_SINK_DEBUG"); return e ? atoi(e) : 0; }();
+    if (dbg < 2) widen_u32_on(ctx, s->stream, vals, s->stage.as<uint64_t>(), n);
+    if (dbg < 1) STARK_CUDA(cudaMemcpyAsync(s->host + s->off, s->stage.p, n * 8, cudaMemcpyDeviceToHost, s->stream));
     s->offs.push_back(s->off);
     s->off += n;
 }
