@@ -701,16 +701,7 @@ static std::unique_ptr<stark_fri::LayerSink> make_sink(stark_ctx* ctx, unsigned 
     ensure_copy_stream(ctx);
     std::unique_ptr<stark_fri::LayerSink> s(new stark_fri::LayerSink());
     s->stream = ctx->copy_stream; s->host = host; s->cap = cap;
-    // pinned (cudaHostAlloc / cudaHostRegister) memory has a device alias: the layers are then written by the SMs, line by
-    // line (fri.cu: widen_to_host); any other memory goes through a staging buffer and the copy engine
-    static const int mode = [] { const char* e = getenv("STARK_SINK_MODE"); return e ? atoi(e) : 1; }();     // 0: always the copy engine
-    void* alias = nullptr;
-    if (mode != 0 && (reinterpret_cast<uintptr_t>(host) & 15) == 0 && cudaHostGetDevicePointer(&alias, host, 0) == cudaSuccess && alias)
-        s->host_dev = static_cast<uint64_t*>(alias);
-    else {
-        cudaGetLastError();                                       // (pageable memory: not an error of ours)
-        s->stage = DevBuf(((size_t)8) << log_n, ctx->copy_stream);
-    }
+    s->stage = DevBuf(((size_t)8) << log_n, ctx->copy_stream);
     return s;
 }
 // `vals` is complete in main-stream order at the time of the call (after_main: the copy stream waits for that point;
@@ -726,14 +717,8 @@ static void sink_push(stark_fri* f, const uint32_t* vals, size_t n, bool after_m
     }
     // experiment knob (tools/exp_by_value.py): 1 = no copy to the host, 2 = neither the widening kernel nor the copy
     static const int dbg = [] { const char* e = getenv("STARK_SINK_DEBUG"); return e ? atoi(e) : 0; }();
-    if (s->host_dev && (s->off & 1) == 0 && (reinterpret_cast<uintptr_t>(vals) & 15) == 0) {
-        static const unsigned ctas = [] { const char* e = getenv("STARK_SINK_CTAS"); int v = e ? atoi(e) : 0; return v > 0 ? (unsigned)v : 32u; }();
-        if (dbg < 1) widen_to_host(ctx, s->stream, vals, s->host_dev + s->off, n, ctas);
-    } else {
-        if (!s->stage.p) s->stage = DevBuf(((size_t)8) << f->log_n, s->stream);
-        if (dbg < 2) widen_u32_on(ctx, s->stream, vals, s->stage.as<uint64_t>(), n);
-        if (dbg < 1) STARK_CUDA(cudaMemcpyAsync(s->host + s->off, s->stage.p, n * 8, cudaMemcpyDeviceToHost, s->stream));
-    }
+    if (dbg < 2) widen_u32_on(ctx, s->stream, vals, s->stage.as<uint64_t>(), n);
+    if (dbg < 1) STARK_CUDA(cudaMemcpyAsync(s->host + s->off, s->stage.p, n * 8, cudaMemcpyDeviceToHost, s->stream));
     s->offs.push_back(s->off);
     s->off += n;
 }

@@ -76,29 +76,6 @@ void widen_u32_on(stark_ctx* ctx, cudaStream_t s, const uint32_t* in, uint64_t* 
     ctx->launches++;
     STARK_CUDA(cudaGetLastError());
 }
-// u32 layer -> u64 values written STRAIGHT into device-mapped pinned host memory by a few grid-striding CTAs: posted PCIe
-// writes of 128-byte lines from the SMs instead of a widening kernel + the copy engine.  The copy engine moves a layer in
-// large bursts, and every small write the latency-critical part of a commit sends the same way (the root into mapped
-// memory, the completion of the stream synchronisation) queues behind them: measured +0.56 ms on a 2^24-domain commit whose
-// copies take 5.4 ms (tools/exp_by_value.py); SM-issued writes interleave at line granularity.
-__global__ void __launch_bounds__(256) widen_to_host_kernel(const uint32_t* __restrict__ in, uint64_t* __restrict__ out, size_t n) {
-    const size_t n4 = n / 4, stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        const uint4 v = reinterpret_cast<const uint4*>(in)[i];
-        reinterpret_cast<ulonglong2*>(out)[2 * i] = make_ulonglong2(v.x, v.y);
-        reinterpret_cast<ulonglong2*>(out)[2 * i + 1] = make_ulonglong2(v.z, v.w);
-    }
-    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) out[4 * n4 + threadIdx.x] = in[4 * n4 + threadIdx.x];
-}
-void widen_to_host(stark_ctx* ctx, cudaStream_t s, const uint32_t* in, uint64_t* mapped_out, size_t n, unsigned max_ctas) {
-    if (!n) return;
-    size_t want = (n / 4 + 255) / 256;
-    if (want < 1) want = 1;
-    const unsigned ctas = (unsigned)(want < max_ctas ? want : max_ctas);
-    widen_to_host_kernel<<<ctas, 256, 0, s>>>(in, mapped_out, n);
-    ctx->launches++;
-    STARK_CUDA(cudaGetLastError());
-}
 void fill_zero(stark_ctx* ctx, uint32_t* p, size_t n) {
     if (n) STARK_CUDA(cudaMemsetAsync(p, 0, n * sizeof(uint32_t), ctx->stream));
 }

@@ -41,7 +41,6 @@ struct stark_fri {
     struct LayerSink {
         cudaStream_t stream = nullptr;
         uint64_t* host = nullptr;
-        uint64_t* host_dev = nullptr;    // device alias of `host` when it is pinned + mapped memory (then the SMs write it directly)
         size_t cap = 0, off = 0;
         std::vector<size_t> offs;        // element offset of layer k in `host`
         starkb200::DevBuf stage;         // u64 staging for one layer (the largest); reused in copy-stream order

@@ -128,8 +128,6 @@ void build_scale_table(stark_ctx* ctx, uint64_t base, uint64_t c0, unsigned log_
 void narrow_u64(stark_ctx* ctx, const uint64_t* in, uint32_t* out, size_t n);      // v % p  (FieldElement::new)
 void widen_u32(stark_ctx* ctx, const uint32_t* in, uint64_t* out, size_t n);
 void widen_u32_on(stark_ctx* ctx, cudaStream_t s, const uint32_t* in, uint64_t* out, size_t n);
-// in (16-byte aligned) -> u64 values in device-mapped pinned HOST memory (16-byte aligned), at most max_ctas CTAs
-void widen_to_host(stark_ctx* ctx, cudaStream_t s, const uint32_t* in, uint64_t* mapped_out, size_t n, unsigned max_ctas);
 void fill_zero(stark_ctx* ctx, uint32_t* p, size_t n);
 // c'[j] = c[2j] + beta*c[2j+1]; result->degree_plus1 = 1 + max{j : c'[j] != 0} (0 for the zero poly)
 void poly_degree(stark_ctx* ctx, const uint32_t* c, size_t len, HostResult* result);

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Where the by-value FRI layers cost time (stark_fri_commit_to_host): the 2^24 headline step with the layers streamed to
 pinned host memory, against the same step without them, and with the copy / the widening kernel switched off
-(STARK_SINK_MODE / _CTAS / _DEBUG, read once per process: this script re-runs itself).  One B200."""
+(STARK_SINK_DEBUG, read once per process: this script re-runs itself).  One B200."""
 import importlib
 import os
 import subprocess
@@ -54,11 +54,6 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         measure()
     else:
-        configs = [({"STARK_SINK_MODE": "0"}, "copy engine: widening kernel into a staging buffer + cudaMemcpyAsync"),
-                   ({"STARK_SINK_MODE": "0", "STARK_SINK_DEBUG": "1"}, "copy engine path, widening kernel only, no copy"),
-                   ({"STARK_SINK_MODE": "0", "STARK_SINK_DEBUG": "2"}, "copy engine path, no kernel, no copy: API bookkeeping only")]
-        for ctas in (8, 16, 32, 64, 128, 296):
-            configs.append(({"STARK_SINK_MODE": "1", "STARK_SINK_CTAS": str(ctas)}, f"SM writes into mapped pinned memory, {ctas} CTAs (the product: 32)"))
-        for env, what in configs:
-            print(" ".join(f"{k}={v}" for k, v in env.items()) + ": " + what, flush=True)
-            subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=dict(os.environ, **env), check=True)
+        for dbg, what in ((0, "widen + copy (the product)"), (1, "widening kernel only, no copy"), (2, "no kernel, no copy: API bookkeeping only")):
+            print(f"STARK_SINK_DEBUG={dbg}: {what}", flush=True)
+            subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=dict(os.environ, STARK_SINK_DEBUG=str(dbg)), check=True)
