@@ -54,6 +54,11 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         measure()
     else:
-        for dbg, what in ((0, "widen + copy (the product)"), (1, "widening kernel only, no copy"), (2, "no kernel, no copy: API bookkeeping only")):
-            print(f"STARK_SINK_DEBUG={dbg}: {what}", flush=True)
-            subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=dict(os.environ, STARK_SINK_DEBUG=str(dbg)), check=True)
+        configs = [({}, "the product: widening kernel into a staging buffer + cudaMemcpyAsync on the copy stream"),
+                   ({"STARK_SINK_DEBUG": "1"}, "widening kernel only, no copy"),
+                   ({"STARK_SINK_DEBUG": "2"}, "no kernel, no copy: API bookkeeping only")]
+        # (a variant whose kernel wrote the u64 values straight into mapped pinned memory, 8 .. 296 CTAs, measured 13.5 .. 26.5 ms
+        # per step against 9.3 ms: profiles/r02_by_value_modes.txt; removed)
+        for env, what in configs:
+            print((" ".join(f"{k}={v}" for k, v in env.items()) or "(default)") + ": " + what, flush=True)
+            subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=dict(os.environ, **env), check=True)
