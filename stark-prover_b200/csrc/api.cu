@@ -733,6 +733,34 @@ static void sink_flush(stark_fri* f) {
         sink_push(f, t->leaves->as<uint32_t>(), t->shape.n, false);
     }
 }
+// The layer the fold about to be launched will produce, computed a second time on the copy stream by the plain fold kernel
+// (12 bytes of HBM traffic per point) and sent from there.  The fused fold-and-hash launch only has the layer complete when
+// most of its tree is hashed, so a copy issued after it runs under the FOLLOWING, smaller layers -- and while the copy engine
+// is bursting towards the host, every small write the latency-bound part of the commit sends the same way (a root into
+// mapped memory, the completion of a stream synchronisation) queues behind it: +0.6 ms on a 2^24-domain commit
+// (tools/exp_by_value.py).  Started at the beginning of its own tree, a layer's copy (8 B per point over PCIe) ends before that
+// tree (one leaf hash + one node per point) does.
+static void sink_push_fold(stark_fri* f, const LeafSource& src, bool after_main) {
+    stark_fri::LayerSink* s = f->sink.get();
+    if (!s) return;
+    stark_ctx* ctx = f->ctx;
+    sink_flush(f);
+    STARK_REQUIRE(src.half <= s->cap - s->off, "fri: the host buffer for the layers is full (2^(log_n+1) elements hold every layer)");
+    if (!s->fold_tmp.p) s->fold_tmp = DevBuf(((size_t)4 << f->log_n) / 2, s->stream);
+    LeafSource s2 = src;
+    s2.job = CoeffJob{};
+    s2.fold_out = s->fold_tmp.as<uint32_t>();
+    if (after_main) {                        // the twiddle table of this size has just been built on the main stream
+        STARK_CUDA(cudaEventRecord(ctx->copy_event, ctx->stream));
+        STARK_CUDA(cudaStreamWaitEvent(s->stream, ctx->copy_event, 0));
+    }
+    fri_fold_on(ctx, s->stream, s2);
+    static const int dbg = [] { const char* e = getenv("STARK_SINK_DEBUG"); return e ? atoi(e) : 0; }();
+    if (dbg < 2) widen_u32_on(ctx, s->stream, s2.fold_out, s->stage.as<uint64_t>(), src.half);
+    if (dbg < 1) STARK_CUDA(cudaMemcpyAsync(s->host + s->off, s->stage.p, src.half * 8, cudaMemcpyDeviceToHost, s->stream));
+    s->offs.push_back(s->off);
+    s->off += src.half;
+}
 
 static void fri_begin_impl(stark_ctx* ctx, DevBufPtr coeffs_padded, size_t len, unsigned log_m, unsigned log_n,
                            uint64_t offset, stark_fri** out, uint8_t root[32], uint64_t* layers_out = nullptr, size_t layers_cap = 0) {
@@ -842,6 +870,7 @@ extern "C" int stark_fri_fold(stark_fri* f, uint64_t beta, uint8_t root[32]) {
     if (f->half_over_offset == 0) f->half_over_offset = h_mul(inv2, h_inv(f->cur_offset, p), p);
     src.inv2_m = ctx->to_mont(inv2);
     src.sb_m = ctx->to_mont(h_mul(beta % p, f->half_over_offset, p));
+    const bool had_tw = ctx->tw.count(f->cur_log) != 0;
     src.winv = ctx->twiddles(f->cur_log).inv();
     // coefficient space: exact degree of even + beta*odd (fri_commit.rs:32-50) -- a few CTAs of the tree's first launch
     if (f->coeff_len > 0) {
@@ -853,7 +882,12 @@ extern "C" int stark_fri_fold(stark_fri* f, uint64_t beta, uint8_t root[32]) {
         f->coeffs = nc;
     }
     auto t = tree_launch(ctx, ev, half, src);
-    sink_flush(f);                           // the previous layer on its way to the host, enqueued under this layer's launches
+    {   // by-value layers: enqueued while the main stream is busy with the launches above (no API call between a root and the
+        // next launch).  This layer from the start of its own tree (sink_push_fold); STARK_SINK_EARLY=0: the previous layer
+        static const bool early = [] { const char* e = getenv("STARK_SINK_EARLY"); return !e || atoi(e) != 0; }();
+        if (early) sink_push_fold(f, src, !had_tw);
+        else sink_flush(f);
+    }
     STARK_CUDA(cudaStreamSynchronize(ctx->stream));
     tree_take_root(t.get());
     if (f->coeff_len > 0) f->coeff_len = (size_t)ctx->h_result->degree_plus1;

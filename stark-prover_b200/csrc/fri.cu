@@ -283,5 +283,11 @@ void fri_fold(stark_ctx* ctx, const LeafSource& src) {
     ctx->launches++;
     STARK_CUDA(cudaGetLastError());
 }
+void fri_fold_on(stark_ctx* ctx, cudaStream_t s, const LeafSource& src) {
+    if (!src.half) return;
+    fri_fold_kernel<<<(unsigned)((src.half + 255) / 256), 256, 0, s>>>(src, ctx->fp);
+    ctx->launches++;
+    STARK_CUDA(cudaGetLastError());
+}
 
 }  // namespace starkb200

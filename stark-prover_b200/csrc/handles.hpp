@@ -44,6 +44,7 @@ struct stark_fri {
         size_t cap = 0, off = 0;
         std::vector<size_t> offs;        // element offset of layer k in `host`
         starkb200::DevBuf stage;         // u64 staging for one layer (the largest); reused in copy-stream order
+        starkb200::DevBuf fold_tmp;      // a folded layer computed on the copy stream ahead of the fused fold-and-hash launch
         ~LayerSink() { if (stream) cudaStreamSynchronize(stream); }
     };
     std::unique_ptr<LayerSink> sink;

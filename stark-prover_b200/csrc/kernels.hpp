@@ -172,6 +172,7 @@ void fourstep_phase_c_launch(stark_ctx* ctx, uint32_t* rows, unsigned log_n, uns
                              bool staged, void* const* peer_flags, uint32_t epoch);
 // plain (unfused) evaluation-space fold of one layer
 void fri_fold(stark_ctx* ctx, const LeafSource& src);
+void fri_fold_on(stark_ctx* ctx, cudaStream_t s, const LeafSource& src);      // the same on another stream
 
 // STARK-101 FibonacciSq composition on the LDE coset (build-defined)
 struct FibSqParams {

@@ -54,7 +54,8 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         measure()
     else:
-        configs = [({}, "the product: widening kernel into a staging buffer + cudaMemcpyAsync on the copy stream"),
+        configs = [({}, "the product: every folded layer recomputed on the copy stream at the START of its tree, widened, cudaMemcpyAsync"),
+                   ({"STARK_SINK_EARLY": "0"}, "a layer sent once the fused fold-and-hash launch has produced it (under the following layers)"),
                    ({"STARK_SINK_DEBUG": "1"}, "widening kernel only, no copy"),
                    ({"STARK_SINK_DEBUG": "2"}, "no kernel, no copy: API bookkeeping only")]
         # (a variant whose kernel wrote the u64 values straight into mapped pinned memory, 8 .. 296 CTAs, measured 13.5 .. 26.5 ms
