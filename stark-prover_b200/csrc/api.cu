@@ -101,6 +101,9 @@ extern "C" int stark_ctx_create(uint64_t modulus, uint64_t generator, int device
     STARK_CUDA(cudaHostAlloc((void**)&c->h_result, sizeof(HostResult), cudaHostAllocMapped));
     memset(c->h_result, 0, sizeof(HostResult));
     STARK_CUDA(cudaHostGetDevicePointer((void**)&c->d_result, c->h_result, 0));
+    STARK_CUDA(cudaHostAlloc((void**)&c->h_top, sizeof(HostTop), cudaHostAllocMapped));
+    memset(c->h_top, 0, sizeof(HostTop));
+    STARK_CUDA(cudaHostGetDevicePointer((void**)&c->d_top, c->h_top, 0));
     // in-tile twiddles: w_{2^small_log}^k, k < 2^(small_log-1)
     size_t ns = c->small_log ? ((size_t)1 << (c->small_log - 1)) : 1;
     std::vector<uint32_t> f(ns), b(ns);
@@ -137,6 +140,7 @@ void stark_ctx_teardown(stark_ctx* ctx) {
     for (auto e : ctx->ev_free) cudaEventDestroy(e);
     ctx->pin_desc.release(); ctx->pin_out.release(); ctx->pin_stage.release();
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
+    if (ctx->h_top) cudaFreeHost(ctx->h_top);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -533,16 +537,58 @@ static void words_to_bytes(const uint32_t w[8], uint8_t out[32]) {
     for (int i = 0; i < 8; i++) { out[4 * i] = (uint8_t)(w[i] >> 24); out[4 * i + 1] = (uint8_t)(w[i] >> 16); out[4 * i + 2] = (uint8_t)(w[i] >> 8); out[4 * i + 3] = (uint8_t)w[i]; }
 }
 // Builds the tree over `src` on the stream (no sync); the root lands in ctx->h_result.
-static std::unique_ptr<stark_tree> tree_launch(stark_ctx* ctx, DevBufPtr leaves, size_t n, const LeafSource& src, HostResult* result = nullptr) {
+static std::unique_ptr<stark_tree> tree_launch(stark_ctx* ctx, DevBufPtr leaves, size_t n, const LeafSource& src, HostResult* result = nullptr,
+                                               uint32_t top_seq = 0) {
     std::unique_ptr<stark_tree> t(new stark_tree());
     t->ctx = ctx; t->leaves = std::move(leaves);
     t->shape = TreeShape::make(n);
     t->nodes = DevBuf(t->shape.total * 32, ctx->stream);
-    merkle_build(ctx, src, t->shape, t->nodes.as<uint32_t>(), result ? result : ctx->d_result);
+    merkle_build(ctx, src, t->shape, t->nodes.as<uint32_t>(), result ? result : ctx->d_result, top_seq);
     return t;
 }
 static void tree_take_root(stark_tree* t) {   // after a stream sync
     memcpy(t->root_words, t->ctx->h_result->root, 32);
+}
+// Early hand-over of a tree's top (common.hpp: HostTop): spins on the sequence number the tail kernel publishes with its
+// first level of <= 32 nodes (and on the coefficient job's, when the launch carried one), then finishes the tree on the host:
+// pairwise SHA-256, a lone node promoted unchanged (the rs_merkle rule the kernels implement).  The kernel is still running
+// when this returns -- whatever is launched next queues behind it.  Should the stream drain without the number showing up
+// (it cannot, every exit of the kernel publishes), the root the kernel wrote is taken as before.
+static void wait_tree_top(stark_ctx* ctx, uint32_t seq, bool has_job, uint32_t root_words[8]) {
+    volatile HostTop* top = ctx->h_top;
+    for (unsigned spins = 1;; spins++) {
+        if (top->top_seq == seq && (!has_job || top->deg_seq == seq)) break;
+        if ((spins & 4095) == 0 && cudaStreamQuery(ctx->stream) != cudaErrorNotReady) {
+            STARK_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (top->top_seq == seq) break;
+            memcpy(root_words, ctx->h_result->root, 32);
+            return;
+        }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    size_t len = top->top_len;
+    STARK_REQUIRE(len >= 1 && len <= (size_t)HOST_TOP_MAX, "merkle: malformed early hand-over of the tree top");
+    uint8_t level[HOST_TOP_MAX][32], cat[64];
+    for (size_t i = 0; i < len; i++) {
+        uint32_t w[8];
+        for (int k = 0; k < 8; k++) w[k] = top->node[i][k];
+        words_to_bytes(w, level[i]);
+    }
+    while (len > 1) {
+        const size_t out = (len + 1) / 2;
+        for (size_t j = 0; j < out; j++) {
+            if (2 * j + 1 < len) {
+                memcpy(cat, level[2 * j], 32); memcpy(cat + 32, level[2 * j + 1], 32);
+                HostSha256::digest(cat, 64, level[j]);
+            } else if (j != 2 * j) memcpy(level[j], level[2 * j], 32);
+        }
+        len = out;
+    }
+    for (int i = 0; i < 8; i++)
+        root_words[i] = ((uint32_t)level[0][4 * i] << 24) | ((uint32_t)level[0][4 * i + 1] << 16) | ((uint32_t)level[0][4 * i + 2] << 8) | level[0][4 * i + 3];
 }
 static std::unique_ptr<stark_tree> tree_commit(stark_ctx* ctx, DevBufPtr leaves, size_t n) {
     STARK_REQUIRE(n >= 1, "MerkleTree::new on an empty vector: root() would panic on unwrap (merkle/mod.rs:25)");
@@ -881,15 +927,24 @@ extern "C" int stark_fri_fold(stark_fri* f, uint64_t beta, uint8_t root[32]) {
         old_coeffs = f->coeffs;              // read by the launch below: its stream-ordered release must come after it
         f->coeffs = nc;
     }
-    auto t = tree_launch(ctx, ev, half, src);
+    // the host takes the tree's top over from the tail kernel instead of waiting for it to end (common.hpp: HostTop)
+    static const bool early_top = [] { const char* e = getenv("STARK_EARLY_TOP"); return !e || atoi(e) != 0; }();
+    uint32_t top_seq = early_top ? ++ctx->top_seq : 0;
+    if (early_top && top_seq == 0) top_seq = ++ctx->top_seq;          // 0 means "off": skip it when the counter wraps
+    const bool has_job = src.job.ctas != 0;
+    if (top_seq && has_job) { src.job.top = ctx->d_top; src.job.seq = top_seq; }
+    auto t = tree_launch(ctx, ev, half, src, nullptr, top_seq);
     {   // by-value layers: enqueued while the main stream is busy with the launches above (no API call between a root and the
         // next launch).  This layer from the start of its own tree (sink_push_fold); STARK_SINK_EARLY=0: the previous layer
         static const bool early = [] { const char* e = getenv("STARK_SINK_EARLY"); return !e || atoi(e) != 0; }();
         if (early) sink_push_fold(f, src, !had_tw);
         else sink_flush(f);
     }
-    STARK_CUDA(cudaStreamSynchronize(ctx->stream));
-    tree_take_root(t.get());
+    if (top_seq) wait_tree_top(ctx, top_seq, has_job, t->root_words);
+    else {
+        STARK_CUDA(cudaStreamSynchronize(ctx->stream));
+        tree_take_root(t.get());
+    }
     if (f->coeff_len > 0) f->coeff_len = (size_t)ctx->h_result->degree_plus1;
     if (root) words_to_bytes(t->root_words, root);
     f->trees.push_back(std::move(t));

@@ -30,6 +30,10 @@ __device__ __forceinline__ void coeff_job_run(const CoeffJob& job, unsigned cta,
             __threadfence();
             job.result->degree_plus1 = atomicExch(&job.scratch->maxv, 0);
             job.scratch->ticket = 0;
+            if (job.top) {                                     // early hand-over: the degree is out before its flag
+                __threadfence_system();
+                *reinterpret_cast<volatile uint32_t*>(&job.top->deg_seq) = job.seq;
+            }
         }
     }
 }

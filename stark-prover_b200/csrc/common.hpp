@@ -174,6 +174,21 @@ struct HostResult {
     uint32_t flag;
 };
 
+// Early hand-over of the top of a FRI layer's tree (merkle.cu: tail kernel, api.cu: wait_tree_top).  Between two layers of a
+// commit the GPU idles while the host learns the root, feeds the transcript, draws beta and launches the next fold: ~7.5 us,
+// 22 times per 2^24 proof.  The last CTA of the tail kernel therefore publishes the first level of <= 32 nodes it produces
+// here (mapped pinned memory) and carries on with the remaining ~5 levels for the stored tree, one dependent parent hash
+// (2.7 us) each; the host finishes the same levels itself with SHA-NI (31 hashes, ~3 us), draws beta and has the next launch
+// queued before the kernel is done.
+struct HostTop {
+    uint32_t top_seq;          // written last (system-scope fence before it): which launch the nodes below belong to
+    uint32_t top_len;          // 1 .. 32 nodes of one level, left to right
+    uint32_t deg_seq;          // the coefficient fold job of that launch has published degree_plus1 (HostResult)
+    uint32_t pad;
+    uint32_t node[32][8];      // digests as the eight big-endian state words
+};
+constexpr int HOST_TOP_MAX = 32;
+
 // ---- host-side modular helpers (u128; setup only, never on the data path) ----
 inline uint64_t h_mul(uint64_t a, uint64_t b, uint64_t m) { return (uint64_t)((unsigned __int128)a * b % m); }
 inline uint64_t h_pow(uint64_t a, uint64_t e, uint64_t m) {
@@ -222,6 +237,9 @@ struct stark_ctx {
     std::map<unsigned, std::unique_ptr<starkb200::TwiddleSet>> tw;
     starkb200::HostResult* h_result = nullptr;  // pinned + mapped
     starkb200::HostResult* d_result = nullptr;  // device alias of h_result
+    starkb200::HostTop* h_top = nullptr;        // pinned + mapped: early hand-over of a tree's top (see HostTop)
+    starkb200::HostTop* d_top = nullptr;
+    uint32_t top_seq = 0;                       // launches that published there so far
     starkb200::PinnedBuf pin_desc, pin_out;     // opening descriptors in, opening records out
     starkb200::PinnedBuf pin_stage;             // host-produced columns on their way to HBM (the FibonacciSq trace)
     starkb200::DevBuf deg_scratch;              // DegScratch of the coefficient fold job (coeff_job.cuh)

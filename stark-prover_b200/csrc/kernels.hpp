@@ -27,6 +27,8 @@ struct CoeffJob {
     unsigned ctas = 0;                 // 0 = no job
     HostResult* result = nullptr;      // degree + 1 of the folded polynomial lands in result->degree_plus1
     DegScratch* scratch = nullptr;
+    HostTop* top = nullptr;            // early hand-over (common.hpp): after degree_plus1, top->deg_seq = seq
+    uint32_t seq = 0;
 };
 constexpr unsigned COEFF_JOB_MAX_CTAS = 96;      // measured: 8 / 32 / 96 / 296 -> commit phase 7.82 / 7.17 / 7.07 / 7.13 ms
 
@@ -52,8 +54,10 @@ void coeff_fold(stark_ctx* ctx, const uint32_t* c, size_t len, uint32_t beta_m, 
 
 // Builds levels 1..depth into `nodes` (TreeShape layout); when `result` is non-null the root's 8 state
 // words are also written there (mapped host memory).  Leaf digests are not stored.
+// top_seq != 0: the launch that finishes the tree also publishes its first level of <= 32 nodes to ctx->d_top under that
+// sequence number (HostTop, common.hpp), so that the host need not wait for the kernel to end.
 void merkle_build(stark_ctx* ctx, const LeafSource& src, const TreeShape& shape, uint32_t* nodes,
-                  HostResult* result);
+                  HostResult* result, uint32_t top_seq = 0);
 
 // One authentication path / element read per descriptor; see merkle.cu.
 struct OpenDesc {

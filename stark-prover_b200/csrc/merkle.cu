@@ -215,7 +215,25 @@ struct TailArgs {
     unsigned* ticket;            // zero between launches (the last CTA resets it)
     HostResult* result;
     FieldParams fp;
+    HostTop* top;                // early hand-over of the top levels (common.hpp: HostTop); nullptr = off
+    uint32_t seq;
 };
+
+// The whole CTA calls this once, with the level it has just produced complete in its threads' registers (thread t holds
+// node t, t < len <= HOST_TOP_MAX): nodes, system-scope fence by every writer, barrier, length, fence, sequence number.
+__device__ __forceinline__ void publish_top(HostTop* top, uint32_t seq, int len, const Digest& o, int t) {
+    if (t < len) {
+#pragma unroll
+        for (int w = 0; w < 8; w++) top->node[t][w] = o.w[w];
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (t == 0) {
+        top->top_len = (uint32_t)len;
+        __threadfence_system();
+        *reinterpret_cast<volatile uint32_t*>(&top->top_seq) = seq;
+    }
+}
 
 template <int SRC>
 __global__ void __launch_bounds__(TAIL_THREADS) merkle_tail_kernel(TailArgs a) {
@@ -237,9 +255,16 @@ __global__ void __launch_bounds__(TAIL_THREADS) merkle_tail_kernel(TailArgs a) {
             else sha256_leaf32(SRC == SRC_FOLD ? fold_at(a.src, 0, a.fp) : a.src.vals[0], d);
             store_digest(out, d);
             if (a.result) for (int i = 0; i < 8; i++) a.result->root[i] = d.w[i];
+            if (a.top) {
+                for (int i = 0; i < 8; i++) a.top->node[0][i] = d.w[i];
+                a.top->top_len = 1;
+                __threadfence_system();
+                *reinterpret_cast<volatile uint32_t*>(&a.top->top_seq) = a.seq;
+            }
         }
         return;
     }
+    bool published = a.top == nullptr;
     int base = (int)bid * 2 * TAIL_THREADS;      // the CTA's window of that level: `width` nodes from `base`
     int width = 2 * TAIL_THREADS;
     int buf = 0;                                 // sm[buf] holds the window (except for the first level)
@@ -274,6 +299,10 @@ __global__ void __launch_bounds__(TAIL_THREADS) merkle_tail_kernel(TailArgs a) {
             }
             first = false;
             out += 8 * (size_t)out_len; len = out_len; base >>= 1; width >>= 1;
+            if (!published && len <= HOST_TOP_MAX && (phase > 0 || nblk == 1)) {      // this CTA holds the whole level
+                publish_top(a.top, a.seq, len, o, t);
+                published = true;
+            }
             if (len == 1) {                                            // that was the root (CTA 0, thread 0 holds it)
                 if (t == 0 && a.result) for (int i = 0; i < 8; i++) a.result->root[i] = o.w[i];
                 return;
@@ -312,20 +341,24 @@ __global__ void __launch_bounds__(TAIL_THREADS) merkle_tail_kernel(TailArgs a) {
             o = d;
         }
         __syncthreads();
+        if (!published && len <= HOST_TOP_MAX) {                       // few chunk roots: they are the level to hand over
+            publish_top(a.top, a.seq, len, o, t);
+            published = true;
+        }
         base = 0; width = TAIL_THREADS;
     }
 }
 
 template <int SRC>
 static void launch_tail(stark_ctx* ctx, const LeafSource& src, const uint32_t* in_digests, size_t n_items, uint32_t* out,
-                        HostResult* result) {
+                        HostResult* result, uint32_t top_seq) {
     if (!ctx->tail_counter.p) {                      // one ticket per context (= per stream): launches are ordered
         ctx->tail_counter = DevBuf(sizeof(unsigned), ctx->stream);
         STARK_CUDA(cudaMemsetAsync(ctx->tail_counter.p, 0, sizeof(unsigned), ctx->stream));
     }
     int ctas = (int)((n_items + 2 * TAIL_THREADS - 1) / (2 * TAIL_THREADS));
     if (ctas < 1) ctas = 1;
-    TailArgs a{src, in_digests, (int)n_items, out, ctx->tail_counter.as<unsigned>(), result, ctx->fp};
+    TailArgs a{src, in_digests, (int)n_items, out, ctx->tail_counter.as<unsigned>(), result, ctx->fp, top_seq ? ctx->d_top : nullptr, top_seq};
     if (SRC == SRC_FOLD) ctas += (int)src.job.ctas;
     merkle_tail_kernel<SRC><<<ctas, TAIL_THREADS, 0, ctx->stream>>>(a);
     ctx->launches++;
@@ -333,7 +366,7 @@ static void launch_tail(stark_ctx* ctx, const LeafSource& src, const uint32_t* i
 
 unsigned merkle_first_launch_threads(size_t n) { return n <= (size_t)TAIL_MAX ? TAIL_THREADS : MERKLE_THREADS; }
 
-void merkle_build(stark_ctx* ctx, const LeafSource& src, const TreeShape& shape, uint32_t* nodes, HostResult* result) {
+void merkle_build(stark_ctx* ctx, const LeafSource& src, const TreeShape& shape, uint32_t* nodes, HostResult* result, uint32_t top_seq) {
     const size_t n = shape.n;
     STARK_REQUIRE(n >= 1, "merkle: empty tree (MerkleTree::root() would panic on unwrap, merkle/mod.rs:25)");
     const unsigned depth = shape.depth;
@@ -343,8 +376,8 @@ void merkle_build(stark_ctx* ctx, const LeafSource& src, const TreeShape& shape,
     auto comp_levels = [&](unsigned from, unsigned to) { double c = 0; for (unsigned l = from; l <= to; l++) c += 2.0 * (double)shape.len[l]; return c; };
     if (n <= (size_t)TAIL_MAX) {                     // a small layer: the whole tree in one launch
         KernelTimer kt(ctx, stark_ctx::CAT_MERKLE_LEAF, 1384.0 * ((double)n + comp_levels(1, depth)));
-        if (fold) launch_tail<SRC_FOLD>(ctx, src, nullptr, n, nodes, result);
-        else launch_tail<SRC_VALUES>(ctx, src, nullptr, n, nodes, result);
+        if (fold) launch_tail<SRC_FOLD>(ctx, src, nullptr, n, nodes, result, top_seq);
+        else launch_tail<SRC_VALUES>(ctx, src, nullptr, n, nodes, result, top_seq);
         STARK_CUDA(cudaGetLastError());
         return;
     }
@@ -377,7 +410,7 @@ void merkle_build(stark_ctx* ctx, const LeafSource& src, const TreeShape& shape,
     }
     {
         KernelTimer kt(ctx, stark_ctx::CAT_MERKLE_NODE, 1384.0 * comp_levels(cur + 1, depth));
-        launch_tail<SRC_DIGESTS>(ctx, LeafSource{}, level_ptr(cur), shape.len[cur], level_ptr(cur + 1), result);
+        launch_tail<SRC_DIGESTS>(ctx, LeafSource{}, level_ptr(cur), shape.len[cur], level_ptr(cur + 1), result, top_seq);
     }
     STARK_CUDA(cudaGetLastError());
 }
